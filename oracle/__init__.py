@@ -1,0 +1,299 @@
+"""TEST INFRASTRUCTURE -- ctypes loader for the CPU oracle (oracle/dsdtm_oracle.cpp) and, when built,
+the reference's own FAST library (oracle/_ref/libfast_ref.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this
+package. Nothing under dsdtm_b200/ does. See dsdtm_oracle.h for the pinning status of each function.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libfast_ref.so")
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference is mounted). Building is not using."""
+    src = os.path.join(_HERE, "dsdtm_oracle.cpp")
+    stale = (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < max(
+        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "dsdtm_oracle.h")))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/Thirdparty/fast/src") and (force or not os.path.exists(_REF)):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+class Cam(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("f", C.c_float)]
+
+
+CORNER_DT = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4")])
+REF_FEAT_DT = np.dtype([("px", "<f4", 2), ("level", "<i4"), ("initial", "<i4"),
+                        ("normal", "<f8", 3), ("point_w", "<f8", 3)])
+ITER_LOG_DT = np.dtype([("level", "<i4"), ("iter", "<i4"), ("n_pts", "<i4"), ("flags", "<i4"),
+                        ("chi2", "<f8"), ("x", "<f8", 6)])
+assert REF_FEAT_DT.itemsize == 64 and ITER_LOG_DT.itemsize == 72 and CORNER_DT.itemsize == 16
+
+_lib = None
+_ref = None
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_shitomasi.restype = C.c_float
+        _lib.orc_cvround.argtypes = [C.c_double]
+    return _lib
+
+
+def have_ref():
+    return os.path.exists(_REF)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(_REF)
+    return _ref
+
+
+def make_cam(width, height, fx, fy, cx, cy, f):
+    return Cam(width, height, fx, fy, cx, cy, f)
+
+
+def u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+# ---------------------------------------------------------------- pyramid
+def pyrdown(img):
+    img = u8(img)
+    h, w = img.shape
+    out = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().orc_pyrdown_u8(_p(img), w, h, w, _p(out))
+    return out
+
+
+def level_dims(w, h, levels):
+    ws, hs = [w], [h]
+    for _ in range(1, levels):
+        ws.append((ws[-1] + 1) // 2)
+        hs.append((hs[-1] + 1) // 2)
+    offs = np.concatenate([[0], np.cumsum([a * b for a, b in zip(ws, hs)])]).astype(np.int32)
+    return np.array(ws, np.int32), np.array(hs, np.int32), offs[:-1].copy(), int(offs[-1])
+
+
+def pyramid(img, levels):
+    """returns (packed u8 buffer, offs, ws, hs)"""
+    img = u8(img)
+    h, w = img.shape
+    ws, hs, offs, total = level_dims(w, h, levels)
+    out = np.empty(total, np.uint8)
+    o = np.empty(levels, np.int32); ww = np.empty(levels, np.int32); hh = np.empty(levels, np.int32)
+    lib().orc_pyramid(_p(img), w, h, levels, _p(out), _p(o), _p(ww), _p(hh))
+    assert (o == offs).all() and (ww == ws).all() and (hh == hs).all()
+    return out, offs, ws, hs
+
+
+def pyr_level(packed, offs, ws, hs, l):
+    return packed[offs[l]:offs[l] + ws[l] * hs[l]].reshape(hs[l], ws[l])
+
+
+# ---------------------------------------------------------------- FAST
+def fast10_detect(img, barrier):
+    img = u8(img)
+    h, w = img.shape
+    xy = np.empty((w * h, 2), np.int16)
+    n = lib().orc_fast10_detect(_p(img), w, h, w, int(barrier), _p(xy), w * h)
+    return xy[:n].copy()
+
+
+def fast10_score(img, xy):
+    img = u8(img)
+    xy = np.ascontiguousarray(xy, np.int16)
+    s = np.empty(len(xy), np.int32)
+    lib().orc_fast10_score(_p(img), img.shape[1], _p(xy), len(xy), _p(s))
+    return s
+
+
+def fast_nonmax(xy, scores):
+    xy = np.ascontiguousarray(xy, np.int16)
+    scores = np.ascontiguousarray(scores, np.int32)
+    keep = np.empty(len(xy), np.int32)
+    m = lib().orc_fast_nonmax_3x3(_p(xy), _p(scores), len(xy), _p(keep))
+    return keep[:m].copy()
+
+
+def ref_fast10_detect(img, barrier, sse2=True):
+    img = u8(img)
+    h, w = img.shape
+    xy = np.empty((w * h, 2), np.int16)
+    n = ref().fastref_detect10(_p(img), w, h, w, int(barrier), int(sse2), _p(xy), w * h)
+    return xy[:n].copy()
+
+
+def ref_fast10_score(img, xy, threshold):
+    img = u8(img)
+    xy = np.ascontiguousarray(xy, np.int16)
+    s = np.empty(len(xy), np.int32)
+    ref().fastref_score10(_p(img), img.shape[1], _p(xy), len(xy), int(threshold), _p(s))
+    return s
+
+
+def ref_fast_nonmax(xy, scores):
+    xy = np.ascontiguousarray(xy, np.int16)
+    scores = np.ascontiguousarray(scores, np.int32)
+    keep = np.empty(len(xy), np.int32)
+    m = ref().fastref_nonmax(_p(xy), _p(scores), len(xy), _p(keep))
+    return keep[:m].copy()
+
+
+def shitomasi(img, u, v):
+    img = u8(img)
+    return float(lib().orc_shitomasi(_p(img), img.shape[1], img.shape[0], img.shape[1], int(u), int(v)))
+
+
+def grid_dims(w, h, cell):
+    return -(-h // cell), -(-w // cell)
+
+
+def detect_cells(packed, offs, ws, hs, cell, occupied=None, thr=5.0):
+    levels = len(ws)
+    rows, cols = grid_dims(int(ws[0]), int(hs[0]), cell)
+    cells = np.zeros(rows * cols, CORNER_DT)
+    occ = u8(occupied) if occupied is not None else None
+    lib().orc_detect_cells(_p(packed), _p(offs), _p(ws), _p(hs), levels, int(ws[0]), int(hs[0]), int(cell),
+                           _p(occ), C.c_double(thr), _p(cells))
+    return cells
+
+
+def detect_select(cells, mask, cell, max_fts, n_existing=0):
+    """cells sorted in place (copy returned), mask painted in place. returns (features, sorted_cells)"""
+    cells = cells.copy()
+    h, w = mask.shape
+    assert mask.dtype == np.uint8 and mask.flags.c_contiguous
+    out = np.zeros(len(cells), CORNER_DT)
+    n = lib().orc_detect_select(_p(cells), len(cells), _p(mask), w, h, int(cell), int(max_fts), int(n_existing), _p(out))
+    return out[:n].copy(), cells
+
+
+def circle_fill(img, cx, cy, r, color=0):
+    assert img.dtype == np.uint8 and img.flags.c_contiguous
+    h, w = img.shape
+    lib().orc_circle_fill(_p(img), w, h, w, int(cx), int(cy), int(r), int(color))
+
+
+def cvround(v):
+    return int(lib().orc_cvround(float(v)))
+
+
+# ---------------------------------------------------------------- sparse alignment
+def sparse_align(cam, ref_pyr, cur_pyr, offs, ws, hs, feats, ref_center, pose_in, max_level, min_level, max_iters,
+                 log_cap=512):
+    feats = np.ascontiguousarray(feats, REF_FEAT_DT)
+    ref_center = np.ascontiguousarray(ref_center, np.float64)
+    pose_in = np.ascontiguousarray(pose_in, np.float64)
+    pose_out = np.empty(7, np.float64)
+    log = np.zeros(log_cap, ITER_LOG_DT)
+    n_log = C.c_int(0)
+    n = lib().orc_sparse_align(C.byref(cam), _p(ref_pyr), _p(cur_pyr), _p(offs), _p(ws), _p(hs), _p(feats), len(feats),
+                               _p(ref_center), _p(pose_in), int(max_level), int(min_level), int(max_iters),
+                               _p(pose_out), _p(log), log_cap, C.byref(n_log))
+    return pose_out, int(n), log[:min(n_log.value, log_cap)].copy()
+
+
+# ---------------------------------------------------------------- feature alignment
+def solve_affine(cam, kf_center, ref_point_w, ref_normal, ref_px, ref_level, pose_c2r):
+    A = np.empty(4, np.float64)
+    lib().orc_solve_affine(C.byref(cam), _p(np.ascontiguousarray(kf_center, np.float64)),
+                           _p(np.ascontiguousarray(ref_point_w, np.float64)),
+                           _p(np.ascontiguousarray(ref_normal, np.float64)),
+                           _p(np.ascontiguousarray(ref_px, np.float32)), int(ref_level),
+                           _p(np.ascontiguousarray(pose_c2r, np.float64)), _p(A))
+    return A.reshape(2, 2)
+
+
+def best_search_level(A, max_level):
+    return int(lib().orc_best_search_level(_p(np.ascontiguousarray(A, np.float64).reshape(-1)), int(max_level)))
+
+
+def warp_affine(A, ref_img, ref_px, ref_level, search_level):
+    ref_img = u8(ref_img)
+    h, w = ref_img.shape
+    out = np.empty(100, np.uint8)
+    lib().orc_warp_affine(_p(np.ascontiguousarray(A, np.float64).reshape(-1)), _p(ref_img), w, h, w,
+                          _p(np.ascontiguousarray(ref_px, np.float32)), int(ref_level), int(search_level), _p(out))
+    return out
+
+
+def patch_no_border(p10):
+    p10 = u8(p10).reshape(-1)
+    out = np.empty(64, np.uint8)
+    lib().orc_patch_no_border(_p(p10), _p(out))
+    return out
+
+
+def align2d(cur_img, patch10, max_iters, px):
+    cur_img = u8(cur_img)
+    h, w = cur_img.shape
+    p10 = u8(patch10).reshape(-1)
+    p8 = patch_no_border(p10)
+    p = np.array(px, np.float64)
+    nit = C.c_int(0)
+    conv = lib().orc_align2d(_p(cur_img), w, h, w, _p(p10), _p(p8), int(max_iters), _p(p), C.byref(nit))
+    return p, bool(conv), nit.value
+
+
+# ---------------------------------------------------------------- SE3
+def se3_exp(x):
+    out = np.empty(7); lib().orc_se3_exp(_p(np.ascontiguousarray(x, np.float64)), _p(out)); return out
+
+
+def se3_mul(a, b):
+    out = np.empty(7)
+    lib().orc_se3_mul(_p(np.ascontiguousarray(a, np.float64)), _p(np.ascontiguousarray(b, np.float64)), _p(out))
+    return out
+
+
+def se3_inv(a):
+    out = np.empty(7); lib().orc_se3_inv(_p(np.ascontiguousarray(a, np.float64)), _p(out)); return out
+
+
+def se3_act(a, p):
+    out = np.empty(3)
+    lib().orc_se3_act(_p(np.ascontiguousarray(a, np.float64)), _p(np.ascontiguousarray(p, np.float64)), _p(out))
+    return out
+
+
+def feature_normal(cam, px):
+    out = np.empty(3)
+    lib().orc_feature_normal(C.byref(cam), _p(np.ascontiguousarray(px, np.float32)), _p(out))
+    return out
+
+
+def pair_batch(cam, levels, ref_pyrs, cur_imgs, feats, n_feats, ref_centers, poses_in, max_level, min_level,
+               max_iters, patches10, patch_px, patch_level, align_iters, n_threads):
+    """CPU restatement of one bench 'step' over n_pairs pairs (pyramid(cur) + Run + Align2D per patch)."""
+    n_pairs = len(n_feats)
+    feats = np.ascontiguousarray(feats, REF_FEAT_DT)
+    fpp = feats.size // n_pairs
+    ppp = patch_level.size // n_pairs
+    poses_out = np.empty((n_pairs, 7)); n_tracked = np.empty(n_pairs, np.int32)
+    px_out = np.empty((n_pairs, ppp, 2)); conv = np.empty((n_pairs, ppp), np.uint8)
+    lib().orc_pair_batch(C.byref(cam), int(levels), _p(u8(ref_pyrs)), _p(u8(cur_imgs)), n_pairs, _p(feats), fpp,
+                         _p(np.ascontiguousarray(n_feats, np.int32)), _p(np.ascontiguousarray(ref_centers, np.float64)),
+                         _p(np.ascontiguousarray(poses_in, np.float64)), int(max_level), int(min_level), int(max_iters),
+                         _p(u8(patches10)), _p(np.ascontiguousarray(patch_px, np.float64)),
+                         _p(np.ascontiguousarray(patch_level, np.int32)), ppp, int(align_iters), int(n_threads),
+                         _p(poses_out), _p(n_tracked), _p(px_out), _p(conv))
+    return poses_out, n_tracked, px_out, conv
