@@ -1,0 +1,71 @@
+"""In-tree build of the sm_100a CUDA library (dsdtm_b200/lib/libdsdtm_gpu.so) with nvcc.
+
+The built .so is git-ignored but travels to the GPU box with the gpurun snapshot. Rebuilds only when a source is newer.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libdsdtm_gpu.so")
+SOURCES = ["capi.cu", "pyramid.cu", "fast.cu", "sparse_align.cu", "align2d.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
+
+
+def nvcc():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found: the CUDA library cannot be built (there is no CPU fallback)")
+    return p
+
+
+def _deps():
+    d = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "ctx.cuh"),
+                                                    os.path.join(ROOT, "include", "dsdtm_gpu.h")]
+    return d
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    objs = []
+    log = []
+    for s in SOURCES:
+        o = os.path.join(LIBDIR, s.replace(".cu", ".o"))
+        src = os.path.join(CSRC, s)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(p) for p in (src, _deps()[-1], _deps()[-2])):
+            cmd = [nvcc()] + NVCC_FLAGS + ["-c", src, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            log.append(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed for %s" % s)
+        objs.append(o)
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    with open(os.path.join(LIBDIR, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(LIB)

@@ -1,0 +1,267 @@
+"""ctypes binding of include/dsdtm_gpu.h (libdsdtm_gpu.so). Harness-side only: tests, bench.py and smoke() call the
+CUDA path through this C-ABI exactly as the C++ adapters in dsdtm_b200/host do. There is NO CPU fallback: if the library
+is missing or no CUDA device is present, everything here raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine")
+
+CORNER_DT = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4")])
+REF_FEAT_DT = np.dtype([("px", "<f4", 2), ("level", "<i4"), ("initial", "<i4"),
+                        ("normal", "<f8", 3), ("point_w", "<f8", 3)])
+ITER_LOG_DT = np.dtype([("level", "<i4"), ("iter", "<i4"), ("n_pts", "<i4"), ("flags", "<i4"),
+                        ("chi2", "<f8"), ("x", "<f8", 6)])
+
+
+class Cam(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("f", C.c_float)]
+
+
+class Params(C.Structure):
+    _fields_ = [("levels", C.c_int), ("cell_size", C.c_int), ("max_feats", C.c_int), ("max_patches", C.c_int),
+                ("max_frames", C.c_int), ("max_batch", C.c_int)]
+
+
+class DsdtmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/dsdtm_gpu.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "dsdtm_abi_version", "dsdtm_create", "dsdtm_create_error", "dsdtm_destroy", "dsdtm_last_error", "dsdtm_sync",
+    "dsdtm_level_info", "dsdtm_frame_stride", "dsdtm_host_alloc", "dsdtm_host_free", "dsdtm_launch_count",
+    "dsdtm_profile", "dsdtm_profile_get", "dsdtm_frame_upload_pyramid", "dsdtm_frames_upload_pyramid",
+    "dsdtm_frames_build_pyramid", "dsdtm_frame_download_level", "dsdtm_fast_cells", "dsdtm_fast_cells_batch",
+    "dsdtm_fast_score_map", "dsdtm_grid_dims", "dsdtm_sparse_align", "dsdtm_sparse_align_batch",
+    "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
+    "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms",
+]
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB):
+        raise DsdtmError("libdsdtm_gpu.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(_build.LIB)
+    L.dsdtm_create.restype = C.c_void_p
+    L.dsdtm_create.argtypes = [C.c_int, C.POINTER(Cam), C.POINTER(Params)]
+    L.dsdtm_create_error.restype = C.c_char_p
+    L.dsdtm_last_error.restype = C.c_char_p
+    L.dsdtm_last_error.argtypes = [C.c_void_p]
+    L.dsdtm_destroy.argtypes = [C.c_void_p]
+    L.dsdtm_frame_stride.restype = C.c_size_t
+    L.dsdtm_frame_stride.argtypes = [C.c_void_p]
+    L.dsdtm_host_alloc.restype = C.c_void_p
+    L.dsdtm_host_alloc.argtypes = [C.c_size_t]
+    L.dsdtm_host_free.argtypes = [C.c_void_p]
+    L.dsdtm_launch_count.restype = C.c_longlong
+    L.dsdtm_launch_count.argtypes = [C.c_void_p]
+    L.dsdtm_last_run_ms.restype = C.c_float
+    L.dsdtm_last_run_ms.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by pinned host memory (cudaMallocHost). Keep the returned array alive while in use."""
+    L = load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = L.dsdtm_host_alloc(max(n, 1))
+    if not ptr:
+        raise DsdtmError("cudaMallocHost failed")
+    buf = (C.c_uint8 * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.ctypes.data] = ptr
+    return arr
+
+
+_PINNED = {}
+
+
+class Context:
+    def __init__(self, cam, levels=5, cell_size=15, max_feats=320, max_patches=320, max_frames=8, max_batch=1, device=0):
+        L = load()
+        self.L = L
+        self.cam = Cam(cam["width"], cam["height"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["f"])
+        self.prm = Params(levels, cell_size, max_feats, max_patches, max_frames, max_batch)
+        self.h = L.dsdtm_create(device, C.byref(self.cam), C.byref(self.prm))
+        if not self.h:
+            raise DsdtmError("dsdtm_create failed: %s" % L.dsdtm_create_error().decode())
+        self.levels = levels
+        self.ws, self.hs, self.offs = [], [], []
+        for l in range(levels):
+            w, h, o = C.c_int(), C.c_int(), C.c_size_t()
+            self._ck(L.dsdtm_level_info(C.c_void_p(self.h), l, C.byref(w), C.byref(h), C.byref(o)))
+            self.ws.append(w.value); self.hs.append(h.value); self.offs.append(o.value)
+        r, c_ = C.c_int(), C.c_int()
+        L.dsdtm_grid_dims(C.c_void_p(self.h), C.byref(r), C.byref(c_))
+        self.grid_rows, self.grid_cols = r.value, c_.value
+        self.n_cells = r.value * c_.value
+        self.width, self.height = cam["width"], cam["height"]
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DsdtmError("dsdtm error %d: %s" % (rc, self.L.dsdtm_last_error(C.c_void_p(self.h)).decode()))
+
+    def close(self):
+        if self.h:
+            self.L.dsdtm_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def hp(self):
+        return C.c_void_p(self.h)
+
+    def sync(self):
+        self._ck(self.L.dsdtm_sync(self.hp))
+
+    def launch_count(self):
+        return int(self.L.dsdtm_launch_count(self.hp))
+
+    def profile(self, on):
+        self._ck(self.L.dsdtm_profile(self.hp, int(on)))
+
+    def profile_get(self, reset=True):
+        ms = (C.c_float * len(STAGES))()
+        n = (C.c_int * len(STAGES))()
+        self._ck(self.L.dsdtm_profile_get(self.hp, ms, n, int(reset)))
+        return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(STAGES)}
+
+    # ---- pyramid
+    def upload(self, slot, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        assert img.shape == (self.height, self.width)
+        self._ck(self.L.dsdtm_frame_upload_pyramid(self.hp, int(slot), _p(img), img.shape[1]))
+
+    def upload_batch(self, first_slot, imgs):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        assert imgs.shape[1:] == (self.height, self.width)
+        self._ck(self.L.dsdtm_frames_upload_pyramid(self.hp, int(first_slot), imgs.shape[0], _p(imgs)))
+
+    def build_pyramid(self, first_slot, n):
+        self._ck(self.L.dsdtm_frames_build_pyramid(self.hp, int(first_slot), int(n)))
+
+    def download_level(self, slot, level):
+        out = np.empty((self.hs[level], self.ws[level]), np.uint8)
+        self._ck(self.L.dsdtm_frame_download_level(self.hp, int(slot), int(level), _p(out)))
+        return out
+
+    # ---- FAST
+    def fast_cells(self, slot, barrier=20, seed_score=5.0, occupied=None, n=1):
+        cells = np.zeros(n * self.n_cells, CORNER_DT)
+        occ = np.ascontiguousarray(occupied, np.uint8) if occupied is not None else None
+        self._ck(self.L.dsdtm_fast_cells_batch(self.hp, int(slot), int(n), int(barrier), C.c_float(seed_score), _p(occ), _p(cells)))
+        return cells if n == 1 else cells.reshape(n, self.n_cells)
+
+    def fast_score_map(self, slot, level, barrier=20):
+        s = np.empty((self.hs[level], self.ws[level]), np.uint8)
+        m = np.empty_like(s)
+        self._ck(self.L.dsdtm_fast_score_map(self.hp, int(slot), int(level), int(barrier), _p(s), _p(m)))
+        return s, m
+
+    # ---- sparse align
+    def sparse_align(self, ref_slot, cur_slot, feats, ref_center, pose_in, max_level, min_level, max_iters, log_cap=256):
+        feats = np.ascontiguousarray(feats, REF_FEAT_DT)
+        pose_out = np.empty(7)
+        n_tracked = C.c_int(0)
+        log = np.zeros(log_cap, ITER_LOG_DT)
+        n_log = C.c_int(0)
+        self._ck(self.L.dsdtm_sparse_align(self.hp, int(ref_slot), int(cur_slot), _p(feats), len(feats),
+                                           _p(np.ascontiguousarray(ref_center, np.float64)),
+                                           _p(np.ascontiguousarray(pose_in, np.float64)), int(max_level), int(min_level),
+                                           int(max_iters), _p(pose_out), C.byref(n_tracked), _p(log), log_cap, C.byref(n_log)))
+        return pose_out, n_tracked.value, log[:min(n_log.value, log_cap)].copy()
+
+    def sparse_align_batch(self, ref_slots, cur_slots, feats, n_feats, ref_centers, poses_in, max_level, min_level, max_iters,
+                           log_cap=0):
+        n = len(ref_slots)
+        feats = np.ascontiguousarray(feats, REF_FEAT_DT).reshape(n, -1)
+        poses_out = np.empty((n, 7)); n_tracked = np.empty(n, np.int32)
+        log = np.zeros((n, max(log_cap, 1)), ITER_LOG_DT) if log_cap else None
+        n_log = np.zeros(n, np.int32)
+        self._ck(self.L.dsdtm_sparse_align_batch(
+            self.hp, n, _p(np.ascontiguousarray(ref_slots, np.int32)), _p(np.ascontiguousarray(cur_slots, np.int32)), _p(feats),
+            feats.shape[1], _p(np.ascontiguousarray(n_feats, np.int32)), _p(np.ascontiguousarray(ref_centers, np.float64)),
+            _p(np.ascontiguousarray(poses_in, np.float64)), int(max_level), int(min_level), int(max_iters), _p(poses_out),
+            _p(n_tracked), _p(log), int(log_cap), _p(n_log)))
+        return poses_out, n_tracked, log, n_log
+
+    # ---- feature alignment
+    def align2d(self, cur_slot, levels, patches10, px, max_iters=10):
+        levels = np.ascontiguousarray(levels, np.int32)
+        patches10 = np.ascontiguousarray(patches10, np.uint8).reshape(len(levels), 100)
+        px = np.array(px, np.float64).reshape(len(levels), 2)
+        conv = np.zeros(len(levels), np.uint8)
+        self._ck(self.L.dsdtm_align2d_batch(self.hp, int(cur_slot), _p(levels), _p(patches10), _p(px), len(levels), int(max_iters), _p(conv)))
+        return px, conv.astype(bool)
+
+    def warp_affine(self, ref_slots, A, ref_px, ref_levels, search_levels):
+        n = len(ref_slots)
+        out = np.empty((n, 100), np.uint8)
+        self._ck(self.L.dsdtm_warp_affine_batch(
+            self.hp, _p(np.ascontiguousarray(ref_slots, np.int32)), _p(np.ascontiguousarray(A, np.float64).reshape(n, 4)),
+            _p(np.ascontiguousarray(ref_px, np.float32).reshape(n, 2)), _p(np.ascontiguousarray(ref_levels, np.int32)),
+            _p(np.ascontiguousarray(search_levels, np.int32)), n, _p(out)))
+        return out
+
+    # ---- batched front end
+    def batch_stage(self, ref_slots, cur_slots, feats, n_feats, ref_centers, poses_in, max_level, min_level, max_iters,
+                    patches10=None, patch_px=None, patch_level=None, align_iters=10):
+        n = len(ref_slots)
+        feats = np.ascontiguousarray(feats, REF_FEAT_DT).reshape(n, -1)
+        ppp = 0 if patch_level is None else np.asarray(patch_level).reshape(n, -1).shape[1]
+        self._n = n; self._ppp = ppp
+        self._ck(self.L.dsdtm_batch_stage(
+            self.hp, n, _p(np.ascontiguousarray(ref_slots, np.int32)), _p(np.ascontiguousarray(cur_slots, np.int32)), _p(feats),
+            feats.shape[1], _p(np.ascontiguousarray(n_feats, np.int32)), _p(np.ascontiguousarray(ref_centers, np.float64)),
+            _p(np.ascontiguousarray(poses_in, np.float64)), int(max_level), int(min_level), int(max_iters),
+            _p(np.ascontiguousarray(patches10, np.uint8)) if ppp else None,
+            _p(np.ascontiguousarray(patch_px, np.float64)) if ppp else None,
+            _p(np.ascontiguousarray(patch_level, np.int32)) if ppp else None, ppp, int(align_iters)))
+
+    def batch_run(self, flags=0):
+        self._ck(self.L.dsdtm_batch_run(self.hp, int(flags)))
+
+    def batch_fetch(self):
+        n, ppp = self._n, self._ppp
+        poses = np.empty((n, 7)); nt = np.empty(n, np.int32)
+        px = np.empty((n, ppp, 2)) if ppp else None
+        conv = np.empty((n, ppp), np.uint8) if ppp else None
+        self._ck(self.L.dsdtm_batch_fetch(self.hp, _p(poses), _p(nt), _p(px), _p(conv)))
+        return poses, nt, px, conv
+
+    def last_run_ms(self):
+        return float(self.L.dsdtm_last_run_ms(self.hp))
+
+    def pair_batch_e2e(self, cur_imgs, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, max_level,
+                       min_level, max_iters, patches10, patch_px, patch_level, ppp, align_iters, out):
+        """All arrays must already be contiguous with the right dtype (pinned for async copies); out = dict of result arrays."""
+        n = len(ref_slots)
+        self._ck(self.L.dsdtm_pair_batch_e2e(
+            self.hp, n, _p(cur_imgs), _p(ref_slots), _p(cur_slots), _p(feats), int(feat_stride), _p(n_feats), _p(ref_centers),
+            _p(poses_in), int(max_level), int(min_level), int(max_iters), _p(patches10), _p(patch_px), _p(patch_level), int(ppp),
+            int(align_iters), _p(out["poses"]), _p(out["n_tracked"]), _p(out.get("px")), _p(out.get("conv"))))

@@ -1,0 +1,665 @@
+// capi.cu -- the extern "C" boundary (include/dsdtm_gpu.h): context, HBM pools, staging, launches, CUDA-graph replay.
+// No compute happens on the host here; if the CUDA device / kernels are unavailable every entry point fails loudly.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "ctx.cuh"
+
+namespace dsdtm {
+
+int build_fast_tiles(const LevelGeom& g, int* out, int* level_first);
+
+static std::string g_create_error;
+
+void stage_begin(dsdtm_ctx* c, int stage)
+{
+    if (!c->profiling) return;
+    StageTimer& t = c->timer;
+    if (t.n >= StageTimer::kMaxEv) stage_collect(c);
+    t.stage[t.n] = stage;
+    cudaEventRecord(t.ev0[t.n], c->stream);
+}
+
+void stage_end(dsdtm_ctx* c, int n_launches)
+{
+    if (!c->profiling) return;
+    StageTimer& t = c->timer;
+    cudaEventRecord(t.ev1[t.n], c->stream);
+    t.launches[t.stage[t.n]] += n_launches;
+    t.n++;
+}
+
+int stage_collect(dsdtm_ctx* c)
+{
+    StageTimer& t = c->timer;
+    if (t.n == 0) return 0;
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < t.n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.ev0[i], t.ev1[i]);
+        t.ms[t.stage[i]] += ms;
+    }
+    t.n = 0;
+    return 0;
+}
+
+template <class T>
+static int dalloc(dsdtm_ctx* c, T** p, size_t n)
+{
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(c, DSDTM_E_NOMEM, "cudaMalloc", e);
+    return 0;
+}
+
+static int ensure_pinned(dsdtm_ctx* c, size_t bytes)
+{
+    if (bytes <= c->pinned_bytes) return 0;
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr; c->pinned_bytes = 0;
+    cudaError_t e = cudaMallocHost((void**)&c->pinned, bytes);
+    if (e != cudaSuccess) return fail(c, DSDTM_E_NOMEM, "cudaMallocHost", e);
+    c->pinned_bytes = bytes;
+    return 0;
+}
+
+static void decode_cells(const dsdtm_ctx* c, const unsigned long long* keys, float seed, dsdtm_corner* out, int n)
+{
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long k = keys[i];
+        if (k == 0) { out[i] = dsdtm_corner{ 0, 0, 0, seed }; continue; }    // ref: src/Feature_detection.cpp:74
+        const unsigned order = ~(unsigned)(k & 0xFFFFFFFFull);
+        const unsigned bits = (unsigned)(k >> 32);
+        float s; std::memcpy(&s, &bits, 4);
+        const int L = order >> 28, y = (order >> 14) & 0x3FFF, x = order & 0x3FFF;
+        out[i] = dsdtm_corner{ x << L, y << L, L, s };                       // ref: :106
+    }
+}
+
+static int check_slot(dsdtm_ctx* c, int slot, int n = 1)
+{
+    if (slot < 0 || n < 0 || slot + n > c->prm.max_frames) return fail(c, DSDTM_E_ARG, "frame slot out of range");
+    return 0;
+}
+
+}  // namespace dsdtm
+
+using namespace dsdtm;
+
+extern "C" {
+
+int dsdtm_abi_version(void) { return DSDTM_ABI_VERSION; }
+const char* dsdtm_create_error(void) { return g_create_error.c_str(); }
+
+dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* prm)
+{
+    g_create_error.clear();
+    if (!cam || !prm) { g_create_error = "null cam/params"; return nullptr; }
+    if (prm->levels < 1 || prm->levels > DSDTM_MAX_LEVELS || cam->width < 8 || cam->height < 8 || cam->width > 16383 ||
+        cam->height > 16383 || prm->cell_size < 1 || prm->max_feats < 1 || prm->max_feats > DSDTM_MAX_FEATS_LIMIT ||
+        prm->max_frames < 1 || prm->max_batch < 1 || prm->max_patches < 0) {
+        g_create_error = "bad cam/params";
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return nullptr; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return nullptr; }
+
+    dsdtm_ctx* c = new dsdtm_ctx();
+    c->device = device; c->cam = *cam; c->prm = *prm;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+
+    // level geometry: dense levels, 16-byte aligned offsets, >= 64 bytes of zero padding at the end of a slot
+    LevelGeom& g = c->geo;
+    g.levels = prm->levels;
+    unsigned off = 0;
+    for (int l = 0; l < g.levels; ++l) {
+        g.w[l] = l ? (g.w[l - 1] + 1) / 2 : cam->width;
+        g.h[l] = l ? (g.h[l - 1] + 1) / 2 : cam->height;
+        g.off[l] = off;
+        off += (unsigned)g.w[l] * g.h[l];
+        off = (off + 15u) & ~15u;
+    }
+    for (int l = g.levels; l < DSDTM_MAX_LEVELS; ++l) { g.w[l] = g.h[l] = 0; g.off[l] = off; }
+    g.frame_stride = (off + 64u + 255u) & ~255u;
+    c->grid_rows = (cam->height + prm->cell_size - 1) / prm->cell_size;     // ref: src/Feature_detection.cpp:18-19 (ceil)
+    c->grid_cols = (cam->width + prm->cell_size - 1) / prm->cell_size;
+    c->n_cells = c->grid_rows * c->grid_cols;
+
+    auto bail = [&](const char* what) -> dsdtm_ctx* {
+        g_create_error = std::string(what) + ": " + c->err;
+        dsdtm_destroy(c);
+        return nullptr;
+    };
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = cudaGetErrorString(e__); return bail(#call); } } while (0)
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream[0], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream[1], cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev_a));
+    CK(cudaEventCreate(&c->ev_b));
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+    for (int i = 0; i < StageTimer::kMaxEv; ++i) { CK(cudaEventCreate(&c->timer.ev0[i])); CK(cudaEventCreate(&c->timer.ev1[i])); }
+
+    const size_t B = prm->max_batch, F = prm->max_feats, P = std::max(prm->max_patches, 1);
+    const size_t pool = (size_t)prm->max_frames * g.frame_stride;
+    if (dalloc(c, &c->frames_d, pool)) return bail("frame pool");
+    CK(cudaMemset(c->frames_d, 0, pool));
+    if (dalloc(c, &c->cells_d, B * c->n_cells) || dalloc(c, &c->occupied_d, B * c->n_cells) ||
+        dalloc(c, &c->scoremap_d, 2 * (size_t)g.w[0] * g.h[0]) || dalloc(c, &c->ref_slots_d, B) || dalloc(c, &c->cur_slots_d, B) ||
+        dalloc(c, &c->feats_d, B * F) || dalloc(c, &c->n_feats_d, B) || dalloc(c, &c->centers_d, B * 3) ||
+        dalloc(c, &c->poses_in_d, B * 7) || dalloc(c, &c->poses_out_d, B * 7) || dalloc(c, &c->n_tracked_d, B) ||
+        dalloc(c, &c->log_d, B * kLogCap) || dalloc(c, &c->n_log_d, B) || dalloc(c, &c->patches_d, B * P * 100) ||
+        dalloc(c, &c->patch_px_d, B * P * 2) || dalloc(c, &c->patch_level_d, B * P) || dalloc(c, &c->patch_slot_d, B * P) ||
+        dalloc(c, &c->patch_conv_d, B * P) || dalloc(c, &c->wa_A_d, B * P * 4) || dalloc(c, &c->wa_px_d, B * P * 2) ||
+        dalloc(c, &c->wa_meta_d, B * P * 3))
+        return bail("device buffers");
+    {
+        const int n = build_fast_tiles(g, nullptr, nullptr);
+        std::vector<int> tiles(n);
+        build_fast_tiles(g, tiles.data(), nullptr);
+        c->n_fast_tiles = n;
+        if (dalloc(c, &c->fast_tiles_d, (size_t)n)) return bail("fast tiles");
+        CK(cudaMemcpy(c->fast_tiles_d, tiles.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    CK(sparse_align_init(c));
+#undef CK
+    return c;
+}
+
+void dsdtm_destroy(dsdtm_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) cudaGraphExecDestroy(c->batch.graph[k]);
+    void* bufs[] = { c->frames_d, c->cells_d, c->occupied_d, c->scoremap_d, c->fast_tiles_d, c->ref_slots_d, c->cur_slots_d,
+                     c->feats_d, c->n_feats_d, c->centers_d, c->poses_in_d, c->poses_out_d, c->n_tracked_d, c->log_d, c->n_log_d,
+                     c->patches_d, c->patch_px_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d };
+    for (void* p : bufs) if (p) cudaFree(p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (int i = 0; i < StageTimer::kMaxEv; ++i) { if (c->timer.ev0[i]) cudaEventDestroy(c->timer.ev0[i]); if (c->timer.ev1[i]) cudaEventDestroy(c->timer.ev1[i]); }
+    for (int i = 0; i < 4; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    for (int i = 0; i < 2; ++i) if (c->copy_stream[i]) cudaStreamDestroy(c->copy_stream[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* dsdtm_last_error(const dsdtm_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int dsdtm_sync(dsdtm_ctx* c)
+{
+    if (!c) return DSDTM_E_ARG;
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int dsdtm_level_info(const dsdtm_ctx* c, int level, int* w, int* h, size_t* offset)
+{
+    if (!c || level < 0 || level >= c->geo.levels) return DSDTM_E_ARG;
+    if (w) *w = c->geo.w[level];
+    if (h) *h = c->geo.h[level];
+    if (offset) *offset = c->geo.off[level];
+    return 0;
+}
+
+size_t dsdtm_frame_stride(const dsdtm_ctx* c) { return c ? c->geo.frame_stride : 0; }
+
+void* dsdtm_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void dsdtm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+long long dsdtm_launch_count(const dsdtm_ctx* c) { return c ? c->launches : 0; }
+
+int dsdtm_profile(dsdtm_ctx* c, int on)
+{
+    if (!c) return DSDTM_E_ARG;
+    if (!on) stage_collect(c);
+    c->profiling = on != 0;
+    return 0;
+}
+
+int dsdtm_profile_get(dsdtm_ctx* c, float ms[DSDTM_STAGE_COUNT], int launches[DSDTM_STAGE_COUNT], int reset)
+{
+    if (!c) return DSDTM_E_ARG;
+    int r = stage_collect(c);
+    if (r) return r;
+    for (int i = 0; i < DSDTM_STAGE_COUNT; ++i) {
+        if (ms) ms[i] = c->timer.ms[i];
+        if (launches) launches[i] = c->timer.launches[i];
+        if (reset) { c->timer.ms[i] = 0; c->timer.launches[i] = 0; }
+    }
+    return 0;
+}
+
+int dsdtm_grid_dims(const dsdtm_ctx* c, int* rows, int* cols)
+{
+    if (!c) return DSDTM_E_ARG;
+    if (rows) *rows = c->grid_rows;
+    if (cols) *cols = c->grid_cols;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ pyramid
+int dsdtm_frame_upload_pyramid(dsdtm_ctx* c, int slot, const uint8_t* img, int stride)
+{
+    if (!c || !img) return DSDTM_E_ARG;
+    if (check_slot(c, slot)) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    if (stride < g.w[0]) return fail(c, DSDTM_E_ARG, "stride < width");
+    DSDTM_CUDA(c, cudaMemcpy2DAsync(c->frames_d + (size_t)slot * g.frame_stride, g.w[0], img, stride, g.w[0], g.h[0],
+                                    cudaMemcpyHostToDevice, c->stream));
+    stage_begin(c, DSDTM_STAGE_PYRAMID);
+    DSDTM_CUDA(c, launch_pyramid(c, slot, 1, c->stream));
+    stage_end(c, g.levels - 1);
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int dsdtm_frames_upload_pyramid(dsdtm_ctx* c, int first_slot, int n, const uint8_t* imgs)
+{
+    if (!c || !imgs) return DSDTM_E_ARG;
+    if (check_slot(c, first_slot, n)) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    const size_t img_bytes = (size_t)g.w[0] * g.h[0];
+    // one strided copy: n rows of img_bytes into slots frame_stride apart
+    DSDTM_CUDA(c, cudaMemcpy2DAsync(c->frames_d + (size_t)first_slot * g.frame_stride, g.frame_stride, imgs, img_bytes, img_bytes, n,
+                                    cudaMemcpyHostToDevice, c->stream));
+    stage_begin(c, DSDTM_STAGE_PYRAMID);
+    DSDTM_CUDA(c, launch_pyramid(c, first_slot, n, c->stream));
+    stage_end(c, g.levels - 1);
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int dsdtm_frames_build_pyramid(dsdtm_ctx* c, int first_slot, int n)
+{
+    if (!c) return DSDTM_E_ARG;
+    if (check_slot(c, first_slot, n)) return DSDTM_E_ARG;
+    stage_begin(c, DSDTM_STAGE_PYRAMID);
+    DSDTM_CUDA(c, launch_pyramid(c, first_slot, n, c->stream));
+    stage_end(c, c->geo.levels - 1);
+    return 0;
+}
+
+int dsdtm_frame_download_level(dsdtm_ctx* c, int slot, int level, uint8_t* out)
+{
+    if (!c || !out || level < 0 || level >= c->geo.levels) return DSDTM_E_ARG;
+    if (check_slot(c, slot)) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    DSDTM_CUDA(c, cudaMemcpyAsync(out, c->frames_d + (size_t)slot * g.frame_stride + g.off[level], (size_t)g.w[level] * g.h[level],
+                                  cudaMemcpyDeviceToHost, c->stream));
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ FAST
+int dsdtm_fast_cells_batch(dsdtm_ctx* c, int first_slot, int n, int barrier, float seed_score, const uint8_t* occupied,
+                           dsdtm_corner* cells_out)
+{
+    if (!c || !cells_out || barrier < 1 || barrier > 254 || !(seed_score >= 0.f)) return c ? fail(c, DSDTM_E_ARG, "bad fast_cells argument") : DSDTM_E_ARG;
+    if (check_slot(c, first_slot, n)) return DSDTM_E_ARG;
+    if (n > c->prm.max_batch) return fail(c, DSDTM_E_ARG, "n > max_batch");
+    const size_t nc = (size_t)n * c->n_cells;
+    if (occupied) DSDTM_CUDA(c, cudaMemcpyAsync(c->occupied_d, occupied, nc, cudaMemcpyHostToDevice, c->stream));
+    stage_begin(c, DSDTM_STAGE_FAST);
+    DSDTM_CUDA(c, launch_fast_cells(c, first_slot, n, barrier, seed_score, occupied != nullptr, c->stream));
+    stage_end(c, 1);
+    if (ensure_pinned(c, nc * sizeof(unsigned long long))) return DSDTM_E_NOMEM;
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->pinned, c->cells_d, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    decode_cells(c, reinterpret_cast<const unsigned long long*>(c->pinned), seed_score, cells_out, (int)nc);
+    return 0;
+}
+
+int dsdtm_fast_cells(dsdtm_ctx* c, int slot, int barrier, float seed_score, const uint8_t* occupied, dsdtm_corner* cells_out)
+{
+    return dsdtm_fast_cells_batch(c, slot, 1, barrier, seed_score, occupied, cells_out);
+}
+
+int dsdtm_fast_score_map(dsdtm_ctx* c, int slot, int level, int barrier, uint8_t* score, uint8_t* nonmax)
+{
+    if (!c || !score || !nonmax || level < 0 || level >= c->geo.levels || barrier < 1 || barrier > 254) return DSDTM_E_ARG;
+    if (check_slot(c, slot)) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    const size_t n = (size_t)g.w[level] * g.h[level], n0 = (size_t)g.w[0] * g.h[0];
+    DSDTM_CUDA(c, cudaMemsetAsync(c->scoremap_d, 0, 2 * n0, c->stream));
+    stage_begin(c, DSDTM_STAGE_FAST);
+    DSDTM_CUDA(c, launch_fast_score_map(c, slot, level, barrier, c->stream));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(score, c->scoremap_d, n, cudaMemcpyDeviceToHost, c->stream));
+    DSDTM_CUDA(c, cudaMemcpyAsync(nonmax, c->scoremap_d + n0, n, cudaMemcpyDeviceToHost, c->stream));
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ sparse align
+static int stage_pairs(dsdtm_ctx* c, int n_pairs, const int* ref_slots, const int* cur_slots, const dsdtm_ref_feat* feats,
+                       int feat_stride, const int* n_feats, const double* ref_centers, const double* poses_in, cudaStream_t s,
+                       int pair0 = 0)
+{
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->ref_slots_d + pair0, ref_slots + pair0, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->cur_slots_d + pair0, cur_slots + pair0, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->feats_d + (size_t)pair0 * feat_stride, feats + (size_t)pair0 * feat_stride,
+                                  (size_t)n_pairs * feat_stride * sizeof(dsdtm_ref_feat), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->n_feats_d + pair0, n_feats + pair0, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->centers_d + 3 * (size_t)pair0, ref_centers + 3 * (size_t)pair0, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->poses_in_d + 7 * (size_t)pair0, poses_in + 7 * (size_t)pair0, (size_t)n_pairs * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+static int check_pairs(dsdtm_ctx* c, int n_pairs, const int* ref_slots, const int* cur_slots, int feat_stride, const int* n_feats,
+                       int max_level, int min_level, int max_iters)
+{
+    if (n_pairs < 1 || n_pairs > c->prm.max_batch) return fail(c, DSDTM_E_ARG, "n_pairs out of range (max_batch)");
+    if (feat_stride < 1 || feat_stride > c->prm.max_feats) return fail(c, DSDTM_E_ARG, "feat_stride > max_feats");
+    if (max_level < 1 || max_level > c->geo.levels || min_level < 0 || min_level >= max_level || max_iters < 0)
+        return fail(c, DSDTM_E_ARG, "bad level range / iterations");
+    for (int i = 0; i < n_pairs; ++i) {
+        if (ref_slots[i] < 0 || ref_slots[i] >= c->prm.max_frames || cur_slots[i] < 0 || cur_slots[i] >= c->prm.max_frames)
+            return fail(c, DSDTM_E_ARG, "pair slot out of range");
+        if (n_feats[i] < 0 || n_feats[i] > feat_stride) return fail(c, DSDTM_E_ARG, "n_feats > feat_stride");
+    }
+    return 0;
+}
+
+int dsdtm_sparse_align_batch(dsdtm_ctx* c, int n_pairs, const int* ref_slots, const int* cur_slots, const dsdtm_ref_feat* feats,
+                             int feat_stride, const int* n_feats, const double* ref_centers, const double* poses_in, int max_level,
+                             int min_level, int max_iters, double* poses_out, int* n_tracked, dsdtm_iter_log* log,
+                             int log_cap_per_pair, int* n_log)
+{
+    if (!c || !ref_slots || !cur_slots || !feats || !n_feats || !ref_centers || !poses_in || !poses_out || !n_tracked) return DSDTM_E_ARG;
+    if (check_pairs(c, n_pairs, ref_slots, cur_slots, feat_stride, n_feats, max_level, min_level, max_iters)) return DSDTM_E_ARG;
+    c->batch.staged = false;
+    if (stage_pairs(c, n_pairs, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, c->stream)) return DSDTM_E_CUDA;
+    const bool want_log = log != nullptr && log_cap_per_pair > 0;
+    stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
+    DSDTM_CUDA(c, launch_sparse_align(c, n_pairs, feat_stride, max_level, min_level, max_iters, want_log, c->stream));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(poses_out, c->poses_out_d, (size_t)n_pairs * 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    DSDTM_CUDA(c, cudaMemcpyAsync(n_tracked, c->n_tracked_d, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (want_log) {
+        if (ensure_pinned(c, (size_t)n_pairs * (kLogCap * sizeof(dsdtm_iter_log) + sizeof(int)))) return DSDTM_E_NOMEM;
+        dsdtm_iter_log* hl = reinterpret_cast<dsdtm_iter_log*>(c->pinned);
+        int* hn = reinterpret_cast<int*>(c->pinned + (size_t)n_pairs * kLogCap * sizeof(dsdtm_iter_log));
+        DSDTM_CUDA(c, cudaMemcpyAsync(hl, c->log_d, (size_t)n_pairs * kLogCap * sizeof(dsdtm_iter_log), cudaMemcpyDeviceToHost, c->stream));
+        DSDTM_CUDA(c, cudaMemcpyAsync(hn, c->n_log_d, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < n_pairs; ++i) {
+            const int n = std::min(std::min(hn[i], kLogCap), log_cap_per_pair);
+            std::memcpy(log + (size_t)i * log_cap_per_pair, hl + (size_t)i * kLogCap, n * sizeof(dsdtm_iter_log));
+            if (n_log) n_log[i] = hn[i];
+        }
+    } else {
+        DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (n_log) for (int i = 0; i < n_pairs; ++i) n_log[i] = 0;
+    }
+    return 0;
+}
+
+int dsdtm_sparse_align(dsdtm_ctx* c, int ref_slot, int cur_slot, const dsdtm_ref_feat* feats, int n_feats, const double ref_center[3],
+                       const double pose_in[7], int max_level, int min_level, int max_iters, double pose_out[7], int* n_tracked,
+                       dsdtm_iter_log* log, int log_cap, int* n_log)
+{
+    if (!c) return DSDTM_E_ARG;
+    if (n_feats < 1 || n_feats > c->prm.max_feats) return fail(c, DSDTM_E_ARG, "n_feats out of range (max_feats)");
+    return dsdtm_sparse_align_batch(c, 1, &ref_slot, &cur_slot, feats, n_feats, &n_feats, ref_center, pose_in, max_level, min_level,
+                                    max_iters, pose_out, n_tracked, log, log_cap, n_log);
+}
+
+// ------------------------------------------------------------------------------------------------ align2d / warp
+int dsdtm_align2d_batch(dsdtm_ctx* c, int cur_slot, const int* level, const uint8_t* patch10, double* px_io, int n, int max_iters,
+                        uint8_t* converged)
+{
+    if (!c || !level || !patch10 || !px_io || !converged || n < 0 || max_iters < 0) return DSDTM_E_ARG;
+    if (check_slot(c, cur_slot)) return DSDTM_E_ARG;
+    if (n == 0) return 0;
+    const size_t cap = (size_t)c->prm.max_batch * std::max(c->prm.max_patches, 1);
+    if ((size_t)n > cap) return fail(c, DSDTM_E_ARG, "n > max_batch * max_patches");
+    for (int i = 0; i < n; ++i) if (level[i] >= c->geo.levels) return fail(c, DSDTM_E_ARG, "patch level out of range");
+    c->batch.staged = false;
+    if (ensure_pinned(c, (size_t)n * sizeof(int))) return DSDTM_E_NOMEM;
+    int* slots = reinterpret_cast<int*>(c->pinned);
+    for (int i = 0; i < n; ++i) slots[i] = cur_slot;
+    cudaStream_t s = c->stream;
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_slot_d, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_level_d, level, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patches_d, patch10, (size_t)n * 100, cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_px_d, px_io, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    stage_begin(c, DSDTM_STAGE_ALIGN2D);
+    DSDTM_CUDA(c, launch_align2d(c, n, max_iters, s));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(px_io, c->patch_px_d, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(converged, c->patch_conv_d, (size_t)n, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dsdtm_warp_affine_batch(dsdtm_ctx* c, const int* ref_slot, const double* A, const float* ref_px, const int* ref_level,
+                            const int* search_level, int n, uint8_t* patch10_out)
+{
+    if (!c || !ref_slot || !A || !ref_px || !ref_level || !search_level || !patch10_out || n < 0) return DSDTM_E_ARG;
+    if (n == 0) return 0;
+    const size_t cap = (size_t)c->prm.max_batch * std::max(c->prm.max_patches, 1);
+    if ((size_t)n > cap) return fail(c, DSDTM_E_ARG, "n > max_batch * max_patches");
+    if (ensure_pinned(c, (size_t)n * 3 * sizeof(int))) return DSDTM_E_NOMEM;
+    int* meta = reinterpret_cast<int*>(c->pinned);
+    for (int i = 0; i < n; ++i) {
+        if (ref_slot[i] < 0 || ref_slot[i] >= c->prm.max_frames || ref_level[i] < 0 || ref_level[i] >= c->geo.levels ||
+            search_level[i] < 0 || search_level[i] > 30)
+            return fail(c, DSDTM_E_ARG, "warp_affine: slot / level out of range");
+        meta[3 * i] = ref_slot[i]; meta[3 * i + 1] = ref_level[i]; meta[3 * i + 2] = search_level[i];
+    }
+    c->batch.staged = false;
+    cudaStream_t s = c->stream;
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->wa_meta_d, meta, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->wa_A_d, A, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->wa_px_d, ref_px, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
+    DSDTM_CUDA(c, launch_warp_affine(c, n, c->patches_d, s));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(patch10_out, c->patches_d, (size_t)n * 100, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ batched front end
+static int stage_patches(dsdtm_ctx* c, int n_pairs, const int* cur_slots, const uint8_t* patches10, const double* patch_px,
+                         const int* patch_level, int ppp, cudaStream_t s, int pair0 = 0)
+{
+    if (ppp <= 0) return 0;
+    const size_t n = (size_t)n_pairs * ppp, o = (size_t)pair0 * ppp;
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patches_d + o * 100, patches10 + o * 100, n * 100, cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_px_d + o * 2, patch_px + o * 2, n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_level_d + o, patch_level + o, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+__global__ void fill_patch_slots_kernel(const int* __restrict__ cur_slots, int* __restrict__ patch_slot, int ppp, int n, int o)
+{
+    const int i = o + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < o + n) patch_slot[i] = cur_slots[i / ppp];
+}
+
+int dsdtm_batch_stage(dsdtm_ctx* c, int n_pairs, const int* ref_slots, const int* cur_slots, const dsdtm_ref_feat* feats, int feat_stride,
+                      const int* n_feats, const double* ref_centers, const double* poses_in, int max_level, int min_level, int max_iters,
+                      const uint8_t* patches10, const double* patch_px, const int* patch_level, int ppp, int align_iters)
+{
+    if (!c || !ref_slots || !cur_slots || !feats || !n_feats || !ref_centers || !poses_in) return DSDTM_E_ARG;
+    if (check_pairs(c, n_pairs, ref_slots, cur_slots, feat_stride, n_feats, max_level, min_level, max_iters)) return DSDTM_E_ARG;
+    if (ppp < 0 || ppp > c->prm.max_patches || align_iters < 0) return fail(c, DSDTM_E_ARG, "patches_per_pair > max_patches");
+    if (ppp > 0 && (!patches10 || !patch_px || !patch_level)) return fail(c, DSDTM_E_ARG, "null patch arrays");
+    cudaStream_t s = c->stream;
+    if (stage_pairs(c, n_pairs, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, s)) return DSDTM_E_CUDA;
+    if (stage_patches(c, n_pairs, cur_slots, patches10, patch_px, patch_level, ppp, s)) return DSDTM_E_CUDA;
+    if (ppp > 0) {
+        const int n = n_pairs * ppp;
+        fill_patch_slots_kernel<<<(n + 255) / 256, 256, 0, s>>>(c->cur_slots_d, c->patch_slot_d, ppp, n, 0);
+        DSDTM_CUDA(c, cudaGetLastError());
+    }
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    auto& b = c->batch;
+    b.staged = true; b.n_pairs = n_pairs; b.feat_stride = feat_stride; b.max_level = max_level; b.min_level = min_level;
+    b.max_iters = max_iters; b.patches_per_pair = ppp; b.align_iters = align_iters;
+    return 0;
+}
+
+// the kernels of one step, enqueued on stream s (captured into a CUDA graph by dsdtm_batch_run)
+static int enqueue_step(dsdtm_ctx* c, int flags, cudaStream_t s, bool timed)
+{
+    auto& b = c->batch;
+    if (flags & 1) {
+        if (timed) stage_begin(c, DSDTM_STAGE_PYRAMID);
+        DSDTM_CUDA(c, launch_pyramid_slots(c, c->cur_slots_d, b.n_pairs, s));
+        if (timed) stage_end(c, c->geo.levels - 1);
+    }
+    if (timed) stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
+    DSDTM_CUDA(c, launch_sparse_align(c, b.n_pairs, b.feat_stride, b.max_level, b.min_level, b.max_iters, false, s));
+    if (timed) stage_end(c, 1);
+    if (b.patches_per_pair > 0) {
+        if (timed) stage_begin(c, DSDTM_STAGE_ALIGN2D);
+        DSDTM_CUDA(c, launch_align2d(c, b.n_pairs * b.patches_per_pair, b.align_iters, s));
+        if (timed) stage_end(c, 1);
+    }
+    return 0;
+}
+
+int dsdtm_batch_run(dsdtm_ctx* c, int flags)
+{
+    if (!c) return DSDTM_E_ARG;
+    auto& b = c->batch;
+    if (!b.staged) return fail(c, DSDTM_E_STATE, "dsdtm_batch_run: no staged batch");
+    const int gi = flags & 1;
+    DSDTM_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+    if (c->profiling) {
+        // per-stage events cannot be recorded inside a captured graph: launch directly
+        int r = enqueue_step(c, flags, c->stream, true);
+        if (r) return r;
+    } else {
+        const int key[8] = { b.n_pairs, b.feat_stride, b.max_level, b.min_level, b.max_iters, b.patches_per_pair, b.align_iters, flags };
+        if (!b.graph[gi] || std::memcmp(key, b.graph_key[gi], sizeof key) != 0) {
+            if (b.graph[gi]) { cudaGraphExecDestroy(b.graph[gi]); b.graph[gi] = nullptr; }
+            cudaGraph_t g = nullptr;
+            const long long l0 = c->launches;
+            DSDTM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int r = enqueue_step(c, flags, c->stream, false);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            c->launches = l0;   // capture does not launch
+            if (r) { if (g) cudaGraphDestroy(g); return r; }
+            if (e != cudaSuccess) return fail(c, DSDTM_E_CUDA, "cudaStreamEndCapture", e);
+            e = cudaGraphInstantiate(&b.graph[gi], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(c, DSDTM_E_CUDA, "cudaGraphInstantiate", e);
+            std::memcpy(b.graph_key[gi], key, sizeof key);
+            // re-record the start event after the (untimed) capture work
+            DSDTM_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+        }
+        DSDTM_CUDA(c, cudaGraphLaunch(b.graph[gi], c->stream));
+        c->launches += ((flags & 1) ? c->geo.levels - 1 : 0) + 1 + (b.patches_per_pair > 0 ? 1 : 0);
+    }
+    DSDTM_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    return 0;
+}
+
+int dsdtm_batch_fetch(dsdtm_ctx* c, double* poses_out, int* n_tracked, double* patch_px_out, uint8_t* patch_conv)
+{
+    if (!c) return DSDTM_E_ARG;
+    auto& b = c->batch;
+    if (!b.staged) return fail(c, DSDTM_E_STATE, "dsdtm_batch_fetch: no staged batch");
+    cudaStream_t s = c->stream;
+    if (poses_out) DSDTM_CUDA(c, cudaMemcpyAsync(poses_out, c->poses_out_d, (size_t)b.n_pairs * 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (n_tracked) DSDTM_CUDA(c, cudaMemcpyAsync(n_tracked, c->n_tracked_d, (size_t)b.n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+    const size_t np = (size_t)b.n_pairs * b.patches_per_pair;
+    if (np && patch_px_out) DSDTM_CUDA(c, cudaMemcpyAsync(patch_px_out, c->patch_px_d, np * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (np && patch_conv) DSDTM_CUDA(c, cudaMemcpyAsync(patch_conv, c->patch_conv_d, np, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) == cudaSuccess) c->last_run_ms = ms;
+    return 0;
+}
+
+float dsdtm_last_run_ms(const dsdtm_ctx* c) { return c ? c->last_run_ms : 0.f; }
+
+int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots, const int* cur_slots,
+                         const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats, const double* ref_centers,
+                         const double* poses_in, int max_level, int min_level, int max_iters, const uint8_t* patches10,
+                         const double* patch_px, const int* patch_level, int ppp, int align_iters, double* poses_out,
+                         int* n_tracked, double* patch_px_out, uint8_t* patch_conv)
+{
+    if (!c || !cur_imgs || !ref_slots || !cur_slots || !feats || !n_feats || !ref_centers || !poses_in || !poses_out || !n_tracked) return DSDTM_E_ARG;
+    if (check_pairs(c, n_pairs, ref_slots, cur_slots, feat_stride, n_feats, max_level, min_level, max_iters)) return DSDTM_E_ARG;
+    if (ppp < 0 || ppp > c->prm.max_patches || align_iters < 0) return fail(c, DSDTM_E_ARG, "patches_per_pair > max_patches");
+    if (ppp > 0 && (!patches10 || !patch_px || !patch_level || !patch_px_out || !patch_conv)) return fail(c, DSDTM_E_ARG, "null patch arrays");
+    c->batch.staged = false;
+    const LevelGeom& g = c->geo;
+    const size_t img_bytes = (size_t)g.w[0] * g.h[0];
+    // chunked pipeline: H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream) and the D2H of chunk k-1.
+    const int n_chunks = std::max(1, std::min(8, n_pairs / 64));
+    const int per = (n_pairs + n_chunks - 1) / n_chunks;
+    cudaStream_t cs = c->copy_stream[0], ds = c->copy_stream[1], ks = c->stream;
+    std::vector<cudaEvent_t> up(n_chunks), done(n_chunks);
+    for (int k = 0; k < n_chunks; ++k) { cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming); }
+    int rc = 0;
+    DSDTM_CUDA(c, cudaEventRecord(c->ev_a, ks));
+    DSDTM_CUDA(c, cudaStreamWaitEvent(cs, c->ev_a, 0));
+    for (int k = 0; k < n_chunks && !rc; ++k) {
+        const int p0 = k * per, n = std::min(per, n_pairs - p0);
+        if (n <= 0) break;
+        // cur images: scatter into their slots (consecutive slots collapse into one strided copy)
+        bool consecutive = true;
+        for (int i = 1; i < n; ++i) if (cur_slots[p0 + i] != cur_slots[p0] + i) { consecutive = false; break; }
+        if (consecutive) {
+            if (cudaMemcpy2DAsync(c->frames_d + (size_t)cur_slots[p0] * g.frame_stride, g.frame_stride, cur_imgs + (size_t)p0 * img_bytes,
+                                  img_bytes, img_bytes, n, cudaMemcpyHostToDevice, cs) != cudaSuccess) rc = fail(c, DSDTM_E_CUDA, "H2D images", cudaGetLastError());
+        } else {
+            for (int i = 0; i < n && !rc; ++i)
+                if (cudaMemcpyAsync(c->frames_d + (size_t)cur_slots[p0 + i] * g.frame_stride, cur_imgs + (size_t)(p0 + i) * img_bytes, img_bytes,
+                                    cudaMemcpyHostToDevice, cs) != cudaSuccess) rc = fail(c, DSDTM_E_CUDA, "H2D image", cudaGetLastError());
+        }
+        if (!rc) rc = stage_pairs(c, n, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, cs, p0);
+        if (!rc) rc = stage_patches(c, n, cur_slots, patches10, patch_px, patch_level, ppp, cs, p0);
+        if (rc) break;
+        cudaEventRecord(up[k], cs);
+        cudaStreamWaitEvent(ks, up[k], 0);
+        if (ppp > 0) fill_patch_slots_kernel<<<(n * ppp + 255) / 256, 256, 0, ks>>>(c->cur_slots_d, c->patch_slot_d, ppp, n * ppp, p0 * ppp);
+        // pyramid for this chunk's cur frames
+        {
+            cudaError_t e = launch_pyramid_slots(c, c->cur_slots_d + p0, n, ks);
+            if (e == cudaSuccess) e = launch_sparse_align(c, n, feat_stride, max_level, min_level, max_iters, false, ks, p0);
+            if (e == cudaSuccess && ppp > 0) e = launch_align2d(c, n * ppp, align_iters, ks, p0 * ppp);
+            if (e != cudaSuccess) { rc = fail(c, DSDTM_E_CUDA, "e2e launch", e); break; }
+        }
+        cudaEventRecord(done[k], ks);
+        cudaStreamWaitEvent(ds, done[k], 0);
+        cudaMemcpyAsync(poses_out + 7 * (size_t)p0, c->poses_out_d + 7 * (size_t)p0, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ds);
+        cudaMemcpyAsync(n_tracked + p0, c->n_tracked_d + p0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ds);
+        if (ppp > 0) {
+            cudaMemcpyAsync(patch_px_out + 2 * (size_t)p0 * ppp, c->patch_px_d + 2 * (size_t)p0 * ppp, (size_t)n * ppp * 2 * sizeof(double), cudaMemcpyDeviceToHost, ds);
+            cudaMemcpyAsync(patch_conv + (size_t)p0 * ppp, c->patch_conv_d + (size_t)p0 * ppp, (size_t)n * ppp, cudaMemcpyDeviceToHost, ds);
+        }
+    }
+    cudaEventRecord(c->ev_chunk[0], ds);
+    cudaStreamWaitEvent(ks, c->ev_chunk[0], 0);
+    cudaEventRecord(c->ev_b, ks);
+    cudaError_t e = cudaStreamSynchronize(ks);
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(ds);
+    for (int k = 0; k < n_chunks; ++k) { cudaEventDestroy(up[k]); cudaEventDestroy(done[k]); }
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(c, DSDTM_E_CUDA, "e2e sync", e);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) == cudaSuccess) c->last_run_ms = ms;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// ctx.cuh -- context, HBM layout and launch plumbing shared by the sm_100a kernels.
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   frame pool   : max_frames slots of frame_stride bytes; a slot holds the whole pyramid, level l dense (stride ==
+//                  width, exactly like cv::pyrDown outputs) at byte offset lvl_off[l] (16-byte aligned), followed by
+//                  >= 64 zero bytes of padding so that 1-past-the-end reads of the reference (Q4) stay inside the slot.
+//   cells        : max_batch * n_cells packed 64-bit keys (score bits << 32 | inverted raster order) for FAST atomicMax.
+//   batch inputs : feats / centers / poses / patches staged contiguously per pair.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/dsdtm_gpu.h"
+
+namespace dsdtm {
+
+struct LevelGeom {
+    int w[DSDTM_MAX_LEVELS];
+    int h[DSDTM_MAX_LEVELS];
+    unsigned off[DSDTM_MAX_LEVELS];  // byte offset inside a frame slot
+    int levels;
+    unsigned frame_stride;           // bytes per slot
+};
+
+struct StageTimer {
+    static const int kMaxEv = 64;
+    cudaEvent_t ev0[kMaxEv], ev1[kMaxEv];
+    int stage[kMaxEv];
+    int n = 0;
+    float ms[DSDTM_STAGE_COUNT] = { 0, 0, 0, 0, 0 };
+    int launches[DSDTM_STAGE_COUNT] = { 0, 0, 0, 0, 0 };
+};
+
+}  // namespace dsdtm
+
+struct dsdtm_ctx {
+    int device = 0;
+    int sm_count = 148;
+    dsdtm_cam cam;
+    dsdtm_params prm;
+    dsdtm::LevelGeom geo;
+    int grid_rows = 0, grid_cols = 0, n_cells = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream[2] = { nullptr, nullptr };
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_chunk[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::string err;
+    long long launches = 0;
+    bool profiling = false;
+    dsdtm::StageTimer timer;
+    float last_run_ms = 0.f;
+
+    // device memory
+    uint8_t* frames_d = nullptr;                 // frame pool
+    unsigned long long* cells_d = nullptr;       // max_batch * n_cells keys
+    uint8_t* occupied_d = nullptr;               // max_batch * n_cells
+    uint8_t* scoremap_d = nullptr;               // 2 * w0*h0 (score, nonmax) parity helper
+    int* fast_tiles_d = nullptr;                 // FAST tile table (level, tx, ty packed)
+    int n_fast_tiles = 0;
+
+    // batch staging (device)
+    int* ref_slots_d = nullptr;
+    int* cur_slots_d = nullptr;
+    dsdtm_ref_feat* feats_d = nullptr;           // max_batch * max_feats
+    int* n_feats_d = nullptr;
+    double* centers_d = nullptr;                 // max_batch * 3
+    double* poses_in_d = nullptr;                // max_batch * 7
+    double* poses_out_d = nullptr;               // max_batch * 7
+    int* n_tracked_d = nullptr;
+    dsdtm_iter_log* log_d = nullptr;             // max_batch * kLogCap
+    int* n_log_d = nullptr;
+    uint8_t* patches_d = nullptr;                // max_batch * max_patches * 100
+    double* patch_px_d = nullptr;                // max_batch * max_patches * 2 (in/out)
+    int* patch_level_d = nullptr;
+    int* patch_slot_d = nullptr;
+    uint8_t* patch_conv_d = nullptr;
+    // warp affine staging
+    double* wa_A_d = nullptr;
+    float* wa_px_d = nullptr;
+    int* wa_meta_d = nullptr;                    // 3 ints per candidate: slot, ref_level, search_level
+
+    // pinned host staging for small synchronous calls
+    uint8_t* pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    // staged batch description
+    struct {
+        bool staged = false;
+        int n_pairs = 0, feat_stride = 0, max_level = 0, min_level = 0, max_iters = 0;
+        int patches_per_pair = 0, align_iters = 0;
+        cudaGraphExec_t graph[2] = { nullptr, nullptr };   // [flags & 1]
+        int graph_key[2][8];
+    } batch;
+};
+
+namespace dsdtm {
+
+static const int kLogCap = 256;  // per-pair iteration-log capacity on the device
+
+inline int fail(dsdtm_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    c->err = buf;
+    return code;
+}
+
+#define DSDTM_CUDA(ctx, call)                                                        \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) return dsdtm::fail((ctx), DSDTM_E_CUDA, #call, e__); \
+    } while (0)
+
+// ---- stage timing (CUDA events on ctx->stream) ----
+void stage_begin(dsdtm_ctx* c, int stage);
+void stage_end(dsdtm_ctx* c, int n_launches);
+int  stage_collect(dsdtm_ctx* c);
+
+// ---- kernel launchers (each returns cudaGetLastError()) ----
+cudaError_t launch_pyramid(dsdtm_ctx* c, int first_slot, int n, cudaStream_t s);
+cudaError_t launch_pyramid_slots(dsdtm_ctx* c, const int* slots_d, int n, cudaStream_t s);
+cudaError_t launch_fast_cells(dsdtm_ctx* c, int first_slot, int n, int barrier, float seed_score, bool use_occupied,
+                              cudaStream_t s);
+cudaError_t launch_fast_score_map(dsdtm_ctx* c, int slot, int level, int barrier, cudaStream_t s);
+cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int max_level, int min_level, int max_iters,
+                                bool want_log, cudaStream_t s, int pair0 = 0);
+cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
+cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s);
+int sparse_align_smem_bytes(int nf_pad);
+cudaError_t sparse_align_init(dsdtm_ctx* c);
+
+}  // namespace dsdtm

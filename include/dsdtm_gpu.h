@@ -1,0 +1,187 @@
+/*
+ * dsdtm_gpu.h -- C-ABI of the B200-native tracking front end (drop-in boundary).
+ *
+ * The reference (gaochq/DSDTM) has no FFI: the seam is three C++ classes and one Frame method, all called
+ * from the tracking thread. Each entry point below names the reference interface it replaces ("ref:" paths are
+ * below the reference root). No C++ / torch type crosses this boundary: plain pointers, sizes, PODs.
+ *
+ * Conventions
+ *   - every pointer is HOST memory unless the name ends in _d; pinned host memory makes copies asynchronous;
+ *   - return 0 = ok, < 0 = error (DSDTM_E_*); never throws, never aborts; dsdtm_last_error() gives the text;
+ *   - a context is single-thread-affine (one per host thread / per GPU), like the reference's tracking thread;
+ *   - pose7 = {qw,qx,qy,qz,tx,ty,tz}: unit quaternion + translation = Sophus::SE3's state;
+ *   - images are 8-bit gray, row-major, level images dense (stride == width) like cv::pyrDown outputs;
+ *   - there is NO CPU fallback: without a CUDA device dsdtm_create() fails.
+ */
+#ifndef DSDTM_GPU_H
+#define DSDTM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSDTM_ABI_VERSION 1
+#define DSDTM_MAX_LEVELS 8
+#define DSDTM_MAX_FEATS_LIMIT 512 /* hard upper bound for dsdtm_params.max_feats */
+
+enum {
+    DSDTM_OK = 0,
+    DSDTM_E_ARG = -1,    /* bad argument */
+    DSDTM_E_CUDA = -2,   /* CUDA runtime error (text in dsdtm_last_error) */
+    DSDTM_E_NOMEM = -3,  /* device / pinned allocation failed */
+    DSDTM_E_STATE = -4   /* call sequence error (e.g. batch not staged) */
+};
+
+typedef struct dsdtm_ctx dsdtm_ctx;
+
+/* ref: include/Camera.h:137-163, src/Camera.cpp:34-48 -- intrinsics are float in the reference on purpose */
+typedef struct {
+    int   width, height;
+    float fx, fy, cx, cy;
+    float f; /* Camera.f: the focal length Sprase_ImgAlign's Jacobian uses (ref: src/Sprase_ImageAlign.cpp:70,160) */
+} dsdtm_cam;
+
+/* ref: Config keys read at src/Feature_detection.cpp:12-16, src/Feature_alignment.cpp:24-30, src/Frame.cpp:51-52 */
+typedef struct {
+    int levels;      /* Camera.MaxPyraLevels (1..DSDTM_MAX_LEVELS) */
+    int cell_size;   /* Camera.CellSize */
+    int max_feats;   /* capacity: reference features per frame pair handed to sparse alignment (<= 512) */
+    int max_patches; /* capacity: Align2D patches per frame */
+    int max_frames;  /* frame slots in the device pool (each holds one full pyramid) */
+    int max_batch;   /* capacity: frame pairs per batched call */
+} dsdtm_params;
+
+/* One reference feature as Sprase_ImgAlign::GetJocabianMat reads it (ref: src/Sprase_ImageAlign.cpp:84-103) */
+typedef struct {
+    float  px[2];      /* Feature::mpx       ref: include/Feature.h:19 */
+    int    level;      /* Feature::mlevel    ref: include/Feature.h:20 */
+    int    initial;    /* Feature::mbInitial ref: include/Feature.h:23 */
+    double normal[3];  /* Feature::mNormal   ref: include/Feature.h:24 */
+    double point_w[3]; /* Feature::Mpt->Get_Pose() snapshot, ref: src/MapPoint.cpp:38-43 */
+} dsdtm_ref_feat;      /* 64 bytes */
+
+/* ref: include/Feature_detection.h:19-33 (struct Corner; angle is always 0 and dropped) */
+typedef struct {
+    int   x, y, level;
+    float score;
+} dsdtm_corner; /* 16 bytes */
+
+/* One Gauss-Newton iteration of Sprase_ImgAlign::GaussNewtonSolver (ref: src/Sprase_ImageAlign.cpp:310-343) */
+typedef struct {
+    int    level, iter;
+    int    n_pts;  /* visible features in this ComputeResiduals call */
+    int    flags;  /* bit0 update accepted, bit1 reverted (chi2 increase / NaN), bit2 NaN solve, bit3 |x|<=1e-8 */
+    double chi2;   /* chi2New = mean squared residual */
+    double x[6];   /* GN step (upsilon, omega) */
+} dsdtm_iter_log;  /* 72 bytes */
+
+/* Per-stage device timing, filled when profiling is on (CUDA events on the context's stream). */
+enum { DSDTM_STAGE_PYRAMID = 0, DSDTM_STAGE_FAST = 1, DSDTM_STAGE_SPARSE_ALIGN = 2, DSDTM_STAGE_ALIGN2D = 3,
+       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_COUNT = 5 };
+
+/* ---------------------------------------------------------------- context ---------------------------------- */
+int         dsdtm_abi_version(void);
+/* Creates a context on CUDA device `device`. Returns NULL on failure (call dsdtm_create_error() for the text). */
+dsdtm_ctx*  dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* params);
+const char* dsdtm_create_error(void);
+void        dsdtm_destroy(dsdtm_ctx* ctx);
+const char* dsdtm_last_error(const dsdtm_ctx* ctx);
+int         dsdtm_sync(dsdtm_ctx* ctx);
+/* level geometry of the device pyramid: width, height and byte offset of `level` inside a frame slot */
+int         dsdtm_level_info(const dsdtm_ctx* ctx, int level, int* w, int* h, size_t* offset);
+size_t      dsdtm_frame_stride(const dsdtm_ctx* ctx);
+/* pinned host memory helpers (for asynchronous copies at the boundary) */
+void*       dsdtm_host_alloc(size_t bytes);
+void        dsdtm_host_free(void* p);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+long long   dsdtm_launch_count(const dsdtm_ctx* ctx);
+/* stage profiling: on != 0 brackets every stage with CUDA events; get returns accumulated ms and launch counts */
+int         dsdtm_profile(dsdtm_ctx* ctx, int on);
+int         dsdtm_profile_get(dsdtm_ctx* ctx, float ms[DSDTM_STAGE_COUNT], int launches[DSDTM_STAGE_COUNT], int reset);
+
+/* ---------------------------------------------------------------- (a) image pyramid ------------------------ */
+/* replaces Frame::ComputeImagePyramid (ref: src/Frame.cpp:74-81; include/Frame.h:32): uploads level 0 and builds
+ * levels 1..levels-1 with cv::pyrDown semantics into frame slot `slot`. stride = bytes per input row. */
+int dsdtm_frame_upload_pyramid(dsdtm_ctx* ctx, int slot, const uint8_t* img, int stride);
+/* batched: n dense (stride == width) images into slots first_slot .. first_slot+n-1 */
+int dsdtm_frames_upload_pyramid(dsdtm_ctx* ctx, int first_slot, int n, const uint8_t* imgs);
+/* device-resident variant: level 0 of the n slots is already in HBM (e.g. written by a previous upload); rebuild levels */
+int dsdtm_frames_build_pyramid(dsdtm_ctx* ctx, int first_slot, int n);
+/* parity helper: copy one level of a slot back (dense w*h bytes) */
+int dsdtm_frame_download_level(dsdtm_ctx* ctx, int slot, int level, uint8_t* out);
+
+/* ---------------------------------------------------------------- (b) FAST + grid cells -------------------- */
+/* replaces the per-level loop of Feature_detector::detect (ref: src/Feature_detection.cpp:74-109): FAST-10 at
+ * `barrier` (reference literal: 20) on every level, 3x3 non-max on the FAST score, Shi-Tomasi score, per-cell best
+ * (strictly greater than seed_score; earliest level, then raster order, wins ties). occupied (grid_rows*grid_cols
+ * bytes, may be NULL) = mvGrid_occupy. cells_out[grid_rows*grid_cols] in cell order; empty cells = {0,0,0,seed_score}.
+ * Sorting and mask-circle selection (ref: :111-150) stay on the host (dsdtm_b200/host). */
+int dsdtm_fast_cells(dsdtm_ctx* ctx, int slot, int barrier, float seed_score, const uint8_t* occupied,
+                     dsdtm_corner* cells_out);
+/* batched over n consecutive slots; occupied (may be NULL) and cells_out are n * grid_rows*grid_cols */
+int dsdtm_fast_cells_batch(dsdtm_ctx* ctx, int first_slot, int n, int barrier, float seed_score,
+                           const uint8_t* occupied, dsdtm_corner* cells_out);
+/* parity helper replacing fast_corner_detect_10[_sse2] + fast_corner_score_10 + fast_nonmax_3x3
+ * (ref: Thirdparty/fast/include/fast/fast.h:20-29): dense maps for one level, w*h bytes each.
+ * score[i] = FAST score (>= barrier) if pixel i is a corner else 0; nonmax[i] = 1 if it survives 3x3 non-max. */
+int dsdtm_fast_score_map(dsdtm_ctx* ctx, int slot, int level, int barrier, uint8_t* score, uint8_t* nonmax);
+int dsdtm_grid_dims(const dsdtm_ctx* ctx, int* rows, int* cols);
+
+/* ---------------------------------------------------------------- (c) sparse image alignment --------------- */
+/* replaces Sprase_ImgAlign::Run's level loop: GetJocabianMat + GaussNewtonSolver for levels max_level-1 .. min_level
+ * (ref: src/Sprase_ImageAlign.cpp:43-55,62-166,240-344). pose_c2r_in = T_cur * T_ref^-1 (ref: :43); the caller composes
+ * pose_c2r_out * T_ref (ref: :57). *n_tracked = Run's return value. log (may be NULL) receives one entry per iteration. */
+int dsdtm_sparse_align(dsdtm_ctx* ctx, int ref_slot, int cur_slot, const dsdtm_ref_feat* feats, int n_feats,
+                       const double ref_center[3], const double pose_c2r_in[7], int max_level, int min_level,
+                       int max_iters, double pose_c2r_out[7], int* n_tracked, dsdtm_iter_log* log, int log_cap,
+                       int* n_log);
+/* batched over independent frame pairs (the sweep of BASELINE.json configs[4]). feats is n_pairs * feat_stride. */
+int dsdtm_sparse_align_batch(dsdtm_ctx* ctx, int n_pairs, const int* ref_slots, const int* cur_slots,
+                             const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats,
+                             const double* ref_centers, const double* poses_in, int max_level, int min_level,
+                             int max_iters, double* poses_out, int* n_tracked, dsdtm_iter_log* log,
+                             int log_cap_per_pair, int* n_log);
+
+/* ---------------------------------------------------------------- (d) feature alignment -------------------- */
+/* replaces Feature_Alignment::Align2DGaussNewton for n patches against ONE current frame
+ * (ref: src/Feature_alignment.cpp:318-417; include/Feature_alignment.h:85). level[i] = pyramid level searched,
+ * patch10 = n x 100 bytes (mPatch_WithBoarder; the 8x8 mPatch is its interior, ref: :261-275),
+ * px_io = n x 2 doubles in LEVEL coordinates (tCurPx), converged[i] = return value. */
+int dsdtm_align2d_batch(dsdtm_ctx* ctx, int cur_slot, const int* level, const uint8_t* patch10, double* px_io, int n,
+                        int max_iters, uint8_t* converged);
+/* replaces Feature_Alignment::WarpAffine + GetPatchNoBoarder for n candidates (ref: src/Feature_alignment.cpp:206-275).
+ * ref_slot[i] = frame slot of the reference keyframe, A = n x 4 doubles (row-major A_cur<-ref),
+ * ref_px = n x 2 floats (Feature::mpx), ref_level / search_level per candidate, patch10_out = n x 100 bytes. */
+int dsdtm_warp_affine_batch(dsdtm_ctx* ctx, const int* ref_slot, const double* A, const float* ref_px,
+                            const int* ref_level, const int* search_level, int n, uint8_t* patch10_out);
+
+/* ---------------------------------------------------------------- batched front end (sweep / bench) -------- */
+/* One "step" over n_pairs independent frame pairs: [pyramid(cur)] -> sparse align -> Align2D of the pair's patches
+ * against its cur frame. Inputs are staged once (H2D), run() only launches kernels on HBM-resident data (CUDA-graph
+ * replayed), fetch() copies results back. patches: n_pairs * patches_per_pair entries, patch_level < 0 = unused.
+ * flags bit0: rebuild the cur pyramids from their level 0 inside run(). */
+int dsdtm_batch_stage(dsdtm_ctx* ctx, int n_pairs, const int* ref_slots, const int* cur_slots,
+                      const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats, const double* ref_centers,
+                      const double* poses_in, int max_level, int min_level, int max_iters,
+                      const uint8_t* patches10, const double* patch_px, const int* patch_level,
+                      int patches_per_pair, int align_iters);
+int dsdtm_batch_run(dsdtm_ctx* ctx, int flags);
+int dsdtm_batch_fetch(dsdtm_ctx* ctx, double* poses_out, int* n_tracked, double* patch_px_out, uint8_t* patch_conv);
+/* end-to-end step with HOST buffers: uploads the n_pairs cur images (dense, pinned recommended) into their cur slots,
+ * stages the per-pair inputs, runs, and fetches -- copies overlapped with compute in chunks on internal streams. */
+int dsdtm_pair_batch_e2e(dsdtm_ctx* ctx, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots,
+                         const int* cur_slots, const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats,
+                         const double* ref_centers, const double* poses_in, int max_level, int min_level,
+                         int max_iters, const uint8_t* patches10, const double* patch_px, const int* patch_level,
+                         int patches_per_pair, int align_iters, double* poses_out, int* n_tracked,
+                         double* patch_px_out, uint8_t* patch_conv);
+/* device time of the last dsdtm_batch_run / e2e call measured with CUDA events on the context's stream [ms] */
+float dsdtm_last_run_ms(const dsdtm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSDTM_GPU_H */

@@ -1,0 +1,79 @@
+"""Shared test helpers: synthetic scenarios checked by the CPU oracle (test infrastructure)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import oracle as O  # noqa: E402
+from dsdtm_b200 import synth as S  # noqa: E402
+
+
+def ocam(cam):
+    return O.make_cam(cam["width"], cam["height"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["f"])
+
+
+def detect_oracle(img, levels=5, cell=15, max_fts=300, thr=5.0):
+    """Feature_detector::detect on the oracle: returns (features CORNER_DT, packed pyramid, offs, ws, hs)."""
+    packed, offs, ws, hs = O.pyramid(img, levels)
+    cells = O.detect_cells(packed, offs, ws, hs, cell, None, thr)
+    mask = np.full(img.shape, 255, np.uint8)
+    feats, _ = O.detect_select(cells, mask, cell, max_fts)
+    return feats, (packed, offs, ws, hs)
+
+
+def ref_feats_from_corners(cam, corners, ref_points, n_pad=None):
+    """dsdtm_ref_feat records for detected corners with analytic depth (Feature + MapPoint snapshot)."""
+    oc = ocam(cam)
+    n = len(corners)
+    F = np.zeros(n if n_pad is None else n_pad, O.REF_FEAT_DT)
+    for i, c in enumerate(corners):
+        F[i]["px"] = (c["x"], c["y"])
+        F[i]["level"] = c["level"]
+        F[i]["initial"] = 1
+        F[i]["normal"] = O.feature_normal(oc, F[i]["px"])
+        F[i]["point_w"] = ref_points[c["y"], c["x"]]
+    return F
+
+
+def make_scenario(seed, cam=S.KINECT, levels=5, max_fts=300, trans=0.02, rot_deg=0.5):
+    pr = S.make_pair(seed, cam, trans, rot_deg)
+    corners, pyr = detect_oracle(pr["ref_img"], levels, 15, max_fts)
+    pr["corners"] = corners
+    pr["feats"] = ref_feats_from_corners(cam, corners, pr["ref_points"])
+    pr["ref_pyr"] = pyr
+    pr["cur_pyr"] = O.pyramid(pr["cur_img"], levels)
+    pr["ref_center"] = -(S.quat_to_R(pr["T_ref"][:4]).T @ pr["T_ref"][4:])
+    return pr
+
+
+def make_patches(cur_pyr, n, seed, max_level=0, pert=1.5, margin=8):
+    """test_Feature_alignment recipe (ref: Test/test_Feature_alignment.cpp:47-86) on a synthetic image: 10x10 reference
+    patches interpolated at sub-pixel truths, start positions perturbed by U(+-pert)."""
+    packed, offs, ws, hs = cur_pyr
+    rng = np.random.default_rng(seed)
+    levels = rng.integers(0, max_level + 1, n).astype(np.int32)
+    patches = np.zeros((n, 100), np.uint8)
+    truth = np.zeros((n, 2))
+    start = np.zeros((n, 2))
+    for i in range(n):
+        L = int(levels[i])
+        img = O.pyr_level(packed, offs, ws, hs, L).astype(np.float64)
+        h, w = img.shape
+        tx = rng.uniform(margin + 6, w - margin - 7)
+        ty = rng.uniform(margin + 6, h - margin - 7)
+        truth[i] = (tx, ty)
+        # generateRefPatchNoWarpInterpolate: bilinear sample of a 10x10 window centred on the truth
+        xs = tx - 5 + np.arange(10)
+        ys = ty - 5 + np.arange(10)
+        x0 = np.floor(xs).astype(int); y0 = np.floor(ys).astype(int)
+        fx = xs - x0; fy = ys - y0
+        I = img
+        p = ((1 - fy)[:, None] * ((1 - fx)[None, :] * I[np.ix_(y0, x0)] + fx[None, :] * I[np.ix_(y0, x0 + 1)]) +
+             fy[:, None] * ((1 - fx)[None, :] * I[np.ix_(y0 + 1, x0)] + fx[None, :] * I[np.ix_(y0 + 1, x0 + 1)]))
+        patches[i] = np.clip(np.rint(p), 0, 255).astype(np.uint8).reshape(-1)
+        start[i] = truth[i] + rng.uniform(-pert, pert, 2)
+    return levels, patches, truth, start
