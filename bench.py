@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- the tracking front end's hot path on batches of independent synthetic frame pairs.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of B frame pairs per GPU, all inputs resident in HBM:
+    pyramid(cur frame) -> Sprase_ImgAlign (levels max_level-1..0, Gauss-Newton on SE3) -> Align2D of the pair's patches.
+`value` = frame pairs / s over all ranks (max-over-ranks device time, CUDA events on the launching stream).
+`e2e`   = the same metric through the C-ABI call with HOST (pinned) buffers: H2D of the cur images + per-pair inputs and
+          D2H of the results inside the timed region.
+The reference arm (--impl reference) times the CPU restatement of the reference (oracle/, kind "port": the reference itself
+needs OpenCV/Eigen/Sophus/Ceres and cannot be built here) on all host threads.
+No pair shards across GPUs: N > 1 = N independent replicas of the batch (weak scaling), no collective on the data path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sparse-align frame pairs/sec (640x480, 300 feats)"
+UNIT = "frame_pairs/s"
+ALIGN_CFG = dict(max_level=4, min_level=0, max_iters=30)      # Test/test_SpraseImg_alignment.cpp:110 -> Sprase_ImgAlign(4, 0, 30)
+LEVELS = 5                                                      # Camera.MaxPyraLevels (Config/kinect.yaml:66)
+ALIGN2D_ITERS = 10                                              # src/Feature_alignment.cpp:152
+N_FEATS = 300
+FEAT_STRIDE = 320
+
+
+def shard(n_total, world, rank):
+    """Contiguous block partition of n_total independent units over `world` ranks."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _pump(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def algorithmic_bytes(n_feats, iters_per_level):
+    """sparse align touches N*49 B of the ref level per level + N*25 B of the cur level per iteration,
+    plus the feature records (64 B each) and the pose in/out."""
+    levels = len(iters_per_level)
+    return n_feats * (64 + 49 * levels + 25 * int(sum(iters_per_level))) + 2 * 56
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dsdtm_b200 import capi, synth as S, workload as W
+
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cam = dict(S.KINECT)
+    B = args.pairs
+    ctx = capi.Context(cam, levels=LEVELS, cell_size=15, max_feats=FEAT_STRIDE, max_patches=N_FEATS, max_frames=2 * B + 2, max_batch=B,
+                       device=local)
+    t0 = time.time()
+    batch = W.build_batch(ctx, cam, B, n_scenes=args.scenes, n_feats=N_FEATS, feat_stride=FEAT_STRIDE, patches_per_pair=N_FEATS,
+                          seed0=W.BASE_SEED + 1000 * rank)
+    prep_s = time.time() - t0
+    ppp = batch["patches_per_pair"]
+    ctx.batch_stage(batch["ref_slots"], batch["cur_slots"], batch["feats"], batch["n_feats"], batch["centers"], batch["poses_in"],
+                    ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], batch["patches"], batch["patch_px"],
+                    batch["patch_level"], ALIGN2D_ITERS)
+
+    def restage():
+        # single-call entry points reuse the staging buffers: stage the batch again before batch_run
+        ctx.batch_stage(batch["ref_slots"], batch["cur_slots"], batch["feats"], batch["n_feats"], batch["centers"], batch["poses_in"],
+                        ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], batch["patches"], batch["patch_px"],
+                        batch["patch_level"], ALIGN2D_ITERS)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---------------- device-resident steps (value)
+    for _ in range(max(args.warmup, 3)):
+        ctx.batch_run(1)
+    ctx.sync()
+    poses, n_tracked, px, conv = ctx.batch_fetch()
+    # sanity: converged to the ground-truth motion (checked on every rank; parity proper lives in tests/)
+    err = np.array([S.pose_dist(poses[i], batch["truth"][i]) for i in range(min(B, 64))])
+    if not (np.median(err[:, 0]) < 5e-4 and np.median(err[:, 1]) < 1e-3):
+        raise SystemExit("bench.py: alignment did not converge to the synthetic ground truth: %s" % np.median(err, 0))
+    clocks = ClockSampler(local)
+    barrier()
+    l0 = ctx.launch_count()
+    clocks.start()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        ctx.batch_run(1)
+    dev_ms = ctx.timer_stop()
+    clk = clocks.stop()
+    launches = ctx.launch_count() - l0
+    barrier()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    ms_per_step = max_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---------------- per-stage device times (profiling pass, outside the timed region; events per stage)
+    ctx.profile(True)
+    ctx.profile_get(reset=True)
+    for _ in range(args.steps):
+        ctx.batch_run(1)
+    stages = ctx.profile_get(reset=True)
+    ctx.profile(False)
+    sa_ms = stages["sparse_align"][0] / max(stages["sparse_align"][1], 1)
+    pyr_ms = stages["pyramid"][0] / args.steps
+    a2d_ms = stages["align2d"][0] / max(stages["align2d"][1], 1)
+    # iterations actually executed (for the algorithmic byte count)
+    _, _, log, nlog = ctx.sparse_align_batch(batch["ref_slots"][:min(B, 64)], batch["cur_slots"][:min(B, 64)], batch["feats"][:min(B, 64)],
+                                             batch["n_feats"][:min(B, 64)], batch["centers"][:min(B, 64)], batch["poses_in"][:min(B, 64)],
+                                             ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], log_cap=128)
+    iters = float(np.mean(nlog))
+    n_levels = ALIGN_CFG["max_level"] - ALIGN_CFG["min_level"]
+    restage()
+    hbm_peak, peak_src = peaks()
+    sa_bytes = B * (int(np.mean(batch["n_feats"])) * (64 + 49 * n_levels + 25 * iters) + 112)
+    g = ctx
+    pyr_bytes = B * sum(g.ws[l - 1] * g.hs[l - 1] + g.ws[l] * g.hs[l] for l in range(1, LEVELS))
+    # FAST stage (keyframes only, not part of the step): timed separately over the ref frames for its roofline
+    nfast = min(B, 256)
+    ctx.profile(True); ctx.profile_get(reset=True)
+    cells_tmp = np.zeros(nfast * ctx.n_cells, capi.CORNER_DT)
+    fast_ms = None
+    try:
+        # consecutive slots 0..nfast-1 hold ref/cur frames alternately: all are valid pyramids
+        for _ in range(3):
+            ctx._ck(ctx.L.dsdtm_fast_cells_batch(ctx.hp, 0, nfast, 20, capi.C.c_float(5.0), None, capi._p(cells_tmp)))
+        st = ctx.profile_get(reset=True)
+        fast_ms = st["fast"][0] / max(st["fast"][1], 1)
+    finally:
+        ctx.profile(False)
+    fast_bytes = nfast * (sum(g.ws[l] * g.hs[l] for l in range(LEVELS)) + ctx.n_cells * 16)
+
+    # ---------------- end-to-end through the C-ABI with host buffers
+    h, w = cam["height"], cam["width"]
+    pin = capi.pinned_empty
+    cur_imgs = pin((B, h, w), np.uint8)
+    for i in range(B):
+        cur_imgs[i] = batch["scenes"][i % batch["n_scenes"]]["cur_img"]
+    hb = dict(ref_slots=pin((B,), np.int32), cur_slots=pin((B,), np.int32), feats=pin((B, FEAT_STRIDE), capi.REF_FEAT_DT),
+              n_feats=pin((B,), np.int32), centers=pin((B, 3), np.float64), poses_in=pin((B, 7), np.float64),
+              patches=pin((B, ppp, 100), np.uint8), patch_px=pin((B, ppp, 2), np.float64), patch_level=pin((B, ppp), np.int32))
+    for k_, src in (("ref_slots", batch["ref_slots"]), ("cur_slots", batch["cur_slots"]), ("feats", batch["feats"]), ("n_feats", batch["n_feats"]),
+                    ("centers", batch["centers"]), ("poses_in", batch["poses_in"]), ("patches", batch["patches"]), ("patch_px", batch["patch_px"]),
+                    ("patch_level", batch["patch_level"])):
+        hb[k_][...] = src
+    out = dict(poses=pin((B, 7), np.float64), n_tracked=pin((B,), np.int32), px=pin((B, ppp, 2), np.float64), conv=pin((B, ppp), np.uint8))
+
+    def e2e_step():
+        ctx.pair_batch_e2e(cur_imgs, hb["ref_slots"], hb["cur_slots"], hb["feats"], FEAT_STRIDE, hb["n_feats"], hb["centers"], hb["poses_in"],
+                           ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], hb["patches"], hb["patch_px"],
+                           hb["patch_level"], ppp, ALIGN2D_ITERS, out)
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    if not np.array_equal(out["poses"], poses):
+        raise SystemExit("bench.py: e2e results differ from the device-resident run")
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_wall = time.perf_counter() - t1
+    barrier()
+    t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+    h2d = int(cur_imgs.nbytes + sum(hb[k_].nbytes for k_ in hb))
+    d2h = int(sum(out[k_].nbytes for k_ in out))
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample, all host threads
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(batch, cam, sample=min(B, args.cpu_sample))
+        # the checker beside the number: CPU port and CUDA path agree on the sampled pairs (tolerances of tests/)
+        cp = cpu.pop("_poses")
+        d = np.array([S.pose_dist(cp[i], poses[i]) for i in range(len(cp))])
+        cpu["max_pose_diff_vs_gpu"] = [float(d[:, 0].max()), float(d[:, 1].max())]
+
+    if rank == 0:
+        sa_gbs = sa_bytes / (sa_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic: %d ray-cast relief scenes tiled to %d pairs/GPU with per-pair start poses; every pair has its own frames, "
+                    "features and patches in HBM" % (batch["n_scenes"], B),
+            "config": {"workload": "configs[0] shape batched: %d independent 640x480 kinect frame pairs per GPU, %d FAST/Shi-Tomasi features, "
+                                   "5-level pyramid(cur) + Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it)" % (B, N_FEATS, ppp),
+                       "pairs_per_gpu": B, "features": N_FEATS, "levels": LEVELS, "sparse_align": ALIGN_CFG, "align2d_iters": ALIGN2D_ITERS,
+                       "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (2 * B * ctx.L.dsdtm_frame_stride(ctx.hp) / 1e6)},
+            "us_per_pair": ms_per_step * 1e3 / B,
+            "gn_iterations_per_pair": iters,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t.item()) * 1e3 / args.steps, "timer": "host wall clock around the C-ABI call"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"kernel": "sparse_align_kernel", "bound": "hbm", "achieved": sa_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": sa_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "ms_per_launch": sa_ms, "algorithmic_bytes_per_launch": sa_bytes,
+                         "note": "dependent Gauss-Newton chain: latency/issue-bound, not bandwidth-bound (SURVEY 8d); see stages"},
+            "stages": {
+                "pyramid": {"ms_per_step": pyr_ms, "GBps": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "frac_hbm": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak,
+                            "algorithmic_bytes": pyr_bytes},
+                "sparse_align": {"ms_per_step": sa_ms, "us_per_pair_per_sm": sa_ms * 1e3 * 148 / B},
+                "align2d": {"ms_per_step": a2d_ms},
+                "fast_cells": {"ms_per_launch": fast_ms, "frames": nfast, "GBps": fast_bytes / (fast_ms * 1e-3) / 1e9 if fast_ms else None,
+                               "frac_hbm": fast_bytes / (fast_ms * 1e-3) / 1e9 / hbm_peak if fast_ms else None, "algorithmic_bytes": fast_bytes,
+                               "note": "keyframe-only stage, not part of the step"}},
+            "cpu_baseline": cpu,
+            "prep_s": prep_s,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(batch, cam, sample, threads=None, reps=1):
+    """The oracle (CPU restatement of the reference, kind 'port') on `sample` pairs of the same workload, all host threads."""
+    import oracle as O
+    from dsdtm_b200 import synth as S
+    threads = threads or (os.cpu_count() or 1)
+    oc = O.make_cam(cam["width"], cam["height"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["f"])
+    k = batch["n_scenes"]
+    ref_pyr = [O.pyramid(sc["ref_img"], LEVELS)[0] for sc in batch["scenes"]]
+    pyr_bytes = len(ref_pyr[0])
+    n = sample
+    ref_pyrs = np.empty((n, pyr_bytes), np.uint8)
+    cur_imgs = np.empty((n, cam["height"], cam["width"]), np.uint8)
+    for i in range(n):
+        ref_pyrs[i] = ref_pyr[i % k]
+        cur_imgs[i] = batch["scenes"][i % k]["cur_img"]
+    feats = batch["feats"][:n].astype(O.REF_FEAT_DT)
+    args = (oc, LEVELS, ref_pyrs, cur_imgs, feats, batch["n_feats"][:n], batch["centers"][:n], batch["poses_in"][:n],
+            ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], batch["patches"][:n], batch["patch_px"][:n],
+            batch["patch_level"][:n], ALIGN2D_ITERS, threads)
+    O.pair_batch(*args)     # warm-up (page in, thread start)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        poses, nt, px, conv = O.pair_batch(*args)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d pairs of the same workload (pyramid(cur)+sparse align+align2d), %d std::threads, %.2f s" % (n, threads, dt),
+            "us_per_pair_per_core": dt / n * threads * 1e6,
+            "_poses": poses}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on the box's host cores, same config / metric / unit."""
+    rank, world, local = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    from dsdtm_b200 import synth as S, workload as W
+    import oracle as O
+    cam = dict(S.KINECT)
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample
+    # the same workload builder needs GPU FAST for feature selection; the reference arm uses the oracle's detector instead
+    scenes = W.render_scenes(args.scenes, cam, seed0=W.BASE_SEED)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    feats = np.zeros((sample, FEAT_STRIDE), O.REF_FEAT_DT); nf = np.zeros(sample, np.int32)
+    centers = np.zeros((sample, 3)); poses = np.tile(S.IDENTITY, (sample, 1))
+    patches = np.zeros((sample, N_FEATS, 100), np.uint8); ppx = np.zeros((sample, N_FEATS, 2)); plv = np.full((sample, N_FEATS), -1, np.int32)
+    per = []
+    for sc in scenes:
+        corners, pyr = H.detect_oracle(sc["ref_img"], LEVELS, 15, N_FEATS)
+        F = H.ref_feats_from_corners(cam, corners, sc["ref_points"], n_pad=FEAT_STRIDE)
+        cur_pyr = O.pyramid(sc["cur_img"], LEVELS)
+        lv, pt, truth, st = H.make_patches(cur_pyr, N_FEATS, sc["seed"], max_level=0, pert=1.0)
+        per.append((F, len(corners), pyr[0], lv, pt, st))
+    k = len(scenes)
+    ref_pyrs = np.empty((sample, len(per[0][2])), np.uint8); cur_imgs = np.empty((sample, cam["height"], cam["width"]), np.uint8)
+    for i in range(sample):
+        F, n, rp, lv, pt, st = per[i % k]
+        feats[i] = F; nf[i] = n; ref_pyrs[i] = rp; cur_imgs[i] = scenes[i % k]["cur_img"]
+        patches[i] = pt; ppx[i] = st; plv[i] = lv
+    oc = O.make_cam(cam["width"], cam["height"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["f"])
+    a = (oc, LEVELS, ref_pyrs, cur_imgs, feats, nf, centers, poses, ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"],
+         patches, ppx, plv, ALIGN2D_ITERS, threads)
+    for _ in range(max(args.warmup, 1)):
+        O.pair_batch(*a)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.pair_batch(*a)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic: %d ray-cast relief scenes tiled to a bounded sample of %d pairs per step" % (k, sample),
+            "config": {"workload": "configs[0] shape batched: independent 640x480 kinect frame pairs, %d features, 5-level pyramid(cur) + "
+                                   "Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it); CPU step = bounded sample of %d pairs" % (N_FEATS, N_FEATS, sample),
+                       "features": N_FEATS, "levels": LEVELS, "sparse_align": ALIGN_CFG, "align2d_iters": ALIGN2D_ITERS},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d pairs per step, %d std::threads (the reference needs OpenCV/Eigen/Sophus/Ceres: not buildable here; "
+                                       "oracle/ restates it line by line)" % (sample, threads)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per GPU per step")
+    ap.add_argument("--scenes", type=int, default=8, help="distinct ray-cast scenes (tiled to --pairs)")
+    ap.add_argument("--cpu-sample", type=int, default=512, help="pairs in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,7 @@ SYMBOLS = [
     "dsdtm_frames_build_pyramid", "dsdtm_frame_download_level", "dsdtm_fast_cells", "dsdtm_fast_cells_batch",
     "dsdtm_fast_score_map", "dsdtm_grid_dims", "dsdtm_sparse_align", "dsdtm_sparse_align_batch",
     "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
-    "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms",
+    "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop",
 ]
 
 
@@ -71,6 +71,9 @@ def load():
     L.dsdtm_launch_count.argtypes = [C.c_void_p]
     L.dsdtm_last_run_ms.restype = C.c_float
     L.dsdtm_last_run_ms.argtypes = [C.c_void_p]
+    L.dsdtm_timer_stop.restype = C.c_float
+    L.dsdtm_timer_stop.argtypes = [C.c_void_p]
+    L.dsdtm_timer_start.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -253,6 +256,15 @@ class Context:
         conv = np.empty((n, ppp), np.uint8) if ppp else None
         self._ck(self.L.dsdtm_batch_fetch(self.hp, _p(poses), _p(nt), _p(px), _p(conv)))
         return poses, nt, px, conv
+
+    def timer_start(self):
+        self._ck(self.L.dsdtm_timer_start(self.hp))
+
+    def timer_stop(self):
+        ms = float(self.L.dsdtm_timer_stop(self.hp))
+        if ms < 0:
+            self._ck(-2)
+        return ms
 
     def last_run_ms(self):
         return float(self.L.dsdtm_last_run_ms(self.hp))

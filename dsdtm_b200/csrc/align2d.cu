@@ -26,7 +26,8 @@ struct A2dArgs {
     const int* patch_slot;      // frame slot per patch
     const int* patch_level;     // < 0 = unused entry
     const uint8_t* patch10;     // n x 100
-    double* px;                 // n x 2 (in/out, level coordinates)
+    const double* px_in;        // n x 2 start positions (level coordinates)
+    double* px;                 // n x 2 refined positions
     uint8_t* conv;              // n
     int n, max_iters, patch0;
 };
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(A2D_WARPS * 32) align2d_kernel(const A2dArgs a
     const int i = a.patch0 + blockIdx.x * A2D_WARPS + warp;
     if (i >= a.patch0 + a.n) return;
     const int L = a.patch_level[i];
-    if (L < 0) { if (lane == 0) a.conv[i] = 0; return; }
+    if (L < 0) { if (lane == 0) { a.conv[i] = 0; a.px[2 * i] = a.px_in[2 * i]; a.px[2 * i + 1] = a.px_in[2 * i + 1]; } return; }
 
     // stage the 10x10 bordered patch (100 bytes = 25 words; patch10 rows are 4-byte aligned because 100 % 4 == 0)
     if (lane < 25) reinterpret_cast<uint32_t*>(s_patch[warp])[lane] = __ldg(reinterpret_cast<const uint32_t*>(a.patch10 + (size_t)i * 100) + lane);
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(A2D_WARPS * 32) align2d_kernel(const A2dArgs a
     const uint8_t* __restrict__ img = a.frames + (size_t)a.patch_slot[i] * a.frame_stride + a.geo.off[L];
     const unsigned img_bytes = (unsigned)cols * (unsigned)rows;
 
-    float u = (float)a.px[2 * i], v = (float)a.px[2 * i + 1];      // ref: :349-350
+    float u = (float)a.px_in[2 * i], v = (float)a.px_in[2 * i + 1];      // ref: :349-350
     float mean_diff = 0.f;
     const float min_update_squared = (float)(0.03 * 0.03);          // ref: :352
     bool converged = false;
@@ -192,7 +193,7 @@ cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStrea
     A2dArgs a;
     a.frames = c->frames_d; a.frame_stride = c->geo.frame_stride; a.geo = c->geo;
     a.patch_slot = c->patch_slot_d; a.patch_level = c->patch_level_d; a.patch10 = c->patches_d;
-    a.px = c->patch_px_d; a.conv = c->patch_conv_d; a.n = n_patches; a.max_iters = max_iters; a.patch0 = patch0;
+    a.px_in = c->patch_px_in_d; a.px = c->patch_px_d; a.conv = c->patch_conv_d; a.n = n_patches; a.max_iters = max_iters; a.patch0 = patch0;
     align2d_kernel<<<(n_patches + A2D_WARPS - 1) / A2D_WARPS, A2D_WARPS * 32, 0, s>>>(a);
     c->launches++;
     return cudaGetLastError();

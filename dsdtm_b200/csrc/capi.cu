@@ -142,6 +142,8 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
     CK(cudaStreamCreateWithFlags(&c->copy_stream[1], cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev_a));
     CK(cudaEventCreate(&c->ev_b));
+    CK(cudaEventCreate(&c->ev_t0));
+    CK(cudaEventCreate(&c->ev_t1));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { CK(cudaEventCreate(&c->timer.ev0[i])); CK(cudaEventCreate(&c->timer.ev1[i])); }
 
@@ -154,7 +156,7 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
         dalloc(c, &c->feats_d, B * F) || dalloc(c, &c->n_feats_d, B) || dalloc(c, &c->centers_d, B * 3) ||
         dalloc(c, &c->poses_in_d, B * 7) || dalloc(c, &c->poses_out_d, B * 7) || dalloc(c, &c->n_tracked_d, B) ||
         dalloc(c, &c->log_d, B * kLogCap) || dalloc(c, &c->n_log_d, B) || dalloc(c, &c->patches_d, B * P * 100) ||
-        dalloc(c, &c->patch_px_d, B * P * 2) || dalloc(c, &c->patch_level_d, B * P) || dalloc(c, &c->patch_slot_d, B * P) ||
+        dalloc(c, &c->patch_px_d, B * P * 2) || dalloc(c, &c->patch_px_in_d, B * P * 2) || dalloc(c, &c->patch_level_d, B * P) || dalloc(c, &c->patch_slot_d, B * P) ||
         dalloc(c, &c->patch_conv_d, B * P) || dalloc(c, &c->wa_A_d, B * P * 4) || dalloc(c, &c->wa_px_d, B * P * 2) ||
         dalloc(c, &c->wa_meta_d, B * P * 3))
         return bail("device buffers");
@@ -179,13 +181,15 @@ void dsdtm_destroy(dsdtm_ctx* c)
     for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) cudaGraphExecDestroy(c->batch.graph[k]);
     void* bufs[] = { c->frames_d, c->cells_d, c->occupied_d, c->scoremap_d, c->fast_tiles_d, c->ref_slots_d, c->cur_slots_d,
                      c->feats_d, c->n_feats_d, c->centers_d, c->poses_in_d, c->poses_out_d, c->n_tracked_d, c->log_d, c->n_log_d,
-                     c->patches_d, c->patch_px_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d };
+                     c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { if (c->timer.ev0[i]) cudaEventDestroy(c->timer.ev0[i]); if (c->timer.ev1[i]) cudaEventDestroy(c->timer.ev1[i]); }
     for (int i = 0; i < 4; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     for (int i = 0; i < 2; ++i) if (c->copy_stream[i]) cudaStreamDestroy(c->copy_stream[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -435,7 +439,7 @@ int dsdtm_align2d_batch(dsdtm_ctx* c, int cur_slot, const int* level, const uint
     DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_slot_d, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
     DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_level_d, level, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
     DSDTM_CUDA(c, cudaMemcpyAsync(c->patches_d, patch10, (size_t)n * 100, cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_px_d, px_io, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_px_in_d, px_io, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     stage_begin(c, DSDTM_STAGE_ALIGN2D);
     DSDTM_CUDA(c, launch_align2d(c, n, max_iters, s));
     stage_end(c, 1);
@@ -480,7 +484,7 @@ static int stage_patches(dsdtm_ctx* c, int n_pairs, const int* cur_slots, const 
     if (ppp <= 0) return 0;
     const size_t n = (size_t)n_pairs * ppp, o = (size_t)pair0 * ppp;
     DSDTM_CUDA(c, cudaMemcpyAsync(c->patches_d + o * 100, patches10 + o * 100, n * 100, cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_px_d + o * 2, patch_px + o * 2, n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_px_in_d + o * 2, patch_px + o * 2, n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_level_d + o, patch_level + o, n * sizeof(int), cudaMemcpyHostToDevice, s));
     return 0;
 }
@@ -589,6 +593,25 @@ int dsdtm_batch_fetch(dsdtm_ctx* c, double* poses_out, int* n_tracked, double* p
 }
 
 float dsdtm_last_run_ms(const dsdtm_ctx* c) { return c ? c->last_run_ms : 0.f; }
+
+int dsdtm_timer_start(dsdtm_ctx* c)
+{
+    if (!c) return DSDTM_E_ARG;
+    DSDTM_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    return 0;
+}
+
+float dsdtm_timer_stop(dsdtm_ctx* c)
+{
+    if (!c) return -1.f;
+    float ms = -1.f;
+    if (cudaEventRecord(c->ev_t1, c->stream) != cudaSuccess || cudaEventSynchronize(c->ev_t1) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1) != cudaSuccess) {
+        fail(c, DSDTM_E_CUDA, "dsdtm_timer_stop", cudaGetLastError());
+        return -1.f;
+    }
+    return ms;
+}
 
 int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots, const int* cur_slots,
                          const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats, const double* ref_centers,

@@ -45,7 +45,7 @@ struct dsdtm_ctx {
     int grid_rows = 0, grid_cols = 0, n_cells = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = { nullptr, nullptr };
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_chunk[4] = { nullptr, nullptr, nullptr, nullptr };
     std::string err;
     long long launches = 0;
@@ -73,7 +73,8 @@ struct dsdtm_ctx {
     dsdtm_iter_log* log_d = nullptr;             // max_batch * kLogCap
     int* n_log_d = nullptr;
     uint8_t* patches_d = nullptr;                // max_batch * max_patches * 100
-    double* patch_px_d = nullptr;                // max_batch * max_patches * 2 (in/out)
+    double* patch_px_in_d = nullptr;             // max_batch * max_patches * 2 (start positions, never written by kernels)
+    double* patch_px_d = nullptr;                // max_batch * max_patches * 2 (refined positions)
     int* patch_level_d = nullptr;
     int* patch_slot_d = nullptr;
     uint8_t* patch_conv_d = nullptr;

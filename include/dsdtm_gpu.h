@@ -180,6 +180,10 @@ int dsdtm_pair_batch_e2e(dsdtm_ctx* ctx, int n_pairs, const uint8_t* cur_imgs, c
                          double* patch_px_out, uint8_t* patch_conv);
 /* device time of the last dsdtm_batch_run / e2e call measured with CUDA events on the context's stream [ms] */
 float dsdtm_last_run_ms(const dsdtm_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of this context is launched on):
+ * start records an event; stop records a second one, synchronises the stream and returns the elapsed ms (< 0 on error). */
+int   dsdtm_timer_start(dsdtm_ctx* ctx);
+float dsdtm_timer_stop(dsdtm_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,217 @@
+"""GPU parity (tolerances of BASELINE.json north_star): kernel (c) sparse alignment, kernel (d) Align2D, WarpAffine."""
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle as O
+from dsdtm_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-5        # rad and m (north_star)
+CHI2_RTOL = 1e-4       # per-iteration chi2, relative (north_star)
+PX_TOL = 1e-3          # refined feature position, px (north_star)
+
+
+def _upload(ctx, sc, ref_slot=0, cur_slot=1):
+    ctx.upload(ref_slot, sc["ref_img"])
+    ctx.upload(cur_slot, sc["cur_img"])
+
+
+def _compare_traces(lo, lg):
+    """Iteration traces agree within tolerance; a +-1 iteration difference is tolerated only at stagnation (chi2 equal to
+    ~1e-13), which did not occur on any seed so far -- so we assert equality of the structure."""
+    assert len(lo) == len(lg)
+    for a, b in zip(lo, lg):
+        assert (a["level"], a["iter"], a["n_pts"], a["flags"]) == (b["level"], b["iter"], b["n_pts"], b["flags"])
+        assert abs(a["chi2"] - b["chi2"]) <= CHI2_RTOL * abs(a["chi2"])
+        assert np.allclose(a["x"], b["x"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("cfg", [(4, 0, 30), (5, 0, 8), (5, 2, 8), (3, 1, 4)])
+def test_sparse_align_matches_oracle(ctx, scenario, cfg):
+    """configs[0]: one synthetic 640x480 pair, kinect intrinsics; ctor (4,0,30) of Test/test_SpraseImg_alignment.cpp:110 and
+    the production (5,0,8) of src/Tracking.cpp:37."""
+    _upload(ctx, scenario)
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    ml, mn, it = cfg
+    po, no, lo = O.sparse_align(H.ocam(scenario["cam"]), packed, scenario["cur_pyr"][0], offs, ws, hs, scenario["feats"],
+                                scenario["ref_center"], S.IDENTITY, ml, mn, it)
+    pg, ng, lg = ctx.sparse_align(0, 1, scenario["feats"], scenario["ref_center"], S.IDENTITY, ml, mn, it)
+    d = S.pose_dist(po, pg)
+    assert d[0] < POSE_TOL and d[1] < POSE_TOL and no == ng
+    _compare_traces(lo, lg)
+    if cfg[:2] == (4, 0) or cfg[:2] == (5, 0):
+        e = S.pose_dist(pg, scenario["T_c2r"])
+        assert e[0] < 2e-4 and e[1] < 5e-4          # converged to the ground-truth motion
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sparse_align_other_seeds_and_nonidentity_ref(ctx, seed):
+    sc = H.make_scenario(seed, trans=0.03, rot_deg=0.8)
+    _upload(ctx, sc, 2, 3)
+    packed, offs, ws, hs = sc["ref_pyr"]
+    start = S.pose_from_xi(np.random.default_rng(seed).uniform(-0.002, 0.002, 6))     # not exactly identity
+    po, no, lo = O.sparse_align(H.ocam(sc["cam"]), packed, sc["cur_pyr"][0], offs, ws, hs, sc["feats"], sc["ref_center"], start, 5, 0, 8)
+    pg, ng, lg = ctx.sparse_align(2, 3, sc["feats"], sc["ref_center"], start, 5, 0, 8)
+    d = S.pose_dist(po, pg)
+    assert d[0] < POSE_TOL and d[1] < POSE_TOL and no == ng
+    _compare_traces(lo, lg)
+
+
+def test_sparse_align_skips_uninitialised_zero_and_border_features(ctx, scenario):
+    """ref: src/Sprase_ImageAlign.cpp:86,95-100 -- mbInitial false, P_w == 0 and features within 3 px of the level border."""
+    _upload(ctx, scenario)
+    F = scenario["feats"].copy()
+    F["initial"][::7] = 0
+    F["point_w"][3::11] = 0.0
+    F["px"][5] = (2.0, 100.0); F["px"][6] = (638.0, 100.0); F["px"][8] = (100.0, 477.5)
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    po, no, lo = O.sparse_align(H.ocam(scenario["cam"]), packed, scenario["cur_pyr"][0], offs, ws, hs, F, scenario["ref_center"], S.IDENTITY, 4, 0, 30)
+    pg, ng, lg = ctx.sparse_align(0, 1, F, scenario["ref_center"], S.IDENTITY, 4, 0, 30)
+    d = S.pose_dist(po, pg)
+    assert d[0] < POSE_TOL and d[1] < POSE_TOL and no == ng and no < 270
+    _compare_traces(lo, lg)
+
+
+def test_sparse_align_nothing_visible_nan_chi2(ctx, scenario):
+    """Q2: chi2/tResNum is NaN when no feature is visible; the pose is left unchanged."""
+    _upload(ctx, scenario)
+    far = S.pose_from_xi([50.0, 0, 0, 0, 0, 0])
+    pg, ng, lg = ctx.sparse_align(0, 1, scenario["feats"], scenario["ref_center"], far, 2, 0, 5)
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    po, no, lo = O.sparse_align(H.ocam(scenario["cam"]), packed, scenario["cur_pyr"][0], offs, ws, hs, scenario["feats"], scenario["ref_center"], far, 2, 0, 5)
+    assert ng == 0 == no and np.isnan(lg[0]["chi2"]) and np.allclose(pg, far) and len(lg) == len(lo)
+    assert [int(e["flags"]) for e in lg] == [int(e["flags"]) for e in lo]
+
+
+def test_sparse_align_batch_equals_single_and_is_deterministic(ctx):
+    scs = [H.make_scenario(s) for s in (11, 12, 13, 14)]
+    n = len(scs)
+    for i, sc in enumerate(scs):
+        ctx.upload(2 * i, sc["ref_img"]); ctx.upload(2 * i + 1, sc["cur_img"])
+    stride = 320
+    feats = np.zeros((n, stride), O.REF_FEAT_DT)
+    nf = np.zeros(n, np.int32)
+    for i, sc in enumerate(scs):
+        nf[i] = len(sc["feats"]); feats[i, :nf[i]] = sc["feats"]
+    centers = np.stack([sc["ref_center"] for sc in scs]); poses = np.tile(S.IDENTITY, (n, 1))
+    ref_slots = np.arange(0, 2 * n, 2); cur_slots = ref_slots + 1
+    p1, t1, log, nlog = ctx.sparse_align_batch(ref_slots, cur_slots, feats, nf, centers, poses, 5, 0, 8, log_cap=64)
+    p2, t2, _, _ = ctx.sparse_align_batch(ref_slots, cur_slots, feats, nf, centers, poses, 5, 0, 8)
+    assert (p1 == p2).all() and (t1 == t2).all()                     # bitwise run-to-run determinism
+    for i, sc in enumerate(scs):
+        packed, offs, ws, hs = sc["ref_pyr"]
+        po, no, lo = O.sparse_align(H.ocam(sc["cam"]), packed, sc["cur_pyr"][0], offs, ws, hs, sc["feats"], sc["ref_center"], S.IDENTITY, 5, 0, 8)
+        d = S.pose_dist(po, p1[i])
+        assert d[0] < POSE_TOL and d[1] < POSE_TOL and no == t1[i]
+        _compare_traces(lo, log[i][:nlog[i]])
+        ps, ns, _ = ctx.sparse_align(2 * i, 2 * i + 1, sc["feats"], sc["ref_center"], S.IDENTITY, 5, 0, 8)
+        assert (ps == p1[i]).all() and ns == t1[i]
+
+
+@pytest.mark.parametrize("iters", [3, 10])
+def test_align2d_300_patches(ctx, scenario, iters):
+    """configs[1]: 300 synthetic 8x8 patches, 2-D LK refinement vs the reference; MaxIters 3 (test) and 10 (production)."""
+    _upload(ctx, scenario)
+    packed, offs, ws, hs = scenario["cur_pyr"]
+    levels, patches, truth, start = H.make_patches(scenario["cur_pyr"], 300, 21, max_level=2)
+    px, conv = ctx.align2d(1, levels, patches, start, iters)
+    n_flag_diff = 0
+    for i in range(300):
+        p, c, _ = O.align2d(O.pyr_level(packed, offs, ws, hs, int(levels[i])), patches[i], iters, start[i])
+        assert np.abs(p - px[i]).max() <= PX_TOL
+        n_flag_diff += int(c != conv[i])
+    assert n_flag_diff == 0          # may differ only when |d|^2 straddles 9e-4 within fp32 rounding; not on this data
+    if iters == 10:
+        err = np.linalg.norm(px - truth, axis=1)[conv]
+        assert conv.sum() >= 290 and np.median(err) < 0.05
+
+
+def test_align2d_border_nan_and_q4_semantics(ctx, scenario):
+    """u_r == cols-4 / v_r == rows-4 iterate (Q4) with linear addressing + zero past the end; NaN and out-of-range break."""
+    _upload(ctx, scenario)
+    packed, offs, ws, hs = scenario["cur_pyr"]
+    rng = np.random.default_rng(4)
+    starts = np.array([[636.3, 200.2], [300.5, 476.4], [636.0, 476.0], [3.9, 100.0], [100.0, 3.2], [637.2, 50.0], [50.0, 477.1],
+                       [np.nan, 100.0], [1e9, 5.0], [4.0, 4.0], [-5.0, 30.0]])
+    n = len(starts)
+    patches = rng.integers(0, 256, (n, 100), dtype=np.uint8)
+    levels = np.zeros(n, np.int32)
+    px, conv = ctx.align2d(1, levels, patches, starts, 10)
+    img = O.pyr_level(packed, offs, ws, hs, 0)
+    for i in range(n):
+        p, c, _ = O.align2d(img, patches[i], 10, starts[i])
+        assert c == conv[i], i
+        assert np.allclose(p, px[i], atol=PX_TOL, equal_nan=True), (i, p, px[i])
+
+
+def test_align2d_unused_entries_and_level_checks(ctx, scenario):
+    from dsdtm_b200 import capi
+    _upload(ctx, scenario)
+    levels, patches, truth, start = H.make_patches(scenario["cur_pyr"], 8, 2)
+    levels[3] = -1
+    px, conv = ctx.align2d(1, levels, patches, start, 10)
+    assert not conv[3] and (px[3] == start[3]).all()
+    levels[3] = 9
+    with pytest.raises(capi.DsdtmError):
+        ctx.align2d(1, levels, patches, start, 10)
+
+
+def test_warp_affine_bit_exact(ctx, scenario):
+    ctx.upload(0, scenario["ref_img"])
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    rng = np.random.default_rng(3)
+    n = 300
+    A = np.tile(np.eye(2), (n, 1, 1)) + rng.uniform(-0.3, 0.3, (n, 2, 2))
+    A[:20] *= rng.uniform(1.5, 3.0, (20, 1, 1))
+    rl = rng.integers(0, 4, n).astype(np.int32)
+    sl = rng.integers(0, 3, n).astype(np.int32); sl[: n // 2] = 0
+    rpx = np.stack([rng.uniform(1, 639, n), rng.uniform(1, 479, n)], 1).astype(np.float32)
+    rpx[:6] = [[0.2, 0.3], [639, 479], [638.9, 100], [320, 478.99], [3, 3], [639.0, 0.0]]
+    got = ctx.warp_affine(np.zeros(n, np.int32), A, rpx, rl, sl)
+    for i in range(n):
+        want = O.warp_affine(A[i], O.pyr_level(packed, offs, ws, hs, int(rl[i])), rpx[i], int(rl[i]), int(sl[i]))
+        assert (want == got[i]).all(), i
+    # Q3: search level >= 1 -> constant patches
+    assert all(len(set(got[i])) == 1 for i in range(n) if sl[i] >= 1)
+
+
+def test_staged_batch_run_graph_replay_and_e2e(ctx):
+    """dsdtm_batch_stage/run/fetch (CUDA-graph replay on HBM-resident inputs) and the host-buffer e2e call give the same
+    results as the single-pair entry points."""
+    from dsdtm_b200 import capi
+    scs = [H.make_scenario(s) for s in (31, 32)]
+    n, stride, ppp = 2, 320, 40
+    for i, sc in enumerate(scs):
+        ctx.upload(2 * i, sc["ref_img"]); ctx.upload(2 * i + 1, sc["cur_img"])
+    feats = np.zeros((n, stride), O.REF_FEAT_DT); nf = np.zeros(n, np.int32)
+    lv = np.zeros((n, ppp), np.int32); pt = np.zeros((n, ppp, 100), np.uint8); st = np.zeros((n, ppp, 2))
+    for i, sc in enumerate(scs):
+        nf[i] = len(sc["feats"]); feats[i, :nf[i]] = sc["feats"]
+        lv[i], pt[i], _, st[i] = H.make_patches(sc["cur_pyr"], ppp, 50 + i, max_level=1)
+    lv[1, 5] = -1
+    centers = np.stack([sc["ref_center"] for sc in scs]); poses = np.tile(S.IDENTITY, (n, 1))
+    ref_slots = np.array([0, 2], np.int32); cur_slots = np.array([1, 3], np.int32)
+    ctx.batch_stage(ref_slots, cur_slots, feats, nf, centers, poses, 5, 0, 8, pt, st, lv, 10)
+    for rep in range(3):                              # graph replay: same answer every time
+        ctx.batch_run(1)
+        poses_b, nt_b, px_b, conv_b = ctx.batch_fetch()
+        if rep:
+            assert (poses_b == last[0]).all() and (px_b == last[2]).all()
+        last = (poses_b, nt_b, px_b, conv_b)
+    assert ctx.last_run_ms() > 0
+    for i, sc in enumerate(scs):
+        ps, ns, _ = ctx.sparse_align(2 * i, 2 * i + 1, sc["feats"], sc["ref_center"], S.IDENTITY, 5, 0, 8)
+        assert (ps == poses_b[i]).all() and ns == nt_b[i]
+        pxs, cs = ctx.align2d(2 * i + 1, lv[i], pt[i], st[i], 10)
+        assert (pxs == px_b[i]).all() and (cs == conv_b[i].astype(bool)).all()
+    # e2e with host buffers: cur images uploaded inside the call
+    cur_imgs = np.stack([sc["cur_img"] for sc in scs])
+    out = dict(poses=np.empty((n, 7)), n_tracked=np.empty(n, np.int32), px=np.empty((n, ppp, 2)), conv=np.empty((n, ppp), np.uint8))
+    ctx.pair_batch_e2e(cur_imgs, ref_slots, cur_slots, feats, stride, nf, centers, poses, 5, 0, 8, pt, st, lv, ppp, 10, out)
+    assert (out["poses"] == poses_b).all() and (out["n_tracked"] == nt_b).all()
+    assert (out["px"] == px_b).all() and (out["conv"] == conv_b).all()
+    with pytest.raises(capi.DsdtmError):
+        ctx.sparse_align_batch(np.arange(20), np.arange(20), np.zeros((20, 4), O.REF_FEAT_DT), np.zeros(20, np.int32),
+                               np.zeros((20, 3)), np.tile(S.IDENTITY, (20, 1)), 5, 0, 8)     # > max_batch

@@ -1,0 +1,168 @@
+"""CPU suite: the oracle against the golden vectors (cv2 4.13, the reference's FAST library, the 167-corner KAT) and,
+when it was built in this container, against oracle/_ref (the reference's own FAST sources)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+
+def test_pyrdown_matches_cv2_goldens(golden):
+    g = golden["pyrdown_cv2"]
+    i = 0
+    while "in%d" % i in g:
+        assert (O.pyrdown(g["in%d" % i]) == g["out%d" % i]).all(), i
+        i += 1
+    assert i == 7
+
+
+def test_pyramid_chain_matches_cv2_on_test1(golden):
+    g = golden["test1_fast"]
+    packed, offs, ws, hs = O.pyramid(g["img"], 5)
+    assert list(ws) == [752, 376, 188, 94, 47] and list(hs) == [480, 240, 120, 60, 30]
+    for l in range(1, 5):
+        assert (O.pyr_level(packed, offs, ws, hs, l) == g["pyr%d" % l]).all(), l
+
+
+def test_fast_kat_167_corners(golden):
+    """ref: Thirdparty/fast/test/test.cpp:20,45,52 -- FAST-10 @75 on test1.png extracts 167 features."""
+    g = golden["test1_fast"]
+    xy = O.fast10_detect(g["img"], 75)
+    assert len(xy) == 167
+    assert (xy == g["xy75"]).all()
+
+
+@pytest.mark.parametrize("barrier", [75, 20])
+def test_fast_detect_score_nonmax_equal_reference_lists(golden, barrier):
+    g = golden["test1_fast"]
+    xy = O.fast10_detect(g["img"], barrier)
+    assert xy.shape == g["xy%d" % barrier].shape and (xy == g["xy%d" % barrier]).all()
+    sc = O.fast10_score(g["img"], xy)
+    assert (sc == g["score%d" % barrier]).all() and sc.min() >= barrier
+    keep = O.fast_nonmax(xy, sc)
+    assert (keep == g["keep%d" % barrier]).all()
+    if barrier == 20:
+        assert len(xy) == 3787 and len(keep) == 843      # SURVEY App. C probe 2
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (reference FAST sources) not built here")
+def test_fast_closed_form_equals_reference_library_on_adversarial_images():
+    rng = np.random.default_rng(5)
+    for t in range(24):
+        h, w = int(rng.integers(7, 70)), int(rng.integers(7, 100))
+        if t % 3 == 0:
+            im = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif t % 3 == 1:
+            im = (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)          # saturation + plateaus
+        else:
+            im = np.repeat(np.repeat(rng.integers(0, 256, (h // 3 + 1, w // 3 + 1), dtype=np.uint8), 3, 0), 3, 1)[:h, :w].copy()
+        for b in (20, 1, 100):
+            a = O.fast10_detect(im, b)
+            for sse in (True, False):
+                r = O.ref_fast10_detect(im, b, sse)
+                assert len(a) == len(r) and (a == r).all(), (h, w, b, sse)
+            if len(a):
+                s = O.fast10_score(im, a)
+                assert (s == O.ref_fast10_score(im, a, b)).all()
+                assert (O.fast_nonmax(a, s) == O.ref_fast_nonmax(a, s)).all()
+
+
+def test_circle_fill_matches_cv2_goldens(golden):
+    g = golden["circle_cv2"]
+    H, W = g["shape"]
+    for (cx, cy, r), bits in zip(g["cases"], g["masks"]):
+        m = np.full((H, W), 255, np.uint8)
+        O.circle_fill(m, cx, cy, r, 0)
+        want = np.unpackbits(bits)[:H * W].reshape(H, W).astype(bool)
+        assert ((m == 0) == want).all(), (cx, cy, r)
+
+
+def test_cvround_is_half_to_even():
+    assert [O.cvround(v) for v in (0.5, 1.5, 2.5, -0.5, -1.5, 2.4999, 2.5001)] == [0, 2, 2, 0, -2, 2, 3]
+
+
+def test_shitomasi_border_and_symmetry():
+    rng = np.random.default_rng(2)
+    im = rng.integers(0, 256, (40, 50), dtype=np.uint8)
+    assert O.shitomasi(im, 4, 20) == 0.0 and O.shitomasi(im, 45, 20) == 0.0      # x_min < 1 / x_max >= cols-1
+    assert O.shitomasi(im, 5, 5) > 0.0
+    assert O.shitomasi(np.full((40, 50), 9, np.uint8), 20, 20) == 0.0
+
+
+def test_detect_selection_respects_mask_and_limit(scenario):
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    cells = O.detect_cells(packed, offs, ws, hs, 15, None, 5.0)
+    mask = np.full((480, 640), 255, np.uint8)
+    feats, sorted_cells = O.detect_select(cells, mask, 15, 300)
+    assert len(feats) == 300 and (np.diff(sorted_cells["score"]) <= 0).all()
+    assert (feats["score"] > 20).all()
+    # every selected feature is > CellSize away (cv::circle disc) from every earlier one
+    for i in range(1, 40):
+        d2 = (feats["x"][:i] - feats["x"][i]) ** 2 + (feats["y"][:i] - feats["y"][i]) ** 2
+        assert d2.min() > 15 * 15 - 30
+    # occupied cells are skipped (ref: src/Feature_detection.cpp:100)
+    occ = np.zeros(len(cells), np.uint8); occ[::2] = 1
+    c2 = O.detect_cells(packed, offs, ws, hs, 15, occ, 5.0)
+    assert (c2["score"][::2] == np.float32(5.0)).all() and (c2[1::2] == cells[1::2]).all()
+
+
+def test_sparse_align_converges_to_ground_truth(scenario):
+    import helpers as H
+    from dsdtm_b200 import synth as S
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    for (ml, it) in ((4, 30), (5, 8)):
+        pose, n, log = O.sparse_align(H.ocam(scenario["cam"]), packed, scenario["cur_pyr"][0], offs, ws, hs, scenario["feats"],
+                                      scenario["ref_center"], S.IDENTITY, ml, 0, it)
+        e0 = S.pose_dist(S.IDENTITY, scenario["T_c2r"])
+        e1 = S.pose_dist(pose, scenario["T_c2r"])
+        assert e1[0] < 0.02 * e0[0] and e1[1] < 0.02 * e0[1] and n > 250
+        assert log[0]["level"] == ml - 1 and log[-1]["level"] == 0
+        # Q6/revert rule: a reverted iteration is always the last one of its level
+        for a, b in zip(log[:-1], log[1:]):
+            if a["flags"] & 2:
+                assert b["level"] == a["level"] - 1 and b["iter"] == 0
+
+
+def test_sparse_align_no_visible_feature_gives_nan_chi2_and_keeps_pose(scenario):
+    import helpers as H
+    from dsdtm_b200 import synth as S
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    far = S.pose_from_xi([50.0, 0, 0, 0, 0, 0])     # everything projects outside the image
+    pose, n, log = O.sparse_align(H.ocam(scenario["cam"]), packed, scenario["cur_pyr"][0], offs, ws, hs, scenario["feats"],
+                                  scenario["ref_center"], far, 2, 0, 5)
+    assert n == 0 and np.isnan(log[0]["chi2"]) and np.allclose(pose, far)
+
+
+def test_align2d_recovers_subpixel_truth(scenario):
+    """test_Feature_alignment recipe (ref: Test/test_Feature_alignment.cpp:56-81): truth (130.2,120.3), offset (1.1,0.8)."""
+    import helpers as H
+    packed, offs, ws, hs = scenario["cur_pyr"]
+    img = O.pyr_level(packed, offs, ws, hs, 0)
+    levels, patches, truth, start = H.make_patches(scenario["cur_pyr"], 50, 11, max_level=0, pert=1.2)
+    errs = []
+    for i in range(50):
+        p, conv, nit = O.align2d(img, patches[i], 10, start[i])
+        if conv:
+            errs.append(np.linalg.norm(p - truth[i]))
+    assert len(errs) >= 45 and np.median(errs) < 0.05
+
+
+def test_warp_affine_integer_division_quirk(scenario):
+    """Q3: for search level >= 1 the sampling grid collapses to the reference pixel -> constant patch."""
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    img = O.pyr_level(packed, offs, ws, hs, 0)
+    p0 = O.warp_affine(np.eye(2), img, (100.0, 90.0), 0, 0)
+    assert (p0.reshape(10, 10) == img[85:95, 95:105]).all()          # identity warp, integer position: x,y in [-5,4]
+    p1 = O.warp_affine(np.eye(2) * 2.0, img, (100.0, 90.0), 0, 1)
+    assert (p1 == img[90, 100]).all()
+
+
+def test_se3_group_axioms():
+    from dsdtm_b200 import synth as S
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        x = rng.uniform(-0.3, 0.3, 6)
+        a = O.se3_exp(x)
+        assert np.allclose(a, S.pose_from_xi(x), atol=1e-12)
+        assert np.allclose(O.se3_mul(a, O.se3_inv(a)), S.IDENTITY, atol=1e-12)
+        p = rng.uniform(-1, 1, 3)
+        assert np.allclose(O.se3_act(a, p), S.pose_act(a, p), atol=1e-12)
