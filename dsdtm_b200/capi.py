@@ -41,7 +41,7 @@ SYMBOLS = [
     "dsdtm_frames_build_pyramid", "dsdtm_frame_download_level", "dsdtm_fast_cells", "dsdtm_fast_cells_batch",
     "dsdtm_fast_score_map", "dsdtm_grid_dims", "dsdtm_sparse_align", "dsdtm_sparse_align_batch",
     "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
-    "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop",
+    "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option",
 ]
 
 
@@ -144,6 +144,9 @@ class Context:
 
     def launch_count(self):
         return int(self.L.dsdtm_launch_count(self.hp))
+
+    def set_option(self, key, value):
+        self._ck(self.L.dsdtm_set_option(self.hp, key.encode(), int(value)))
 
     def profile(self, on):
         self._ck(self.L.dsdtm_profile(self.hp, int(on)))

@@ -52,6 +52,7 @@ struct dsdtm_ctx {
     bool profiling = false;
     dsdtm::StageTimer timer;
     float last_run_ms = 0.f;
+    int sa_wpp_override = 0;                     // 0 = pick warps-per-pair from the batch size
 
     // device memory
     uint8_t* frames_d = nullptr;                 // frame pool

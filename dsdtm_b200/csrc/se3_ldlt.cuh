@@ -1,0 +1,183 @@
+// se3_ldlt.cuh -- the serial tail of one Gauss-Newton iteration: 6x6 pivoted LDL^T solve (Eigen's ldlt() semantics)
+// and T <- T * SE3::exp(x) (Sophus non-templated semantics). Written so that EVERY array index is a compile-time
+// constant after unrolling: the whole state lives in registers (round-1 profile: the first version kept A[36] in local
+// memory and this section was 70 % of the kernel, profiles/r1_sparse_align_v1.md).
+// __host__ __device__ so that the CPU suite can check it against the oracle without a GPU.
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define DSDTM_HD __host__ __device__ __forceinline__
+#else
+#define DSDTM_HD inline
+#endif
+
+namespace dsdtm {
+
+template <class T>
+DSDTM_HD void cswap(bool p, T& a, T& b)
+{
+    const T ta = p ? b : a;
+    const T tb = p ? a : b;
+    a = ta; b = tb;
+}
+
+// H: full symmetric 6x6 (row-major, both triangles filled). Pivoted LDL^T (largest remaining |diagonal|, first wins),
+// then x = P^T L^-T D^+ L^-1 P b with Eigen's rule "pivot <= 1/highest -> component 0".
+DSDTM_HD void ldlt6_solve_reg(const double (&Hin)[6][6], const double (&bin)[6], double (&x)[6])
+{
+    double A[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) A[i][j] = Hin[i][j];
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = bin[i];
+    int tr[6] = { 0, 1, 2, 3, 4, 5 };
+    bool zero_matrix = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        if (zero_matrix) continue;      // Eigen: an all-zero matrix stops the factorisation at k == 0 with identity transpositions
+        // pivot search over the remaining diagonal (first maximum wins)
+        int big = k;
+        double bigv = fabs(A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const double v = fabs(A[i][i]);
+            const bool g = v > bigv;
+            bigv = g ? v : bigv;
+            big = g ? i : big;
+        }
+        tr[k] = big;
+        // symmetric swap of rows/cols k and big in the lower triangle, written as predicated swaps over every candidate
+        // so that all register-array indices stay compile-time constants
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const bool p = (big == i);
+#pragma unroll
+            for (int j = 0; j < k; ++j) cswap(p, A[k][j], A[i][j]);        // rows k / big, columns left of k
+#pragma unroll
+            for (int r = i + 1; r < 6; ++r) cswap(p, A[r][k], A[r][i]);    // columns k / big, rows below big
+            cswap(p, A[k][k], A[i][i]);
+#pragma unroll
+            for (int r = k + 1; r < i; ++r) cswap(p, A[r][k], A[i][r]);    // the "elbow" between k and big
+        }
+        if (k > 0) {
+            double temp[6];
+#pragma unroll
+            for (int j = 0; j < k; ++j) temp[j] = A[j][j] * A[k][j];
+            double s = 0;
+#pragma unroll
+            for (int j = 0; j < k; ++j) s += A[k][j] * temp[j];
+            A[k][k] -= s;
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) {
+                double s2 = 0;
+#pragma unroll
+                for (int j = 0; j < k; ++j) s2 += A[i][j] * temp[j];
+                A[i][k] -= s2;
+            }
+        }
+        const double akk = A[k][k];
+        const bool valid = fabs(akk) > 0.0;
+        if (k == 0 && !valid) {
+            zero_matrix = true;
+            tr[0] = 0;
+        } else if (k < 5 && valid) {
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) A[i][k] = A[i][k] / akk;
+        }
+    }
+    // P b
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) cswap(tr[k] == i, y[k], y[i]);
+    // L^-1
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+    const double tol = 1.0 / 1.7976931348623157e308;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = (fabs(A[i][i]) > tol) ? y[i] / A[i][i] : 0.0;
+    // L^-T
+#pragma unroll
+    for (int i = 5; i >= 0; --i)
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
+    // P^T
+#pragma unroll
+    for (int k = 5; k >= 0; --k)
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) cswap(tr[k] == i, y[k], y[i]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
+}
+
+struct Quat { double w, x, y, z; };
+
+// out = T * exp(x); pose7 = {qw,qx,qy,qz,tx,ty,tz}. (ref: src/Sprase_ImageAlign.cpp:335; Sophus SE3::exp, SE3::operator*=)
+DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&out)[7])
+{
+    const double SMALL_EPS = 1e-10;
+    const double u0 = x[0], u1 = x[1], u2 = x[2], o0 = x[3], o1 = x[4], o2 = x[5];
+    const double theta = sqrt(o0 * o0 + o1 * o1 + o2 * o2);
+    const double half = 0.5 * theta;
+    double imag;
+    const double real = cos(half);
+    if (theta < SMALL_EPS) {
+        const double t2 = theta * theta, t4 = t2 * t2;
+        imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
+    } else {
+        imag = sin(half) / theta;
+    }
+    double ew = real, ex = imag * o0, ey = imag * o1, ez = imag * o2;
+    {
+        const double n = sqrt(ex * ex + ey * ey + ez * ez + ew * ew);
+        ex /= n; ey /= n; ez /= n; ew /= n;
+    }
+    // V = I + a*Omega + b*Omega^2 (or R(e) for tiny theta);  et = V * upsilon
+    double et0, et1, et2;
+    if (theta < SMALL_EPS) {
+        const double tx = 2 * ex, ty = 2 * ey, tz = 2 * ez;
+        const double twx = tx * ew, twy = ty * ew, twz = tz * ew;
+        const double txx = tx * ex, txy = ty * ex, txz = tz * ex;
+        const double tyy = ty * ey, tyz = tz * ey, tzz = tz * ez;
+        et0 = (1 - (tyy + tzz)) * u0 + (txy - twz) * u1 + (txz + twy) * u2;
+        et1 = (txy + twz) * u0 + (1 - (txx + tzz)) * u1 + (tyz - twx) * u2;
+        et2 = (txz - twy) * u0 + (tyz + twx) * u1 + (1 - (txx + tyy)) * u2;
+    } else {
+        const double t2 = theta * theta;
+        const double a = (1 - cos(theta)) / t2;
+        const double b = (theta - sin(theta)) / (t2 * theta);
+        // Omega = [0 -o2 o1; o2 0 -o0; -o1 o0 0]; Omega^2 entries
+        const double O2_00 = -o2 * o2 - o1 * o1, O2_01 = o1 * o0, O2_02 = o2 * o0;
+        const double O2_10 = o0 * o1, O2_11 = -o2 * o2 - o0 * o0, O2_12 = o2 * o1;
+        const double O2_20 = o0 * o2, O2_21 = o1 * o2, O2_22 = -o1 * o1 - o0 * o0;
+        const double V00 = 1.0 + b * O2_00, V01 = a * -o2 + b * O2_01, V02 = a * o1 + b * O2_02;
+        const double V10 = a * o2 + b * O2_10, V11 = 1.0 + b * O2_11, V12 = a * -o0 + b * O2_12;
+        const double V20 = a * -o1 + b * O2_20, V21 = a * o0 + b * O2_21, V22 = 1.0 + b * O2_22;
+        et0 = V00 * u0 + V01 * u1 + V02 * u2;
+        et1 = V10 * u0 + V11 * u1 + V12 * u2;
+        et2 = V20 * u0 + V21 * u1 + V22 * u2;
+    }
+    // T * E : t = t_T + R(q_T) et ; q = normalize(q_T * q_E)
+    const double aw = T[0], ax = T[1], ay = T[2], az = T[3];
+    double uv0 = ay * et2 - az * et1, uv1 = az * et0 - ax * et2, uv2 = ax * et1 - ay * et0;
+    uv0 += uv0; uv1 += uv1; uv2 += uv2;
+    const double c0 = ay * uv2 - az * uv1, c1 = az * uv0 - ax * uv2, c2 = ax * uv1 - ay * uv0;
+    const double rw = aw * ew - ax * ex - ay * ey - az * ez;
+    const double rx = aw * ex + ax * ew + ay * ez - az * ey;
+    const double ry = aw * ey + ay * ew + az * ex - ax * ez;
+    const double rz = aw * ez + az * ew + ax * ey - ay * ex;
+    const double n = sqrt(rx * rx + ry * ry + rz * rz + rw * rw);
+    out[0] = rw / n; out[1] = rx / n; out[2] = ry / n; out[3] = rz / n;
+    out[4] = T[4] + (et0 + aw * uv0 + c0);
+    out[5] = T[5] + (et1 + aw * uv1 + c1);
+    out[6] = T[6] + (et2 + aw * uv2 + c2);
+}
+
+}  // namespace dsdtm

@@ -255,6 +255,12 @@ def align2d(cur_img, patch10, max_iters, px):
 
 
 # ---------------------------------------------------------------- SE3
+def ldlt6_solve(H, b):
+    x = np.empty(6)
+    lib().orc_ldlt6_solve(_p(np.ascontiguousarray(H, np.float64).reshape(-1)), _p(np.ascontiguousarray(b, np.float64)), _p(x))
+    return x
+
+
 def se3_exp(x):
     out = np.empty(7); lib().orc_se3_exp(_p(np.ascontiguousarray(x, np.float64)), _p(out)); return out
 

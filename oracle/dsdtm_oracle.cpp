@@ -443,6 +443,7 @@ void orc_feature_normal(const orc_cam* cam, const float px[2], double normal[3])
     normal[0] = n[0] / nn; normal[1] = n[1] / nn; normal[2] = n[2] / nn;
 }
 
+void orc_ldlt6_solve(const double H[36], const double b[6], double x[6]) { ldlt6_solve(H, b, x); }
 void orc_se3_exp(const double x[6], double pose[7]) { se3_to(se3_exp(x), pose); }
 void orc_se3_mul(const double a[7], const double b[7], double out[7]) { se3_to(se3_mul(se3_from(a), se3_from(b)), out); }
 void orc_se3_inv(const double a[7], double out[7]) { se3_to(se3_inv(se3_from(a)), out); }

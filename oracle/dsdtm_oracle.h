@@ -108,6 +108,8 @@ void orc_patch_no_border(const uint8_t patch10[100], uint8_t patch8[64]);
 int orc_align2d(const uint8_t* cur_img, int w, int h, int stride, const uint8_t patch10[100],
                 const uint8_t patch8[64], int max_iters, double px[2], int* n_iters_out);
 
+/* Eigen LDLT<Matrix6d>::solve restatement (App. B.4); H row-major 6x6 (lower triangle read) */
+void orc_ldlt6_solve(const double H[36], const double b[6], double x[6]);
 /* ---- SE3 helpers (Sophus non-templated semantics, App. B.3) ---- */
 void orc_se3_exp(const double x[6], double pose[7]);
 void orc_se3_mul(const double a[7], const double b[7], double out[7]);

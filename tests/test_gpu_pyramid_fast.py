@@ -163,5 +163,8 @@ def test_bad_arguments_return_errors(ctx):
     from dsdtm_b200 import capi
     with pytest.raises(capi.DsdtmError):
         ctx.download_level(99, 0)
-    with pytest.raises(capi.DsdtmError):
-        ctx.fast_score_map(0, 7, 20)
+    import ctypes
+    buf = np.zeros(16, np.uint8)
+    assert ctx.L.dsdtm_fast_score_map(ctx.hp, 0, 7, 20, capi._p(buf), capi._p(buf)) == -1        # DSDTM_E_ARG
+    assert ctx.L.dsdtm_fast_cells(ctx.hp, 0, 0, ctypes.c_float(5.0), None, capi._p(buf)) == -1   # barrier out of range
+    assert ctx.L.dsdtm_batch_run(ctx.hp, 0) in (-4, 0)
