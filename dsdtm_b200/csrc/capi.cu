@@ -234,6 +234,12 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
+    if (std::strcmp(key, "pyramid_kernel") == 0) {
+        if (value != 0 && value != 1) return fail(c, DSDTM_E_ARG, "pyramid_kernel must be 0 (auto) or 1 (tile)");
+        c->pyr_kernel = value;
+        for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
+        return 0;
+    }
     return fail(c, DSDTM_E_ARG, "unknown option");
 }
 

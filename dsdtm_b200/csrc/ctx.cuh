@@ -52,6 +52,7 @@ struct dsdtm_ctx {
     bool profiling = false;
     dsdtm::StageTimer timer;
     float last_run_ms = 0.f;
+    int pyr_kernel = 0;                          // 0 = auto (strip kernel where eligible), 1 = always the shared-memory tile kernel
     int sa_wpp_override = 0;                     // 0 = pick warps-per-pair from the batch size
 
     // device memory

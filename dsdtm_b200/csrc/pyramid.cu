@@ -4,12 +4,17 @@
 // arguments: dst(y,x) = (sum_{i,j in [-2,2]} k_i k_j src(R(2y+i), R(2x+j)) + 128) >> 8, k = [1 4 6 4 1],
 // R = BORDER_REFLECT_101, dst size ((w+1)/2, (h+1)/2). Integer arithmetic => bit-exact in any evaluation order.
 //
-// One launch per level over a batch of frames (grid.z = frame). A 256-thread CTA produces a 64x16 output tile:
-//   1. the (2*64+8) x (2*16+3) source window is staged in shared memory with coalesced 32-bit row loads
-//      (byte loads with reflect-101 on border tiles / widths that are not a multiple of 4),
-//   2. horizontal 5-tap pass into a u16 buffer (35 x 64),
-//   3. vertical 5-tap pass, 4 outputs per thread packed into one 32-bit store.
+// One launch per level over a batch of frames. Two kernels:
+//   pyrdown_strip_kernel (levels with w % 8 == 0 and dw % 4 == 0, i.e. every level of 640x480 and the two big levels of
+//   752x480): no shared memory. A thread owns 4 adjacent output columns and walks down a strip of RPT output rows with a
+//   5-row sliding window held in registers. Per source row it issues one 8-byte and two 4-byte aligned loads (consecutive
+//   lanes read consecutive 8-byte words: fully coalesced), does the horizontal [1 4 6 4 1] pass with two PRMT + four DP4A,
+//   keeps the four 12-bit sums packed as 2 x u16 in two registers, and the vertical pass works on the packed pairs
+//   (max 16 * 4080 = 65280 < 2^16: no carry between halves). One 32-bit store per 4 outputs.
+//   pyrdown_tile_kernel (any size; odd / tiny levels): 64x16 output tile staged through shared memory with reflect-101.
 // HBM-bound stage: algorithmic bytes per frame = sum_l (w_{l-1} h_{l-1} + w_l h_l) (510 000 B @640x480x5).
+// Round-1 profile (profiles/r1_bench_first.md): the tile kernel alone ran at 600 GB/s = 9 % of HBM peak, issue-bound on
+// byte-wide shared-memory traffic -- hence the register/DP4A strip kernel.
 #include "ctx.cuh"
 
 namespace dsdtm {
@@ -30,7 +35,7 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return i;
 }
 
-__global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ frames, unsigned frame_stride, int first_slot,
+__global__ void __launch_bounds__(256) pyrdown_tile_kernel(uint8_t* __restrict__ frames, unsigned frame_stride, int first_slot,
                                                       const int* __restrict__ slots, unsigned src_off, unsigned dst_off,
                                                       int w, int h, int dw, int dh)
 {
@@ -95,13 +100,75 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ fram
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RPT = 8;   // output rows per thread strip
+
+__device__ __forceinline__ int reflect_row(int r, int h)
+{
+    r = (r < 0) ? -r : r;
+    return (r >= h) ? 2 * h - 2 - r : r;
+}
+
+// horizontal pass of one source row for output columns x..x+3 (x % 4 == 0): returns the four sums packed as 2 x (2 x u16)
+__device__ __forceinline__ uint2 hrow(const uint8_t* __restrict__ row, int x, int w)
+{
+    const int c0 = 2 * x;                                            // multiple of 8
+    const uint2 mid = __ldg(reinterpret_cast<const uint2*>(row + c0));          // cols c0 .. c0+7
+    const uint32_t w0 = mid.x, w1 = mid.y;
+    // cols c0-2, c0-1 (reflect-101 at the left edge: -2 -> 2, -1 -> 1) in bytes 2,3 of wm1
+    const uint32_t wm1 = (x > 0) ? __ldg(reinterpret_cast<const uint32_t*>(row + c0 - 4)) : __byte_perm(w0, 0, 0x1200);
+    // col c0+8 (reflect-101 at the right edge: w -> w-2 = c0+6) in byte 0 of w2
+    const uint32_t w2 = (c0 + 8 < w) ? __ldg(reinterpret_cast<const uint32_t*>(row + c0 + 8)) : (w1 >> 16);
+    const uint32_t K = 0x04060401u;                                  // taps 1,4,6,4 on bytes 0..3; the fifth tap (1) is the addend
+    const uint32_t h0 = __dp4a(__byte_perm(wm1, w0, 0x5432), K, (w0 >> 16) & 0xFFu);
+    const uint32_t h1 = __dp4a(w0, K, w1 & 0xFFu);
+    const uint32_t h2 = __dp4a(__byte_perm(w0, w1, 0x5432), K, (w1 >> 16) & 0xFFu);
+    const uint32_t h3 = __dp4a(w1, K, w2 & 0xFFu);
+    return make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+}
+
+__global__ void __launch_bounds__(128) pyrdown_strip_kernel(uint8_t* __restrict__ frames, unsigned frame_stride, int first_slot,
+                                                            const int* __restrict__ slots, unsigned src_off, unsigned dst_off,
+                                                            int w, int h, int dw, int dh, int n_items)
+{
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    const int xq = dw >> 2;                               // column groups per row
+    const int strip = item / xq, x = (item - strip * xq) << 2;
+    const int slot = slots ? slots[blockIdx.y] : first_slot + blockIdx.y;
+    const uint8_t* __restrict__ src = frames + (size_t)slot * frame_stride + src_off;
+    uint8_t* __restrict__ dst = frames + (size_t)slot * frame_stride + dst_off;
+    const int y0 = strip * RPT;
+    // window rows 2y-2 .. 2y+2
+    uint2 r0 = hrow(src + (size_t)reflect_row(2 * y0 - 2, h) * w, x, w);
+    uint2 r1 = hrow(src + (size_t)reflect_row(2 * y0 - 1, h) * w, x, w);
+    uint2 r2 = hrow(src + (size_t)(2 * y0) * w, x, w);
+#pragma unroll 2
+    for (int y = y0; y < min(y0 + RPT, dh); ++y) {
+        const uint2 r3 = hrow(src + (size_t)reflect_row(2 * y + 1, h) * w, x, w);
+        const uint2 r4 = hrow(src + (size_t)reflect_row(2 * y + 2, h) * w, x, w);
+        // vertical [1 4 6 4 1] on packed u16 pairs, then (s + 128) >> 8 per half
+        uint32_t a = r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + 0x00800080u;
+        uint32_t b = r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + 0x00800080u;
+        // bytes 1 and 3 of a / b are the four results
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * dw + x) = __byte_perm(a, b, 0x7531);
+        r0 = r2; r1 = r3; r2 = r4;
+    }
+}
+
 cudaError_t launch_levels(dsdtm_ctx* c, int first_slot, const int* slots_d, int n, cudaStream_t s)
 {
     const LevelGeom& g = c->geo;
     for (int l = 1; l < g.levels; ++l) {
-        dim3 grid((g.w[l] + TW - 1) / TW, (g.h[l] + TH - 1) / TH, n);
-        pyrdown_kernel<<<grid, 256, 0, s>>>(c->frames_d, g.frame_stride, first_slot, slots_d, g.off[l - 1], g.off[l],
-                                            g.w[l - 1], g.h[l - 1], g.w[l], g.h[l]);
+        const int w = g.w[l - 1], h = g.h[l - 1], dw = g.w[l], dh = g.h[l];
+        if ((w & 7) == 0 && (dw & 3) == 0 && h >= 3 && 2 * dw == w && c->pyr_kernel != 1) {
+            const int n_items = (dw >> 2) * ((dh + RPT - 1) / RPT);
+            dim3 grid((n_items + 127) / 128, n);
+            pyrdown_strip_kernel<<<grid, 128, 0, s>>>(c->frames_d, g.frame_stride, first_slot, slots_d, g.off[l - 1], g.off[l], w, h, dw, dh, n_items);
+        } else {
+            dim3 grid((dw + TW - 1) / TW, (dh + TH - 1) / TH, n);
+            pyrdown_tile_kernel<<<grid, 256, 0, s>>>(c->frames_d, g.frame_stride, first_slot, slots_d, g.off[l - 1], g.off[l], w, h, dw, dh);
+        }
         c->launches++;
     }
     return cudaGetLastError();

@@ -65,10 +65,20 @@ __device__ __forceinline__ void qrot(double qw, double qx, double qy, double qz,
     o2 = __dadd_rn(__dadd_rn(v2, __dmul_rn(qw, uv2)), c2);
 }
 
-// non-contracted bilinear sample: ((w0*i0 + w1*i1) + w2*i2) + w3*i3   (ref: :147-148, :281)
+// bilinear sample ((w0*i0 + w1*i1) + w2*i2) + w3*i3 in the reference's left-to-right order (ref: :147-148, :281).
+// Default: the three additions are fused (1 DMUL + 3 DFMA instead of 4 DMUL + 3 DADD: the fp64 pipe is the binding unit,
+// profiles/r1_sparse_align_v2.md); each sample then differs from the reference's FMA-free x86 value by <= 1 ulp (1e-16
+// relative), far inside the 1e-4 chi2 / 1e-5 pose tolerances. -DDSDTM_SA_STRICT=1 restores the non-contracted form.
+#ifndef DSDTM_SA_STRICT
+#define DSDTM_SA_STRICT 0
+#endif
 __device__ __forceinline__ double bil(double w0, double w1, double w2, double w3, double i0, double i1, double i2, double i3)
 {
+#if DSDTM_SA_STRICT
     return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w0, i0), __dmul_rn(w1, i1)), __dmul_rn(w2, i2)), __dmul_rn(w3, i3));
+#else
+    return fma(w3, i3, fma(w2, i2, fma(w1, i1, __dmul_rn(w0, i0))));
+#endif
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -206,6 +216,21 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                 const double su = u - uf, sv = v - vf;
                 const double tl = __dmul_rn(1.0 - su, 1.0 - sv), tr = __dmul_rn(su, 1.0 - sv);
                 const double bl = __dmul_rn(1.0 - su, sv), br = __dmul_rn(su, sv);            // ref: :267-270
+                // current-image 5x5 window rows vi-2 .. vi+2, cols ui-2 .. ui+2: all ten aligned 32-bit loads are issued here,
+                // before the reference-side arithmetic, so that their L1/L2 latency is covered by independent fp64 work
+                uint32_t cw0[5], cw1[5];
+                {
+                    const unsigned c0w = (unsigned)(vi - 2) * (unsigned)cols + (unsigned)(ui - 2);
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        const unsigned ad = c0w + (unsigned)r * (unsigned)cols;
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(cimg + (ad & ~3u));
+                        const uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
+                        const int sh = 8 * (ad & 3u);
+                        cw0[r] = __funnelshift_r(lo, hi, sh);
+                        cw1[r] = hi >> sh;
+                    }
+                }
                 RefRows R;
                 {
                     const float2 sub = s_sub[f];
@@ -219,43 +244,41 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                 R.grid_row(0, 0, 1);
                 R.load_row(0, 2);
                 R.grid_row(1, 1, 0);
-                // current-image 5x5 window rows vi-2 .. vi+2, cols ui-2 .. ui+2
-                const unsigned c0w = (unsigned)(vi - 2) * (unsigned)cols + (unsigned)(ui - 2);
                 double Cw[2][5];
-                auto load_cur = [&](int slot, int r) {
-                    const unsigned ad = c0w + (unsigned)r * (unsigned)cols;
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(cimg + (ad & ~3u));
-                    const uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
-                    const int sh = 8 * (ad & 3u);
-                    const uint32_t w0 = __funnelshift_r(lo, hi, sh), w1 = hi >> sh;
+                auto cvt_cur = [&](int slot, int r) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) Cw[slot][c] = u8_to_f64(w0, c);
-                    Cw[slot][4] = u8_to_f64(w1, 0);
+                    for (int c = 0; c < 4; ++c) Cw[slot][c] = u8_to_f64(cw0[r], c);
+                    Cw[slot][4] = u8_to_f64(cw1[r], 0);
                 };
-                load_cur(0, 0);
+                cvt_cur(0, 0);
                 double Sx = 0, Sy = 0, c2 = 0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    // G row r+2 from neighbourhood rows r+2 (already in Nd[r&1 ? 1 : 0]...) and r+3
-                    // slots: after the prologue Nd[0] = row 2, Nd[1] = row 1. Row r+2 sits in slot (r & 1) ? 1 : 0, row r+3 goes to the other.
-                    const int sa = (r & 1), sb = sa ^ 1;          // sa holds row r+2, sb receives row r+3
+                    // after the prologue Nd[0] = row 2, Nd[1] = row 1: row r+2 sits in slot (r & 1), row r+3 goes to the other
+                    const int sa = (r & 1), sb = sa ^ 1;
                     R.load_row(sb, r + 3);
                     R.grid_row((r + 2) % 3, sa, sb);
-                    load_cur((r + 1) & 1, r + 1);
+                    cvt_cur((r + 1) & 1, r + 1);
                     const int g0 = r % 3, g1 = (r + 1) % 3, g2 = (r + 2) % 3;   // G rows r, r+1, r+2
                     const int ca = r & 1, cb = ca ^ 1;                          // Cw rows r, r+1
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const double refv = R.G[g1][c + 1];
-                        const double dx = __dmul_rn(0.5, __dsub_rn(R.G[g1][c + 2], R.G[g1][c]));          // ref: :150-153
-                        const double dy = __dmul_rn(0.5, __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]));      // ref: :155-158
+                        // 2*dx, 2*dy: the reference's 0.5 factor (ref: :150-158) is applied once to the sums below (exact: power of two)
+                        const double dx2 = __dsub_rn(R.G[g1][c + 2], R.G[g1][c]);
+                        const double dy2 = __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]);
                         const double cur = bil(tl, tr, bl, br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
                         const double res = __dsub_rn(cur, refv);                                          // ref: :282
+#if DSDTM_SA_STRICT
                         c2 = __dadd_rn(c2, __dmul_rn(res, res));                                          // ref: :284
-                        Sx = fma(dx, res, Sx);
-                        Sy = fma(dy, res, Sy);
+#else
+                        c2 = fma(res, res, c2);
+#endif
+                        Sx = fma(dx2, res, Sx);
+                        Sy = fma(dy2, res, Sy);
                     }
                 }
+                Sx *= 0.5; Sy *= 0.5;
                 // GetJocabianBA(P) rows (ref: :169-193); a1 = b0 = 0.   b_j = fs * (a * Sx + b * Sy)
                 const double zi = 1.0 / P2, zi2 = zi * zi;
                 const double a0 = -zi, a2 = P0 * zi2, a3 = P1 * a2, a4 = -(1.0 + P0 * a2), a5 = P1 * zi;
@@ -303,11 +326,12 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                         const int g0 = r % 3, g1 = (r + 1) % 3, g2 = (r + 2) % 3;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const double dx = __dmul_rn(0.5, __dsub_rn(R.G[g1][c + 2], R.G[g1][c]));
-                            const double dy = __dmul_rn(0.5, __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]));
-                            Sxx = fma(dx, dx, Sxx); Sxy = fma(dx, dy, Sxy); Syy = fma(dy, dy, Syy);
+                            const double dx2 = __dsub_rn(R.G[g1][c + 2], R.G[g1][c]);
+                            const double dy2 = __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]);
+                            Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy);
                         }
                     }
+                    Sxx *= 0.25; Sxy *= 0.25; Syy *= 0.25;       // (0.5 d2)^2, exact
                     const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
                     const double zi = 1.0 / P2, zi2 = zi * zi;
                     const double av[6] = { -zi, 0.0, P0 * zi2, P1 * (P0 * zi2), -(1.0 + P0 * (P0 * zi2)), P1 * zi };

@@ -12,6 +12,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--scenes", type=int, default=2)
     ap.add_argument("--fast", type=int, default=0, help="also run fast_cells_batch over this many frames")
+    ap.add_argument("--wpp", type=int, default=0)
     ap.add_argument("--direct", action="store_true", help="launch kernels directly instead of graph replay")
     a = ap.parse_args()
     cam = dict(S.KINECT)
@@ -21,6 +22,7 @@ def main():
     ctx.batch_stage(batch["ref_slots"], batch["cur_slots"], batch["feats"], batch["n_feats"], batch["centers"], batch["poses_in"],
                     bench.ALIGN_CFG["max_level"], bench.ALIGN_CFG["min_level"], bench.ALIGN_CFG["max_iters"], batch["patches"], batch["patch_px"],
                     batch["patch_level"], bench.ALIGN2D_ITERS)
+    ctx.set_option("sa_warps_per_pair", a.wpp)
     if a.direct:
         ctx.profile(True)
     for _ in range(a.steps):
