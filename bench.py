@@ -44,7 +44,8 @@ def shard(n_total, world, rank):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons; started early (nvidia-smi needs ~1 s to produce its first line) and
+    filtered to the wall-clock window of the timed region afterwards."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -56,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -64,18 +65,28 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.p.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.p and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
 
     def stop(self):
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=2)
+            except Exception:
+                self.p.kill()
+
+    def summary(self, t0, t1):
         if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=2)
-        except Exception:
-            self.p.kill()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1 + 0.03:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -148,6 +159,8 @@ def run_ours(args):
             dist.barrier()
 
     # ---------------- device-resident steps (value)
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         ctx.batch_run(1)
     ctx.sync()
@@ -156,15 +169,15 @@ def run_ours(args):
     err = np.array([S.pose_dist(poses[i], batch["truth"][i]) for i in range(min(B, 64))])
     if not (np.median(err[:, 0]) < 5e-4 and np.median(err[:, 1]) < 1e-3):
         raise SystemExit("bench.py: alignment did not converge to the synthetic ground truth: %s" % np.median(err, 0))
-    clocks = ClockSampler(local)
     barrier()
     l0 = ctx.launch_count()
-    clocks.start()
+    clocks.wait_first()
+    tw0 = time.perf_counter()
     ctx.timer_start()
     for _ in range(args.steps):
         ctx.batch_run(1)
     dev_ms = ctx.timer_stop()
-    clk = clocks.stop()
+    tw1 = time.perf_counter()
     launches = ctx.launch_count() - l0
     barrier()
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -239,6 +252,12 @@ def run_ours(args):
     for _ in range(args.steps):
         e2e_step()
     e2e_wall = time.perf_counter() - t1
+    clocks.stop()
+    clk = clocks.summary(tw0, tw1)
+    clk["window"] = "device-resident timed region"
+    if clk["samples"] < 3:       # short region: widen to the e2e timed region as well, and say so
+        clk = clocks.summary(tw0, t1 + e2e_wall)
+        clk["window"] = "device-resident + e2e timed regions"
     barrier()
     t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -380,12 +399,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step")
     ap.add_argument("--scenes", type=int, default=8, help="distinct ray-cast scenes (tiled to --pairs)")
-    ap.add_argument("--cpu-sample", type=int, default=512, help="pairs in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

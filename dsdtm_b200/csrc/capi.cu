@@ -656,12 +656,15 @@ int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, con
     for (int k = 0; k < n_chunks && !rc; ++k) {
         const int p0 = k * per, n = std::min(per, n_pairs - p0);
         if (n <= 0) break;
-        // cur images: scatter into their slots (consecutive slots collapse into one strided copy)
-        bool consecutive = true;
-        for (int i = 1; i < n; ++i) if (cur_slots[p0 + i] != cur_slots[p0] + i) { consecutive = false; break; }
-        if (consecutive) {
-            if (cudaMemcpy2DAsync(c->frames_d + (size_t)cur_slots[p0] * g.frame_stride, g.frame_stride, cur_imgs + (size_t)p0 * img_bytes,
-                                  img_bytes, img_bytes, n, cudaMemcpyHostToDevice, cs) != cudaSuccess) rc = fail(c, DSDTM_E_CUDA, "H2D images", cudaGetLastError());
+        // cur images: scatter into their slots. Slots in arithmetic progression (the usual ref/cur interleaving gives
+        // stride 2) collapse into ONE strided 2-D copy; per-image copies cost ~2x in DMA setup (profiles/r1_e2e.md).
+        int sstride = (n > 1) ? cur_slots[p0 + 1] - cur_slots[p0] : 1;
+        bool regular = sstride > 0;
+        for (int i = 1; i < n && regular; ++i) if (cur_slots[p0 + i] != cur_slots[p0] + i * sstride) regular = false;
+        if (regular) {
+            if (cudaMemcpy2DAsync(c->frames_d + (size_t)cur_slots[p0] * g.frame_stride, (size_t)sstride * g.frame_stride,
+                                  cur_imgs + (size_t)p0 * img_bytes, img_bytes, img_bytes, n, cudaMemcpyHostToDevice, cs) != cudaSuccess)
+                rc = fail(c, DSDTM_E_CUDA, "H2D images", cudaGetLastError());
         } else {
             for (int i = 0; i < n && !rc; ++i)
                 if (cudaMemcpyAsync(c->frames_d + (size_t)cur_slots[p0 + i] * g.frame_stride, cur_imgs + (size_t)(p0 + i) * img_bytes, img_bytes,
@@ -676,7 +679,7 @@ int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, con
         // pyramid for this chunk's cur frames
         {
             cudaError_t e = launch_pyramid_slots(c, c->cur_slots_d + p0, n, ks);
-            if (e == cudaSuccess) e = launch_sparse_align(c, n, feat_stride, max_level, min_level, max_iters, false, ks, p0);
+            if (e == cudaSuccess) e = launch_sparse_align(c, n, feat_stride, max_level, min_level, max_iters, false, ks, p0, n_pairs);
             if (e == cudaSuccess && ppp > 0) e = launch_align2d(c, n * ppp, align_iters, ks, p0 * ppp);
             if (e != cudaSuccess) { rc = fail(c, DSDTM_E_CUDA, "e2e launch", e); break; }
         }

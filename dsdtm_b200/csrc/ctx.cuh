@@ -130,7 +130,7 @@ cudaError_t launch_fast_cells(dsdtm_ctx* c, int first_slot, int n, int barrier, 
                               cudaStream_t s);
 cudaError_t launch_fast_score_map(dsdtm_ctx* c, int slot, int level, int barrier, cudaStream_t s);
 cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int max_level, int min_level, int max_iters,
-                                bool want_log, cudaStream_t s, int pair0 = 0);
+                                bool want_log, cudaStream_t s, int pair0 = 0, int n_pairs_total = 0);
 cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
 cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s);
 int sparse_align_smem_bytes(int nf_pad);

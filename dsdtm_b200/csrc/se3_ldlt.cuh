@@ -117,6 +117,55 @@ DSDTM_HD void ldlt6_solve_reg(const double (&Hin)[6][6], const double (&bin)[6],
     for (int i = 0; i < 6; ++i) x[i] = y[i];
 }
 
+// Fast path: unpivoted LDL^T in registers (~150 instructions instead of ~2500 for the predicated-swap pivoted version:
+// the pivoted code alone is larger than the 32 KB instruction cache, profiles/r1_sparse_align_v2.md). For a symmetric
+// positive definite H both factorisations solve the same system and differ only in rounding (backward stable either way).
+// Returns false -- caller falls back to ldlt6_solve_reg, i.e. Eigen's exact pivoted semantics -- when a pivot is not
+// safely positive (rank-deficient / indefinite / NaN input).
+DSDTM_HD bool ldlt6_solve_spd(const double (&A)[6][6], const double (&b)[6], double (&x)[6])
+{
+    double L[6][6], d[6];
+    double maxdiag = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) maxdiag = fmax(maxdiag, fabs(A[i][i]));
+    const double thresh = 1e-11 * maxdiag;
+    bool ok = maxdiag > 0.0 && maxdiag < 1.7976931348623157e308;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double dk = A[k][k];
+#pragma unroll
+        for (int j = 0; j < k; ++j) dk -= L[k][j] * L[k][j] * d[j];
+        d[k] = dk;
+        ok = ok && (dk > thresh);
+        const double inv = 1.0 / dk;
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            double v = A[i][k];
+#pragma unroll
+            for (int j = 0; j < k; ++j) v -= L[i][j] * L[k][j] * d[j];
+            L[i][k] = v * inv;
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = b[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) v -= L[i][j] * y[j];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = y[i] / d[i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) v -= L[j][i] * x[j];
+        x[i] = v;
+    }
+    return ok;
+}
+
 struct Quat { double w, x, y, z; };
 
 // out = T * exp(x); pose7 = {qw,qx,qy,qz,tx,ty,tz}. (ref: src/Sprase_ImageAlign.cpp:335; Sophus SE3::exp, SE3::operator*=)

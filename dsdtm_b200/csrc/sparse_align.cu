@@ -6,12 +6,12 @@
 // Design (DESIGN.md "Sparse alignment"; profiles/r1_sparse_align_v1.md explains why v1 was replaced):
 //   * one CTA of WPP warps per frame pair, each lane owns ceil(N / (32*WPP)) reference features; the whole
 //     level x iteration loop runs on the device (the chain of dependent GN steps never returns to the host).
-//     WPP = 1 packs 7 independent pairs on one SM (throughput: other pairs fill the serial solve of this one),
+//     WPP = 1 packs 6 independent pairs on one SM (throughput: other pairs fill the serial solve of this one),
 //     WPP = 10 gives one feature per lane (single-pair latency);
 //   * per level the 7x7 u8 neighbourhood of every reference feature (49 B), its 3-D point and sub-pixel offsets are
-//     staged ONCE in shared memory (89 B / feature instead of the 384 B of precomputed fp64 patches, which limited v1
-//     to one pair per SM); the bilinear reference samples and their central differences are re-derived from the bytes
-//     with exactly the reference's expressions each iteration (2x the flops, 1/4 the shared memory, 7x the residency);
+//     staged ONCE in shared memory (113 B / feature incl. the parked second moments, instead of the 384 B of precomputed
+//     fp64 patches which limited v1 to one pair per SM); the bilinear reference samples and their central differences are re-derived from the bytes
+//     with the reference's expressions each iteration (2x the flops, 1/3 the shared memory, 6x the residency);
 //   * inverse-compositional structure: the Jacobian row of pixel p of feature j is
 //         J_jp = (dx_jp * a_j + dy_jp * b_j) * (f * scale)          (ref: :160; a_j, b_j = rows of GetJocabianBA(P_j))
 //     so  sum_p J_jp J_jp^T = (f*scale)^2 (Sxx a a^T + Sxy (a b^T + b a^T) + Syy b b^T) is pose-independent: H is
@@ -24,6 +24,8 @@
 //   * lane 0 solves the 6x6 system with Eigen's pivoted LDL^T entirely in registers (se3_ldlt.cuh), applies SE3::exp and
 //     the reference's accept / revert / converge rules, and publishes the pose through shared memory.
 #include "ctx.cuh"
+#include <type_traits>
+
 #include "se3_ldlt.cuh"
 
 namespace dsdtm {
@@ -113,15 +115,40 @@ struct RefRows {
     }
 };
 
+// the serial tail of one GN iteration, kept out of line: it runs on one lane once per iteration and must not bloat
+// (or evict from the instruction cache) the per-feature loop
+__device__ __noinline__ void solve_and_update(const double* __restrict__ sH /*21 packed*/, const double (&bvec)[6], double (&x)[6])
+{
+    double Hm[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) { Hm[r][c] = sH[r * (r + 1) / 2 + c]; Hm[c][r] = Hm[r][c]; }
+    if (!ldlt6_solve_spd(Hm, bvec, x)) ldlt6_solve_reg(Hm, bvec, x);       // ref: :318 (Eigen ldlt().solve)
+}
+
+__device__ __noinline__ void pose_update(const double* T, const double (&x)[6], double* Tn)
+{
+    double Tc[7], To[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) Tc[q] = T[q];
+    se3_mul_exp(Tc, x, To);                                                // ref: :335
+#pragma unroll
+    for (int q = 0; q < 7; ++q) Tn[q] = To[q];
+}
+
+struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
+
 template <int WPP>
-__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1)) sparse_align_kernel(const SaArgs a)
+__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? 3 : 1)) sparse_align_kernel(const SaArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int NF = a.nf;
-    double* s_P = reinterpret_cast<double*>(s_raw);                               // [3][NF]
-    uint32_t* s_nb = reinterpret_cast<uint32_t*>(s_raw + (size_t)24 * NF);        // [14][NF]
-    float2* s_sub = reinterpret_cast<float2*>(s_raw + (size_t)(24 + 4 * NB_WORDS) * NF);   // [NF] sub-pixel offsets
-    uint8_t* s_valid = s_raw + (size_t)(24 + 4 * NB_WORDS + 8) * NF;              // [NF]
+    double* s_P = reinterpret_cast<double*>(s_raw);                                        // [3][NF] point in the ref camera
+    double* s_S = reinterpret_cast<double*>(s_raw + (size_t)24 * NF);                      // [3][NF] Sxx, Sxy, Syy of the ref patch
+    uint32_t* s_nb = reinterpret_cast<uint32_t*>(s_raw + (size_t)48 * NF);                 // [14][NF] 7x7 u8 neighbourhood
+    float2* s_sub = reinterpret_cast<float2*>(s_raw + (size_t)(48 + 4 * NB_WORDS) * NF);   // [NF] sub-pixel offsets
+    uint8_t* s_valid = s_raw + (size_t)(48 + 4 * NB_WORDS + 8) * NF;                       // [NF]
     __shared__ double s_red[WPP][8];
     __shared__ int s_cnt[WPP];
     __shared__ double s_redH[WPP][22];
@@ -169,7 +196,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                         s_P[2 * NF + f] = __dmul_rn(ft.normal[2], depth);
                         const int fxi = __double2int_rd(px), fyi = __double2int_rd(py);
                         s_sub[f] = make_float2((float)(px - fxi), (float)(py - fyi));                 // exact: px is a float scaled by 2^-level
-                        // rows fyi-3 .. fyi+3, cols fxi-3 .. fxi+3 : two aligned 32-bit loads + funnel shift per row
+                        // rows fyi-3 .. fyi+3, cols fxi-3 .. fxi+3 : three aligned 32-bit loads + funnel shifts per row
                         const unsigned a0 = (unsigned)(fyi - 3) * (unsigned)cols + (unsigned)(fxi - 3);
 #pragma unroll
                         for (int r = 0; r < 7; ++r) {
@@ -197,9 +224,14 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
             double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0, accc = 0;
             int cnt = 0;
             unsigned vis_mask = 0;
-            int k = 0;
-            for (int f = tid; f < nfeat; f += NT, ++k) {
-                if (!s_valid[f]) continue;
+
+            // stage 1 of a feature: projection, bounds test and the ten aligned 32-bit loads of its 5x5 current-image window.
+            // It is issued one feature AHEAD of the fp64 arithmetic (software pipeline) so the gather latency is covered.
+            auto stage1 = [&](int f, Pre& p) {
+                p.valid = false; p.vis = false;
+                if (f >= nfeat) return;
+                if (!s_valid[f]) return;
+                p.valid = true;
                 const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
                 double Q0, Q1, Q2;
                 qrot(qw, qx, qy, qz, P0, P1, P2, Q0, Q1, Q2);                                  // ref: :254
@@ -209,28 +241,31 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                 const double v = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fy, Q1), Q2), cy), scale);
                 const double uf = floor(u), vf = floor(v);
                 // ref: :262 with border 3; evaluated in double so that NaN / huge values are rejected like the reference's INT_MIN
-                if (!(uf >= 3.0 && vf >= 3.0 && uf < (double)(cols - 3) && vf < (double)(rows - 3))) continue;
-                vis_mask |= 1u << k;
-                ++cnt;
+                if (!(uf >= 3.0 && vf >= 3.0 && uf < (double)(cols - 3) && vf < (double)(rows - 3))) return;
+                p.vis = true;
                 const int ui = (int)uf, vi = (int)vf;
                 const double su = u - uf, sv = v - vf;
-                const double tl = __dmul_rn(1.0 - su, 1.0 - sv), tr = __dmul_rn(su, 1.0 - sv);
-                const double bl = __dmul_rn(1.0 - su, sv), br = __dmul_rn(su, sv);            // ref: :267-270
-                // current-image 5x5 window rows vi-2 .. vi+2, cols ui-2 .. ui+2: all ten aligned 32-bit loads are issued here,
-                // before the reference-side arithmetic, so that their L1/L2 latency is covered by independent fp64 work
-                uint32_t cw0[5], cw1[5];
-                {
-                    const unsigned c0w = (unsigned)(vi - 2) * (unsigned)cols + (unsigned)(ui - 2);
+                p.tl = __dmul_rn(1.0 - su, 1.0 - sv); p.tr = __dmul_rn(su, 1.0 - sv);
+                p.bl = __dmul_rn(1.0 - su, sv); p.br = __dmul_rn(su, sv);                     // ref: :267-270
+                const unsigned c0w = (unsigned)(vi - 2) * (unsigned)cols + (unsigned)(ui - 2);
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) {
-                        const unsigned ad = c0w + (unsigned)r * (unsigned)cols;
-                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(cimg + (ad & ~3u));
-                        const uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
-                        const int sh = 8 * (ad & 3u);
-                        cw0[r] = __funnelshift_r(lo, hi, sh);
-                        cw1[r] = hi >> sh;
-                    }
+                for (int r = 0; r < 5; ++r) {
+                    const unsigned ad = c0w + (unsigned)r * (unsigned)cols;
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(cimg + (ad & ~3u));
+                    const uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
+                    const int sh = 8 * (ad & 3u);
+                    p.cw0[r] = __funnelshift_r(lo, hi, sh);
+                    p.cw1[r] = hi >> sh;
                 }
+            };
+
+            // stage 2: the fp64 arithmetic of one feature. FIRST (iteration 0 of a level) also derives the pose-independent
+            // second moments Sxx, Sxy, Syy of every VALID feature (visible or not) and parks them in shared memory for H.
+            auto stage2 = [&](auto first_tag, int f, int k, const Pre& me) {
+                constexpr bool FIRST = decltype(first_tag)::value;
+                if (!(FIRST ? me.valid : me.vis)) return;
+                const bool vis = me.vis;
+                if (vis) { vis_mask |= 1u << k; ++cnt; }
                 RefRows R;
                 {
                     const float2 sub = s_sub[f];
@@ -239,7 +274,6 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                     R.w10 = __dmul_rn(1.0 - sx, sy); R.w11 = __dmul_rn(sx, sy);               // ref: :129-132
                 }
                 R.nb = s_nb + f; R.NF = NF;
-                // G rows 0 and 1 (neighbourhood rows 0,1,2)
                 R.load_row(0, 0); R.load_row(1, 1);
                 R.grid_row(0, 0, 1);
                 R.load_row(0, 2);
@@ -247,11 +281,11 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                 double Cw[2][5];
                 auto cvt_cur = [&](int slot, int r) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) Cw[slot][c] = u8_to_f64(cw0[r], c);
-                    Cw[slot][4] = u8_to_f64(cw1[r], 0);
+                    for (int c = 0; c < 4; ++c) Cw[slot][c] = u8_to_f64(me.cw0[r], c);
+                    Cw[slot][4] = u8_to_f64(me.cw1[r], 0);
                 };
                 cvt_cur(0, 0);
-                double Sx = 0, Sy = 0, c2 = 0;
+                double Sx = 0, Sy = 0, c2 = 0, Sxx = 0, Sxy = 0, Syy = 0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     // after the prologue Nd[0] = row 2, Nd[1] = row 1: row r+2 sits in slot (r & 1), row r+3 goes to the other
@@ -267,7 +301,8 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                         // 2*dx, 2*dy: the reference's 0.5 factor (ref: :150-158) is applied once to the sums below (exact: power of two)
                         const double dx2 = __dsub_rn(R.G[g1][c + 2], R.G[g1][c]);
                         const double dy2 = __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]);
-                        const double cur = bil(tl, tr, bl, br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
+                        if (FIRST) { Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy); }
+                        const double cur = bil(me.tl, me.tr, me.bl, me.br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
                         const double res = __dsub_rn(cur, refv);                                          // ref: :282
 #if DSDTM_SA_STRICT
                         c2 = __dadd_rn(c2, __dmul_rn(res, res));                                          // ref: :284
@@ -278,15 +313,33 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                         Sy = fma(dy2, res, Sy);
                     }
                 }
+                if (FIRST) { s_S[f] = 0.25 * Sxx; s_S[NF + f] = 0.25 * Sxy; s_S[2 * NF + f] = 0.25 * Syy; }   // (0.5 d2)^2, exact scaling
+                if (FIRST && !vis) return;
                 Sx *= 0.5; Sy *= 0.5;
                 // GetJocabianBA(P) rows (ref: :169-193); a1 = b0 = 0.   b_j = fs * (a * Sx + b * Sy)
+                const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
                 const double zi = 1.0 / P2, zi2 = zi * zi;
                 const double a0 = -zi, a2 = P0 * zi2, a3 = P1 * a2, a4 = -(1.0 + P0 * a2), a5 = P1 * zi;
                 const double b1 = -zi, b2 = P1 * zi2, b3 = 1.0 + P1 * b2, b4 = -P0 * b2, b5 = -P0 * zi;
                 acc0 += fs * (a0 * Sx); acc1 += fs * (b1 * Sy); acc2 += fs * (a2 * Sx + b2 * Sy);
                 acc3 += fs * (a3 * Sx + b3 * Sy); acc4 += fs * (a4 * Sx + b4 * Sy); acc5 += fs * (a5 * Sx + b5 * Sy);
                 accc += c2;
-            }
+            };
+
+            auto run_pass = [&](auto first_tag) {
+                Pre cur;
+                cur.valid = false; cur.vis = false;
+                int k = -1;
+                for (int f = tid; f < nfeat + NT; f += NT, ++k) {
+                    Pre nxt;
+                    stage1(f, nxt);
+                    const Pre me = cur;
+                    cur = nxt;
+                    stage2(first_tag, f - NT, k, me);
+                }
+            };
+            if (it == 0) run_pass(std::true_type{}); else run_pass(std::false_type{});
+
             acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2); acc3 = warp_sum(acc3);
             acc4 = warp_sum(acc4); acc5 = warp_sum(acc5); accc = warp_sum(accc);
             cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -298,45 +351,19 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
             const int need_H = __syncthreads_or((it == 0) || (vis_mask != prev_vis));
             prev_vis = vis_mask;
             if (need_H) {
-                // H = fs^2 sum_visible (Sxx a a^T + Sxy (a b^T + b a^T) + Syy b b^T), lower triangle packed row-major
+                // H = fs^2 sum_visible (Sxx a a^T + Sxy (a b^T + b a^T) + Syy b b^T), lower triangle packed row-major,
+                // assembled from the parked second moments (no image arithmetic here)
                 double hacc[21];
 #pragma unroll
                 for (int i = 0; i < 21; ++i) hacc[i] = 0.0;
                 int kk = 0;
                 for (int f = tid; f < nfeat; f += NT, ++kk) {
                     if (!((vis_mask >> kk) & 1u)) continue;
-                    RefRows R;
-                    {
-                        const float2 sub = s_sub[f];
-                        const double sx = (double)sub.x, sy = (double)sub.y;
-                        R.w00 = __dmul_rn(1.0 - sx, 1.0 - sy); R.w01 = __dmul_rn(sx, 1.0 - sy);
-                        R.w10 = __dmul_rn(1.0 - sx, sy); R.w11 = __dmul_rn(sx, sy);
-                    }
-                    R.nb = s_nb + f; R.NF = NF;
-                    R.load_row(0, 0); R.load_row(1, 1);
-                    R.grid_row(0, 0, 1);
-                    R.load_row(0, 2);
-                    R.grid_row(1, 1, 0);
-                    double Sxx = 0, Sxy = 0, Syy = 0;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int sa = (r & 1), sb = sa ^ 1;
-                        R.load_row(sb, r + 3);
-                        R.grid_row((r + 2) % 3, sa, sb);
-                        const int g0 = r % 3, g1 = (r + 1) % 3, g2 = (r + 2) % 3;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const double dx2 = __dsub_rn(R.G[g1][c + 2], R.G[g1][c]);
-                            const double dy2 = __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]);
-                            Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy);
-                        }
-                    }
-                    Sxx *= 0.25; Sxy *= 0.25; Syy *= 0.25;       // (0.5 d2)^2, exact
                     const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
                     const double zi = 1.0 / P2, zi2 = zi * zi;
                     const double av[6] = { -zi, 0.0, P0 * zi2, P1 * (P0 * zi2), -(1.0 + P0 * (P0 * zi2)), P1 * zi };
                     const double bv[6] = { 0.0, -zi, P1 * zi2, 1.0 + P1 * (P1 * zi2), -P0 * (P1 * zi2), -P0 * zi };
-                    const double cxx = fs2 * Sxx, cxy = fs2 * Sxy, cyy = fs2 * Syy;
+                    const double cxx = fs2 * s_S[f], cxy = fs2 * s_S[NF + f], cyy = fs2 * s_S[2 * NF + f];
 #pragma unroll
                     for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -371,14 +398,9 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                 __syncwarp();
                 if (lane == 0) {
                     const double chi2New = accc / (double)(16 * cnt);                      // ref: :298 (NaN if nothing visible)
-                    double Hm[6][6];
-#pragma unroll
-                    for (int r = 0; r < 6; ++r)
-#pragma unroll
-                        for (int c = 0; c <= r; ++c) { Hm[r][c] = s_H[r * (r + 1) / 2 + c]; Hm[c][r] = Hm[r][c]; }
                     const double bvec[6] = { acc0, acc1, acc2, acc3, acc4, acc5 };
                     double x[6];
-                    ldlt6_solve_reg(Hm, bvec, x);                                          // ref: :318
+                    solve_and_update(s_H, bvec, x);                                        // ref: :318
                     int flags = 0;
                     bool stop = false;
                     if (isnan(x[0])) { stop = true; flags |= 4; }                          // ref: :321-326
@@ -388,12 +410,10 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
                         flags |= 2;
                         stop = true;
                     } else {
-                        double Tc[7], Tn[7];
+                        double Tn[7];
+                        pose_update(s_T, x, Tn);                                           // ref: :335
 #pragma unroll
-                        for (int q = 0; q < 7; ++q) Tc[q] = s_T[q];
-                        se3_mul_exp(Tc, x, Tn);                                            // ref: :335
-#pragma unroll
-                        for (int q = 0; q < 7; ++q) { s_Told[q] = Tc[q]; s_T[q] = Tn[q]; } // ref: :336-337
+                        for (int q = 0; q < 7; ++q) { s_Told[q] = s_T[q]; s_T[q] = Tn[q]; } // ref: :336-337
                         s_chi2prev = chi2New;                                              // ref: :339
                         flags |= 1;
                         double mx = 0;
@@ -431,7 +451,8 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 7 : (WPP == 4 ? 3 : 1))
     }
 }
 
-int smem_bytes(int nf) { return (24 + 4 * NB_WORDS + 8 + 1) * nf; }
+int smem_bytes(int nf) { return (48 + 4 * NB_WORDS + 8 + 1) * nf; }
+int round_nf(int max_feats) { return (max_feats + 15) / 16 * 16; }
 
 template <int WPP>
 cudaError_t launch(const SaArgs& a, int n_pairs, cudaStream_t s)
@@ -446,7 +467,7 @@ int sparse_align_smem_bytes(int nf) { return smem_bytes(nf); }
 
 cudaError_t sparse_align_init(dsdtm_ctx* c)
 {
-    const int nf = (c->prm.max_feats + 31) / 32 * 32;
+    const int nf = round_nf(c->prm.max_feats);
     const int bytes = smem_bytes(nf);
     cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -455,19 +476,18 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
     return e;
 }
 
-// warps per pair: enough pairs to fill the chip -> 1 warp per pair (7 pairs resident per SM); few pairs -> wide CTAs for latency
+// warps per pair, measured on B200 (profiles/r1_sparse_align_v3.md, 2072 pairs, ms per launch): 1 -> 1.71, 2 -> 1.70,
+// 4 -> 1.22, 10 -> one pair per SM. Four warps per pair keeps the warps of a CTA on the same code (instruction-cache
+// locality: the kernel is ~120 KB of SASS) while three CTAs per SM overlap each other's serial solve; a lone pair gets
+// ten warps (one feature per lane) for latency.
 int sparse_align_pick_wpp(const dsdtm_ctx* c, int n_pairs)
 {
     if (c->sa_wpp_override > 0) return c->sa_wpp_override;
-    const int sms = c->sm_count;
-    if (n_pairs >= 4 * sms) return 1;
-    if (n_pairs >= 2 * sms) return 2;
-    if (n_pairs >= sms) return 4;
-    return 10;
+    return (n_pairs >= c->sm_count) ? 4 : 10;
 }
 
 cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int max_level, int min_level, int max_iters,
-                                bool want_log, cudaStream_t s, int pair0)
+                                bool want_log, cudaStream_t s, int pair0, int n_pairs_total)
 {
     SaArgs a;
     a.frames = c->frames_d; a.frame_stride = c->geo.frame_stride; a.geo = c->geo;
@@ -477,10 +497,11 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
     a.log = want_log ? c->log_d : nullptr; a.n_log = want_log ? c->n_log_d : nullptr; a.log_cap = kLogCap;
     a.fx = c->cam.fx; a.fy = c->cam.fy; a.cx = c->cam.cx; a.cy = c->cam.cy; a.f = c->cam.f;
     a.max_level = max_level; a.min_level = min_level; a.max_iters = max_iters;
-    a.nf = (c->prm.max_feats + 31) / 32 * 32;
+    a.nf = round_nf(c->prm.max_feats);
     a.pair0 = pair0;
     c->launches++;
-    switch (sparse_align_pick_wpp(c, n_pairs)) {
+    // warps-per-pair is chosen from the size of the WHOLE batch so that chunked (e2e) and single-launch runs reduce in the same order
+    switch (sparse_align_pick_wpp(c, n_pairs_total > 0 ? n_pairs_total : n_pairs)) {
     case 1: return launch<1>(a, n_pairs, s);
     case 2: return launch<2>(a, n_pairs, s);
     case 4: return launch<4>(a, n_pairs, s);
