@@ -1,0 +1,586 @@
+// dsdtm_host.cpp -- bodies of the reference's front-end classes as marshalling + C-ABI calls (see dsdtm_host.h).
+#include "dsdtm_host.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace DSDTM {
+
+// ================================================================================================ value types
+int cvRound(double v) { return (int)std::nearbyint(v); }
+
+SE3::SE3() { p[0] = 1; for (int i = 1; i < 7; ++i) p[i] = 0; }
+SE3::SE3(const double q[7]) { std::memcpy(p, q, sizeof p); }
+
+static void quat_rot(const double* q, const double* v, double* o)   // Eigen _transformVector
+{
+    double uv[3] = { q[2] * v[2] - q[3] * v[1], q[3] * v[0] - q[1] * v[2], q[1] * v[1] - q[2] * v[0] };
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    const double c[3] = { q[2] * uv[2] - q[3] * uv[1], q[3] * uv[0] - q[1] * uv[2], q[1] * uv[1] - q[2] * uv[0] };
+    for (int i = 0; i < 3; ++i) o[i] = v[i] + q[0] * uv[i] + c[i];
+}
+
+SE3 SE3::operator*(const SE3& o) const   // translation_ += so3_*o.translation_; so3_ *= o.so3_ (normalised)
+{
+    SE3 r;
+    double rt[3];
+    quat_rot(p, o.p + 4, rt);
+    for (int i = 0; i < 3; ++i) r.p[4 + i] = p[4 + i] + rt[i];
+    const double aw = p[0], ax = p[1], ay = p[2], az = p[3], bw = o.p[0], bx = o.p[1], by = o.p[2], bz = o.p[3];
+    double q[4] = { aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                    aw * by + ay * bw + az * bx - ax * bz, aw * bz + az * bw + ax * by - ay * bx };
+    const double n = std::sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3] + q[0] * q[0]);
+    for (int i = 0; i < 4; ++i) r.p[i] = q[i] / n;
+    return r;
+}
+
+SE3 SE3::inverse() const
+{
+    SE3 r;
+    r.p[0] = p[0]; r.p[1] = -p[1]; r.p[2] = -p[2]; r.p[3] = -p[3];
+    const double nt[3] = { p[4] * -1., p[5] * -1., p[6] * -1. };
+    quat_rot(r.p, nt, r.p + 4);
+    return r;
+}
+
+Vector3d SE3::operator*(const Vector3d& v) const
+{
+    double o[3];
+    quat_rot(p, v.v, o);
+    return Vector3d(o[0] + p[4], o[1] + p[5], o[2] + p[6]);
+}
+
+SE3 SE3::exp(const double x[6])
+{
+    const double* om = x + 3;
+    const double theta = std::sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    SE3 r;
+    double imag;
+    if (theta < 1e-10) { const double t2 = theta * theta; imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t2 * t2; }
+    else imag = std::sin(0.5 * theta) / theta;
+    double q[4] = { std::cos(0.5 * theta), imag * om[0], imag * om[1], imag * om[2] };
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) r.p[i] = q[i] / n;
+    const double O[9] = { 0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0 };
+    double V[9];
+    if (theta < 1e-10) {
+        const double w = r.p[0], a = r.p[1], b = r.p[2], c = r.p[3];
+        const double R[9] = { 1 - 2 * (b * b + c * c), 2 * (a * b - w * c), 2 * (a * c + w * b), 2 * (a * b + w * c), 1 - 2 * (a * a + c * c),
+                              2 * (b * c - w * a), 2 * (a * c - w * b), 2 * (b * c + w * a), 1 - 2 * (a * a + b * b) };
+        std::memcpy(V, R, sizeof V);
+    } else {
+        double O2[9];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += O[3 * i + k] * O[3 * k + j]; O2[3 * i + j] = s; }
+        const double t2 = theta * theta, a = (1 - std::cos(theta)) / t2, b = (theta - std::sin(theta)) / (t2 * theta);
+        for (int i = 0; i < 9; ++i) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * O[i] + b * O2[i];
+    }
+    for (int i = 0; i < 3; ++i) r.p[4 + i] = V[3 * i] * x[0] + V[3 * i + 1] * x[1] + V[3 * i + 2] * x[2];
+    return r;
+}
+
+Mat8::Mat8(int rows_, int cols_, uchar fill) : rows(rows_), cols(cols_), step(cols_)
+{
+    store = std::make_shared<std::vector<uchar>>((size_t)rows * cols, fill);
+    data = store->data();
+}
+
+Mat8::Mat8(int rows_, int cols_, const uchar* src, int src_step) : rows(rows_), cols(cols_), step(cols_)
+{
+    store = std::make_shared<std::vector<uchar>>((size_t)rows * cols);
+    data = store->data();
+    for (int y = 0; y < rows; ++y) std::memcpy(data + (size_t)y * cols, src + (size_t)y * src_step, cols);
+}
+
+// cv::circle(img, center, radius, color, -1): OpenCV's filled midpoint circle (checked against cv2 goldens in tests/)
+void circle(Mat8& img, Point2f center, int radius, uchar color)
+{
+    const int cx = cvRound(center.x), cy = cvRound(center.y), w = img.cols, h = img.rows;
+    auto span = [&](int y, int x0, int x1) {
+        if (y < 0 || y >= h) return;
+        x0 = std::max(x0, 0); x1 = std::min(x1, w - 1);
+        if (x0 <= x1) std::memset(img.data + (size_t)y * img.step + x0, color, (size_t)(x1 - x0 + 1));
+    };
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        span(cy - dy, cx - dx, cx + dx); span(cy + dy, cx - dx, cx + dx);
+        span(cy - dx, cx - dy, cx + dy); span(cy + dx, cx - dy, cx + dy);
+        dy++; err += plus; plus += 2;
+        const int mask = (err <= 0) - 1;
+        err -= minus & mask; dx += mask; minus -= mask & 2;
+    }
+}
+
+// ================================================================================================ Config
+std::map<std::string, std::string>& Config::table() { static std::map<std::string, std::string> t; return t; }
+void Config::Clear() { table().clear(); }
+void Config::Set(const std::string& k, const std::string& v) { table()[k] = v; }
+bool Config::Has(const std::string& k) { return table().count(k) != 0; }
+
+void Config::setParameterFile(const std::string& path)
+{
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("Config: parameter file " + path + " does not exist");   // ref: src/Config.cpp:17-21
+    std::string line;
+    while (std::getline(f, line)) {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos) line = line.substr(0, hash);
+        if (line.empty() || line[0] == '%' || line.compare(0, 3, "---") == 0) continue;
+        // unresolved merge-conflict markers of the shipped kinect.yaml are skipped; the later block wins
+        if (line.compare(0, 7, "<<<<<<<") == 0 || line.compare(0, 7, "=======") == 0 || line.compare(0, 7, ">>>>>>>") == 0) continue;
+        const size_t colon = line.find(':');
+        if (colon == std::string::npos) continue;
+        auto trim = [](std::string s) { const char* ws = " \t\r\n\""; s.erase(0, s.find_first_not_of(ws)); s.erase(s.find_last_not_of(ws) + 1); return s; };
+        const std::string k = trim(line.substr(0, colon)), v = trim(line.substr(colon + 1));
+        if (!k.empty() && !v.empty()) table()[k] = v;
+    }
+}
+
+template <> int Config::Get<int>(const std::string& k)
+{
+    auto it = table().find(k);
+    if (it == table().end()) return 0;   // cv::FileStorage yields 0 for a missing node
+    return (int)std::strtod(it->second.c_str(), nullptr);
+}
+template <> float Config::Get<float>(const std::string& k) { auto it = table().find(k); return it == table().end() ? 0.f : (float)std::strtod(it->second.c_str(), nullptr); }
+template <> double Config::Get<double>(const std::string& k) { auto it = table().find(k); return it == table().end() ? 0.0 : std::strtod(it->second.c_str(), nullptr); }
+template <> std::string Config::Get<std::string>(const std::string& k) { auto it = table().find(k); return it == table().end() ? std::string() : it->second; }
+
+// ================================================================================================ Camera
+Camera::Camera()
+{
+    mf = Config::Get<float>("Camera.f");
+    mfx = Config::Get<float>("Camera.fx"); mfy = Config::Get<float>("Camera.fy");
+    mcx = Config::Get<float>("Camera.cx"); mcy = Config::Get<float>("Camera.cy");
+    mwidth = Config::Get<int>("Camera.width"); mheight = Config::Get<int>("Camera.height");
+}
+
+Vector2d Camera::Camera2Pixel(const Vector3d& P) const { return Vector2d(mfx * P[0] / P[2] + mcx, mfy * P[1] / P[2] + mcy); }
+Vector3d Camera::Pixel2Camera(const Point2f& pt, const float& depth) const
+{
+    return Vector3d(depth * (pt.x - mcx) / mfx, depth * (pt.y - mcy) / mfy, depth);   // float arithmetic, then widened (Q8)
+}
+Vector3d Camera::Pixel2Camera(const Vector2d& pt, const float& depth) const
+{
+    return Vector3d(depth * (pt(0) - mcx) / mfx, depth * (pt(1) - mcy) / mfy, depth);
+}
+bool Camera::IsInImage(const Point2f p, int b, int level) const
+{
+    return cvRound(p.x) >= b && cvRound(p.x) < mwidth / (1 << level) - b && cvRound(p.y) >= b && cvRound(p.y) < mheight / (1 << level) - b;
+}
+
+// ================================================================================================ GPU runtime
+static GpuRuntime* g_runtime = nullptr;
+
+GpuRuntime& GpuRuntime::Instance()
+{
+    if (!g_runtime) g_runtime = new GpuRuntime();
+    return *g_runtime;
+}
+void GpuRuntime::Shutdown() { delete g_runtime; g_runtime = nullptr; }
+
+GpuRuntime::GpuRuntime()
+{
+    dsdtm_cam cam;
+    cam.width = Config::Get<int>("Camera.width"); cam.height = Config::Get<int>("Camera.height");
+    cam.fx = Config::Get<float>("Camera.fx"); cam.fy = Config::Get<float>("Camera.fy");
+    cam.cx = Config::Get<float>("Camera.cx"); cam.cy = Config::Get<float>("Camera.cy");
+    cam.f = Config::Get<float>("Camera.f");
+    dsdtm_params prm;
+    prm.levels = mLevels = Config::Get<int>("Camera.MaxPyraLevels");
+    prm.cell_size = Config::Get<int>("Camera.CellSize");
+    const int max_fts = std::max(Config::Get<int>("Camera.Max_fts"), 16);
+    prm.max_feats = std::min(std::max(max_fts, 64), DSDTM_MAX_FEATS_LIMIT);
+    const int rows = (cam.height + prm.cell_size - 1) / std::max(prm.cell_size, 1), cols = (cam.width + prm.cell_size - 1) / std::max(prm.cell_size, 1);
+    prm.max_patches = std::max(4 * rows * cols, 1024);      // speculative batch of every reprojected candidate
+    prm.max_frames = mMaxFrames = Config::Has("Gpu.MaxFrames") ? Config::Get<int>("Gpu.MaxFrames") : 32;
+    prm.max_batch = 1;
+    mCtx = dsdtm_create(Config::Has("Gpu.Device") ? Config::Get<int>("Gpu.Device") : 0, &cam, &prm);
+    if (!mCtx) throw std::runtime_error(std::string("DSDTM GPU front end unavailable (no CPU fallback): ") + dsdtm_create_error());
+    mOwner.assign(mMaxFrames, nullptr);
+    mStamp.assign(mMaxFrames, 0);
+}
+
+GpuRuntime::~GpuRuntime()
+{
+    for (auto* o : mOwner) if (o) o->slot = -1;
+    if (mCtx) dsdtm_destroy(mCtx);
+}
+
+int GpuRuntime::Acquire(GpuSlot* owner)
+{
+    int best = -1;
+    for (int i = 0; i < mMaxFrames; ++i) if (!mOwner[i]) { best = i; break; }
+    if (best < 0) {   // evict the least recently used pyramid; its owner re-uploads on next use
+        for (int i = 0; i < mMaxFrames; ++i) if (best < 0 || mStamp[i] < mStamp[best]) best = i;
+        mOwner[best]->slot = -1;
+    }
+    mOwner[best] = owner;
+    mStamp[best] = ++mClock;
+    return best;
+}
+
+void GpuRuntime::Release(int slot) { if (slot >= 0 && slot < mMaxFrames) mOwner[slot] = nullptr; }
+
+std::shared_ptr<GpuSlot> GpuRuntime::Upload(const Mat8& img)
+{
+    auto s = std::make_shared<GpuSlot>(img);
+    Resident(s);
+    return s;
+}
+
+int GpuRuntime::Resident(const std::shared_ptr<GpuSlot>& s)
+{
+    if (s->slot >= 0) { mStamp[s->slot] = ++mClock; return s->slot; }
+    s->slot = Acquire(s.get());
+    if (dsdtm_frame_upload_pyramid(mCtx, s->slot, s->host.data, s->host.step) != 0)
+        throw std::runtime_error(std::string("dsdtm_frame_upload_pyramid: ") + dsdtm_last_error(mCtx));
+    return s->slot;
+}
+
+GpuSlot::~GpuSlot() { if (g_runtime && slot >= 0) g_runtime->Release(slot); }
+
+// ================================================================================================ Frame / KeyFrame / MapPoint
+Frame::Frame(CameraPtr cam, const Mat8& gray, double ts) : mCamera(cam), mdCloTimestamp(ts), mColorImg(gray)
+{
+    mPyra_levels = Config::Get<int>("Camera.MaxPyraLevels");      // ref: src/Frame.cpp:51-52
+    mMin_Dist = Config::Get<int>("Camera.Min_dist");
+    mvImg_Pyr.resize(mPyra_levels);
+    ComputeImagePyramid(mColorImg, mvImg_Pyr);                    // ref: :55
+    mImgMask = Mat8(mCamera->mheight, mCamera->mwidth, 255);      // ref: :64-65
+    mDynamicMask = Mat8(mCamera->mheight, mCamera->mwidth, 0);
+}
+
+Frame::~Frame() {}
+
+void Frame::ComputeImagePyramid(const Mat8 image, std::vector<Mat8>& pyr)   // ref: src/Frame.cpp:74-81
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    pyr[0] = image;                                               // level 0 aliases the caller's image
+    mGpu = rt.Upload(image);                                      // H2D + pyrDown chain on the device
+    for (int l = 1; l < (int)pyr.size(); ++l) {
+        int w, h;
+        dsdtm_level_info(rt.ctx(), l, &w, &h, nullptr);
+        pyr[l] = Mat8(h, w, 0);
+        // host copies keep mvImg_Pyr usable by code outside the hot path (viewer, depth lookup); the GPU stages never read them
+        if (dsdtm_frame_download_level(rt.ctx(), mGpu->slot, l, pyr[l].data) != 0)
+            throw std::runtime_error(std::string("dsdtm_frame_download_level: ") + dsdtm_last_error(rt.ctx()));
+    }
+}
+
+void Frame::Add_Feature(Feature* f, bool normal)                  // ref: src/Frame.cpp:83-92
+{
+    if (normal) { f->mNormal = mCamera->Pixel2Camera(f->mpx, 1.0f); f->mNormal.normalize(); }
+    mvFeatures.push_back(f);
+}
+
+void Frame::Set_Pose(const SE3& pose)                             // ref: src/Frame.cpp:167-174
+{
+    mT_c2w = pose;
+    mOw = mT_c2w.inverse().translation();
+}
+
+Vector2d Frame::World2Pixel(const Vector3d& p) const { return mCamera->Camera2Pixel(mT_c2w * p); }   // ref: :318-323
+
+void Frame::Set_Mask()                                            // ref: src/Frame.cpp:286-298
+{
+    for (size_t k = 0; k < mvFeatures.size(); ++k)
+        if (k < mvMapPoints.size() && mvMapPoints[k]) circle(mImgMask, mvFeatures[k]->mpx, mMin_Dist, 0);
+    for (int i = 0; i < mDynamicMask.rows * mDynamicMask.cols; ++i) mDynamicMask.data[i] = mDynamicMask.data[i] > 200 ? 255 : 0;
+    for (int i = 0; i < mImgMask.rows * mImgMask.cols; ++i) {
+        const int v = (int)mImgMask.data[i] - (int)mDynamicMask.data[i];
+        mImgMask.data[i] = (uchar)std::max(v, 0);                 // saturating subtraction
+    }
+}
+
+KeyFrame::KeyFrame(Frame* f) : mvImg_Pyr(f->mvImg_Pyr), mvFeatures(f->mvFeatures), mGpu(f->mGpu) { Set_Pose(f->Get_Pose()); }
+void KeyFrame::Set_Pose(const SE3& p) { mT_c2w = p; mOw = mT_c2w.inverse().translation(); }
+
+bool MapPoint::Get_ClosetObs(const Frame* frame, Feature*& feature, KeyFrame*& kf) const   // ref: src/MapPoint.cpp:133-174
+{
+    if (mObservations.empty()) return false;
+    const Vector3d pose = Get_Pose();
+    Vector3d dir = frame->Get_CameraCnt() - pose;
+    dir.normalize();
+    double best = 0;
+    auto best_it = mObservations.begin();
+    for (auto it = mObservations.begin(); it != mObservations.end(); ++it) {
+        Vector3d d = it->first->Get_CameraCnt() - pose;
+        d.normalize();
+        const double c = d.dot(dir);
+        if (c > best) { best = c; best_it = it; }
+    }
+    feature = best_it->first->mvFeatures[best_it->second];
+    kf = best_it->first;
+    return !(best < 0.5);
+}
+
+// ================================================================================================ Feature_detector
+Feature_detector::Feature_detector()                              // ref: src/Feature_detection.cpp:10-21
+{
+    mCell_size = Config::Get<int>("Camera.CellSize");
+    mPyr_levels = Config::Get<int>("Camera.MaxPyraLevels");
+    mMax_fts = Config::Get<int>("Camera.Max_fts");
+    mImg_width = Config::Get<int>("Camera.width");
+    mImg_height = Config::Get<int>("Camera.height");
+    mGrid_rows = (int)std::ceil(1.0 * mImg_height / mCell_size);
+    mGrid_cols = (int)std::ceil(1.0 * mImg_width / mCell_size);
+    mvGrid_occupy.resize((size_t)mGrid_rows * mGrid_cols, false);
+}
+
+void Feature_detector::Set_ExistingFeatures(const Features& features)      // ref: :43-50
+{
+    mvGrid_occupy.assign((size_t)mGrid_rows * mGrid_cols, false);
+    for (Feature* f : features)
+        mvGrid_occupy[(size_t)static_cast<int>(f->mpx.y / mCell_size) * mGrid_cols + static_cast<int>(f->mpx.x / mCell_size)] = true;
+}
+
+void Feature_detector::Set_ExistingFeatures(const std::vector<Point2f>& features)   // ref: :52-62 (note the cast placement)
+{
+    mvGrid_occupy.assign((size_t)mGrid_rows * mGrid_cols, false);
+    for (const Point2f& f : features)
+        mvGrid_occupy.at((size_t)(static_cast<int>((f.y / mCell_size) * mGrid_cols) + static_cast<int>(f.x / mCell_size))) = true;
+}
+
+void Feature_detector::ResetGrid() { std::fill(mvGrid_occupy.begin(), mvGrid_occupy.end(), false); }
+
+void Feature_detector::detect(Frame* frame, const double detection_threshold, const bool)   // ref: :69-154
+{
+    if ((int)frame->mvFeatures.size() >= mMax_fts) return;
+    GpuRuntime& rt = GpuRuntime::Instance();
+    const int slot = rt.Resident(frame->mGpu);
+    const int n = mGrid_rows * mGrid_cols;
+    std::vector<uint8_t> occ(n);
+    for (int i = 0; i < n; ++i) occ[i] = mvGrid_occupy[i] ? 1 : 0;
+    std::vector<dsdtm_corner> cells(n);
+    // levels loop + FAST + non-max + Shi-Tomasi + per-cell best on the device (ref: :76-109)
+    if (dsdtm_fast_cells(rt.ctx(), slot, 20, (float)detection_threshold, occ.data(), cells.data()) != 0)
+        throw std::runtime_error(std::string("dsdtm_fast_cells: ") + dsdtm_last_error(rt.ctx()));
+    Corners corners;
+    corners.reserve(n);
+    for (int i = 0; i < n; ++i) corners.emplace_back(cells[i].x, cells[i].y, cells[i].score, cells[i].level, 0.0f);
+    std::sort(corners.begin(), corners.end());                    // ref: :111 -- same (unstable) std::sort on the same comparator
+    if (frame->mvFeatures.size() > 0) frame->Set_Mask();          // ref: :120-123
+    for (size_t it = 0; it < corners.size(); ++it) {              // ref: :125-150
+        const Corner c = corners[it];
+        if (c.score > 20) {
+            const Point2f p((float)c.x, (float)c.y);
+            if (frame->mImgMask.at(cvRound(p.y), cvRound(p.x)) == 255) {
+                frame->Add_Feature(new Feature(frame, p, c.level), 0);
+                circle(frame->mImgMask, p, mCell_size, 0);
+            }
+        }
+        if ((int)frame->mvFeatures.size() >= mMax_fts) break;
+    }
+    ResetGrid();
+    frame->mImgMask.release();                                    // ref: :152-153
+}
+
+// ================================================================================================ Sprase_ImgAlign
+Sprase_ImgAlign::Sprase_ImgAlign(int tMaxLevel, int tMinLevel, int tMaxIterators)
+    : mnMaxLevel(tMaxLevel), mnMinLevel(tMinLevel), mnMaxIterators(tMaxIterators)
+{
+    mnMinfts = Config::Get<int>("Camera.Min_fts");                // ref: src/Sprase_ImageAlign.cpp:14
+}
+
+int Sprase_ImgAlign::Run(FramePtr cur, FramePtr ref)              // ref: src/Sprase_ImageAlign.cpp:29-60
+{
+    mLog.clear();
+    if ((int)ref->mvFeatures.size() < mnMinfts) return 0;         // ref: :34-38 "Too few features to track"
+    GpuRuntime& rt = GpuRuntime::Instance();
+    // snapshot every map point ONCE on the tracking thread (the mapper moves them under mutex, SURVEY 7 "thread-safety at the seam")
+    std::vector<dsdtm_ref_feat> feats;
+    feats.reserve(ref->mvFeatures.size());
+    for (Feature* f : ref->mvFeatures) {
+        dsdtm_ref_feat r;
+        r.px[0] = f->mpx.x; r.px[1] = f->mpx.y; r.level = f->mlevel; r.initial = f->mbInitial ? 1 : 0;
+        for (int k = 0; k < 3; ++k) r.normal[k] = f->mNormal[k];
+        const Vector3d P = (f->mbInitial && f->Mpt) ? f->Mpt->Get_Pose() : Vector3d();
+        for (int k = 0; k < 3; ++k) r.point_w[k] = P[k];
+        feats.push_back(r);
+    }
+    const SE3 T_c2r = cur->Get_Pose() * ref->Get_Pose().inverse();   // ref: :43
+    const Vector3d cen = ref->Get_CameraCnt();
+    double pose_out[7];
+    int n_tracked = 0, n_log = 0;
+    mLog.resize(256);
+    const int ref_slot = rt.Resident(ref->mGpu), cur_slot = rt.Resident(cur->mGpu);
+    // chunks of max_feats would change the reference's single linear system; the capacity is sized from Camera.Max_fts instead
+    if (dsdtm_sparse_align(rt.ctx(), ref_slot, cur_slot, feats.data(), (int)feats.size(), cen.v, T_c2r.data(), mnMaxLevel, mnMinLevel,
+                           mnMaxIterators, pose_out, &n_tracked, mLog.data(), (int)mLog.size(), &n_log) != 0)
+        throw std::runtime_error(std::string("dsdtm_sparse_align: ") + dsdtm_last_error(rt.ctx()));
+    mLog.resize(std::min<size_t>(n_log, mLog.size()));
+    cur->Set_Pose(SE3(pose_out) * ref->Get_Pose());               // ref: :57
+    return n_tracked;                                             // ref: :59
+}
+
+// ================================================================================================ Feature_Alignment
+struct Feature_Alignment::Prepared {
+    int ref_slot, ref_level, search_level;
+    double A[4];
+    float ref_px[2];
+};
+
+Feature_Alignment::Feature_Alignment(CameraPtr camera) : mCam(camera)   // ref: src/Feature_alignment.cpp:11-44
+{
+    mMax_pts = Config::Get<int>("Camera.Max_tkfts");
+    mPyr_levels = Config::Get<int>("Camera.MaxPyraLevels");
+    mCell_size = Config::Get<int>("Camera.CellSize");
+    mGrid_Rows = (int)std::ceil(1.0 * mCam->mheight / mCell_size);
+    mGrid_Cols = (int)std::ceil(1.0 * mCam->mwidth / mCell_size);
+    mCells.resize((size_t)mGrid_Rows * mGrid_Cols);
+    for (auto& c : mCells) c = new Cell;
+    // the reference also builds a shuffled mCellOrder that it never uses (Q9): cells are visited in index order
+}
+
+Feature_Alignment::~Feature_Alignment() { for (auto* c : mCells) delete c; }
+void Feature_Alignment::ResetGrid() { for (auto* c : mCells) c->clear(); }
+
+bool Feature_Alignment::ReprojectPoint(FramePtr frame, MapPoint* mp)     // ref: :54-69
+{
+    const Vector2d px = frame->World2Pixel(mp->Get_Pose());
+    if (mCam->IsInImage(Point2f((float)px(0), (float)px(1)), 8)) {
+        const int index = static_cast<int>(px(1) / mCell_size) * mGrid_Cols + static_cast<int>(px(0) / mCell_size);
+        mCells[index]->push_back(Candidate(mp, px));
+        return true;
+    }
+    return false;
+}
+
+Matrix2d Feature_Alignment::SolveAffineMatrix(KeyFrame* kf, const FramePtr cur, Feature* rf, const MapPoint*)   // ref: :160-190
+{
+    Matrix2d A;
+    const int HalfLarger = mHalf_PatchSize + 1, level = rf->mlevel;
+    const Vector3d P = (kf->Get_CameraCnt() - rf->Mpt->Get_Pose()).norm() * rf->mNormal;
+    const Point2f rp = rf->mpx;
+    const Vector2d pxU(rp.x + HalfLarger * (1 << level), rp.y), pxV(rp.x, rp.y + HalfLarger * (1 << level));
+    Vector3d PU = mCam->Pixel2Camera(pxU, 1.0f), PV = mCam->Pixel2Camera(pxV, 1.0f);
+    PU.normalize(); PV.normalize();
+    PU = PU * (P(2) / PU(2)); PV = PV * (P(2) / PV(2));
+    const SE3 T = cur->Get_Pose() * kf->Get_Pose().inverse();
+    const Vector2d c = mCam->Camera2Pixel(T * P), cu = mCam->Camera2Pixel(T * PU), cv = mCam->Camera2Pixel(T * PV);
+    A(0, 0) = (cu(0) - c(0)) / HalfLarger; A(1, 0) = (cu(1) - c(1)) / HalfLarger;
+    A(0, 1) = (cv(0) - c(0)) / HalfLarger; A(1, 1) = (cv(1) - c(1)) / HalfLarger;
+    return A;
+}
+
+int Feature_Alignment::GetBestSearchLevel(Matrix2d A, int max_level)      // ref: :192-204
+{
+    int L = 0;
+    double D = A.determinant();
+    while (D > 3.0 && L < max_level) { L++; D = D * 0.25; }
+    return L;
+}
+
+// host-side map walk of FindMatchDirect up to (not including) the pixel work (ref: :128-146)
+bool Feature_Alignment::Prepare(const MapPoint* mp, const FramePtr frame, const Vector2d&, Prepared& out)
+{
+    Feature* rf = nullptr;
+    KeyFrame* kf = nullptr;
+    if (!mp->Get_ClosetObs(frame.get(), rf, kf)) return false;
+    if (!mCam->IsInImage(Point2f(rf->mpx.x / (1 << rf->mlevel), rf->mpx.y / (1 << rf->mlevel)), mHalf_PatchSize + 1, rf->mlevel)) return false;
+    const Matrix2d A = SolveAffineMatrix(kf, frame, rf, mp);
+    out.search_level = GetBestSearchLevel(A, mPyr_levels - 3);
+    out.ref_slot = GpuRuntime::Instance().Resident(kf->mGpu);
+    out.ref_level = rf->mlevel;
+    out.A[0] = A(0, 0); out.A[1] = A(0, 1); out.A[2] = A(1, 0); out.A[3] = A(1, 1);
+    out.ref_px[0] = rf->mpx.x; out.ref_px[1] = rf->mpx.y;
+    return true;
+}
+
+void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref: :71-121
+{
+    // The reference walks cells in index order, candidates by found-count, and stops a cell at the first match; a match
+    // paints the mask and thereby only changes which LATER candidates are tried, never their alignment result. So: sort
+    // the cells (as the reference does, in place), align every candidate of every cell speculatively in ONE GPU batch
+    // (WarpAffine + Align2D), then replay the greedy selection on the host in the reference's order.
+    GpuRuntime& rt = GpuRuntime::Instance();
+    struct Item { Candidate* cand; bool prepared; int batch_index; };
+    std::vector<std::vector<Item>> items(mCells.size());
+    std::vector<int> ref_slot, ref_level, search_level;
+    std::vector<double> A, px;
+    std::vector<float> ref_px;
+    for (size_t ci = 0; ci < mCells.size(); ++ci) {
+        Cell* cell = mCells[ci];
+        cell->sort([](Candidate& a, Candidate& b) { return a.mMpPoint->Get_FoundNums() > b.mMpPoint->Get_FoundNums(); });   // ref: :88,123-126
+        for (Candidate& c : *cell) {
+            Item it{ &c, false, -1 };
+            Prepared p;
+            if (!c.mMpPoint->IsBad() && Prepare(c.mMpPoint, frame, c.mPx, p)) {
+                it.prepared = true;
+                it.batch_index = (int)ref_slot.size();
+                ref_slot.push_back(p.ref_slot); ref_level.push_back(p.ref_level); search_level.push_back(p.search_level);
+                A.insert(A.end(), p.A, p.A + 4);
+                ref_px.push_back(p.ref_px[0]); ref_px.push_back(p.ref_px[1]);
+                px.push_back(c.mPx[0] / (1 << p.search_level)); px.push_back(c.mPx[1] / (1 << p.search_level));   // ref: :150
+            }
+            items[ci].push_back(it);
+        }
+    }
+    const int n = (int)ref_slot.size();
+    std::vector<uint8_t> patches((size_t)n * 100), conv(n);
+    if (n > 0) {
+        const int cur_slot = rt.Resident(frame->mGpu);
+        // a re-upload of `frame` may have evicted a keyframe slot resolved above: resolve again (cheap, usually a no-op)
+        if (dsdtm_warp_affine_batch(rt.ctx(), ref_slot.data(), A.data(), ref_px.data(), ref_level.data(), search_level.data(), n, patches.data()) != 0)
+            throw std::runtime_error(std::string("dsdtm_warp_affine_batch: ") + dsdtm_last_error(rt.ctx()));
+        if (dsdtm_align2d_batch(rt.ctx(), cur_slot, search_level.data(), patches.data(), px.data(), n, 10, conv.data()) != 0)
+            throw std::runtime_error(std::string("dsdtm_align2d_batch: ") + dsdtm_last_error(rt.ctx()));
+    }
+    // replay (ref: :75-82, :91-118)
+    int matches = 0;
+    for (size_t ci = 0; ci < mCells.size(); ++ci) {
+        for (Item& it : items[ci]) {
+            Candidate& c = *it.cand;
+            if (c.mMpPoint->IsBad()) continue;
+            if (frame->mImgMask.at(cvRound((float)c.mPx[1]), cvRound((float)c.mPx[0])) != 255) continue;
+            if (!it.prepared) continue;
+            const int b = it.batch_index;
+            const int L = search_level[b];
+            c.mPx = Vector2d(px[2 * b] * (1 << L), px[2 * b + 1] * (1 << L));   // ref: :154 (tPt is updated even on failure)
+            if (!conv[b]) continue;
+            c.mMpPoint->IncreaseFound();
+            Feature* f = new Feature(frame.get(), Point2f((float)c.mPx[0], (float)c.mPx[1]), L);
+            f->SetPose(c.mMpPoint);
+            circle(frame->mImgMask, Point2f((float)c.mPx[0], (float)c.mPx[1]), mCell_size, 0);
+            frame->Add_Feature(f);
+            frame->Add_MapPoint(c.mMpPoint);
+            matches++;
+            break;                                               // ReprojectCell returns at the first match
+        }
+        if (matches >= 200) break;                               // ref: :80 literal
+    }
+    mLastMatches = matches;
+}
+
+bool Feature_Alignment::FindMatchDirect(const MapPoint* mp, const FramePtr frame, Vector2d& pt, int& level)   // ref: :128-158
+{
+    Prepared p;
+    if (!Prepare(mp, frame, pt, p)) return false;
+    GpuRuntime& rt = GpuRuntime::Instance();
+    uint8_t patch[100], conv = 0;
+    double px[2] = { pt[0] / (1 << p.search_level), pt[1] / (1 << p.search_level) };
+    const int cur_slot = rt.Resident(frame->mGpu);
+    if (dsdtm_warp_affine_batch(rt.ctx(), &p.ref_slot, p.A, p.ref_px, &p.ref_level, &p.search_level, 1, patch) != 0 ||
+        dsdtm_align2d_batch(rt.ctx(), cur_slot, &p.search_level, patch, px, 1, 10, &conv) != 0)
+        throw std::runtime_error(std::string("FindMatchDirect: ") + dsdtm_last_error(rt.ctx()));
+    pt = Vector2d(px[0] * (1 << p.search_level), px[1] * (1 << p.search_level));
+    level = p.search_level;
+    return conv != 0;
+}
+
+bool Feature_Alignment::Align2DGaussNewton(const FramePtr cur, int level, uchar* patch10, uchar*, int MaxIters, Vector2d& px)   // ref: :318-417
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    uint8_t conv = 0;
+    double p[2] = { px[0], px[1] };
+    if (dsdtm_align2d_batch(rt.ctx(), rt.Resident(cur->mGpu), &level, patch10, p, 1, MaxIters, &conv) != 0)
+        throw std::runtime_error(std::string("dsdtm_align2d_batch: ") + dsdtm_last_error(rt.ctx()));
+    px = Vector2d(p[0], p[1]);
+    return conv != 0;
+}
+
+}  // namespace DSDTM

@@ -1,0 +1,300 @@
+// dsdtm_host.h -- C++ host side of the drop-in: the reference's class interfaces for the tracking front end
+// (namespace DSDTM; same class names, method names, argument meaning and error behaviour as called from Tracking,
+// ref: src/Tracking.cpp:31-37,204,224,260,299,415-416,476; src/Initializer.cpp:44; src/Frame.cpp:55), with bodies that
+// marshal into the C-ABI of include/dsdtm_gpu.h. No OpenCV / Eigen / Sophus: the few value types the interfaces need
+// (Point2f, Vector2d/3d, Matrix2d, SE3, an 8-bit Mat) are provided here with the semantics the hot path relies on.
+// A maintainer of the reference keeps cv::Mat / Eigen / Sophus and replaces only the method bodies: see INTEGRATION.md.
+//
+// There is no CPU fallback: every compute method goes through dsdtm_* and throws std::runtime_error if the GPU
+// context cannot be created (the reference has no error channel on these methods either; it would simply crash).
+#ifndef DSDTM_HOST_H
+#define DSDTM_HOST_H
+
+#include <cmath>
+#include <cstdint>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dsdtm_gpu.h"
+
+namespace DSDTM {
+
+typedef unsigned char uchar;
+
+// ------------------------------------------------------------------------------------------ value types
+struct Point2f { float x, y; Point2f(float x_ = 0, float y_ = 0) : x(x_), y(y_) {} };
+
+struct Vector2d {
+    double v[2];
+    Vector2d(double a = 0, double b = 0) { v[0] = a; v[1] = b; }
+    double& operator()(int i) { return v[i]; }
+    double operator()(int i) const { return v[i]; }
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+    Vector2d operator-(const Vector2d& o) const { return Vector2d(v[0] - o.v[0], v[1] - o.v[1]); }
+    Vector2d operator*(double s) const { return Vector2d(v[0] * s, v[1] * s); }
+    Vector2d operator/(double s) const { return Vector2d(v[0] / s, v[1] / s); }
+};
+
+struct Vector3d {
+    double v[3];
+    Vector3d(double a = 0, double b = 0, double c = 0) { v[0] = a; v[1] = b; v[2] = c; }
+    double& operator()(int i) { return v[i]; }
+    double operator()(int i) const { return v[i]; }
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+    Vector3d operator-(const Vector3d& o) const { return Vector3d(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+    Vector3d operator+(const Vector3d& o) const { return Vector3d(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
+    Vector3d operator*(double s) const { return Vector3d(v[0] * s, v[1] * s, v[2] * s); }
+    double dot(const Vector3d& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
+    double norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+    void normalize() { const double n = norm(); v[0] /= n; v[1] /= n; v[2] /= n; }
+    bool isZero() const { return v[0] == 0 && v[1] == 0 && v[2] == 0; }
+};
+inline Vector3d operator*(double s, const Vector3d& a) { return a * s; }
+
+struct Matrix2d {
+    double m[2][2];
+    Matrix2d() { m[0][0] = m[1][1] = 1; m[0][1] = m[1][0] = 0; }
+    double& operator()(int r, int c) { return m[r][c]; }
+    double operator()(int r, int c) const { return m[r][c]; }
+    double determinant() const { return m[0][0] * m[1][1] - m[1][0] * m[0][1]; }
+};
+
+// Sophus::SE3 (non-templated): unit quaternion + translation; pose7 = {qw,qx,qy,qz,tx,ty,tz}
+class SE3 {
+public:
+    SE3();
+    explicit SE3(const double pose7[7]);
+    static SE3 exp(const double x[6]);
+    SE3 inverse() const;
+    SE3 operator*(const SE3& o) const;
+    Vector3d operator*(const Vector3d& p) const;
+    Vector3d translation() const { return Vector3d(p[4], p[5], p[6]); }
+    const double* data() const { return p; }
+private:
+    double p[7];
+};
+
+// 8-bit single-channel image with cv::Mat-like sharing semantics (level 0 of a pyramid aliases the caller's image)
+class Mat8 {
+public:
+    int rows = 0, cols = 0, step = 0;
+    uchar* data = nullptr;
+    Mat8() {}
+    Mat8(int rows_, int cols_, uchar fill);
+    Mat8(int rows_, int cols_, const uchar* src, int src_step);   // copies
+    bool empty() const { return data == nullptr; }
+    uchar& at(int y, int x) { return data[(size_t)y * step + x]; }
+    uchar at(int y, int x) const { return data[(size_t)y * step + x]; }
+    void release() { store.reset(); data = nullptr; rows = cols = step = 0; }
+private:
+    std::shared_ptr<std::vector<uchar>> store;
+};
+
+int cvRound(double v);                                       // round-half-to-even like OpenCV on x86
+void circle(Mat8& img, Point2f center, int radius, uchar color);   // cv::circle(img, c, r, color, -1)
+
+// ------------------------------------------------------------------------------------------ Config / Camera
+// ref: include/Config.h:28-31 -- dotted-key YAML subset ("%YAML:1.0", comments, key: value)
+class Config {
+public:
+    static void setParameterFile(const std::string& path);
+    static void Set(const std::string& key, const std::string& value);
+    static bool Has(const std::string& key);
+    template <typename T> static T Get(const std::string& key);
+    static void Clear();
+private:
+    static std::map<std::string, std::string>& table();
+};
+
+class Camera {   // ref: include/Camera.h:137-163, src/Camera.cpp:32-60,167-193
+public:
+    Camera();    // reads Camera.* from Config
+    Vector2d Camera2Pixel(const Vector3d& p) const;
+    Vector3d Pixel2Camera(const Point2f& px, const float& depth) const;      // float evaluation (Q8)
+    Vector3d Pixel2Camera(const Vector2d& px, const float& depth) const;
+    bool IsInImage(const Point2f pt, int boundary = 0, int level = 0) const;
+    float mf, mfx, mfy, mcx, mcy;
+    int mwidth, mheight;
+};
+typedef std::shared_ptr<Camera> CameraPtr;
+
+// ------------------------------------------------------------------------------------------ data model (boundary types only)
+class Frame;
+class KeyFrame;
+class MapPoint;
+
+struct Feature {   // ref: include/Feature.h:16-51
+    Frame* mframe;
+    Point2f mpx;
+    int mlevel;
+    bool mbInitial;
+    Vector3d mNormal;
+    MapPoint* Mpt;
+    Feature(Frame* frame, const Point2f& px, int level) : mframe(frame), mpx(px), mlevel(level), mbInitial(false), mNormal(0, 0, 0), Mpt(nullptr) {}
+    void SetPose(MapPoint* mp) { Mpt = mp; mbInitial = true; }
+};
+typedef std::vector<Feature*> Features;
+
+class MapPoint {   // ref: include/MapPoint.h, src/MapPoint.cpp:38-43,126-181 (the members the hot path reads)
+public:
+    explicit MapPoint(const Vector3d& pose) : mPose(pose) {}
+    Vector3d Get_Pose() const { std::unique_lock<std::mutex> l(mMutexPos); return mPose; }
+    void Set_Pose(const Vector3d& p) { std::unique_lock<std::mutex> l(mMutexPos); mPose = p; }
+    bool IsBad() const { return mbBad; }
+    void SetBad(bool b) { mbBad = b; }
+    int Get_FoundNums() const { return mnFound; }
+    void IncreaseFound(int n = 1) { mnFound += n; }
+    void Add_Observation(KeyFrame* kf, size_t idx) { mObservations[kf] = idx; }
+    bool Get_ClosetObs(const Frame* frame, Feature*& feature, KeyFrame*& kf) const;
+private:
+    mutable std::mutex mMutexPos;
+    Vector3d mPose;
+    bool mbBad = false;
+    int mnFound = 1;
+    std::map<KeyFrame*, size_t> mObservations;
+};
+
+class GpuSlot;   // device residency of one pyramid (RAII; shared between a Frame and the KeyFrame made from it)
+
+class Frame {   // ref: include/Frame.h:18-136, src/Frame.cpp:48-92,167-174,286-298,318-323
+public:
+    Frame(CameraPtr cam, const Mat8& gray, double timestamp = 0);
+    virtual ~Frame();
+    void ComputeImagePyramid(const Mat8 image, std::vector<Mat8>& pyr);      // GPU: dsdtm_frame_upload_pyramid
+    void Add_Feature(Feature* f, bool normal = true);
+    void Add_MapPoint(MapPoint* mp) { mvMapPoints.push_back(mp); }
+    void Set_Pose(const SE3& pose);
+    SE3 Get_Pose() const { return mT_c2w; }
+    Vector3d Get_CameraCnt() const { return mOw; }
+    Vector2d World2Pixel(const Vector3d& p) const;
+    void Set_Mask();
+
+    CameraPtr mCamera;
+    double mdCloTimestamp;
+    Mat8 mColorImg;
+    std::vector<Mat8> mvImg_Pyr;
+    Features mvFeatures;
+    std::vector<MapPoint*> mvMapPoints;
+    Mat8 mImgMask, mDynamicMask;
+    int mPyra_levels, mMin_Dist;
+    std::shared_ptr<GpuSlot> mGpu;     // new member: where the pyramid lives in HBM
+protected:
+    SE3 mT_c2w;
+    Vector3d mOw;
+};
+typedef std::shared_ptr<Frame> FramePtr;
+
+class KeyFrame {   // ref: include/Keyframe.h, src/Keyframe.cpp:10-22 (copy of the frame's images, features and pose)
+public:
+    explicit KeyFrame(Frame* frame);
+    SE3 Get_Pose() const { return mT_c2w; }
+    void Set_Pose(const SE3& p);
+    Vector3d Get_CameraCnt() const { return mOw; }
+    std::vector<Mat8> mvImg_Pyr;
+    Features mvFeatures;
+    std::shared_ptr<GpuSlot> mGpu;
+private:
+    SE3 mT_c2w;
+    Vector3d mOw;
+};
+
+// ------------------------------------------------------------------------------------------ the hot-path classes
+struct Corner {   // ref: include/Feature_detection.h:19-33
+    int x, y, level;
+    float score, angle;
+    Corner(int x_, int y_, float score_, int level_, float angle_) : x(x_), y(y_), level(level_), score(score_), angle(angle_) {}
+    bool operator<(const Corner& c) const { return c.score < score; }
+};
+typedef std::vector<Corner> Corners;
+
+class Feature_detector {   // ref: include/Feature_detection.h:36-74
+public:
+    Feature_detector();
+    void Set_ExistingFeatures(const Features& features);
+    void Set_ExistingFeatures(const std::vector<Point2f>& features);
+    void detect(Frame* frame, const double detection_threshold, const bool tFirst = true);
+    void ResetGrid();
+    int mImg_height, mImg_width, mCell_size, mPyr_levels, mGrid_rows, mGrid_cols, mMax_fts;
+    std::vector<bool> mvGrid_occupy;
+};
+
+class Sprase_ImgAlign {   // ref: include/Sprase_ImageAlign.h:20-69
+public:
+    Sprase_ImgAlign(int tMaxLevel, int tMinLevel, int tMaxIterators);
+    int Run(FramePtr tCurFrame, FramePtr tRefFrame);
+    // last run's Gauss-Newton trace (new: the reference only prints; used by the parity tests)
+    const std::vector<dsdtm_iter_log>& LastLog() const { return mLog; }
+protected:
+    int mnMaxLevel, mnMinLevel, mnMaxIterators, mnMinfts;
+    std::vector<dsdtm_iter_log> mLog;
+};
+
+static const int mHalf_PatchSize = 4;   // ref: include/Feature_alignment.h:21
+
+class Feature_Alignment {   // ref: include/Feature_alignment.h:23-99
+public:
+    struct Candidate {
+        MapPoint* mMpPoint;
+        Vector2d mPx;
+        Candidate(MapPoint* pt, Vector2d px) : mMpPoint(pt), mPx(px) {}
+    };
+    typedef std::list<Candidate> Cell;
+    explicit Feature_Alignment(CameraPtr camera);
+    ~Feature_Alignment();
+    void ResetGrid();
+    bool ReprojectPoint(FramePtr tFrame, MapPoint* tMPoint);
+    void SearchLocalPoints(FramePtr tFrame);
+    // single-candidate forms kept for API parity (each is a batch of one on the GPU)
+    bool FindMatchDirect(const MapPoint* tMpPoint, const FramePtr tFrame, Vector2d& tPt, int& tLevel);
+    Matrix2d SolveAffineMatrix(KeyFrame* tReferKframe, const FramePtr tCurFrame, Feature* tReferFeature, const MapPoint* tMpPoint);
+    int GetBestSearchLevel(Matrix2d tAffineMat, int tMaxLevel);
+    static bool Align2DGaussNewton(const FramePtr tCurFrame, int tLevel, uchar* tPatch_WithBoarder, uchar* tPatch, int MaxIters, Vector2d& tCurPx);
+    int LastMatches() const { return mLastMatches; }
+private:
+    struct Prepared;   // one candidate after the host-side map walk
+    bool Prepare(const MapPoint* mp, const FramePtr frame, const Vector2d& px, Prepared& out);
+    CameraPtr mCam;
+    std::vector<Cell*> mCells;
+    int mCell_size, mGrid_Cols, mGrid_Rows, mMax_pts, mPyr_levels;
+    int mLastMatches = 0;
+};
+
+// ------------------------------------------------------------------------------------------ GPU runtime
+// One dsdtm_ctx per process/thread of tracking, created lazily from Config (Camera.*, Gpu.Device, Gpu.MaxFrames).
+class GpuRuntime {
+public:
+    static GpuRuntime& Instance();
+    static void Shutdown();
+    dsdtm_ctx* ctx() { return mCtx; }
+    std::shared_ptr<GpuSlot> Upload(const Mat8& level0);          // uploads + builds the pyramid, returns the residency handle
+    int Resident(const std::shared_ptr<GpuSlot>& s);             // slot index, re-uploading from the host copy if it was evicted
+    int levels() const { return mLevels; }
+    void Release(int slot);
+    ~GpuRuntime();
+private:
+    GpuRuntime();
+    int Acquire(GpuSlot* owner);
+    dsdtm_ctx* mCtx = nullptr;
+    int mLevels = 0, mMaxFrames = 0;
+    std::vector<GpuSlot*> mOwner;      // per slot
+    std::vector<unsigned long long> mStamp;
+    unsigned long long mClock = 0;
+    friend class GpuSlot;
+};
+
+class GpuSlot {
+public:
+    GpuSlot(const Mat8& img) : host(img) {}
+    ~GpuSlot();
+    Mat8 host;        // level 0 (shared buffer): lets the runtime re-upload after an eviction
+    int slot = -1;
+};
+
+}  // namespace DSDTM
+#endif

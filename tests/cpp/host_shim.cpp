@@ -1,0 +1,151 @@
+// host_shim.cpp -- TEST INFRASTRUCTURE: a C shim over the C++ host adapters (dsdtm_b200/host) so that pytest can drive
+// DSDTM::Frame / Feature_detector / Sprase_ImgAlign / Feature_Alignment exactly as Tracking would.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../dsdtm_b200/host/dsdtm_host.h"
+
+using namespace DSDTM;
+
+struct HsFrame { FramePtr f; std::vector<MapPoint*> owned; };
+struct HsKf { KeyFrame* kf; };
+static std::string g_err;
+
+extern "C" {
+
+const char* hs_last_error() { return g_err.c_str(); }
+void hs_reset() { GpuRuntime::Shutdown(); Config::Clear(); }
+void hs_config_set(const char* k, const char* v) { Config::Set(k, v); }
+int hs_config_load(const char* path) { try { Config::setParameterFile(path); return 0; } catch (std::exception& e) { g_err = e.what(); return -1; } }
+double hs_config_get(const char* k) { return Config::Get<double>(k); }
+int hs_config_get_int(const char* k) { return Config::Get<int>(k); }
+
+void* hs_camera_new() { return new CameraPtr(new Camera()); }
+
+void* hs_frame_new(void* cam, const uint8_t* img, int w, int h, const double* pose7)
+{
+    try {
+        Mat8 m(h, w, img, w);
+        auto* hf = new HsFrame{ FramePtr(new Frame(*static_cast<CameraPtr*>(cam), m, 0.0)), {} };
+        hf->f->Set_Pose(SE3(pose7));
+        return hf;
+    } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void hs_frame_free(void* f) { delete static_cast<HsFrame*>(f); }
+void hs_frame_set_pose(void* f, const double* pose7) { static_cast<HsFrame*>(f)->f->Set_Pose(SE3(pose7)); }
+void hs_frame_get_pose(void* f, double* pose7) { std::memcpy(pose7, static_cast<HsFrame*>(f)->f->Get_Pose().data(), 7 * sizeof(double)); }
+int hs_frame_level(void* f, int l, uint8_t* out)
+{
+    const Mat8& m = static_cast<HsFrame*>(f)->f->mvImg_Pyr[l];
+    for (int y = 0; y < m.rows; ++y) std::memcpy(out + (size_t)y * m.cols, m.data + (size_t)y * m.step, m.cols);
+    return m.rows * m.cols;
+}
+int hs_frame_n_features(void* f) { return (int)static_cast<HsFrame*>(f)->f->mvFeatures.size(); }
+void hs_frame_get_features(void* f, float* px, int* level, int* initial)
+{
+    const Features& fs = static_cast<HsFrame*>(f)->f->mvFeatures;
+    for (size_t i = 0; i < fs.size(); ++i) { px[2 * i] = fs[i]->mpx.x; px[2 * i + 1] = fs[i]->mpx.y; level[i] = fs[i]->mlevel; initial[i] = fs[i]->mbInitial; }
+}
+void hs_frame_mask(void* f, uint8_t* out)
+{
+    const Mat8& m = static_cast<HsFrame*>(f)->f->mImgMask;
+    if (!m.empty()) std::memcpy(out, m.data, (size_t)m.rows * m.cols);
+}
+
+// Feature_detector::detect as Initializer / CraeteKeyframe call it (ref: src/Initializer.cpp:44, src/Tracking.cpp:415-416)
+int hs_detect(void* f, double thr, int use_existing)
+{
+    try {
+        Feature_detector det;
+        Frame* fr = static_cast<HsFrame*>(f)->f.get();
+        if (use_existing) det.Set_ExistingFeatures(fr->mvFeatures);
+        det.detect(fr, thr);
+        return (int)fr->mvFeatures.size();
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// CreateInitialMapRGBD-like: bearing vectors + one MapPoint per feature with a non-zero world point
+void hs_frame_attach_points(void* f, const double* pts, const uint8_t* has)
+{
+    HsFrame* hf = static_cast<HsFrame*>(f);
+    Frame* fr = hf->f.get();
+    fr->mvMapPoints.assign(fr->mvFeatures.size(), nullptr);
+    for (size_t i = 0; i < fr->mvFeatures.size(); ++i) {
+        Feature* ft = fr->mvFeatures[i];
+        ft->mNormal = fr->mCamera->Pixel2Camera(ft->mpx, 1.0f);
+        ft->mNormal.normalize();
+        if (!has[i]) continue;
+        MapPoint* mp = new MapPoint(Vector3d(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+        hf->owned.push_back(mp);
+        ft->SetPose(mp);
+        fr->mvMapPoints[i] = mp;
+    }
+}
+
+int hs_sparse_align_run(int maxl, int minl, int iters, void* cur, void* ref, double* pose_out, dsdtm_iter_log* log, int cap, int* n_log)
+{
+    try {
+        Sprase_ImgAlign sa(maxl, minl, iters);
+        const int n = sa.Run(static_cast<HsFrame*>(cur)->f, static_cast<HsFrame*>(ref)->f);
+        std::memcpy(pose_out, static_cast<HsFrame*>(cur)->f->Get_Pose().data(), 7 * sizeof(double));
+        const auto& l = sa.LastLog();
+        *n_log = (int)l.size();
+        for (int i = 0; i < (int)l.size() && i < cap; ++i) log[i] = l[i];
+        return n;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+void* hs_keyframe_new(void* f)
+{
+    Frame* fr = static_cast<HsFrame*>(f)->f.get();
+    KeyFrame* kf = new KeyFrame(fr);
+    for (size_t i = 0; i < kf->mvFeatures.size(); ++i)
+        if (kf->mvFeatures[i]->Mpt) kf->mvFeatures[i]->Mpt->Add_Observation(kf, i);
+    return new HsKf{ kf };
+}
+
+// UpdateLocalMap + SearchLocalPoints (ref: src/Tracking.cpp:258-313,224): reproject the map points of `kf` into `cur`, then match.
+// found[i] (optional) presets MapPoint found-counts to exercise the per-cell ordering. Returns matches; new features are
+// appended to cur (read back with hs_frame_get_features).
+int hs_search_local_points(void* cam, void* cur, void* kf, const int* found, int* n_reprojected)
+{
+    try {
+        Feature_Alignment fa(*static_cast<CameraPtr*>(cam));
+        KeyFrame* k = static_cast<HsKf*>(kf)->kf;
+        FramePtr c = static_cast<HsFrame*>(cur)->f;
+        fa.ResetGrid();
+        int nr = 0;
+        for (size_t i = 0; i < k->mvFeatures.size(); ++i) {
+            MapPoint* mp = k->mvFeatures[i]->Mpt;
+            if (!mp) continue;
+            if (found) mp->IncreaseFound(found[i] - mp->Get_FoundNums());
+            if (fa.ReprojectPoint(c, mp)) nr++;
+        }
+        if (n_reprojected) *n_reprojected = nr;
+        fa.SearchLocalPoints(c);
+        return fa.LastMatches();
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+int hs_align2d_single(void* cur, int level, const uint8_t* patch10, int iters, double* px)
+{
+    try {
+        uint8_t p10[100], p8[64];
+        std::memcpy(p10, patch10, 100);
+        Vector2d v(px[0], px[1]);
+        const bool ok = Feature_Alignment::Align2DGaussNewton(static_cast<HsFrame*>(cur)->f, level, p10, p8, iters, v);
+        px[0] = v[0]; px[1] = v[1];
+        return ok ? 1 : 0;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+void hs_circle(uint8_t* img, int w, int h, float cx, float cy, int r, int color)
+{
+    Mat8 m(h, w, img, w);
+    circle(m, Point2f(cx, cy), r, (uchar)color);
+    std::memcpy(img, m.data, (size_t)w * h);
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""The drop-in boundary: the reference's class interfaces (DSDTM::Frame::ComputeImagePyramid, Feature_detector::detect,
+Sprase_ImgAlign::Run, Feature_Alignment::SearchLocalPoints) driven as Tracking drives them, checked against the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+import hostlib as HL
+import oracle as O
+from dsdtm_b200 import synth as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ CPU-side host logic
+def test_config_parser_reads_reference_style_yaml_with_conflict_markers(built, tmp_path):
+    y = tmp_path / "kinect.yaml"
+    y.write_text("%YAML:1.0\n# Camera Parameters\n<<<<<<< HEAD\nCamera.fx: 520.9\n=======\nCamera.fx: 517.306408\n>>>>>>> dev\n"
+                 "Camera.fy: 516.469215   # fr3\nCamera.width: 640\nCamera.MaxPyraLevels: 5\nCamera.f: 525\nname: \"kinect\"\n")
+    L = HL.lib()
+    L.hs_reset()
+    assert L.hs_config_load(str(y).encode()) == 0
+    assert L.hs_config_get(b"Camera.fx") == pytest.approx(517.306408)       # the later block wins, like a resolved merge
+    assert L.hs_config_get(b"Camera.fy") == pytest.approx(516.469215)
+    assert L.hs_config_get_int(b"Camera.width") == 640 and L.hs_config_get_int(b"Camera.MaxPyraLevels") == 5
+    assert L.hs_config_get_int(b"Camera.Missing") == 0                     # cv::FileStorage yields 0 for a missing node
+    assert L.hs_config_load(b"/nonexistent.yaml") == -1 and b"does not exist" in L.hs_last_error()
+
+
+def test_host_circle_matches_cv2_goldens(built, golden):
+    g = golden["circle_cv2"]
+    Hh, W = g["shape"]
+    for (cx, cy, r), bits in zip(g["cases"], g["masks"]):
+        m = np.full((Hh, W), 255, np.uint8)
+        HL.lib().hs_circle(HL._p(m), int(W), int(Hh), float(cx), float(cy), int(r), 0)
+        assert ((m == 0) == np.unpackbits(bits)[:Hh * W].reshape(Hh, W).astype(bool)).all(), (cx, cy, r)
+
+
+def test_host_adapters_fail_loudly_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cam_h = HL.configure(S.KINECT)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        HL.HFrame(cam_h, np.zeros((480, 640), np.uint8), S.IDENTITY)
+
+
+# ------------------------------------------------------------------------------------------------ GPU: the classes as Tracking calls them
+@pytest.fixture(scope="module")
+def rig(built, scenario):
+    cam_h = HL.configure(scenario["cam"], max_fts=300)
+    ref = HL.HFrame(cam_h, scenario["ref_img"], scenario["T_ref"])
+    cur = HL.HFrame(cam_h, scenario["cur_img"], scenario["T_ref"])       # cur.Set_Pose(last.Get_Pose()), ref: src/Tracking.cpp:201
+    return dict(cam=cam_h, ref=ref, cur=cur)
+
+
+@pytest.mark.gpu
+def test_frame_compute_image_pyramid(rig, scenario):
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    for l in range(5):
+        want = O.pyr_level(packed, offs, ws, hs, l)
+        assert (rig["ref"].level(l, want.shape) == want).all(), l
+
+
+@pytest.mark.gpu
+def test_feature_detector_detect_equals_reference_selection(rig, scenario):
+    """Initializer path: detect(frame, 5.0) on a fresh frame (ref: src/Initializer.cpp:44)."""
+    n = rig["ref"].detect(5.0)
+    px, lv, ini = rig["ref"].features()
+    want = scenario["corners"]
+    assert n == len(want) == 300
+    assert (px[:, 0] == want["x"]).all() and (px[:, 1] == want["y"]).all() and (lv == want["level"]).all()
+    assert not ini.any()
+    assert rig["ref"].mask().max() == 0            # mImgMask.release() at the end of detect (ref: :153)
+
+
+@pytest.mark.gpu
+def test_sprase_imgalign_run(rig, scenario):
+    """TrackWithLastFrame: Run(cur, last) (ref: src/Tracking.cpp:199-217) with map points attached to the ref features."""
+    ref, cur = rig["ref"], rig["cur"]
+    if HL.lib().hs_frame_n_features(ref.h) == 0:
+        ref.detect(5.0)
+    c = scenario["corners"]
+    pts = scenario["ref_points"][c["y"], c["x"]]
+    ref.attach_points(pts, np.ones(len(c), np.uint8))
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    for cfg in ((4, 0, 30), (5, 0, 8)):
+        cur.set_pose(scenario["T_ref"])
+        n, pose, log = HL.sparse_align_run(*cfg, cur, ref)
+        po, no, lo = O.sparse_align(H.ocam(scenario["cam"]), packed, scenario["cur_pyr"][0], offs, ws, hs, scenario["feats"],
+                                    scenario["ref_center"], S.IDENTITY, *cfg)
+        want = O.se3_mul(po, scenario["T_ref"])                      # ref: src/Sprase_ImageAlign.cpp:57
+        d = S.pose_dist(want, pose)
+        assert d[0] < 1e-5 and d[1] < 1e-5 and n == no
+        assert len(log) == len(lo) and all(abs(a["chi2"] - b["chi2"]) <= 1e-4 * abs(a["chi2"]) for a, b in zip(lo, log))
+        e = S.pose_dist(pose, scenario["T_cur"])
+        assert e[0] < 2e-4 and e[1] < 5e-4
+
+
+@pytest.mark.gpu
+def test_sprase_imgalign_too_few_features_returns_zero(built, scenario):
+    cam_h = HL.configure(scenario["cam"], min_fts=15)
+    ref = HL.HFrame(cam_h, scenario["ref_img"], S.IDENTITY)
+    cur = HL.HFrame(cam_h, scenario["cur_img"], S.IDENTITY)
+    n, pose, log = HL.sparse_align_run(4, 0, 30, cur, ref)              # ref frame has no features (< Camera.Min_fts)
+    assert n == 0 and len(log) == 0 and np.allclose(pose, S.IDENTITY)   # ref: src/Sprase_ImageAlign.cpp:34-38
+
+
+def _emulate_search_local_points(sc, kf_feats, cur_pose, found, cell=15, levels=5):
+    """SearchLocalPoints restated with oracle primitives (ref: src/Feature_alignment.cpp:54-158): reproject, bin, sort by
+    found count (stable list::sort), first match per cell, mask painting, stop at 200."""
+    cam = sc["cam"]; oc = H.ocam(cam)
+    w, h = cam["width"], cam["height"]
+    gcols = -(-w // cell)
+    cells = {}
+    fx, fy, cx, cy = (float(np.float32(cam[k])) for k in ("fx", "fy", "cx", "cy"))
+    for i, f in enumerate(kf_feats):
+        q = O.se3_act(cur_pose, f["point_w"])
+        px = np.array([fx * q[0] / q[2] + cx, fy * q[1] / q[2] + cy])
+        rx, ry = O.cvround(np.float32(px[0])), O.cvround(np.float32(px[1]))
+        if rx >= 8 and rx < w - 8 and ry >= 8 and ry < h - 8:
+            cells.setdefault(int(px[1] / cell) * gcols + int(px[0] / cell), []).append((i, px))
+    mask = np.full((h, w), 255, np.uint8)
+    packed, offs, ws, hs = sc["ref_pyr"]
+    cpacked = sc["cur_pyr"][0]
+    kf_center = sc["ref_center"]
+    T_c2r = O.se3_mul(cur_pose, O.se3_inv(sc["T_ref"]))
+    out = []
+    matches = 0
+    for k in sorted(cells):
+        cands = sorted(cells[k], key=lambda c: -found[c[0]])            # stable, like std::list::sort
+        for i, px in cands:
+            if mask[O.cvround(np.float32(px[1])), O.cvround(np.float32(px[0]))] != 255:
+                continue
+            f = kf_feats[i]
+            # Get_ClosetObs: one observation, cos angle between (kf centre - P) and (cur centre - P)
+            cur_center = O.se3_inv(cur_pose)[4:]
+            a = kf_center - f["point_w"]; b = cur_center - f["point_w"]
+            if np.dot(a / np.linalg.norm(a), b / np.linalg.norm(b)) < 0.5:
+                continue
+            L0 = int(f["level"])
+            rpx = f["px"] / np.float32(1 << L0)
+            if not (O.cvround(rpx[0]) >= 5 and O.cvround(rpx[0]) < w // (1 << L0) - 5 and O.cvround(rpx[1]) >= 5 and O.cvround(rpx[1]) < h // (1 << L0) - 5):
+                continue
+            A = O.solve_affine(oc, kf_center, f["point_w"], f["normal"], f["px"], L0, T_c2r)
+            SL = O.best_search_level(A, levels - 3)
+            patch = O.warp_affine(A, O.pyr_level(packed, offs, ws, hs, L0), f["px"], L0, SL)
+            p, conv, _ = O.align2d(O.pyr_level(cpacked, offs, ws, hs, SL), patch, 10, px / (1 << SL))
+            p = p * (1 << SL)
+            if not conv:
+                continue
+            out.append((i, p, SL))
+            cx_, cy_ = O.cvround(np.float32(p[0])), O.cvround(np.float32(p[1]))
+            O.circle_fill(mask, cx_, cy_, cell, 0)
+            matches += 1
+            break
+        if matches >= 200:
+            break
+    return out, mask
+
+
+@pytest.mark.gpu
+def test_feature_alignment_search_local_points(built, scenario):
+    """TrackWithLocalMap: UpdateLocalMap's ReprojectPoint loop + SearchLocalPoints (ref: src/Tracking.cpp:219-313) against a
+    one-keyframe map; the speculative GPU batch + host replay must reproduce the reference's sequential greedy matching."""
+    sc = scenario
+    cam_h = HL.configure(sc["cam"], max_fts=300)
+    ref = HL.HFrame(cam_h, sc["ref_img"], sc["T_ref"])
+    assert ref.detect(5.0) == 300
+    c = sc["corners"]
+    ref.attach_points(sc["ref_points"][c["y"], c["x"]], np.ones(len(c), np.uint8))
+    kf = HL.lib().hs_keyframe_new(ref.h)
+    cur = HL.HFrame(cam_h, sc["cur_img"], sc["T_cur"])                   # pose after sparse alignment ~ ground truth
+    rng = np.random.default_rng(5)
+    found = rng.integers(1, 6, len(c)).astype(np.int32)
+    nrep = C.c_int(0)
+    m = HL.lib().hs_search_local_points(cam_h, cur.h, kf, HL._p(found), C.byref(nrep))
+    assert m >= 0, HL.lib().hs_last_error()
+    px, lv, ini = cur.features()
+    want, want_mask = _emulate_search_local_points(sc, sc["feats"], sc["T_cur"], found)
+    assert m == len(want) == len(px) and m > 100 and m <= 200
+    for (i, p, SL), gp, gl in zip(want, px, lv):
+        assert gl == SL and np.abs(np.float32(p) - gp).max() <= 1e-3      # refined feature position tolerance (north_star)
+    assert ini.all()
+    assert (cur.mask() == want_mask).all()
+    # refined positions land on the true reprojections
+    truth = np.array([want_i[1] for want_i in want])
+    assert np.median(np.linalg.norm(px - truth, axis=1)) < 1e-3
