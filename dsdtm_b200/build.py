@@ -17,6 +17,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
 
 
+def extra_flags():
+    """DSDTM_NVCC_FLAGS lets experiments add -D switches (e.g. on the GPU box) without editing sources."""
+    return os.environ.get("DSDTM_NVCC_FLAGS", "").split()
+
+
 def nvcc():
     p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(p):
@@ -47,7 +52,7 @@ def build(force=False, verbose=False):
         o = os.path.join(LIBDIR, s.replace(".cu", ".o"))
         src = os.path.join(CSRC, s)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(p) for p in (src, _deps()[-1], _deps()[-2])):
-            cmd = [nvcc()] + NVCC_FLAGS + ["-c", src, "-o", o]
+            cmd = [nvcc()] + NVCC_FLAGS + extra_flags() + ["-c", src, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log.append(r.stderr)
             if r.returncode != 0:

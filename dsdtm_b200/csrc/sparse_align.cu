@@ -139,8 +139,15 @@ __device__ __noinline__ void pose_update(const double* T, const double (&x)[6], 
 
 struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 
+#ifndef DSDTM_SA_PIPELINE
+#define DSDTM_SA_PIPELINE 0      // 1 = issue feature k+1's gather before feature k's arithmetic. Measured slower (1.22 vs 1.12 ms, profiles/r1_sparse_align_v3.md): registers
+#endif
+#ifndef DSDTM_SA_MINB4
+#define DSDTM_SA_MINB4 3         // resident CTAs per SM the 4-warp variant is compiled for (register cap 65536 / (128 * MINB4))
+#endif
+
 template <int WPP>
-__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? 3 : 1)) sparse_align_kernel(const SaArgs a)
+__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_SA_MINB4 : 1)) sparse_align_kernel(const SaArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int NF = a.nf;
@@ -327,6 +334,15 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? 3 : 1))
             };
 
             auto run_pass = [&](auto first_tag) {
+#if !DSDTM_SA_PIPELINE
+                int kq = 0;
+                for (int f = tid; f < nfeat; f += NT, ++kq) {
+                    Pre me;
+                    stage1(f, me);
+                    stage2(first_tag, f, kq, me);
+                }
+                return;
+#endif
                 Pre cur;
                 cur.valid = false; cur.vis = false;
                 int k = -1;
