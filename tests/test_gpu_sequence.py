@@ -1,0 +1,191 @@
+"""configs[3] / configs[4] of BASELINE.json at test scale.
+
+* test_tracking_front_end_sequence: the front-end calls of Tracking (ref: src/Tracking.cpp:45-145,199-313,412-464) over a
+  synthetic RGB-D sequence at TUM shape through the C++ adapters -- pyramid, FAST + grid selection on keyframes, sparse
+  alignment against the last frame, reprojection + feature alignment against the keyframe map -- checked frame by frame
+  against the same loop restated with the oracle. (The 1000-frame length of configs[3] is a bench-scale number; parity is
+  per frame, so a short sequence exercises every transition: init keyframe, tracking, new keyframe.)
+* test_batched_sweep_752x480: configs[4] at reduced count -- independent EuRoC-geometry pairs through the batched entry
+  point, each pair against the oracle, plus the size-independent properties used at full size (batch == singles,
+  permutation invariance, determinism)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers as H
+import hostlib as HL
+import oracle as O
+from dsdtm_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+LEVELS, CELL = 5, 15
+
+
+def _trajectory(n, seed=3):
+    rng = np.random.default_rng(seed)
+    v = np.concatenate([rng.uniform(-0.012, 0.012, 3), np.deg2rad(rng.uniform(-0.3, 0.3, 3))])
+    poses = [S.IDENTITY.copy()]
+    for k in range(1, n):
+        step = v * (1.0 + 0.2 * np.sin(0.7 * k))
+        poses.append(S.pose_mul(S.pose_from_xi(step), poses[-1]))
+    return poses
+
+
+class OracleFrame:
+    def __init__(self, img, pose):
+        self.img = img
+        self.pyr = O.pyramid(img, LEVELS)
+        self.pose = np.array(pose)
+        self.feats = np.zeros(0, O.REF_FEAT_DT)       # features with map points (px, level, normal, point_w)
+
+
+def _oracle_sparse_align(oc, cur, ref, cfg):
+    packed, offs, ws, hs = ref.pyr
+    center = O.se3_inv(ref.pose)[4:]
+    T0 = O.se3_mul(cur.pose, O.se3_inv(ref.pose))
+    po, n, log = O.sparse_align(oc, packed, cur.pyr[0], offs, ws, hs, ref.feats, center, T0, *cfg)
+    return O.se3_mul(po, ref.pose), n
+
+
+def _oracle_search(oc, cam, cur, kf, found):
+    """SearchLocalPoints against a one-keyframe map, restated with oracle primitives (ref: src/Feature_alignment.cpp:54-158)."""
+    w, h = cam["width"], cam["height"]
+    gcols = -(-w // CELL)
+    fx, fy, cx, cy = (float(np.float32(cam[k])) for k in ("fx", "fy", "cx", "cy"))
+    cells = {}
+    for i, f in enumerate(kf.feats):
+        q = O.se3_act(cur.pose, f["point_w"])
+        px = np.array([fx * q[0] / q[2] + cx, fy * q[1] / q[2] + cy])
+        rx, ry = O.cvround(np.float32(px[0])), O.cvround(np.float32(px[1]))
+        if 8 <= rx < w - 8 and 8 <= ry < h - 8:
+            cells.setdefault(int(px[1] / CELL) * gcols + int(px[0] / CELL), []).append((i, px))
+    mask = np.full((h, w), 255, np.uint8)
+    packed, offs, ws, hs = kf.pyr
+    kf_center = O.se3_inv(kf.pose)[4:]
+    cur_center = O.se3_inv(cur.pose)[4:]
+    T_c2r = O.se3_mul(cur.pose, O.se3_inv(kf.pose))
+    out = []
+    for k in sorted(cells):
+        for i, px in sorted(cells[k], key=lambda c: -found[c[0]]):
+            if mask[O.cvround(np.float32(px[1])), O.cvround(np.float32(px[0]))] != 255:
+                continue
+            f = kf.feats[i]
+            a = kf_center - f["point_w"]; b = cur_center - f["point_w"]
+            if np.dot(a / np.linalg.norm(a), b / np.linalg.norm(b)) < 0.5:
+                continue
+            L0 = int(f["level"])
+            rpx = f["px"] / np.float32(1 << L0)
+            if not (5 <= O.cvround(rpx[0]) < w // (1 << L0) - 5 and 5 <= O.cvround(rpx[1]) < h // (1 << L0) - 5):
+                continue
+            A = O.solve_affine(oc, kf_center, f["point_w"], f["normal"], f["px"], L0, T_c2r)
+            SL = O.best_search_level(A, LEVELS - 3)
+            patch = O.warp_affine(A, O.pyr_level(packed, offs, ws, hs, L0), f["px"], L0, SL)
+            p, conv, _ = O.align2d(O.pyr_level(cur.pyr[0], offs, ws, hs, SL), patch, 10, px / (1 << SL))
+            p = p * (1 << SL)
+            if not conv:
+                continue
+            out.append((i, np.float32(p), SL))
+            O.circle_fill(mask, O.cvround(np.float32(p[0])), O.cvround(np.float32(p[1])), CELL, 0)
+            break
+        if len(out) >= 200:
+            break
+    return out
+
+
+def test_tracking_front_end_sequence(built):
+    cam = dict(S.KINECT)
+    oc = H.ocam(cam)
+    scene = S.Scene(77)
+    n_frames = 7
+    poses = _trajectory(n_frames)
+    cam_h = HL.configure(cam, max_fts=300, max_frames=16)
+    cfg = (5, 0, 8)                                       # production ctor (ref: src/Tracking.cpp:37)
+
+    # ---- frame 0: Initializer::Init_RGBDCam = detect + map points from depth (ref: src/Initializer.cpp:40-57,147-196)
+    img0, _, pts0 = S.render(scene, cam, poses[0], want_points=True)
+    g0 = HL.HFrame(cam_h, img0, poses[0])
+    assert g0.detect(5.0) == 300
+    px0, lv0, _ = g0.features()
+    o0 = OracleFrame(img0, poses[0])
+    corners, _ = H.detect_oracle(img0, LEVELS, CELL, 300)
+    assert (px0[:, 0] == corners["x"]).all() and (px0[:, 1] == corners["y"]).all() and (lv0 == corners["level"]).all()
+    world = pts0[corners["y"], corners["x"]]
+    g0.attach_points(world, np.ones(len(corners), np.uint8))
+    o0.feats = H.ref_feats_from_corners(cam, corners, pts0)
+    kf_h = HL.lib().hs_keyframe_new(g0.h)
+    o_kf = o0
+    found = np.ones(len(corners), np.int32)
+
+    g_last, o_last = g0, o0
+    for k in range(1, n_frames):
+        img, _ = S.render(scene, cam, poses[k])
+        # Track_RGBDCam: new Frame (pyramid), cur.Set_Pose(last.Get_Pose()), Run(cur, last)  (ref: src/Tracking.cpp:57,199-205)
+        g_cur = HL.HFrame(cam_h, img, g_last.pose())
+        o_cur = OracleFrame(img, o_last.pose)
+        for l in range(LEVELS):
+            packed, offs, ws, hs = o_cur.pyr
+            assert (g_cur.level(l, (hs[l], ws[l])) == O.pyr_level(packed, offs, ws, hs, l)).all()
+        n_g, pose_g, _ = HL.sparse_align_run(*cfg, g_cur, g_last)
+        pose_o, n_o = _oracle_sparse_align(oc, o_cur, o_last, cfg)
+        o_cur.pose = pose_o
+        d = S.pose_dist(pose_o, pose_g)
+        assert d[0] < 1e-5 and d[1] < 1e-5 and n_g == n_o and n_g >= 20, (k, d, n_g, n_o)      # < 20 would mean Lost (ref: :208)
+        e = S.pose_dist(pose_g, poses[k])
+        assert e[0] < 1e-3 and e[1] < 3e-3, (k, e)
+        # TrackWithLocalMap: reproject the keyframe's map points, SearchLocalPoints (ref: :219-313)
+        nrep = C.c_int(0)
+        m = HL.lib().hs_search_local_points(cam_h, g_cur.h, kf_h, HL._p(found), C.byref(nrep))
+        want = _oracle_search(oc, cam, o_cur, o_kf, found)
+        px, lv, ini = g_cur.features()
+        assert m == len(want) == len(px) and m > 100, (k, m, len(want))
+        for (i, p, SL), gp, gl in zip(want, px, lv):
+            assert gl == SL and np.abs(p - gp).max() <= 1e-3
+        # MapPoint::IncreaseFound on every match (ref: src/Feature_alignment.cpp:106); the matched features become the next
+        # frame's reference features (px refined, level, bearing from px, same map point)
+        F = np.zeros(len(want), O.REF_FEAT_DT)
+        for j, (i, p, SL) in enumerate(want):
+            found[i] += 1
+            F[j]["px"] = px[j]; F[j]["level"] = SL; F[j]["initial"] = 1
+            F[j]["normal"] = O.feature_normal(oc, px[j]); F[j]["point_w"] = o_kf.feats[i]["point_w"]
+        o_cur.feats = F
+        g_last, o_last = g_cur, o_cur
+
+
+def test_batched_sweep_752x480(built):
+    from dsdtm_b200 import capi
+    cam = dict(S.EUROC)
+    n, stride = 6, 320
+    ctx = capi.Context(cam, levels=5, cell_size=15, max_feats=stride, max_patches=8, max_frames=2 * n, max_batch=n)
+    assert ctx.ws == [752, 376, 188, 94, 47] and ctx.hs == [480, 240, 120, 60, 30]        # SURVEY 3.5 (tile kernel for 94, 47)
+    scs = [H.make_scenario(100 + i, cam) for i in range(3)]
+    feats = np.zeros((n, stride), O.REF_FEAT_DT); nf = np.zeros(n, np.int32)
+    centers = np.zeros((n, 3)); poses = np.tile(S.IDENTITY, (n, 1))
+    rng = np.random.default_rng(1)
+    for i in range(n):
+        sc = scs[i % 3]
+        ctx.upload(2 * i, sc["ref_img"]); ctx.upload(2 * i + 1, sc["cur_img"])
+        nf[i] = len(sc["feats"]); feats[i, :nf[i]] = sc["feats"]; centers[i] = sc["ref_center"]
+        if i >= 3:
+            poses[i] = S.pose_from_xi(rng.uniform(-0.003, 0.003, 6))
+    for l in range(5):
+        packed, offs, ws, hs = scs[0]["cur_pyr"]
+        assert (ctx.download_level(1, l) == O.pyr_level(packed, offs, ws, hs, l)).all()
+    ref_slots = 2 * np.arange(n); cur_slots = ref_slots + 1
+    pb, tb, log, nlog = ctx.sparse_align_batch(ref_slots, cur_slots, feats, nf, centers, poses, 5, 0, 8, log_cap=64)
+    for i in range(n):
+        sc = scs[i % 3]
+        packed, offs, ws, hs = sc["ref_pyr"]
+        po, no, lo = O.sparse_align(H.ocam(cam), packed, sc["cur_pyr"][0], offs, ws, hs, sc["feats"], sc["ref_center"], poses[i], 5, 0, 8)
+        d = S.pose_dist(po, pb[i])
+        assert d[0] < 1e-5 and d[1] < 1e-5 and no == tb[i]
+        assert len(lo) == nlog[i] and all(abs(a["chi2"] - b["chi2"]) <= 1e-4 * abs(a["chi2"]) for a, b in zip(lo, log[i]))
+        e = S.pose_dist(pb[i], sc["T_c2r"])
+        assert e[0] < 3e-4 and e[1] < 1e-3
+    # size-independent properties (what the full 4096-pair sweep is checked with): permutation invariance and determinism
+    perm = rng.permutation(n)
+    pp, tp, _, _ = ctx.sparse_align_batch(ref_slots[perm], cur_slots[perm], feats[perm], nf[perm], centers[perm], poses[perm], 5, 0, 8)
+    assert (pp == pb[perm]).all() and (tp == tb[perm]).all()
+    p2, t2, _, _ = ctx.sparse_align_batch(ref_slots, cur_slots, feats, nf, centers, poses, 5, 0, 8)
+    assert (p2 == pb).all()
+    ctx.close()
