@@ -11,7 +11,7 @@
 //
 // Work decomposition (v2; v1 used one 512-thread CTA per tile with five __syncthreads phases and spent most of its time at
 // those barriers, profiles/r1_pyramid_fast_align2d.md): one WARP per 32x16 tile of one level of one frame, four independent
-// warps per CTA, no CTA barrier at all (tile table covers all levels, grid.y = frame). The (32+16)x(16+10) halo tile is
+// warps per CTA, no CTA barrier at all (tile table covers all levels, grid.y = frame). The 48x26 halo tile is
 // staged in the warp's slice of shared memory with 8-byte row loads. Phase A rejects most pixels with the two opposite-pair
 // tests (any 10-arc contains >= 1 of each opposite ring pair); survivors are compacted with ballot + popc into a small
 // per-warp queue and phase B (ring masks, 10-arc bit test, closed-form score) runs on batches of 32 candidates, one per
@@ -23,13 +23,12 @@ namespace dsdtm {
 
 namespace {
 
-constexpr int FT_W = 32, FT_H = 16;        // interior tile
+constexpr int FT_W = 30, FT_H = 16;        // interior tile: 30 wide so that interior + 1-px non-max ring = 32 columns = one lane each
 constexpr int HALO = 5;                    // shi-tomasi needs +-5, fast score of the 1-px nonmax ring needs +-4
-constexpr int XOFF = 8;                    // staged columns start at x0 - 8 (8-byte aligned row loads)
-constexpr int SMP = 48;                    // staged row pitch = staged columns (x0-8 .. x0+39)
+constexpr int SMP = 48;                    // staged row pitch = staged columns [xa, xa+48), xa = (x0-5) rounded down to 8
 constexpr int SMH = FT_H + 2 * HALO;       // 26 staged rows (y0-5 .. y0+20)
-constexpr int SC_W = FT_W + 2, SC_H = FT_H + 2;   // score tile incl. 1-px ring
-constexpr int SC_P = 36;                   // score row pitch
+constexpr int SC_W = FT_W + 2, SC_H = FT_H + 2;   // score tile incl. 1-px ring: 32 x 18
+constexpr int SC_P = 32;                   // score row pitch
 constexpr int WARPS = 4;
 constexpr int QCAP = 64;
 
@@ -70,6 +69,7 @@ struct FastArgs {
     const uint8_t* occupied;             // n * n_cells or null
     unsigned long long* cells;           // n * n_cells keys
     int n_cells, grid_cols, cell_size;
+    unsigned cell_magic;                 // floor(2^32 / cell_size) + 1: exact x / cell_size for x < 65536 via __umulhi
     // score-map mode (parity helper): single level, dense outputs
     uint8_t* score_out; uint8_t* nonmax_out;
 };
@@ -81,10 +81,10 @@ struct WarpSmem {
 };
 
 // phase B for one candidate position i (index into the 18x34 score region)
-__device__ __forceinline__ void score_candidate(WarpSmem& sm, int i, int b)
+__device__ __forceinline__ void score_candidate(WarpSmem& sm, int i, int b, int xoff)
 {
-    const int r = i / SC_W, c = i - r * SC_W;
-    const int sr = r + HALO - 1, sc = c + XOFF - 1;
+    const int r = i >> 5, c = i & 31;
+    const int sr = r + HALO - 1, sc = c + xoff - 1;
     const int p = sm.img[sr][sc];
     int d[16];
     unsigned bright = 0, dark = 0;
@@ -117,11 +117,13 @@ __global__ void __launch_bounds__(32 * WARPS) fast_kernel(const FastArgs a)
     const uint8_t* __restrict__ img = a.frames + (size_t)(a.first_slot + frame) * a.frame_stride + a.geo.off[L];
     const int x0 = txi * FT_W, y0 = tyi * FT_H;
 
-    // ---- stage the halo tile: rows y0-5 .. y0+20, cols x0-8 .. x0+39 (zero outside the image)
+    // ---- stage the halo tile: rows y0-5 .. y0+20, cols [xa, xa+48) with xa = (x0-5) & ~7 (zero outside the image)
+    const int xa = (x0 - HALO) & ~7;           // arithmetic: -5 -> -8
+    const int xoff = x0 - xa;                  // column of x0 inside the staged tile (5..12)
     if ((w & 7) == 0) {
         for (int i = lane; i < SMH * (SMP / 8); i += 32) {
             const int r = i / (SMP / 8), sgm = i - r * (SMP / 8);
-            const int y = y0 - HALO + r, x = x0 - XOFF + 8 * sgm;
+            const int y = y0 - HALO + r, x = xa + 8 * sgm;
             uint2 v = make_uint2(0u, 0u);
             if (y >= 0 && y < h && x >= 0 && x < w) v = __ldg(reinterpret_cast<const uint2*>(img + (size_t)y * w + x));
             *reinterpret_cast<uint2*>(&sm.img[r][8 * sgm]) = v;
@@ -129,61 +131,67 @@ __global__ void __launch_bounds__(32 * WARPS) fast_kernel(const FastArgs a)
     } else {
         for (int i = lane; i < SMH * SMP; i += 32) {
             const int r = i / SMP, c = i - r * SMP;
-            const int y = y0 - HALO + r, x = x0 - XOFF + c;
+            const int y = y0 - HALO + r, x = xa + c;
             sm.img[r][c] = (x >= 0 && x < w && y >= 0 && y < h) ? __ldg(img + (size_t)y * w + x) : (uint8_t)0;
         }
     }
     for (int i = lane; i < SC_H * SC_P / 4; i += 32) reinterpret_cast<uint32_t*>(&sm.score[0][0])[i] = 0u;
     __syncwarp();
 
-    // ---- phase A (quick reject over the (32+2)x(16+2) score region) + warp-level compaction + phase B on full batches
+    // ---- phase A (quick reject; lane = column of the 32-wide score region, one row per iteration) + warp-level compaction
+    //      + phase B on full batches of 32 candidates
     const int b = a.barrier;
     int qn = 0;
-    for (int base = 0; base < SC_H * SC_W; base += 32) {
-        const int i = base + lane;
-        bool cand = false;
-        if (i < SC_H * SC_W) {
-            const int r = i / SC_W, c = i - r * SC_W;
-            const int y = y0 - 1 + r, x = x0 - 1 + c;
-            if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {     // ref: fast_10.cpp:36,41 scan bounds
-                const int sr = r + HALO - 1, sc = c + XOFF - 1;
+    {
+        const int c = lane;
+        const int x = x0 - 1 + c;
+        const bool xok = x >= 3 && x < w - 3;                         // ref: fast_10.cpp:41 scan bounds
+        const int sc = c + xoff - 1;
+        for (int r = 0; r < SC_H; ++r) {
+            const int y = y0 - 1 + r;
+            bool cand = false;
+            if (xok && y >= 3 && y < h - 3) {                         // ref: fast_10.cpp:36
+                const int sr = r + HALO - 1;
                 const int p = sm.img[sr][sc];
                 const int d0 = sm.img[sr + 3][sc] - p, d8 = sm.img[sr - 3][sc] - p;
                 const int d4 = sm.img[sr][sc + 3] - p, d12 = sm.img[sr][sc - 3] - p;
-                const bool br = (d0 > b || d8 > b) && (d4 > b || d12 > b);
-                const bool dk = (d0 < -b || d8 < -b) && (d4 < -b || d12 < -b);
-                cand = br || dk;
+                // bright: (d0 > b || d8 > b) && (d4 > b || d12 > b);  dark: the same with < -b
+                cand = (min(max(d0, d8), max(d4, d12)) > b) || (max(min(d0, d8), min(d4, d12)) < -b);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (cand) sm.queue[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(r * 32 + c);
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                score_candidate(sm, sm.queue[lane], b, xoff);
+                __syncwarp();
+                const unsigned short carry = (lane < qn - 32) ? sm.queue[32 + lane] : (unsigned short)0;
+                __syncwarp();
+                if (lane < qn - 32) sm.queue[lane] = carry;
+                qn -= 32;
+                __syncwarp();
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (cand) sm.queue[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
-        qn += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-            score_candidate(sm, sm.queue[lane], b);
-            __syncwarp();
-            const unsigned short carry = (lane < qn - 32) ? sm.queue[32 + lane] : (unsigned short)0;
-            __syncwarp();
-            if (lane < qn - 32) sm.queue[lane] = carry;
-            qn -= 32;
-            __syncwarp();
-        }
     }
-    if (lane < qn) score_candidate(sm, sm.queue[lane], b);
+    if (lane < qn) score_candidate(sm, sm.queue[lane], b, xoff);
     __syncwarp();
 
-    // ---- non-max over the interior, row by row (lane = column); survivors handled by the whole warp
+    // ---- non-max over the interior, row by row. Lane c owns score column c (0..31); a sliding 3-row window of its column
+    //      lives in one register (3 bytes), the left / right columns arrive by shuffle. Interior columns are lanes 1..30.
+    const int c = lane;
+    const int x = x0 - 1 + c;
+    unsigned col = (unsigned)sm.score[0][c] | ((unsigned)sm.score[1][c] << 8);      // rows r, r+1 of the window (bytes 0, 1)
     for (int r = 0; r < FT_H; ++r) {
-        const int c = lane;
-        const int y = y0 + r, x = x0 + c;
-        const int s = sm.score[r + 1][c + 1];
-        bool keep = false;
-        if (s > 0 && x < w && y < h) {
-            keep = sm.score[r][c] < s && sm.score[r][c + 1] < s && sm.score[r][c + 2] < s && sm.score[r + 1][c] < s &&
-                   sm.score[r + 1][c + 2] < s && sm.score[r + 2][c] < s && sm.score[r + 2][c + 1] < s && sm.score[r + 2][c + 2] < s;
-        }
+        const int y = y0 + r;
+        col |= (unsigned)sm.score[r + 2][c] << 16;                                  // byte 2 = row r+2
+        const int s0 = col & 0xFF, s = (col >> 8) & 0xFF, s2 = (col >> 16) & 0xFF;
+        const int own02 = max(s0, s2);                       // the two vertical neighbours
+        const int col3 = max(own02, s);                      // column maximum, handed to the left / right lanes
+        const int nb = max(max(__shfl_up_sync(0xffffffffu, col3, 1), __shfl_down_sync(0xffffffffu, col3, 1)), own02);
+        const bool keep = (c >= 1) && (c <= FT_W) && s > 0 && x < w && y < h && nb < s;
+        col >>= 8;
         if (a.score_out) {
-            if (x < w && y < h) {
+            if (c >= 1 && c <= FT_W && x < w && y < h) {
                 a.score_out[(size_t)y * w + x] = (uint8_t)s;
                 a.nonmax_out[(size_t)y * w + x] = keep ? 1 : 0;
             }
@@ -191,10 +199,10 @@ __global__ void __launch_bounds__(32 * WARPS) fast_kernel(const FastArgs a)
         }
         unsigned km = __ballot_sync(0xffffffffu, keep);
         while (km) {
-            const int cc = __ffs(km) - 1;
+            const int cc = __ffs(km) - 1;               // score column of the corner; image x = x0 - 1 + cc
             km &= km - 1;
-            const int xx = x0 + cc;
-            const int k = ((y << L) / a.cell_size) * a.grid_cols + (xx << L) / a.cell_size;      // ref: Feature_detection.cpp:97-98
+            const int xx = x0 - 1 + cc;
+            const int k = (int)__umulhi((unsigned)(y << L), a.cell_magic) * a.grid_cols + (int)__umulhi((unsigned)(xx << L), a.cell_magic);   // ref: Feature_detection.cpp:97-98
             if (a.occupied && a.occupied[(size_t)frame * a.n_cells + k]) continue;               // ref: :100
             float score = 0.f;
             // ref: :172 "patch too close to the boundary" -> 0
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(32 * WARPS) fast_kernel(const FastArgs a)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int pix = lane + 32 * e;                 // 8x8 box: rows y-4..y+3, cols x-4..x+3
-                    const int sr = r + HALO - 4 + (pix >> 3), sc = cc + XOFF - 4 + (pix & 7);
+                    const int sr = r + HALO - 4 + (pix >> 3), sc = cc - 1 + xoff - 4 + (pix & 7);
                     const int dx = (int)sm.img[sr][sc + 1] - (int)sm.img[sr][sc - 1];
                     const int dy = (int)sm.img[sr + 1][sc] - (int)sm.img[sr - 1][sc];
                     sxx += dx * dx; syy += dy * dy; sxy += dx * dy;
@@ -236,6 +244,7 @@ FastArgs make_args(dsdtm_ctx* c, int first_slot)
     a.tiles = c->fast_tiles_d; a.n_tiles = c->n_fast_tiles; a.geo = c->geo;
     a.barrier = 20; a.seed_score = 0;
     a.occupied = nullptr; a.cells = c->cells_d; a.n_cells = c->n_cells; a.grid_cols = c->grid_cols; a.cell_size = c->prm.cell_size;
+    a.cell_magic = (unsigned)(0x100000000ull / (unsigned)c->prm.cell_size) + 1u;
     a.score_out = nullptr; a.nonmax_out = nullptr;
     return a;
 }

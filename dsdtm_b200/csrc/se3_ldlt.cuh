@@ -166,6 +166,61 @@ DSDTM_HD bool ldlt6_solve_spd(const double (&A)[6][6], const double (&b)[6], dou
     return ok;
 }
 
+// Split form of ldlt6_solve_spd for callers that reuse one factorisation for several right-hand sides (the sparse-alignment
+// H only changes when the visibility set changes): factor once into 15 strictly-lower entries of L (row-major packed) and the
+// 6 pivots d, then substitute per right-hand side. Same arithmetic and operation order as ldlt6_solve_spd.
+DSDTM_HD bool ldlt6_factor_spd(const double (&A)[6][6], double (&Lp)[15], double (&d)[6])
+{
+    double L[6][6];
+    double maxdiag = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) maxdiag = fmax(maxdiag, fabs(A[i][i]));
+    const double thresh = 1e-11 * maxdiag;
+    bool ok = maxdiag > 0.0 && maxdiag < 1.7976931348623157e308;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double dk = A[k][k];
+#pragma unroll
+        for (int j = 0; j < k; ++j) dk -= L[k][j] * L[k][j] * d[j];
+        d[k] = dk;
+        ok = ok && (dk > thresh);
+        const double inv = 1.0 / dk;
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            double v = A[i][k];
+#pragma unroll
+            for (int j = 0; j < k; ++j) v -= L[i][j] * L[k][j] * d[j];
+            L[i][k] = v * inv;
+        }
+    }
+#pragma unroll
+    for (int i = 1; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) Lp[i * (i - 1) / 2 + j] = L[i][j];
+    return ok;
+}
+
+DSDTM_HD void ldlt6_subst_spd(const double (&Lp)[15], const double (&d)[6], const double (&b)[6], double (&x)[6])
+{
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = b[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) v -= Lp[i * (i - 1) / 2 + j] * y[j];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = y[i] / d[i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) v -= Lp[j * (j - 1) / 2 + i] * x[j];
+        x[i] = v;
+    }
+}
+
 struct Quat { double w, x, y, z; };
 
 // out = T * exp(x); pose7 = {qw,qx,qy,qz,tx,ty,tz}. (ref: src/Sprase_ImageAlign.cpp:335; Sophus SE3::exp, SE3::operator*=)

@@ -116,15 +116,39 @@ struct RefRows {
 };
 
 // the serial tail of one GN iteration, kept out of line: it runs on one lane once per iteration and must not bloat
-// (or evict from the instruction cache) the per-feature loop
-__device__ __noinline__ void solve_and_update(const double* __restrict__ sH /*21 packed*/, const double (&bvec)[6], double (&x)[6])
+// (or evict from the instruction cache) the per-feature loop. H only changes when the visibility set changes, so the
+// factorisation is cached in shared memory (sF: 15 entries of L, 6 pivots, 1 flag) and most iterations only substitute.
+__device__ __noinline__ void solve_and_update(const double* __restrict__ sH /*21 packed*/, double* __restrict__ sF /*22*/, bool refactor,
+                                              const double (&bvec)[6], double (&x)[6])
 {
-    double Hm[6][6];
+    if (refactor) {
+        double Hm[6][6], Lp[15], d[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+        for (int r = 0; r < 6; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) { Hm[r][c] = sH[r * (r + 1) / 2 + c]; Hm[c][r] = Hm[r][c]; }
-    if (!ldlt6_solve_spd(Hm, bvec, x)) ldlt6_solve_reg(Hm, bvec, x);       // ref: :318 (Eigen ldlt().solve)
+            for (int c = 0; c <= r; ++c) { Hm[r][c] = sH[r * (r + 1) / 2 + c]; Hm[c][r] = Hm[r][c]; }
+        const bool ok = ldlt6_factor_spd(Hm, Lp, d);
+#pragma unroll
+        for (int i = 0; i < 15; ++i) sF[i] = Lp[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sF[15 + i] = d[i];
+        sF[21] = ok ? 1.0 : 0.0;
+    }
+    if (sF[21] != 0.0) {
+        double Lp[15], d[6];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) Lp[i] = sF[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) d[i] = sF[15 + i];
+        ldlt6_subst_spd(Lp, d, bvec, x);                                   // ref: :318 (Eigen ldlt().solve), SPD fast path
+    } else {
+        double Hm[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) { Hm[r][c] = sH[r * (r + 1) / 2 + c]; Hm[c][r] = Hm[r][c]; }
+        ldlt6_solve_reg(Hm, bvec, x);                                      // Eigen's pivoted LDL^T incl. its zero-pivot rule
+    }
 }
 
 __device__ __noinline__ void pose_update(const double* T, const double (&x)[6], double* Tn)
@@ -147,7 +171,7 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 #endif
 
 template <int WPP>
-__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_SA_MINB4 : 1)) sparse_align_kernel(const SaArgs a)
+__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_SA_MINB4 : (WPP == 5 ? 3 : 1))) sparse_align_kernel(const SaArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int NF = a.nf;
@@ -160,6 +184,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_S
     __shared__ int s_cnt[WPP];
     __shared__ double s_redH[WPP][22];
     __shared__ double s_H[21];
+    __shared__ double s_F[22];
     __shared__ double s_T[7], s_Told[7];
     __shared__ double s_chi2prev;
     __shared__ int s_stop, s_npts, s_nlog;
@@ -416,7 +441,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_S
                     const double chi2New = accc / (double)(16 * cnt);                      // ref: :298 (NaN if nothing visible)
                     const double bvec[6] = { acc0, acc1, acc2, acc3, acc4, acc5 };
                     double x[6];
-                    solve_and_update(s_H, bvec, x);                                        // ref: :318
+                    solve_and_update(s_H, s_F, need_H != 0, bvec, x);                      // ref: :318
                     int flags = 0;
                     bool stop = false;
                     if (isnan(x[0])) { stop = true; flags |= 4; }                          // ref: :321-326
@@ -488,6 +513,7 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
     cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
@@ -521,6 +547,7 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
     case 1: return launch<1>(a, n_pairs, s);
     case 2: return launch<2>(a, n_pairs, s);
     case 4: return launch<4>(a, n_pairs, s);
+    case 5: return launch<5>(a, n_pairs, s);
     default: return launch<10>(a, n_pairs, s);
     }
 }
