@@ -53,6 +53,8 @@ struct dsdtm_ctx {
     dsdtm::StageTimer timer;
     float last_run_ms = 0.f;
     int pyr_kernel = 0;                          // 0 = auto (strip kernel where eligible), 1 = always the shared-memory tile kernel
+    int sa_variant = 0;                          // 0 = shared-memory recompute kernel, 1 = L2 workspace kernel
+    double* sa_ws_d = nullptr;                   // max_batch * 48 * nf doubles (variant 1)
     int sa_wpp_override = 0;                     // 0 = pick warps-per-pair from the batch size
 
     // device memory
@@ -134,6 +136,7 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
 cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
 cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s);
 int sparse_align_smem_bytes(int nf_pad);
+size_t sparse_align_ws_doubles(int max_feats);
 cudaError_t sparse_align_init(dsdtm_ctx* c);
 
 }  // namespace dsdtm

@@ -40,7 +40,8 @@ struct SaArgs {
     dsdtm_iter_log* log; int* n_log; int log_cap;
     float fx, fy, cx, cy, f;
     int max_level, min_level, max_iters;
-    int nf;      // shared-memory column count (multiple of 32, >= every n_feats)
+    double* ws;  // variant 1: per-pair workspace [48][nf] doubles (ref, 2dx, 2dy per patch pixel), L2-resident
+    int nf;      // shared-memory column count (multiple of 16, >= every n_feats)
     int pair0;
 };
 
@@ -103,6 +104,13 @@ struct RefRows {
     __device__ __forceinline__ void load_row(int slot, int y)
     {
         const uint32_t lo = nb[(2 * y) * NF], hi = nb[(2 * y + 1) * NF];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Nd[slot][c] = u8_to_f64(lo, c);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Nd[slot][4 + c] = u8_to_f64(hi, c);
+    }
+    __device__ __forceinline__ void load_row_words(int slot, uint32_t lo, uint32_t hi)
+    {
 #pragma unroll
         for (int c = 0; c < 4; ++c) Nd[slot][c] = u8_to_f64(lo, c);
 #pragma unroll
@@ -492,19 +500,330 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_S
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant 1 ("workspace"): the pose-independent reference samples (ref, 2*dx, 2*dy for the 16 patch pixels) are computed
+// ONCE per level by the owning lane -- with exactly the same expressions as variant 0 -- and parked in a per-pair global
+// workspace laid out [48][nf] so that consecutive lanes read consecutive doubles (256-byte coalesced, ld.global.cg: the
+// data lives in L2, 115 KB per resident pair). An iteration then only does the current-image side: 12 loads + 16 bilinear
+// samples per feature instead of re-deriving the 6x6 grid from bytes (~465 instead of ~700 instructions per feature and
+// iteration), and shared memory drops to 49 B / feature. A lane only ever reads what it wrote itself.
+template <int WPP>
+__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 8 : (WPP == 4 ? 4 : (WPP == 5 ? 3 : 1))) sparse_align_ws_kernel(const SaArgs a)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int NF = a.nf;
+    double* s_P = reinterpret_cast<double*>(s_raw);                                        // [3][NF] point in the ref camera
+    double* s_S = reinterpret_cast<double*>(s_raw + (size_t)24 * NF);                      // [3][NF] Sxx, Sxy, Syy of the ref patch
+    uint8_t* s_valid = s_raw + (size_t)48 * NF;                                            // [NF]
+    __shared__ double s_red[WPP][8];
+    __shared__ int s_cnt[WPP];
+    __shared__ double s_redH[WPP][22];
+    __shared__ double s_H[21];
+    __shared__ double s_F[22];
+    __shared__ double s_T[7], s_Told[7];
+    __shared__ double s_chi2prev;
+    __shared__ int s_stop, s_npts, s_nlog;
+
+    constexpr int NT = 32 * WPP;
+    const int pair = blockIdx.x + a.pair0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nfeat = min(a.n_feats[pair], NF);
+    const uint8_t* __restrict__ ref_frame = a.frames + (size_t)a.ref_slots[pair] * a.frame_stride;
+    const uint8_t* __restrict__ cur_frame = a.frames + (size_t)a.cur_slots[pair] * a.frame_stride;
+    double* __restrict__ ws = a.ws + (size_t)pair * 48 * NF;
+    const double cen0 = a.centers[3 * pair], cen1 = a.centers[3 * pair + 1], cen2 = a.centers[3 * pair + 2];
+    const double fx = (double)a.fx, fy = (double)a.fy, cx = (double)a.cx, cy = (double)a.cy;
+
+    if (tid < 7) { s_T[tid] = a.poses_in[7 * pair + tid]; s_Told[tid] = s_T[tid]; }
+    if (tid == 0) { s_npts = 0; s_nlog = 0; s_stop = 0; s_chi2prev = 0.0; }
+    __syncthreads();
+
+    for (int level = a.max_level - 1; level >= a.min_level; --level) {
+        const int cols = a.geo.w[level], rows = a.geo.h[level];
+        const float tScale = 1.0f / (float)(1 << level);
+        const double scale = (double)tScale;
+        const double fs = (double)a.f * scale;     // == (v * f) * scale bit-exactly, scale being a power of two
+        const double fs2 = fs * fs;
+
+        // ------------------------------------------------ GetJocabianMat (ref: :62-166), pose-independent: once per level
+        {
+            const uint8_t* __restrict__ img = ref_frame + a.geo.off[level];
+            for (int f = tid; f < nfeat; f += NT) {
+                const dsdtm_ref_feat ft = a.feats[(size_t)pair * a.feat_stride + f];
+                bool valid = false;
+                if (ft.initial) {                                                                      // ref: :86
+                    const double px = (double)ft.px[0] * scale, py = (double)ft.px[1] * scale;       // ref: :89-91
+                    const bool zero = (ft.point_w[0] == 0.0 && ft.point_w[1] == 0.0 && ft.point_w[2] == 0.0);
+                    const int boarder = 3;                                                             // ref: :67
+                    if (!(zero || px - boarder < 0 || py - boarder < 0 || px + boarder >= cols || py + boarder >= rows)) {   // ref: :95-96
+                        valid = true;
+                        const double d0 = __dsub_rn(ft.point_w[0], cen0), d1 = __dsub_rn(ft.point_w[1], cen1), d2 = __dsub_rn(ft.point_w[2], cen2);
+                        const double depth = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));   // ref: :117-118
+                        s_P[f] = __dmul_rn(ft.normal[0], depth);                                      // ref: :119
+                        s_P[NF + f] = __dmul_rn(ft.normal[1], depth);
+                        s_P[2 * NF + f] = __dmul_rn(ft.normal[2], depth);
+                        const int fxi = __double2int_rd(px), fyi = __double2int_rd(py);
+                        const double sx = px - fxi, sy = py - fyi;
+                        RefRows R;
+                        R.w00 = __dmul_rn(1.0 - sx, 1.0 - sy); R.w01 = __dmul_rn(sx, 1.0 - sy);
+                        R.w10 = __dmul_rn(1.0 - sx, sy); R.w11 = __dmul_rn(sx, sy);                   // ref: :129-132
+                        // rows fyi-3 .. fyi+3, cols fxi-3 .. fxi+3 : three aligned 32-bit loads + funnel shifts per row
+                        uint32_t lo[7], hi[7];
+                        const unsigned a0 = (unsigned)(fyi - 3) * (unsigned)cols + (unsigned)(fxi - 3);
+#pragma unroll
+                        for (int r = 0; r < 7; ++r) {
+                            const unsigned ad = a0 + (unsigned)r * (unsigned)cols;
+                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (ad & ~3u));
+                            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+                            const int sh = 8 * (ad & 3u);
+                            lo[r] = __funnelshift_r(w0, w1, sh);
+                            hi[r] = __funnelshift_r(w1, w2, sh);
+                        }
+                        R.load_row_words(0, lo[0], hi[0]); R.load_row_words(1, lo[1], hi[1]);
+                        R.grid_row(0, 0, 1);
+                        R.load_row_words(0, lo[2], hi[2]);
+                        R.grid_row(1, 1, 0);
+                        double Sxx = 0, Sxy = 0, Syy = 0;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int sa = (r & 1), sb = sa ^ 1;
+                            R.load_row_words(sb, lo[r + 3], hi[r + 3]);
+                            R.grid_row((r + 2) % 3, sa, sb);
+                            const int g0 = r % 3, g1 = (r + 1) % 3, g2 = (r + 2) % 3;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const double refv = R.G[g1][c + 1];
+                                const double dx2 = __dsub_rn(R.G[g1][c + 2], R.G[g1][c]);                // 2*dx (ref: :150-153)
+                                const double dy2 = __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]);            // 2*dy (ref: :155-158)
+                                const int p = 4 * r + c;
+                                __stcg(ws + (size_t)(3 * p) * NF + f, refv);
+                                __stcg(ws + (size_t)(3 * p + 1) * NF + f, dx2);
+                                __stcg(ws + (size_t)(3 * p + 2) * NF + f, dy2);
+                                Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy);
+                            }
+                        }
+                        s_S[f] = 0.25 * Sxx; s_S[NF + f] = 0.25 * Sxy; s_S[2 * NF + f] = 0.25 * Syy;   // (0.5 d2)^2, exact scaling
+                    }
+                }
+                s_valid[f] = valid ? 1 : 0;
+            }
+        }
+        __syncthreads();
+
+        unsigned prev_vis = 0;
+        const uint8_t* __restrict__ cimg = cur_frame + a.geo.off[level];
+
+        // ------------------------------------------------ GaussNewtonSolver (ref: :301-344)
+        for (int it = 0; it < a.max_iters; ++it) {
+            const double qw = s_T[0], qx = s_T[1], qy = s_T[2], qz = s_T[3];
+            const double t0 = s_T[4], t1 = s_T[5], t2 = s_T[6];
+            double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0, accc = 0;
+            int cnt = 0;
+            unsigned vis_mask = 0;
+            int k = 0;
+            for (int f = tid; f < nfeat; f += NT, ++k) {
+                if (!s_valid[f]) continue;
+                const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
+                double Q0, Q1, Q2;
+                qrot(qw, qx, qy, qz, P0, P1, P2, Q0, Q1, Q2);                                  // ref: :254
+                Q0 = __dadd_rn(Q0, t0); Q1 = __dadd_rn(Q1, t1); Q2 = __dadd_rn(Q2, t2);
+                // Camera2Pixel * tScale (ref: src/Camera.cpp:167-171, :255): (fx*X)/Z + cx
+                const double u = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fx, Q0), Q2), cx), scale);
+                const double v = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fy, Q1), Q2), cy), scale);
+                const double uf = floor(u), vf = floor(v);
+                // ref: :262 with border 3; evaluated in double so that NaN / huge values are rejected like the reference's INT_MIN
+                if (!(uf >= 3.0 && vf >= 3.0 && uf < (double)(cols - 3) && vf < (double)(rows - 3))) continue;
+                vis_mask |= 1u << k;
+                ++cnt;
+                const int ui = (int)uf, vi = (int)vf;
+                const double su = u - uf, sv = v - vf;
+                const double tl = __dmul_rn(1.0 - su, 1.0 - sv), tr = __dmul_rn(su, 1.0 - sv);
+                const double bl = __dmul_rn(1.0 - su, sv), br = __dmul_rn(su, sv);            // ref: :267-270
+                // current-image 5x5 window rows vi-2 .. vi+2, cols ui-2 .. ui+2
+                uint32_t cw0[5], cw1[5];
+                {
+                    const unsigned c0w = (unsigned)(vi - 2) * (unsigned)cols + (unsigned)(ui - 2);
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        const unsigned ad = c0w + (unsigned)r * (unsigned)cols;
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(cimg + (ad & ~3u));
+                        const uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
+                        const int sh = 8 * (ad & 3u);
+                        cw0[r] = __funnelshift_r(lo, hi, sh);
+                        cw1[r] = hi >> sh;
+                    }
+                }
+                const double* __restrict__ wf = ws + f;
+                double Cw[2][5];
+                auto cvt_cur = [&](int slot, int r) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) Cw[slot][c] = u8_to_f64(cw0[r], c);
+                    Cw[slot][4] = u8_to_f64(cw1[r], 0);
+                };
+                cvt_cur(0, 0);
+                double Sx = 0, Sy = 0, c2 = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    double rv[4], gx[4], gy[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int p = 4 * r + c;
+                        rv[c] = __ldcg(wf + (size_t)(3 * p) * NF);
+                        gx[c] = __ldcg(wf + (size_t)(3 * p + 1) * NF);
+                        gy[c] = __ldcg(wf + (size_t)(3 * p + 2) * NF);
+                    }
+                    cvt_cur((r + 1) & 1, r + 1);
+                    const int ca = r & 1, cb = ca ^ 1;                          // Cw rows r, r+1
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double cur = bil(tl, tr, bl, br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
+                        const double res = __dsub_rn(cur, rv[c]);                                         // ref: :282
+#if DSDTM_SA_STRICT
+                        c2 = __dadd_rn(c2, __dmul_rn(res, res));                                          // ref: :284
+#else
+                        c2 = fma(res, res, c2);
+#endif
+                        Sx = fma(gx[c], res, Sx);
+                        Sy = fma(gy[c], res, Sy);
+                    }
+                }
+                Sx *= 0.5; Sy *= 0.5;
+                // GetJocabianBA(P) rows (ref: :169-193); a1 = b0 = 0.   b_j = fs * (a * Sx + b * Sy)
+                const double zi = 1.0 / P2, zi2 = zi * zi;
+                const double a0 = -zi, a2 = P0 * zi2, a3 = P1 * a2, a4 = -(1.0 + P0 * a2), a5 = P1 * zi;
+                const double b1 = -zi, b2 = P1 * zi2, b3 = 1.0 + P1 * b2, b4 = -P0 * b2, b5 = -P0 * zi;
+                acc0 += fs * (a0 * Sx); acc1 += fs * (b1 * Sy); acc2 += fs * (a2 * Sx + b2 * Sy);
+                acc3 += fs * (a3 * Sx + b3 * Sy); acc4 += fs * (a4 * Sx + b4 * Sy); acc5 += fs * (a5 * Sx + b5 * Sy);
+                accc += c2;
+            }
+            acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2); acc3 = warp_sum(acc3);
+            acc4 = warp_sum(acc4); acc5 = warp_sum(acc5); accc = warp_sum(accc);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (WPP > 1 && lane == 0) {
+                s_red[warp][0] = acc0; s_red[warp][1] = acc1; s_red[warp][2] = acc2; s_red[warp][3] = acc3;
+                s_red[warp][4] = acc4; s_red[warp][5] = acc5; s_red[warp][6] = accc;
+                s_cnt[warp] = cnt;
+            }
+            const int need_H = __syncthreads_or((it == 0) || (vis_mask != prev_vis));
+            prev_vis = vis_mask;
+            if (need_H) {
+                // H = fs^2 sum_visible (Sxx a a^T + Sxy (a b^T + b a^T) + Syy b b^T), lower triangle packed row-major,
+                // assembled from the parked second moments (no image arithmetic here)
+                double hacc[21];
+#pragma unroll
+                for (int i = 0; i < 21; ++i) hacc[i] = 0.0;
+                int kk = 0;
+                for (int f = tid; f < nfeat; f += NT, ++kk) {
+                    if (!((vis_mask >> kk) & 1u)) continue;
+                    const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
+                    const double zi = 1.0 / P2, zi2 = zi * zi;
+                    const double av[6] = { -zi, 0.0, P0 * zi2, P1 * (P0 * zi2), -(1.0 + P0 * (P0 * zi2)), P1 * zi };
+                    const double bv[6] = { 0.0, -zi, P1 * zi2, 1.0 + P1 * (P1 * zi2), -P0 * (P1 * zi2), -P0 * zi };
+                    const double cxx = fs2 * s_S[f], cxy = fs2 * s_S[NF + f], cyy = fs2 * s_S[2 * NF + f];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = 0; c <= r; ++c)
+                            hacc[r * (r + 1) / 2 + c] += cxx * (av[r] * av[c]) + cxy * (av[r] * bv[c] + bv[r] * av[c]) + cyy * (bv[r] * bv[c]);
+                }
+#pragma unroll
+                for (int i = 0; i < 21; ++i) {
+                    const double h = warp_sum(hacc[i]);
+                    if (WPP > 1) { if (lane == 0) s_redH[warp][i] = h; }
+                    else if (lane == 0) s_H[i] = h;
+                }
+                if (WPP > 1) __syncthreads();
+            }
+            if (warp == 0) {
+                if (WPP > 1) {
+                    if (need_H && lane < 21) {
+                        double h = 0;
+                        for (int w = 0; w < WPP; ++w) h += s_redH[w][lane];
+                        s_H[lane] = h;
+                    }
+                    double red = 0;
+                    if (lane < 7) for (int w = 0; w < WPP; ++w) red += s_red[w][lane];
+                    int npts = 0;
+                    for (int w = 0; w < WPP; ++w) npts += s_cnt[w];
+                    acc0 = __shfl_sync(0xffffffffu, red, 0); acc1 = __shfl_sync(0xffffffffu, red, 1);
+                    acc2 = __shfl_sync(0xffffffffu, red, 2); acc3 = __shfl_sync(0xffffffffu, red, 3);
+                    acc4 = __shfl_sync(0xffffffffu, red, 4); acc5 = __shfl_sync(0xffffffffu, red, 5);
+                    accc = __shfl_sync(0xffffffffu, red, 6);
+                    cnt = npts;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    const double chi2New = accc / (double)(16 * cnt);                      // ref: :298 (NaN if nothing visible)
+                    const double bvec[6] = { acc0, acc1, acc2, acc3, acc4, acc5 };
+                    double x[6];
+                    solve_and_update(s_H, s_F, need_H != 0, bvec, x);                      // ref: :318
+                    int flags = 0;
+                    bool stop = false;
+                    if (isnan(x[0])) { stop = true; flags |= 4; }                          // ref: :321-326
+                    if ((it > 0 && chi2New > s_chi2prev) || stop) {                        // ref: :328-332
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) s_T[q] = s_Told[q];
+                        flags |= 2;
+                        stop = true;
+                    } else {
+                        double Tn[7];
+                        pose_update(s_T, x, Tn);                                           // ref: :335
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) { s_Told[q] = s_T[q]; s_T[q] = Tn[q]; } // ref: :336-337
+                        s_chi2prev = chi2New;                                              // ref: :339
+                        flags |= 1;
+                        double mx = 0;
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) mx = fmax(mx, fabs(x[q]));
+                        if (mx <= 1e-8) { stop = true; flags |= 8; }                       // ref: :341
+                    }
+                    s_npts = cnt;
+                    s_stop = stop ? 1 : 0;
+                    if (a.log) {
+                        const int n = s_nlog;
+                        if (n < a.log_cap) {
+                            dsdtm_iter_log* e = a.log + (size_t)pair * a.log_cap + n;
+                            e->level = level; e->iter = it; e->n_pts = cnt; e->flags = flags; e->chi2 = chi2New;
+#pragma unroll
+                            for (int q = 0; q < 6; ++q) e->x[q] = x[q];
+                        }
+                        s_nlog = n + 1;
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_stop) break;
+        }
+        // ref: :308 tT_c2rOld(tT_c2r) and chi2 = 0 at the start of every level
+        __syncthreads();
+        if (tid < 7) s_Told[tid] = s_T[tid];
+        if (tid == 0) { s_stop = 0; s_chi2prev = 0.0; }
+        __syncthreads();
+    }
+    if (tid < 7) a.poses_out[7 * pair + tid] = s_T[tid];
+    if (tid == 0) {
+        a.n_tracked[pair] = s_npts;
+        if (a.n_log) a.n_log[pair] = s_nlog;
+    }
+}
+
 int smem_bytes(int nf) { return (48 + 4 * NB_WORDS + 8 + 1) * nf; }
 int round_nf(int max_feats) { return (max_feats + 15) / 16 * 16; }
+
+int smem_bytes_ws(int nf) { return (48 + 1) * nf; }
 
 template <int WPP>
 cudaError_t launch(const SaArgs& a, int n_pairs, cudaStream_t s)
 {
-    sparse_align_kernel<WPP><<<n_pairs, 32 * WPP, smem_bytes(a.nf), s>>>(a);
+    if (a.ws) sparse_align_ws_kernel<WPP><<<n_pairs, 32 * WPP, smem_bytes_ws(a.nf), s>>>(a);
+    else sparse_align_kernel<WPP><<<n_pairs, 32 * WPP, smem_bytes(a.nf), s>>>(a);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 int sparse_align_smem_bytes(int nf) { return smem_bytes(nf); }
+size_t sparse_align_ws_doubles(int max_feats) { return (size_t)48 * round_nf(max_feats); }
 
 cudaError_t sparse_align_init(dsdtm_ctx* c)
 {
@@ -515,6 +834,12 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    const int bw = smem_bytes_ws(nf);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     return e;
 }
 
@@ -540,6 +865,7 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
     a.fx = c->cam.fx; a.fy = c->cam.fy; a.cx = c->cam.cx; a.cy = c->cam.cy; a.f = c->cam.f;
     a.max_level = max_level; a.min_level = min_level; a.max_iters = max_iters;
     a.nf = round_nf(c->prm.max_feats);
+    a.ws = (c->sa_variant == 1) ? c->sa_ws_d : nullptr;
     a.pair0 = pair0;
     c->launches++;
     // warps-per-pair is chosen from the size of the WHOLE batch so that chunked (e2e) and single-launch runs reduce in the same order

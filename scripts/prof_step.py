@@ -13,6 +13,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=2)
     ap.add_argument("--fast", type=int, default=0, help="also run fast_cells_batch over this many frames")
     ap.add_argument("--wpp", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--direct", action="store_true", help="launch kernels directly instead of graph replay")
     a = ap.parse_args()
     cam = dict(S.KINECT)
@@ -23,6 +24,7 @@ def main():
                     bench.ALIGN_CFG["max_level"], bench.ALIGN_CFG["min_level"], bench.ALIGN_CFG["max_iters"], batch["patches"], batch["patch_px"],
                     batch["patch_level"], bench.ALIGN2D_ITERS)
     ctx.set_option("sa_warps_per_pair", a.wpp)
+    ctx.set_option("sa_variant", a.variant)
     if a.direct:
         ctx.profile(True)
     for _ in range(a.steps):

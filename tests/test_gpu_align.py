@@ -59,6 +59,25 @@ def test_sparse_align_other_seeds_and_nonidentity_ref(ctx, seed):
     _compare_traces(lo, lg)
 
 
+@pytest.mark.parametrize("opt", [("sa_variant", 1), ("sa_warps_per_pair", 1), ("sa_warps_per_pair", 2), ("sa_warps_per_pair", 4), ("sa_warps_per_pair", 5)])
+def test_sparse_align_kernel_variants_agree_with_oracle(ctx, scenario, opt):
+    """Tuning knobs never change results beyond the reduction-order tolerance: the L2-workspace variant and every
+    warps-per-pair instantiation against the oracle."""
+    _upload(ctx, scenario)
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    po, no, lo = O.sparse_align(H.ocam(scenario["cam"]), packed, scenario["cur_pyr"][0], offs, ws, hs, scenario["feats"],
+                                scenario["ref_center"], S.IDENTITY, 5, 0, 8)
+    ctx.set_option(*opt)
+    try:
+        pg, ng, lg = ctx.sparse_align(0, 1, scenario["feats"], scenario["ref_center"], S.IDENTITY, 5, 0, 8)
+    finally:
+        ctx.set_option("sa_variant", 0)
+        ctx.set_option("sa_warps_per_pair", 0)
+    d = S.pose_dist(po, pg)
+    assert d[0] < POSE_TOL and d[1] < POSE_TOL and no == ng
+    _compare_traces(lo, lg)
+
+
 def test_sparse_align_skips_uninitialised_zero_and_border_features(ctx, scenario):
     """ref: src/Sprase_ImageAlign.cpp:86,95-100 -- mbInitial false, P_w == 0 and features within 3 px of the level border."""
     _upload(ctx, scenario)
