@@ -5,8 +5,8 @@
 // reference: H = sum J J^T over the 8x8 interior of the 10x10 bordered patch (exact in fp32: quarter-integers < 2^22),
 // Hinv by the 3x3 cofactor formula (Eigen Matrix3f::inverse), then <= max_iters iterations of bilinear sampling,
 // Jres accumulation and the (u, v, mean) update; converged iff du^2 + dv^2 < 0.03^2.
-// Lane l owns pixels l and l+32 of the patch; the three Jres sums are reduced with a warp xor-shuffle butterfly (bitwise
-// identical in every lane => uniform control flow). The reference sums the 64 terms sequentially in fp32, the butterfly
+// One half-warp per patch: lane l owns 4 pixels; the three Jres sums are reduced with a 16-lane xor-shuffle butterfly (bitwise
+// identical in every lane of the half => uniform control flow per patch). The reference sums the 64 terms sequentially in fp32, the butterfly
 // is a tree: documented tolerance 1e-3 px on the refined position.
 // Q4 (ref: :367-368 uses '>' where SVO uses '>='): with u_r == cols-4 or v_r == rows-4 the reference reads one byte past
 // the row / image. We reproduce the linear addressing (next row's first pixel) and read bytes past the end of the level
@@ -39,36 +39,60 @@ __device__ __forceinline__ float wsum(float v)
     return v;
 }
 
-constexpr int A2D_WARPS = 8;
+constexpr int A2D_WARPS = 8;          // 8 warps = 16 patches per CTA
 
+// sum over the 16 lanes of a half-warp (xor butterfly with offsets < 16 never crosses the half)
+__device__ __forceinline__ float hsum(float v)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int hsum_i(int v)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// v2: one HALF-warp per patch (16 lanes x 4 pixels). The per-patch scalar work (weights, 3x3 update, control) is shared by
+// two patches per warp instruction and the butterflies are 4 levels deep instead of 5: ~35 % fewer instructions per patch
+// than the warp-per-patch v1, which was issue-bound (71 % issue slots busy, profiles/r1_pyramid_fast_align2d.md).
 __global__ void __launch_bounds__(A2D_WARPS * 32) align2d_kernel(const A2dArgs a)
 {
-    __shared__ uint8_t s_patch[A2D_WARPS][104];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = a.patch0 + blockIdx.x * A2D_WARPS + warp;
-    if (i >= a.patch0 + a.n) return;
+    __shared__ __align__(16) uint8_t s_patch[A2D_WARPS * 2][104];
+    const int half = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    const int last = a.patch0 + a.n - 1;
+    const int iraw = a.patch0 + blockIdx.x * (A2D_WARPS * 2) + half;
+    if (iraw - (half & 1) > last) return;                 // whole warp out of range (both halves)
+    const bool exists = iraw <= last;
+    const int i = exists ? iraw : last;                   // a missing odd half shadows the last patch and never writes
     const int L = a.patch_level[i];
-    if (L < 0) { if (lane == 0) { a.conv[i] = 0; a.px[2 * i] = a.px_in[2 * i]; a.px[2 * i + 1] = a.px_in[2 * i + 1]; } return; }
+    bool active = exists && L >= 0;
+    if (exists && L < 0 && l16 == 0) { a.conv[i] = 0; a.px[2 * i] = a.px_in[2 * i]; a.px[2 * i + 1] = a.px_in[2 * i + 1]; }
+    const int Lc = L < 0 ? 0 : L;
 
     // stage the 10x10 bordered patch (100 bytes = 25 words; patch10 rows are 4-byte aligned because 100 % 4 == 0)
-    if (lane < 25) reinterpret_cast<uint32_t*>(s_patch[warp])[lane] = __ldg(reinterpret_cast<const uint32_t*>(a.patch10 + (size_t)i * 100) + lane);
+    for (int q = l16; q < 25; q += 16)
+        reinterpret_cast<uint32_t*>(s_patch[half])[q] = __ldg(reinterpret_cast<const uint32_t*>(a.patch10 + (size_t)i * 100) + q);
     __syncwarp();
 
-    // lane owns pixels e = lane and lane + 32 : row = e / 8, col = e % 8 of the 8x8 interior
-    float rdx[2], rdy[2], rref[2];
-    float h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0;
+    // lane owns pixels e = l16 + 16 k (k = 0..3): row = e / 8 = (l16 >> 3) + 2k, col = l16 & 7 of the 8x8 interior
+    const int pc = l16 & 7, pr0 = l16 >> 3;
+    float rdx[4], rdy[4], rref[4];
+    int i00 = 0, i01 = 0, i02 = 0, i11 = 0, i12 = 0;      // sums of the integer pixel differences (2*dx, 2*dy)
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int e = lane + 32 * k, r = e >> 3, c = e & 7;
-        const uint8_t* it = s_patch[warp] + (r + 1) * 10 + 1 + c;
-        rdx[k] = 0.5f * (float)((int)it[1] - (int)it[-1]);          // ref: :336 (exact half-integers)
-        rdy[k] = 0.5f * (float)((int)it[10] - (int)it[-10]);        // ref: :337
+    for (int k = 0; k < 4; ++k) {
+        const uint8_t* it = s_patch[half] + (pr0 + 2 * k + 1) * 10 + 1 + pc;
+        const int ddx = (int)it[1] - (int)it[-1], ddy = (int)it[10] - (int)it[-10];
+        rdx[k] = 0.5f * (float)ddx;                        // ref: :336 (exact half-integers)
+        rdy[k] = 0.5f * (float)ddy;                        // ref: :337
         rref[k] = (float)it[0];
-        h00 += rdx[k] * rdx[k]; h01 += rdx[k] * rdy[k]; h02 += rdx[k];
-        h11 += rdy[k] * rdy[k]; h12 += rdy[k];
+        i00 += ddx * ddx; i01 += ddx * ddy; i02 += ddx; i11 += ddy * ddy; i12 += ddy;
     }
-    // all sums are exact in fp32 in any order (multiples of 1/4 below 2^22)
-    h00 = wsum(h00); h01 = wsum(h01); h02 = wsum(h02); h11 = wsum(h11); h12 = wsum(h12);
+    // H = sum J J^T with J = (dx, dy, 1): every entry is an integer / 4 (or / 2) below 2^22, exact in fp32 in any order
+    const float h00 = 0.25f * (float)hsum_i(i00), h01 = 0.25f * (float)hsum_i(i01), h02 = 0.5f * (float)hsum_i(i02);
+    const float h11 = 0.25f * (float)hsum_i(i11), h12 = 0.5f * (float)hsum_i(i12);
     const float h22 = 64.0f;
     // Eigen 3x3 inverse: cofactor(i,j) = m(i1,j1) m(i2,j2) - m(i1,j2) m(i2,j1); det = sum_i cof(i,0) m(i,0)
     float Hinv[9];
@@ -87,8 +111,8 @@ __global__ void __launch_bounds__(A2D_WARPS * 32) align2d_kernel(const A2dArgs a
 #undef M
     }
 
-    const int cols = a.geo.w[L], rows = a.geo.h[L];
-    const uint8_t* __restrict__ img = a.frames + (size_t)a.patch_slot[i] * a.frame_stride + a.geo.off[L];
+    const int cols = a.geo.w[Lc], rows = a.geo.h[Lc];
+    const uint8_t* __restrict__ img = a.frames + (size_t)a.patch_slot[i] * a.frame_stride + a.geo.off[Lc];
     const unsigned img_bytes = (unsigned)cols * (unsigned)rows;
 
     float u = (float)a.px_in[2 * i], v = (float)a.px_in[2 * i + 1];      // ref: :349-350
@@ -98,38 +122,50 @@ __global__ void __launch_bounds__(A2D_WARPS * 32) align2d_kernel(const A2dArgs a
     for (int it = 0; it < a.max_iters; ++it) {
         const float uf = floorf(u), vf = floorf(v);
         // ref: :367-369 (Q4 '>'); written on floats so that NaN / huge values break like the reference
-        if (!(uf >= 4.f && vf >= 4.f && uf <= (float)(cols - 4) && vf <= (float)(rows - 4))) break;
-        const int u_r = (int)uf, v_r = (int)vf;
-        const float sx = u - uf, sy = v - vf;
+        if (active && !(uf >= 4.f && vf >= 4.f && uf <= (float)(cols - 4) && vf <= (float)(rows - 4))) active = false;
+        if (!__any_sync(0xffffffffu, active)) break;       // both patches of the warp are done
+        // a finished half keeps executing the (warp-wide) shuffles on clamped coordinates and discards the result
+        const int u_r = active ? (int)uf : 4, v_r = active ? (int)vf : 4;
+        const float sx = active ? u - uf : 0.f, sy = active ? v - vf : 0.f;
         const float wTL = (float)((1.0 - (double)sx) * (1.0 - (double)sy));   // ref: :373 (double arithmetic, narrowed)
         const float wTR = __fmul_rn(sx, 1.0f - sy);                          // ref: :374 (float arithmetic)
         const float wBL = (float)((1.0 - (double)sx) * (double)sy);          // ref: :375
         const float wBR = __fmul_rn(sx, sy);                                 // ref: :376
         float j0 = 0.f, j1 = 0.f, j2 = 0.f;
+        const unsigned o0 = (unsigned)(v_r + pr0 - 4) * (unsigned)cols + (unsigned)(u_r - 4 + pc);
+        // the whole 9x9 window lies inside the level image unless the Q4 edge case is hit (u_r == cols-4 or v_r == rows-4)
+        const bool inside = (u_r + 4 < cols) && (v_r + 4 < rows);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int e = lane + 32 * k, r = e >> 3, c = e & 7;
-            const unsigned o = (unsigned)(v_r + r - 4) * (unsigned)cols + (unsigned)(u_r - 4 + c);
+        for (int k = 0; k < 4; ++k) {
+            const unsigned o = o0 + (unsigned)(2 * k) * (unsigned)cols;
             const unsigned o2 = o + (unsigned)cols;
-            const float i00 = (float)(o < img_bytes ? __ldg(img + o) : 0);
-            const float i01 = (float)(o + 1 < img_bytes ? __ldg(img + o + 1) : 0);
-            const float i10 = (float)(o2 < img_bytes ? __ldg(img + o2) : 0);
-            const float i11 = (float)(o2 + 1 < img_bytes ? __ldg(img + o2 + 1) : 0);
-            const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, i00), __fmul_rn(wTR, i01)), __fmul_rn(wBL, i10)), __fmul_rn(wBR, i11));   // ref: :386
+            float p00, p01, p10, p11;
+            if (inside) {
+                p00 = (float)__ldg(img + o); p01 = (float)__ldg(img + o + 1);
+                p10 = (float)__ldg(img + o2); p11 = (float)__ldg(img + o2 + 1);
+            } else {
+                p00 = (float)(o < img_bytes ? __ldg(img + o) : 0);
+                p01 = (float)(o + 1 < img_bytes ? __ldg(img + o + 1) : 0);
+                p10 = (float)(o2 < img_bytes ? __ldg(img + o2) : 0);
+                p11 = (float)(o2 + 1 < img_bytes ? __ldg(img + o2 + 1) : 0);
+            }
+            const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, p00), __fmul_rn(wTR, p01)), __fmul_rn(wBL, p10)), __fmul_rn(wBR, p11));   // ref: :386
             const float res = __fadd_rn(__fsub_rn(s, rref[k]), mean_diff);                                                                  // ref: :387
             j0 = __fsub_rn(j0, __fmul_rn(res, rdx[k]));
             j1 = __fsub_rn(j1, __fmul_rn(res, rdy[k]));
             j2 = __fsub_rn(j2, res);
         }
-        j0 = wsum(j0); j1 = wsum(j1); j2 = wsum(j2);
+        j0 = hsum(j0); j1 = hsum(j1); j2 = hsum(j2);
         // ref: :395 tUpdate = Hinv * Jres (row-wise, left to right)
         const float d0 = __fadd_rn(__fadd_rn(__fmul_rn(Hinv[0], j0), __fmul_rn(Hinv[1], j1)), __fmul_rn(Hinv[2], j2));
         const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(Hinv[3], j0), __fmul_rn(Hinv[4], j1)), __fmul_rn(Hinv[5], j2));
         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(Hinv[6], j0), __fmul_rn(Hinv[7], j1)), __fmul_rn(Hinv[8], j2));
-        u = __fadd_rn(u, d0); v = __fadd_rn(v, d1); mean_diff = __fadd_rn(mean_diff, d2);
-        if (__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)) < min_update_squared) { converged = true; break; }   // ref: :400
+        if (active) {
+            u = __fadd_rn(u, d0); v = __fadd_rn(v, d1); mean_diff = __fadd_rn(mean_diff, d2);
+            if (__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)) < min_update_squared) { converged = true; active = false; }   // ref: :400
+        }
     }
-    if (lane == 0) {
+    if (exists && L >= 0 && l16 == 0) {
         a.px[2 * i] = (double)u; a.px[2 * i + 1] = (double)v;     // ref: :414
         a.conv[i] = converged ? 1 : 0;
     }
@@ -194,7 +230,7 @@ cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStrea
     a.frames = c->frames_d; a.frame_stride = c->geo.frame_stride; a.geo = c->geo;
     a.patch_slot = c->patch_slot_d; a.patch_level = c->patch_level_d; a.patch10 = c->patches_d;
     a.px_in = c->patch_px_in_d; a.px = c->patch_px_d; a.conv = c->patch_conv_d; a.n = n_patches; a.max_iters = max_iters; a.patch0 = patch0;
-    align2d_kernel<<<(n_patches + A2D_WARPS - 1) / A2D_WARPS, A2D_WARPS * 32, 0, s>>>(a);
+    align2d_kernel<<<(n_patches + 2 * A2D_WARPS - 1) / (2 * A2D_WARPS), A2D_WARPS * 32, 0, s>>>(a);
     c->launches++;
     return cudaGetLastError();
 }
