@@ -108,6 +108,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, pairs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r1_traffic.json, taken at 4096 pairs), scaled per pair. None if the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p)).get(kernel)
+    return None if not t else float(t["bytes_per_pair"]) * pairs
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -295,9 +305,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"kernel": "sparse_align_kernel", "bound": "hbm", "achieved": sa_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": sa_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": sa_gbs / hbm_peak, "traffic": measured_traffic("sparse_align_kernel", B), "peak_source": peak_src,
                          "ms_per_launch": sa_ms, "algorithmic_bytes_per_launch": sa_bytes,
-                         "note": "dependent Gauss-Newton chain: latency/issue-bound, not bandwidth-bound (SURVEY 8d); see stages"},
+                         "note": "dependent Gauss-Newton chain: latency/issue-bound, not bandwidth-bound (SURVEY 8d): ncu issue slots busy 32 %, "
+                                 "fp64 pipe ~35 %, DRAM 14 %, L1/TEX hit 74 % (profiles/r1_sa_bench_summary.txt); traffic is the ncu DRAM byte count "
+                                 "(32-byte sectors for 5-byte window rows) scaled per pair; see stages for the HBM-bound kernels"},
             "stages": {
                 "pyramid": {"ms_per_step": pyr_ms, "GBps": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "frac_hbm": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak,
                             "algorithmic_bytes": pyr_bytes},
