@@ -8,13 +8,16 @@ import numpy as np
 
 from . import build as _build
 
-STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine")
+STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine", "cand_prep")
 
 CORNER_DT = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4")])
 REF_FEAT_DT = np.dtype([("px", "<f4", 2), ("level", "<i4"), ("initial", "<i4"),
                         ("normal", "<f8", 3), ("point_w", "<f8", 3)])
 ITER_LOG_DT = np.dtype([("level", "<i4"), ("iter", "<i4"), ("n_pts", "<i4"), ("flags", "<i4"),
                         ("chi2", "<f8"), ("x", "<f8", 6)])
+CANDIDATE_DT = np.dtype([("ref_slot", "<i4"), ("ref_level", "<i4"), ("ref_px", "<f4", 2), ("ref_normal", "<f8", 3),
+                         ("ref_point_w", "<f8", 3), ("kf_center", "<f8", 3), ("pose_c2r", "<f8", 7), ("px", "<f8", 2)])
+assert CANDIDATE_DT.itemsize == 160
 
 
 class Cam(C.Structure):
@@ -41,7 +44,7 @@ SYMBOLS = [
     "dsdtm_frames_build_pyramid", "dsdtm_frame_download_level", "dsdtm_fast_cells", "dsdtm_fast_cells_batch",
     "dsdtm_fast_score_map", "dsdtm_grid_dims", "dsdtm_sparse_align", "dsdtm_sparse_align_batch",
     "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
-    "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option",
+    "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
 ]
 
 
@@ -233,6 +236,15 @@ class Context:
             _p(np.ascontiguousarray(ref_px, np.float32).reshape(n, 2)), _p(np.ascontiguousarray(ref_levels, np.int32)),
             _p(np.ascontiguousarray(search_levels, np.int32)), n, _p(out)))
         return out
+
+    def feature_align_batch(self, cur_slot, cands, max_search_level, max_iters=10, want_A=False):
+        cands = np.ascontiguousarray(cands, CANDIDATE_DT)
+        n = len(cands)
+        px = np.empty((n, 2)); lv = np.empty(n, np.int32); conv = np.zeros(n, np.uint8)
+        A = np.empty((n, 2, 2)) if want_A else None
+        self._ck(self.L.dsdtm_feature_align_batch(self.hp, int(cur_slot), _p(cands), n, int(max_search_level), int(max_iters),
+                                                  _p(px), _p(lv), _p(conv), _p(A)))
+        return px, lv, conv.astype(bool), A
 
     # ---- batched front end
     def batch_stage(self, ref_slots, cur_slots, feats, n_feats, ref_centers, poses_in, max_level, min_level, max_iters,

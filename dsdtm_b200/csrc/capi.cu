@@ -158,7 +158,7 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
         dalloc(c, &c->log_d, B * kLogCap) || dalloc(c, &c->n_log_d, B) || dalloc(c, &c->patches_d, B * P * 100) ||
         dalloc(c, &c->patch_px_d, B * P * 2) || dalloc(c, &c->patch_px_in_d, B * P * 2) || dalloc(c, &c->patch_level_d, B * P) || dalloc(c, &c->patch_slot_d, B * P) ||
         dalloc(c, &c->patch_conv_d, B * P) || dalloc(c, &c->wa_A_d, B * P * 4) || dalloc(c, &c->wa_px_d, B * P * 2) ||
-        dalloc(c, &c->wa_meta_d, B * P * 3) || dalloc(c, &c->sa_ws_d, B * sparse_align_ws_doubles(prm->max_feats)))
+        dalloc(c, &c->wa_meta_d, B * P * 3) || dalloc(c, &c->cand_d, B * P) || dalloc(c, &c->sa_ws_d, B * sparse_align_ws_doubles(prm->max_feats)))
         return bail("device buffers");
     {
         const int n = build_fast_tiles(g, nullptr, nullptr);
@@ -181,7 +181,7 @@ void dsdtm_destroy(dsdtm_ctx* c)
     for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) cudaGraphExecDestroy(c->batch.graph[k]);
     void* bufs[] = { c->frames_d, c->cells_d, c->occupied_d, c->scoremap_d, c->fast_tiles_d, c->ref_slots_d, c->cur_slots_d,
                      c->feats_d, c->n_feats_d, c->centers_d, c->poses_in_d, c->poses_out_d, c->n_tracked_d, c->log_d, c->n_log_d,
-                     c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d };
+                     c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d, c->cand_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { if (c->timer.ev0[i]) cudaEventDestroy(c->timer.ev0[i]); if (c->timer.ev1[i]) cudaEventDestroy(c->timer.ev1[i]); }
@@ -498,6 +498,42 @@ int dsdtm_warp_affine_batch(dsdtm_ctx* c, const int* ref_slot, const double* A, 
     stage_end(c, 1);
     DSDTM_CUDA(c, cudaMemcpyAsync(patch10_out, c->patches_d, (size_t)n * 100, cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dsdtm_feature_align_batch(dsdtm_ctx* c, int cur_slot, const dsdtm_candidate* cands, int n, int max_search_level, int max_iters,
+                              double* px_out, int* level_out, uint8_t* converged, double* A_out)
+{
+    if (!c || !cands || !px_out || !level_out || !converged || n < 0 || max_iters < 0 || max_search_level < 0) return DSDTM_E_ARG;
+    if (check_slot(c, cur_slot)) return DSDTM_E_ARG;
+    if (n == 0) return 0;
+    const size_t cap = (size_t)c->prm.max_batch * std::max(c->prm.max_patches, 1);
+    if ((size_t)n > cap) return fail(c, DSDTM_E_ARG, "n > max_batch * max_patches");
+    if (max_search_level >= c->geo.levels) return fail(c, DSDTM_E_ARG, "max_search_level >= levels");
+    for (int i = 0; i < n; ++i)
+        if (cands[i].ref_slot < 0 || cands[i].ref_slot >= c->prm.max_frames || cands[i].ref_level < 0 || cands[i].ref_level >= c->geo.levels)
+            return fail(c, DSDTM_E_ARG, "candidate: slot / level out of range");
+    c->batch.staged = false;
+    cudaStream_t s = c->stream;
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->cand_d, cands, (size_t)n * sizeof(dsdtm_candidate), cudaMemcpyHostToDevice, s));
+    stage_begin(c, DSDTM_STAGE_CAND_PREP);
+    DSDTM_CUDA(c, launch_candidate_prep(c, n, cur_slot, max_search_level, s));
+    stage_end(c, 1);
+    stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
+    DSDTM_CUDA(c, launch_warp_affine(c, n, c->patches_d, s));
+    stage_end(c, 1);
+    stage_begin(c, DSDTM_STAGE_ALIGN2D);
+    DSDTM_CUDA(c, launch_align2d(c, n, max_iters, s));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(px_out, c->patch_px_d, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(level_out, c->patch_level_d, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(converged, c->patch_conv_d, (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (A_out) DSDTM_CUDA(c, cudaMemcpyAsync(A_out, c->wa_A_d, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {                                   // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
+        const double sc = (double)(1 << level_out[i]);
+        px_out[2 * i] *= sc; px_out[2 * i + 1] *= sc;
+    }
     return 0;
 }
 

@@ -30,8 +30,8 @@ struct StageTimer {
     cudaEvent_t ev0[kMaxEv], ev1[kMaxEv];
     int stage[kMaxEv];
     int n = 0;
-    float ms[DSDTM_STAGE_COUNT] = { 0, 0, 0, 0, 0 };
-    int launches[DSDTM_STAGE_COUNT] = { 0, 0, 0, 0, 0 };
+    float ms[DSDTM_STAGE_COUNT] = { 0, 0, 0, 0, 0, 0 };
+    int launches[DSDTM_STAGE_COUNT] = { 0, 0, 0, 0, 0, 0 };
 };
 
 }  // namespace dsdtm
@@ -86,6 +86,7 @@ struct dsdtm_ctx {
     double* wa_A_d = nullptr;
     float* wa_px_d = nullptr;
     int* wa_meta_d = nullptr;                    // 3 ints per candidate: slot, ref_level, search_level
+    dsdtm_candidate* cand_d = nullptr;           // max_batch * max_patches candidates (fused pipeline)
 
     // pinned host staging for small synchronous calls
     uint8_t* pinned = nullptr;
@@ -135,6 +136,7 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
                                 bool want_log, cudaStream_t s, int pair0 = 0, int n_pairs_total = 0);
 cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
 cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s);
+cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s);
 int sparse_align_smem_bytes(int nf_pad);
 size_t sparse_align_ws_doubles(int max_feats);
 cudaError_t sparse_align_init(dsdtm_ctx* c);

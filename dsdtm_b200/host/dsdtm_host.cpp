@@ -419,9 +419,7 @@ int Sprase_ImgAlign::Run(FramePtr cur, FramePtr ref)              // ref: src/Sp
 
 // ================================================================================================ Feature_Alignment
 struct Feature_Alignment::Prepared {
-    int ref_slot, ref_level, search_level;
-    double A[4];
-    float ref_px[2];
+    dsdtm_candidate c;     // everything SolveAffineMatrix reads, snapshotted on the tracking thread
 };
 
 Feature_Alignment::Feature_Alignment(CameraPtr camera) : mCam(camera)   // ref: src/Feature_alignment.cpp:11-44
@@ -475,19 +473,23 @@ int Feature_Alignment::GetBestSearchLevel(Matrix2d A, int max_level)      // ref
     return L;
 }
 
-// host-side map walk of FindMatchDirect up to (not including) the pixel work (ref: :128-146)
-bool Feature_Alignment::Prepare(const MapPoint* mp, const FramePtr frame, const Vector2d&, Prepared& out)
+// host-side map walk of FindMatchDirect (ref: :128-140): the observation lookup and the two early-outs. The arithmetic that
+// follows (SolveAffineMatrix, GetBestSearchLevel, WarpAffine, Align2D) runs on the device: dsdtm_feature_align_batch.
+bool Feature_Alignment::Prepare(const MapPoint* mp, const FramePtr frame, const Vector2d& px, Prepared& out)
 {
     Feature* rf = nullptr;
     KeyFrame* kf = nullptr;
     if (!mp->Get_ClosetObs(frame.get(), rf, kf)) return false;
     if (!mCam->IsInImage(Point2f(rf->mpx.x / (1 << rf->mlevel), rf->mpx.y / (1 << rf->mlevel)), mHalf_PatchSize + 1, rf->mlevel)) return false;
-    const Matrix2d A = SolveAffineMatrix(kf, frame, rf, mp);
-    out.search_level = GetBestSearchLevel(A, mPyr_levels - 3);
-    out.ref_slot = GpuRuntime::Instance().Resident(kf->mGpu);
-    out.ref_level = rf->mlevel;
-    out.A[0] = A(0, 0); out.A[1] = A(0, 1); out.A[2] = A(1, 0); out.A[3] = A(1, 1);
-    out.ref_px[0] = rf->mpx.x; out.ref_px[1] = rf->mpx.y;
+    dsdtm_candidate& c = out.c;
+    c.ref_slot = GpuRuntime::Instance().Resident(kf->mGpu);
+    c.ref_level = rf->mlevel;
+    c.ref_px[0] = rf->mpx.x; c.ref_px[1] = rf->mpx.y;
+    const Vector3d P = rf->Mpt->Get_Pose(), O = kf->Get_CameraCnt();
+    const SE3 T = frame->Get_Pose() * kf->Get_Pose().inverse();          // ref: :181
+    for (int k = 0; k < 3; ++k) { c.ref_normal[k] = rf->mNormal[k]; c.ref_point_w[k] = P[k]; c.kf_center[k] = O[k]; }
+    for (int k = 0; k < 7; ++k) c.pose_c2r[k] = T.data()[k];
+    c.px[0] = px[0]; c.px[1] = px[1];
     return true;
 }
 
@@ -500,9 +502,7 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
     GpuRuntime& rt = GpuRuntime::Instance();
     struct Item { Candidate* cand; bool prepared; int batch_index; };
     std::vector<std::vector<Item>> items(mCells.size());
-    std::vector<int> ref_slot, ref_level, search_level;
-    std::vector<double> A, px;
-    std::vector<float> ref_px;
+    std::vector<dsdtm_candidate> cands;
     for (size_t ci = 0; ci < mCells.size(); ++ci) {
         Cell* cell = mCells[ci];
         cell->sort([](Candidate& a, Candidate& b) { return a.mMpPoint->Get_FoundNums() > b.mMpPoint->Get_FoundNums(); });   // ref: :88,123-126
@@ -511,24 +511,20 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
             Prepared p;
             if (!c.mMpPoint->IsBad() && Prepare(c.mMpPoint, frame, c.mPx, p)) {
                 it.prepared = true;
-                it.batch_index = (int)ref_slot.size();
-                ref_slot.push_back(p.ref_slot); ref_level.push_back(p.ref_level); search_level.push_back(p.search_level);
-                A.insert(A.end(), p.A, p.A + 4);
-                ref_px.push_back(p.ref_px[0]); ref_px.push_back(p.ref_px[1]);
-                px.push_back(c.mPx[0] / (1 << p.search_level)); px.push_back(c.mPx[1] / (1 << p.search_level));   // ref: :150
+                it.batch_index = (int)cands.size();
+                cands.push_back(p.c);
             }
             items[ci].push_back(it);
         }
     }
-    const int n = (int)ref_slot.size();
-    std::vector<uint8_t> patches((size_t)n * 100), conv(n);
+    const int n = (int)cands.size();
+    std::vector<double> px((size_t)2 * n);
+    std::vector<int> search_level(n);
+    std::vector<uint8_t> conv(n);
     if (n > 0) {
         const int cur_slot = rt.Resident(frame->mGpu);
-        // a re-upload of `frame` may have evicted a keyframe slot resolved above: resolve again (cheap, usually a no-op)
-        if (dsdtm_warp_affine_batch(rt.ctx(), ref_slot.data(), A.data(), ref_px.data(), ref_level.data(), search_level.data(), n, patches.data()) != 0)
-            throw std::runtime_error(std::string("dsdtm_warp_affine_batch: ") + dsdtm_last_error(rt.ctx()));
-        if (dsdtm_align2d_batch(rt.ctx(), cur_slot, search_level.data(), patches.data(), px.data(), n, 10, conv.data()) != 0)
-            throw std::runtime_error(std::string("dsdtm_align2d_batch: ") + dsdtm_last_error(rt.ctx()));
+        if (dsdtm_feature_align_batch(rt.ctx(), cur_slot, cands.data(), n, mPyr_levels - 3, 10, px.data(), search_level.data(), conv.data(), nullptr) != 0)
+            throw std::runtime_error(std::string("dsdtm_feature_align_batch: ") + dsdtm_last_error(rt.ctx()));
     }
     // replay (ref: :75-82, :91-118)
     int matches = 0;
@@ -540,7 +536,7 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
             if (!it.prepared) continue;
             const int b = it.batch_index;
             const int L = search_level[b];
-            c.mPx = Vector2d(px[2 * b] * (1 << L), px[2 * b + 1] * (1 << L));   // ref: :154 (tPt is updated even on failure)
+            c.mPx = Vector2d(px[2 * b], px[2 * b + 1]);            // ref: :154 (tPt is updated even on failure; already level-0 scaled)
             if (!conv[b]) continue;
             c.mMpPoint->IncreaseFound();
             Feature* f = new Feature(frame.get(), Point2f((float)c.mPx[0], (float)c.mPx[1]), L);
@@ -561,14 +557,13 @@ bool Feature_Alignment::FindMatchDirect(const MapPoint* mp, const FramePtr frame
     Prepared p;
     if (!Prepare(mp, frame, pt, p)) return false;
     GpuRuntime& rt = GpuRuntime::Instance();
-    uint8_t patch[100], conv = 0;
-    double px[2] = { pt[0] / (1 << p.search_level), pt[1] / (1 << p.search_level) };
-    const int cur_slot = rt.Resident(frame->mGpu);
-    if (dsdtm_warp_affine_batch(rt.ctx(), &p.ref_slot, p.A, p.ref_px, &p.ref_level, &p.search_level, 1, patch) != 0 ||
-        dsdtm_align2d_batch(rt.ctx(), cur_slot, &p.search_level, patch, px, 1, 10, &conv) != 0)
+    uint8_t conv = 0;
+    double px[2];
+    int L = 0;
+    if (dsdtm_feature_align_batch(rt.ctx(), rt.Resident(frame->mGpu), &p.c, 1, mPyr_levels - 3, 10, px, &L, &conv, nullptr) != 0)
         throw std::runtime_error(std::string("FindMatchDirect: ") + dsdtm_last_error(rt.ctx()));
-    pt = Vector2d(px[0] * (1 << p.search_level), px[1] * (1 << p.search_level));
-    level = p.search_level;
+    pt = Vector2d(px[0], px[1]);
+    level = L;
     return conv != 0;
 }
 

@@ -80,7 +80,7 @@ typedef struct {
 
 /* Per-stage device timing, filled when profiling is on (CUDA events on the context's stream). */
 enum { DSDTM_STAGE_PYRAMID = 0, DSDTM_STAGE_FAST = 1, DSDTM_STAGE_SPARSE_ALIGN = 2, DSDTM_STAGE_ALIGN2D = 3,
-       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_COUNT = 5 };
+       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_CAND_PREP = 5, DSDTM_STAGE_COUNT = 6 };
 
 /* ---------------------------------------------------------------- context ---------------------------------- */
 int         dsdtm_abi_version(void);
@@ -160,6 +160,28 @@ int dsdtm_align2d_batch(dsdtm_ctx* ctx, int cur_slot, const int* level, const ui
  * ref_px = n x 2 floats (Feature::mpx), ref_level / search_level per candidate, patch10_out = n x 100 bytes. */
 int dsdtm_warp_affine_batch(dsdtm_ctx* ctx, const int* ref_slot, const double* A, const float* ref_px,
                             const int* ref_level, const int* search_level, int n, uint8_t* patch10_out);
+
+/* ---------------------------------------------------------------- (f-1) fused candidate pipeline ---------- */
+/* One candidate of Feature_Alignment::FindMatchDirect after the host-side observation lookup (MapPoint::Get_ClosetObs,
+ * ref: src/MapPoint.cpp:133-174; src/Feature_alignment.cpp:135-140): everything SolveAffineMatrix reads. */
+typedef struct {
+    int    ref_slot;        /* frame slot of the reference keyframe's pyramid */
+    int    ref_level;       /* reference Feature::mlevel */
+    float  ref_px[2];       /* reference Feature::mpx */
+    double ref_normal[3];   /* reference Feature::mNormal */
+    double ref_point_w[3];  /* reference feature's Mpt->Get_Pose() (ref: :167) */
+    double kf_center[3];    /* KeyFrame::Get_CameraCnt() */
+    double pose_c2r[7];     /* T_cur * T_kf^-1 (ref: :181) */
+    double px[2];           /* Candidate::mPx: reprojection of the map point into the current frame, level 0 */
+} dsdtm_candidate;          /* 160 bytes */
+
+/* replaces SolveAffineMatrix + GetBestSearchLevel + WarpAffine + GetPatchNoBoarder + Align2DGaussNewton of FindMatchDirect
+ * (ref: src/Feature_alignment.cpp:142-156) for n candidates against ONE current frame, without returning to the host
+ * between the stages. max_search_level = Camera.MaxPyraLevels - 3 (ref: :144). Outputs: px_out = n x 2 refined positions
+ * scaled back to level 0 (ref: :154), level_out = search level (ref: :156), converged = return value; A_out (optional,
+ * may be NULL) = n x 4 row-major affine matrices for inspection. */
+int dsdtm_feature_align_batch(dsdtm_ctx* ctx, int cur_slot, const dsdtm_candidate* cands, int n, int max_search_level,
+                              int max_iters, double* px_out, int* level_out, uint8_t* converged, double* A_out);
 
 /* ---------------------------------------------------------------- batched front end (sweep / bench) -------- */
 /* One "step" over n_pairs independent frame pairs: [pyramid(cur)] -> sparse align -> Align2D of the pair's patches

@@ -196,6 +196,47 @@ def test_warp_affine_bit_exact(ctx, scenario):
     assert all(len(set(got[i])) == 1 for i in range(n) if sl[i] >= 1)
 
 
+def test_fused_candidate_pipeline_matches_oracle_stage_by_stage(ctx, scenario):
+    """SolveAffineMatrix + GetBestSearchLevel + WarpAffine + Align2D as one device pipeline
+    (dsdtm_feature_align_batch) against the oracle's per-candidate chain (ref: src/Feature_alignment.cpp:142-156)."""
+    from dsdtm_b200 import capi
+    sc = scenario
+    _upload(ctx, sc)                     # slot 0 = reference keyframe, slot 1 = current frame
+    packed, offs, ws, hs = sc["ref_pyr"]
+    oc = H.ocam(sc["cam"])
+    F = sc["feats"]
+    n = len(F)
+    rng = np.random.default_rng(8)
+    # current pose = ground truth, plus a few exaggerated motions so that det(A) > 3 exercises search levels >= 1 (Q3 path)
+    poses = np.tile(sc["T_c2r"], (n, 1))
+    for j in range(0, n, 9):
+        poses[j] = S.pose_from_xi([0.0, 0.0, -1.05 - 0.2 * rng.uniform(), 0, 0, 0])       # move towards the scene: magnification > sqrt(3)
+    kf_center = sc["ref_center"]
+    cands = np.zeros(n, capi.CANDIDATE_DT)
+    fx, fy, cx, cy = (float(np.float32(sc["cam"][k])) for k in ("fx", "fy", "cx", "cy"))
+    for i in range(n):
+        q = O.se3_act(poses[i], F[i]["point_w"])
+        cands[i]["ref_slot"] = 0; cands[i]["ref_level"] = F[i]["level"]; cands[i]["ref_px"] = F[i]["px"]
+        cands[i]["ref_normal"] = F[i]["normal"]; cands[i]["ref_point_w"] = F[i]["point_w"]; cands[i]["kf_center"] = kf_center
+        cands[i]["pose_c2r"] = poses[i]
+        cands[i]["px"] = (fx * q[0] / q[2] + cx + rng.uniform(-1, 1), fy * q[1] / q[2] + cy + rng.uniform(-1, 1))
+    px, lv, conv, A = ctx.feature_align_batch(1, cands, 2, 10, want_A=True)
+    levels_seen = set()
+    for i in range(n):
+        Ao = O.solve_affine(oc, kf_center, F[i]["point_w"], F[i]["normal"], F[i]["px"], int(F[i]["level"]), poses[i])
+        assert np.allclose(A[i], Ao, rtol=1e-13, atol=1e-15), i
+        Lo = O.best_search_level(Ao, 2)
+        assert lv[i] == Lo
+        levels_seen.add(Lo)
+        patch = O.warp_affine(Ao, O.pyr_level(packed, offs, ws, hs, int(F[i]["level"])), F[i]["px"], int(F[i]["level"]), Lo)
+        p, c, _ = O.align2d(O.pyr_level(sc["cur_pyr"][0], offs, ws, hs, Lo), patch, 10, cands[i]["px"] / (1 << Lo))
+        assert c == conv[i], i
+        assert np.allclose(p * (1 << Lo), px[i], atol=PX_TOL * (1 << Lo), equal_nan=True), i
+    assert len(levels_seen) >= 2 and conv.sum() > 200
+    # Q3: no candidate with search level >= 1 can converge (constant patch -> singular H)
+    assert not conv[lv >= 1].any()
+
+
 def test_staged_batch_run_graph_replay_and_e2e(ctx):
     """dsdtm_batch_stage/run/fetch (CUDA-graph replay on HBM-resident inputs) and the host-buffer e2e call give the same
     results as the single-pair entry points."""
