@@ -235,6 +235,31 @@ def run_ours(args):
         ctx.profile(False)
     fast_bytes = nfast * (sum(g.ws[l] * g.hs[l] for l in range(LEVELS)) + ctx.n_cells * 16)
 
+    # ---------------- single-pair latency (BASELINE target: < 200 us sparse alignment + feature refinement per 640x480 frame)
+    def stage_n(n):
+        ctx.batch_stage(batch["ref_slots"][:n], batch["cur_slots"][:n], batch["feats"][:n], batch["n_feats"][:n], batch["centers"][:n],
+                        batch["poses_in"][:n], ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], batch["patches"][:n],
+                        batch["patch_px"][:n], batch["patch_level"][:n], ALIGN2D_ITERS)
+    stage_n(1)
+    for _ in range(5):
+        ctx.batch_run(1)
+    ctx.sync()
+    reps = 50
+    ctx.timer_start()
+    for _ in range(reps):
+        ctx.batch_run(1)                      # CUDA-graph replay of pyramid + sparse align + align2d for ONE pair
+    lat_ms = ctx.timer_stop() / reps
+    ctx.profile(True); ctx.profile_get(reset=True)
+    for _ in range(reps):
+        ctx.batch_run(1)
+    lst = ctx.profile_get(reset=True)
+    ctx.profile(False)
+    latency = {"frame_us": lat_ms * 1e3, "sparse_align_us": lst["sparse_align"][0] / reps * 1e3, "align2d_us": lst["align2d"][0] / reps * 1e3,
+               "pyramid_us": lst["pyramid"][0] / reps * 1e3, "sparse_plus_refine_us": (lst["sparse_align"][0] + lst["align2d"][0]) / reps * 1e3,
+               "note": "one pair, 300 features + 300 patches; frame_us = graph replay of all 6 kernels (events on the launching stream); "
+                       "per-stage numbers from direct launches with an event pair per stage"}
+    restage()
+
     # ---------------- end-to-end through the C-ABI with host buffers
     h, w = cam["height"], cam["width"]
     pin = capi.pinned_empty
@@ -300,6 +325,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (2 * B * ctx.L.dsdtm_frame_stride(ctx.hp) / 1e6)},
             "us_per_pair": ms_per_step * 1e3 / B,
             "gn_iterations_per_pair": iters,
+            "latency": latency,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t.item()) * 1e3 / args.steps, "timer": "host wall clock around the C-ABI call"},
             "gpu_launches": int(launches),

@@ -15,6 +15,15 @@
 
 namespace dsdtm {
 
+DSDTM_HD double dsdtm_rsqrt(double v)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrt(v);
+#else
+    return 1.0 / sqrt(v);
+#endif
+}
+
 template <class T>
 DSDTM_HD void cswap(bool p, T& a, T& b)
 {
@@ -169,8 +178,9 @@ DSDTM_HD bool ldlt6_solve_spd(const double (&A)[6][6], const double (&b)[6], dou
 // Split form of ldlt6_solve_spd for callers that reuse one factorisation for several right-hand sides (the sparse-alignment
 // H only changes when the visibility set changes): factor once into 15 strictly-lower entries of L (row-major packed) and the
 // 6 pivots d, then substitute per right-hand side. Same arithmetic and operation order as ldlt6_solve_spd.
-DSDTM_HD bool ldlt6_factor_spd(const double (&A)[6][6], double (&Lp)[15], double (&d)[6])
+DSDTM_HD bool ldlt6_factor_spd(const double (&A)[6][6], double (&Lp)[15], double (&dinv)[6])
 {
+    double d[6];
     double L[6][6];
     double maxdiag = 0.0;
 #pragma unroll
@@ -185,6 +195,7 @@ DSDTM_HD bool ldlt6_factor_spd(const double (&A)[6][6], double (&Lp)[15], double
         d[k] = dk;
         ok = ok && (dk > thresh);
         const double inv = 1.0 / dk;
+        dinv[k] = inv;                       // the substitution multiplies by the reciprocal pivot (one division per pivot, none per solve)
 #pragma unroll
         for (int i = k + 1; i < 6; ++i) {
             double v = A[i][k];
@@ -200,7 +211,7 @@ DSDTM_HD bool ldlt6_factor_spd(const double (&A)[6][6], double (&Lp)[15], double
     return ok;
 }
 
-DSDTM_HD void ldlt6_subst_spd(const double (&Lp)[15], const double (&d)[6], const double (&b)[6], double (&x)[6])
+DSDTM_HD void ldlt6_subst_spd(const double (&Lp)[15], const double (&dinv)[6], const double (&b)[6], double (&x)[6])
 {
     double y[6];
 #pragma unroll
@@ -211,7 +222,7 @@ DSDTM_HD void ldlt6_subst_spd(const double (&Lp)[15], const double (&d)[6], cons
         y[i] = v;
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] = y[i] / d[i];
+    for (int i = 0; i < 6; ++i) y[i] = y[i] * dinv[i];
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double v = y[i];
@@ -226,22 +237,37 @@ struct Quat { double w, x, y, z; };
 // out = T * exp(x); pose7 = {qw,qx,qy,qz,tx,ty,tz}. (ref: src/Sprase_ImageAlign.cpp:335; Sophus SE3::exp, SE3::operator*=)
 DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&out)[7])
 {
+    // This runs on ONE lane while the rest of the CTA waits, so the dependent chain is kept short: one sincos (the full-angle
+    // values come from the half-angle identities), reciprocals instead of repeated divisions. Against the literal Sophus
+    // sequence (the oracle) the result differs by a few ulp (tests/test_host_math.py: <= 1e-15 absolute).
     const double SMALL_EPS = 1e-10;
     const double u0 = x[0], u1 = x[1], u2 = x[2], o0 = x[3], o1 = x[4], o2 = x[5];
-    const double theta = sqrt(o0 * o0 + o1 * o1 + o2 * o2);
+    const double t2 = o0 * o0 + o1 * o1 + o2 * o2;
+    const double theta = sqrt(t2);
     const double half = 0.5 * theta;
-    double imag;
-    const double real = cos(half);
+    double sh, ch;
+#if defined(__CUDA_ARCH__)
+    sincos(half, &sh, &ch);
+#else
+    sh = sin(half); ch = cos(half);
+#endif
+    double imag, a, b;
     if (theta < SMALL_EPS) {
-        const double t2 = theta * theta, t4 = t2 * t2;
+        const double t4 = t2 * t2;
         imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
+        a = 0.0; b = 0.0;
     } else {
-        imag = sin(half) / theta;
+        const double it = 1.0 / theta;
+        imag = sh * it;
+        const double ct = 2.0 * ch * ch - 1.0, st = 2.0 * sh * ch;     // cos(theta), sin(theta)
+        const double it2 = it * it;
+        a = (1 - ct) * it2;                                            // (1 - cos theta) / theta^2
+        b = (theta - st) * (it2 * it);                                 // (theta - sin theta) / theta^3
     }
-    double ew = real, ex = imag * o0, ey = imag * o1, ez = imag * o2;
+    double ew = ch, ex = imag * o0, ey = imag * o1, ez = imag * o2;
     {
-        const double n = sqrt(ex * ex + ey * ey + ez * ez + ew * ew);
-        ex /= n; ey /= n; ez /= n; ew /= n;
+        const double rn = dsdtm_rsqrt(ex * ex + ey * ey + ez * ez + ew * ew);
+        ex *= rn; ey *= rn; ez *= rn; ew *= rn;
     }
     // V = I + a*Omega + b*Omega^2 (or R(e) for tiny theta);  et = V * upsilon
     double et0, et1, et2;
@@ -254,9 +280,6 @@ DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&o
         et1 = (txy + twz) * u0 + (1 - (txx + tzz)) * u1 + (tyz - twx) * u2;
         et2 = (txz - twy) * u0 + (tyz + twx) * u1 + (1 - (txx + tyy)) * u2;
     } else {
-        const double t2 = theta * theta;
-        const double a = (1 - cos(theta)) / t2;
-        const double b = (theta - sin(theta)) / (t2 * theta);
         // Omega = [0 -o2 o1; o2 0 -o0; -o1 o0 0]; Omega^2 entries
         const double O2_00 = -o2 * o2 - o1 * o1, O2_01 = o1 * o0, O2_02 = o2 * o0;
         const double O2_10 = o0 * o1, O2_11 = -o2 * o2 - o0 * o0, O2_12 = o2 * o1;
@@ -277,8 +300,8 @@ DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&o
     const double rx = aw * ex + ax * ew + ay * ez - az * ey;
     const double ry = aw * ey + ay * ew + az * ex - ax * ez;
     const double rz = aw * ez + az * ew + ax * ey - ay * ex;
-    const double n = sqrt(rx * rx + ry * ry + rz * rz + rw * rw);
-    out[0] = rw / n; out[1] = rx / n; out[2] = ry / n; out[3] = rz / n;
+    const double rn = dsdtm_rsqrt(rx * rx + ry * ry + rz * rz + rw * rw);
+    out[0] = rw * rn; out[1] = rx * rn; out[2] = ry * rn; out[3] = rz * rn;
     out[4] = T[4] + (et0 + aw * uv0 + c0);
     out[5] = T[5] + (et1 + aw * uv1 + c1);
     out[6] = T[6] + (et2 + aw * uv2 + c2);

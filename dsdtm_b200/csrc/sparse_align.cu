@@ -126,7 +126,15 @@ struct RefRows {
 // the serial tail of one GN iteration, kept out of line: it runs on one lane once per iteration and must not bloat
 // (or evict from the instruction cache) the per-feature loop. H only changes when the visibility set changes, so the
 // factorisation is cached in shared memory (sF: 15 entries of L, 6 pivots, 1 flag) and most iterations only substitute.
-__device__ __noinline__ void solve_and_update(const double* __restrict__ sH /*21 packed*/, double* __restrict__ sF /*22*/, bool refactor,
+#ifndef DSDTM_SA_TAIL_INLINE
+#define DSDTM_SA_TAIL_INLINE 1
+#endif
+#if DSDTM_SA_TAIL_INLINE
+#define DSDTM_TAIL_ATTR __forceinline__
+#else
+#define DSDTM_TAIL_ATTR __noinline__
+#endif
+__device__ DSDTM_TAIL_ATTR void solve_and_update(const double* __restrict__ sH /*21 packed*/, double* __restrict__ sF /*22*/, bool refactor,
                                               const double (&bvec)[6], double (&x)[6])
 {
     if (refactor) {
@@ -159,7 +167,7 @@ __device__ __noinline__ void solve_and_update(const double* __restrict__ sH /*21
     }
 }
 
-__device__ __noinline__ void pose_update(const double* T, const double (&x)[6], double* Tn)
+__device__ DSDTM_TAIL_ATTR void pose_update(const double* T, const double (&x)[6], double* Tn)
 {
     double Tc[7], To[7];
 #pragma unroll
@@ -277,8 +285,15 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_S
                 qrot(qw, qx, qy, qz, P0, P1, P2, Q0, Q1, Q2);                                  // ref: :254
                 Q0 = __dadd_rn(Q0, t0); Q1 = __dadd_rn(Q1, t1); Q2 = __dadd_rn(Q2, t2);
                 // Camera2Pixel * tScale (ref: src/Camera.cpp:167-171, :255): (fx*X)/Z + cx
+#if DSDTM_SA_STRICT
                 const double u = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fx, Q0), Q2), cx), scale);
                 const double v = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fy, Q1), Q2), cy), scale);
+#else
+                // one reciprocal instead of two divisions: u, v within 1 ulp (1e-13 px) of the reference's (fx*X)/Z
+                const double iz = 1.0 / Q2;
+                const double u = __dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(fx, Q0), iz), cx), scale);
+                const double v = __dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(fy, Q1), iz), cy), scale);
+#endif
                 const double uf = floor(u), vf = floor(v);
                 // ref: :262 with border 3; evaluated in double so that NaN / huge values are rejected like the reference's INT_MIN
                 if (!(uf >= 3.0 && vf >= 3.0 && uf < (double)(cols - 3) && vf < (double)(rows - 3))) return;
@@ -628,8 +643,15 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 8 : (WPP == 4 ? 4 : (WP
                 qrot(qw, qx, qy, qz, P0, P1, P2, Q0, Q1, Q2);                                  // ref: :254
                 Q0 = __dadd_rn(Q0, t0); Q1 = __dadd_rn(Q1, t1); Q2 = __dadd_rn(Q2, t2);
                 // Camera2Pixel * tScale (ref: src/Camera.cpp:167-171, :255): (fx*X)/Z + cx
+#if DSDTM_SA_STRICT
                 const double u = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fx, Q0), Q2), cx), scale);
                 const double v = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fy, Q1), Q2), cy), scale);
+#else
+                // one reciprocal instead of two divisions: u, v within 1 ulp (1e-13 px) of the reference's (fx*X)/Z
+                const double iz = 1.0 / Q2;
+                const double u = __dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(fx, Q0), iz), cx), scale);
+                const double v = __dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(fy, Q1), iz), cy), scale);
+#endif
                 const double uf = floor(u), vf = floor(v);
                 // ref: :262 with border 3; evaluated in double so that NaN / huge values are rejected like the reference's INT_MIN
                 if (!(uf >= 3.0 && vf >= 3.0 && uf < (double)(cols - 3) && vf < (double)(rows - 3))) continue;
