@@ -443,7 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step")
-    ap.add_argument("--scenes", type=int, default=8, help="distinct ray-cast scenes (tiled to --pairs)")
+    ap.add_argument("--scenes", type=int, default=16, help="distinct ray-cast scenes (tiled to --pairs)")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -14,7 +14,8 @@
 //   pyrdown_tile_kernel (any size; odd / tiny levels): 64x16 output tile staged through shared memory with reflect-101.
 // HBM-bound stage: algorithmic bytes per frame = sum_l (w_{l-1} h_{l-1} + w_l h_l) (510 000 B @640x480x5).
 // Round-1 profile (profiles/r1_bench_first.md): the tile kernel alone ran at 600 GB/s = 9 % of HBM peak, issue-bound on
-// byte-wide shared-memory traffic -- hence the register/DP4A strip kernel.
+// byte-wide shared-memory traffic -- hence the register/DP4A strip kernel. (Fetching the 3 halo bytes from neighbouring lanes by
+// shuffle instead of two extra L1-hit 4-byte loads was measured SLOWER: 0.384 vs 0.267 ms per 2072 frames.)
 #include "ctx.cuh"
 
 namespace dsdtm {

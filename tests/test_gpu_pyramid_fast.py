@@ -45,6 +45,23 @@ def test_pyramid_odd_and_tiny_shapes(shape):
     c.close()
 
 
+def test_pyramid_tile_kernel_option_is_bit_exact_too(ctx, scenario):
+    """"pyramid_kernel" = 1 forces the shared-memory tile kernel on every level (the strip kernel's fallback path)."""
+    from dsdtm_b200 import capi
+    ctx.set_option("pyramid_kernel", 1)
+    try:
+        ctx.upload(5, scenario["cur_img"])
+    finally:
+        ctx.set_option("pyramid_kernel", 0)
+    packed, offs, ws, hs = scenario["cur_pyr"]
+    for l in range(5):
+        assert (ctx.download_level(5, l) == O.pyr_level(packed, offs, ws, hs, l)).all(), l
+    with pytest.raises(capi.DsdtmError):
+        ctx.set_option("pyramid_kernel", 7)
+    with pytest.raises(capi.DsdtmError):
+        ctx.set_option("no_such_option", 1)
+
+
 def test_pyramid_batch_and_rebuild(ctx, scenario):
     imgs = np.stack([scenario["ref_img"], scenario["cur_img"], scenario["ref_img"][::-1].copy()])
     ctx.upload_batch(2, imgs)
