@@ -93,6 +93,46 @@ def test_sparse_align_skips_uninitialised_zero_and_border_features(ctx, scenario
     _compare_traces(lo, lg)
 
 
+def test_sparse_align_many_features_and_other_geometry(built):
+    """Camera.Max_fts = 500 (Config/kinect.yaml:68) on EuRoC geometry: several features per lane in every kernel variant,
+    capacity 512, 4-level pyramid, cell size 30."""
+    from dsdtm_b200 import capi
+    cam = dict(S.EUROC)
+    sc = H.make_scenario(41, cam, levels=4, max_fts=500)
+    assert len(sc["feats"]) > 320
+    c = capi.Context(cam, levels=4, cell_size=30, max_feats=512, max_patches=8, max_frames=2, max_batch=1)
+    c.upload(0, sc["ref_img"]); c.upload(1, sc["cur_img"])
+    packed, offs, ws, hs = sc["ref_pyr"]
+    po, no, lo = O.sparse_align(H.ocam(cam), packed, sc["cur_pyr"][0], offs, ws, hs, sc["feats"], sc["ref_center"], S.IDENTITY, 4, 0, 30)
+    for wpp in (0, 1, 4):
+        c.set_option("sa_warps_per_pair", wpp)
+        pg, ng, lg = c.sparse_align(0, 1, sc["feats"], sc["ref_center"], S.IDENTITY, 4, 0, 30)
+        d = S.pose_dist(po, pg)
+        assert d[0] < POSE_TOL and d[1] < POSE_TOL and no == ng, (wpp, d)
+        _compare_traces(lo, lg)
+    with pytest.raises(capi.DsdtmError):                      # more features than the capacity is an error, never a silent truncation
+        c.sparse_align(0, 1, np.zeros(600, O.REF_FEAT_DT), sc["ref_center"], S.IDENTITY, 4, 0, 30)
+    c.close()
+
+
+def test_sparse_align_rank_deficient_system_is_handled(ctx, scenario):
+    """Two visible features give a rank-4 H. In floating point the two 'zero' pivots come out as rounding noise (1e-17
+    relative), Eigen's ldlt().solve divides by them (its zero rule only triggers below 5e-309), and the step is dominated
+    by that noise IN THE REFERENCE ITSELF: it changes with the summation order, so no implementation can match it bit for
+    bit. What must hold: the SPD fast path rejects the system and hands it to the pivoted LDL^T (no NaN, no crash), the
+    pose-independent quantities agree (visible count, first chi2), and the result is deterministic."""
+    _upload(ctx, scenario)
+    F = scenario["feats"][:2].copy()
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    po, no, lo = O.sparse_align(H.ocam(scenario["cam"]), packed, scenario["cur_pyr"][0], offs, ws, hs, F, scenario["ref_center"], S.IDENTITY, 2, 0, 4)
+    pg, ng, lg = ctx.sparse_align(0, 1, F, scenario["ref_center"], S.IDENTITY, 2, 0, 4)
+    pg2, ng2, lg2 = ctx.sparse_align(0, 1, F, scenario["ref_center"], S.IDENTITY, 2, 0, 4)
+    assert lo[0]["n_pts"] == lg[0]["n_pts"] == 2
+    assert abs(lo[0]["chi2"] - lg[0]["chi2"]) <= 1e-9 * lo[0]["chi2"]
+    assert np.isfinite(pg).all() and np.isfinite(lg["x"]).all()
+    assert (pg == pg2).all() and ng == ng2 and (lg["x"] == lg2["x"]).all()
+
+
 def test_sparse_align_nothing_visible_nan_chi2(ctx, scenario):
     """Q2: chi2/tResNum is NaN when no feature is visible; the pose is left unchanged."""
     _upload(ctx, scenario)
