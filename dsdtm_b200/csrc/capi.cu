@@ -229,7 +229,7 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
 {
     if (!c || !key) return DSDTM_E_ARG;
     if (std::strcmp(key, "sa_warps_per_pair") == 0) {
-        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 5 && value != 10) return fail(c, DSDTM_E_ARG, "sa_warps_per_pair must be 0, 1, 2, 4, 5 or 10");
+        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 5 && value != 10) return fail(c, DSDTM_E_ARG, "sa_warps_per_pair must be 0, 1, 2, 3, 4, 5 or 10");
         c->sa_wpp_override = value;
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;

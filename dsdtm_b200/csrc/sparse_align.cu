@@ -187,7 +187,7 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 #endif
 
 template <int WPP>
-__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_SA_MINB4 : (WPP == 5 ? 3 : 1))) sparse_align_kernel(const SaArgs a)
+__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? 4 : (WPP == 4 ? DSDTM_SA_MINB4 : (WPP == 5 ? 3 : 1)))) sparse_align_kernel(const SaArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int NF = a.nf;
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 4 ? DSDTM_S
 // samples per feature instead of re-deriving the 6x6 grid from bytes (~465 instead of ~700 instructions per feature and
 // iteration), and shared memory drops to 49 B / feature. A lane only ever reads what it wrote itself.
 template <int WPP>
-__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 8 : (WPP == 4 ? 4 : (WPP == 5 ? 3 : 1))) sparse_align_ws_kernel(const SaArgs a)
+__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 8 : (WPP == 3 ? 4 : (WPP == 4 ? 4 : (WPP == 5 ? 3 : 1)))) sparse_align_ws_kernel(const SaArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int NF = a.nf;
@@ -853,12 +853,14 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
     const int bytes = smem_bytes(nf);
     cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     const int bw = smem_bytes_ws(nf);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
@@ -894,6 +896,7 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
     switch (sparse_align_pick_wpp(c, n_pairs_total > 0 ? n_pairs_total : n_pairs)) {
     case 1: return launch<1>(a, n_pairs, s);
     case 2: return launch<2>(a, n_pairs, s);
+    case 3: return launch<3>(a, n_pairs, s);
     case 4: return launch<4>(a, n_pairs, s);
     case 5: return launch<5>(a, n_pairs, s);
     default: return launch<10>(a, n_pairs, s);
