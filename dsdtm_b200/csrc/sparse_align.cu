@@ -49,8 +49,17 @@ constexpr int NB_WORDS = 14;   // 7 rows x 2 words (7 bytes) of the reference ne
 
 __device__ __forceinline__ double u8_to_f64(uint32_t word, int byte)
 {
+#ifndef DSDTM_SA_CVT
+#define DSDTM_SA_CVT 1      // measured (ms per 2072 pairs): 0 magic-number add 0.847, 1 PRMT + I2F.F64 0.816, 2 shift + I2F.F64 0.828; all exact
+#endif
+#if DSDTM_SA_CVT == 0
     // exact int -> double without the slow I2F.F64 path: 2^52 + b has b in its low mantissa bits
     return __hiloint2double(0x43300000, (int)__byte_perm(word, 0, 0x4440 | byte)) - 4503599627370496.0;
+#elif DSDTM_SA_CVT == 1
+    return (double)__byte_perm(word, 0, 0x4440 | byte);                 // PRMT + I2F.F64.U32
+#else
+    return (double)(unsigned char)(word >> (8 * byte));                 // lets ptxas pick I2F.F64.U8 with a byte selector
+#endif
 }
 
 __device__ __forceinline__ void qrot(double qw, double qx, double qy, double qz, double v0, double v1, double v2,
