@@ -144,6 +144,11 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
     CK(cudaEventCreate(&c->ev_b));
     CK(cudaEventCreate(&c->ev_t0));
     CK(cudaEventCreate(&c->ev_t1));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxStepStreams; ++i) {
+        CK(cudaStreamCreateWithFlags(&c->step_stream[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { CK(cudaEventCreate(&c->timer.ev0[i])); CK(cudaEventCreate(&c->timer.ev1[i])); }
 
@@ -190,6 +195,11 @@ void dsdtm_destroy(dsdtm_ctx* c)
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < kMaxStepStreams; ++i) {
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+        if (c->step_stream[i]) cudaStreamDestroy(c->step_stream[i]);
+    }
     for (int i = 0; i < 2; ++i) if (c->copy_stream[i]) cudaStreamDestroy(c->copy_stream[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -237,6 +247,12 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
     if (std::strcmp(key, "sa_variant") == 0) {
         if (value != 0 && value != 1) return fail(c, DSDTM_E_ARG, "sa_variant must be 0 (shared-memory recompute) or 1 (L2 workspace)");
         c->sa_variant = value;
+        for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
+        return 0;
+    }
+    if (std::strcmp(key, "step_chunks") == 0) {
+        if (value < 1 || value > kMaxStepStreams) return fail(c, DSDTM_E_ARG, "step_chunks must be 1..8");
+        c->step_chunks = value;
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
@@ -582,18 +598,39 @@ int dsdtm_batch_stage(dsdtm_ctx* c, int n_pairs, const int* ref_slots, const int
 static int enqueue_step(dsdtm_ctx* c, int flags, cudaStream_t s, bool timed)
 {
     auto& b = c->batch;
-    if (flags & 1) {
-        if (timed) stage_begin(c, DSDTM_STAGE_PYRAMID);
-        DSDTM_CUDA(c, launch_pyramid_slots(c, c->cur_slots_d, b.n_pairs, s));
-        if (timed) stage_end(c, c->geo.levels - 1);
-    }
-    if (timed) stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
-    DSDTM_CUDA(c, launch_sparse_align(c, b.n_pairs, b.feat_stride, b.max_level, b.min_level, b.max_iters, false, s));
-    if (timed) stage_end(c, 1);
-    if (b.patches_per_pair > 0) {
-        if (timed) stage_begin(c, DSDTM_STAGE_ALIGN2D);
-        DSDTM_CUDA(c, launch_align2d(c, b.n_pairs * b.patches_per_pair, b.align_iters, s));
+    const int chunks = (timed || c->step_chunks <= 1 || b.n_pairs < 4 * c->sm_count) ? 1 : std::min(c->step_chunks, kMaxStepStreams);
+    if (chunks == 1) {
+        if (flags & 1) {
+            if (timed) stage_begin(c, DSDTM_STAGE_PYRAMID);
+            DSDTM_CUDA(c, launch_pyramid_slots(c, c->cur_slots_d, b.n_pairs, s));
+            if (timed) stage_end(c, c->geo.levels - 1);
+        }
+        if (timed) stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
+        DSDTM_CUDA(c, launch_sparse_align(c, b.n_pairs, b.feat_stride, b.max_level, b.min_level, b.max_iters, false, s));
         if (timed) stage_end(c, 1);
+        if (b.patches_per_pair > 0) {
+            if (timed) stage_begin(c, DSDTM_STAGE_ALIGN2D);
+            DSDTM_CUDA(c, launch_align2d(c, b.n_pairs * b.patches_per_pair, b.align_iters, s));
+            if (timed) stage_end(c, 1);
+        }
+        return 0;
+    }
+    // Chunked step: the pairs are split into `chunks` groups, each running pyramid -> sparse align -> Align2D on its own
+    // stream (fork / join through events, captured into the same CUDA graph). The per-pair dependency order is unchanged;
+    // the issue-bound Align2D / pyramid kernels of one chunk fill the idle issue slots of the latency-bound sparse-alignment
+    // kernel of another (profiles/r1_step_chunks.md).
+    const int per = (b.n_pairs + chunks - 1) / chunks;
+    DSDTM_CUDA(c, cudaEventRecord(c->ev_fork, s));
+    for (int k = 0; k < chunks; ++k) {
+        const int p0 = k * per, n = std::min(per, b.n_pairs - p0);
+        if (n <= 0) break;
+        cudaStream_t sk = c->step_stream[k];
+        DSDTM_CUDA(c, cudaStreamWaitEvent(sk, c->ev_fork, 0));
+        if (flags & 1) DSDTM_CUDA(c, launch_pyramid_slots(c, c->cur_slots_d + p0, n, sk));
+        DSDTM_CUDA(c, launch_sparse_align(c, n, b.feat_stride, b.max_level, b.min_level, b.max_iters, false, sk, p0, b.n_pairs));
+        if (b.patches_per_pair > 0) DSDTM_CUDA(c, launch_align2d(c, n * b.patches_per_pair, b.align_iters, sk, p0 * b.patches_per_pair));
+        DSDTM_CUDA(c, cudaEventRecord(c->ev_join[k], sk));
+        DSDTM_CUDA(c, cudaStreamWaitEvent(s, c->ev_join[k], 0));
     }
     return 0;
 }
@@ -629,7 +666,10 @@ int dsdtm_batch_run(dsdtm_ctx* c, int flags)
             DSDTM_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
         }
         DSDTM_CUDA(c, cudaGraphLaunch(b.graph[gi], c->stream));
-        c->launches += ((flags & 1) ? c->geo.levels - 1 : 0) + 1 + (b.patches_per_pair > 0 ? 1 : 0);
+        {
+            const int chunks = (c->step_chunks <= 1 || b.n_pairs < 4 * c->sm_count) ? 1 : std::min(c->step_chunks, kMaxStepStreams);
+            c->launches += (long long)chunks * (((flags & 1) ? c->geo.levels - 1 : 0) + 1 + (b.patches_per_pair > 0 ? 1 : 0));
+        }
     }
     DSDTM_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
     return 0;

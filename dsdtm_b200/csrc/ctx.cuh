@@ -36,6 +36,8 @@ struct StageTimer {
 
 }  // namespace dsdtm
 
+namespace dsdtm { static const int kMaxStepStreams = 8; }
+
 struct dsdtm_ctx {
     int device = 0;
     int sm_count = 148;
@@ -47,6 +49,9 @@ struct dsdtm_ctx {
     cudaStream_t copy_stream[2] = { nullptr, nullptr };
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_chunk[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t step_stream[dsdtm::kMaxStepStreams] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[dsdtm::kMaxStepStreams] = {};
+    int step_chunks = 1;                         // dsdtm_batch_run: pairs split over this many concurrent streams
     std::string err;
     long long launches = 0;
     bool profiling = false;

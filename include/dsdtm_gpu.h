@@ -99,7 +99,9 @@ void        dsdtm_host_free(void* p);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 long long   dsdtm_launch_count(const dsdtm_ctx* ctx);
 /* tuning knobs (never change results): "sa_warps_per_pair" = 0 (auto) | 1 | 2 | 4 | 10;
- * "pyramid_kernel" = 0 (auto: register/DP4A strip kernel where the level shape allows) | 1 (shared-memory tile kernel) */
+ * "pyramid_kernel" = 0 (auto: register/DP4A strip kernel where the level shape allows) | 1 (shared-memory tile kernel);
+ * "sa_variant" = 0 (shared-memory recompute kernel) | 1 (L2 workspace kernel); "step_chunks" = 1..8 concurrent streams
+ * over which dsdtm_batch_run splits the pairs of a step (per-pair stage order unchanged) */
 int         dsdtm_set_option(dsdtm_ctx* ctx, const char* key, int value);
 /* stage profiling: on != 0 brackets every stage with CUDA events; get returns accumulated ms and launch counts */
 int         dsdtm_profile(dsdtm_ctx* ctx, int on);

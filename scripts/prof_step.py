@@ -14,6 +14,7 @@ def main():
     ap.add_argument("--fast", type=int, default=0, help="also run fast_cells_batch over this many frames")
     ap.add_argument("--wpp", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--chunks", type=int, default=1)
     ap.add_argument("--direct", action="store_true", help="launch kernels directly instead of graph replay")
     a = ap.parse_args()
     cam = dict(S.KINECT)
@@ -25,10 +26,18 @@ def main():
                     batch["patch_level"], bench.ALIGN2D_ITERS)
     ctx.set_option("sa_warps_per_pair", a.wpp)
     ctx.set_option("sa_variant", a.variant)
+    ctx.set_option("step_chunks", a.chunks)
     if a.direct:
         ctx.profile(True)
+    if not a.direct:
+        for _ in range(3):
+            ctx.batch_run(1)
+        ctx.sync()
+        ctx.timer_start()
     for _ in range(a.steps):
         ctx.batch_run(1)
+    if not a.direct:
+        print("graph replay: %.4f ms per step (chunks=%d)" % (ctx.timer_stop() / a.steps, a.chunks))
     ctx.sync()
     if a.direct:
         print(ctx.profile_get())
