@@ -12,11 +12,12 @@ using namespace DSDTM;
 struct HsFrame { FramePtr f; std::vector<MapPoint*> owned; };
 struct HsKf { KeyFrame* kf; };
 static std::string g_err;
+static std::vector<MapPoint*> g_mps;      // creation-order registry: index = map point id used by the Python side
 
 extern "C" {
 
 const char* hs_last_error() { return g_err.c_str(); }
-void hs_reset() { GpuRuntime::Shutdown(); Config::Clear(); }
+void hs_reset() { GpuRuntime::Shutdown(); Config::Clear(); g_mps.clear(); }
 void hs_config_set(const char* k, const char* v) { Config::Set(k, v); }
 int hs_config_load(const char* path) { try { Config::setParameterFile(path); return 0; } catch (std::exception& e) { g_err = e.what(); return -1; } }
 double hs_config_get(const char* k) { return Config::Get<double>(k); }
@@ -79,10 +80,44 @@ void hs_frame_attach_points(void* f, const double* pts, const uint8_t* has)
         if (!has[i]) continue;
         MapPoint* mp = new MapPoint(Vector3d(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
         hf->owned.push_back(mp);
+        g_mps.push_back(mp);
         ft->SetPose(mp);
         fr->mvMapPoints[i] = mp;
     }
 }
+
+// CraeteKeyframe's loop over the features (ref: src/Tracking.cpp:422-454): features that already carry a map point keep it;
+// the NEW ones (index >= start, added by detect) get their bearing (UndistortFeatures with zero distortion) and, where
+// has[i - start] is set, a map point at pts[i - start].
+void hs_frame_attach_points_from(void* f, int start, const double* pts, const uint8_t* has)
+{
+    HsFrame* hf = static_cast<HsFrame*>(f);
+    Frame* fr = hf->f.get();
+    fr->mvMapPoints.resize(fr->mvFeatures.size(), nullptr);
+    for (size_t i = (size_t)start; i < fr->mvFeatures.size(); ++i) {
+        Feature* ft = fr->mvFeatures[i];
+        ft->mNormal = fr->mCamera->Pixel2Camera(ft->mpx, 1.0f);
+        ft->mNormal.normalize();
+        if (!has[i - start]) continue;
+        const double* p = pts + 3 * (i - start);
+        MapPoint* mp = new MapPoint(Vector3d(p[0], p[1], p[2]));
+        hf->owned.push_back(mp);
+        g_mps.push_back(mp);
+        ft->SetPose(mp);
+        fr->mvMapPoints[i] = mp;
+    }
+}
+
+// map point id (creation order) per feature, -1 if none
+void hs_frame_feature_mp_ids(void* f, int* ids)
+{
+    const Features& fs = static_cast<HsFrame*>(f)->f->mvFeatures;
+    for (size_t i = 0; i < fs.size(); ++i) {
+        ids[i] = -1;
+        for (size_t k = 0; k < g_mps.size(); ++k) if (g_mps[k] == fs[i]->Mpt) { ids[i] = (int)k; break; }
+    }
+}
+int hs_mappoint_found(int id) { return (id >= 0 && id < (int)g_mps.size()) ? g_mps[id]->Get_FoundNums() : -1; }
 
 int hs_sparse_align_run(int maxl, int minl, int iters, void* cur, void* ref, double* pose_out, dsdtm_iter_log* log, int cap, int* n_log)
 {
@@ -122,6 +157,34 @@ int hs_search_local_points(void* cam, void* cur, void* kf, const int* found, int
             if (!mp) continue;
             if (found) mp->IncreaseFound(found[i] - mp->Get_FoundNums());
             if (fa.ReprojectPoint(c, mp)) nr++;
+        }
+        if (n_reprojected) *n_reprojected = nr;
+        fa.SearchLocalPoints(c);
+        return fa.LastMatches();
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// UpdateLocalMap over a list of local keyframes (ref: src/Tracking.cpp:276-305): every map point is reprojected once
+// (mLastProjectedFrameId), in keyframe order then feature order; then SearchLocalPoints.
+int hs_search_local_points_multi(void* cam, void* cur, void** kfs, int n_kfs, int* n_reprojected)
+{
+    try {
+        Feature_Alignment fa(*static_cast<CameraPtr*>(cam));
+        FramePtr c = static_cast<HsFrame*>(cur)->f;
+        fa.ResetGrid();
+        std::vector<MapPoint*> seen;
+        int nr = 0;
+        for (int q = 0; q < n_kfs; ++q) {
+            KeyFrame* k = static_cast<HsKf*>(kfs[q])->kf;
+            for (size_t i = 0; i < k->mvFeatures.size(); ++i) {
+                MapPoint* mp = k->mvFeatures[i]->Mpt;
+                if (!mp || mp->IsBad()) continue;
+                bool dup = false;
+                for (MapPoint* s : seen) if (s == mp) { dup = true; break; }
+                if (dup) continue;
+                seen.push_back(mp);
+                if (fa.ReprojectPoint(c, mp)) nr++;
+            }
         }
         if (n_reprojected) *n_reprojected = nr;
         fa.SearchLocalPoints(c);

@@ -49,6 +49,9 @@ def lib():
         L.hs_sparse_align_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_keyframe_new.argtypes = [C.c_void_p]
         L.hs_search_local_points.argtypes = [C.c_void_p] * 5
+        L.hs_search_local_points_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.hs_frame_attach_points_from.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hs_frame_feature_mp_ids.argtypes = [C.c_void_p, C.c_void_p]
         L.hs_align2d_single.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_circle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
         _lib = L
@@ -99,6 +102,15 @@ class HFrame:
     def attach_points(self, pts, has):
         lib().hs_frame_attach_points(self.h, _p(np.ascontiguousarray(pts, np.float64)), _p(np.ascontiguousarray(has, np.uint8)))
 
+    def attach_points_from(self, start, pts, has):
+        lib().hs_frame_attach_points_from(self.h, int(start), _p(np.ascontiguousarray(pts, np.float64)), _p(np.ascontiguousarray(has, np.uint8)))
+
+    def mp_ids(self):
+        n = lib().hs_frame_n_features(self.h)
+        ids = np.empty(n, np.int32)
+        lib().hs_frame_feature_mp_ids(self.h, _p(ids))
+        return ids
+
     def pose(self):
         p = np.empty(7); lib().hs_frame_get_pose(self.h, _p(p)); return p
 
@@ -111,6 +123,15 @@ class HFrame:
     def free(self):
         if self.h:
             lib().hs_frame_free(self.h); self.h = None
+
+
+def search_local_points_multi(cam_h, cur, kf_handles):
+    arr = (C.c_void_p * len(kf_handles))(*kf_handles)
+    nrep = C.c_int(0)
+    m = lib().hs_search_local_points_multi(cam_h, cur.h, arr, len(kf_handles), C.byref(nrep))
+    if m < 0:
+        raise RuntimeError(lib().hs_last_error().decode())
+    return m, nrep.value
 
 
 def sparse_align_run(maxl, minl, iters, cur, ref):

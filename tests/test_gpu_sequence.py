@@ -189,3 +189,161 @@ def test_batched_sweep_752x480(built):
     p2, t2, _, _ = ctx.sparse_align_batch(ref_slots, cur_slots, feats, nf, centers, poses, 5, 0, 8)
     assert (p2 == pb).all()
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ multi-keyframe sequence
+class OMap:
+    """Oracle-side model of the pieces of Map / MapPoint / KeyFrame the hot path reads."""
+    def __init__(self):
+        self.mp_point = []      # id -> world point
+        self.mp_found = []      # id -> found count (MapPoint::mnFound starts at 1)
+        self.mp_obs = []        # id -> list of (kf index, feature index)
+        self.kfs = []           # OracleFrame + .feat_mp (map point id per feature)
+
+    def new_mp(self, p):
+        self.mp_point.append(np.array(p)); self.mp_found.append(1); self.mp_obs.append([])
+        return len(self.mp_point) - 1
+
+
+def _oracle_search_multi(oc, cam, cur, omap, kf_order):
+    """UpdateLocalMap + SearchLocalPoints over several keyframes (ref: src/Tracking.cpp:276-305, src/Feature_alignment.cpp:54-158,
+    src/MapPoint.cpp:133-174)."""
+    w, h = cam["width"], cam["height"]
+    gcols = -(-w // CELL)
+    fx, fy, cx, cy = (float(np.float32(cam[k])) for k in ("fx", "fy", "cx", "cy"))
+    cells, seen = {}, set()
+    for q in kf_order:
+        for mp in omap.kfs[q].feat_mp:
+            if mp < 0 or mp in seen:
+                continue
+            seen.add(mp)
+            qq = O.se3_act(cur.pose, omap.mp_point[mp])
+            px = np.array([fx * qq[0] / qq[2] + cx, fy * qq[1] / qq[2] + cy])
+            rx, ry = O.cvround(np.float32(px[0])), O.cvround(np.float32(px[1]))
+            if 8 <= rx < w - 8 and 8 <= ry < h - 8:
+                cells.setdefault(int(px[1] / CELL) * gcols + int(px[0] / CELL), []).append((mp, px))
+    mask = np.full((h, w), 255, np.uint8)
+    cur_center = O.se3_inv(cur.pose)[4:]
+    out = []
+    for k in sorted(cells):
+        for mp, px in sorted(cells[k], key=lambda c: -omap.mp_found[c[0]]):
+            if mask[O.cvround(np.float32(px[1])), O.cvround(np.float32(px[0]))] != 255:
+                continue
+            P = omap.mp_point[mp]
+            b = cur_center - P; b = b / np.linalg.norm(b)
+            best, best_obs = 0.0, omap.mp_obs[mp][0]
+            for (qk, fi) in omap.mp_obs[mp]:
+                a = O.se3_inv(omap.kfs[qk].pose)[4:] - P
+                c = float(np.dot(a / np.linalg.norm(a), b))
+                if c > best:
+                    best, best_obs = c, (qk, fi)
+            if best < 0.5:
+                continue
+            kf = omap.kfs[best_obs[0]]
+            f = kf.feats[best_obs[1]]
+            L0 = int(f["level"])
+            rpx = f["px"] / np.float32(1 << L0)
+            if not (5 <= O.cvround(rpx[0]) < w // (1 << L0) - 5 and 5 <= O.cvround(rpx[1]) < h // (1 << L0) - 5):
+                continue
+            packed, offs, ws, hs = kf.pyr
+            kf_center = O.se3_inv(kf.pose)[4:]
+            T_c2r = O.se3_mul(cur.pose, O.se3_inv(kf.pose))
+            A = O.solve_affine(oc, kf_center, f["point_w"], f["normal"], f["px"], L0, T_c2r)
+            SL = O.best_search_level(A, LEVELS - 3)
+            patch = O.warp_affine(A, O.pyr_level(packed, offs, ws, hs, L0), f["px"], L0, SL)
+            p, conv, _ = O.align2d(O.pyr_level(cur.pyr[0], offs, ws, hs, SL), patch, 10, px / (1 << SL))
+            p = p * (1 << SL)
+            if not conv:
+                continue
+            out.append((mp, np.float32(p), SL, best_obs[0]))
+            O.circle_fill(mask, O.cvround(np.float32(p[0])), O.cvround(np.float32(p[1])), CELL, 0)
+            break
+        if len(out) >= 200:
+            break
+    return out
+
+
+def test_front_end_sequence_with_second_keyframe(built):
+    """Same loop as above, plus Tracking::CraeteKeyframe in the middle (ref: src/Tracking.cpp:412-464): Set_ExistingFeatures +
+    detect on a frame that already carries matched features (occupancy grid, Frame::Set_Mask with Min_dist circles), new map
+    points, a second keyframe, and afterwards a local map of two keyframes where MapPoint::Get_ClosetObs picks the
+    observation by viewing angle."""
+    cam = dict(S.KINECT)
+    oc = H.ocam(cam)
+    scene = S.Scene(91)
+    n_frames, kf_at = 8, 4
+    poses = _trajectory(n_frames, seed=9)
+    cam_h = HL.configure(cam, max_fts=300, max_frames=24)
+    cfg = (5, 0, 8)
+    omap = OMap()
+
+    img0, _, pts0 = S.render(scene, cam, poses[0], want_points=True)
+    g0 = HL.HFrame(cam_h, img0, poses[0]); o0 = OracleFrame(img0, poses[0])
+    assert g0.detect(5.0) == 300
+    corners, _ = H.detect_oracle(img0, LEVELS, CELL, 300)
+    g0.attach_points(pts0[corners["y"], corners["x"]], np.ones(len(corners), np.uint8))
+    o0.feats = H.ref_feats_from_corners(cam, corners, pts0)
+    o0.feat_mp = [omap.new_mp(o0.feats[i]["point_w"]) for i in range(len(corners))]
+    for i, mp in enumerate(o0.feat_mp):
+        omap.mp_obs[mp].append((0, i))
+    omap.kfs.append(o0)
+    kf_handles = [HL.lib().hs_keyframe_new(g0.h)]
+
+    g_last, o_last = g0, o0
+    for k in range(1, n_frames):
+        img, _, pts = S.render(scene, cam, poses[k], want_points=True)
+        g_cur = HL.HFrame(cam_h, img, g_last.pose()); o_cur = OracleFrame(img, o_last.pose)
+        n_g, pose_g, _ = HL.sparse_align_run(*cfg, g_cur, g_last)
+        pose_o, n_o = _oracle_sparse_align(oc, o_cur, o_last, cfg)
+        o_cur.pose = pose_o
+        d = S.pose_dist(pose_o, pose_g)
+        assert d[0] < 1e-5 and d[1] < 1e-5 and n_g == n_o and n_g >= 20, (k, d, n_g, n_o)
+        m, nrep = HL.search_local_points_multi(cam_h, g_cur, kf_handles)
+        want = _oracle_search_multi(oc, cam, o_cur, omap, list(range(len(omap.kfs))))
+        px, lv, ini = g_cur.features()
+        ids = g_cur.mp_ids()
+        assert m == len(want) == len(px) and m > 100, (k, m, len(want))
+        for (mp, p, SL, _), gp, gl, gid in zip(want, px, lv, ids):
+            assert gid == mp and gl == SL and np.abs(p - gp).max() <= 1e-3
+        F = np.zeros(len(want), O.REF_FEAT_DT)
+        for j, (mp, p, SL, _) in enumerate(want):
+            omap.mp_found[mp] += 1
+            F[j]["px"] = px[j]; F[j]["level"] = SL; F[j]["initial"] = 1
+            F[j]["normal"] = O.feature_normal(oc, px[j]); F[j]["point_w"] = omap.mp_point[mp]
+        o_cur.feats = F
+        o_cur.feat_mp = [w_[0] for w_ in want]
+        if k >= kf_at + 1:
+            assert len({w_[3] for w_ in want}) == 2, "both keyframes should serve as closest observation somewhere"
+
+        if k == kf_at:
+            # ---- CraeteKeyframe: Set_ExistingFeatures(cur features) + detect(cur, 5.0), then map points for the new features
+            n_old = len(px)
+            n_all = g_cur.detect(5.0, use_existing=True)
+            px2, lv2, ini2 = g_cur.features()
+            # oracle: occupancy from the existing features (ref: src/Feature_detection.cpp:43-50), Set_Mask circles of Min_dist at
+            # features WITH map points (ref: src/Frame.cpp:286-298), then the usual sort + selection
+            packed, offs, ws, hs = o_cur.pyr
+            rows_, cols_ = O.grid_dims(cam["width"], cam["height"], CELL)
+            occ = np.zeros(rows_ * cols_, np.uint8)
+            for p in px:
+                occ[int(p[1] / np.float32(CELL)) * cols_ + int(p[0] / np.float32(CELL))] = 1
+            cells = O.detect_cells(packed, offs, ws, hs, CELL, occ, 5.0)
+            mask = np.full((cam["height"], cam["width"]), 255, np.uint8)
+            for p in px:
+                O.circle_fill(mask, O.cvround(p[0]), O.cvround(p[1]), 15, 0)          # Camera.Min_dist = 15
+            new_c, _ = O.detect_select(cells, mask, CELL, 300, n_existing=n_old)
+            assert n_all == n_old + len(new_c) and n_all > n_old
+            assert (px2[n_old:, 0] == new_c["x"]).all() and (px2[n_old:, 1] == new_c["y"]).all() and (lv2[n_old:] == new_c["level"]).all()
+            newpts = pts[new_c["y"], new_c["x"]]
+            g_cur.attach_points_from(n_old, newpts, np.ones(len(new_c), np.uint8))
+            Fn = H.ref_feats_from_corners(cam, new_c, pts)
+            o_cur.feats = np.concatenate([o_cur.feats, Fn])
+            new_ids = [omap.new_mp(Fn[i]["point_w"]) for i in range(len(new_c))]
+            o_cur.feat_mp = o_cur.feat_mp + new_ids
+            kfi = len(omap.kfs)
+            for i, mp in enumerate(o_cur.feat_mp):
+                omap.mp_obs[mp].append((kfi, i))
+            omap.kfs.append(o_cur)
+            kf_handles.append(HL.lib().hs_keyframe_new(g_cur.h))
+            assert (g_cur.mp_ids() == np.array(o_cur.feat_mp)).all()
+        g_last, o_last = g_cur, o_cur
