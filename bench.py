@@ -125,13 +125,6 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
-def algorithmic_bytes(n_feats, iters_per_level):
-    """sparse align touches N*49 B of the ref level per level + N*25 B of the cur level per iteration,
-    plus the feature records (64 B each) and the pose in/out."""
-    levels = len(iters_per_level)
-    return n_feats * (64 + 49 * levels + 25 * int(sum(iters_per_level))) + 2 * 56
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
