@@ -216,6 +216,7 @@ int GpuRuntime::Acquire(GpuSlot* owner)
     for (int i = 0; i < mMaxFrames; ++i) if (!mOwner[i]) { best = i; break; }
     if (best < 0) {   // evict the least recently used pyramid; its owner re-uploads on next use
         for (int i = 0; i < mMaxFrames; ++i) if (best < 0 || mStamp[i] < mStamp[best]) best = i;
+        if (mStamp[best] > mEpochStart) mEpochEvicted = true;      // a slot handed out inside the current epoch was recycled
         mOwner[best]->slot = -1;
     }
     mOwner[best] = owner;
@@ -495,6 +496,7 @@ bool Feature_Alignment::Prepare(const MapPoint* mp, const FramePtr frame, const 
 
 void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref: :71-121
 {
+    GpuRuntime::Instance().BeginEpoch();
     // The reference walks cells in index order, candidates by found-count, and stops a cell at the first match; a match
     // paints the mask and thereby only changes which LATER candidates are tried, never their alignment result. So: sort
     // the cells (as the reference does, in place), align every candidate of every cell speculatively in ONE GPU batch
@@ -503,6 +505,7 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
     struct Item { Candidate* cand; bool prepared; int batch_index; };
     std::vector<std::vector<Item>> items(mCells.size());
     std::vector<dsdtm_candidate> cands;
+    const int cur_slot_first = rt.Resident(frame->mGpu);     // touch the current frame first: it must stay resident as well
     for (size_t ci = 0; ci < mCells.size(); ++ci) {
         Cell* cell = mCells[ci];
         cell->sort([](Candidate& a, Candidate& b) { return a.mMpPoint->Get_FoundNums() > b.mMpPoint->Get_FoundNums(); });   // ref: :88,123-126
@@ -523,6 +526,10 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
     std::vector<uint8_t> conv(n);
     if (n > 0) {
         const int cur_slot = rt.Resident(frame->mGpu);
+        // Resolving many keyframes can recycle a slot that an earlier candidate already points to when the pool is smaller than
+        // the local map (+ the current frame). That would silently sample the wrong image: fail loudly instead.
+        if (cur_slot != cur_slot_first || !rt.SlotsStillValid())
+            throw std::runtime_error("Feature_Alignment::SearchLocalPoints: frame pool too small for the local map (raise Gpu.MaxFrames)");
         if (dsdtm_feature_align_batch(rt.ctx(), cur_slot, cands.data(), n, mPyr_levels - 3, 10, px.data(), search_level.data(), conv.data(), nullptr) != 0)
             throw std::runtime_error(std::string("dsdtm_feature_align_batch: ") + dsdtm_last_error(rt.ctx()));
     }

@@ -276,6 +276,9 @@ public:
     int Resident(const std::shared_ptr<GpuSlot>& s);             // slot index, re-uploading from the host copy if it was evicted
     int levels() const { return mLevels; }
     void Release(int slot);
+    // epoch = one batched call that resolves several slots before using them: detects a slot being recycled in between
+    void BeginEpoch() { mEpochStart = mClock; mEpochEvicted = false; }
+    bool SlotsStillValid() const { return !mEpochEvicted; }
     ~GpuRuntime();
 private:
     GpuRuntime();
@@ -284,7 +287,8 @@ private:
     int mLevels = 0, mMaxFrames = 0;
     std::vector<GpuSlot*> mOwner;      // per slot
     std::vector<unsigned long long> mStamp;
-    unsigned long long mClock = 0;
+    unsigned long long mClock = 0, mEpochStart = 0;
+    bool mEpochEvicted = false;
     friend class GpuSlot;
 };
 

@@ -347,3 +347,25 @@ def test_front_end_sequence_with_second_keyframe(built):
             kf_handles.append(HL.lib().hs_keyframe_new(g_cur.h))
             assert (g_cur.mp_ids() == np.array(o_cur.feat_mp)).all()
         g_last, o_last = g_cur, o_cur
+
+
+def test_frame_pool_too_small_fails_loudly(built):
+    """A pool smaller than (local keyframes + current frame) would recycle a slot that an earlier candidate of the same batch
+    points to. The adapter must refuse (never sample the wrong image silently)."""
+    cam = dict(S.KINECT)
+    scene = S.Scene(5)
+    poses = _trajectory(3, seed=2)
+    cam_h = HL.configure(cam, max_fts=120, max_frames=2)
+    kfs = []
+    frames = []
+    for k in range(2):
+        img, _, pts = S.render(scene, cam, poses[k], want_points=True)
+        g = HL.HFrame(cam_h, img, poses[k])
+        n = g.detect(5.0)
+        px, lv, _ = g.features()
+        g.attach_points(pts[px[:, 1].astype(int), px[:, 0].astype(int)], np.ones(n, np.uint8))
+        kfs.append(HL.lib().hs_keyframe_new(g.h)); frames.append(g)
+    img, _ = S.render(scene, cam, poses[2])
+    cur = HL.HFrame(cam_h, img, poses[2])
+    with pytest.raises(RuntimeError, match="frame pool too small"):
+        HL.search_local_points_multi(cam_h, cur, kfs)
