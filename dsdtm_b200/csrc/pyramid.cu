@@ -15,7 +15,9 @@
 // HBM-bound stage: algorithmic bytes per frame = sum_l (w_{l-1} h_{l-1} + w_l h_l) (510 000 B @640x480x5).
 // Round-1 profile (profiles/r1_bench_first.md): the tile kernel alone ran at 600 GB/s = 9 % of HBM peak, issue-bound on
 // byte-wide shared-memory traffic -- hence the register/DP4A strip kernel. (Fetching the 3 halo bytes from neighbouring lanes by
-// shuffle instead of two extra L1-hit 4-byte loads was measured SLOWER: 0.384 vs 0.267 ms per 2072 frames.)
+// shuffle instead of two extra L1-hit 4-byte loads was measured SLOWER: 0.384 vs 0.267 ms per 2072 frames.
+// An 8-outputs-per-thread variant (one 16-byte load per row, 44 registers) and rows-per-thread 4/16/32 x unroll 2/4 were also
+// measured: none beat 4 outputs x 8 rows x unroll 2 (0.498 ms per 4096 frames; see profiles/r1_pyramid_fast_align2d.md).)
 #include "ctx.cuh"
 
 namespace dsdtm {
@@ -102,7 +104,14 @@ __global__ void __launch_bounds__(256) pyrdown_tile_kernel(uint8_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int RPT = 8;   // output rows per thread strip
+#ifndef DSDTM_PYR_RPT
+#define DSDTM_PYR_RPT 8
+#endif
+#ifndef DSDTM_PYR_UNROLL
+#define DSDTM_PYR_UNROLL 2
+#endif
+constexpr int PYR_UNROLL = DSDTM_PYR_UNROLL;
+constexpr int RPT = DSDTM_PYR_RPT;   // output rows per thread strip
 
 __device__ __forceinline__ int reflect_row(int r, int h)
 {
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(128) pyrdown_strip_kernel(uint8_t* __restrict_
     uint2 r0 = hrow(src + (size_t)reflect_row(2 * y0 - 2, h) * w, x, w);
     uint2 r1 = hrow(src + (size_t)reflect_row(2 * y0 - 1, h) * w, x, w);
     uint2 r2 = hrow(src + (size_t)(2 * y0) * w, x, w);
-#pragma unroll 2
+#pragma unroll PYR_UNROLL
     for (int y = y0; y < min(y0 + RPT, dh); ++y) {
         const uint2 r3 = hrow(src + (size_t)reflect_row(2 * y + 1, h) * w, x, w);
         const uint2 r4 = hrow(src + (size_t)reflect_row(2 * y + 2, h) * w, x, w);

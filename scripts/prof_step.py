@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--wpp", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--chunks", type=int, default=1)
+    ap.add_argument("--pyr", type=int, default=0, help="pyramid_kernel option (0 auto, 1 tile)")
     ap.add_argument("--direct", action="store_true", help="launch kernels directly instead of graph replay")
     a = ap.parse_args()
     cam = dict(S.KINECT)
@@ -27,6 +28,7 @@ def main():
     ctx.set_option("sa_warps_per_pair", a.wpp)
     ctx.set_option("sa_variant", a.variant)
     ctx.set_option("step_chunks", a.chunks)
+    ctx.set_option("pyramid_kernel", a.pyr)
     if a.direct:
         ctx.profile(True)
     if not a.direct:
