@@ -8,7 +8,7 @@ import numpy as np
 
 from . import build as _build
 
-STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine", "cand_prep")
+STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine", "cand_prep", "local_map")
 
 CORNER_DT = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4")])
 REF_FEAT_DT = np.dtype([("px", "<f4", 2), ("level", "<i4"), ("initial", "<i4"),
@@ -18,6 +18,12 @@ ITER_LOG_DT = np.dtype([("level", "<i4"), ("iter", "<i4"), ("n_pts", "<i4"), ("f
 CANDIDATE_DT = np.dtype([("ref_slot", "<i4"), ("ref_level", "<i4"), ("ref_px", "<f4", 2), ("ref_normal", "<f8", 3),
                          ("ref_point_w", "<f8", 3), ("kf_center", "<f8", 3), ("pose_c2r", "<f8", 7), ("px", "<f8", 2)])
 assert CANDIDATE_DT.itemsize == 160
+KF_VIEW_DT = np.dtype([("slot", "<i4"), ("reserved", "<i4"), ("center", "<f8", 3), ("pose_c2w", "<f8", 7)])
+OBS_DT = np.dtype([("kf", "<i4"), ("level", "<i4"), ("px", "<f4", 2), ("normal", "<f8", 3), ("point_w", "<f8", 3)])
+MAP_POINT_DT = np.dtype([("point_w", "<f8", 3), ("obs_begin", "<i4"), ("obs_count", "<i4")])
+REPROJ_DT = np.dtype([("px_proj", "<f8", 2), ("px", "<f8", 2), ("cell", "<i4"), ("obs", "<i4"), ("flags", "<i4"), ("level", "<i4")])
+assert KF_VIEW_DT.itemsize == 88 and OBS_DT.itemsize == 64 and MAP_POINT_DT.itemsize == 32 and REPROJ_DT.itemsize == 48
+LM_IN_IMAGE, LM_OBS_OK, LM_REF_OK, LM_CONVERGED = 1, 2, 4, 8
 
 
 class Cam(C.Structure):
@@ -45,6 +51,7 @@ SYMBOLS = [
     "dsdtm_fast_score_map", "dsdtm_grid_dims", "dsdtm_sparse_align", "dsdtm_sparse_align_batch",
     "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
+    "dsdtm_local_map_align_batch",
 ]
 
 
@@ -245,6 +252,14 @@ class Context:
         self._ck(self.L.dsdtm_feature_align_batch(self.hp, int(cur_slot), _p(cands), n, int(max_search_level), int(max_iters),
                                                   _p(px), _p(lv), _p(conv), _p(A)))
         return px, lv, conv.astype(bool), A
+
+    def local_map_align_batch(self, cur_slot, pose_cur_c2w, cur_center, kfs, obs, pts, max_search_level, max_iters=10):
+        kfs = np.ascontiguousarray(kfs, KF_VIEW_DT); obs = np.ascontiguousarray(obs, OBS_DT); pts = np.ascontiguousarray(pts, MAP_POINT_DT)
+        out = np.zeros(len(pts), REPROJ_DT)
+        self._ck(self.L.dsdtm_local_map_align_batch(
+            self.hp, int(cur_slot), _p(np.ascontiguousarray(pose_cur_c2w, np.float64)), _p(np.ascontiguousarray(cur_center, np.float64)),
+            _p(kfs), len(kfs), _p(obs), len(obs), _p(pts), len(pts), int(max_search_level), int(max_iters), _p(out)))
+        return out
 
     # ---- batched front end
     def batch_stage(self, ref_slots, cur_slots, feats, n_feats, ref_centers, poses_in, max_level, min_level, max_iters,

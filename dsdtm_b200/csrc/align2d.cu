@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const WaArgs a)
     const int i = blockIdx.x * 8 + warp;
     if (i >= a.n) return;
     const int slot = a.meta[3 * i], rl = a.meta[3 * i + 1], sl = a.meta[3 * i + 2];
+    if (slot < 0) return;                                           // candidate skipped by candidate_prep_kernel
     const double A00 = a.A[4 * i], A01 = a.A[4 * i + 1], A10 = a.A[4 * i + 2], A11 = a.A[4 * i + 3];
     // Eigen 2x2 inverse in double, then cast<float>() (ref: :211)
     const double det = __dsub_rn(__dmul_rn(A00, A11), __dmul_rn(A10, A01));
@@ -251,6 +252,12 @@ __global__ void __launch_bounds__(128) candidate_prep_kernel(const CpArgs a)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const dsdtm_candidate c = a.cand[i];
+    if (c.ref_slot < 0) {                                           // rejected before FindMatchDirect's arithmetic (local_map.cu)
+        a.meta[3 * i] = -1; a.meta[3 * i + 1] = 0; a.meta[3 * i + 2] = 0;
+        a.patch_level[i] = -1; a.patch_slot[i] = a.cur_slot;
+        a.px_in[2 * i] = c.px[0]; a.px_in[2 * i + 1] = c.px[1];
+        return;
+    }
     const double fx = (double)a.fx, fy = (double)a.fy, cx = (double)a.cx, cy = (double)a.cy;
     const int HalfLarger = 5;                                       // mHalf_PatchSize + 1
     // ref: :167  P = ||O_kf - P_w|| * mNormal

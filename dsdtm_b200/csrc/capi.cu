@@ -52,6 +52,17 @@ static int dalloc(dsdtm_ctx* c, T** p, size_t n)
     return 0;
 }
 
+template <class T>
+static int grow(dsdtm_ctx* c, T** p, size_t* cap, size_t n)
+{
+    if (n <= *cap) return 0;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    const size_t want = std::max<size_t>(n + n / 2, 256);
+    if (dalloc(c, p, want)) return DSDTM_E_NOMEM;
+    *cap = want;
+    return 0;
+}
+
 static int ensure_pinned(dsdtm_ctx* c, size_t bytes)
 {
     if (bytes <= c->pinned_bytes) return 0;
@@ -186,7 +197,8 @@ void dsdtm_destroy(dsdtm_ctx* c)
     for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) cudaGraphExecDestroy(c->batch.graph[k]);
     void* bufs[] = { c->frames_d, c->cells_d, c->occupied_d, c->scoremap_d, c->fast_tiles_d, c->ref_slots_d, c->cur_slots_d,
                      c->feats_d, c->n_feats_d, c->centers_d, c->poses_in_d, c->poses_out_d, c->n_tracked_d, c->log_d, c->n_log_d,
-                     c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d, c->cand_d };
+                     c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d, c->cand_d,
+                     c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { if (c->timer.ev0[i]) cudaEventDestroy(c->timer.ev0[i]); if (c->timer.ev1[i]) cudaEventDestroy(c->timer.ev1[i]); }
@@ -549,6 +561,71 @@ int dsdtm_feature_align_batch(dsdtm_ctx* c, int cur_slot, const dsdtm_candidate*
     for (int i = 0; i < n; ++i) {                                   // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
         const double sc = (double)(1 << level_out[i]);
         px_out[2 * i] *= sc; px_out[2 * i + 1] *= sc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ (f-1) local map
+int dsdtm_local_map_align_batch(dsdtm_ctx* c, int cur_slot, const double pose_cur_c2w[7], const double cur_center[3],
+                                const dsdtm_kf_view* kfs, int n_kfs, const dsdtm_obs* obs, int n_obs, const dsdtm_map_point* pts,
+                                int n_pts, int max_search_level, int max_iters, dsdtm_reproj* out)
+{
+    if (!c || !pose_cur_c2w || !cur_center || n_kfs < 0 || n_obs < 0 || n_pts < 0 || max_iters < 0 || max_search_level < 0) return DSDTM_E_ARG;
+    if ((n_kfs && !kfs) || (n_obs && !obs) || (n_pts && (!pts || !out))) return fail(c, DSDTM_E_ARG, "null table");
+    if (check_slot(c, cur_slot)) return DSDTM_E_ARG;
+    if (n_pts == 0) return 0;
+    const size_t cap = (size_t)c->prm.max_batch * std::max(c->prm.max_patches, 1);
+    if ((size_t)n_pts > cap) return fail(c, DSDTM_E_ARG, "n_pts > max_batch * max_patches");
+    if (max_search_level >= c->geo.levels) return fail(c, DSDTM_E_ARG, "max_search_level >= levels");
+    for (int k = 0; k < n_kfs; ++k)
+        if (kfs[k].slot < 0 || kfs[k].slot >= c->prm.max_frames) return fail(c, DSDTM_E_ARG, "keyframe: slot out of range");
+    for (int j = 0; j < n_obs; ++j)
+        if (obs[j].kf < 0 || obs[j].kf >= n_kfs || obs[j].level < 0 || obs[j].level >= c->geo.levels)
+            return fail(c, DSDTM_E_ARG, "observation: keyframe index / level out of range");
+    for (int i = 0; i < n_pts; ++i)
+        if (pts[i].obs_count < 0 || pts[i].obs_begin < 0 || (long long)pts[i].obs_begin + pts[i].obs_count > n_obs)
+            return fail(c, DSDTM_E_ARG, "map point: observation range out of bounds");
+    c->batch.staged = false;
+    {
+        const size_t kcap0 = c->lm_kfs_cap, pcap0 = c->lm_pts_cap;
+        if (grow(c, &c->lm_kfs_d, &c->lm_kfs_cap, (size_t)n_kfs) || grow(c, &c->lm_obs_d, &c->lm_obs_cap, (size_t)n_obs) ||
+            grow(c, &c->lm_pts_d, &c->lm_pts_cap, (size_t)n_pts))
+            return DSDTM_E_NOMEM;
+        if (c->lm_kfs_cap != kcap0) { size_t z = 0; if (grow(c, &c->lm_pose_d, &z, c->lm_kfs_cap * 7)) return DSDTM_E_NOMEM; }
+        if (c->lm_pts_cap != pcap0) { size_t z = 0; if (grow(c, &c->lm_reproj_d, &z, c->lm_pts_cap)) return DSDTM_E_NOMEM; }
+    }
+    cudaStream_t s = c->stream;
+    if (n_kfs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_kfs_d, kfs, (size_t)n_kfs * sizeof(dsdtm_kf_view), cudaMemcpyHostToDevice, s));
+    if (n_obs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_obs_d, obs, (size_t)n_obs * sizeof(dsdtm_obs), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_pts_d, pts, (size_t)n_pts * sizeof(dsdtm_map_point), cudaMemcpyHostToDevice, s));
+    stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+    DSDTM_CUDA(c, launch_local_map(c, pose_cur_c2w, cur_center, n_kfs, n_pts, s));
+    stage_end(c, 2);
+    stage_begin(c, DSDTM_STAGE_CAND_PREP);
+    DSDTM_CUDA(c, launch_candidate_prep(c, n_pts, cur_slot, max_search_level, s));
+    stage_end(c, 1);
+    stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
+    DSDTM_CUDA(c, launch_warp_affine(c, n_pts, c->patches_d, s));
+    stage_end(c, 1);
+    stage_begin(c, DSDTM_STAGE_ALIGN2D);
+    DSDTM_CUDA(c, launch_align2d(c, n_pts, max_iters, s));
+    stage_end(c, 1);
+    const size_t need = (size_t)n_pts * (2 * sizeof(double) + sizeof(int) + 1);
+    if (ensure_pinned(c, need)) return DSDTM_E_NOMEM;
+    double* px_h = reinterpret_cast<double*>(c->pinned);
+    int* lvl_h = reinterpret_cast<int*>(px_h + 2 * (size_t)n_pts);
+    uint8_t* conv_h = reinterpret_cast<uint8_t*>(lvl_h + n_pts);
+    DSDTM_CUDA(c, cudaMemcpyAsync(out, c->lm_reproj_d, (size_t)n_pts * sizeof(dsdtm_reproj), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(px_h, c->patch_px_d, (size_t)n_pts * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(lvl_h, c->patch_level_d, (size_t)n_pts * sizeof(int), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(conv_h, c->patch_conv_d, (size_t)n_pts, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    for (int i = 0; i < n_pts; ++i) {
+        if (lvl_h[i] < 0) continue;                                 // not aligned: px stays the projection, level -1
+        const double sc = (double)(1 << lvl_h[i]);                  // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
+        out[i].px[0] = px_h[2 * i] * sc; out[i].px[1] = px_h[2 * i + 1] * sc;
+        out[i].level = lvl_h[i];
+        if (conv_h[i]) out[i].flags |= DSDTM_LM_CONVERGED;
     }
     return 0;
 }

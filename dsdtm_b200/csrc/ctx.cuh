@@ -30,8 +30,8 @@ struct StageTimer {
     cudaEvent_t ev0[kMaxEv], ev1[kMaxEv];
     int stage[kMaxEv];
     int n = 0;
-    float ms[DSDTM_STAGE_COUNT] = { 0, 0, 0, 0, 0, 0 };
-    int launches[DSDTM_STAGE_COUNT] = { 0, 0, 0, 0, 0, 0 };
+    float ms[DSDTM_STAGE_COUNT] = {};
+    int launches[DSDTM_STAGE_COUNT] = {};
 };
 
 }  // namespace dsdtm
@@ -92,6 +92,12 @@ struct dsdtm_ctx {
     float* wa_px_d = nullptr;
     int* wa_meta_d = nullptr;                    // 3 ints per candidate: slot, ref_level, search_level
     dsdtm_candidate* cand_d = nullptr;           // max_batch * max_patches candidates (fused pipeline)
+    // local-map snapshots (f-1), grown on demand
+    dsdtm_kf_view* lm_kfs_d = nullptr;   size_t lm_kfs_cap = 0;
+    dsdtm_obs* lm_obs_d = nullptr;       size_t lm_obs_cap = 0;
+    dsdtm_map_point* lm_pts_d = nullptr; size_t lm_pts_cap = 0;
+    double* lm_pose_d = nullptr;                 // lm_kfs_cap * 7 : T_cur * T_kf^-1
+    dsdtm_reproj* lm_reproj_d = nullptr;         // lm_pts_cap
 
     // pinned host staging for small synchronous calls
     uint8_t* pinned = nullptr;
@@ -142,6 +148,7 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
 cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
 cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s);
 cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s);
+cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s);
 int sparse_align_smem_bytes(int nf_pad);
 size_t sparse_align_ws_doubles(int max_feats);
 cudaError_t sparse_align_init(dsdtm_ctx* c);

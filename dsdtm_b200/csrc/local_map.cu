@@ -1,0 +1,154 @@
+// local_map.cu -- SURVEY 8f-1: the map walk in front of FindMatchDirect, on flat snapshots of the local map.
+//
+//   kf_pose_kernel   : one thread per keyframe, T_c2r = T_cur * T_kf^-1 (ref: src/Feature_alignment.cpp:181) with Sophus
+//                      semantics (inverse = conjugate + rotated negated translation; product normalises the quaternion).
+//   local_map_kernel : one thread per map point:
+//                        Frame::World2Pixel + Camera::IsInImage(px, 8) + cell index   (ref: src/Feature_alignment.cpp:54-69)
+//                        MapPoint::Get_ClosetObs                                       (ref: src/MapPoint.cpp:133-174)
+//                        IsInImage(ref px / 2^level, 5, level)                         (ref: src/Feature_alignment.cpp:138)
+//                      and writes the dsdtm_candidate that candidate_prep_kernel (align2d.cu) consumes, so the chain
+//                      reproject -> observation -> affine -> warp -> Align2D never returns to the host.
+// fp64 in the reference's operation order, non-contracted (__dmul_rn / __dadd_rn), so every value that reaches the integer
+// decisions (cvRound, cell index, strict '>' on the cosine) is the one the CPU computes. A few thousand points per frame:
+// latency-bound by construction (one short dependent chain per thread); the point of the stage is removing the host round
+// trip between sparse alignment and Align2D, not bandwidth.
+#include "ctx.cuh"
+
+namespace dsdtm {
+
+namespace {
+
+struct LmArgs {
+    const dsdtm_kf_view* kfs; int n_kfs;
+    const dsdtm_obs* obs;
+    const dsdtm_map_point* pts; int n_pts;
+    double pose_cur[7]; double cur_center[3];
+    float fx, fy, cx, cy;
+    int width, height, cell_size, grid_cols;
+    double* kf_pose;            // n_kfs x 7
+    dsdtm_candidate* cand;      // n_pts
+    dsdtm_reproj* out;          // n_pts
+};
+
+// Eigen QuaternionBase::_transformVector, q = {w, x, y, z}
+__device__ __forceinline__ void qrot(const double* q, double v0, double v1, double v2, double& o0, double& o1, double& o2)
+{
+    double uv0 = __dsub_rn(__dmul_rn(q[2], v2), __dmul_rn(q[3], v1));
+    double uv1 = __dsub_rn(__dmul_rn(q[3], v0), __dmul_rn(q[1], v2));
+    double uv2 = __dsub_rn(__dmul_rn(q[1], v1), __dmul_rn(q[2], v0));
+    uv0 = __dadd_rn(uv0, uv0); uv1 = __dadd_rn(uv1, uv1); uv2 = __dadd_rn(uv2, uv2);
+    const double c0 = __dsub_rn(__dmul_rn(q[2], uv2), __dmul_rn(q[3], uv1));
+    const double c1 = __dsub_rn(__dmul_rn(q[3], uv0), __dmul_rn(q[1], uv2));
+    const double c2 = __dsub_rn(__dmul_rn(q[1], uv1), __dmul_rn(q[2], uv0));
+    o0 = __dadd_rn(__dadd_rn(v0, __dmul_rn(q[0], uv0)), c0);
+    o1 = __dadd_rn(__dadd_rn(v1, __dmul_rn(q[0], uv1)), c1);
+    o2 = __dadd_rn(__dadd_rn(v2, __dmul_rn(q[0], uv2)), c2);
+}
+
+__global__ void __launch_bounds__(64) kf_pose_kernel(const LmArgs a)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_kfs) return;
+    const double* p = a.kfs[k].pose_c2w;
+    // SE3::inverse(): so3 = conjugate, t = so3 * (t * -1)
+    const double iq[4] = { p[0], -p[1], -p[2], -p[3] };
+    double it0, it1, it2;
+    qrot(iq, __dmul_rn(p[4], -1.0), __dmul_rn(p[5], -1.0), __dmul_rn(p[6], -1.0), it0, it1, it2);
+    // SE3::operator*: t = t_a + R_a t_b ; q = q_a q_b (Eigen product) ; normalise
+    const double* A = a.pose_cur;
+    double r0, r1, r2;
+    qrot(A, it0, it1, it2, r0, r1, r2);
+    const double t0 = __dadd_rn(A[4], r0), t1 = __dadd_rn(A[5], r1), t2 = __dadd_rn(A[6], r2);
+    const double aw = A[0], ax = A[1], ay = A[2], az = A[3], bw = iq[0], bx = iq[1], by = iq[2], bz = iq[3];
+    double w = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(aw, bw), __dmul_rn(ax, bx)), __dmul_rn(ay, by)), __dmul_rn(az, bz));
+    double x = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(aw, bx), __dmul_rn(ax, bw)), __dmul_rn(ay, bz)), __dmul_rn(az, by));
+    double y = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(aw, by), __dmul_rn(ay, bw)), __dmul_rn(az, bx)), __dmul_rn(ax, bz));
+    double z = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(aw, bz), __dmul_rn(az, bw)), __dmul_rn(ax, by)), __dmul_rn(ay, bx));
+    const double n = sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)), __dmul_rn(w, w)));
+    x = __ddiv_rn(x, n); y = __ddiv_rn(y, n); z = __ddiv_rn(z, n); w = __ddiv_rn(w, n);
+    double* o = a.kf_pose + 7 * k;
+    o[0] = w; o[1] = x; o[2] = y; o[3] = z; o[4] = t0; o[5] = t1; o[6] = t2;
+}
+
+// Camera::IsInImage (ref: src/Camera.cpp:187-193): cvRound(float) is round-half-even; integer division of the image size.
+__device__ __forceinline__ bool in_image(float x, float y, int boundary, int level, int width, int height)
+{
+    const int rx = __float2int_rn(x), ry = __float2int_rn(y);
+    return rx >= boundary && rx < width / (1 << level) - boundary && ry >= boundary && ry < height / (1 << level) - boundary;
+}
+
+__global__ void __launch_bounds__(128) local_map_kernel(const LmArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_pts) return;
+    const dsdtm_map_point mp = a.pts[i];
+    const double P0 = mp.point_w[0], P1 = mp.point_w[1], P2 = mp.point_w[2];
+    // Frame::World2Pixel (ref: src/Frame.cpp:318-323): Camera2Pixel(T_c2w * P) = fx * X / Z + cx
+    double q0, q1, q2;
+    qrot(a.pose_cur, P0, P1, P2, q0, q1, q2);
+    q0 = __dadd_rn(q0, a.pose_cur[4]); q1 = __dadd_rn(q1, a.pose_cur[5]); q2 = __dadd_rn(q2, a.pose_cur[6]);
+    const double u = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fx, q0), q2), (double)a.cx);
+    const double v = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fy, q1), q2), (double)a.cy);
+    int flags = 0, cell = -1, best = -1;
+    if (in_image(__double2float_rn(u), __double2float_rn(v), 8, 0, a.width, a.height)) {          // ref: :58
+        flags |= DSDTM_LM_IN_IMAGE;
+        cell = (int)__ddiv_rn(v, (double)a.cell_size) * a.grid_cols + (int)__ddiv_rn(u, (double)a.cell_size);   // ref: :60-61
+    }
+    // MapPoint::Get_ClosetObs: direction point -> current camera, then the observation with the largest cosine (strict >)
+    double f0 = __dsub_rn(a.cur_center[0], P0), f1 = __dsub_rn(a.cur_center[1], P1), f2 = __dsub_rn(a.cur_center[2], P2);
+    double n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1)), __dmul_rn(f2, f2)));
+    f0 = __ddiv_rn(f0, n); f1 = __ddiv_rn(f1, n); f2 = __ddiv_rn(f2, n);
+    double best_cos = 0.0;
+    if (mp.obs_count > 0) best = mp.obs_begin;                                                        // min_it = begin()
+    for (int j = 0; j < mp.obs_count; ++j) {
+        const double* O = a.kfs[a.obs[mp.obs_begin + j].kf].center;
+        double r0 = __dsub_rn(O[0], P0), r1 = __dsub_rn(O[1], P1), r2 = __dsub_rn(O[2], P2);
+        const double rn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2)));
+        r0 = __ddiv_rn(r0, rn); r1 = __ddiv_rn(r1, rn); r2 = __ddiv_rn(r2, rn);
+        const double c = __dadd_rn(__dadd_rn(__dmul_rn(r0, f0), __dmul_rn(r1, f1)), __dmul_rn(r2, f2));
+        if (c > best_cos) { best_cos = c; best = mp.obs_begin + j; }
+    }
+    dsdtm_candidate cd;
+    cd.ref_slot = -1; cd.ref_level = 0;
+    cd.px[0] = u; cd.px[1] = v;
+    if (best >= 0) {
+        if (!(best_cos < 0.5)) flags |= DSDTM_LM_OBS_OK;                                              // ref: MapPoint.cpp:170
+        const dsdtm_obs ob = a.obs[best];
+        const float sc = (float)(1 << ob.level);
+        if (in_image(__fdiv_rn(ob.px[0], sc), __fdiv_rn(ob.px[1], sc), 5, ob.level, a.width, a.height)) flags |= DSDTM_LM_REF_OK;
+        const int all = DSDTM_LM_IN_IMAGE | DSDTM_LM_OBS_OK | DSDTM_LM_REF_OK;
+        if ((flags & all) == all) {
+            const dsdtm_kf_view& kf = a.kfs[ob.kf];
+            cd.ref_slot = kf.slot; cd.ref_level = ob.level;
+            cd.ref_px[0] = ob.px[0]; cd.ref_px[1] = ob.px[1];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { cd.ref_normal[k] = ob.normal[k]; cd.ref_point_w[k] = ob.point_w[k]; cd.kf_center[k] = kf.center[k]; }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) cd.pose_c2r[k] = a.kf_pose[7 * ob.kf + k];
+        }
+    }
+    a.cand[i] = cd;
+    dsdtm_reproj r;
+    r.px_proj[0] = u; r.px_proj[1] = v; r.px[0] = u; r.px[1] = v;
+    r.cell = cell; r.obs = best; r.flags = flags; r.level = -1;
+    a.out[i] = r;
+}
+
+}  // namespace
+
+cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s)
+{
+    LmArgs a;
+    a.kfs = c->lm_kfs_d; a.n_kfs = n_kfs; a.obs = c->lm_obs_d; a.pts = c->lm_pts_d; a.n_pts = n_pts;
+    for (int k = 0; k < 7; ++k) a.pose_cur[k] = pose_cur[k];
+    for (int k = 0; k < 3; ++k) a.cur_center[k] = cur_center[k];
+    a.fx = c->cam.fx; a.fy = c->cam.fy; a.cx = c->cam.cx; a.cy = c->cam.cy;
+    a.width = c->cam.width; a.height = c->cam.height; a.cell_size = c->prm.cell_size; a.grid_cols = c->grid_cols;
+    a.kf_pose = c->lm_pose_d; a.cand = c->cand_d; a.out = c->lm_reproj_d;
+    kf_pose_kernel<<<(n_kfs + 63) / 64, 64, 0, s>>>(a);
+    local_map_kernel<<<(n_pts + 127) / 128, 128, 0, s>>>(a);
+    c->launches += 2;
+    return cudaGetLastError();
+}
+
+}  // namespace dsdtm

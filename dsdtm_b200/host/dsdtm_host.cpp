@@ -499,39 +499,71 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
     GpuRuntime::Instance().BeginEpoch();
     // The reference walks cells in index order, candidates by found-count, and stops a cell at the first match; a match
     // paints the mask and thereby only changes which LATER candidates are tried, never their alignment result. So: sort
-    // the cells (as the reference does, in place), align every candidate of every cell speculatively in ONE GPU batch
-    // (WarpAffine + Align2D), then replay the greedy selection on the host in the reference's order.
+    // the cells (as the reference does, in place), snapshot the map points of all candidates with their observations into
+    // flat tables, let the device do Get_ClosetObs + the IsInImage gate + SolveAffineMatrix + WarpAffine + Align2D for all
+    // of them in ONE call (dsdtm_local_map_align_batch), then replay the greedy selection in the reference's order.
     GpuRuntime& rt = GpuRuntime::Instance();
-    struct Item { Candidate* cand; bool prepared; int batch_index; };
+    struct Item { Candidate* cand; int index; };               // index into the point table, -1 = IsBad at snapshot time
     std::vector<std::vector<Item>> items(mCells.size());
-    std::vector<dsdtm_candidate> cands;
+    std::vector<dsdtm_kf_view> kfs;
+    std::map<KeyFrame*, int> kf_index;
+    std::vector<dsdtm_obs> obs;
+    std::vector<dsdtm_map_point> pts;
     const int cur_slot_first = rt.Resident(frame->mGpu);     // touch the current frame first: it must stay resident as well
     for (size_t ci = 0; ci < mCells.size(); ++ci) {
         Cell* cell = mCells[ci];
         cell->sort([](Candidate& a, Candidate& b) { return a.mMpPoint->Get_FoundNums() > b.mMpPoint->Get_FoundNums(); });   // ref: :88,123-126
         for (Candidate& c : *cell) {
-            Item it{ &c, false, -1 };
-            Prepared p;
-            if (!c.mMpPoint->IsBad() && Prepare(c.mMpPoint, frame, c.mPx, p)) {
-                it.prepared = true;
-                it.batch_index = (int)cands.size();
-                cands.push_back(p.c);
+            Item it{ &c, -1 };
+            if (!c.mMpPoint->IsBad()) {
+                dsdtm_map_point mp;
+                const Vector3d P = c.mMpPoint->Get_Pose();
+                for (int k = 0; k < 3; ++k) mp.point_w[k] = P[k];
+                mp.obs_begin = (int)obs.size();
+                for (const auto& o : c.mMpPoint->Get_Observations()) {          // std::map order = the reference's iteration order
+                    KeyFrame* kf = o.first;
+                    auto found = kf_index.find(kf);
+                    if (found == kf_index.end()) {
+                        dsdtm_kf_view v{};
+                        v.slot = rt.Resident(kf->mGpu);
+                        const Vector3d O = kf->Get_CameraCnt();
+                        const SE3 T = kf->Get_Pose();
+                        for (int k = 0; k < 3; ++k) v.center[k] = O[k];
+                        for (int k = 0; k < 7; ++k) v.pose_c2w[k] = T.data()[k];
+                        found = kf_index.emplace(kf, (int)kfs.size()).first;
+                        kfs.push_back(v);
+                    }
+                    const Feature* f = kf->mvFeatures[o.second];
+                    dsdtm_obs ob{};
+                    ob.kf = found->second; ob.level = f->mlevel; ob.px[0] = f->mpx.x; ob.px[1] = f->mpx.y;
+                    const Vector3d Pf = f->Mpt ? f->Mpt->Get_Pose() : P;         // ref: :167 rf->Mpt->Get_Pose()
+                    for (int k = 0; k < 3; ++k) { ob.normal[k] = f->mNormal[k]; ob.point_w[k] = Pf[k]; }
+                    obs.push_back(ob);
+                }
+                mp.obs_count = (int)obs.size() - mp.obs_begin;
+                it.index = (int)pts.size();
+                pts.push_back(mp);
             }
             items[ci].push_back(it);
         }
     }
-    const int n = (int)cands.size();
-    std::vector<double> px((size_t)2 * n);
-    std::vector<int> search_level(n);
-    std::vector<uint8_t> conv(n);
+    const int n = (int)pts.size();
+    std::vector<dsdtm_reproj> res(n);
     if (n > 0) {
         const int cur_slot = rt.Resident(frame->mGpu);
-        // Resolving many keyframes can recycle a slot that an earlier candidate already points to when the pool is smaller than
-        // the local map (+ the current frame). That would silently sample the wrong image: fail loudly instead.
+        // Resolving many keyframes can recycle a slot that an earlier table entry already points to when the pool is smaller
+        // than the set of keyframes observing the local map (+ the current frame). That would silently sample the wrong image:
+        // fail loudly instead. (180 GB of HBM hold ~400 k VGA pyramids: size Gpu.MaxFrames for the whole map.)
         if (cur_slot != cur_slot_first || !rt.SlotsStillValid())
             throw std::runtime_error("Feature_Alignment::SearchLocalPoints: frame pool too small for the local map (raise Gpu.MaxFrames)");
-        if (dsdtm_feature_align_batch(rt.ctx(), cur_slot, cands.data(), n, mPyr_levels - 3, 10, px.data(), search_level.data(), conv.data(), nullptr) != 0)
-            throw std::runtime_error(std::string("dsdtm_feature_align_batch: ") + dsdtm_last_error(rt.ctx()));
+        const SE3 Tc = frame->Get_Pose();
+        const Vector3d Oc = frame->Get_CameraCnt();
+        double pose[7], center[3];
+        for (int k = 0; k < 7; ++k) pose[k] = Tc.data()[k];
+        for (int k = 0; k < 3; ++k) center[k] = Oc[k];
+        if (dsdtm_local_map_align_batch(rt.ctx(), cur_slot, pose, center, kfs.data(), (int)kfs.size(), obs.data(), (int)obs.size(),
+                                        pts.data(), n, mPyr_levels - 3, 10, res.data()) != 0)
+            throw std::runtime_error(std::string("dsdtm_local_map_align_batch: ") + dsdtm_last_error(rt.ctx()));
     }
     // replay (ref: :75-82, :91-118)
     int matches = 0;
@@ -540,11 +572,13 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
             Candidate& c = *it.cand;
             if (c.mMpPoint->IsBad()) continue;
             if (frame->mImgMask.at(cvRound((float)c.mPx[1]), cvRound((float)c.mPx[0])) != 255) continue;
-            if (!it.prepared) continue;
-            const int b = it.batch_index;
-            const int L = search_level[b];
-            c.mPx = Vector2d(px[2 * b], px[2 * b + 1]);            // ref: :154 (tPt is updated even on failure; already level-0 scaled)
-            if (!conv[b]) continue;
+            if (it.index < 0) continue;
+            const dsdtm_reproj& r = res[it.index];
+            const int gates = DSDTM_LM_OBS_OK | DSDTM_LM_REF_OK;   // FindMatchDirect's early-outs (:135-140), evaluated on the device
+            if ((r.flags & gates) != gates || r.level < 0) continue;
+            const int L = r.level;
+            c.mPx = Vector2d(r.px[0], r.px[1]);                    // ref: :154 (tPt is updated even on failure; already level-0 scaled)
+            if (!(r.flags & DSDTM_LM_CONVERGED)) continue;
             c.mMpPoint->IncreaseFound();
             Feature* f = new Feature(frame.get(), Point2f((float)c.mPx[0], (float)c.mPx[1]), L);
             f->SetPose(c.mMpPoint);

@@ -152,6 +152,7 @@ public:
     void IncreaseFound(int n = 1) { mnFound += n; }
     void Add_Observation(KeyFrame* kf, size_t idx) { mObservations[kf] = idx; }
     bool Get_ClosetObs(const Frame* frame, Feature*& feature, KeyFrame*& kf) const;
+    std::map<KeyFrame*, size_t> Get_Observations() const { return mObservations; }   // ref: src/MapPoint.cpp (copy under mMutexObs)
 private:
     mutable std::mutex mMutexPos;
     Vector3d mPose;

@@ -80,7 +80,7 @@ typedef struct {
 
 /* Per-stage device timing, filled when profiling is on (CUDA events on the context's stream). */
 enum { DSDTM_STAGE_PYRAMID = 0, DSDTM_STAGE_FAST = 1, DSDTM_STAGE_SPARSE_ALIGN = 2, DSDTM_STAGE_ALIGN2D = 3,
-       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_CAND_PREP = 5, DSDTM_STAGE_COUNT = 6 };
+       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_CAND_PREP = 5, DSDTM_STAGE_LOCAL_MAP = 6, DSDTM_STAGE_COUNT = 7 };
 
 /* ---------------------------------------------------------------- context ---------------------------------- */
 int         dsdtm_abi_version(void);
@@ -184,6 +184,50 @@ typedef struct {
  * may be NULL) = n x 4 row-major affine matrices for inspection. */
 int dsdtm_feature_align_batch(dsdtm_ctx* ctx, int cur_slot, const dsdtm_candidate* cands, int n, int max_search_level,
                               int max_iters, double* px_out, int* level_out, uint8_t* converged, double* A_out);
+
+/* ---------------------------------------------------------------- (f-1) local map on the device ------------ */
+/* The map walk that feeds FindMatchDirect -- Feature_Alignment::ReprojectPoint (ref: src/Feature_alignment.cpp:54-69) for
+ * every local map point (Tracking::UpdateLocalMap, ref: src/Tracking.cpp:258-313) and MapPoint::Get_ClosetObs
+ * (ref: src/MapPoint.cpp:133-174) with the IsInImage gate of :138 -- runs on flat snapshots of the local map, and chains
+ * into the candidate pipeline above without returning to the host. The host snapshots the tables once per frame (the
+ * mapper thread mutates the objects, SURVEY 8b "threading"). */
+typedef struct {
+    int32_t slot;           /* frame slot of the keyframe's pyramid */
+    int32_t reserved;
+    double  center[3];      /* KeyFrame::Get_CameraCnt() */
+    double  pose_c2w[7];    /* KeyFrame::Get_Pose() */
+} dsdtm_kf_view;            /* 88 bytes */
+typedef struct {
+    int32_t kf;             /* index into the dsdtm_kf_view table (key of MapPoint::mObservations) */
+    int32_t level;          /* observing Feature::mlevel */
+    float   px[2];          /* observing Feature::mpx */
+    double  normal[3];      /* observing Feature::mNormal */
+    double  point_w[3];     /* observing Feature::Mpt->Get_Pose() (ref: src/Feature_alignment.cpp:167) */
+} dsdtm_obs;                /* 64 bytes */
+typedef struct {
+    double  point_w[3];     /* MapPoint::Get_Pose() */
+    int32_t obs_begin;      /* first observation in the dsdtm_obs table ... */
+    int32_t obs_count;      /* ... listed in the iteration order of MapPoint::mObservations (ties keep the first) */
+} dsdtm_map_point;          /* 32 bytes */
+enum { DSDTM_LM_IN_IMAGE = 1,   /* ReprojectPoint returned true (IsInImage(px, 8)) */
+       DSDTM_LM_OBS_OK = 2,     /* Get_ClosetObs returned true (cos of the viewing angle >= 0.5) */
+       DSDTM_LM_REF_OK = 4,     /* the observing feature passes IsInImage(px / 2^level, 5, level) (ref: :138) */
+       DSDTM_LM_CONVERGED = 8 };/* Align2DGaussNewton returned true */
+typedef struct {
+    double  px_proj[2];     /* Frame::World2Pixel(point) = Candidate::mPx before alignment (level 0) */
+    double  px[2];          /* after FindMatchDirect (ref: :154); == px_proj when the candidate was not aligned */
+    int32_t cell;           /* grid cell of ReprojectPoint (:60-61), -1 when not in the image */
+    int32_t obs;            /* chosen observation (index into the dsdtm_obs table), -1 when the point has none */
+    int32_t flags;          /* DSDTM_LM_* */
+    int32_t level;          /* search level (ref: :156), -1 when the candidate was not aligned */
+} dsdtm_reproj;             /* 48 bytes */
+/* pose_cur_c2w / cur_center: Frame::Get_Pose() / Frame::Get_CameraCnt() of the current frame. Every point with
+ * IN_IMAGE|OBS_OK|REF_OK is aligned (SolveAffineMatrix .. Align2DGaussNewton, as dsdtm_feature_align_batch); the greedy,
+ * mask-dependent selection of SearchLocalPoints (:71-121) stays with the caller. n_pts <= max_batch * max_patches. */
+int dsdtm_local_map_align_batch(dsdtm_ctx* ctx, int cur_slot, const double pose_cur_c2w[7], const double cur_center[3],
+                                const dsdtm_kf_view* kfs, int n_kfs, const dsdtm_obs* obs, int n_obs,
+                                const dsdtm_map_point* pts, int n_pts, int max_search_level, int max_iters,
+                                dsdtm_reproj* out);
 
 /* ---------------------------------------------------------------- batched front end (sweep / bench) -------- */
 /* One "step" over n_pairs independent frame pairs: [pyramid(cur)] -> sparse align -> Align2D of the pair's patches

@@ -53,6 +53,10 @@ def lib():
         _lib = C.CDLL(_LIB)
         _lib.orc_shitomasi.restype = C.c_float
         _lib.orc_cvround.argtypes = [C.c_double]
+        _lib.orc_feature_depth.restype = C.c_float
+        _lib.orc_is_in_image.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int]
+        _lib.orc_depth_convert.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+        _lib.orc_unproject.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
     return _lib
 
 
@@ -284,6 +288,53 @@ def se3_act(a, p):
 def feature_normal(cam, px):
     out = np.empty(3)
     lib().orc_feature_normal(C.byref(cam), _p(np.ascontiguousarray(px, np.float32)), _p(out))
+    return out
+
+
+def is_in_image(cam, x, y, boundary, level=0):
+    return bool(lib().orc_is_in_image(C.byref(cam), float(np.float32(x)), float(np.float32(y)), int(boundary), int(level)))
+
+
+def reproject_point(cam, pose_cur_c2w, point_w, cell_size, grid_cols):
+    """-> (in_image, px[2], cell or -1)"""
+    px = np.empty(2); cell = C.c_int(-1)
+    ok = lib().orc_reproject_point(C.byref(cam), _p(np.ascontiguousarray(pose_cur_c2w, np.float64)), _p(np.ascontiguousarray(point_w, np.float64)),
+                                   int(cell_size), int(grid_cols), _p(px), C.byref(cell))
+    return bool(ok), px, (cell.value if ok else -1)
+
+
+def closest_obs(cur_center, point_w, kf_centers):
+    """-> (returned bool, index of the chosen observation or -1)"""
+    kc = np.ascontiguousarray(kf_centers, np.float64).reshape(-1, 3)
+    best = C.c_int(-1)
+    ok = lib().orc_closest_obs(_p(np.ascontiguousarray(cur_center, np.float64)), _p(np.ascontiguousarray(point_w, np.float64)),
+                               _p(kc), len(kc), C.byref(best))
+    return bool(ok), best.value
+
+
+def undistort_points(cam, dist, src):
+    src = np.ascontiguousarray(src, np.float32).reshape(-1, 2)
+    dst = np.empty_like(src)
+    lib().orc_undistort_points(C.byref(cam), _p(np.ascontiguousarray(dist, np.float32)), _p(src), len(src), _p(dst))
+    return dst
+
+
+def depth_convert(depth_u16, depth_scale):
+    d = np.ascontiguousarray(depth_u16, np.uint16)
+    out = np.empty(d.shape, np.float32)
+    lib().orc_depth_convert(_p(d), d.size, float(np.float32(depth_scale)), _p(out))
+    return out
+
+
+def feature_depth(depth_f32, px):
+    d = np.ascontiguousarray(depth_f32, np.float32)
+    return float(lib().orc_feature_depth(_p(d), d.shape[1], d.shape[0], _p(np.ascontiguousarray(px, np.float32))))
+
+
+def unproject(cam, pose_c2w, px, d):
+    out = np.empty(3)
+    lib().orc_unproject(C.byref(cam), _p(np.ascontiguousarray(pose_c2w, np.float64)), _p(np.ascontiguousarray(px, np.float32)),
+                        float(np.float32(d)), _p(out))
     return out
 
 

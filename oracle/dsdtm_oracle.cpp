@@ -443,6 +443,104 @@ void orc_feature_normal(const orc_cam* cam, const float px[2], double normal[3])
     normal[0] = n[0] / nn; normal[1] = n[1] / nn; normal[2] = n[2] / nn;
 }
 
+// ------------------------------------------------------------------------------------------
+// ReprojectPoint / Get_ClosetObs / IsInImage
+// ------------------------------------------------------------------------------------------
+int orc_is_in_image(const orc_cam* cam, float x, float y, int boundary, int level)   // ref: src/Camera.cpp:187-193
+{
+    const int rx = orc_cvround(x), ry = orc_cvround(y);
+    return rx >= boundary && rx < cam->width / (1 << level) - boundary && ry >= boundary && ry < cam->height / (1 << level) - boundary;
+}
+
+int orc_reproject_point(const orc_cam* cam, const double pose_cur_c2w[7], const double point_w[3], int cell_size, int grid_cols,
+                        double px[2], int* cell)                                   // ref: src/Feature_alignment.cpp:54-69
+{
+    double q[3];
+    se3_act(se3_from(pose_cur_c2w), point_w, q);                                   // ref: src/Frame.cpp:320
+    px[0] = (double)cam->fx * q[0] / q[2] + (double)cam->cx;                       // ref: src/Camera.cpp:167-171
+    px[1] = (double)cam->fy * q[1] / q[2] + (double)cam->cy;
+    if (!orc_is_in_image(cam, (float)px[0], (float)px[1], 8, 0)) return 0;         // ref: :58
+    *cell = static_cast<int>(px[1] / cell_size) * grid_cols + static_cast<int>(px[0] / cell_size);   // ref: :60-61
+    return 1;
+}
+
+int orc_closest_obs(const double cur_center[3], const double point_w[3], const double* kf_centers, int n_obs, int* best)
+{                                                                                  // ref: src/MapPoint.cpp:133-174
+    if (n_obs <= 0) { *best = -1; return 0; }
+    double f[3] = { cur_center[0] - point_w[0], cur_center[1] - point_w[1], cur_center[2] - point_w[2] };
+    double n = std::sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    f[0] /= n; f[1] /= n; f[2] /= n;                                               // Eigen normalize(): *this /= norm()
+    double min_angle = 0;
+    int it = 0;
+    for (int j = 0; j < n_obs; ++j) {
+        double r[3] = { kf_centers[3 * j] - point_w[0], kf_centers[3 * j + 1] - point_w[1], kf_centers[3 * j + 2] - point_w[2] };
+        const double rn = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        r[0] /= rn; r[1] /= rn; r[2] /= rn;
+        const double c = r[0] * f[0] + r[1] * f[1] + r[2] * f[2];
+        if (c > min_angle) { min_angle = c; it = j; }                              // ref: :154-158
+    }
+    *best = it;
+    return !(min_angle < 0.5);                                                     // ref: :170-171
+}
+
+// ------------------------------------------------------------------------------------------
+// keyframe ingest
+// ------------------------------------------------------------------------------------------
+void orc_undistort_points(const orc_cam* cam, const float dist[5], const float* src, int n, float* dst)
+{
+    // OpenCV cvUndistortPointsInternal (imgproc/src/undistort.dispatch.cpp), CV_32F K / dist widened to double, no R,
+    // P = K, criteria = (MAX_ITER, 5): not under /root/reference, restated from the published algorithm.
+    const double fx = cam->fx, fy = cam->fy, cx = cam->cx, cy = cam->cy;
+    const double ifx = 1. / fx, ify = 1. / fy;
+    const double k0 = dist[0], k1 = dist[1], p1 = dist[2], p2 = dist[3], k2 = dist[4];   // k[0] k[1] k[2] k[3] k[4]; k[5..] = 0
+    for (int i = 0; i < n; ++i) {
+        double x = src[2 * i], y = src[2 * i + 1];
+        const double u = x, v = y;
+        x = (x - cx) * ifx;
+        y = (y - cy) * ify;
+        const double x0 = x, y0 = y;                                               // identity tilt: invProj = 1
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0 * r2 + 0) * r2 + 0) * r2) / (1 + ((k2 * r2 + k1) * r2 + k0) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + 0 * r2 + 0 * r2 * r2;
+            const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + 0 * r2 + 0 * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        // RR = P * I = K : xx = fx*x + 0*y + cx, ww = 1/(0*x + 0*y + 1)
+        const double xx = fx * x + 0 * y + cx, yy = 0 * x + fy * y + cy, ww = 1. / (0 * x + 0 * y + 1);
+        dst[2 * i] = (float)(xx * ww);
+        dst[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+void orc_depth_convert(const uint16_t* depth, int n, float depth_scale, float* out)  // ref: src/Tracking.cpp:56
+{
+    const float a = (float)(double)(1.0f / depth_scale);                           // alpha travels as double, cvt uses float
+    for (int i = 0; i < n; ++i) out[i] = (float)depth[i] * a;
+}
+
+float orc_feature_depth(const float* depth, int w, int h, const float px[2])       // ref: src/Frame.cpp:200-224
+{
+    const int x = orc_cvround(px[0]), y = orc_cvround(px[1]);
+    auto at = [&](int xx, int yy) -> float { return (xx < 0 || yy < 0 || xx >= w || yy >= h) ? 0.f : depth[(size_t)yy * w + xx]; };
+    float d = at(x, y);
+    if (d != 0) return d;
+    const int dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, -1, 0, 1 };
+    for (int i = 0; i < 4; ++i) {
+        d = at(x + dx[i], y + dy[i]);
+        if (d != 0) return d;
+    }
+    return -1.0f;
+}
+
+void orc_unproject(const orc_cam* cam, const double pose_c2w[7], const float px[2], float d, double out[3])
+{                                                                                  // ref: src/Frame.cpp:152-157
+    const double p[3] = { (double)(d * (px[0] - cam->cx) / cam->fx), (double)(d * (px[1] - cam->cy) / cam->fy), (double)d };
+    se3_act(se3_inv(se3_from(pose_c2w)), p, out);
+}
+
 void orc_ldlt6_solve(const double H[36], const double b[6], double x[6]) { ldlt6_solve(H, b, x); }
 void orc_se3_exp(const double x[6], double pose[7]) { se3_to(se3_exp(x), pose); }
 void orc_se3_mul(const double a[7], const double b[7], double out[7]) { se3_to(se3_mul(se3_from(a), se3_from(b)), out); }

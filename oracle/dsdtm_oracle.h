@@ -118,6 +118,30 @@ void orc_se3_act(const double a[7], const double p[3], double out[3]);
 /* ref: src/Camera.cpp:173-178 + src/Frame.cpp:83-92 : float Pixel2Camera(px,1.0) widened, then normalize() */
 void orc_feature_normal(const orc_cam* cam, const float px[2], double normal[3]);
 
+/* ---- the map walk in front of FindMatchDirect ---- */
+/* ref: src/Camera.cpp:187-193 Camera::IsInImage (cvRound of the float pixel, integer division of the image size) */
+int orc_is_in_image(const orc_cam* cam, float x, float y, int boundary, int level);
+/* ref: src/Feature_alignment.cpp:54-69 ReprojectPoint + src/Frame.cpp:318-323 World2Pixel; returns 1 when the point lands
+ * inside IsInImage(px, 8); px is always written, *cell only when in the image */
+int orc_reproject_point(const orc_cam* cam, const double pose_cur_c2w[7], const double point_w[3], int cell_size,
+                        int grid_cols, double px[2], int* cell);
+/* ref: src/MapPoint.cpp:133-174 Get_ClosetObs; kf_centers = n_obs x 3 in mObservations iteration order; *best = chosen
+ * observation (0 when n_obs > 0 and no cosine is positive, -1 when n_obs == 0); returns the bool of the reference */
+int orc_closest_obs(const double cur_center[3], const double point_w[3], const double* kf_centers, int n_obs, int* best);
+
+/* ---- keyframe ingest ---- */
+/* cv::undistortPoints(src, dst, K, dist, noArray(), K) as called at ref: src/Frame.cpp:121-122 : K and dist are CV_32F
+ * (ref: src/Camera.cpp:53-68) widened to double, 5 fixed-point iterations (OpenCV default criteria), float in / float out.
+ * dist = {k1, k2, p1, p2, k3}. PINNED against cv2 4.13 goldens (tests/golden/undistort_cv2.npz). */
+void orc_undistort_points(const orc_cam* cam, const float dist[5], const float* src, int n, float* dst);
+/* ref: src/Tracking.cpp:56 depthImg.convertTo(CV_32F, 1.0f/mDepthScale) on CV_16U input: float(src) * float(alpha) */
+void orc_depth_convert(const uint16_t* depth, int n, float depth_scale, float* out);
+/* ref: src/Frame.cpp:200-224 Get_FeatureDetph(Point2f): cvRound, centre then the 4-neighbourhood in the order
+ * (-1,0) (0,-1) (1,0) (0,1), -1.0 when all are 0. Reads outside the image (undefined in the reference) count as 0. */
+float orc_feature_depth(const float* depth, int w, int h, const float px[2]);
+/* ref: src/Frame.cpp:152-157 UnProject: T_c2w^-1 * Pixel2Camera(px, d) (src/Camera.cpp:173-178 evaluated in float) */
+void orc_unproject(const orc_cam* cam, const double pose_c2w[7], const float px[2], float d, double out[3]);
+
 /* Batched CPU driver used only for the cpu_baseline / reference bench arm: runs pyramid(cur) +
  * sparse align + align2d for pairs [0,n) with n_threads std::threads. Layout documented in bench.py. */
 int orc_pair_batch(const orc_cam* cam, int levels, const uint8_t* ref_pyrs, const uint8_t* cur_imgs, int n_pairs,

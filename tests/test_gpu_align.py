@@ -277,6 +277,93 @@ def test_fused_candidate_pipeline_matches_oracle_stage_by_stage(ctx, scenario):
     assert not conv[lv >= 1].any()
 
 
+def test_local_map_stage_matches_oracle(ctx, scenario):
+    """ReprojectPoint + Get_ClosetObs + the IsInImage gate + FindMatchDirect's arithmetic as one device call
+    (dsdtm_local_map_align_batch) against the oracle's per-point chain (ref: src/Feature_alignment.cpp:54-69,128-158,
+    src/MapPoint.cpp:133-174). Integer outputs (flags, cell, chosen observation, level) exact; px within the north_star tolerance."""
+    from dsdtm_b200 import capi
+    sc = scenario
+    _upload(ctx, sc)                     # slot 0 = keyframe image, slot 1 = current frame
+    packed, offs, ws, hs = sc["ref_pyr"]
+    cam = sc["cam"]; oc = H.ocam(cam)
+    rng = np.random.default_rng(17)
+    T_cur = sc["T_cur"]
+    cur_center = O.se3_inv(T_cur)[4:]
+    # keyframe table: the real reference frame, the same image seen from a shifted pose, and a keyframe far to the side
+    kf_pose = [sc["T_ref"], S.pose_mul(S.pose_from_xi([0.25, -0.1, 0.05, 0.0, 0.03, 0.0]), sc["T_ref"]),
+               S.pose_mul(S.pose_from_xi([3.0, 0.5, 1.5, 0.0, -0.9, 0.0]), sc["T_ref"]), S.pose_mul(S.pose_from_xi([-0.1, 0.05, 0.0, 0.01, 0.0, 0.02]), sc["T_ref"])]
+    kfs = np.zeros(len(kf_pose), capi.KF_VIEW_DT)
+    for k, T in enumerate(kf_pose):
+        kfs[k]["slot"] = 0 if k != 3 else 1
+        kfs[k]["pose_c2w"] = T; kfs[k]["center"] = O.se3_inv(T)[4:]
+    F = sc["feats"]
+    pts_w = [F[i]["point_w"] for i in range(len(F))]
+    pts_w += [np.array([rng.uniform(-4, 4), rng.uniform(-3, 3), rng.uniform(-1.0, 6.0)]) for _ in range(200)]   # some behind / outside
+    pts_w += [np.array([0.3, 0.2, 0.0])]                                                                       # z = 0 in the ref camera
+    obs, pts = [], np.zeros(len(pts_w), capi.MAP_POINT_DT)
+    for i, P in enumerate(pts_w):
+        pts[i]["point_w"] = P; pts[i]["obs_begin"] = len(obs)
+        cnt = 0 if i % 37 == 36 else int(rng.integers(1, 5))
+        for k in rng.permutation(len(kf_pose))[:cnt]:
+            ob = np.zeros((), capi.OBS_DT)
+            f = F[i % len(F)]
+            ob["kf"] = k; ob["level"] = f["level"] if k == 0 else rng.integers(0, 4)
+            ob["px"] = f["px"] if rng.uniform() < 0.8 else (rng.uniform(0, 640), rng.uniform(0, 480))       # some fail the :138 gate
+            ob["normal"] = O.feature_normal(oc, ob["px"]); ob["point_w"] = P
+            obs.append(ob)
+        pts[i]["obs_count"] = cnt
+    obs = np.array(obs, capi.OBS_DT)
+    out = ctx.local_map_align_batch(1, T_cur, cur_center, kfs, obs, pts, 2, 10)
+    rows, cols = O.grid_dims(cam["width"], cam["height"], 15)
+    n_aligned = n_conv = 0
+    seen = set()
+    mism = []
+    for i, P in enumerate(pts_w):
+        r = out[i]
+        inimg, px, cell = O.reproject_point(oc, T_cur, P, 15, cols)
+        assert np.array_equal(px, r["px_proj"], equal_nan=True), (i, px, r["px_proj"])
+        assert cell == r["cell"] and bool(r["flags"] & capi.LM_IN_IMAGE) == inimg, i
+        b, c = int(pts[i]["obs_begin"]), int(pts[i]["obs_count"])
+        ok, best = O.closest_obs(cur_center, P, [kfs[int(obs[b + j]["kf"])]["center"] for j in range(c)])
+        assert r["obs"] == (b + best if c else -1) and bool(r["flags"] & capi.LM_OBS_OK) == ok, i
+        ref_ok = False
+        if c:
+            ob = obs[b + best]
+            L0 = int(ob["level"])
+            rp = ob["px"] / np.float32(1 << L0)
+            ref_ok = O.is_in_image(oc, rp[0], rp[1], 5, L0)
+        assert bool(r["flags"] & capi.LM_REF_OK) == ref_ok, i
+        seen.add(int(r["flags"]) & 7)
+        if not (inimg and ok and ref_ok):
+            assert r["level"] == -1 and not (r["flags"] & capi.LM_CONVERGED) and np.array_equal(r["px"], r["px_proj"], equal_nan=True), i
+            continue
+        n_aligned += 1
+        kf = kfs[int(ob["kf"])]
+        T_c2r = O.se3_mul(T_cur, O.se3_inv(kf["pose_c2w"]))
+        A = O.solve_affine(oc, kf["center"], ob["point_w"], ob["normal"], ob["px"], L0, T_c2r)
+        SL = O.best_search_level(A, 2)
+        assert r["level"] == SL, i
+        img_pyr = sc["ref_pyr"][0] if kf["slot"] == 0 else sc["cur_pyr"][0]
+        patch = O.warp_affine(A, O.pyr_level(img_pyr, offs, ws, hs, L0), ob["px"], L0, SL)
+        p, conv, _ = O.align2d(O.pyr_level(sc["cur_pyr"][0], offs, ws, hs, SL), patch, 10, px / (1 << SL))
+        assert conv == bool(r["flags"] & capi.LM_CONVERGED), i
+        if not np.allclose(p * (1 << SL), r["px"], atol=PX_TOL * (1 << SL), equal_nan=True):
+            # a non-converged Gauss-Newton run on a deliberately wrong patch wanders for 10 iterations and amplifies the
+            # reduction-order difference of the fp32 sums; only those may differ
+            wandered = (not conv) and np.abs(p * (1 << SL) - px).max() > 2.0
+            mism.append((i, conv, wandered, SL, int(ob["kf"]), p * (1 << SL), r["px"].copy(), px))
+        n_conv += conv
+    assert all(m[2] for m in mism) and len(mism) <= n_aligned // 20, (len(mism), n_aligned, mism[:12])
+    assert n_aligned > 200 and n_conv > 100 and len(seen) >= 5, (n_aligned, n_conv, seen)
+    # bad tables are refused
+    bad = obs.copy(); bad[0]["kf"] = len(kfs)
+    with pytest.raises(capi.DsdtmError):
+        ctx.local_map_align_batch(1, T_cur, cur_center, kfs, bad, pts, 2, 10)
+    badp = pts.copy(); badp[-1]["obs_begin"] = len(obs); badp[-1]["obs_count"] = 1
+    with pytest.raises(capi.DsdtmError):
+        ctx.local_map_align_batch(1, T_cur, cur_center, kfs, obs, badp, 2, 10)
+
+
 def test_staged_batch_run_graph_replay_and_e2e(ctx):
     """dsdtm_batch_stage/run/fetch (CUDA-graph replay on HBM-resident inputs) and the host-buffer e2e call give the same
     results as the single-pair entry points."""

@@ -166,3 +166,38 @@ def test_se3_group_axioms():
         assert np.allclose(O.se3_mul(a, O.se3_inv(a)), S.IDENTITY, atol=1e-12)
         p = rng.uniform(-1, 1, 3)
         assert np.allclose(O.se3_act(a, p), S.pose_act(a, p), atol=1e-12)
+
+
+def test_undistort_points_matches_cv2_golden(golden):
+    """SURVEY 8f-3: the restatement of cv::undistortPoints as called by Frame::UndistortFeatures (ref: src/Frame.cpp:121-122)
+    against cv2 4.13 on the reference's own distortion sets (tests/golden/make_golden_ingest.py)."""
+    g = golden["undistort_cv2"]
+    for name in ("euroc", "default", "zero", "strong"):
+        K, D, src, dst = g[name + "_K"], g[name + "_D"], g[name + "_src"], g[name + "_dst"]
+        w, h = (int(v) for v in g[name + "_wh"])
+        cam = O.make_cam(w, h, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), float(K[0, 0]))
+        got = O.undistort_points(cam, D, src)
+        bad = int((got.view(np.uint32) != dst.view(np.uint32)).sum())
+        assert bad == 0, (name, bad, np.abs(got - dst).max())
+    z = g["zero_src"]
+    assert np.abs(g["zero_dst"] - z).max() < 1e-4        # zero distortion: identity up to the float round trip
+
+
+def test_depth_lookup_and_convert_restatements():
+    """ref: src/Tracking.cpp:56 (convertTo CV_32F, 1/scale) and src/Frame.cpp:200-224 (Get_FeatureDetph)."""
+    rng = np.random.default_rng(5)
+    d16 = rng.integers(0, 65536, (48, 64)).astype(np.uint16)
+    for scale in (5000.0, 1000.0, 1.0):
+        want = d16.astype(np.float32) * np.float32(np.float32(1.0) / np.float32(scale))
+        assert (O.depth_convert(d16, scale) == want).all()
+    d = np.zeros((10, 12), np.float32)
+    d[5, 4] = 2.5            # left neighbour of (5,5) in image coords is (x=4,y=5)
+    d[4, 5] = 3.5            # upper neighbour
+    assert O.feature_depth(d, (5.2, 4.6)) == 2.5     # cvRound -> (5,5); centre 0 -> (-1,0) first
+    d[5, 4] = 0
+    assert O.feature_depth(d, (5.0, 5.0)) == 3.5     # then (0,-1)
+    d[4, 5] = 0
+    assert O.feature_depth(d, (5.0, 5.0)) == -1.0
+    d[5, 5] = 1.25
+    assert O.feature_depth(d, (5.49, 4.51)) == 1.25
+    assert O.feature_depth(d, (0.0, 0.0)) == -1.0    # neighbours outside the image count as 0
