@@ -8,7 +8,7 @@ import numpy as np
 
 from . import build as _build
 
-STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine", "cand_prep", "local_map")
+STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine", "cand_prep", "local_map", "ingest")
 
 CORNER_DT = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4")])
 REF_FEAT_DT = np.dtype([("px", "<f4", 2), ("level", "<i4"), ("initial", "<i4"),
@@ -24,6 +24,9 @@ MAP_POINT_DT = np.dtype([("point_w", "<f8", 3), ("obs_begin", "<i4"), ("obs_coun
 REPROJ_DT = np.dtype([("px_proj", "<f8", 2), ("px", "<f8", 2), ("cell", "<i4"), ("obs", "<i4"), ("flags", "<i4"), ("level", "<i4")])
 assert KF_VIEW_DT.itemsize == 88 and OBS_DT.itemsize == 64 and MAP_POINT_DT.itemsize == 32 and REPROJ_DT.itemsize == 48
 LM_IN_IMAGE, LM_OBS_OK, LM_REF_OK, LM_CONVERGED = 1, 2, 4, 8
+LIFTED_DT = np.dtype([("px", "<f4", 2), ("depth", "<f4"), ("status", "<i4"), ("normal", "<f8", 3), ("point_w", "<f8", 3)])
+assert LIFTED_DT.itemsize == 64
+LIFT_SKIPPED, LIFT_OK, LIFT_NO_DEPTH = 0, 1, 2
 
 
 class Cam(C.Structure):
@@ -51,7 +54,7 @@ SYMBOLS = [
     "dsdtm_fast_score_map", "dsdtm_grid_dims", "dsdtm_sparse_align", "dsdtm_sparse_align_batch",
     "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
-    "dsdtm_local_map_align_batch",
+    "dsdtm_local_map_align_batch", "dsdtm_depth_upload", "dsdtm_depth_convert_f32", "dsdtm_keyframe_lift",
 ]
 
 
@@ -259,6 +262,25 @@ class Context:
         self._ck(self.L.dsdtm_local_map_align_batch(
             self.hp, int(cur_slot), _p(np.ascontiguousarray(pose_cur_c2w, np.float64)), _p(np.ascontiguousarray(cur_center, np.float64)),
             _p(kfs), len(kfs), _p(obs), len(obs), _p(pts), len(pts), int(max_search_level), int(max_iters), _p(out)))
+        return out
+
+    # ---- keyframe ingest (f-3 / f-4)
+    def depth_upload(self, depth_slot, depth_u16):
+        d = np.ascontiguousarray(depth_u16, np.uint16)
+        assert d.shape == (self.height, self.width)
+        self._ck(self.L.dsdtm_depth_upload(self.hp, int(depth_slot), _p(d), 0))
+
+    def depth_convert_f32(self, first_depth_slot, n, depth_scale, fetch=True):
+        out = np.empty((n, self.height, self.width), np.float32) if fetch else None
+        self._ck(self.L.dsdtm_depth_convert_f32(self.hp, int(first_depth_slot), int(n), C.c_float(depth_scale), _p(out)))
+        return out
+
+    def keyframe_lift(self, depth_slot, pose_c2w, dist, depth_scale, px_in, initial=None):
+        px = np.ascontiguousarray(px_in, np.float32).reshape(-1, 2)
+        ini = None if initial is None else np.ascontiguousarray(initial, np.uint8)
+        out = np.zeros(len(px), LIFTED_DT)
+        self._ck(self.L.dsdtm_keyframe_lift(self.hp, int(depth_slot), _p(np.ascontiguousarray(pose_c2w, np.float64)),
+                                            _p(np.ascontiguousarray(dist, np.float32)), C.c_float(depth_scale), _p(px), _p(ini), len(px), _p(out)))
         return out
 
     # ---- batched front end

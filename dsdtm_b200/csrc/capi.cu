@@ -198,7 +198,8 @@ void dsdtm_destroy(dsdtm_ctx* c)
     void* bufs[] = { c->frames_d, c->cells_d, c->occupied_d, c->scoremap_d, c->fast_tiles_d, c->ref_slots_d, c->cur_slots_d,
                      c->feats_d, c->n_feats_d, c->centers_d, c->poses_in_d, c->poses_out_d, c->n_tracked_d, c->log_d, c->n_log_d,
                      c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d, c->cand_d,
-                     c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d };
+                     c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d,
+                     c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { if (c->timer.ev0[i]) cudaEventDestroy(c->timer.ev0[i]); if (c->timer.ev1[i]) cudaEventDestroy(c->timer.ev1[i]); }
@@ -269,9 +270,15 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
         return 0;
     }
     if (std::strcmp(key, "pyramid_kernel") == 0) {
-        if (value != 0 && value != 1) return fail(c, DSDTM_E_ARG, "pyramid_kernel must be 0 (auto) or 1 (tile)");
+        if (value != 0 && value != 1 && value != 2) return fail(c, DSDTM_E_ARG, "pyramid_kernel must be 0 (auto: bulk-staged where eligible), 1 (tile) or 2 (register strip)");
         c->pyr_kernel = value;
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
+        return 0;
+    }
+    if (std::strcmp(key, "depth_slots") == 0) {
+        if (value < 1 || value > 65536) return fail(c, DSDTM_E_ARG, "depth_slots must be 1..65536");
+        if (c->depth_d) return fail(c, DSDTM_E_ARG, "depth_slots must be set before the depth pool is first used");
+        c->depth_slots = value;
         return 0;
     }
     return fail(c, DSDTM_E_ARG, "unknown option");
@@ -627,6 +634,79 @@ int dsdtm_local_map_align_batch(dsdtm_ctx* c, int cur_slot, const double pose_cu
         out[i].level = lvl_h[i];
         if (conv_h[i]) out[i].flags |= DSDTM_LM_CONVERGED;
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ (f-3 / f-4) ingest
+static int ensure_depth_pool(dsdtm_ctx* c)
+{
+    if (c->depth_d) return 0;
+    const size_t px = (size_t)c->cam.width * c->cam.height;
+    if (dalloc(c, &c->depth_d, px * c->depth_slots)) return DSDTM_E_NOMEM;
+    cudaError_t e = cudaMemset(c->depth_d, 0, px * c->depth_slots * sizeof(uint16_t));
+    if (e != cudaSuccess) return fail(c, DSDTM_E_CUDA, "cudaMemset(depth pool)", e);
+    return 0;
+}
+
+int dsdtm_depth_upload(dsdtm_ctx* c, int depth_slot, const uint16_t* depth, int stride_bytes)
+{
+    if (!c || !depth) return DSDTM_E_ARG;
+    if (depth_slot < 0 || depth_slot >= c->depth_slots) return fail(c, DSDTM_E_ARG, "depth slot out of range (option depth_slots)");
+    const int w = c->cam.width, h = c->cam.height;
+    if (stride_bytes == 0) stride_bytes = 2 * w;
+    if (stride_bytes < 2 * w) return fail(c, DSDTM_E_ARG, "depth stride < 2 * width");
+    if (ensure_depth_pool(c)) return DSDTM_E_NOMEM;
+    cudaStream_t s = c->stream;
+    DSDTM_CUDA(c, cudaMemcpy2DAsync(c->depth_d + (size_t)depth_slot * w * h, 2 * (size_t)w, depth, (size_t)stride_bytes, 2 * (size_t)w, h,
+                                    cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dsdtm_depth_convert_f32(dsdtm_ctx* c, int first_depth_slot, int n, float depth_scale, float* out)
+{
+    if (!c || n < 0) return DSDTM_E_ARG;
+    if (first_depth_slot < 0 || first_depth_slot + n > c->depth_slots) return fail(c, DSDTM_E_ARG, "depth slot range out of bounds (option depth_slots)");
+    if (!(depth_scale > 0.f)) return fail(c, DSDTM_E_ARG, "depth_scale must be > 0");
+    if (n == 0) return 0;
+    if (ensure_depth_pool(c)) return DSDTM_E_NOMEM;
+    const size_t px = (size_t)c->cam.width * c->cam.height;
+    if (!c->depth_f32_d && dalloc(c, &c->depth_f32_d, px * c->depth_slots)) return DSDTM_E_NOMEM;
+    cudaStream_t s = c->stream;
+    stage_begin(c, DSDTM_STAGE_INGEST);
+    DSDTM_CUDA(c, launch_depth_convert(c, first_depth_slot, n, depth_scale, s));
+    stage_end(c, 1);
+    if (out) DSDTM_CUDA(c, cudaMemcpyAsync(out, c->depth_f32_d + (size_t)first_depth_slot * px, px * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dsdtm_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], const float dist[5], float depth_scale,
+                        const float* px_in, const uint8_t* initial, int n, dsdtm_lifted* out)
+{
+    if (!c || !pose_c2w || !dist || n < 0 || (n && (!px_in || !out))) return DSDTM_E_ARG;
+    if (depth_slot >= c->depth_slots) return fail(c, DSDTM_E_ARG, "depth slot out of range (option depth_slots)");
+    if (depth_slot >= 0 && !(depth_scale > 0.f)) return fail(c, DSDTM_E_ARG, "depth_scale must be > 0");
+    if (n == 0) return 0;
+    if (depth_slot >= 0 && ensure_depth_pool(c)) return DSDTM_E_NOMEM;
+    if ((size_t)n > c->lift_cap) {
+        size_t z0 = 0, z1 = 0, z2 = 0;
+        const size_t want = std::max<size_t>((size_t)n, 512);
+        if (c->lift_px_d) { cudaFree(c->lift_px_d); c->lift_px_d = nullptr; }
+        if (c->lift_initial_d) { cudaFree(c->lift_initial_d); c->lift_initial_d = nullptr; }
+        if (c->lift_out_d) { cudaFree(c->lift_out_d); c->lift_out_d = nullptr; }
+        c->lift_cap = 0;
+        if (grow(c, &c->lift_px_d, &z0, 2 * want) || grow(c, &c->lift_initial_d, &z1, want) || grow(c, &c->lift_out_d, &z2, want)) return DSDTM_E_NOMEM;
+        c->lift_cap = want;
+    }
+    cudaStream_t s = c->stream;
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->lift_px_d, px_in, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (initial) DSDTM_CUDA(c, cudaMemcpyAsync(c->lift_initial_d, initial, (size_t)n, cudaMemcpyHostToDevice, s));
+    stage_begin(c, DSDTM_STAGE_INGEST);
+    DSDTM_CUDA(c, launch_keyframe_lift(c, depth_slot, pose_c2w, dist, depth_slot >= 0 ? depth_scale : 1.0f, initial != nullptr, n, s));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(out, c->lift_out_d, (size_t)n * sizeof(dsdtm_lifted), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
     return 0;
 }
 

@@ -98,6 +98,13 @@ struct dsdtm_ctx {
     dsdtm_map_point* lm_pts_d = nullptr; size_t lm_pts_cap = 0;
     double* lm_pose_d = nullptr;                 // lm_kfs_cap * 7 : T_cur * T_kf^-1
     dsdtm_reproj* lm_reproj_d = nullptr;         // lm_pts_cap
+    // keyframe ingest (f-3 / f-4), allocated on first use
+    int depth_slots = 4;
+    uint16_t* depth_d = nullptr;                 // depth_slots * w*h raw depth
+    float* depth_f32_d = nullptr;                // depth_slots * w*h (only for dsdtm_depth_convert_f32)
+    float* lift_px_d = nullptr;          size_t lift_cap = 0;
+    uint8_t* lift_initial_d = nullptr;
+    dsdtm_lifted* lift_out_d = nullptr;
 
     // pinned host staging for small synchronous calls
     uint8_t* pinned = nullptr;
@@ -148,6 +155,9 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
 cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
 cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s);
 cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s);
+cudaError_t launch_depth_convert(dsdtm_ctx* c, int first_slot, int n, float depth_scale, cudaStream_t s);
+cudaError_t launch_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], const float dist[5], float depth_scale,
+                                 bool have_initial, int n, cudaStream_t s);
 cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s);
 int sparse_align_smem_bytes(int nf_pad);
 size_t sparse_align_ws_doubles(int max_feats);

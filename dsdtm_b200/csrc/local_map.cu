@@ -13,6 +13,7 @@
 // latency-bound by construction (one short dependent chain per thread); the point of the stage is removing the host round
 // trip between sparse alignment and Align2D, not bandwidth.
 #include "ctx.cuh"
+#include "se3_exact.cuh"
 
 namespace dsdtm {
 
@@ -30,44 +31,16 @@ struct LmArgs {
     dsdtm_reproj* out;          // n_pts
 };
 
-// Eigen QuaternionBase::_transformVector, q = {w, x, y, z}
-__device__ __forceinline__ void qrot(const double* q, double v0, double v1, double v2, double& o0, double& o1, double& o2)
-{
-    double uv0 = __dsub_rn(__dmul_rn(q[2], v2), __dmul_rn(q[3], v1));
-    double uv1 = __dsub_rn(__dmul_rn(q[3], v0), __dmul_rn(q[1], v2));
-    double uv2 = __dsub_rn(__dmul_rn(q[1], v1), __dmul_rn(q[2], v0));
-    uv0 = __dadd_rn(uv0, uv0); uv1 = __dadd_rn(uv1, uv1); uv2 = __dadd_rn(uv2, uv2);
-    const double c0 = __dsub_rn(__dmul_rn(q[2], uv2), __dmul_rn(q[3], uv1));
-    const double c1 = __dsub_rn(__dmul_rn(q[3], uv0), __dmul_rn(q[1], uv2));
-    const double c2 = __dsub_rn(__dmul_rn(q[1], uv1), __dmul_rn(q[2], uv0));
-    o0 = __dadd_rn(__dadd_rn(v0, __dmul_rn(q[0], uv0)), c0);
-    o1 = __dadd_rn(__dadd_rn(v1, __dmul_rn(q[0], uv1)), c1);
-    o2 = __dadd_rn(__dadd_rn(v2, __dmul_rn(q[0], uv2)), c2);
-}
-
 __global__ void __launch_bounds__(64) kf_pose_kernel(const LmArgs a)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.n_kfs) return;
-    const double* p = a.kfs[k].pose_c2w;
-    // SE3::inverse(): so3 = conjugate, t = so3 * (t * -1)
-    const double iq[4] = { p[0], -p[1], -p[2], -p[3] };
-    double it0, it1, it2;
-    qrot(iq, __dmul_rn(p[4], -1.0), __dmul_rn(p[5], -1.0), __dmul_rn(p[6], -1.0), it0, it1, it2);
-    // SE3::operator*: t = t_a + R_a t_b ; q = q_a q_b (Eigen product) ; normalise
-    const double* A = a.pose_cur;
-    double r0, r1, r2;
-    qrot(A, it0, it1, it2, r0, r1, r2);
-    const double t0 = __dadd_rn(A[4], r0), t1 = __dadd_rn(A[5], r1), t2 = __dadd_rn(A[6], r2);
-    const double aw = A[0], ax = A[1], ay = A[2], az = A[3], bw = iq[0], bx = iq[1], by = iq[2], bz = iq[3];
-    double w = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(aw, bw), __dmul_rn(ax, bx)), __dmul_rn(ay, by)), __dmul_rn(az, bz));
-    double x = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(aw, bx), __dmul_rn(ax, bw)), __dmul_rn(ay, bz)), __dmul_rn(az, by));
-    double y = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(aw, by), __dmul_rn(ay, bw)), __dmul_rn(az, bx)), __dmul_rn(ax, bz));
-    double z = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(aw, bz), __dmul_rn(az, bw)), __dmul_rn(ax, by)), __dmul_rn(ay, bx));
-    const double n = sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)), __dmul_rn(w, w)));
-    x = __ddiv_rn(x, n); y = __ddiv_rn(y, n); z = __ddiv_rn(z, n); w = __ddiv_rn(w, n);
+    double inv[7], T[7];
+    se3_inv_exact(a.kfs[k].pose_c2w, inv);
+    se3_mul_exact(a.pose_cur, inv, T);
     double* o = a.kf_pose + 7 * k;
-    o[0] = w; o[1] = x; o[2] = y; o[3] = z; o[4] = t0; o[5] = t1; o[6] = t2;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) o[j] = T[j];
 }
 
 // Camera::IsInImage (ref: src/Camera.cpp:187-193): cvRound(float) is round-half-even; integer division of the image size.
@@ -85,7 +58,7 @@ __global__ void __launch_bounds__(128) local_map_kernel(const LmArgs a)
     const double P0 = mp.point_w[0], P1 = mp.point_w[1], P2 = mp.point_w[2];
     // Frame::World2Pixel (ref: src/Frame.cpp:318-323): Camera2Pixel(T_c2w * P) = fx * X / Z + cx
     double q0, q1, q2;
-    qrot(a.pose_cur, P0, P1, P2, q0, q1, q2);
+    qrot_exact(a.pose_cur, P0, P1, P2, q0, q1, q2);
     q0 = __dadd_rn(q0, a.pose_cur[4]); q1 = __dadd_rn(q1, a.pose_cur[5]); q2 = __dadd_rn(q2, a.pose_cur[6]);
     const double u = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fx, q0), q2), (double)a.cx);
     const double v = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fy, q1), q2), (double)a.cy);
@@ -145,7 +118,7 @@ cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const doubl
     a.fx = c->cam.fx; a.fy = c->cam.fy; a.cx = c->cam.cx; a.cy = c->cam.cy;
     a.width = c->cam.width; a.height = c->cam.height; a.cell_size = c->prm.cell_size; a.grid_cols = c->grid_cols;
     a.kf_pose = c->lm_pose_d; a.cand = c->cand_d; a.out = c->lm_reproj_d;
-    kf_pose_kernel<<<(n_kfs + 63) / 64, 64, 0, s>>>(a);
+    if (n_kfs > 0) kf_pose_kernel<<<(n_kfs + 63) / 64, 64, 0, s>>>(a);
     local_map_kernel<<<(n_pts + 127) / 128, 128, 0, s>>>(a);
     c->launches += 2;
     return cudaGetLastError();

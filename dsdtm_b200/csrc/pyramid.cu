@@ -166,12 +166,112 @@ __global__ void __launch_bounds__(128) pyrdown_strip_kernel(uint8_t* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Bulk-staged kernel (levels whose source width is a multiple of 16): level images are dense, so the 2*TH+3 source rows
+// of a tile of TH output rows are ONE contiguous byte range. One elected thread issues a single cp.async.bulk (TMA 1-D)
+// for it and everybody waits on the mbarrier; memory latency is covered by the other resident CTAs (a tile is ~12-22 KB,
+// 10-18 CTAs per SM), not by per-thread loads, and the arithmetic reads shared memory with immediate offsets: ~45
+// instructions per 4 outputs instead of ~100 in the strip kernel, which was co-limited by issue slots (60 % busy at 52 % of
+// DRAM throughput, profiles/r1_pyramid_fast_align2d.md).
+#ifndef DSDTM_PYR_BULK_RPT
+#define DSDTM_PYR_BULK_RPT 8        // output rows per thread
+#endif
+#ifndef DSDTM_PYR_BULK_THREADS
+#define DSDTM_PYR_BULK_THREADS 160  // target CTA size; a tile is xq column groups x (threads / xq) sub-strips
+#endif
+constexpr int BRPT = DSDTM_PYR_BULK_RPT;
+constexpr int BULK_PAD = 16;        // bytes in front of / behind the staged rows (edge threads read one word outside)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint2 hrow_s(const uint8_t* row, int c0, bool left, bool right)
+{
+    const uint2 mid = *reinterpret_cast<const uint2*>(row + c0);
+    const uint32_t w0 = mid.x, w1 = mid.y;
+    uint32_t wm1 = *reinterpret_cast<const uint32_t*>(row + c0 - 4);
+    uint32_t w2 = *reinterpret_cast<const uint32_t*>(row + c0 + 8);
+    if (left) wm1 = __byte_perm(w0, 0, 0x1200);          // reflect-101: cols -2, -1 -> 2, 1
+    if (right) w2 = w1 >> 16;                            // col w -> w - 2
+    const uint32_t K = 0x04060401u;
+    const uint32_t h0 = __dp4a(__byte_perm(wm1, w0, 0x5432), K, __byte_perm(w0, 0, 0x4442));
+    const uint32_t h1 = __dp4a(w0, K, __byte_perm(w1, 0, 0x4440));
+    const uint32_t h2 = __dp4a(__byte_perm(w0, w1, 0x5432), K, __byte_perm(w1, 0, 0x4442));
+    const uint32_t h3 = __dp4a(w1, K, __byte_perm(w2, 0, 0x4440));
+    return make_uint2(__byte_perm(h0, h1, 0x5410), __byte_perm(h2, h3, 0x5410));
+}
+
+__global__ void __launch_bounds__(1024) pyrdown_bulk_kernel(uint8_t* __restrict__ frames, unsigned frame_stride, int first_slot,
+                                                            const int* __restrict__ slots, unsigned src_off, unsigned dst_off,
+                                                            int w, int h, int dw, int dh, int tile_rows)
+{
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    uint8_t* s_rows = s_raw + BULK_PAD;
+    const int slot = slots ? slots[blockIdx.y] : first_slot + blockIdx.y;
+    const uint8_t* __restrict__ src = frames + (size_t)slot * frame_stride + src_off;
+    uint8_t* __restrict__ dst = frames + (size_t)slot * frame_stride + dst_off;
+    const int ty0 = blockIdx.x * tile_rows, ty1 = min(ty0 + tile_rows, dh);
+    const int lo = max(2 * ty0 - 2, 0), hi = min(2 * ty1, h - 1);            // source rows lo..hi: one contiguous range
+    const uint32_t bytes = (uint32_t)(hi - lo + 1) * (uint32_t)w;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(s_rows)), "l"(src + (size_t)lo * w), "r"(bytes), "r"(smem_u32(&s_bar)) : "memory");
+    }
+    // per-thread geometry while the copy is in flight
+    const int xq = dw >> 2;
+    const int strip = threadIdx.x / xq, g = threadIdx.x - strip * xq;
+    const int c0 = 8 * g;
+    const bool left = g == 0, right = g == xq - 1;
+    const int y0 = ty0 + strip * BRPT, y1 = min(y0 + BRPT, ty1);
+    {
+        uint32_t done = 0;
+        int spins = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(&s_bar)) : "memory");
+            if (!done && ++spins > (1 << 22)) __trap();      // a lost copy must not hang the GPU
+        }
+    }
+    if (y0 >= y1) return;
+    const uint8_t* base = s_rows - (size_t)lo * w;       // base + r * w = staged source row r
+    uint2 r0 = hrow_s(base + reflect_row(2 * y0 - 2, h) * w, c0, left, right);
+    uint2 r1 = hrow_s(base + reflect_row(2 * y0 - 1, h) * w, c0, left, right);
+    uint2 r2 = hrow_s(base + (2 * y0) * w, c0, left, right);
+    uint8_t* out = dst + (size_t)y0 * dw + 4 * g;
+#pragma unroll 2
+    for (int y = y0; y < y1; ++y) {
+        const uint2 r3 = hrow_s(base + reflect_row(2 * y + 1, h) * w, c0, left, right);
+        const uint2 r4 = hrow_s(base + reflect_row(2 * y + 2, h) * w, c0, left, right);
+        const uint32_t a = r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + 0x00800080u;
+        const uint32_t b = r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + 0x00800080u;
+        *reinterpret_cast<uint32_t*>(out) = __byte_perm(a, b, 0x7531);
+        out += dw;
+        r0 = r2; r1 = r3; r2 = r4;
+    }
+}
+
 cudaError_t launch_levels(dsdtm_ctx* c, int first_slot, const int* slots_d, int n, cudaStream_t s)
 {
     const LevelGeom& g = c->geo;
     for (int l = 1; l < g.levels; ++l) {
         const int w = g.w[l - 1], h = g.h[l - 1], dw = g.w[l], dh = g.h[l];
-        if ((w & 7) == 0 && (dw & 3) == 0 && h >= 3 && 2 * dw == w && c->pyr_kernel != 1) {
+        if ((w & 15) == 0 && h >= 3 && 2 * dw == w && (dw >> 2) <= 1024 && (size_t)(2 * BRPT + 3) * w + 2 * BULK_PAD <= 48 * 1024 && c->pyr_kernel == 0) {
+            const int xq = dw >> 2;
+            int strips = std::max(1, DSDTM_PYR_BULK_THREADS / xq);
+            strips = std::min(strips, (dh + BRPT - 1) / BRPT);
+            while (xq * strips > 1024) --strips;
+            while (strips > 1 && (size_t)(2 * strips * BRPT + 3) * w + 2 * BULK_PAD > 48 * 1024) --strips;
+            const int tile_rows = strips * BRPT;
+            const size_t smem = (size_t)(2 * tile_rows + 3) * w + 2 * BULK_PAD;
+            dim3 grid((dh + tile_rows - 1) / tile_rows, n);
+            pyrdown_bulk_kernel<<<grid, xq * strips, smem, s>>>(c->frames_d, g.frame_stride, first_slot, slots_d, g.off[l - 1], g.off[l], w, h, dw, dh, tile_rows);
+        } else if ((w & 7) == 0 && (dw & 3) == 0 && h >= 3 && 2 * dw == w && c->pyr_kernel != 1) {
             const int n_items = (dw >> 2) * ((dh + RPT - 1) / RPT);
             dim3 grid((n_items + 127) / 128, n);
             pyrdown_strip_kernel<<<grid, 128, 0, s>>>(c->frames_d, g.frame_stride, first_slot, slots_d, g.off[l - 1], g.off[l], w, h, dw, dh, n_items);

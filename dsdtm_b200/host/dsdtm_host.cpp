@@ -156,6 +156,9 @@ Camera::Camera()
     mfx = Config::Get<float>("Camera.fx"); mfy = Config::Get<float>("Camera.fy");
     mcx = Config::Get<float>("Camera.cx"); mcy = Config::Get<float>("Camera.cy");
     mwidth = Config::Get<int>("Camera.width"); mheight = Config::Get<int>("Camera.height");
+    mk1 = Config::Has("Camera.k1") ? Config::Get<float>("Camera.k1") : 0.f; mk2 = Config::Has("Camera.k2") ? Config::Get<float>("Camera.k2") : 0.f;
+    mp1 = Config::Has("Camera.p1") ? Config::Get<float>("Camera.p1") : 0.f; mp2 = Config::Has("Camera.p2") ? Config::Get<float>("Camera.p2") : 0.f;
+    mk3 = Config::Has("Camera.k3") ? Config::Get<float>("Camera.k3") : 0.f;
 }
 
 Vector2d Camera::Camera2Pixel(const Vector3d& P) const { return Vector2d(mfx * P[0] / P[2] + mcx, mfy * P[1] / P[2] + mcy); }
@@ -255,7 +258,7 @@ Frame::Frame(CameraPtr cam, const Mat8& gray, double ts) : mCamera(cam), mdCloTi
     mDynamicMask = Mat8(mCamera->mheight, mCamera->mwidth, 0);
 }
 
-Frame::~Frame() {}
+Frame::~Frame() { if (g_runtime && g_runtime->DepthOwner() == this) g_runtime->SetDepthOwner(nullptr); }
 
 void Frame::ComputeImagePyramid(const Mat8 image, std::vector<Mat8>& pyr)   // ref: src/Frame.cpp:74-81
 {
@@ -285,6 +288,50 @@ void Frame::Set_Pose(const SE3& pose)                             // ref: src/Fr
 }
 
 Vector2d Frame::World2Pixel(const Vector3d& p) const { return mCamera->Camera2Pixel(mT_c2w * p); }   // ref: :318-323
+
+// ---- RGB-D keyframe path. One depth slot is enough: only the frame that is becoming a keyframe needs its depth on the device.
+void Frame::SetDepth(const uint16_t* depth, int stride_bytes, float depth_scale)
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    if (dsdtm_depth_upload(rt.ctx(), 0, depth, stride_bytes) != 0)
+        throw std::runtime_error(std::string("dsdtm_depth_upload: ") + dsdtm_last_error(rt.ctx()));
+    rt.SetDepthOwner(this);
+    mHasDepth = true; mDepthScale = depth_scale;
+}
+
+void Frame::UndistortFeatures()                                   // ref: src/Frame.cpp:94-150 (+ :152-157, :200-224 for the cache)
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    const int n = (int)mvFeatures.size();
+    mvMapPoints.resize(n);
+    if (n == 0) { mLifted.clear(); return; }
+    if (mHasDepth && rt.DepthOwner() != this)
+        throw std::runtime_error("Frame::UndistortFeatures: the depth slot now holds another frame's depth (call SetDepth again)");
+    std::vector<float> px((size_t)2 * n);
+    std::vector<uint8_t> initial(n);
+    for (int i = 0; i < n; ++i) { px[2 * i] = mvFeatures[i]->mpx.x; px[2 * i + 1] = mvFeatures[i]->mpx.y; initial[i] = mvFeatures[i]->mbInitial; }
+    const float dist[5] = { mCamera->mk1, mCamera->mk2, mCamera->mp1, mCamera->mp2, mCamera->mk3 };
+    mLifted.assign(n, dsdtm_lifted{});
+    if (dsdtm_keyframe_lift(rt.ctx(), mHasDepth ? 0 : -1, mT_c2w.data(), dist, mDepthScale, px.data(), initial.data(), n, mLifted.data()) != 0)
+        throw std::runtime_error(std::string("dsdtm_keyframe_lift: ") + dsdtm_last_error(rt.ctx()));
+    for (int i = 0; i < n; ++i) {
+        if (mvFeatures[i]->mbInitial) continue;                  // ref: :140-141
+        mvFeatures[i]->mpx = Point2f(mLifted[i].px[0], mLifted[i].px[1]);
+        mvFeatures[i]->mNormal = Vector3d(mLifted[i].normal[0], mLifted[i].normal[1], mLifted[i].normal[2]);
+    }
+}
+
+float Frame::Get_FeatureDetph(const Feature* feature)             // ref: src/Frame.cpp:176-198
+{
+    for (size_t i = 0; i < mvFeatures.size() && i < mLifted.size(); ++i)
+        if (mvFeatures[i] == feature) {
+            if (mLifted[i].status == DSDTM_LIFT_SKIPPED) break;
+            return mLifted[i].depth;
+        }
+    throw std::runtime_error("Frame::Get_FeatureDetph: feature was not lifted (call UndistortFeatures after SetDepth; mbInitial features are skipped as in the reference)");
+}
+
+Vector3d Frame::UnProject(const Point2f px, const float d) { return mT_c2w.inverse() * mCamera->Pixel2Camera(px, d); }   // ref: :152-157
 
 void Frame::Set_Mask()                                            // ref: src/Frame.cpp:286-298
 {

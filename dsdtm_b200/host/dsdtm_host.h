@@ -120,6 +120,7 @@ public:
     Vector3d Pixel2Camera(const Vector2d& px, const float& depth) const;
     bool IsInImage(const Point2f pt, int boundary = 0, int level = 0) const;
     float mf, mfx, mfy, mcx, mcy;
+    float mk1, mk2, mp1, mp2, mk3;       // ref: src/Camera.cpp:41-45 (0 when the config has no Camera.k1 .. k3)
     int mwidth, mheight;
 };
 typedef std::shared_ptr<Camera> CameraPtr;
@@ -175,6 +176,13 @@ public:
     Vector3d Get_CameraCnt() const { return mOw; }
     Vector2d World2Pixel(const Vector3d& p) const;
     void Set_Mask();
+    // RGB-D keyframe path (ref: src/Frame.cpp:94-157,200-224; src/Tracking.cpp:56,412-464). SetDepth replaces the CV_32F
+    // cv::Mat mDepthImg: the raw 16-bit image goes to HBM, scaling by 1/depth_scale happens at the lookups.
+    void SetDepth(const uint16_t* depth, int stride_bytes, float depth_scale);
+    void UndistortFeatures();                          // GPU: dsdtm_keyframe_lift over all features (also fills the cache below)
+    float Get_FeatureDetph(const Feature* feature);    // value of the reference's lookup, from the cache of UndistortFeatures
+    Vector3d UnProject(const Point2f px, const float d);
+    const std::vector<dsdtm_lifted>& Lifted() const { return mLifted; }   // new: per-feature device results (depth, world point)
 
     CameraPtr mCamera;
     double mdCloTimestamp;
@@ -185,6 +193,9 @@ public:
     Mat8 mImgMask, mDynamicMask;
     int mPyra_levels, mMin_Dist;
     std::shared_ptr<GpuSlot> mGpu;     // new member: where the pyramid lives in HBM
+    bool mHasDepth = false;
+    float mDepthScale = 1.0f;
+    std::vector<dsdtm_lifted> mLifted;
 protected:
     SE3 mT_c2w;
     Vector3d mOw;
@@ -280,6 +291,8 @@ public:
     // epoch = one batched call that resolves several slots before using them: detects a slot being recycled in between
     void BeginEpoch() { mEpochStart = mClock; mEpochEvicted = false; }
     bool SlotsStillValid() const { return !mEpochEvicted; }
+    void SetDepthOwner(const Frame* f) { mDepthOwner = f; }      // depth slot 0 holds this frame's depth image
+    const Frame* DepthOwner() const { return mDepthOwner; }
     ~GpuRuntime();
 private:
     GpuRuntime();
@@ -290,6 +303,7 @@ private:
     std::vector<unsigned long long> mStamp;
     unsigned long long mClock = 0, mEpochStart = 0;
     bool mEpochEvicted = false;
+    const Frame* mDepthOwner = nullptr;
     friend class GpuSlot;
 };
 

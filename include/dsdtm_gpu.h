@@ -80,7 +80,7 @@ typedef struct {
 
 /* Per-stage device timing, filled when profiling is on (CUDA events on the context's stream). */
 enum { DSDTM_STAGE_PYRAMID = 0, DSDTM_STAGE_FAST = 1, DSDTM_STAGE_SPARSE_ALIGN = 2, DSDTM_STAGE_ALIGN2D = 3,
-       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_CAND_PREP = 5, DSDTM_STAGE_LOCAL_MAP = 6, DSDTM_STAGE_COUNT = 7 };
+       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_CAND_PREP = 5, DSDTM_STAGE_LOCAL_MAP = 6, DSDTM_STAGE_INGEST = 7, DSDTM_STAGE_COUNT = 8 };
 
 /* ---------------------------------------------------------------- context ---------------------------------- */
 int         dsdtm_abi_version(void);
@@ -228,6 +228,29 @@ int dsdtm_local_map_align_batch(dsdtm_ctx* ctx, int cur_slot, const double pose_
                                 const dsdtm_kf_view* kfs, int n_kfs, const dsdtm_obs* obs, int n_obs,
                                 const dsdtm_map_point* pts, int n_pts, int max_search_level, int max_iters,
                                 dsdtm_reproj* out);
+
+/* ---------------------------------------------------------------- (f-3 / f-4) keyframe ingest ------------- */
+/* Depth images live in their own small pool of raw 16-bit frames (option "depth_slots", default 4, allocated on first
+ * use). The CV_32F image of Tracking::Track_RGBDCam (ref: src/Tracking.cpp:56, convertTo(CV_32F, 1/DepthScale)) is never
+ * needed by the hot path: the <= 5 lookups per new feature convert on the fly with the same single rounding. */
+int dsdtm_depth_upload(dsdtm_ctx* ctx, int depth_slot, const uint16_t* depth, int stride_bytes);
+/* The float image itself for n consecutive depth slots (ref: src/Tracking.cpp:56); out = n*h*w floats on the host, or NULL
+ * to leave the result in HBM (timing). */
+int dsdtm_depth_convert_f32(dsdtm_ctx* ctx, int first_depth_slot, int n, float depth_scale, float* out);
+enum { DSDTM_LIFT_SKIPPED = 0,   /* Feature::mbInitial was set: untouched (ref: src/Frame.cpp:140-141, src/Tracking.cpp:427-433) */
+       DSDTM_LIFT_OK = 1,        /* undistorted, normal, depth and world point valid */
+       DSDTM_LIFT_NO_DEPTH = 2 };/* undistorted + normal only: Get_FeatureDetph returned -1 (or no depth slot given) */
+typedef struct {
+    float   px[2];          /* Feature::mpx after Frame::UndistortFeatures (ref: src/Frame.cpp:94-150) */
+    float   depth;          /* Frame::Get_FeatureDetph(px) (ref: src/Frame.cpp:200-224), -1 when none */
+    int32_t status;         /* DSDTM_LIFT_* */
+    double  normal[3];      /* Feature::mNormal = normalize(Pixel2Camera(px, 1)) (ref: src/Frame.cpp:146-147) */
+    double  point_w[3];     /* Frame::UnProject(px, depth) (ref: src/Frame.cpp:152-157): the new MapPoint's position */
+} dsdtm_lifted;             /* 64 bytes */
+/* Tracking::CraeteKeyframe's per-feature arithmetic (ref: src/Tracking.cpp:412-464) for the n features of one frame in one
+ * launch. dist = {k1,k2,p1,p2,k3} (ref: src/Camera.cpp:41-45); depth_slot < 0: undistort + normal only; initial may be NULL. */
+int dsdtm_keyframe_lift(dsdtm_ctx* ctx, int depth_slot, const double pose_c2w[7], const float dist[5], float depth_scale,
+                        const float* px_in, const uint8_t* initial, int n, dsdtm_lifted* out);
 
 /* ---------------------------------------------------------------- batched front end (sweep / bench) -------- */
 /* One "step" over n_pairs independent frame pairs: [pyramid(cur)] -> sparse align -> Align2D of the pair's patches

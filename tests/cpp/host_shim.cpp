@@ -67,6 +67,31 @@ int hs_detect(void* f, double thr, int use_existing)
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// Tracking::CraeteKeyframe's RGB-D part (ref: src/Tracking.cpp:412-464): SetDepth (replaces the CV_32F mDepthImg), UndistortFeatures,
+// then per non-initial feature Get_FeatureDetph + UnProject. out: n x {px.x, px.y, depth, world xyz (device), world xyz (host UnProject)}
+int hs_frame_keyframe_lift(void* f, const uint16_t* depth, float depth_scale, double* out9, double* normals3)
+{
+    try {
+        Frame* fr = static_cast<HsFrame*>(f)->f.get();
+        fr->SetDepth(depth, 0, depth_scale);
+        fr->UndistortFeatures();
+        const auto& L = fr->Lifted();
+        for (size_t i = 0; i < fr->mvFeatures.size(); ++i) {
+            Feature* ft = fr->mvFeatures[i];
+            double* o = out9 + 9 * i;
+            o[0] = ft->mpx.x; o[1] = ft->mpx.y;
+            for (int k = 0; k < 3; ++k) normals3[3 * i + k] = ft->mNormal[k];
+            if (ft->mbInitial) { o[2] = -2.0; continue; }
+            const float z = fr->Get_FeatureDetph(ft);
+            o[2] = z;
+            if (z < 0) continue;
+            const Vector3d P = fr->UnProject(ft->mpx, z);
+            for (int k = 0; k < 3; ++k) { o[3 + k] = L[i].point_w[k]; o[6 + k] = P[k]; }
+        }
+        return (int)fr->mvFeatures.size();
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // CreateInitialMapRGBD-like: bearing vectors + one MapPoint per feature with a non-zero world point
 void hs_frame_attach_points(void* f, const double* pts, const uint8_t* has)
 {

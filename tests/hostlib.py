@@ -53,6 +53,7 @@ def lib():
         L.hs_frame_attach_points_from.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hs_frame_feature_mp_ids.argtypes = [C.c_void_p, C.c_void_p]
         L.hs_align2d_single.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.hs_frame_keyframe_lift.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.hs_circle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
         _lib = L
     return _lib
@@ -62,9 +63,12 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def configure(cam, levels=5, cell=15, max_fts=300, min_fts=15, min_dist=15, max_frames=16):
+def configure(cam, levels=5, cell=15, max_fts=300, min_fts=15, min_dist=15, max_frames=16, dist=None):
     L = lib()
     L.hs_reset()
+    if dist is not None:
+        for k, v in zip(("Camera.k1", "Camera.k2", "Camera.p1", "Camera.p2", "Camera.k3"), dist):
+            L.hs_config_set(k.encode(), repr(float(v)).encode())
     for k, v in (("Camera.width", cam["width"]), ("Camera.height", cam["height"]), ("Camera.fx", cam["fx"]), ("Camera.fy", cam["fy"]),
                  ("Camera.cx", cam["cx"]), ("Camera.cy", cam["cy"]), ("Camera.f", cam["f"]), ("Camera.MaxPyraLevels", levels),
                  ("Camera.MinPyraLevels", 0), ("Camera.CellSize", cell), ("Camera.Max_fts", max_fts), ("Camera.Max_tkfts", 200),
@@ -104,6 +108,15 @@ class HFrame:
 
     def attach_points_from(self, start, pts, has):
         lib().hs_frame_attach_points_from(self.h, int(start), _p(np.ascontiguousarray(pts, np.float64)), _p(np.ascontiguousarray(has, np.uint8)))
+
+    def keyframe_lift(self, depth_u16, depth_scale):
+        """SetDepth + UndistortFeatures + Get_FeatureDetph + UnProject -> (n x 9 table, n x 3 normals), see host_shim.cpp"""
+        n = lib().hs_frame_n_features(self.h)
+        out = np.zeros((n, 9)); nrm = np.zeros((n, 3))
+        d = np.ascontiguousarray(depth_u16, np.uint16)
+        if lib().hs_frame_keyframe_lift(self.h, _p(d), C.c_float(depth_scale), _p(out), _p(nrm)) < 0:
+            raise RuntimeError(lib().hs_last_error().decode())
+        return out, nrm
 
     def mp_ids(self):
         n = lib().hs_frame_n_features(self.h)

@@ -32,7 +32,7 @@ def test_pyramid_bit_exact_752x480_against_cv2_golden(golden):
     c.close()
 
 
-@pytest.mark.parametrize("shape", [(481, 641), (33, 140), (61, 81), (16, 128), (9, 9)])
+@pytest.mark.parametrize("shape", [(481, 641), (33, 140), (61, 81), (16, 128), (9, 9), (67, 256), (480, 1920), (37, 96), (12, 32), (200, 4096)])
 def test_pyramid_odd_and_tiny_shapes(shape):
     rng = np.random.default_rng(shape[0] * 1000 + shape[1])
     img = rng.integers(0, 256, shape, dtype=np.uint8)
@@ -46,16 +46,19 @@ def test_pyramid_odd_and_tiny_shapes(shape):
 
 
 def test_pyramid_tile_kernel_option_is_bit_exact_too(ctx, scenario):
-    """"pyramid_kernel" = 1 forces the shared-memory tile kernel on every level (the strip kernel's fallback path)."""
+    """"pyramid_kernel" = 1 forces the shared-memory tile kernel on every level, 2 the register strip kernel (the fallbacks of
+    the default bulk-staged kernel)."""
     from dsdtm_b200 import capi
-    ctx.set_option("pyramid_kernel", 1)
-    try:
-        ctx.upload(5, scenario["cur_img"])
-    finally:
-        ctx.set_option("pyramid_kernel", 0)
     packed, offs, ws, hs = scenario["cur_pyr"]
-    for l in range(5):
-        assert (ctx.download_level(5, l) == O.pyr_level(packed, offs, ws, hs, l)).all(), l
+    for opt in (1, 2):
+        ctx.set_option("pyramid_kernel", opt)
+        try:
+            ctx.upload(5, scenario["ref_img"])       # different content first, so a kernel that writes nothing is caught
+            ctx.upload(5, scenario["cur_img"])
+        finally:
+            ctx.set_option("pyramid_kernel", 0)
+        for l in range(5):
+            assert (ctx.download_level(5, l) == O.pyr_level(packed, offs, ws, hs, l)).all(), (opt, l)
     with pytest.raises(capi.DsdtmError):
         ctx.set_option("pyramid_kernel", 7)
     with pytest.raises(capi.DsdtmError):

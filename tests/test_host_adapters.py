@@ -188,3 +188,37 @@ def test_feature_alignment_search_local_points(built, scenario):
     # refined positions land on the true reprojections
     truth = np.array([want_i[1] for want_i in want])
     assert np.median(np.linalg.norm(px - truth, axis=1)) < 1e-3
+
+
+@pytest.mark.gpu
+def test_frame_rgbd_keyframe_path(built, scenario):
+    """Tracking::CraeteKeyframe's per-feature arithmetic through the Frame interface (ref: src/Tracking.cpp:412-464):
+    detect -> UndistortFeatures (ref: src/Frame.cpp:94-150) -> Get_FeatureDetph (:200-224) -> UnProject (:152-157), with the
+    EuRoC distortion set on the kinect geometry, against the oracle (cv2-pinned undistortPoints)."""
+    sc = scenario
+    dist = (-0.28368365, 0.07451284, -0.00010473, -3.55590700e-05, 0.0)
+    cam_h = HL.configure(sc["cam"], max_fts=300, dist=dist)
+    oc = H.ocam(sc["cam"])
+    pose = S.pose_from_xi([0.1, -0.05, 0.02, 0.02, -0.03, 0.01])
+    fr = HL.HFrame(cam_h, sc["ref_img"], pose)
+    assert fr.detect(5.0) == 300
+    px0, lv, _ = fr.features()
+    rng = np.random.default_rng(12)
+    d16 = rng.integers(500, 40000, sc["ref_img"].shape).astype(np.uint16)
+    d16[rng.uniform(size=d16.shape) < 0.4] = 0
+    df = O.depth_convert(d16, 5000.0)
+    tab, nrm = fr.keyframe_lift(d16, 5000.0)
+    px1, _, _ = fr.features()
+    und = O.undistort_points(oc, dist, px0)
+    assert (px1.view(np.uint32) == und.view(np.uint32)).all()                  # mpx rewritten in place, bit-equal to cv2's result
+    n_ok = 0
+    for i in range(len(und)):
+        assert np.allclose(nrm[i], O.feature_normal(oc, und[i]), rtol=0, atol=1e-15)
+        z = O.feature_depth(df, und[i])
+        assert tab[i, 2] == np.float32(z)
+        if z >= 0:
+            want = O.unproject(oc, pose, und[i], z)
+            assert np.allclose(tab[i, 3:6], want, rtol=0, atol=1e-12) and np.allclose(tab[i, 6:9], want, rtol=0, atol=1e-12)
+            n_ok += 1
+    assert 100 < n_ok < 300
+    fr.free()
