@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) pyrdown_strip_kernel(uint8_t* __restrict_
 // instructions per 4 outputs instead of ~100 in the strip kernel, which was co-limited by issue slots (60 % busy at 52 % of
 // DRAM throughput, profiles/r1_pyramid_fast_align2d.md).
 #ifndef DSDTM_PYR_BULK_RPT
-#define DSDTM_PYR_BULK_RPT 8        // output rows per thread
+#define DSDTM_PYR_BULK_RPT 12       // output rows per thread (sweep: profiles/r1_pyramid_fast_align2d.md)
 #endif
 #ifndef DSDTM_PYR_BULK_THREADS
 #define DSDTM_PYR_BULK_THREADS 160  // target CTA size; a tile is xq column groups x (threads / xq) sub-strips
