@@ -58,7 +58,13 @@ __device__ __forceinline__ int hsum_i(int v)
 // v2: one HALF-warp per patch (16 lanes x 4 pixels). The per-patch scalar work (weights, 3x3 update, control) is shared by
 // two patches per warp instruction and the butterflies are 4 levels deep instead of 5: ~35 % fewer instructions per patch
 // than the warp-per-patch v1, which was issue-bound (71 % issue slots busy, profiles/r1_pyramid_fast_align2d.md).
-__global__ void __launch_bounds__(A2D_WARPS * 32) align2d_kernel(const A2dArgs a)
+// v3: a lane owns four CONSECUTIVE rows of one column, so its 4 x (2 x 2) bilinear taps are a 5 x 2 block: 10 byte loads and
+// conversions per iteration instead of 16, one inside/edge branch per iteration instead of four; registers capped at 48
+// (5 CTAs per SM). 0.756 -> 0.632 ms per 1.23 M patches.
+#ifndef DSDTM_A2D_MINB
+#define DSDTM_A2D_MINB 5      // 48 registers: 0.632 ms per 1.23 M patches (1 -> 74 regs 0.809, 6 -> 40 regs 0.633, 8 -> 32 regs 0.739)
+#endif
+__global__ void __launch_bounds__(A2D_WARPS * 32, DSDTM_A2D_MINB) align2d_kernel(const A2dArgs a)
 {
     __shared__ __align__(16) uint8_t s_patch[A2D_WARPS * 2][104];
     const int half = threadIdx.x >> 4, l16 = threadIdx.x & 15;
@@ -77,13 +83,14 @@ __global__ void __launch_bounds__(A2D_WARPS * 32) align2d_kernel(const A2dArgs a
         reinterpret_cast<uint32_t*>(s_patch[half])[q] = __ldg(reinterpret_cast<const uint32_t*>(a.patch10 + (size_t)i * 100) + q);
     __syncwarp();
 
-    // lane owns pixels e = l16 + 16 k (k = 0..3): row = e / 8 = (l16 >> 3) + 2k, col = l16 & 7 of the 8x8 interior
-    const int pc = l16 & 7, pr0 = l16 >> 3;
+    // lane owns column pc = l16 & 7 and the four CONSECUTIVE rows 4 * (l16 >> 3) + k (k = 0..3) of the 8x8 interior: its
+    // bilinear taps are a 5 x 2 block of the current image (10 byte loads per iteration instead of 16)
+    const int pc = l16 & 7, pr0 = (l16 >> 3) * 4;
     float rdx[4], rdy[4], rref[4];
     int i00 = 0, i01 = 0, i02 = 0, i11 = 0, i12 = 0;      // sums of the integer pixel differences (2*dx, 2*dy)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint8_t* it = s_patch[half] + (pr0 + 2 * k + 1) * 10 + 1 + pc;
+        const uint8_t* it = s_patch[half] + (pr0 + k + 1) * 10 + 1 + pc;
         const int ddx = (int)it[1] - (int)it[-1], ddy = (int)it[10] - (int)it[-10];
         rdx[k] = 0.5f * (float)ddx;                        // ref: :336 (exact half-integers)
         rdy[k] = 0.5f * (float)ddy;                        // ref: :337
@@ -135,22 +142,25 @@ __global__ void __launch_bounds__(A2D_WARPS * 32) align2d_kernel(const A2dArgs a
         const unsigned o0 = (unsigned)(v_r + pr0 - 4) * (unsigned)cols + (unsigned)(u_r - 4 + pc);
         // the whole 9x9 window lies inside the level image unless the Q4 edge case is hit (u_r == cols-4 or v_r == rows-4)
         const bool inside = (u_r + 4 < cols) && (v_r + 4 < rows);
+        float pl[5], pr[5];                                 // left / right tap of rows pr0 .. pr0 + 4
+        if (inside) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const unsigned o = o0 + (unsigned)k * (unsigned)cols;
+                pl[k] = (float)__ldg(img + o); pr[k] = (float)__ldg(img + o + 1);
+            }
+        } else {                                            // ref: linear addressing, zeros past the end of the level image (Q4)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const unsigned o = o0 + (unsigned)k * (unsigned)cols;
+                pl[k] = (float)(o < img_bytes ? __ldg(img + o) : 0);
+                pr[k] = (float)(o + 1 < img_bytes ? __ldg(img + o + 1) : 0);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const unsigned o = o0 + (unsigned)(2 * k) * (unsigned)cols;
-            const unsigned o2 = o + (unsigned)cols;
-            float p00, p01, p10, p11;
-            if (inside) {
-                p00 = (float)__ldg(img + o); p01 = (float)__ldg(img + o + 1);
-                p10 = (float)__ldg(img + o2); p11 = (float)__ldg(img + o2 + 1);
-            } else {
-                p00 = (float)(o < img_bytes ? __ldg(img + o) : 0);
-                p01 = (float)(o + 1 < img_bytes ? __ldg(img + o + 1) : 0);
-                p10 = (float)(o2 < img_bytes ? __ldg(img + o2) : 0);
-                p11 = (float)(o2 + 1 < img_bytes ? __ldg(img + o2 + 1) : 0);
-            }
-            const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, p00), __fmul_rn(wTR, p01)), __fmul_rn(wBL, p10)), __fmul_rn(wBR, p11));   // ref: :386
-            const float res = __fadd_rn(__fsub_rn(s, rref[k]), mean_diff);                                                                  // ref: :387
+            const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wTL, pl[k]), __fmul_rn(wTR, pr[k])), __fmul_rn(wBL, pl[k + 1])), __fmul_rn(wBR, pr[k + 1]));   // ref: :386
+            const float res = __fadd_rn(__fsub_rn(s, rref[k]), mean_diff);                                                                              // ref: :387
             j0 = __fsub_rn(j0, __fmul_rn(res, rdx[k]));
             j1 = __fsub_rn(j1, __fmul_rn(res, rdy[k]));
             j2 = __fsub_rn(j2, res);
