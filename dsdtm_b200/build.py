@@ -29,10 +29,14 @@ def nvcc():
     return p
 
 
+def _headers():
+    """Every header a translation unit may include: a change to any of them rebuilds every object (the context struct is
+    shared by all of them; a stale object with an old layout corrupts memory silently)."""
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "dsdtm_gpu.h")]
+
+
 def _deps():
-    d = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "se3_exact.cuh"),
-                                                    os.path.join(ROOT, "include", "dsdtm_gpu.h")]
-    return d
+    return [os.path.join(CSRC, s) for s in SOURCES] + _headers()
 
 
 def stale():
@@ -51,7 +55,7 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         o = os.path.join(LIBDIR, s.replace(".cu", ".o"))
         src = os.path.join(CSRC, s)
-        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(p) for p in (src, _deps()[-1], _deps()[-2])):
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(p) for p in [src] + _headers()):
             cmd = [nvcc()] + NVCC_FLAGS + extra_flags() + ["-c", src, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log.append(r.stderr)

@@ -74,6 +74,89 @@ static int ensure_pinned(dsdtm_ctx* c, size_t bytes)
     return 0;
 }
 
+// Small synchronous calls (one frame, a few hundred features / patches) are dominated by driver overhead when their inputs
+// and outputs are pageable host buffers: every cudaMemcpyAsync on pageable memory is staged and synchronised by the driver
+// (~8 us each, 8-10 per call). The Stager bounces them through a fixed pinned arena instead: inputs are memcpy'd into it and
+// copied from there (truly asynchronous, ~2 us per call), outputs land in it and are handed out after the one stream
+// synchronisation. Calls whose buffers do not fit use the caller's pointers directly (large batches should pass pinned
+// memory from dsdtm_host_alloc anyway).
+static const size_t kStageBytes = 1u << 20;
+struct Stager {
+    dsdtm_ctx* c;
+    size_t off = 0;
+    bool active;
+    struct Out { void* dst; const void* src; size_t bytes; } outs[8];
+    int n_outs = 0;
+    Stager(dsdtm_ctx* ctx, size_t total_bytes) : c(ctx), active(ctx->stage_pin != nullptr && total_bytes + 16 * 16 <= kStageBytes) {}
+    uint8_t* carve(size_t bytes) { uint8_t* p = c->stage_pin + off; off += (bytes + 15) & ~(size_t)15; return p; }
+    const void* in(const void* src, size_t bytes)
+    {
+        if (!active || bytes == 0) return src;
+        uint8_t* p = carve(bytes);
+        std::memcpy(p, src, bytes);
+        return p;
+    }
+    void* out(void* dst, size_t bytes)
+    {
+        if (!active || bytes == 0 || n_outs == 8) return dst;
+        uint8_t* p = carve(bytes);
+        outs[n_outs++] = Out{ dst, p, bytes };
+        return p;
+    }
+    void finish() { for (int i = 0; i < n_outs; ++i) std::memcpy(outs[i].dst, outs[i].src, outs[i].bytes); }   // after the stream sync
+};
+
+// The two calls made once per tracked frame (dsdtm_sparse_align, dsdtm_align2d_batch) go one step further: all inputs are
+// packed into the pinned arena and travel in ONE host-to-device copy into its device mirror, the kernels read and write the
+// mirror directly (the context's staging pointers are swapped for the duration of the launch), and all outputs come back in
+// ONE device-to-host copy. 6 + 2..4 serialised DMA operations per call become 1 + 1.
+struct Arena {
+    dsdtm_ctx* c;
+    size_t in_off = 0, out_off = 0, out_end = 0;
+    bool active;
+    struct Out { void* dst; size_t off; size_t bytes; } outs[8];
+    int n_outs = 0;
+    static size_t pad(size_t b) { return (b + 15) & ~(size_t)15; }
+    Arena(dsdtm_ctx* ctx, size_t in_bytes, size_t out_bytes, int n_in, int n_out)
+        : c(ctx), active(ctx->stage_pin && ctx->stage_dev && in_bytes + out_bytes + 16 * (size_t)(n_in + n_out) + 512 <= kStageBytes)
+    {
+        out_off = out_end = (in_bytes + 16 * (size_t)n_in + 255) & ~(size_t)255;
+    }
+    template <class T> T* in(const T* src, size_t n)                 // copies n elements into the arena, returns the DEVICE address
+    {
+        const size_t o = in_off;
+        std::memcpy(c->stage_pin + o, src, n * sizeof(T));
+        in_off += pad(n * sizeof(T));
+        return reinterpret_cast<T*>(c->stage_dev + o);
+    }
+    template <class T> T* in_fill(size_t n, T** host)                // same, but the caller fills the host side itself
+    {
+        const size_t o = in_off;
+        *host = reinterpret_cast<T*>(c->stage_pin + o);
+        in_off += pad(n * sizeof(T));
+        return reinterpret_cast<T*>(c->stage_dev + o);
+    }
+    template <class T> T* out(T* dst, size_t n)                      // reserves an output range, returns the DEVICE address
+    {
+        const size_t o = out_end;
+        out_end += pad(n * sizeof(T));
+        if (dst) outs[n_outs++] = Out{ dst, o, n * sizeof(T) };
+        return reinterpret_cast<T*>(c->stage_dev + o);
+    }
+    template <class T> const T* host_view(const T* dev) const { return reinterpret_cast<const T*>(c->stage_pin + (reinterpret_cast<const uint8_t*>(dev) - c->stage_dev)); }
+    cudaError_t upload(cudaStream_t s) { return cudaMemcpyAsync(c->stage_dev, c->stage_pin, in_off, cudaMemcpyHostToDevice, s); }
+    cudaError_t download(cudaStream_t s)
+    {
+        return cudaMemcpyAsync(c->stage_pin + out_off, c->stage_dev + out_off, out_end - out_off, cudaMemcpyDeviceToHost, s);
+    }
+    void finish() { for (int i = 0; i < n_outs; ++i) std::memcpy(outs[i].dst, c->stage_pin + outs[i].off, outs[i].bytes); }
+};
+template <class T> struct PtrSwap {     // points a context staging pointer at the arena for the duration of a launch
+    T*& ref; T* saved;
+    PtrSwap(T*& r, T* v) : ref(r), saved(r) { r = v; }
+    ~PtrSwap() { ref = saved; }
+};
+
 static void decode_cells(const dsdtm_ctx* c, const unsigned long long* keys, float seed, dsdtm_corner* out, int n)
 {
     for (int i = 0; i < n; ++i) {
@@ -185,6 +268,8 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
         CK(cudaMemcpy(c->fast_tiles_d, tiles.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     }
     CK(sparse_align_init(c));
+    CK(cudaMallocHost((void**)&c->stage_pin, kStageBytes));
+    CK(cudaMalloc((void**)&c->stage_dev, kStageBytes));
 #undef CK
     return c;
 }
@@ -202,6 +287,8 @@ void dsdtm_destroy(dsdtm_ctx* c)
                      c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->stage_pin) cudaFreeHost(c->stage_pin);
+    if (c->stage_dev) cudaFree(c->stage_dev);
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { if (c->timer.ev0[i]) cudaEventDestroy(c->timer.ev0[i]); if (c->timer.ev1[i]) cudaEventDestroy(c->timer.ev1[i]); }
     for (int i = 0; i < 4; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -409,15 +496,18 @@ int dsdtm_fast_score_map(dsdtm_ctx* c, int slot, int level, int barrier, uint8_t
 // ------------------------------------------------------------------------------------------------ sparse align
 static int stage_pairs(dsdtm_ctx* c, int n_pairs, const int* ref_slots, const int* cur_slots, const dsdtm_ref_feat* feats,
                        int feat_stride, const int* n_feats, const double* ref_centers, const double* poses_in, cudaStream_t s,
-                       int pair0 = 0)
+                       int pair0 = 0, Stager* st = nullptr)
 {
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->ref_slots_d + pair0, ref_slots + pair0, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->cur_slots_d + pair0, cur_slots + pair0, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->feats_d + (size_t)pair0 * feat_stride, feats + (size_t)pair0 * feat_stride,
-                                  (size_t)n_pairs * feat_stride * sizeof(dsdtm_ref_feat), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->n_feats_d + pair0, n_feats + pair0, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->centers_d + 3 * (size_t)pair0, ref_centers + 3 * (size_t)pair0, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->poses_in_d + 7 * (size_t)pair0, poses_in + 7 * (size_t)pair0, (size_t)n_pairs * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+    auto src = [&](const void* p, size_t bytes) { return st ? st->in(p, bytes) : p; };
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->ref_slots_d + pair0, src(ref_slots + pair0, n_pairs * sizeof(int)), n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->cur_slots_d + pair0, src(cur_slots + pair0, n_pairs * sizeof(int)), n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    const size_t fb = (size_t)n_pairs * feat_stride * sizeof(dsdtm_ref_feat);
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->feats_d + (size_t)pair0 * feat_stride, src(feats + (size_t)pair0 * feat_stride, fb), fb, cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->n_feats_d + pair0, src(n_feats + pair0, n_pairs * sizeof(int)), n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->centers_d + 3 * (size_t)pair0, src(ref_centers + 3 * (size_t)pair0, (size_t)n_pairs * 3 * sizeof(double)),
+                                  (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->poses_in_d + 7 * (size_t)pair0, src(poses_in + 7 * (size_t)pair0, (size_t)n_pairs * 7 * sizeof(double)),
+                                  (size_t)n_pairs * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
     return 0;
 }
 
@@ -444,20 +534,65 @@ int dsdtm_sparse_align_batch(dsdtm_ctx* c, int n_pairs, const int* ref_slots, co
     if (!c || !ref_slots || !cur_slots || !feats || !n_feats || !ref_centers || !poses_in || !poses_out || !n_tracked) return DSDTM_E_ARG;
     if (check_pairs(c, n_pairs, ref_slots, cur_slots, feat_stride, n_feats, max_level, min_level, max_iters)) return DSDTM_E_ARG;
     c->batch.staged = false;
-    if (stage_pairs(c, n_pairs, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, c->stream)) return DSDTM_E_CUDA;
     const bool want_log = log != nullptr && log_cap_per_pair > 0;
+    const size_t log_bytes = want_log ? (size_t)n_pairs * (kLogCap * sizeof(dsdtm_iter_log) + sizeof(int)) : 0;
+    {
+        const size_t nfe = (size_t)n_pairs * feat_stride;
+        Arena ar(c, (size_t)n_pairs * (3 * sizeof(int) + 10 * sizeof(double)) + nfe * sizeof(dsdtm_ref_feat),
+                 (size_t)n_pairs * (7 * sizeof(double) + 2 * sizeof(int)) + (size_t)n_pairs * kLogCap * sizeof(dsdtm_iter_log), 6, 4);
+        if (ar.active) {
+            cudaStream_t s = c->stream;
+            PtrSwap<int> p0(c->ref_slots_d, ar.in(ref_slots, n_pairs)), p1(c->cur_slots_d, ar.in(cur_slots, n_pairs)), p2(c->n_feats_d, ar.in(n_feats, n_pairs));
+            PtrSwap<double> p3(c->centers_d, ar.in(ref_centers, (size_t)n_pairs * 3)), p4(c->poses_in_d, ar.in(poses_in, (size_t)n_pairs * 7));
+            PtrSwap<dsdtm_ref_feat> p5(c->feats_d, ar.in(feats, nfe));
+            PtrSwap<double> q0(c->poses_out_d, ar.out(poses_out, (size_t)n_pairs * 7));
+            PtrSwap<int> q1(c->n_tracked_d, ar.out(n_tracked, n_pairs)), q2(c->n_log_d, ar.out((int*)nullptr, n_pairs));
+            // the log travels back only when it is wanted: it is the last range, download() stops before it otherwise
+            const size_t end_no_log = ar.out_end;
+            PtrSwap<dsdtm_iter_log> q3(c->log_d, ar.out((dsdtm_iter_log*)nullptr, (size_t)n_pairs * kLogCap));
+            if (!want_log) ar.out_end = end_no_log;
+            DSDTM_CUDA(c, ar.upload(s));
+            stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
+            DSDTM_CUDA(c, launch_sparse_align(c, n_pairs, feat_stride, max_level, min_level, max_iters, want_log, s));
+            stage_end(c, 1);
+            DSDTM_CUDA(c, ar.download(s));
+            DSDTM_CUDA(c, cudaStreamSynchronize(s));
+            ar.finish();
+            const int* hn = ar.host_view(c->n_log_d);
+            const dsdtm_iter_log* hl = ar.host_view(c->log_d);
+            for (int i = 0; i < n_pairs; ++i) {
+                if (want_log) {
+                    const int n = std::min(std::min(hn[i], kLogCap), log_cap_per_pair);
+                    std::memcpy(log + (size_t)i * log_cap_per_pair, hl + (size_t)i * kLogCap, n * sizeof(dsdtm_iter_log));
+                }
+                if (n_log) n_log[i] = want_log ? hn[i] : 0;
+            }
+            return 0;
+        }
+    }
+    Stager st(c, (size_t)n_pairs * (3 * sizeof(int) + 10 * sizeof(double) + (size_t)feat_stride * sizeof(dsdtm_ref_feat)) +
+                 (size_t)n_pairs * (7 * sizeof(double) + sizeof(int)) + log_bytes);
+    if (stage_pairs(c, n_pairs, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, c->stream, 0, &st)) return DSDTM_E_CUDA;
     stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
     DSDTM_CUDA(c, launch_sparse_align(c, n_pairs, feat_stride, max_level, min_level, max_iters, want_log, c->stream));
     stage_end(c, 1);
-    DSDTM_CUDA(c, cudaMemcpyAsync(poses_out, c->poses_out_d, (size_t)n_pairs * 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    DSDTM_CUDA(c, cudaMemcpyAsync(n_tracked, c->n_tracked_d, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(poses_out, (size_t)n_pairs * 7 * sizeof(double)), c->poses_out_d, (size_t)n_pairs * 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(n_tracked, n_pairs * sizeof(int)), c->n_tracked_d, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (want_log) {
-        if (ensure_pinned(c, (size_t)n_pairs * (kLogCap * sizeof(dsdtm_iter_log) + sizeof(int)))) return DSDTM_E_NOMEM;
-        dsdtm_iter_log* hl = reinterpret_cast<dsdtm_iter_log*>(c->pinned);
-        int* hn = reinterpret_cast<int*>(c->pinned + (size_t)n_pairs * kLogCap * sizeof(dsdtm_iter_log));
-        DSDTM_CUDA(c, cudaMemcpyAsync(hl, c->log_d, (size_t)n_pairs * kLogCap * sizeof(dsdtm_iter_log), cudaMemcpyDeviceToHost, c->stream));
+        dsdtm_iter_log* hl;
+        int* hn;
+        if (st.active) {
+            hl = reinterpret_cast<dsdtm_iter_log*>(st.carve((size_t)n_pairs * kLogCap * sizeof(dsdtm_iter_log)));
+            hn = reinterpret_cast<int*>(st.carve((size_t)n_pairs * sizeof(int)));
+        } else {
+            if (ensure_pinned(c, log_bytes)) return DSDTM_E_NOMEM;
+            hl = reinterpret_cast<dsdtm_iter_log*>(c->pinned);
+            hn = reinterpret_cast<int*>(c->pinned + (size_t)n_pairs * kLogCap * sizeof(dsdtm_iter_log));
+        }
         DSDTM_CUDA(c, cudaMemcpyAsync(hn, c->n_log_d, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        DSDTM_CUDA(c, cudaMemcpyAsync(hl, c->log_d, (size_t)n_pairs * kLogCap * sizeof(dsdtm_iter_log), cudaMemcpyDeviceToHost, c->stream));
         DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+        st.finish();
         for (int i = 0; i < n_pairs; ++i) {
             const int n = std::min(std::min(hn[i], kLogCap), log_cap_per_pair);
             std::memcpy(log + (size_t)i * log_cap_per_pair, hl + (size_t)i * kLogCap, n * sizeof(dsdtm_iter_log));
@@ -465,6 +600,7 @@ int dsdtm_sparse_align_batch(dsdtm_ctx* c, int n_pairs, const int* ref_slots, co
         }
     } else {
         DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+        st.finish();
         if (n_log) for (int i = 0; i < n_pairs; ++i) n_log[i] = 0;
     }
     return 0;
@@ -491,20 +627,42 @@ int dsdtm_align2d_batch(dsdtm_ctx* c, int cur_slot, const int* level, const uint
     if ((size_t)n > cap) return fail(c, DSDTM_E_ARG, "n > max_batch * max_patches");
     for (int i = 0; i < n; ++i) if (level[i] >= c->geo.levels) return fail(c, DSDTM_E_ARG, "patch level out of range");
     c->batch.staged = false;
+    {
+        Arena ar(c, (size_t)n * (2 * sizeof(int) + 100 + 2 * sizeof(double)), (size_t)n * (2 * sizeof(double) + 1), 4, 2);
+        if (ar.active) {
+            cudaStream_t s = c->stream;
+            int* slots_h;
+            PtrSwap<int> p0(c->patch_slot_d, ar.in_fill(n, &slots_h)), p1(c->patch_level_d, ar.in(level, n));
+            for (int i = 0; i < n; ++i) slots_h[i] = cur_slot;
+            PtrSwap<uint8_t> p2(c->patches_d, ar.in(patch10, (size_t)n * 100));
+            PtrSwap<double> p3(c->patch_px_in_d, ar.in(px_io, (size_t)n * 2)), q0(c->patch_px_d, ar.out(px_io, (size_t)n * 2));
+            PtrSwap<uint8_t> q1(c->patch_conv_d, ar.out(converged, n));
+            DSDTM_CUDA(c, ar.upload(s));
+            stage_begin(c, DSDTM_STAGE_ALIGN2D);
+            DSDTM_CUDA(c, launch_align2d(c, n, max_iters, s));
+            stage_end(c, 1);
+            DSDTM_CUDA(c, ar.download(s));
+            DSDTM_CUDA(c, cudaStreamSynchronize(s));
+            ar.finish();
+            return 0;
+        }
+    }
     if (ensure_pinned(c, (size_t)n * sizeof(int))) return DSDTM_E_NOMEM;
     int* slots = reinterpret_cast<int*>(c->pinned);
     for (int i = 0; i < n; ++i) slots[i] = cur_slot;
     cudaStream_t s = c->stream;
+    Stager st(c, (size_t)n * (sizeof(int) + 100 + 4 * sizeof(double) + 1));
     DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_slot_d, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_level_d, level, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->patches_d, patch10, (size_t)n * 100, cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_px_in_d, px_io, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_level_d, st.in(level, (size_t)n * sizeof(int)), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patches_d, st.in(patch10, (size_t)n * 100), (size_t)n * 100, cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->patch_px_in_d, st.in(px_io, (size_t)n * 2 * sizeof(double)), (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
     stage_begin(c, DSDTM_STAGE_ALIGN2D);
     DSDTM_CUDA(c, launch_align2d(c, n, max_iters, s));
     stage_end(c, 1);
-    DSDTM_CUDA(c, cudaMemcpyAsync(px_io, c->patch_px_d, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(converged, c->patch_conv_d, (size_t)n, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(px_io, (size_t)n * 2 * sizeof(double)), c->patch_px_d, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(converged, (size_t)n), c->patch_conv_d, (size_t)n, cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    st.finish();
     return 0;
 }
 
@@ -550,7 +708,8 @@ int dsdtm_feature_align_batch(dsdtm_ctx* c, int cur_slot, const dsdtm_candidate*
             return fail(c, DSDTM_E_ARG, "candidate: slot / level out of range");
     c->batch.staged = false;
     cudaStream_t s = c->stream;
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->cand_d, cands, (size_t)n * sizeof(dsdtm_candidate), cudaMemcpyHostToDevice, s));
+    Stager st(c, (size_t)n * (sizeof(dsdtm_candidate) + 2 * sizeof(double) + sizeof(int) + 1 + (A_out ? 4 * sizeof(double) : 0)));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->cand_d, st.in(cands, (size_t)n * sizeof(dsdtm_candidate)), (size_t)n * sizeof(dsdtm_candidate), cudaMemcpyHostToDevice, s));
     stage_begin(c, DSDTM_STAGE_CAND_PREP);
     DSDTM_CUDA(c, launch_candidate_prep(c, n, cur_slot, max_search_level, s));
     stage_end(c, 1);
@@ -560,11 +719,12 @@ int dsdtm_feature_align_batch(dsdtm_ctx* c, int cur_slot, const dsdtm_candidate*
     stage_begin(c, DSDTM_STAGE_ALIGN2D);
     DSDTM_CUDA(c, launch_align2d(c, n, max_iters, s));
     stage_end(c, 1);
-    DSDTM_CUDA(c, cudaMemcpyAsync(px_out, c->patch_px_d, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(level_out, c->patch_level_d, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(converged, c->patch_conv_d, (size_t)n, cudaMemcpyDeviceToHost, s));
-    if (A_out) DSDTM_CUDA(c, cudaMemcpyAsync(A_out, c->wa_A_d, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(px_out, (size_t)n * 2 * sizeof(double)), c->patch_px_d, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(level_out, (size_t)n * sizeof(int)), c->patch_level_d, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(converged, (size_t)n), c->patch_conv_d, (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (A_out) DSDTM_CUDA(c, cudaMemcpyAsync(st.out(A_out, (size_t)n * 4 * sizeof(double)), c->wa_A_d, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    st.finish();
     for (int i = 0; i < n; ++i) {                                   // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
         const double sc = (double)(1 << level_out[i]);
         px_out[2 * i] *= sc; px_out[2 * i + 1] *= sc;
@@ -602,9 +762,10 @@ int dsdtm_local_map_align_batch(dsdtm_ctx* c, int cur_slot, const double pose_cu
         if (c->lm_pts_cap != pcap0) { size_t z = 0; if (grow(c, &c->lm_reproj_d, &z, c->lm_pts_cap)) return DSDTM_E_NOMEM; }
     }
     cudaStream_t s = c->stream;
-    if (n_kfs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_kfs_d, kfs, (size_t)n_kfs * sizeof(dsdtm_kf_view), cudaMemcpyHostToDevice, s));
-    if (n_obs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_obs_d, obs, (size_t)n_obs * sizeof(dsdtm_obs), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_pts_d, pts, (size_t)n_pts * sizeof(dsdtm_map_point), cudaMemcpyHostToDevice, s));
+    Stager st(c, (size_t)n_kfs * sizeof(dsdtm_kf_view) + (size_t)n_obs * sizeof(dsdtm_obs) + (size_t)n_pts * (sizeof(dsdtm_map_point) + sizeof(dsdtm_reproj)));
+    if (n_kfs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_kfs_d, st.in(kfs, (size_t)n_kfs * sizeof(dsdtm_kf_view)), (size_t)n_kfs * sizeof(dsdtm_kf_view), cudaMemcpyHostToDevice, s));
+    if (n_obs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_obs_d, st.in(obs, (size_t)n_obs * sizeof(dsdtm_obs)), (size_t)n_obs * sizeof(dsdtm_obs), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_pts_d, st.in(pts, (size_t)n_pts * sizeof(dsdtm_map_point)), (size_t)n_pts * sizeof(dsdtm_map_point), cudaMemcpyHostToDevice, s));
     stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
     DSDTM_CUDA(c, launch_local_map(c, pose_cur_c2w, cur_center, n_kfs, n_pts, s));
     stage_end(c, 2);
@@ -622,11 +783,12 @@ int dsdtm_local_map_align_batch(dsdtm_ctx* c, int cur_slot, const double pose_cu
     double* px_h = reinterpret_cast<double*>(c->pinned);
     int* lvl_h = reinterpret_cast<int*>(px_h + 2 * (size_t)n_pts);
     uint8_t* conv_h = reinterpret_cast<uint8_t*>(lvl_h + n_pts);
-    DSDTM_CUDA(c, cudaMemcpyAsync(out, c->lm_reproj_d, (size_t)n_pts * sizeof(dsdtm_reproj), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(out, (size_t)n_pts * sizeof(dsdtm_reproj)), c->lm_reproj_d, (size_t)n_pts * sizeof(dsdtm_reproj), cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaMemcpyAsync(px_h, c->patch_px_d, (size_t)n_pts * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaMemcpyAsync(lvl_h, c->patch_level_d, (size_t)n_pts * sizeof(int), cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaMemcpyAsync(conv_h, c->patch_conv_d, (size_t)n_pts, cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    st.finish();
     for (int i = 0; i < n_pts; ++i) {
         if (lvl_h[i] < 0) continue;                                 // not aligned: px stays the projection, level -1
         const double sc = (double)(1 << lvl_h[i]);                  // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
@@ -700,13 +862,15 @@ int dsdtm_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], 
         c->lift_cap = want;
     }
     cudaStream_t s = c->stream;
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->lift_px_d, px_in, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (initial) DSDTM_CUDA(c, cudaMemcpyAsync(c->lift_initial_d, initial, (size_t)n, cudaMemcpyHostToDevice, s));
+    Stager st(c, (size_t)n * (2 * sizeof(float) + 1 + sizeof(dsdtm_lifted)));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->lift_px_d, st.in(px_in, (size_t)n * 2 * sizeof(float)), (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (initial) DSDTM_CUDA(c, cudaMemcpyAsync(c->lift_initial_d, st.in(initial, (size_t)n), (size_t)n, cudaMemcpyHostToDevice, s));
     stage_begin(c, DSDTM_STAGE_INGEST);
     DSDTM_CUDA(c, launch_keyframe_lift(c, depth_slot, pose_c2w, dist, depth_slot >= 0 ? depth_scale : 1.0f, initial != nullptr, n, s));
     stage_end(c, 1);
-    DSDTM_CUDA(c, cudaMemcpyAsync(out, c->lift_out_d, (size_t)n * sizeof(dsdtm_lifted), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(out, (size_t)n * sizeof(dsdtm_lifted)), c->lift_out_d, (size_t)n * sizeof(dsdtm_lifted), cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    st.finish();
     return 0;
 }
 

@@ -109,6 +109,8 @@ struct dsdtm_ctx {
     // pinned host staging for small synchronous calls
     uint8_t* pinned = nullptr;
     size_t pinned_bytes = 0;
+    uint8_t* stage_pin = nullptr;                // fixed pinned arena for the small synchronous calls (see Stager / Arena in capi.cu)
+    uint8_t* stage_dev = nullptr;                // its device mirror
 
     // staged batch description
     struct {
