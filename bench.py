@@ -268,12 +268,12 @@ def run_ours(args):
                                                                   ALIGN_CFG["max_iters"], P_(po0), C_.byref(ntr0), None, 0, C_.byref(nlog0))),
              ("align2d_call_us", ctx.L.dsdtm_align2d_batch, (ctx.hp, cs0, P_(lv0), P_(pt0), P_(pxio), len(lv0), ALIGN2D_ITERS, P_(conv0))))
     capi_lat = {}
-    for name, fn, args in calls:
+    for name, fn, cargs in calls:
         tsum = 0.0
         for it in range(reps + 5):
             pxio[...] = px0
             t0 = time.perf_counter()
-            rc = fn(*args)
+            rc = fn(*cargs)
             if it >= 5:
                 tsum += time.perf_counter() - t0
             if rc != 0:
