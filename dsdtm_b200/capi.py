@@ -55,6 +55,7 @@ SYMBOLS = [
     "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
     "dsdtm_local_map_align_batch", "dsdtm_depth_upload", "dsdtm_depth_convert_f32", "dsdtm_keyframe_lift",
+    "dsdtm_frame_upload_pyramid_host",
 ]
 
 
@@ -175,6 +176,17 @@ class Context:
         img = np.ascontiguousarray(img, np.uint8)
         assert img.shape == (self.height, self.width)
         self._ck(self.L.dsdtm_frame_upload_pyramid(self.hp, int(slot), _p(img), img.shape[1]))
+
+    def upload_with_levels(self, slot, img):
+        """upload + pyramid + host copies of levels 1.. in one call -> list of level images (level 0 is img itself)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        assert img.shape == (self.height, self.width)
+        offs = self.offs
+        last = self.levels - 1
+        tail = offs[last] + self.ws[last] * self.hs[last] - offs[1]
+        buf = np.empty(tail, np.uint8)
+        self._ck(self.L.dsdtm_frame_upload_pyramid_host(self.hp, int(slot), _p(img), img.shape[1], _p(buf)))
+        return [img] + [buf[offs[l] - offs[1]: offs[l] - offs[1] + self.ws[l] * self.hs[l]].reshape(self.hs[l], self.ws[l]) for l in range(1, self.levels)]
 
     def upload_batch(self, first_slot, imgs):
         imgs = np.ascontiguousarray(imgs, np.uint8)

@@ -416,6 +416,27 @@ int dsdtm_frame_upload_pyramid(dsdtm_ctx* c, int slot, const uint8_t* img, int s
     return 0;
 }
 
+int dsdtm_frame_upload_pyramid_host(dsdtm_ctx* c, int slot, const uint8_t* img, int stride, uint8_t* levels_out)
+{
+    if (!c || !img) return DSDTM_E_ARG;
+    if (check_slot(c, slot)) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    if (stride < g.w[0]) return fail(c, DSDTM_E_ARG, "stride < width");
+    if (g.levels < 2) levels_out = nullptr;
+    cudaStream_t s = c->stream;
+    DSDTM_CUDA(c, cudaMemcpy2DAsync(c->frames_d + (size_t)slot * g.frame_stride, g.w[0], img, stride, g.w[0], g.h[0], cudaMemcpyHostToDevice, s));
+    stage_begin(c, DSDTM_STAGE_PYRAMID);
+    DSDTM_CUDA(c, launch_pyramid(c, slot, 1, s));
+    stage_end(c, g.levels - 1);
+    const size_t tail = levels_out ? (size_t)g.off[g.levels - 1] + (size_t)g.w[g.levels - 1] * g.h[g.levels - 1] - g.off[1] : 0;
+    Stager st(c, tail);
+    if (levels_out)
+        DSDTM_CUDA(c, cudaMemcpyAsync(st.out(levels_out, tail), c->frames_d + (size_t)slot * g.frame_stride + g.off[1], tail, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    st.finish();
+    return 0;
+}
+
 int dsdtm_frames_upload_pyramid(dsdtm_ctx* c, int first_slot, int n, const uint8_t* imgs)
 {
     if (!c || !imgs) return DSDTM_E_ARG;
@@ -762,40 +783,47 @@ int dsdtm_local_map_align_batch(dsdtm_ctx* c, int cur_slot, const double pose_cu
         if (c->lm_pts_cap != pcap0) { size_t z = 0; if (grow(c, &c->lm_reproj_d, &z, c->lm_pts_cap)) return DSDTM_E_NOMEM; }
     }
     cudaStream_t s = c->stream;
-    Stager st(c, (size_t)n_kfs * sizeof(dsdtm_kf_view) + (size_t)n_obs * sizeof(dsdtm_obs) + (size_t)n_pts * (sizeof(dsdtm_map_point) + sizeof(dsdtm_reproj)));
-    if (n_kfs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_kfs_d, st.in(kfs, (size_t)n_kfs * sizeof(dsdtm_kf_view)), (size_t)n_kfs * sizeof(dsdtm_kf_view), cudaMemcpyHostToDevice, s));
-    if (n_obs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_obs_d, st.in(obs, (size_t)n_obs * sizeof(dsdtm_obs)), (size_t)n_obs * sizeof(dsdtm_obs), cudaMemcpyHostToDevice, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_pts_d, st.in(pts, (size_t)n_pts * sizeof(dsdtm_map_point)), (size_t)n_pts * sizeof(dsdtm_map_point), cudaMemcpyHostToDevice, s));
-    stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
-    DSDTM_CUDA(c, launch_local_map(c, pose_cur_c2w, cur_center, n_kfs, n_pts, s));
-    stage_end(c, 2);
-    stage_begin(c, DSDTM_STAGE_CAND_PREP);
-    DSDTM_CUDA(c, launch_candidate_prep(c, n_pts, cur_slot, max_search_level, s));
-    stage_end(c, 1);
-    stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
-    DSDTM_CUDA(c, launch_warp_affine(c, n_pts, c->patches_d, s));
-    stage_end(c, 1);
-    stage_begin(c, DSDTM_STAGE_ALIGN2D);
-    DSDTM_CUDA(c, launch_align2d(c, n_pts, max_iters, s));
-    stage_end(c, 1);
-    const size_t need = (size_t)n_pts * (2 * sizeof(double) + sizeof(int) + 1);
-    if (ensure_pinned(c, need)) return DSDTM_E_NOMEM;
-    double* px_h = reinterpret_cast<double*>(c->pinned);
-    int* lvl_h = reinterpret_cast<int*>(px_h + 2 * (size_t)n_pts);
-    uint8_t* conv_h = reinterpret_cast<uint8_t*>(lvl_h + n_pts);
-    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(out, (size_t)n_pts * sizeof(dsdtm_reproj)), c->lm_reproj_d, (size_t)n_pts * sizeof(dsdtm_reproj), cudaMemcpyDeviceToHost, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(px_h, c->patch_px_d, (size_t)n_pts * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(lvl_h, c->patch_level_d, (size_t)n_pts * sizeof(int), cudaMemcpyDeviceToHost, s));
-    DSDTM_CUDA(c, cudaMemcpyAsync(conv_h, c->patch_conv_d, (size_t)n_pts, cudaMemcpyDeviceToHost, s));
-    DSDTM_CUDA(c, cudaStreamSynchronize(s));
-    st.finish();
-    for (int i = 0; i < n_pts; ++i) {
-        if (lvl_h[i] < 0) continue;                                 // not aligned: px stays the projection, level -1
-        const double sc = (double)(1 << lvl_h[i]);                  // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
-        out[i].px[0] = px_h[2 * i] * sc; out[i].px[1] = px_h[2 * i + 1] * sc;
-        out[i].level = lvl_h[i];
-        if (conv_h[i]) out[i].flags |= DSDTM_LM_CONVERGED;
+    const size_t kb = (size_t)n_kfs * sizeof(dsdtm_kf_view), ob = (size_t)n_obs * sizeof(dsdtm_obs), pb = (size_t)n_pts * sizeof(dsdtm_map_point);
+    const size_t rb = (size_t)n_pts * sizeof(dsdtm_reproj);
+    auto chain = [&]() -> int {
+        stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+        DSDTM_CUDA(c, launch_local_map(c, pose_cur_c2w, cur_center, n_kfs, n_pts, s));
+        stage_end(c, 2);
+        stage_begin(c, DSDTM_STAGE_CAND_PREP);
+        DSDTM_CUDA(c, launch_candidate_prep(c, n_pts, cur_slot, max_search_level, s));
+        stage_end(c, 1);
+        stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
+        DSDTM_CUDA(c, launch_warp_affine(c, n_pts, c->patches_d, s));
+        stage_end(c, 1);
+        stage_begin(c, DSDTM_STAGE_ALIGN2D);
+        DSDTM_CUDA(c, launch_align2d(c, n_pts, max_iters, s));
+        stage_end(c, 1);
+        stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+        DSDTM_CUDA(c, launch_local_map_finalize(c, n_pts, s));
+        stage_end(c, 1);
+        return 0;
+    };
+    Arena ar(c, kb + ob + pb, rb, 3, 1);
+    if (ar.active) {                                                // one copy in, six small kernels, one copy out
+        dsdtm_kf_view kf_dummy{};
+        dsdtm_obs obs_dummy{};
+        PtrSwap<dsdtm_kf_view> p0(c->lm_kfs_d, ar.in(n_kfs ? kfs : &kf_dummy, n_kfs ? (size_t)n_kfs : 1));
+        PtrSwap<dsdtm_obs> p1(c->lm_obs_d, ar.in(n_obs ? obs : &obs_dummy, n_obs ? (size_t)n_obs : 1));
+        PtrSwap<dsdtm_map_point> p2(c->lm_pts_d, ar.in(pts, (size_t)n_pts));
+        PtrSwap<dsdtm_reproj> q0(c->lm_reproj_d, ar.out(out, (size_t)n_pts));
+        DSDTM_CUDA(c, ar.upload(s));
+        if (chain()) return DSDTM_E_CUDA;
+        DSDTM_CUDA(c, ar.download(s));
+        DSDTM_CUDA(c, cudaStreamSynchronize(s));
+        ar.finish();
+        return 0;
     }
+    if (n_kfs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_kfs_d, kfs, kb, cudaMemcpyHostToDevice, s));
+    if (n_obs) DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_obs_d, obs, ob, cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->lm_pts_d, pts, pb, cudaMemcpyHostToDevice, s));
+    if (chain()) return DSDTM_E_CUDA;
+    DSDTM_CUDA(c, cudaMemcpyAsync(out, c->lm_reproj_d, rb, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
     return 0;
 }
 

@@ -107,7 +107,28 @@ __global__ void __launch_bounds__(128) local_map_kernel(const LmArgs a)
     a.out[i] = r;
 }
 
+// After Align2D: fold (refined px * 2^level, level, converged) into the per-point records so that ONE copy returns everything.
+__global__ void __launch_bounds__(128) local_map_finalize_kernel(dsdtm_reproj* __restrict__ out, const double* __restrict__ px,
+                                                                 const int* __restrict__ level, const uint8_t* __restrict__ conv, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int L = level[i];
+    if (L < 0) return;                                              // not aligned: px stays the projection, level -1
+    const double sc = (double)(1 << L);                             // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
+    out[i].px[0] = __dmul_rn(px[2 * i], sc); out[i].px[1] = __dmul_rn(px[2 * i + 1], sc);
+    out[i].level = L;
+    if (conv[i]) out[i].flags |= DSDTM_LM_CONVERGED;
+}
+
 }  // namespace
+
+cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s)
+{
+    local_map_finalize_kernel<<<(n_pts + 127) / 128, 128, 0, s>>>(c->lm_reproj_d, c->patch_px_d, c->patch_level_d, c->patch_conv_d, n_pts);
+    c->launches++;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s)
 {

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -229,10 +230,12 @@ int GpuRuntime::Acquire(GpuSlot* owner)
 
 void GpuRuntime::Release(int slot) { if (slot >= 0 && slot < mMaxFrames) mOwner[slot] = nullptr; }
 
-std::shared_ptr<GpuSlot> GpuRuntime::Upload(const Mat8& img)
+std::shared_ptr<GpuSlot> GpuRuntime::Upload(const Mat8& img, uint8_t* levels_out)
 {
     auto s = std::make_shared<GpuSlot>(img);
-    Resident(s);
+    s->slot = Acquire(s.get());
+    if (dsdtm_frame_upload_pyramid_host(mCtx, s->slot, s->host.data, s->host.step, levels_out) != 0)
+        throw std::runtime_error(std::string("dsdtm_frame_upload_pyramid_host: ") + dsdtm_last_error(mCtx));
     return s;
 }
 
@@ -264,14 +267,18 @@ void Frame::ComputeImagePyramid(const Mat8 image, std::vector<Mat8>& pyr)   // r
 {
     GpuRuntime& rt = GpuRuntime::Instance();
     pyr[0] = image;                                               // level 0 aliases the caller's image
-    mGpu = rt.Upload(image);                                      // H2D + pyrDown chain on the device
-    for (int l = 1; l < (int)pyr.size(); ++l) {
-        int w, h;
-        dsdtm_level_info(rt.ctx(), l, &w, &h, nullptr);
-        pyr[l] = Mat8(h, w, 0);
-        // host copies keep mvImg_Pyr usable by code outside the hot path (viewer, depth lookup); the GPU stages never read them
-        if (dsdtm_frame_download_level(rt.ctx(), mGpu->slot, l, pyr[l].data) != 0)
-            throw std::runtime_error(std::string("dsdtm_frame_download_level: ") + dsdtm_last_error(rt.ctx()));
+    // H2D + pyrDown chain on the device; the host copies of levels 1.. (mvImg_Pyr stays usable by code outside the hot path:
+    // viewer, depth lookup -- the GPU stages never read them) come back in the same synchronisation
+    const int L = (int)pyr.size();
+    std::vector<uint8_t> tail;
+    std::vector<size_t> off(L, 0);
+    std::vector<int> lw(L, 0), lh(L, 0);
+    for (int l = 0; l < L; ++l) dsdtm_level_info(rt.ctx(), l, &lw[l], &lh[l], &off[l]);
+    if (L > 1) tail.resize(off[L - 1] + (size_t)lw[L - 1] * lh[L - 1] - off[1]);
+    mGpu = rt.Upload(image, tail.empty() ? nullptr : tail.data());
+    for (int l = 1; l < L; ++l) {
+        pyr[l] = Mat8(lh[l], lw[l], 0);
+        std::memcpy(pyr[l].data, tail.data() + (off[l] - off[1]), (size_t)lw[l] * lh[l]);
     }
 }
 
@@ -543,6 +550,7 @@ bool Feature_Alignment::Prepare(const MapPoint* mp, const FramePtr frame, const 
 
 void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref: :71-121
 {
+    const auto T0 = std::chrono::steady_clock::now();
     GpuRuntime::Instance().BeginEpoch();
     // The reference walks cells in index order, candidates by found-count, and stops a cell at the first match; a match
     // paints the mask and thereby only changes which LATER candidates are tried, never their alignment result. So: sort
@@ -596,6 +604,7 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
     }
     const int n = (int)pts.size();
     std::vector<dsdtm_reproj> res(n);
+    const auto T1 = std::chrono::steady_clock::now();
     if (n > 0) {
         const int cur_slot = rt.Resident(frame->mGpu);
         // Resolving many keyframes can recycle a slot that an earlier table entry already points to when the pool is smaller
@@ -612,6 +621,7 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
                                         pts.data(), n, mPyr_levels - 3, 10, res.data()) != 0)
             throw std::runtime_error(std::string("dsdtm_local_map_align_batch: ") + dsdtm_last_error(rt.ctx()));
     }
+    const auto T2 = std::chrono::steady_clock::now();
     // replay (ref: :75-82, :91-118)
     int matches = 0;
     for (size_t ci = 0; ci < mCells.size(); ++ci) {
@@ -636,6 +646,11 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
             break;                                               // ReprojectCell returns at the first match
         }
         if (matches >= 200) break;                               // ref: :80 literal
+    }
+    if (getenv("DSDTM_HOST_TIMING")) {
+        const auto T3 = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "SearchLocalPoints: snapshot %.1f us, gpu %.1f us, replay %.1f us (n=%d)\n", us(T0, T1), us(T1, T2), us(T2, T3), n);
     }
     mLastMatches = matches;
 }

@@ -284,7 +284,8 @@ public:
     static GpuRuntime& Instance();
     static void Shutdown();
     dsdtm_ctx* ctx() { return mCtx; }
-    std::shared_ptr<GpuSlot> Upload(const Mat8& level0);          // uploads + builds the pyramid, returns the residency handle
+    // uploads + builds the pyramid, returns the residency handle; levels_out (optional) receives the host copies of levels 1..
+    std::shared_ptr<GpuSlot> Upload(const Mat8& level0, uint8_t* levels_out = nullptr);
     int Resident(const std::shared_ptr<GpuSlot>& s);             // slot index, re-uploading from the host copy if it was evicted
     int levels() const { return mLevels; }
     void Release(int slot);

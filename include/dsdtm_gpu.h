@@ -111,6 +111,10 @@ int         dsdtm_profile_get(dsdtm_ctx* ctx, float ms[DSDTM_STAGE_COUNT], int l
 /* replaces Frame::ComputeImagePyramid (ref: src/Frame.cpp:74-81; include/Frame.h:32): uploads level 0 and builds
  * levels 1..levels-1 with cv::pyrDown semantics into frame slot `slot`. stride = bytes per input row. */
 int dsdtm_frame_upload_pyramid(dsdtm_ctx* ctx, int slot, const uint8_t* img, int stride);
+/* same, and additionally returns the host copies of levels 1..levels-1 that Frame::mvImg_Pyr carries (ref: include/Frame.h
+ * mvImg_Pyr) in the SAME synchronisation: levels_out receives dsdtm_frame_stride() - level-1-offset bytes laid out like the
+ * slot (level l at dsdtm_level_info offset[l] - offset[1], dense rows). levels_out may be NULL. */
+int dsdtm_frame_upload_pyramid_host(dsdtm_ctx* ctx, int slot, const uint8_t* img, int stride, uint8_t* levels_out);
 /* batched: n dense (stride == width) images into slots first_slot .. first_slot+n-1 */
 int dsdtm_frames_upload_pyramid(dsdtm_ctx* ctx, int first_slot, int n, const uint8_t* imgs);
 /* device-resident variant: level 0 of the n slots is already in HBM (e.g. written by a previous upload); rebuild levels */

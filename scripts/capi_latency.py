@@ -44,6 +44,18 @@ def main():
             fn(*args)
             t += time.perf_counter() - t0
         print("%-16s %.1f us per call (pre-marshalled arguments)" % (name, t / 200 * 1e6))
+    # the production configuration of Tracking (ref: src/Tracking.cpp:37: Sprase_ImgAlign(MaxPyraLevels, MinPyraLevels, 8)) with the log
+    log2 = np.zeros(256, capi.ITER_LOG_DT)
+    a2 = (ctx.hp, rs, cs, P(feats), nf, P(cen), P(pose), 5, 0, 8, P(pose_out), C.byref(ntr), P(log2), 256, C.byref(nlog))
+    for _ in range(10):
+        assert L.dsdtm_sparse_align(*a2) == 0
+    ctx.profile(True); ctx.profile_get()
+    t0 = time.perf_counter()
+    for _ in range(100):
+        L.dsdtm_sparse_align(*a2)
+    dt = (time.perf_counter() - t0) / 100 * 1e6
+    st = ctx.profile_get(); ctx.profile(False)
+    print("sparse_align(5,0,8) + log: %.1f us per call, kernel %.1f us, %d GN iterations" % (dt, st["sparse_align"][0] / st["sparse_align"][1] * 1e3, nlog.value))
     ctx.profile(True); ctx.profile_get()
     for _ in range(50):
         for f in calls.values():

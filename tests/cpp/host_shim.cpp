@@ -14,10 +14,19 @@ struct HsKf { KeyFrame* kf; };
 static std::string g_err;
 static std::vector<MapPoint*> g_mps;      // creation-order registry: index = map point id used by the Python side
 
+// Tracking owns ONE Feature_Alignment for its whole life (ref: src/Tracking.cpp:31-37); so does the shim, per camera
+static std::unique_ptr<Feature_Alignment> g_fa;
+static void* g_fa_cam = nullptr;
+static Feature_Alignment& feature_alignment(void* cam)
+{
+    if (!g_fa || g_fa_cam != cam) { g_fa.reset(new Feature_Alignment(*static_cast<CameraPtr*>(cam))); g_fa_cam = cam; }
+    return *g_fa;
+}
+
 extern "C" {
 
 const char* hs_last_error() { return g_err.c_str(); }
-void hs_reset() { GpuRuntime::Shutdown(); Config::Clear(); g_mps.clear(); }
+void hs_reset() { g_fa.reset(); g_fa_cam = nullptr; GpuRuntime::Shutdown(); Config::Clear(); g_mps.clear(); }
 void hs_config_set(const char* k, const char* v) { Config::Set(k, v); }
 int hs_config_load(const char* path) { try { Config::setParameterFile(path); return 0; } catch (std::exception& e) { g_err = e.what(); return -1; } }
 double hs_config_get(const char* k) { return Config::Get<double>(k); }
@@ -172,7 +181,7 @@ void* hs_keyframe_new(void* f)
 int hs_search_local_points(void* cam, void* cur, void* kf, const int* found, int* n_reprojected)
 {
     try {
-        Feature_Alignment fa(*static_cast<CameraPtr*>(cam));
+        Feature_Alignment& fa = feature_alignment(cam);
         KeyFrame* k = static_cast<HsKf*>(kf)->kf;
         FramePtr c = static_cast<HsFrame*>(cur)->f;
         fa.ResetGrid();
@@ -194,7 +203,7 @@ int hs_search_local_points(void* cam, void* cur, void* kf, const int* found, int
 int hs_search_local_points_multi(void* cam, void* cur, void** kfs, int n_kfs, int* n_reprojected)
 {
     try {
-        Feature_Alignment fa(*static_cast<CameraPtr*>(cam));
+        Feature_Alignment& fa = feature_alignment(cam);
         FramePtr c = static_cast<HsFrame*>(cur)->f;
         fa.ResetGrid();
         std::vector<MapPoint*> seen;
