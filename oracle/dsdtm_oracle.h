@@ -10,8 +10,8 @@
  *   - FAST-10 detect/score/nonmax : PINNED against the reference's own Thirdparty/fast
  *     sources compiled into oracle/_ref/libfast_ref.so, and the 167-corner KAT of
  *     Thirdparty/fast/test/test.cpp:20,45,52.
- *   - pyrDown, circle             : PINNED against cv2 4.13 goldens (tests/golden/).
- *   - Shi-Tomasi, grid selection, sparse alignment, WarpAffine, Align2D:
+ *   - pyrDown, circle, undistortPoints : PINNED against cv2 4.13 goldens (tests/golden/).
+ *   - Shi-Tomasi, grid selection, sparse alignment, WarpAffine, Align2D, ReprojectPoint / Get_ClosetObs, depth lookup, UnProject:
  *     PARITY UNPINNED -- the reference ships no golden vector for them and cannot be
  *     built here (needs OpenCV/Eigen/Sophus/Ceres/glog/Boost/Pangolin); restated line by
  *     line from the cited sources, Sophus/Eigen semantics restated from their published
