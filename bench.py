@@ -354,6 +354,7 @@ def run_ours(args):
     if clk["samples"] < 3:       # short region: widen to the e2e timed region as well, and say so
         clk = clocks.summary(tw0, t1 + e2e_wall)
         clk["window"] = "device-resident + e2e timed regions"
+    clk["e2e_region"] = clocks.summary(t1, t1 + e2e_wall)     # the same sampler over the e2e timed region alone
     barrier()
     t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
