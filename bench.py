@@ -143,8 +143,11 @@ def run_ours(args):
     ctx = capi.Context(cam, levels=LEVELS, cell_size=15, max_feats=FEAT_STRIDE, max_patches=N_FEATS, max_frames=2 * B + 2, max_batch=B,
                        device=local)
     t0 = time.time()
+    # scene rendering is CPU work outside the timed regions: share the host cores between the ranks of the box
+    render_procs = max(1, min(args.scenes, (os.cpu_count() or 2) // (2 * world)))
+    scenes = W.render_scenes(args.scenes, cam, seed0=W.BASE_SEED + 1000 * rank, procs=render_procs)
     batch = W.build_batch(ctx, cam, B, n_scenes=args.scenes, n_feats=N_FEATS, feat_stride=FEAT_STRIDE, patches_per_pair=N_FEATS,
-                          seed0=W.BASE_SEED + 1000 * rank)
+                          seed0=W.BASE_SEED + 1000 * rank, scenes=scenes)
     prep_s = time.time() - t0
     ppp = batch["patches_per_pair"]
     ctx.batch_stage(batch["ref_slots"], batch["cur_slots"], batch["feats"], batch["n_feats"], batch["centers"], batch["poses_in"],
