@@ -402,3 +402,41 @@ def test_staged_batch_run_graph_replay_and_e2e(ctx):
     with pytest.raises(capi.DsdtmError):
         ctx.sparse_align_batch(np.arange(20), np.arange(20), np.zeros((20, 4), O.REF_FEAT_DT), np.zeros(20, np.int32),
                                np.zeros((20, 3)), np.tile(S.IDENTITY, (20, 1)), 5, 0, 8)     # > max_batch
+
+
+def test_large_calls_take_the_direct_copy_path_and_agree_with_the_packed_arena_path(built, scenario):
+    """The per-frame entry points pack small calls into a 1 MB pinned arena (one copy each way); calls that do not fit use the
+    caller's buffers directly. Both paths must give identical results: 9000 patches / 8000 map points against the same data in
+    small calls."""
+    from dsdtm_b200 import capi
+    sc = scenario
+    c = capi.Context(sc["cam"], levels=5, cell_size=15, max_feats=320, max_patches=320, max_frames=4, max_batch=32)
+    try:
+        c.upload(0, sc["ref_img"]); c.upload(1, sc["cur_img"])
+        levels, patches, truth, start = H.make_patches(sc["cur_pyr"], 300, 21, max_level=2)
+        px_s, conv_s = c.align2d(1, levels, patches, start, 10)
+        reps = 30
+        px_l, conv_l = c.align2d(1, np.tile(levels, reps), np.tile(patches, (reps, 1)), np.tile(start, (reps, 1)), 10)
+        assert (px_l.reshape(reps, 300, 2) == px_s).all() and (conv_l.reshape(reps, 300) == conv_s).all()
+
+        F = sc["feats"]
+        T_cur = sc["T_cur"]; cen = O.se3_inv(T_cur)[4:]
+        kfs = np.zeros(1, capi.KF_VIEW_DT); kfs[0]["slot"] = 0; kfs[0]["pose_c2w"] = sc["T_ref"]; kfs[0]["center"] = O.se3_inv(sc["T_ref"])[4:]
+        n = len(F)
+        obs = np.zeros(n, capi.OBS_DT); pts = np.zeros(n, capi.MAP_POINT_DT)
+        for i in range(n):
+            obs[i]["kf"] = 0; obs[i]["level"] = F[i]["level"]; obs[i]["px"] = F[i]["px"]; obs[i]["normal"] = F[i]["normal"]; obs[i]["point_w"] = F[i]["point_w"]
+            pts[i]["point_w"] = F[i]["point_w"]; pts[i]["obs_begin"] = i; pts[i]["obs_count"] = 1
+        small = c.local_map_align_batch(1, T_cur, cen, kfs, obs, pts, 2, 10)
+        reps = 8000 // n + 1
+        obs_l = np.tile(obs, reps); pts_l = np.tile(pts, reps)
+        pts_l["obs_begin"] = np.arange(len(pts_l))
+        large = c.local_map_align_batch(1, T_cur, cen, kfs, obs_l, pts_l, 2, 10)
+        for k in ("px_proj", "px", "cell", "flags", "level"):
+            L = large[k].reshape((reps, n) + large[k].shape[1:])
+            for r in range(reps):
+                assert np.array_equal(L[r], small[k], equal_nan=(small[k].dtype.kind == "f")), (k, r)
+        assert (large["obs"] == np.arange(len(pts_l))).all()
+        assert (small["flags"] & capi.LM_CONVERGED).astype(bool).sum() > 200
+    finally:
+        c.close()
