@@ -31,6 +31,10 @@ constexpr int SC_W = FT_W + 2, SC_H = FT_H + 2;   // score tile incl. 1-px ring:
 constexpr int SC_P = 32;                   // score row pitch
 constexpr int WARPS = 4;
 constexpr int QCAP = 64;
+#ifndef DSDTM_FAST_UNROLL_A
+#define DSDTM_FAST_UNROLL_A 1
+#endif
+constexpr int DSDTM_FAST_UNROLL_A_C = DSDTM_FAST_UNROLL_A;
 
 __constant__ int c_ring_dx[16] = { 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1 };
 __constant__ int c_ring_dy[16] = { 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3 };
@@ -94,12 +98,16 @@ __device__ __forceinline__ void score_candidate(WarpSmem& sm, int i, int b, int 
         bright |= (d[k] > b) ? (1u << k) : 0u;
         dark |= (d[k] < -b) ? (1u << k) : 0u;
     }
-    if (has_arc10(bright) || has_arc10(dark)) {
-        const int sb = max_arc_min10(d);
+    const bool isb = has_arc10(bright);
+    if (isb || has_arc10(dark)) {
+        // score = max(S_bright, S_dark) - 1 with S = max over 10-arcs of min over the arc. Two 10-arcs of a 16-ring share at least
+        // 4 pixels, so when a bright 10-arc exists every arc contains a brighter pixel and S_dark < 0 < S_bright (and vice versa):
+        // only the polarity that made the pixel a corner has to be evaluated.
+        if (!isb) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = -d[k];
-        const int sd = max_arc_min10(d);
-        sm.score[r][c] = (uint8_t)(max(sb, sd) - 1);     // in [barrier, 254]
+            for (int k = 0; k < 16; ++k) d[k] = -d[k];
+        }
+        sm.score[r][c] = (uint8_t)(max_arc_min10(d) - 1);     // in [barrier, 254]
     }
 }
 
@@ -147,6 +155,7 @@ __global__ void __launch_bounds__(32 * WARPS) fast_kernel(const FastArgs a)
         const int x = x0 - 1 + c;
         const bool xok = x >= 3 && x < w - 3;                         // ref: fast_10.cpp:41 scan bounds
         const int sc = c + xoff - 1;
+#pragma unroll DSDTM_FAST_UNROLL_A_C
         for (int r = 0; r < SC_H; ++r) {
             const int y = y0 - 1 + r;
             bool cand = false;
