@@ -55,7 +55,7 @@ SYMBOLS = [
     "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
     "dsdtm_local_map_align_batch", "dsdtm_depth_upload", "dsdtm_depth_convert_f32", "dsdtm_keyframe_lift",
-    "dsdtm_frame_upload_pyramid_host",
+    "dsdtm_frame_upload_pyramid_host", "dsdtm_frames_upload_clahe_pyramid",
 ]
 
 
@@ -187,6 +187,17 @@ class Context:
         buf = np.empty(tail, np.uint8)
         self._ck(self.L.dsdtm_frame_upload_pyramid_host(self.hp, int(slot), _p(img), img.shape[1], _p(buf)))
         return [img] + [buf[offs[l] - offs[1]: offs[l] - offs[1] + self.ws[l] * self.hs[l]].reshape(self.hs[l], self.ws[l]) for l in range(1, self.levels)]
+
+    def upload_clahe(self, first_slot, imgs, clip_limit=3.0, tiles=(8, 8), fetch=True):
+        """CLAHE + pyramid for n raw images -> the equalised level-0 images (n, h, w) when fetch"""
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        if imgs.ndim == 2:
+            imgs = imgs[None]
+        assert imgs.shape[1:] == (self.height, self.width)
+        out = np.empty_like(imgs) if fetch else None
+        self._ck(self.L.dsdtm_frames_upload_clahe_pyramid(self.hp, int(first_slot), len(imgs), _p(imgs), C.c_double(clip_limit),
+                                                          int(tiles[0]), int(tiles[1]), _p(out)))
+        return out
 
     def upload_batch(self, first_slot, imgs):
         imgs = np.ascontiguousarray(imgs, np.uint8)

@@ -284,7 +284,7 @@ void dsdtm_destroy(dsdtm_ctx* c)
                      c->feats_d, c->n_feats_d, c->centers_d, c->poses_in_d, c->poses_out_d, c->n_tracked_d, c->log_d, c->n_log_d,
                      c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d, c->cand_d,
                      c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d,
-                     c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d };
+                     c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d, c->clahe_src_d, c->clahe_lut_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->stage_pin) cudaFreeHost(c->stage_pin);
@@ -899,6 +899,34 @@ int dsdtm_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], 
     DSDTM_CUDA(c, cudaMemcpyAsync(st.out(out, (size_t)n * sizeof(dsdtm_lifted)), c->lift_out_d, (size_t)n * sizeof(dsdtm_lifted), cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
     st.finish();
+    return 0;
+}
+
+int dsdtm_frames_upload_clahe_pyramid(dsdtm_ctx* c, int first_slot, int n, const uint8_t* imgs, double clip_limit, int tiles_x, int tiles_y,
+                                      uint8_t* level0_out)
+{
+    if (!c || !imgs || n < 0) return DSDTM_E_ARG;
+    if (n == 0) return 0;
+    if (check_slot(c, first_slot, n)) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    const int w = g.w[0], h = g.h[0];
+    if (tiles_x < 1 || tiles_y < 1 || tiles_x > clahe_max_tiles_x() || w % tiles_x || h % tiles_y)
+        return fail(c, DSDTM_E_ARG, "CLAHE: the image size must be divisible by the tile grid, tiles_x <= 16");
+    if (h / tiles_y < clahe_rows_per_cta()) return fail(c, DSDTM_E_ARG, "CLAHE: tile height must be >= 8");
+    const size_t px = (size_t)w * h, lut = (size_t)tiles_x * tiles_y * 256;
+    if (grow(c, &c->clahe_src_d, &c->clahe_cap, px * n) || grow(c, &c->clahe_lut_d, &c->clahe_lut_cap, lut * n)) return DSDTM_E_NOMEM;
+    cudaStream_t s = c->stream;
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->clahe_src_d, imgs, px * n, cudaMemcpyHostToDevice, s));
+    stage_begin(c, DSDTM_STAGE_INGEST);
+    DSDTM_CUDA(c, launch_clahe(c, first_slot, n, clip_limit, tiles_x, tiles_y, s));
+    stage_end(c, 2);
+    stage_begin(c, DSDTM_STAGE_PYRAMID);
+    DSDTM_CUDA(c, launch_pyramid(c, first_slot, n, s));
+    stage_end(c, g.levels - 1);
+    if (level0_out)
+        DSDTM_CUDA(c, cudaMemcpy2DAsync(level0_out, px, c->frames_d + (size_t)first_slot * g.frame_stride + g.off[0], g.frame_stride, px, n,
+                                        cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
     return 0;
 }
 

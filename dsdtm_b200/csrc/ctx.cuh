@@ -105,6 +105,8 @@ struct dsdtm_ctx {
     float* lift_px_d = nullptr;          size_t lift_cap = 0;
     uint8_t* lift_initial_d = nullptr;
     dsdtm_lifted* lift_out_d = nullptr;
+    uint8_t* clahe_src_d = nullptr;      size_t clahe_cap = 0;       // raw images waiting for CLAHE (frames)
+    uint8_t* clahe_lut_d = nullptr;      size_t clahe_lut_cap = 0;   // per frame tiles * 256 bytes
 
     // pinned host staging for small synchronous calls
     uint8_t* pinned = nullptr;
@@ -157,6 +159,9 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
 cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
 cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s);
 cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s);
+cudaError_t launch_clahe(dsdtm_ctx* c, int first_slot, int n, double clip_limit, int tiles_x, int tiles_y, cudaStream_t s);
+int clahe_max_tiles_x();
+int clahe_rows_per_cta();
 cudaError_t launch_depth_convert(dsdtm_ctx* c, int first_slot, int n, float depth_scale, cudaStream_t s);
 cudaError_t launch_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], const float dist[5], float depth_scale,
                                  bool have_initial, int n, cudaStream_t s);

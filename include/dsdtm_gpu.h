@@ -256,6 +256,15 @@ typedef struct {
 int dsdtm_keyframe_lift(dsdtm_ctx* ctx, int depth_slot, const double pose_c2w[7], const float dist[5], float depth_scale,
                         const float* px_in, const uint8_t* initial, int n, dsdtm_lifted* out);
 
+/* cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply(img) -- the preprocessing the reference's drivers run in front
+ * of the Frame constructor (ref: Test/test_Feature_detection.cpp:85-86, Test/test_Euroc.cpp:64, Test/test_Optimizer.cpp:75,
+ * all with (3.0, 8x8)) -- fused with Frame::ComputeImagePyramid: the n dense raw images are equalised into level 0 of slots
+ * first_slot.. and their pyramids are built. Bit-exact against OpenCV. The image size must be divisible by the tile grid
+ * (OpenCV pads otherwise; not implemented), tiles_x <= 16, tile height >= 8. level0_out (optional, may be NULL): the
+ * equalised images back on the host (n * h * w bytes). */
+int dsdtm_frames_upload_clahe_pyramid(dsdtm_ctx* ctx, int first_slot, int n, const uint8_t* imgs, double clip_limit,
+                                      int tiles_x, int tiles_y, uint8_t* level0_out);
+
 /* ---------------------------------------------------------------- batched front end (sweep / bench) -------- */
 /* One "step" over n_pairs independent frame pairs: [pyramid(cur)] -> sparse align -> Align2D of the pair's patches
  * against its cur frame. Inputs are staged once (H2D), run() only launches kernels on HBM-resident data (CUDA-graph

@@ -338,6 +338,18 @@ def unproject(cam, pose_c2w, px, d):
     return out
 
 
+def clahe(img, clip_limit=3.0, tiles=(8, 8)):
+    """cv::createCLAHE(clip_limit, tiles)->apply(img) for sizes divisible by the tile grid."""
+    a = u8(img)
+    h, w = a.shape
+    assert w % tiles[0] == 0 and h % tiles[1] == 0
+    out = np.empty_like(a)
+    f = lib().orc_clahe
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    f(_p(a), w, h, float(clip_limit), int(tiles[0]), int(tiles[1]), _p(out))
+    return out
+
+
 def pair_batch(cam, levels, ref_pyrs, cur_imgs, feats, n_feats, ref_centers, poses_in, max_level, min_level,
                max_iters, patches10, patch_px, patch_level, align_iters, n_threads):
     """CPU restatement of one bench 'step' over n_pairs pairs (pyramid(cur) + Run + Align2D per patch)."""

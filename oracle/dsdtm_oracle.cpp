@@ -541,6 +541,69 @@ void orc_unproject(const orc_cam* cam, const double pose_c2w[7], const float px[
     se3_act(se3_inv(se3_from(pose_c2w)), p, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// cv::CLAHE::apply, CV_8UC1 (OpenCV imgproc/src/clahe.cpp: CLAHE_CalcLut_Body + CLAHE_Interpolation_Body), sizes divisible
+// by the tile grid. Integer histogram / clip / redistribution, float LUT scale and float bilinear blend of four tile LUTs.
+// ------------------------------------------------------------------------------------------
+void orc_clahe(const uint8_t* src, int w, int h, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst)
+{
+    const int tw = w / tiles_x, th = h / tiles_y, total = tw * th, hist_size = 256;
+    const float lut_scale = static_cast<float>(hist_size - 1) / total;
+    int clip = 0;
+    if (clip_limit > 0.0) {
+        clip = static_cast<int>(clip_limit * total / hist_size);
+        clip = std::max(clip, 1);
+    }
+    std::vector<uint8_t> lut((size_t)tiles_x * tiles_y * hist_size);
+    for (int ty = 0; ty < tiles_y; ++ty)
+        for (int tx = 0; tx < tiles_x; ++tx) {
+            int hist[256] = { 0 };
+            for (int y = 0; y < th; ++y) {
+                const uint8_t* row = src + (size_t)(ty * th + y) * w + tx * tw;
+                for (int x = 0; x < tw; ++x) hist[row[x]]++;
+            }
+            if (clip > 0) {
+                int clipped = 0;
+                for (int i = 0; i < hist_size; ++i)
+                    if (hist[i] > clip) { clipped += hist[i] - clip; hist[i] = clip; }
+                const int batch = clipped / hist_size;
+                int residual = clipped - batch * hist_size;
+                for (int i = 0; i < hist_size; ++i) hist[i] += batch;
+                if (residual != 0) {
+                    const int step = std::max(hist_size / residual, 1);
+                    for (int i = 0; i < hist_size && residual > 0; i += step, residual--) hist[i]++;
+                }
+            }
+            uint8_t* l = &lut[(size_t)(ty * tiles_x + tx) * hist_size];
+            int sum = 0;
+            for (int i = 0; i < hist_size; ++i) {
+                sum += hist[i];
+                const int v = orc_cvround((float)sum * lut_scale);      // saturate_cast<uchar>(float): cvRound + clamp
+                l[i] = (uint8_t)std::min(std::max(v, 0), 255);
+            }
+        }
+    const float inv_tw = 1.0f / tw, inv_th = 1.0f / th;
+    for (int y = 0; y < h; ++y) {
+        const float tyf = y * inv_th - 0.5f;
+        int ty1 = (int)std::floor(tyf), ty2 = ty1 + 1;
+        const float ya = tyf - ty1, ya1 = 1.0f - ya;
+        ty1 = std::max(ty1, 0); ty2 = std::min(ty2, tiles_y - 1);
+        const uint8_t* p1 = &lut[(size_t)ty1 * tiles_x * hist_size];
+        const uint8_t* p2 = &lut[(size_t)ty2 * tiles_x * hist_size];
+        for (int x = 0; x < w; ++x) {
+            const float txf = x * inv_tw - 0.5f;
+            int tx1 = (int)std::floor(txf), tx2 = tx1 + 1;
+            const float xa = txf - tx1, xa1 = 1.0f - xa;
+            tx1 = std::max(tx1, 0); tx2 = std::min(tx2, tiles_x - 1);
+            const int v = src[(size_t)y * w + x];
+            const int i1 = tx1 * hist_size + v, i2 = tx2 * hist_size + v;
+            const float res = (p1[i1] * xa1 + p1[i2] * xa) * ya1 + (p2[i1] * xa1 + p2[i2] * xa) * ya;
+            const int r = orc_cvround(res);
+            dst[(size_t)y * w + x] = (uint8_t)std::min(std::max(r, 0), 255);
+        }
+    }
+}
+
 void orc_ldlt6_solve(const double H[36], const double b[6], double x[6]) { ldlt6_solve(H, b, x); }
 void orc_se3_exp(const double x[6], double pose[7]) { se3_to(se3_exp(x), pose); }
 void orc_se3_mul(const double a[7], const double b[7], double out[7]) { se3_to(se3_mul(se3_from(a), se3_from(b)), out); }

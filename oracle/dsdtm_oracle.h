@@ -10,7 +10,7 @@
  *   - FAST-10 detect/score/nonmax : PINNED against the reference's own Thirdparty/fast
  *     sources compiled into oracle/_ref/libfast_ref.so, and the 167-corner KAT of
  *     Thirdparty/fast/test/test.cpp:20,45,52.
- *   - pyrDown, circle, undistortPoints : PINNED against cv2 4.13 goldens (tests/golden/).
+ *   - pyrDown, circle, undistortPoints, CLAHE : PINNED against cv2 4.13 goldens (tests/golden/).
  *   - Shi-Tomasi, grid selection, sparse alignment, WarpAffine, Align2D, ReprojectPoint / Get_ClosetObs, depth lookup, UnProject:
  *     PARITY UNPINNED -- the reference ships no golden vector for them and cannot be
  *     built here (needs OpenCV/Eigen/Sophus/Ceres/glog/Boost/Pangolin); restated line by
@@ -141,6 +141,12 @@ void orc_depth_convert(const uint16_t* depth, int n, float depth_scale, float* o
 float orc_feature_depth(const float* depth, int w, int h, const float px[2]);
 /* ref: src/Frame.cpp:152-157 UnProject: T_c2w^-1 * Pixel2Camera(px, d) (src/Camera.cpp:173-178 evaluated in float) */
 void orc_unproject(const orc_cam* cam, const double pose_c2w[7], const float px[2], float d, double out[3]);
+
+/* cv::CLAHE::apply on CV_8UC1 (cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y)); ref: Test/test_Feature_detection.cpp:85-86,
+ * Test/test_Euroc.cpp:64, Test/test_Optimizer.cpp:75 use (3.0, 8x8) in front of the Frame constructor). OpenCV's algorithm
+ * (imgproc/src/clahe.cpp, not under /root/reference) restated for image sizes divisible by the tile grid (no border padding).
+ * PINNED against cv2 4.13 goldens (tests/golden/clahe_cv2.npz). */
+void orc_clahe(const uint8_t* src, int w, int h, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst);
 
 /* Batched CPU driver used only for the cpu_baseline / reference bench arm: runs pyramid(cur) +
  * sparse align + align2d for pairs [0,n) with n_threads std::threads. Layout documented in bench.py. */

@@ -17,7 +17,7 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
-    return {k: np.load(os.path.join(d, k + ".npz")) for k in ("test1_fast", "pyrdown_cv2", "circle_cv2", "undistort_cv2")}
+    return {k: np.load(os.path.join(d, k + ".npz")) for k in ("test1_fast", "pyrdown_cv2", "circle_cv2", "undistort_cv2", "clahe_cv2")}
 
 
 @pytest.fixture(scope="session")

@@ -34,3 +34,16 @@ for name, c in CAMS.items():
     out[name + "_wh"] = np.array([c["w"], c["h"]], np.int32)
 np.savez_compressed(os.path.join(HERE, "undistort_cv2.npz"), **out)
 print("undistort_cv2.npz written, cv2", cv2.__version__)
+
+# ---- CLAHE (ref: Test/test_Feature_detection.cpp:85-86, Test/test_Euroc.cpp:64, Test/test_Optimizer.cpp:75: createCLAHE(3.0, 8x8))
+#   clahe_cv2.npz : cv2.createCLAHE(clip, tiles).apply(img) for the deterministic numpy inputs of tests/helpers.py (clahe_input)
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(HERE)))
+import helpers as Hh  # noqa: E402
+
+cl = {}
+for name, h, w, clip, tiles in Hh.CLAHE_CASES:
+    img = Hh.clahe_input(name, h, w)
+    cl[name] = cv2.createCLAHE(clip, tiles).apply(img)
+np.savez_compressed(os.path.join(HERE, "clahe_cv2.npz"), **cl)
+print("clahe_cv2.npz written")

@@ -77,3 +77,27 @@ def make_patches(cur_pyr, n, seed, max_level=0, pert=1.5, margin=8):
         patches[i] = np.clip(np.rint(p), 0, 255).astype(np.uint8).reshape(-1)
         start[i] = truth[i] + rng.uniform(-pert, pert, 2)
     return levels, patches, truth, start
+
+
+CLAHE_CASES = [  # (name, h, w, clip limit, tiles)
+    ("tex320", 240, 320, 3.0, (8, 8)), ("rand160", 120, 160, 3.0, (8, 8)), ("blocks96", 64, 96, 2.0, (4, 4)),
+    ("ramp752", 480, 752, 3.0, (8, 8)), ("flat128", 96, 128, 40.0, (8, 8)), ("tiny", 64, 96, 0.5, (8, 8)),
+]
+
+
+def clahe_input(name, h, w):
+    """Deterministic pure-numpy test images for the CLAHE goldens (no cv2 at test time)."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    if name.startswith("tex"):
+        v = 120 + 60 * np.sin(x * 0.11) * np.cos(y * 0.07) + 30 * np.sin((x + 2 * y) * 0.31) + 15 * np.cos(x * y * 0.001)
+    elif name.startswith("rand"):
+        v = np.random.default_rng(160).integers(0, 256, (h, w)).astype(np.float64)
+    elif name.startswith("blocks"):
+        v = np.zeros((h, w)); v[:, : w // 2] = 17; v[h // 3:, w // 3:] = 200; v[::7, ::5] = 255
+    elif name.startswith("ramp"):
+        v = 90 + 40 * x / w + 10 * np.sin(y * 0.2) + ((x.astype(int) * 7 + y.astype(int) * 13) % 5)
+    elif name.startswith("flat"):
+        v = np.full((h, w), 128.0); v[10:20, 10:40] = 131
+    else:
+        v = (x * 3 + y * 5) % 256
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)

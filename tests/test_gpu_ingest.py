@@ -91,3 +91,29 @@ def test_keyframe_lift_reproduces_cv2_golden(golden, built):
         out = c.keyframe_lift(-1, S.IDENTITY, D, 1.0, src)
         assert (out["px"].view(np.uint32) == dst.view(np.uint32)).all(), name
         c.close()
+
+
+def test_clahe_upload_is_bit_exact_and_feeds_the_pyramid(golden, built):
+    """cv::createCLAHE(clip, tiles)->apply + ComputeImagePyramid as one device call, against the cv2 4.13 golden and the oracle,
+    single and batched (ref: Test/test_Feature_detection.cpp:85-89)."""
+    from dsdtm_b200 import capi
+    g = golden["clahe_cv2"]
+    for name, h, w, clip, tiles in H.CLAHE_CASES:
+        img = H.clahe_input(name, h, w)
+        cam = dict(width=w, height=h, fx=400.0, fy=400.0, cx=w / 2.0, cy=h / 2.0, f=400.0)
+        levels = 3 if min(h, w) >= 96 else 2
+        c = capi.Context(cam, levels=levels, cell_size=15, max_feats=64, max_patches=8, max_frames=4, max_batch=1)
+        try:
+            imgs = np.stack([img, img[::-1].copy(), np.roll(img, 5, axis=1)])
+            out = c.upload_clahe(1, imgs, clip, tiles)
+            assert (out[0] == g[name]).all(), name                                  # cv2 itself
+            for k in range(3):
+                want = O.clahe(imgs[k], clip, tiles)
+                assert (out[k] == want).all(), (name, k)
+                packed, offs, ws, hs = O.pyramid(want, levels)
+                for l in range(levels):
+                    assert (c.download_level(1 + k, l) == O.pyr_level(packed, offs, ws, hs, l)).all(), (name, k, l)
+            with pytest.raises(capi.DsdtmError):
+                c.upload_clahe(0, img, clip, (7, 8) if w % 7 else (9, 8))         # not divisible: refused, not padded
+        finally:
+            c.close()

@@ -201,3 +201,13 @@ def test_depth_lookup_and_convert_restatements():
     d[5, 5] = 1.25
     assert O.feature_depth(d, (5.49, 4.51)) == 1.25
     assert O.feature_depth(d, (0.0, 0.0)) == -1.0    # neighbours outside the image count as 0
+
+
+def test_clahe_matches_cv2_golden(golden):
+    """cv::createCLAHE(clip, tiles)->apply (the preprocessing of the reference's test drivers, Test/test_Feature_detection.cpp:85-86)
+    against cv2 4.13 on deterministic numpy inputs (tests/golden/make_golden_ingest.py)."""
+    import helpers as H
+    g = golden["clahe_cv2"]
+    for name, h, w, clip, tiles in H.CLAHE_CASES:
+        img = H.clahe_input(name, h, w)
+        assert (O.clahe(img, clip, tiles) == g[name]).all(), name
