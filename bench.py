@@ -283,6 +283,30 @@ def run_ours(args):
                 raise RuntimeError("%s failed: %s" % (name, ctx.L.dsdtm_last_error(ctx.hp)))
         capi_lat[name] = tsum / reps * 1e6
     capi_lat["sparse_plus_refine_call_us"] = capi_lat["sparse_align_call_us"] + capi_lat["align2d_call_us"]
+    # the whole front end of one frame as ONE call with one synchronisation (dsdtm_track_frame): upload + pyramid + sparse alignment +
+    # device-side pose composition + reprojection / closest observation / affine warp / Align2D of the key frame's 300 map points
+    T_ref0 = np.ascontiguousarray(batch["scenes"][0]["T_ref"], np.float64)
+    kfs0 = np.zeros(1, capi.KF_VIEW_DT); kfs0[0]["slot"] = rs0; kfs0[0]["pose_c2w"] = T_ref0; kfs0[0]["center"] = cen0
+    obs0 = np.zeros(nf0, capi.OBS_DT); pts0 = np.zeros(nf0, capi.MAP_POINT_DT)
+    obs0["kf"] = 0; obs0["level"] = f0["level"]; obs0["px"] = f0["px"]; obs0["normal"] = f0["normal"]; obs0["point_w"] = f0["point_w"]
+    pts0["point_w"] = f0["point_w"]; pts0["obs_begin"] = np.arange(nf0); pts0["obs_count"] = 1
+    ti = capi.TrackIn(); to = capi.TrackOut(); rep0 = np.zeros(nf0, capi.REPROJ_DT)
+    ti.ref_slot, ti.cur_slot, ti.img, ti.stride = rs0, cs0, img0.ctypes.data, img0.shape[1]
+    ti.feats, ti.n_feats = f0.ctypes.data, nf0
+    ti.ref_center[:] = [float(v) for v in cen0]; ti.pose_ref_c2w[:] = [float(v) for v in T_ref0]; ti.pose_c2r_in[:] = [float(v) for v in pose0]
+    ti.max_level, ti.min_level, ti.max_iters = ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"]
+    ti.kfs, ti.n_kfs, ti.obs, ti.n_obs, ti.pts, ti.n_pts = kfs0.ctypes.data, 1, obs0.ctypes.data, nf0, pts0.ctypes.data, nf0
+    ti.max_search_level, ti.align_iters = LEVELS - 3, ALIGN2D_ITERS
+    tsum = 0.0
+    for it in range(reps + 5):
+        t0 = time.perf_counter()
+        rc = ctx.L.dsdtm_track_frame(ctx.hp, C_.byref(ti), C_.byref(to), P_(rep0))
+        if it >= 5:
+            tsum += time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError("dsdtm_track_frame failed: %s" % ctx.L.dsdtm_last_error(ctx.hp))
+    capi_lat["track_frame_call_us"] = tsum / reps * 1e6
+    capi_lat["track_frame_matches"] = int(((rep0["flags"] & capi.LM_CONVERGED) != 0).sum())
     capi_lat["note"] = ("one frame through the three synchronous single-pair C-ABI calls with pageable host buffers, host wall clock "
                         "(H2D of inputs, kernel, D2H of results and the stream synchronisation inside each call)")
     latency["capi"] = capi_lat

@@ -34,6 +34,19 @@ class Cam(C.Structure):
                 ("cx", C.c_float), ("cy", C.c_float), ("f", C.c_float)]
 
 
+class TrackIn(C.Structure):
+    _fields_ = [("ref_slot", C.c_int32), ("cur_slot", C.c_int32), ("img", C.c_void_p), ("stride", C.c_int32),
+                ("feats", C.c_void_p), ("n_feats", C.c_int32), ("ref_center", C.c_double * 3), ("pose_ref_c2w", C.c_double * 7),
+                ("pose_c2r_in", C.c_double * 7), ("max_level", C.c_int32), ("min_level", C.c_int32), ("max_iters", C.c_int32),
+                ("kfs", C.c_void_p), ("n_kfs", C.c_int32), ("obs", C.c_void_p), ("n_obs", C.c_int32), ("pts", C.c_void_p), ("n_pts", C.c_int32),
+                ("max_search_level", C.c_int32), ("align_iters", C.c_int32)]
+
+
+class TrackOut(C.Structure):
+    _fields_ = [("pose_c2r", C.c_double * 7), ("pose_cur_c2w", C.c_double * 7), ("cur_center", C.c_double * 3), ("n_tracked", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class Params(C.Structure):
     _fields_ = [("levels", C.c_int), ("cell_size", C.c_int), ("max_feats", C.c_int), ("max_patches", C.c_int),
                 ("max_frames", C.c_int), ("max_batch", C.c_int)]
@@ -55,7 +68,7 @@ SYMBOLS = [
     "dsdtm_align2d_batch", "dsdtm_warp_affine_batch", "dsdtm_batch_stage", "dsdtm_batch_run", "dsdtm_batch_fetch",
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
     "dsdtm_local_map_align_batch", "dsdtm_depth_upload", "dsdtm_depth_convert_f32", "dsdtm_keyframe_lift",
-    "dsdtm_frame_upload_pyramid_host", "dsdtm_frames_upload_clahe_pyramid",
+    "dsdtm_frame_upload_pyramid_host", "dsdtm_frames_upload_clahe_pyramid", "dsdtm_track_frame",
 ]
 
 
@@ -305,6 +318,27 @@ class Context:
         self._ck(self.L.dsdtm_keyframe_lift(self.hp, int(depth_slot), _p(np.ascontiguousarray(pose_c2w, np.float64)),
                                             _p(np.ascontiguousarray(dist, np.float32)), C.c_float(depth_scale), _p(px), _p(ini), len(px), _p(out)))
         return out
+
+    def track_frame(self, ref_slot, cur_slot, img, feats, ref_center, pose_ref_c2w, pose_c2r_in, sa_cfg, kfs, obs, pts, max_search_level,
+                    align_iters=10):
+        """dsdtm_track_frame: upload + pyramid + sparse align + pose composition + local-map alignment in one call.
+        Returns (TrackOut fields as dict, REPROJ_DT array)."""
+        img = np.ascontiguousarray(img, np.uint8); feats = np.ascontiguousarray(feats, REF_FEAT_DT)
+        kfs = np.ascontiguousarray(kfs, KF_VIEW_DT); obs = np.ascontiguousarray(obs, OBS_DT); pts = np.ascontiguousarray(pts, MAP_POINT_DT)
+        ti = TrackIn()
+        ti.ref_slot, ti.cur_slot, ti.img, ti.stride = int(ref_slot), int(cur_slot), img.ctypes.data, img.shape[1]
+        ti.feats, ti.n_feats = feats.ctypes.data, len(feats)
+        ti.ref_center[:] = [float(v) for v in ref_center]; ti.pose_ref_c2w[:] = [float(v) for v in pose_ref_c2w]
+        ti.pose_c2r_in[:] = [float(v) for v in pose_c2r_in]
+        ti.max_level, ti.min_level, ti.max_iters = (int(v) for v in sa_cfg)
+        ti.kfs, ti.n_kfs, ti.obs, ti.n_obs, ti.pts, ti.n_pts = kfs.ctypes.data, len(kfs), obs.ctypes.data, len(obs), pts.ctypes.data, len(pts)
+        ti.max_search_level, ti.align_iters = int(max_search_level), int(align_iters)
+        to = TrackOut()
+        rep = np.zeros(len(pts), REPROJ_DT)
+        self._keep = (img, feats, kfs, obs, pts)
+        self._ck(self.L.dsdtm_track_frame(self.hp, C.byref(ti), C.byref(to), _p(rep)))
+        return dict(pose_c2r=np.array(to.pose_c2r[:]), pose_cur_c2w=np.array(to.pose_cur_c2w[:]), cur_center=np.array(to.cur_center[:]),
+                    n_tracked=int(to.n_tracked)), rep
 
     # ---- batched front end
     def batch_stage(self, ref_slots, cur_slots, feats, n_feats, ref_centers, poses_in, max_level, min_level, max_iters,

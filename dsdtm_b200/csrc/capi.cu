@@ -827,6 +827,91 @@ int dsdtm_local_map_align_batch(dsdtm_ctx* c, int cur_slot, const double pose_cu
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ one call per frame
+int dsdtm_track_frame(dsdtm_ctx* c, const dsdtm_track_in* in, dsdtm_track_out* out, dsdtm_reproj* reproj)
+{
+    if (!c || !in || !out || !in->img || !in->feats) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    const int nf = in->n_feats, n_kfs = in->n_kfs, n_obs = in->n_obs, n_pts = in->n_pts;
+    if (nf < 1 || nf > c->prm.max_feats) return fail(c, DSDTM_E_ARG, "n_feats out of range (max_feats)");
+    if (check_pairs(c, 1, &in->ref_slot, &in->cur_slot, nf, &nf, in->max_level, in->min_level, in->max_iters)) return DSDTM_E_ARG;
+    if (in->stride < g.w[0]) return fail(c, DSDTM_E_ARG, "stride < width");
+    if (n_kfs < 0 || n_obs < 0 || n_pts < 0 || in->align_iters < 0 || in->max_search_level < 0 || in->max_search_level >= g.levels)
+        return fail(c, DSDTM_E_ARG, "bad local-map arguments");
+    if ((n_kfs && !in->kfs) || (n_obs && !in->obs) || (n_pts && (!in->pts || !reproj))) return fail(c, DSDTM_E_ARG, "null table");
+    if ((size_t)n_pts > (size_t)c->prm.max_batch * std::max(c->prm.max_patches, 1)) return fail(c, DSDTM_E_ARG, "n_pts > max_batch * max_patches");
+    for (int k = 0; k < n_kfs; ++k)
+        if (in->kfs[k].slot < 0 || in->kfs[k].slot >= c->prm.max_frames) return fail(c, DSDTM_E_ARG, "keyframe: slot out of range");
+    for (int j = 0; j < n_obs; ++j)
+        if (in->obs[j].kf < 0 || in->obs[j].kf >= n_kfs || in->obs[j].level < 0 || in->obs[j].level >= g.levels)
+            return fail(c, DSDTM_E_ARG, "observation: keyframe index / level out of range");
+    for (int i = 0; i < n_pts; ++i)
+        if (in->pts[i].obs_count < 0 || in->pts[i].obs_begin < 0 || (long long)in->pts[i].obs_begin + in->pts[i].obs_count > n_obs)
+            return fail(c, DSDTM_E_ARG, "map point: observation range out of bounds");
+    const size_t kb = (size_t)std::max(n_kfs, 1) * sizeof(dsdtm_kf_view), ob = (size_t)std::max(n_obs, 1) * sizeof(dsdtm_obs);
+    const size_t pb = (size_t)std::max(n_pts, 1) * sizeof(dsdtm_map_point), rb = (size_t)std::max(n_pts, 1) * sizeof(dsdtm_reproj);
+    Arena ar(c, 3 * sizeof(int) + 10 * sizeof(double) + (size_t)nf * sizeof(dsdtm_ref_feat) + kb + ob + pb,
+             (7 + 10) * sizeof(double) + 2 * sizeof(int) + rb, 9, 5);
+    if (!ar.active) return fail(c, DSDTM_E_ARG, "dsdtm_track_frame: inputs exceed the 1 MB staging arena (use the separate calls)");
+    {   // the per-keyframe pose scratch follows the capacity of the keyframe table (before any pointer is swapped)
+        const size_t kcap0 = c->lm_kfs_cap;
+        if (grow(c, &c->lm_kfs_d, &c->lm_kfs_cap, (size_t)std::max(n_kfs, 1))) return DSDTM_E_NOMEM;
+        if (c->lm_kfs_cap != kcap0) { size_t z = 0; if (grow(c, &c->lm_pose_d, &z, c->lm_kfs_cap * 7)) return DSDTM_E_NOMEM; }
+    }
+    c->batch.staged = false;
+    cudaStream_t s = c->stream;
+    dsdtm_kf_view kf_dummy{};
+    dsdtm_obs obs_dummy{};
+    dsdtm_map_point pt_dummy{};
+    PtrSwap<int> p0(c->ref_slots_d, ar.in(&in->ref_slot, 1)), p1(c->cur_slots_d, ar.in(&in->cur_slot, 1)), p2(c->n_feats_d, ar.in(&nf, 1));
+    PtrSwap<double> p3(c->centers_d, ar.in(in->ref_center, 3)), p4(c->poses_in_d, ar.in(in->pose_c2r_in, 7));
+    PtrSwap<dsdtm_ref_feat> p5(c->feats_d, ar.in(in->feats, (size_t)nf));
+    PtrSwap<dsdtm_kf_view> p6(c->lm_kfs_d, ar.in(n_kfs ? in->kfs : &kf_dummy, (size_t)std::max(n_kfs, 1)));
+    PtrSwap<dsdtm_obs> p7(c->lm_obs_d, ar.in(n_obs ? in->obs : &obs_dummy, (size_t)std::max(n_obs, 1)));
+    PtrSwap<dsdtm_map_point> p8(c->lm_pts_d, ar.in(n_pts ? in->pts : &pt_dummy, (size_t)std::max(n_pts, 1)));
+    double* pose_c2r_d = ar.out(out->pose_c2r, 7);
+    double* pose10_d = ar.out((double*)nullptr, 10);
+    PtrSwap<double> q0(c->poses_out_d, pose_c2r_d);
+    PtrSwap<int> q1(c->n_tracked_d, ar.out(&out->n_tracked, 1)), q2(c->n_log_d, ar.out((int*)nullptr, 1));
+    PtrSwap<dsdtm_reproj> q3(c->lm_reproj_d, ar.out(n_pts ? reproj : (dsdtm_reproj*)nullptr, (size_t)std::max(n_pts, 1)));
+    DSDTM_CUDA(c, cudaMemcpy2DAsync(c->frames_d + (size_t)in->cur_slot * g.frame_stride, g.w[0], in->img, in->stride, g.w[0], g.h[0], cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, ar.upload(s));
+    stage_begin(c, DSDTM_STAGE_PYRAMID);
+    DSDTM_CUDA(c, launch_pyramid(c, in->cur_slot, 1, s));
+    stage_end(c, g.levels - 1);
+    stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
+    DSDTM_CUDA(c, launch_sparse_align(c, 1, nf, in->max_level, in->min_level, in->max_iters, false, s));
+    stage_end(c, 1);
+    stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+    DSDTM_CUDA(c, launch_compose_pose(c, pose_c2r_d, in->pose_ref_c2w, pose10_d, s));
+    stage_end(c, 1);
+    if (n_pts > 0) {
+        stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+        DSDTM_CUDA(c, launch_local_map(c, nullptr, nullptr, n_kfs, n_pts, s, pose10_d));
+        stage_end(c, 2);
+        stage_begin(c, DSDTM_STAGE_CAND_PREP);
+        DSDTM_CUDA(c, launch_candidate_prep(c, n_pts, in->cur_slot, in->max_search_level, s));
+        stage_end(c, 1);
+        stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
+        DSDTM_CUDA(c, launch_warp_affine(c, n_pts, c->patches_d, s));
+        stage_end(c, 1);
+        stage_begin(c, DSDTM_STAGE_ALIGN2D);
+        DSDTM_CUDA(c, launch_align2d(c, n_pts, in->align_iters, s));
+        stage_end(c, 1);
+        stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+        DSDTM_CUDA(c, launch_local_map_finalize(c, n_pts, s));
+        stage_end(c, 1);
+    }
+    DSDTM_CUDA(c, ar.download(s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    ar.finish();
+    const double* p10 = ar.host_view(pose10_d);
+    for (int k = 0; k < 7; ++k) out->pose_cur_c2w[k] = p10[k];
+    for (int k = 0; k < 3; ++k) out->cur_center[k] = p10[7 + k];
+    out->reserved = 0;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ (f-3 / f-4) ingest
 static int ensure_depth_pool(dsdtm_ctx* c)
 {

@@ -166,7 +166,9 @@ cudaError_t launch_depth_convert(dsdtm_ctx* c, int first_slot, int n, float dept
 cudaError_t launch_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], const float dist[5], float depth_scale,
                                  bool have_initial, int n, cudaStream_t s);
 cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s);
-cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s);
+cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s,
+                             const double* pose_dev = nullptr);
+cudaError_t launch_compose_pose(dsdtm_ctx* c, const double* t_c2r_d, const double pose_ref_c2w[7], double* out10_d, cudaStream_t s);
 int sparse_align_smem_bytes(int nf_pad);
 size_t sparse_align_ws_doubles(int max_feats);
 cudaError_t sparse_align_init(dsdtm_ctx* c);

@@ -24,6 +24,7 @@ struct LmArgs {
     const dsdtm_obs* obs;
     const dsdtm_map_point* pts; int n_pts;
     double pose_cur[7]; double cur_center[3];
+    const double* pose_dev;     // optional: {pose_c2w[7], centre[3]} produced on the device (dsdtm_track_frame); overrides the two above
     float fx, fy, cx, cy;
     int width, height, cell_size, grid_cols;
     double* kf_pose;            // n_kfs x 7
@@ -35,9 +36,11 @@ __global__ void __launch_bounds__(64) kf_pose_kernel(const LmArgs a)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.n_kfs) return;
-    double inv[7], T[7];
+    double inv[7], T[7], pc[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) pc[j] = a.pose_dev ? a.pose_dev[j] : a.pose_cur[j];
     se3_inv_exact(a.kfs[k].pose_c2w, inv);
-    se3_mul_exact(a.pose_cur, inv, T);
+    se3_mul_exact(pc, inv, T);
     double* o = a.kf_pose + 7 * k;
 #pragma unroll
     for (int j = 0; j < 7; ++j) o[j] = T[j];
@@ -57,9 +60,14 @@ __global__ void __launch_bounds__(128) local_map_kernel(const LmArgs a)
     const dsdtm_map_point mp = a.pts[i];
     const double P0 = mp.point_w[0], P1 = mp.point_w[1], P2 = mp.point_w[2];
     // Frame::World2Pixel (ref: src/Frame.cpp:318-323): Camera2Pixel(T_c2w * P) = fx * X / Z + cx
+    double pc[7], cc[3];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) pc[j] = a.pose_dev ? a.pose_dev[j] : a.pose_cur[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) cc[j] = a.pose_dev ? a.pose_dev[7 + j] : a.cur_center[j];
     double q0, q1, q2;
-    qrot_exact(a.pose_cur, P0, P1, P2, q0, q1, q2);
-    q0 = __dadd_rn(q0, a.pose_cur[4]); q1 = __dadd_rn(q1, a.pose_cur[5]); q2 = __dadd_rn(q2, a.pose_cur[6]);
+    qrot_exact(pc, P0, P1, P2, q0, q1, q2);
+    q0 = __dadd_rn(q0, pc[4]); q1 = __dadd_rn(q1, pc[5]); q2 = __dadd_rn(q2, pc[6]);
     const double u = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fx, q0), q2), (double)a.cx);
     const double v = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fy, q1), q2), (double)a.cy);
     int flags = 0, cell = -1, best = -1;
@@ -68,7 +76,7 @@ __global__ void __launch_bounds__(128) local_map_kernel(const LmArgs a)
         cell = (int)__ddiv_rn(v, (double)a.cell_size) * a.grid_cols + (int)__ddiv_rn(u, (double)a.cell_size);   // ref: :60-61
     }
     // MapPoint::Get_ClosetObs: direction point -> current camera, then the observation with the largest cosine (strict >)
-    double f0 = __dsub_rn(a.cur_center[0], P0), f1 = __dsub_rn(a.cur_center[1], P1), f2 = __dsub_rn(a.cur_center[2], P2);
+    double f0 = __dsub_rn(cc[0], P0), f1 = __dsub_rn(cc[1], P1), f2 = __dsub_rn(cc[2], P2);
     double n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1)), __dmul_rn(f2, f2)));
     f0 = __ddiv_rn(f0, n); f1 = __ddiv_rn(f1, n); f2 = __ddiv_rn(f2, n);
     double best_cos = 0.0;
@@ -107,6 +115,22 @@ __global__ void __launch_bounds__(128) local_map_kernel(const LmArgs a)
     a.out[i] = r;
 }
 
+// Sprase_ImgAlign::Run's last line on the device (ref: src/Sprase_ImageAlign.cpp:57 cur.Set_Pose(T_c2r * ref.Get_Pose()); src/Frame.cpp:167-174
+// Set_Pose: mOw = inverse().translation()): out = {pose_c2w[7], centre[3]} for the local-map kernels of the same call.
+struct ComposeArgs { const double* t_c2r; double pose_ref[7]; double* out; };
+__global__ void compose_pose_kernel(const ComposeArgs a)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double T[7], Tc[7], inv[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) T[j] = a.t_c2r[j];
+    se3_mul_exact(T, a.pose_ref, Tc);
+    se3_inv_exact(Tc, inv);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) a.out[j] = Tc[j];
+    a.out[7] = inv[4]; a.out[8] = inv[5]; a.out[9] = inv[6];
+}
+
 // After Align2D: fold (refined px * 2^level, level, converged) into the per-point records so that ONE copy returns everything.
 __global__ void __launch_bounds__(128) local_map_finalize_kernel(dsdtm_reproj* __restrict__ out, const double* __restrict__ px,
                                                                  const int* __restrict__ level, const uint8_t* __restrict__ conv, int n)
@@ -130,12 +154,24 @@ cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s)
+cudaError_t launch_compose_pose(dsdtm_ctx* c, const double* t_c2r_d, const double pose_ref_c2w[7], double* out10_d, cudaStream_t s)
+{
+    ComposeArgs a;
+    a.t_c2r = t_c2r_d; a.out = out10_d;
+    for (int k = 0; k < 7; ++k) a.pose_ref[k] = pose_ref_c2w[k];
+    compose_pose_kernel<<<1, 32, 0, s>>>(a);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s,
+                             const double* pose_dev)
 {
     LmArgs a;
+    a.pose_dev = pose_dev;
     a.kfs = c->lm_kfs_d; a.n_kfs = n_kfs; a.obs = c->lm_obs_d; a.pts = c->lm_pts_d; a.n_pts = n_pts;
-    for (int k = 0; k < 7; ++k) a.pose_cur[k] = pose_cur[k];
-    for (int k = 0; k < 3; ++k) a.cur_center[k] = cur_center[k];
+    for (int k = 0; k < 7; ++k) a.pose_cur[k] = pose_cur ? pose_cur[k] : 0.0;
+    for (int k = 0; k < 3; ++k) a.cur_center[k] = cur_center ? cur_center[k] : 0.0;
     a.fx = c->cam.fx; a.fy = c->cam.fy; a.cx = c->cam.cx; a.cy = c->cam.cy;
     a.width = c->cam.width; a.height = c->cam.height; a.cell_size = c->prm.cell_size; a.grid_cols = c->grid_cols;
     a.kf_pose = c->lm_pose_d; a.cand = c->cand_d; a.out = c->lm_reproj_d;

@@ -265,6 +265,36 @@ int dsdtm_keyframe_lift(dsdtm_ctx* ctx, int depth_slot, const double pose_c2w[7]
 int dsdtm_frames_upload_clahe_pyramid(dsdtm_ctx* ctx, int first_slot, int n, const uint8_t* imgs, double clip_limit,
                                       int tiles_x, int tiles_y, uint8_t* level0_out);
 
+/* ---------------------------------------------------------------- one call per tracked frame ---------------- */
+/* Tracking::Track_RGBDCam's front end for one frame (ref: src/Tracking.cpp:57,199-224) as ONE call with ONE synchronisation:
+ *   new Frame(img)                        -> upload + pyramid into cur_slot                     (ref: src/Frame.cpp:48-81)
+ *   Sprase_ImgAlign::Run(cur, ref)        -> T_c2r from pose_c2r_in; cur pose = T_c2r * T_ref   (ref: src/Sprase_ImageAlign.cpp:29-60)
+ *   UpdateLocalMap + SearchLocalPoints    -> ReprojectPoint / Get_ClosetObs / FindMatchDirect for every local map point with
+ *                                            the NEW pose, which never leaves the device        (ref: src/Feature_alignment.cpp:54-158)
+ * The greedy mask-dependent selection over the returned records stays with the caller, as for dsdtm_local_map_align_batch.
+ * For maintainers who can change Tracking's call sequence; the three separate calls give identical results. */
+typedef struct {
+    int32_t ref_slot, cur_slot;
+    const uint8_t* img; int32_t stride;              /* the new frame (host), bytes per row */
+    const dsdtm_ref_feat* feats; int32_t n_feats;    /* features of the reference frame (as for dsdtm_sparse_align) */
+    double ref_center[3];                            /* reference Frame::Get_CameraCnt() */
+    double pose_ref_c2w[7];                          /* reference Frame::Get_Pose() */
+    double pose_c2r_in[7];                           /* cur.Get_Pose() * ref.Get_Pose().inverse() (ref: src/Sprase_ImageAlign.cpp:43) */
+    int32_t max_level, min_level, max_iters;         /* Sprase_ImgAlign constructor arguments */
+    const dsdtm_kf_view* kfs; int32_t n_kfs;         /* local map snapshot (as for dsdtm_local_map_align_batch) */
+    const dsdtm_obs* obs; int32_t n_obs;
+    const dsdtm_map_point* pts; int32_t n_pts;
+    int32_t max_search_level, align_iters;
+} dsdtm_track_in;
+typedef struct {
+    double  pose_c2r[7];    /* Sprase_ImgAlign::mT_c2r */
+    double  pose_cur_c2w[7];/* cur.Set_Pose(mT_c2r * ref.Get_Pose()) */
+    double  cur_center[3];  /* cur.Get_CameraCnt() */
+    int32_t n_tracked;      /* return value of Run */
+    int32_t reserved;
+} dsdtm_track_out;          /* 144 bytes */
+int dsdtm_track_frame(dsdtm_ctx* ctx, const dsdtm_track_in* in, dsdtm_track_out* out, dsdtm_reproj* reproj /* n_pts */);
+
 /* ---------------------------------------------------------------- batched front end (sweep / bench) -------- */
 /* One "step" over n_pairs independent frame pairs: [pyramid(cur)] -> sparse align -> Align2D of the pair's patches
  * against its cur frame. Inputs are staged once (H2D), run() only launches kernels on HBM-resident data (CUDA-graph

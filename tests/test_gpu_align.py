@@ -440,3 +440,40 @@ def test_large_calls_take_the_direct_copy_path_and_agree_with_the_packed_arena_p
         assert (small["flags"] & capi.LM_CONVERGED).astype(bool).sum() > 200
     finally:
         c.close()
+
+
+def test_track_frame_single_call_equals_the_three_separate_calls(ctx, scenario):
+    """dsdtm_track_frame = new Frame + Sprase_ImgAlign::Run + UpdateLocalMap/SearchLocalPoints' device part in one call with one
+    synchronisation (ref: src/Tracking.cpp:57,199-224); the pose found by the sparse alignment is composed with the reference pose
+    on the device and feeds the local-map kernels without visiting the host. Must equal the separate calls bit for bit."""
+    from dsdtm_b200 import capi
+    sc = scenario
+    ctx.upload(0, sc["ref_img"])
+    F = sc["feats"]; n = len(F)
+    T_ref = sc["T_ref"]
+    pose_in = O.se3_mul(T_ref, O.se3_inv(T_ref))                       # cur.Set_Pose(last.Get_Pose()) -> T_c2r = identity
+    kfs = np.zeros(1, capi.KF_VIEW_DT); kfs[0]["slot"] = 0; kfs[0]["pose_c2w"] = T_ref; kfs[0]["center"] = sc["ref_center"]
+    obs = np.zeros(n, capi.OBS_DT); pts = np.zeros(n, capi.MAP_POINT_DT)
+    for i in range(n):
+        obs[i]["kf"] = 0; obs[i]["level"] = F[i]["level"]; obs[i]["px"] = F[i]["px"]; obs[i]["normal"] = F[i]["normal"]; obs[i]["point_w"] = F[i]["point_w"]
+        pts[i]["point_w"] = F[i]["point_w"]; pts[i]["obs_begin"] = i; pts[i]["obs_count"] = 1
+    # --- separate calls (slot 1), pose composition on the host with the oracle's Sophus arithmetic
+    ctx.upload(1, sc["cur_img"])
+    p_out, ntr, _ = ctx.sparse_align(0, 1, F, sc["ref_center"], pose_in, 4, 0, 30)
+    T_cur = O.se3_mul(p_out, T_ref); cen = O.se3_inv(T_cur)[4:]
+    rep_sep = ctx.local_map_align_batch(1, T_cur, cen, kfs, obs, pts, 2, 10)
+    # --- one call (slot 2 gets the frame)
+    out, rep = ctx.track_frame(0, 2, sc["cur_img"], F, sc["ref_center"], T_ref, pose_in, (4, 0, 30), kfs, obs, pts, 2, 10)
+    assert (out["pose_c2r"] == p_out).all() and out["n_tracked"] == ntr
+    assert (out["pose_cur_c2w"] == T_cur).all() and (out["cur_center"] == cen).all()      # device composition == Sophus restatement
+    for k in rep.dtype.names:
+        assert np.array_equal(rep[k], rep_sep[k], equal_nan=(rep[k].dtype.kind == "f")), k
+    packed, offs, ws, hs = sc["cur_pyr"]
+    for l in range(5):
+        assert (ctx.download_level(2, l) == O.pyr_level(packed, offs, ws, hs, l)).all()
+    assert (rep["flags"] & capi.LM_CONVERGED).astype(bool).sum() > 200
+    d = S.pose_dist(out["pose_c2r"], sc["T_c2r"])
+    assert d[0] < 1e-3 and d[1] < 3e-3
+    # no local map: alignment only
+    out2, rep2 = ctx.track_frame(0, 2, sc["cur_img"], F, sc["ref_center"], T_ref, pose_in, (4, 0, 30), kfs[:0], obs[:0], pts[:0], 2, 10)
+    assert (out2["pose_c2r"] == p_out).all() and len(rep2) == 0
