@@ -369,3 +369,60 @@ def test_frame_pool_too_small_fails_loudly(built):
     cur = HL.HFrame(cam_h, img, poses[2])
     with pytest.raises(RuntimeError, match="frame pool too small"):
         HL.search_local_points_multi(cam_h, cur, kfs)
+
+
+# ------------------------------------------------------------------------------------------------ RGB-D sequence with the key-frame lift
+@pytest.mark.gpu
+def test_rgbd_sequence_with_device_keyframe_lift(built):
+    """A 25-frame RGB-D run through the adapter classes in which every map point comes from the device key-frame path
+    (ref: src/Tracking.cpp:412-464: detect -> UndistortFeatures -> Get_FeatureDetph -> UnProject): TUM-style 16-bit depth
+    (scale 5000), key frames every 8 frames, tracked pose checked against the ground-truth trajectory and the lifted points
+    against the analytic scene. No oracle here: this is the functional end-to-end check of SURVEY 8f-3 inside the loop; the
+    per-call parity tests are in test_gpu_ingest.py / test_host_adapters.py."""
+    cam = dict(S.KINECT)
+    scene = S.Scene(123)
+    n_frames, kf_every, scale = 25, 8, 5000.0
+    poses = _trajectory(n_frames, seed=21)
+    cam_h = HL.configure(cam, max_fts=300, max_frames=24, dist=(0.0, 0.0, 0.0, 0.0, 0.0))
+    cfg = (5, 0, 8)
+
+    def depth16(z):
+        return np.clip(np.rint(z * scale), 0, 65535).astype(np.uint16)
+
+    def lift(frame, z, pts, start):
+        """CraeteKeyframe on `frame`: device lift of all features, map points for the new ones (index >= start) with a depth."""
+        tab, _ = frame.keyframe_lift(depth16(z), scale)
+        px, lv, ini = frame.features()
+        new = np.arange(start, len(px))
+        has = (tab[new, 2] > 0).astype(np.uint8)
+        assert has.sum() == len(new)                                     # the synthetic depth has no holes
+        want = pts[np.rint(px[new, 1]).astype(int), np.rint(px[new, 0]).astype(int)]
+        got = tab[new, 3:6]
+        assert np.abs(got - want).max() < 2e-3, np.abs(got - want).max()  # 16-bit depth quantisation (0.2 mm) + pixel-centre sampling
+        frame.attach_points_from(int(start), got, has)
+        return len(new)
+
+    img0, z0, pts0 = S.render(scene, cam, poses[0], want_points=True)
+    g0 = HL.HFrame(cam_h, img0, poses[0])
+    assert g0.detect(5.0) == 300
+    assert lift(g0, z0, pts0, 0) == 300
+    kf_handles = [HL.lib().hs_keyframe_new(g0.h)]
+    g_last = g0
+    n_kf = 1
+    for k in range(1, n_frames):
+        img, z, pts = S.render(scene, cam, poses[k], want_points=True)
+        g_cur = HL.HFrame(cam_h, img, g_last.pose())
+        n, pose, _ = HL.sparse_align_run(*cfg, g_cur, g_last)
+        e = S.pose_dist(pose, poses[k])
+        assert n >= 100 and e[0] < 1.5e-3 and e[1] < 4e-3, (k, n, e)      # tracks the ground truth (no drift beyond the per-frame noise)
+        m, nrep = HL.search_local_points_multi(cam_h, g_cur, kf_handles)
+        assert m >= 150, (k, m)
+        if k % kf_every == 0:
+            n_old = len(g_cur.features()[0])
+            n_all = g_cur.detect(5.0, use_existing=True)
+            assert n_all > n_old
+            assert lift(g_cur, z, pts, n_old) == n_all - n_old
+            kf_handles.append(HL.lib().hs_keyframe_new(g_cur.h))
+            n_kf += 1
+        g_last = g_cur
+    assert n_kf == 4
