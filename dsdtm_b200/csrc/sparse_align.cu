@@ -191,6 +191,9 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 #ifndef DSDTM_SA_PIPELINE
 #define DSDTM_SA_PIPELINE 0      // 1 = issue feature k+1's gather before feature k's arithmetic. Measured slower (1.22 vs 1.12 ms, profiles/r1_sparse_align_v3.md): registers
 #endif
+// (Tried and removed: staging an 8 x 7 window of the CURRENT image per feature in shared memory at level start, so that the
+// iterations of a level stop re-gathering it from global memory. 173 instead of 113 B/feature of shared memory took more L1
+// away than the re-gathers cost: 1.68 vs 1.55 ms per 4096 pairs, 86 vs 84 us for a single pair. profiles/r1_sparse_align_v3.md)
 #ifndef DSDTM_SA_MINB4
 #define DSDTM_SA_MINB4 3         // resident CTAs per SM the 4-warp variant is compiled for (register cap 65536 / (128 * MINB4))
 #endif
