@@ -32,13 +32,6 @@ struct A2dArgs {
     int n, max_iters, patch0;
 };
 
-__device__ __forceinline__ float wsum(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 constexpr int A2D_WARPS = 8;          // 8 warps = 16 patches per CTA
 
 // sum over the 16 lanes of a half-warp (xor butterfly with offsets < 16 never crosses the half)

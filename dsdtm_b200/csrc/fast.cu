@@ -27,14 +27,14 @@ constexpr int FT_W = 30, FT_H = 16;        // interior tile: 30 wide so that int
 constexpr int HALO = 5;                    // shi-tomasi needs +-5, fast score of the 1-px nonmax ring needs +-4
 constexpr int SMP = 48;                    // staged row pitch = staged columns [xa, xa+48), xa = (x0-5) rounded down to 8
 constexpr int SMH = FT_H + 2 * HALO;       // 26 staged rows (y0-5 .. y0+20)
-constexpr int SC_W = FT_W + 2, SC_H = FT_H + 2;   // score tile incl. 1-px ring: 32 x 18
+constexpr int SC_H = FT_H + 2;             // score tile incl. 1-px ring: 32 (= FT_W + 2, one lane each) x 18
 constexpr int SC_P = 32;                   // score row pitch
 constexpr int WARPS = 4;
 constexpr int QCAP = 64;
 #ifndef DSDTM_FAST_UNROLL_A
 #define DSDTM_FAST_UNROLL_A 1
 #endif
-constexpr int DSDTM_FAST_UNROLL_A_C = DSDTM_FAST_UNROLL_A;
+constexpr int FAST_UNROLL_A = DSDTM_FAST_UNROLL_A;   // phase-A row-loop unroll (sweep in profiles/: 1, 2, 3 equal, 6 slower)
 
 __constant__ int c_ring_dx[16] = { 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1 };
 __constant__ int c_ring_dy[16] = { 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3 };
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(32 * WARPS) fast_kernel(const FastArgs a)
         const int x = x0 - 1 + c;
         const bool xok = x >= 3 && x < w - 3;                         // ref: fast_10.cpp:41 scan bounds
         const int sc = c + xoff - 1;
-#pragma unroll DSDTM_FAST_UNROLL_A_C
+#pragma unroll FAST_UNROLL_A
         for (int r = 0; r < SC_H; ++r) {
             const int y = y0 - 1 + r;
             bool cand = false;
