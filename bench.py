@@ -437,8 +437,8 @@ def run_ours(args):
             "roofline": {"kernel": "sparse_align_kernel", "bound": "hbm", "achieved": sa_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": sa_gbs / hbm_peak, "traffic": measured_traffic("sparse_align_kernel", B), "peak_source": peak_src,
                          "ms_per_launch": sa_ms, "algorithmic_bytes_per_launch": sa_bytes,
-                         "note": "dependent Gauss-Newton chain: latency/issue-bound, not bandwidth-bound (SURVEY 8d): ncu issue slots busy 32 %, "
-                                 "fp64 pipe ~35 %, DRAM 14 %, L1/TEX hit 74 % (profiles/r1_sa_bench_summary.txt); traffic is the ncu DRAM byte count "
+                         "note": "dependent Gauss-Newton chain: latency/issue-bound, not bandwidth-bound (SURVEY 8d): ncu issue slots busy 38 %, "
+                                 "fp64 pipe 38 %, DRAM 18 %, L1/TEX hit 74 % (profiles/r1_sa_bench_summary.txt); traffic is the ncu DRAM byte count "
                                  "(32-byte sectors for 5-byte window rows) scaled per pair; see stages for the HBM-bound kernels"},
             "stages": {
                 "pyramid": {"ms_per_step": pyr_ms, "GBps": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "frac_hbm": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak,
