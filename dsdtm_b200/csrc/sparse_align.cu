@@ -194,12 +194,15 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 // (Tried and removed: staging an 8 x 7 window of the CURRENT image per feature in shared memory at level start, so that the
 // iterations of a level stop re-gathering it from global memory. 173 instead of 113 B/feature of shared memory took more L1
 // away than the re-gathers cost: 1.68 vs 1.55 ms per 4096 pairs, 86 vs 84 us for a single pair. profiles/r1_sparse_align_v3.md)
+#ifndef DSDTM_SA_MINB3
+#define DSDTM_SA_MINB3 4         // resident CTAs per SM the 3-warp variant is compiled for (5 -> 128 regs, 60 B spills: 1.79 vs 1.52 ms; 6 -> 96 regs: 2.89 ms)
+#endif
 #ifndef DSDTM_SA_MINB4
 #define DSDTM_SA_MINB4 3         // resident CTAs per SM the 4-warp variant is compiled for (register cap 65536 / (128 * MINB4))
 #endif
 
 template <int WPP>
-__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? 4 : (WPP == 4 ? DSDTM_SA_MINB4 : (WPP == 5 ? 3 : 1)))) sparse_align_kernel(const SaArgs a)
+__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_SA_MINB3 : (WPP == 4 ? DSDTM_SA_MINB4 : (WPP == 5 ? 3 : 1)))) sparse_align_kernel(const SaArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int NF = a.nf;
