@@ -108,6 +108,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_summary(kernel):
+    """Pipe / issue figures of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json); {} if absent."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    t = json.load(open(p)).get(kernel) or {}
+    return {k: t[k] for k in ("issue_slots_busy_pct", "fp64_pipe_pct", "dram_throughput_pct", "l1tex_hit_pct", "l2_hit_pct", "source") if k in t}
+
+
 def measured_traffic(kernel, pairs):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
     (profiles/r1_traffic.json, taken at 4096 pairs), scaled per pair. None if the capture is absent."""
@@ -436,7 +445,7 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"kernel": "sparse_align_kernel", "bound": "hbm", "achieved": sa_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": sa_gbs / hbm_peak, "traffic": measured_traffic("sparse_align_kernel", B), "peak_source": peak_src,
-                         "ms_per_launch": sa_ms, "algorithmic_bytes_per_launch": sa_bytes,
+                         "ms_per_launch": sa_ms, "algorithmic_bytes_per_launch": sa_bytes, "ncu": ncu_summary("sparse_align_kernel"),
                          "note": "dependent Gauss-Newton chain: latency/issue-bound, not bandwidth-bound (SURVEY 8d): ncu issue slots busy 38 %, "
                                  "fp64 pipe 38 %, DRAM 18 %, L1/TEX hit 74 % (profiles/r1_sa_bench_summary.txt); traffic is the ncu DRAM byte count "
                                  "(32-byte sectors for 5-byte window rows) scaled per pair; see stages for the HBM-bound kernels"},
