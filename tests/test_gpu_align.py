@@ -477,3 +477,23 @@ def test_track_frame_single_call_equals_the_three_separate_calls(ctx, scenario):
     # no local map: alignment only
     out2, rep2 = ctx.track_frame(0, 2, sc["cur_img"], F, sc["ref_center"], T_ref, pose_in, (4, 0, 30), kfs[:0], obs[:0], pts[:0], 2, 10)
     assert (out2["pose_c2r"] == p_out).all() and len(rep2) == 0
+
+
+def test_track_frame_refuses_bad_arguments(ctx, scenario):
+    from dsdtm_b200 import capi
+    sc = scenario
+    ctx.upload(0, sc["ref_img"])
+    F = sc["feats"]
+    kfs = np.zeros(1, capi.KF_VIEW_DT); kfs[0]["pose_c2w"] = sc["T_ref"]; kfs[0]["center"] = sc["ref_center"]
+    obs = np.zeros(2, capi.OBS_DT); obs["point_w"] = F[:2]["point_w"]; obs["px"] = F[:2]["px"]; obs["normal"] = F[:2]["normal"]
+    pts = np.zeros(2, capi.MAP_POINT_DT); pts["point_w"] = F[:2]["point_w"]; pts["obs_begin"] = [0, 1]; pts["obs_count"] = 1
+    ok = lambda **kw: ctx.track_frame(kw.get("ref", 0), kw.get("cur", 2), sc["cur_img"], kw.get("feats", F), sc["ref_center"], sc["T_ref"], S.IDENTITY,
+                                      kw.get("cfg", (4, 0, 30)), kw.get("kfs", kfs), kw.get("obs", obs), kw.get("pts", pts), kw.get("msl", 2), 10)
+    ok()                                                                  # the well-formed call works
+    bad_obs = obs.copy(); bad_obs[1]["kf"] = 3
+    bad_pts = pts.copy(); bad_pts[1]["obs_begin"] = 2
+    bad_kfs = kfs.copy(); bad_kfs[0]["slot"] = 99
+    for kw in (dict(cur=99), dict(ref=-1), dict(cfg=(9, 0, 30)), dict(cfg=(4, 4, 30)), dict(msl=7), dict(obs=bad_obs), dict(pts=bad_pts), dict(kfs=bad_kfs)):
+        with pytest.raises(capi.DsdtmError):
+            ok(**kw)
+    ok()                                                                  # and the context is still usable afterwards
