@@ -441,6 +441,15 @@ Sprase_ImgAlign::Sprase_ImgAlign(int tMaxLevel, int tMinLevel, int tMaxIterators
     mnMinfts = Config::Get<int>("Camera.Min_fts");                // ref: src/Sprase_ImageAlign.cpp:14
 }
 
+void Sprase_ImgAlign::Reset() { mT_c2r = SE3(); mLog.clear(); }   // ref: src/Sprase_ImageAlign.cpp:22-27 (the device holds no per-run state)
+
+void Sprase_ImgAlign::GetJocabianBA(const Vector3d& p, double J[12]) const   // ref: :169-193
+{
+    const double x = p[0], y = p[1], z_inv = 1.0 / p[2], z_inv2 = z_inv * z_inv;
+    J[0] = -z_inv; J[1] = 0.0; J[2] = x * z_inv2; J[3] = y * J[2]; J[4] = -(1.0 + x * J[2]); J[5] = y * z_inv;
+    J[6] = 0.0; J[7] = -z_inv; J[8] = y * z_inv2; J[9] = 1.0 + y * J[8]; J[10] = -x * J[8]; J[11] = -x * z_inv;
+}
+
 int Sprase_ImgAlign::Run(FramePtr cur, FramePtr ref)              // ref: src/Sprase_ImageAlign.cpp:29-60
 {
     mLog.clear();
@@ -468,7 +477,8 @@ int Sprase_ImgAlign::Run(FramePtr cur, FramePtr ref)              // ref: src/Sp
                            mnMaxIterators, pose_out, &n_tracked, mLog.data(), (int)mLog.size(), &n_log) != 0)
         throw std::runtime_error(std::string("dsdtm_sparse_align: ") + dsdtm_last_error(rt.ctx()));
     mLog.resize(std::min<size_t>(n_log, mLog.size()));
-    cur->Set_Pose(SE3(pose_out) * ref->Get_Pose());               // ref: :57
+    mT_c2r = SE3(pose_out);
+    cur->Set_Pose(mT_c2r * ref->Get_Pose());                     // ref: :57
     return n_tracked;                                             // ref: :59
 }
 
@@ -668,6 +678,24 @@ bool Feature_Alignment::FindMatchDirect(const MapPoint* mp, const FramePtr frame
     pt = Vector2d(px[0], px[1]);
     level = L;
     return conv != 0;
+}
+
+bool Feature_Alignment::CellComparator(Candidate& c1, Candidate& c2) { return c1.mMpPoint->Get_FoundNums() > c2.mMpPoint->Get_FoundNums(); }
+
+void Feature_Alignment::WarpAffine(const Matrix2d A, KeyFrame* kf, Feature* rf, const int search_level, uchar* patch10)   // ref: :206-259
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    const int slot = rt.Resident(kf->mGpu), rl = rf->mlevel, sl = search_level;
+    const double a[4] = { A(0, 0), A(0, 1), A(1, 0), A(1, 1) };
+    const float px[2] = { rf->mpx.x, rf->mpx.y };
+    if (dsdtm_warp_affine_batch(rt.ctx(), &slot, a, px, &rl, &sl, 1, patch10) != 0)
+        throw std::runtime_error(std::string("dsdtm_warp_affine_batch: ") + dsdtm_last_error(rt.ctx()));
+}
+
+void Feature_Alignment::GetPatchNoBoarder()                      // ref: :261-275 (inner 8 x 8 of the 10 x 10 patch)
+{
+    for (int y = 1; y < 9; ++y)
+        for (int x = 1; x < 9; ++x) mPatch[(y - 1) * 8 + (x - 1)] = mPatch_WithBoarder[y * 10 + x];
 }
 
 bool Feature_Alignment::Align2DGaussNewton(const FramePtr cur, int level, uchar* patch10, uchar*, int MaxIters, Vector2d& px)   // ref: :318-417

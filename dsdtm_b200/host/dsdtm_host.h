@@ -239,11 +239,16 @@ public:
 class Sprase_ImgAlign {   // ref: include/Sprase_ImageAlign.h:20-69
 public:
     Sprase_ImgAlign(int tMaxLevel, int tMinLevel, int tMaxIterators);
+    void Reset();                                             // ref: src/Sprase_ImageAlign.cpp:22-27
     int Run(FramePtr tCurFrame, FramePtr tRefFrame);
+    // the 2 x 6 Jacobian of the normalised projection w.r.t. the pose (ref: :169-193), row-major; host math, kept for API parity
+    void GetJocabianBA(const Vector3d& tPoint, double J[12]) const;
+    const SE3& Get_T_c2r() const { return mT_c2r; }           // mT_c2r of the last Run
     // last run's Gauss-Newton trace (new: the reference only prints; used by the parity tests)
     const std::vector<dsdtm_iter_log>& LastLog() const { return mLog; }
 protected:
     int mnMaxLevel, mnMinLevel, mnMaxIterators, mnMinfts;
+    SE3 mT_c2r;
     std::vector<dsdtm_iter_log> mLog;
 };
 
@@ -266,6 +271,13 @@ public:
     bool FindMatchDirect(const MapPoint* tMpPoint, const FramePtr tFrame, Vector2d& tPt, int& tLevel);
     Matrix2d SolveAffineMatrix(KeyFrame* tReferKframe, const FramePtr tCurFrame, Feature* tReferFeature, const MapPoint* tMpPoint);
     int GetBestSearchLevel(Matrix2d tAffineMat, int tMaxLevel);
+    // ref: :206-259 / :261-275; single-candidate forms (a batch of one on the GPU). tPatchLarger = 10 x 10 bytes, the 8 x 8 interior
+    // is written to mPatch by GetPatchNoBoarder as in the reference.
+    void WarpAffine(const Matrix2d tA_c2r, KeyFrame* tReferKframe, Feature* tRefFeature, const int tSearchLevel, uchar* tPatchLarger);
+    void GetPatchNoBoarder();
+    static bool CellComparator(Candidate& c1, Candidate& c2);     // ref: :123-126
+    uchar mPatch[2 * mHalf_PatchSize * 2 * mHalf_PatchSize];
+    uchar mPatch_WithBoarder[(2 * mHalf_PatchSize + 2) * (2 * mHalf_PatchSize + 2)];
     static bool Align2DGaussNewton(const FramePtr tCurFrame, int tLevel, uchar* tPatch_WithBoarder, uchar* tPatch, int MaxIters, Vector2d& tCurPx);
     int LastMatches() const { return mLastMatches; }
 private:

@@ -238,6 +238,22 @@ int hs_align2d_single(void* cur, int level, const uint8_t* patch10, int iters, d
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// Feature_Alignment::WarpAffine + GetPatchNoBoarder for feature `idx` of a key frame (single-candidate forms, ref: :206-275)
+int hs_warp_affine_single(void* cam, void* kf, int idx, const double* A4, int search_level, uint8_t* patch10, uint8_t* patch8)
+{
+    try {
+        Feature_Alignment& fa = feature_alignment(cam);
+        KeyFrame* k = static_cast<HsKf*>(kf)->kf;
+        Matrix2d A;
+        A(0, 0) = A4[0]; A(0, 1) = A4[1]; A(1, 0) = A4[2]; A(1, 1) = A4[3];
+        fa.WarpAffine(A, k, k->mvFeatures[idx], search_level, fa.mPatch_WithBoarder);
+        fa.GetPatchNoBoarder();
+        std::memcpy(patch10, fa.mPatch_WithBoarder, 100);
+        std::memcpy(patch8, fa.mPatch, 64);
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
 void hs_circle(uint8_t* img, int w, int h, float cx, float cy, int r, int color)
 {
     Mat8 m(h, w, img, w);

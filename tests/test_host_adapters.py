@@ -222,3 +222,25 @@ def test_frame_rgbd_keyframe_path(built, scenario):
             n_ok += 1
     assert 100 < n_ok < 300
     fr.free()
+
+
+@pytest.mark.gpu
+def test_single_candidate_warp_affine_and_patch_forms(built, scenario):
+    """Feature_Alignment::WarpAffine + GetPatchNoBoarder as public single-candidate calls (ref: src/Feature_alignment.cpp:206-275)."""
+    sc = scenario
+    cam_h = HL.configure(sc["cam"], max_fts=300)
+    ref = HL.HFrame(cam_h, sc["ref_img"], sc["T_ref"])
+    assert ref.detect(5.0) == 300
+    corners = sc["corners"]
+    ref.attach_points(sc["ref_points"][corners["y"], corners["x"]], np.ones(len(corners), np.uint8))
+    kf = HL.lib().hs_keyframe_new(ref.h)
+    packed, offs, ws, hs = sc["ref_pyr"]
+    rng = np.random.default_rng(4)
+    for idx in (0, 7, 123, 299):
+        A = np.eye(2) + rng.uniform(-0.2, 0.2, (2, 2))
+        L0 = int(corners[idx]["level"])
+        p10 = np.zeros(100, np.uint8); p8 = np.zeros(64, np.uint8)
+        assert HL.lib().hs_warp_affine_single(cam_h, kf, idx, HL._p(np.ascontiguousarray(A)), 0, HL._p(p10), HL._p(p8)) == 0, HL.lib().hs_last_error()
+        want = O.warp_affine(A, O.pyr_level(packed, offs, ws, hs, L0), sc["feats"][idx]["px"], L0, 0)
+        assert (p10 == want).all() and (p8 == O.patch_no_border(want)).all(), idx
+    ref.free()
