@@ -59,7 +59,7 @@ def test_sparse_align_other_seeds_and_nonidentity_ref(ctx, seed):
     _compare_traces(lo, lg)
 
 
-@pytest.mark.parametrize("opt", [("sa_variant", 1), ("sa_warps_per_pair", 1), ("sa_warps_per_pair", 2), ("sa_warps_per_pair", 4), ("sa_warps_per_pair", 5)])
+@pytest.mark.parametrize("opt", [("sa_variant", 1), ("sa_warps_per_pair", 1), ("sa_warps_per_pair", 2), ("sa_warps_per_pair", 3), ("sa_warps_per_pair", 4), ("sa_warps_per_pair", 5)])
 def test_sparse_align_kernel_variants_agree_with_oracle(ctx, scenario, opt):
     """Tuning knobs never change results beyond the reduction-order tolerance: the L2-workspace variant and every
     warps-per-pair instantiation against the oracle."""
@@ -497,3 +497,40 @@ def test_track_frame_refuses_bad_arguments(ctx, scenario):
         with pytest.raises(capi.DsdtmError):
             ok(**kw)
     ok()                                                                  # and the context is still usable afterwards
+
+
+def test_large_batch_uses_the_throughput_kernel_and_matches_the_oracle(built):
+    """A batch of >= 4 pairs per SM switches sparse_align to its 3-warps-per-pair instantiation (four CTAs per SM). 640 pairs =
+    replicas of two scenes with per-replica start poses: every pair against the oracle (on the distinct inputs), replicas with equal
+    inputs bit-equal, staged graph replay equal to the direct batch call."""
+    from dsdtm_b200 import capi
+    cam = dict(S.KINECT)
+    n, stride = 640, 320
+    ctx = capi.Context(cam, levels=5, cell_size=15, max_feats=stride, max_patches=8, max_frames=2 * n, max_batch=n)
+    try:
+        scs = [H.make_scenario(200 + i, cam) for i in range(2)]
+        rng = np.random.default_rng(5)
+        starts = [S.IDENTITY] + [S.pose_from_xi(rng.uniform(-0.003, 0.003, 6)) for _ in range(3)]
+        imgs = np.stack([scs[(i // 2) % 2]["ref_img" if i % 2 == 0 else "cur_img"] for i in range(2 * n)])
+        for c0 in range(0, 2 * n, 256):
+            ctx.upload_batch(c0, imgs[c0:c0 + 256])
+        feats = np.zeros((n, stride), O.REF_FEAT_DT); nf = np.zeros(n, np.int32); centers = np.zeros((n, 3)); poses = np.zeros((n, 7))
+        for i in range(n):
+            sc = scs[i % 2]
+            nf[i] = len(sc["feats"]); feats[i, :nf[i]] = sc["feats"]; centers[i] = sc["ref_center"]; poses[i] = starts[(i // 2) % 4]
+        ref_slots = 2 * np.arange(n); cur_slots = ref_slots + 1
+        pb, tb, _, _ = ctx.sparse_align_batch(ref_slots, cur_slots, feats, nf, centers, poses, 4, 0, 30)
+        for k in range(8):                                        # the 8 distinct (scene, start pose) combinations
+            sc = scs[k % 2]
+            packed, offs, ws, hs = sc["ref_pyr"]
+            po, no, _ = O.sparse_align(H.ocam(cam), packed, sc["cur_pyr"][0], offs, ws, hs, sc["feats"], sc["ref_center"], starts[(k // 2) % 4], 4, 0, 30)
+            same = np.arange(k, n, 8)
+            d = S.pose_dist(po, pb[k])
+            assert d[0] < POSE_TOL and d[1] < POSE_TOL and no == tb[k], (k, d)
+            assert (pb[same] == pb[k]).all() and (tb[same] == tb[k]).all(), k
+        ctx.batch_stage(ref_slots, cur_slots, feats, nf, centers, poses, 4, 0, 30)
+        ctx.batch_run(0); ctx.batch_run(0)
+        pg, tg, _, _ = ctx.batch_fetch()
+        assert (pg == pb).all() and (tg == tb).all()
+    finally:
+        ctx.close()
