@@ -8,7 +8,7 @@ import numpy as np
 
 from . import build as _build
 
-STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine", "cand_prep", "local_map", "ingest")
+STAGES = ("pyramid", "fast", "sparse_align", "align2d", "warp_affine", "cand_prep", "local_map", "ingest", "pose_opt")
 
 CORNER_DT = np.dtype([("x", "<i4"), ("y", "<i4"), ("level", "<i4"), ("score", "<f4")])
 REF_FEAT_DT = np.dtype([("px", "<f4", 2), ("level", "<i4"), ("initial", "<i4"),
@@ -27,6 +27,12 @@ LM_IN_IMAGE, LM_OBS_OK, LM_REF_OK, LM_CONVERGED = 1, 2, 4, 8
 LIFTED_DT = np.dtype([("px", "<f4", 2), ("depth", "<f4"), ("status", "<i4"), ("normal", "<f8", 3), ("point_w", "<f8", 3)])
 assert LIFTED_DT.itemsize == 64
 LIFT_SKIPPED, LIFT_OK, LIFT_NO_DEPTH = 0, 1, 2
+BA_OBS_DT = np.dtype([("normal", "<f8", 3), ("point_w", "<f8", 3), ("level", "<i4"), ("reserved", "<i4")])
+BA_SUMMARY_DT = np.dtype([("iterations", "<i4"), ("termination", "<i4"), ("n_successful", "<i4"), ("n_obs", "<i4"),
+                          ("initial_cost", "<f8"), ("final_cost", "<f8")])
+assert BA_OBS_DT.itemsize == 56 and BA_SUMMARY_DT.itemsize == 32
+BA_FUNCTION_TOL, BA_PARAMETER_TOL, BA_GRADIENT_TOL, BA_NO_CONVERGENCE, BA_FAILURE, BA_MIN_RADIUS, BA_NO_RESIDUALS = range(7)
+BA_MAX_OBS = 4096
 
 
 class Cam(C.Structure):
@@ -69,6 +75,7 @@ SYMBOLS = [
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
     "dsdtm_local_map_align_batch", "dsdtm_depth_upload", "dsdtm_depth_convert_f32", "dsdtm_keyframe_lift",
     "dsdtm_frame_upload_pyramid_host", "dsdtm_frames_upload_clahe_pyramid", "dsdtm_track_frame",
+    "dsdtm_pose_optimize", "dsdtm_pose_optimize_batch",
 ]
 
 
@@ -318,6 +325,28 @@ class Context:
         self._ck(self.L.dsdtm_keyframe_lift(self.hp, int(depth_slot), _p(np.ascontiguousarray(pose_c2w, np.float64)),
                                             _p(np.ascontiguousarray(dist, np.float32)), C.c_float(depth_scale), _p(px), _p(ini), len(px), _p(out)))
         return out
+
+    def pose_optimize_batch(self, obs, n_obs, poses_in, max_iters=100, want_res=True):
+        """dsdtm_pose_optimize_batch: obs = (n_frames, obs_stride) BA_OBS_DT, n_obs per frame, poses (n_frames, 7).
+        Returns (poses_out, res_norm or None, summaries)."""
+        obs = np.ascontiguousarray(obs, BA_OBS_DT)
+        n_obs = np.ascontiguousarray(n_obs, np.int32).reshape(-1)
+        nf = len(n_obs)
+        obs = obs.reshape(nf, -1) if nf else obs.reshape(0, 0)
+        poses_in = np.ascontiguousarray(poses_in, np.float64).reshape(nf, 7)
+        out = np.zeros((nf, 7)); summ = np.zeros(nf, BA_SUMMARY_DT)
+        res = np.zeros(obs.shape, np.float64) if want_res else None
+        self._ck(self.L.dsdtm_pose_optimize_batch(self.hp, nf, _p(obs), int(obs.shape[1]), _p(n_obs), _p(poses_in), int(max_iters), _p(out),
+                                                  _p(res), _p(summ)))
+        return out, res, summ
+
+    def pose_optimize(self, obs, pose_in, max_iters=100):
+        """dsdtm_pose_optimize (Optimizer::PoseOptimization of one frame). Returns (pose_out, res_norm, summary record)."""
+        obs = np.ascontiguousarray(obs, BA_OBS_DT).reshape(-1)
+        pose_in = np.ascontiguousarray(pose_in, np.float64).reshape(7)
+        out = np.zeros(7); res = np.zeros(len(obs)); summ = np.zeros(1, BA_SUMMARY_DT)
+        self._ck(self.L.dsdtm_pose_optimize(self.hp, _p(obs), len(obs), _p(pose_in), int(max_iters), _p(out), _p(res), _p(summ)))
+        return out, res, summ[0]
 
     def track_frame(self, ref_slot, cur_slot, img, feats, ref_center, pose_ref_c2w, pose_c2r_in, sa_cfg, kfs, obs, pts, max_search_level,
                     align_iters=10):

@@ -268,6 +268,7 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
         CK(cudaMemcpy(c->fast_tiles_d, tiles.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     }
     CK(sparse_align_init(c));
+    CK(pose_opt_init(c));
     CK(cudaMallocHost((void**)&c->stage_pin, kStageBytes));
     CK(cudaMalloc((void**)&c->stage_dev, kStageBytes));
 #undef CK
@@ -284,7 +285,8 @@ void dsdtm_destroy(dsdtm_ctx* c)
                      c->feats_d, c->n_feats_d, c->centers_d, c->poses_in_d, c->poses_out_d, c->n_tracked_d, c->log_d, c->n_log_d,
                      c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d, c->cand_d,
                      c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d,
-                     c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d, c->clahe_src_d, c->clahe_lut_d };
+                     c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d, c->clahe_src_d, c->clahe_lut_d,
+                     c->po_obs_d, c->po_res_d, c->po_nobs_d, c->po_pose_in_d, c->po_pose_out_d, c->po_sum_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->stage_pin) cudaFreeHost(c->stage_pin);
@@ -985,6 +987,54 @@ int dsdtm_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], 
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
     st.finish();
     return 0;
+}
+
+// Optimizer::PoseOptimization (ref: src/Optimizer.cpp:20-101) for n_frames independent frames: one copy in per array, one launch,
+// one copy out per requested array, one synchronisation.
+int dsdtm_pose_optimize_batch(dsdtm_ctx* c, int n_frames, const dsdtm_ba_obs* obs, int obs_stride, const int* n_obs,
+                              const double* poses_in, int max_iters, double* poses_out, double* res_norm, dsdtm_ba_summary* summaries)
+{
+    if (!c) return DSDTM_E_ARG;
+    if (n_frames < 0 || obs_stride < 0 || max_iters < 0) return fail(c, DSDTM_E_ARG, "negative count");
+    if (n_frames == 0) return 0;
+    if (!n_obs || !poses_in || !poses_out) return fail(c, DSDTM_E_ARG, "null pointer");
+    int max_obs = 0;
+    for (int i = 0; i < n_frames; ++i) {
+        if (n_obs[i] < 0 || n_obs[i] > obs_stride) return fail(c, DSDTM_E_ARG, "n_obs outside [0, obs_stride]");
+        max_obs = std::max(max_obs, n_obs[i]);
+    }
+    if (max_obs > DSDTM_BA_MAX_OBS) return fail(c, DSDTM_E_ARG, "more than DSDTM_BA_MAX_OBS observations in a frame");
+    if (max_obs > 0 && !obs) return fail(c, DSDTM_E_ARG, "null pointer");
+    for (int i = 0; i < n_frames; ++i)
+        for (int k = 0; k < n_obs[i]; ++k) {
+            const int L = obs[(size_t)i * obs_stride + k].level;
+            if (L < 0 || L > 30) return fail(c, DSDTM_E_ARG, "observation level outside [0, 30]");
+        }
+    const size_t n_rec = (size_t)n_frames * obs_stride;
+    if (grow(c, &c->po_obs_d, &c->po_obs_cap, n_rec) || grow(c, &c->po_nobs_d, &c->po_nobs_cap, (size_t)n_frames) ||
+        grow(c, &c->po_pose_in_d, &c->po_pose_in_cap, 7 * (size_t)n_frames) || grow(c, &c->po_pose_out_d, &c->po_pose_out_cap, 7 * (size_t)n_frames) ||
+        grow(c, &c->po_sum_d, &c->po_sum_cap, (size_t)n_frames) || (res_norm && grow(c, &c->po_res_d, &c->po_res_cap, n_rec)))
+        return DSDTM_E_NOMEM;
+    cudaStream_t s = c->stream;
+    Stager st(c, n_rec * (sizeof(dsdtm_ba_obs) + (res_norm ? sizeof(double) : 0)) + (size_t)n_frames * (sizeof(int) + 14 * sizeof(double) + sizeof(dsdtm_ba_summary)));
+    if (n_rec) DSDTM_CUDA(c, cudaMemcpyAsync(c->po_obs_d, st.in(obs, n_rec * sizeof(dsdtm_ba_obs)), n_rec * sizeof(dsdtm_ba_obs), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->po_nobs_d, st.in(n_obs, (size_t)n_frames * sizeof(int)), (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->po_pose_in_d, st.in(poses_in, 7 * (size_t)n_frames * sizeof(double)), 7 * (size_t)n_frames * sizeof(double), cudaMemcpyHostToDevice, s));
+    stage_begin(c, DSDTM_STAGE_POSE_OPT);
+    DSDTM_CUDA(c, launch_pose_opt(c, n_frames, obs_stride, max_obs, max_iters, res_norm != nullptr, summaries != nullptr, s));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(st.out(poses_out, 7 * (size_t)n_frames * sizeof(double)), c->po_pose_out_d, 7 * (size_t)n_frames * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (res_norm && n_rec) DSDTM_CUDA(c, cudaMemcpyAsync(st.out(res_norm, n_rec * sizeof(double)), c->po_res_d, n_rec * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (summaries) DSDTM_CUDA(c, cudaMemcpyAsync(st.out(summaries, (size_t)n_frames * sizeof(dsdtm_ba_summary)), c->po_sum_d, (size_t)n_frames * sizeof(dsdtm_ba_summary), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    st.finish();
+    return 0;
+}
+
+int dsdtm_pose_optimize(dsdtm_ctx* c, const dsdtm_ba_obs* obs, int n_obs, const double pose_in[7], int max_iters, double pose_out[7],
+                        double* res_norm, dsdtm_ba_summary* summary)
+{
+    return dsdtm_pose_optimize_batch(c, 1, obs, n_obs, &n_obs, pose_in, max_iters, pose_out, res_norm, summary);
 }
 
 int dsdtm_frames_upload_clahe_pyramid(dsdtm_ctx* c, int first_slot, int n, const uint8_t* imgs, double clip_limit, int tiles_x, int tiles_y,

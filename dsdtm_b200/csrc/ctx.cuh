@@ -107,6 +107,13 @@ struct dsdtm_ctx {
     dsdtm_lifted* lift_out_d = nullptr;
     uint8_t* clahe_src_d = nullptr;      size_t clahe_cap = 0;       // raw images waiting for CLAHE (frames)
     uint8_t* clahe_lut_d = nullptr;      size_t clahe_lut_cap = 0;   // per frame tiles * 256 bytes
+    // pose refinement (f-2), grown on demand
+    dsdtm_ba_obs* po_obs_d = nullptr;    size_t po_obs_cap = 0;      // n_frames * obs_stride records
+    double* po_res_d = nullptr;          size_t po_res_cap = 0;      // residual norms, same indexing
+    int* po_nobs_d = nullptr;            size_t po_nobs_cap = 0;
+    double* po_pose_in_d = nullptr;      size_t po_pose_in_cap = 0;  // 7 per frame
+    double* po_pose_out_d = nullptr;     size_t po_pose_out_cap = 0;
+    dsdtm_ba_summary* po_sum_d = nullptr; size_t po_sum_cap = 0;
 
     // pinned host staging for small synchronous calls
     uint8_t* pinned = nullptr;
@@ -169,6 +176,9 @@ cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s);
 cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s,
                              const double* pose_dev = nullptr);
 cudaError_t launch_compose_pose(dsdtm_ctx* c, const double* t_c2r_d, const double pose_ref_c2w[7], double* out10_d, cudaStream_t s);
+cudaError_t pose_opt_init(dsdtm_ctx* c);
+cudaError_t launch_pose_opt(dsdtm_ctx* c, int n_frames, int obs_stride, int max_obs, int max_iters, bool want_res, bool want_sum,
+                            cudaStream_t s);
 int sparse_align_smem_bytes(int nf_pad);
 size_t sparse_align_ws_doubles(int max_feats);
 cudaError_t sparse_align_init(dsdtm_ctx* c);

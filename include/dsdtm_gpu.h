@@ -80,7 +80,7 @@ typedef struct {
 
 /* Per-stage device timing, filled when profiling is on (CUDA events on the context's stream). */
 enum { DSDTM_STAGE_PYRAMID = 0, DSDTM_STAGE_FAST = 1, DSDTM_STAGE_SPARSE_ALIGN = 2, DSDTM_STAGE_ALIGN2D = 3,
-       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_CAND_PREP = 5, DSDTM_STAGE_LOCAL_MAP = 6, DSDTM_STAGE_INGEST = 7, DSDTM_STAGE_COUNT = 8 };
+       DSDTM_STAGE_WARP_AFFINE = 4, DSDTM_STAGE_CAND_PREP = 5, DSDTM_STAGE_LOCAL_MAP = 6, DSDTM_STAGE_INGEST = 7, DSDTM_STAGE_POSE_OPT = 8, DSDTM_STAGE_COUNT = 9 };
 
 /* ---------------------------------------------------------------- context ---------------------------------- */
 int         dsdtm_abi_version(void);
@@ -264,6 +264,41 @@ int dsdtm_keyframe_lift(dsdtm_ctx* ctx, int depth_slot, const double pose_c2w[7]
  * equalised images back on the host (n * h * w bytes). */
 int dsdtm_frames_upload_clahe_pyramid(dsdtm_ctx* ctx, int first_slot, int n, const uint8_t* imgs, double clip_limit,
                                       int tiles_x, int tiles_y, uint8_t* level0_out);
+
+/* ---------------------------------------------------------------- pose refinement after matching (8f-2) ---- */
+/* Optimizer::PoseOptimization(FramePtr, int) (ref: src/Optimizer.cpp:20-101; residual / Jacobian / parameterisation
+ * ref: include/Optimizer.h:129-258): motion-only bundle adjustment of the current frame over its matched map points -- the
+ * step Tracking runs right after SearchLocalPoints (ref: src/Tracking.cpp:236). The reference delegates to ceres::Solve
+ * (trust-region Levenberg-Marquardt, DENSE_SCHUR, CauchyLoss(1.0), max_num_iterations = 100 -- its tIterations argument is
+ * ignored; pass max_iters = 100 for the same behaviour); the device routine runs that algorithm, one warp per frame.
+ * One record per residual block, i.e. per feature of the frame with Mpt != NULL, !Mpt->IsBad() and mbInitial, in
+ * mvFeatures order (ref: src/Optimizer.cpp:46-68). */
+typedef struct {
+    double  normal[3];   /* Feature::mNormal (the observation is normal.xy / normal.z)   ref: include/Optimizer.h:164-165 */
+    double  point_w[3];  /* Feature::Mpt->Get_Pose()                                     ref: src/Optimizer.cpp:58 */
+    int32_t level;       /* Feature::mlevel: the residual is divided by 1 << level       ref: include/Optimizer.h:167 */
+    int32_t reserved;
+} dsdtm_ba_obs;          /* 56 bytes */
+enum { DSDTM_BA_FUNCTION_TOL = 0, DSDTM_BA_PARAMETER_TOL = 1, DSDTM_BA_GRADIENT_TOL = 2, DSDTM_BA_NO_CONVERGENCE = 3,
+       DSDTM_BA_FAILURE = 4, DSDTM_BA_MIN_RADIUS = 5, DSDTM_BA_NO_RESIDUALS = 6 };
+typedef struct {
+    int32_t iterations;    /* minimizer iterations after iteration 0 (ceres summary.iterations.size() - 1) */
+    int32_t termination;   /* DSDTM_BA_* : which of Ceres' stopping rules ended the solve */
+    int32_t n_successful;  /* accepted steps */
+    int32_t n_obs;
+    double  initial_cost, final_cost;   /* sum over blocks of rho(|r|^2) / 2 */
+} dsdtm_ba_summary;        /* 32 bytes */
+/* n_frames independent frames: frame i owns obs[i * obs_stride .. + n_obs[i]), poses 7 doubles per frame (Frame::Get_Pose()
+ * in, the argument of Frame::Set_Pose() out). res_norm (optional, n_frames * obs_stride): GetReprojectReidual() of the
+ * final problem (ref: src/Optimizer.cpp:298-318), which the caller compares with LocalBAthreshhold / Camera.f to call
+ * MapPoint::EraseFound (ref: :81-94). summaries optional. n_obs[i] <= DSDTM_BA_MAX_OBS. */
+#define DSDTM_BA_MAX_OBS 4096
+int dsdtm_pose_optimize_batch(dsdtm_ctx* ctx, int n_frames, const dsdtm_ba_obs* obs, int obs_stride, const int* n_obs,
+                              const double* poses_in, int max_iters, double* poses_out, double* res_norm,
+                              dsdtm_ba_summary* summaries);
+/* one frame (the call PoseOptimization maps to) */
+int dsdtm_pose_optimize(dsdtm_ctx* ctx, const dsdtm_ba_obs* obs, int n_obs, const double pose_in[7], int max_iters,
+                        double pose_out[7], double* res_norm, dsdtm_ba_summary* summary);
 
 /* ---------------------------------------------------------------- one call per tracked frame ---------------- */
 /* Tracking::Track_RGBDCam's front end for one frame (ref: src/Tracking.cpp:57,199-224) as ONE call with ONE synchronisation:

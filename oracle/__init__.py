@@ -366,3 +366,21 @@ def pair_batch(cam, levels, ref_pyrs, cur_imgs, feats, n_feats, ref_centers, pos
                          _p(np.ascontiguousarray(patch_level, np.int32)), ppp, int(align_iters), int(n_threads),
                          _p(poses_out), _p(n_tracked), _p(px_out), _p(conv))
     return poses_out, n_tracked, px_out, conv
+
+
+BA_SUMMARY_DT = np.dtype([("iterations", "<i4"), ("termination", "<i4"), ("n_successful", "<i4"), ("pad", "<i4"),
+                          ("initial_cost", "<f8"), ("final_cost", "<f8")])
+BA_FUNCTION_TOL, BA_PARAMETER_TOL, BA_GRADIENT_TOL, BA_NO_CONVERGENCE, BA_FAILURE, BA_MIN_RADIUS, BA_NO_RESIDUALS = range(7)
+
+
+def pose_optimization(normals, levels, points_w, pose_in, max_iters=100):
+    """Optimizer::PoseOptimization (ceres::Solve restated). Returns (pose_out[7], res_norm[n], summary record)."""
+    nm = np.ascontiguousarray(normals, np.float64).reshape(-1, 3)
+    lv = np.ascontiguousarray(levels, np.int32).reshape(-1)
+    pw = np.ascontiguousarray(points_w, np.float64).reshape(-1, 3)
+    assert len(nm) == len(lv) == len(pw)
+    out = np.zeros(7); res = np.zeros(len(lv)); summ = np.zeros(1, BA_SUMMARY_DT)
+    f = lib().orc_pose_optimization
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(len(lv), _p(nm), _p(lv), _p(pw), _p(np.ascontiguousarray(pose_in, np.float64)), int(max_iters), _p(out), _p(res), _p(summ))
+    return out, res, summ[0]

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <thread>
 #include <vector>
 
@@ -939,6 +940,329 @@ int orc_align2d(const uint8_t* img, int w, int h, int stride, const uint8_t p10[
     px[0] = u; px[1] = v;
     if (n_iters_out) *n_iters_out = it_count;
     return converged ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Optimizer::PoseOptimization. ref: src/Optimizer.cpp:20-101, include/Optimizer.h:129-258.
+//
+// The reference hands the problem to ceres::Solve (ceres-solver is a find_package dependency, CMakeLists.txt:23, version
+// unpinned, not under /root/reference and not installed here) with: one 6-vector parameter block [t, log(R)] carrying
+// PoseLocalParameterization (Plus = left multiplication by SE3(SO3::exp(d[3..5]), d[0..2]), ComputeJacobian = identity),
+// one constant 3-vector block per map point, FullBA_Problem residuals (2 rows) under CauchyLoss(1.0), DENSE_SCHUR,
+// max_num_iterations = 100 (the tIterations argument is ignored), everything else at Solver::Options defaults.
+// What is restated below is ceres-solver's published trust-region algorithm for exactly that configuration
+// (1.10 .. 1.14 agree on it; file names of 1.13): trust_region_minimizer.cc (IterationZero, the main loop, the three
+// tolerances, Jacobi scaling 1/(1+sqrt(colnorm2)) fixed at iteration 0), levenberg_marquardt_strategy.cc (D = sqrt(clamp(
+// diag(J'J),1e-6,1e32)/radius), radius /= max(1/3, 1-(2q-1)^3) on success, radius /= decrease_factor (2,4,8..) on
+// failure), residual_block.cc + corrector.cc (cost = rho(s)/2; rho'' <= 0 for Cauchy => residual and Jacobian are both
+// scaled by sqrt(rho')), loss_function.cc (CauchyLoss), schur_eliminator_impl.h with one e-block and no f-block
+// (step = LLT-inverse(D^2 + sum e'e) * sum e'b), program_evaluator.h (sequential sums, num_threads = 1).
+// PARITY UNPINNED: no golden value exists in the reference (Test/test_Optimizer.cpp prints nothing checkable).
+// Self-consistency checks live in tests/test_oracle_golden.py (scipy least_squares(loss='cauchy') reaches the same optimum).
+// ------------------------------------------------------------------------------------------
+namespace {
+
+const double SOPHUS_SMALL_EPS = 1e-10;
+
+Quat so3_exp(const double om[3])  // Sophus SO3::expAndTheta (so3.cpp), then the normalising SO3(Quaternion) constructor
+{
+    const double theta = std::sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    const double half = 0.5 * theta;
+    double imag;
+    const double real = std::cos(half);
+    if (theta < SOPHUS_SMALL_EPS) {
+        const double t2 = theta * theta, t4 = t2 * t2;
+        imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
+    } else {
+        imag = std::sin(half) / theta;
+    }
+    Quat q = { real, imag * om[0], imag * om[1], imag * om[2] };
+    qnormalize(q);
+    return q;
+}
+
+void so3_log(const Quat& q, double out[3])  // Sophus SO3::logAndTheta (atan-based; the |w| < eps branch is overwritten there too)
+{
+    const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+    const double w = q.w;
+    const double squared_w = w * w;
+    double f;
+    if (n < SOPHUS_SMALL_EPS) f = 2. / w - 2. * (n * n) / (w * squared_w);
+    else f = 2 * std::atan(n / w) / n;
+    out[0] = f * q.x; out[1] = f * q.y; out[2] = f * q.z;
+}
+
+struct PoseBA {
+    int n;
+    const double* normals;   // Feature::mNormal
+    const int* levels;       // Feature::mlevel
+    const double* points;    // MapPoint::Get_Pose()
+    std::vector<double> J;   // n x 2 x 6 row-major, loss-corrected (and column-scaled once scaled() ran)
+    std::vector<double> r;   // n x 2, loss-corrected
+    double grad[6];
+
+    // FullBA_Problem::Evaluate (ref: include/Optimizer.h:141-205) on residual block k; raw residual and, if wanted, raw Jacobian
+    void block(const Quat& q, const double t[3], int k, double res[2], double* jac) const
+    {
+        double c[3];
+        qrot(q, points + 3 * k, c);
+        c[0] += t[0]; c[1] += t[1]; c[2] += t[2];
+        const double pred[2] = { c[0] / c[2], c[1] / c[2] };
+        const double* nm = normals + 3 * k;
+        const double obs[2] = { nm[0] / nm[2], nm[1] / nm[2] };
+        const double div = (double)(1 << levels[k]);
+        res[0] = (obs[0] - pred[0]) / div;
+        res[1] = (obs[1] - pred[1]) / div;
+        if (jac) {
+            const double x = c[0], y = c[1];
+            const double z_inv = 1.0 / c[2];
+            const double z_inv2 = z_inv * z_inv;
+            jac[0] = -z_inv; jac[1] = 0.0; jac[2] = x * z_inv2; jac[3] = y * jac[2]; jac[4] = -(1.0 + x * jac[2]); jac[5] = y * z_inv;
+            jac[6] = 0.0; jac[7] = -z_inv; jac[8] = y * z_inv2; jac[9] = 1.0 + y * jac[8]; jac[10] = -x * jac[8]; jac[11] = -x * z_inv;
+        }
+    }
+    // ProgramEvaluator::Evaluate: cost (and, with want_jac, corrected residuals / Jacobian / gradient). false on non-finite values.
+    bool evaluate(const double x[6], bool want_jac, double* cost)
+    {
+        const Quat q = so3_exp(x + 3);
+        double c = 0.0;
+        if (want_jac) for (int i = 0; i < 6; ++i) grad[i] = 0.0;
+        for (int k = 0; k < n; ++k) {
+            double res[2];
+            double* jac = want_jac ? &J[12 * (size_t)k] : nullptr;
+            block(q, x, k, res, jac);
+            const double s = res[0] * res[0] + res[1] * res[1];
+            // CauchyLoss(1.0): b = 1, c = 1
+            const double sum = 1.0 + s * 1.0;
+            const double inv = 1.0 / sum;
+            const double rho0 = 1.0 * std::log(sum);
+            const double rho1 = std::max(std::numeric_limits<double>::min(), inv);
+            c += 0.5 * rho0;
+            if (!std::isfinite(rho0)) return false;
+            if (want_jac) {
+                const double sqrt_rho1 = std::sqrt(rho1);   // Corrector: rho[2] = -inv*inv <= 0 => alpha = 0, scaling = sqrt(rho')
+                for (int i = 0; i < 12; ++i) jac[i] *= sqrt_rho1;
+                r[2 * k] = res[0] * sqrt_rho1; r[2 * k + 1] = res[1] * sqrt_rho1;
+                for (int col = 0; col < 6; ++col) {
+                    double tmp = 0.0;
+                    tmp += jac[col] * r[2 * k];
+                    tmp += jac[6 + col] * r[2 * k + 1];
+                    grad[col] += tmp;
+                }
+            }
+        }
+        *cost = c;
+        return std::isfinite(c);
+    }
+};
+
+// PoseLocalParameterization::Plus (ref: include/Optimizer.h:220-236)
+void pose_plus(const double x[6], const double d[6], double out[6])
+{
+    Se3 told, tdelta;
+    told.q = so3_exp(x + 3); told.t[0] = x[0]; told.t[1] = x[1]; told.t[2] = x[2];
+    tdelta.q = so3_exp(d + 3); tdelta.t[0] = d[0]; tdelta.t[1] = d[1]; tdelta.t[2] = d[2];
+    const Se3 tnew = se3_mul(tdelta, told);
+    out[0] = tnew.t[0]; out[1] = tnew.t[1]; out[2] = tnew.t[2];
+    so3_log(tnew.q, out + 3);
+}
+
+// Eigen LLT (lower, unblocked) of a 6x6 SPD matrix, then M^-1 = llt.solve(I) and y = M^-1 g (InvertPSDMatrix + product)
+bool llt6_inverse_times(const double M[36], const double g[6], double y[6])
+{
+    double L[36];
+    std::memcpy(L, M, sizeof(L));
+    for (int k = 0; k < 6; ++k) {
+        double x = L[k * 6 + k];
+        for (int j = 0; j < k; ++j) x -= L[k * 6 + j] * L[k * 6 + j];
+        if (!(x > 0.0)) return false;
+        x = std::sqrt(x);
+        L[k * 6 + k] = x;
+        for (int i = k + 1; i < 6; ++i) {
+            double s = L[i * 6 + k];
+            for (int j = 0; j < k; ++j) s -= L[i * 6 + j] * L[k * 6 + j];
+            L[i * 6 + k] = s / x;
+        }
+    }
+    double inv[36];
+    for (int c = 0; c < 6; ++c) {
+        double v[6];
+        for (int i = 0; i < 6; ++i) v[i] = (i == c) ? 1.0 : 0.0;
+        for (int i = 0; i < 6; ++i) { for (int j = 0; j < i; ++j) v[i] -= L[i * 6 + j] * v[j]; v[i] /= L[i * 6 + i]; }
+        for (int i = 5; i >= 0; --i) { for (int j = i + 1; j < 6; ++j) v[i] -= L[j * 6 + i] * v[j]; v[i] /= L[i * 6 + i]; }
+        for (int i = 0; i < 6; ++i) inv[i * 6 + c] = v[i];
+    }
+    for (int i = 0; i < 6; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < 6; ++j) s += inv[i * 6 + j] * g[j];
+        y[i] = s;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" int orc_pose_optimization(int n_obs, const double* normals, const int* levels, const double* points_w,
+                                     const double pose_in[7], int max_iters, double pose_out[7], double* res_norm,
+                                     orc_ba_summary* summary)
+{
+    const double kFunctionTol = 1e-6, kGradientTol = 1e-10, kParameterTol = 1e-8, kMinRelDecrease = 1e-3;
+    const double kMinDiag = 1e-6, kMaxDiag = 1e32, kMaxRadius = 1e16, kMinRadius = 1e-32;
+    const int kMaxInvalid = 5;
+    orc_ba_summary sm;
+    std::memset(&sm, 0, sizeof sm);
+
+    // ref: src/Optimizer.cpp:34-36
+    const Se3 T0 = se3_from(pose_in);
+    double x[6] = { T0.t[0], T0.t[1], T0.t[2], 0, 0, 0 };
+    so3_log(T0.q, x + 3);
+
+    PoseBA ba;
+    ba.n = n_obs; ba.normals = normals; ba.levels = levels; ba.points = points_w;
+    ba.J.resize(12 * (size_t)std::max(n_obs, 1)); ba.r.resize(2 * (size_t)std::max(n_obs, 1));
+
+    auto finish = [&](int term) {
+        sm.termination = term;
+        // ref: src/Optimizer.cpp:79
+        Se3 T; T.q = so3_exp(x + 3); T.t[0] = x[0]; T.t[1] = x[1]; T.t[2] = x[2];
+        se3_to(T, pose_out);
+        // ref: src/Optimizer.cpp:298-318 GetReprojectReidual: raw residual norm of every block at the final parameters
+        if (res_norm)
+            for (int k = 0; k < n_obs; ++k) {
+                double res[2];
+                ba.block(T.q, x, k, res, nullptr);
+                res_norm[k] = std::sqrt(res[0] * res[0] + res[1] * res[1]);
+            }
+        if (summary) *summary = sm;
+        return term;
+    };
+
+    if (n_obs == 0) return finish(ORC_BA_NO_RESIDUALS);   // Ceres: "No non-constant parameter blocks found" => parameters untouched
+
+    // ---- IterationZero
+    double x_cost = 0.0;
+    if (!ba.evaluate(x, true, &x_cost)) { sm.initial_cost = sm.final_cost = x_cost; return finish(ORC_BA_FAILURE); }
+    sm.initial_cost = sm.final_cost = x_cost;
+    double scale[6];
+    for (int c = 0; c < 6; ++c) {
+        double s = 0.0;
+        for (int k = 0; k < 2 * n_obs; ++k) s += ba.J[6 * (size_t)k + c] * ba.J[6 * (size_t)k + c];
+        scale[c] = 1.0 / (1.0 + std::sqrt(s));
+    }
+    auto scale_columns = [&]() { for (int k = 0; k < 2 * n_obs; ++k) for (int c = 0; c < 6; ++c) ba.J[6 * (size_t)k + c] *= scale[c]; };
+    scale_columns();
+    auto gradient_max_norm = [&]() {
+        double ng[6], proj[6];
+        for (int i = 0; i < 6; ++i) ng[i] = -ba.grad[i];
+        pose_plus(x, ng, proj);
+        double m = 0.0;
+        for (int i = 0; i < 6; ++i) m = std::max(m, std::fabs(x[i] - proj[i]));
+        return m;
+    };
+    double gmax = gradient_max_norm();
+    double x_norm = 0.0; for (int i = 0; i < 6; ++i) x_norm += x[i] * x[i]; x_norm = std::sqrt(x_norm);
+
+    double radius = 1e4, decrease_factor = 2.0;
+    bool reuse_diagonal = false;
+    double diagonal[6];
+    int n_invalid = 0;
+    bool last_successful = true;   // IterationZero ends with step_is_successful = true
+    int iteration = 0;
+
+    for (;;) {
+        // ---- FinalizeIterationAndCheckIfMinimizerCanContinue
+        if (iteration >= max_iters) return finish(ORC_BA_NO_CONVERGENCE);
+        if (last_successful && gmax <= kGradientTol) return finish(ORC_BA_GRADIENT_TOL);
+        if (radius < kMinRadius) return finish(ORC_BA_MIN_RADIUS);
+        ++iteration;
+        sm.iterations = iteration;
+        last_successful = false;
+
+        // ---- LevenbergMarquardtStrategy::ComputeStep
+        if (!reuse_diagonal) {
+            for (int c = 0; c < 6; ++c) {
+                double s = 0.0;
+                for (int k = 0; k < 2 * n_obs; ++k) s += ba.J[6 * (size_t)k + c] * ba.J[6 * (size_t)k + c];
+                diagonal[c] = std::min(std::max(s, kMinDiag), kMaxDiag);
+            }
+        }
+        double D[6];
+        for (int c = 0; c < 6; ++c) D[c] = std::sqrt(diagonal[c] / radius);
+        reuse_diagonal = true;
+        // SchurEliminator::BackSubstitute with the single e-block: ete = D^2 + sum e'e ; y = ete^-1 sum e'b
+        double ete[36], g[6];
+        for (int i = 0; i < 36; ++i) ete[i] = 0.0;
+        for (int c = 0; c < 6; ++c) { ete[7 * c] = D[c] * D[c]; g[c] = 0.0; }
+        for (int k = 0; k < n_obs; ++k) {
+            const double* e = &ba.J[12 * (size_t)k];
+            for (int c = 0; c < 6; ++c) {
+                double tmp = 0.0;
+                tmp += e[c] * ba.r[2 * k];
+                tmp += e[6 + c] * ba.r[2 * k + 1];
+                g[c] += tmp;
+            }
+            for (int a = 0; a < 6; ++a)
+                for (int b = 0; b < 6; ++b) {
+                    double tmp = 0.0;
+                    tmp += e[a] * e[b];
+                    tmp += e[6 + a] * e[6 + b];
+                    ete[a * 6 + b] += tmp;
+                }
+        }
+        double step[6];
+        bool valid = llt6_inverse_times(ete, g, step);
+        for (int c = 0; c < 6; ++c) { if (!std::isfinite(step[c])) valid = false; step[c] = -step[c]; }
+        double model_cost_change = 0.0;
+        if (valid) {
+            // model_cost_change = -(J step)'(f + J step / 2)
+            double acc = 0.0;
+            for (int k = 0; k < 2 * n_obs; ++k) {
+                double m = 0.0;
+                for (int c = 0; c < 6; ++c) m += ba.J[6 * (size_t)k + c] * step[c];
+                acc += m * (ba.r[k] + m / 2.0);
+            }
+            model_cost_change = -acc;
+            valid = model_cost_change > 0.0;
+        }
+        if (!valid) {
+            // HandleInvalidStep
+            if (++n_invalid >= kMaxInvalid) return finish(ORC_BA_FAILURE);
+            radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+            continue;
+        }
+        n_invalid = 0;
+        double delta[6], cand[6];
+        for (int c = 0; c < 6; ++c) delta[c] = step[c] * scale[c];
+        pose_plus(x, delta, cand);
+        double cand_cost = 0.0;
+        if (!ba.evaluate(cand, false, &cand_cost)) cand_cost = std::numeric_limits<double>::max();
+
+        // ---- ParameterToleranceReached / FunctionToleranceReached (the candidate is NOT taken when they fire)
+        double step_norm = 0.0; for (int c = 0; c < 6; ++c) step_norm += (x[c] - cand[c]) * (x[c] - cand[c]); step_norm = std::sqrt(step_norm);
+        if (step_norm <= kParameterTol * (x_norm + kParameterTol)) return finish(ORC_BA_PARAMETER_TOL);
+        const double cost_change = x_cost - cand_cost;
+        if (std::fabs(cost_change) <= kFunctionTol * x_cost) return finish(ORC_BA_FUNCTION_TOL);
+
+        const double relative_decrease = cost_change / model_cost_change;
+        if (relative_decrease > kMinRelDecrease) {
+            // HandleSuccessfulStep
+            for (int c = 0; c < 6; ++c) x[c] = cand[c];
+            x_norm = 0.0; for (int i = 0; i < 6; ++i) x_norm += x[i] * x[i]; x_norm = std::sqrt(x_norm);
+            if (!ba.evaluate(x, true, &x_cost)) return finish(ORC_BA_FAILURE);
+            scale_columns();
+            gmax = gradient_max_norm();
+            sm.final_cost = x_cost;
+            sm.n_successful++;
+            last_successful = true;
+            const double q = 2.0 * relative_decrease - 1.0;
+            radius = radius / std::max(1.0 / 3.0, 1.0 - q * q * q);
+            radius = std::min(kMaxRadius, radius);
+            decrease_factor = 2.0;
+            reuse_diagonal = false;
+        } else {
+            radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------

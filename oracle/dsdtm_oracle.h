@@ -148,6 +148,24 @@ void orc_unproject(const orc_cam* cam, const double pose_c2w[7], const float px[
  * PINNED against cv2 4.13 goldens (tests/golden/clahe_cv2.npz). */
 void orc_clahe(const uint8_t* src, int w, int h, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst);
 
+/* ---- Optimizer::PoseOptimization (ref: src/Optimizer.cpp:20-101, include/Optimizer.h:129-258) ----
+ * ceres::Solve with the reference's configuration restated (trust-region Levenberg-Marquardt, DENSE_SCHUR on the single pose
+ * block, CauchyLoss(1.0), PoseLocalParameterization, 100 iterations; see the .cpp). PARITY UNPINNED (Ceres is neither under
+ * /root/reference nor installed; the reference holds no golden value). normals = Feature::mNormal (3 per observation),
+ * levels = Feature::mlevel, points_w = MapPoint::Get_Pose(); res_norm[k] = GetReprojectReidual()[k] at the final pose. */
+enum { ORC_BA_FUNCTION_TOL = 0, ORC_BA_PARAMETER_TOL = 1, ORC_BA_GRADIENT_TOL = 2, ORC_BA_NO_CONVERGENCE = 3,
+       ORC_BA_FAILURE = 4, ORC_BA_MIN_RADIUS = 5, ORC_BA_NO_RESIDUALS = 6 };
+typedef struct {
+    int    iterations;      /* minimizer iterations after iteration 0 (summary.iterations.size() - 1) */
+    int    termination;     /* ORC_BA_* */
+    int    n_successful;    /* accepted steps */
+    int    pad;
+    double initial_cost, final_cost;
+} orc_ba_summary;
+int orc_pose_optimization(int n_obs, const double* normals, const int* levels, const double* points_w,
+                          const double pose_in[7], int max_iters, double pose_out[7], double* res_norm,
+                          orc_ba_summary* summary);
+
 /* Batched CPU driver used only for the cpu_baseline / reference bench arm: runs pyramid(cur) +
  * sparse align + align2d for pairs [0,n) with n_threads std::threads. Layout documented in bench.py. */
 int orc_pair_batch(const orc_cam* cam, int levels, const uint8_t* ref_pyrs, const uint8_t* cur_imgs, int n_pairs,

@@ -1,0 +1,130 @@
+"""CPU suite for SURVEY 8f-2 (Optimizer::PoseOptimization, ref: src/Optimizer.cpp:20-101):
+* the oracle's restatement of ceres::Solve for the reference's configuration reaches the optimum of the Cauchy cost that an
+  independent minimiser (scipy BFGS on the same cost) finds -- the only anchor available: Ceres is neither under the reference
+  root nor installed and the reference holds no golden value (PARITY UNPINNED);
+* the product routine (dsdtm_b200/csrc/pose_opt.cuh, compiled for the host with the serial lane policy -- the very source the
+  kernel runs) takes the same decisions as the oracle (iterations, accepted steps, stopping rule) and lands on the same pose."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle as O
+from dsdtm_b200 import synth as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BA_OBS_DT = np.dtype([("normal", "<f8", 3), ("point_w", "<f8", 3), ("level", "<i4"), ("reserved", "<i4")])
+BA_SUMMARY_DT = np.dtype([("iterations", "<i4"), ("termination", "<i4"), ("n_successful", "<i4"), ("n_obs", "<i4"),
+                          ("initial_cost", "<f8"), ("final_cost", "<f8")])
+
+
+@pytest.fixture(scope="module")
+def prod():
+    d = os.path.join(ROOT, "tests", "cpp", "_build")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, "libpose_opt_host.so")
+    src = os.path.join(ROOT, "tests", "cpp", "pose_opt_host.cpp")
+    deps = [src, os.path.join(ROOT, "dsdtm_b200", "csrc", "pose_opt.cuh"), os.path.join(ROOT, "include", "dsdtm_gpu.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+    lib = C.CDLL(so)
+    lib.prod_pose_optimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def run(pr, max_iters=100):
+        o = H.ba_obs_records(pr, BA_OBS_DT)
+        out = np.zeros(7); res = np.zeros(len(o)); sm = np.zeros(1, BA_SUMMARY_DT)
+        lib.prod_pose_optimize(len(o), o.ctypes.data, np.ascontiguousarray(pr["pose_in"]).ctypes.data, max_iters, out.ctypes.data,
+                               res.ctypes.data, sm.ctypes.data)
+        return out, res, sm[0]
+    return run
+
+
+def _orc(pr, max_iters=100):
+    return O.pose_optimization(pr["normals"], pr["levels"], pr["points_w"], pr["pose_in"], max_iters)
+
+
+def _cost(pr, pose):
+    Rm = S.quat_to_R(pose[:4])
+    c = pr["points_w"] @ Rm.T + pose[4:]
+    obs = pr["normals"][:, :2] / pr["normals"][:, 2:3]
+    r = (obs - c[:, :2] / c[:, 2:3]) / (1 << pr["levels"])[:, None]
+    return 0.5 * np.log1p((r ** 2).sum(1)).sum(), np.sqrt((r ** 2).sum(1))
+
+
+def test_oracle_reaches_the_minimum_an_independent_minimiser_finds():
+    from scipy.optimize import minimize
+    from scipy.spatial.transform import Rotation as Rot
+    for seed in range(6):
+        pr = H.make_ba_problem(seed, n=200, max_level=0)          # level 0: the reference's Jacobian is the true derivative
+        pose, res, sm = _orc(pr)
+        assert sm["termination"] == O.BA_FUNCTION_TOL and 2 <= sm["iterations"] <= 10
+        assert sm["final_cost"] < sm["initial_cost"]
+        c_ours, r_ours = _cost(pr, pose)
+        assert abs(c_ours - sm["final_cost"]) <= 1e-12 * max(1.0, c_ours)
+        assert np.abs(r_ours - res).max() < 1e-14                   # GetReprojectReidual
+
+        def f(p):
+            q = Rot.from_rotvec(p[3:]).as_quat()
+            return _cost(pr, np.r_[q[3], q[:3], p[:3]])[0]
+        p0 = np.r_[pr["pose_in"][4:], Rot.from_quat(np.r_[pr["pose_in"][1:4], pr["pose_in"][0]]).as_rotvec()]
+        m = minimize(f, p0, method="BFGS", options=dict(gtol=1e-12))
+        assert c_ours - m.fun < 1e-6 * m.fun                        # Ceres stops at a relative cost change of 1e-6
+        pf = np.r_[pose[4:], Rot.from_quat(np.r_[pose[1:4], pose[0]]).as_rotvec()]
+        assert np.abs(pf - m.x).max() < 2e-5
+
+
+def test_oracle_stopping_rules_and_edge_cases():
+    pr = H.make_ba_problem(11, n=120)
+    # the iteration cap (ceres max_num_iterations): the pose is the last ACCEPTED one
+    p1, _, s1 = _orc(pr, max_iters=1)
+    assert s1["termination"] == O.BA_NO_CONVERGENCE and s1["iterations"] == 1 and s1["n_successful"] == 1
+    p0, _, s0 = _orc(pr, max_iters=0)
+    assert s0["termination"] == O.BA_NO_CONVERGENCE and s0["iterations"] == 0
+    assert np.abs(p0 - pr["pose_in"]).max() < 1e-15                 # exp(log(R)) round trip only
+    # no residual block: Ceres leaves the parameters alone
+    e = dict(normals=np.zeros((0, 3)), levels=np.zeros(0, np.int32), points_w=np.zeros((0, 3)), pose_in=pr["pose_in"])
+    pe, re_, se = _orc(e)
+    assert se["termination"] == O.BA_NO_RESIDUALS and np.abs(pe - pr["pose_in"]).max() < 1e-15 and len(re_) == 0
+    # exact data: the gradient rule (or the function rule at cost ~ 0) ends it at the truth
+    ex = H.make_ba_problem(8, n=64, noise=0.0, outliers=0.0, start_rot=0.02, start_trans=0.05)
+    px, rx, sx = _orc(ex)
+    assert np.abs(px - ex["truth"]).max() < 1e-7 and rx.max() < 1e-7
+    # a far start goes through rejected steps (iterations > accepted steps) and still converges
+    far = H.make_ba_problem(2, n=33, max_level=1, start_rot=0.3, start_trans=1.0)
+    pf, _, sf = _orc(far)
+    assert sf["iterations"] > sf["n_successful"] + 1 and sf["final_cost"] < sf["initial_cost"]
+
+
+@pytest.mark.parametrize("case", H.BA_CASES)
+def test_product_routine_takes_the_oracles_decisions(prod, case):
+    seed, n, noise, outl, lvl, srot, strans = case
+    pr = H.make_ba_problem(seed, n=n, noise=noise, outliers=outl, max_level=lvl, start_rot=srot, start_trans=strans)
+    a, ra, sa = _orc(pr)
+    b, rb, sb = prod(pr)
+    assert (sb["iterations"], sb["termination"], sb["n_successful"]) == (sa["iterations"], sa["termination"], sa["n_successful"])
+    assert sb["n_obs"] == n
+    # rounding-only differences: J'J scaled after accumulation, Cholesky substitution instead of the explicit inverse
+    assert np.abs(a - b).max() < 1e-9 and np.abs(ra - rb).max() < 1e-9
+    assert abs(sa["final_cost"] - sb["final_cost"]) <= 1e-9 * max(1.0, sa["final_cost"])
+    assert abs(sa["initial_cost"] - sb["initial_cost"]) <= 1e-12 * max(1.0, sa["initial_cost"])
+
+
+def test_product_routine_many_seeds_and_caps(prod):
+    for seed in range(100, 160):
+        pr = H.make_ba_problem(seed, n=[200, 300, 37, 5, 1, 500][seed % 6], max_level=[0, 3][seed % 2], noise=[1e-3, 1e-2][(seed // 2) % 2],
+                               outliers=[0.1, 0.4][(seed // 4) % 2], start_trans=[0.02, 0.5][seed % 7 == 0])
+        a, _, sa = _orc(pr)
+        b, _, sb = prod(pr)
+        assert (sb["iterations"], sb["termination"], sb["n_successful"]) == (sa["iterations"], sa["termination"], sa["n_successful"]), seed
+        assert np.abs(a - b).max() < 1e-9, seed
+    pr = H.make_ba_problem(3, n=150, max_level=3)
+    for cap in (0, 1, 2, 5):
+        a, _, sa = _orc(pr, cap)
+        b, _, sb = prod(pr, cap)
+        assert (sb["iterations"], sb["termination"]) == (sa["iterations"], sa["termination"]) and np.abs(a - b).max() < 1e-10
+    e = dict(normals=np.zeros((0, 3)), levels=np.zeros(0, np.int32), points_w=np.zeros((0, 3)), pose_in=pr["pose_in"])
+    b, rb, sb = prod(e)
+    assert sb["termination"] == O.BA_NO_RESIDUALS and np.abs(b - pr["pose_in"]).max() < 1e-15
