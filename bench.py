@@ -355,6 +355,50 @@ def run_ours(args):
         ctx.profile(False)
     restage()
 
+    # ---------------- pose refinement after matching (Optimizer::PoseOptimization), not part of the step
+    pose_opt = None
+    if rank == 0:
+        try:
+            nf_po = min(B, 4096)
+            base_po = [W.make_ba_problem(300 + i, n=N_FEATS, max_level=i % 4) for i in range(16)]
+            rec = []
+            for pr in base_po:
+                o = np.zeros(N_FEATS, capi.BA_OBS_DT)
+                o["normal"] = pr["normals"]; o["point_w"] = pr["points_w"]; o["level"] = pr["levels"]
+                rec.append(o)
+            obs_po = np.stack([rec[i % 16] for i in range(nf_po)])
+            nobs_po = np.full(nf_po, N_FEATS, np.int32)
+            poses_po = np.stack([base_po[i % 16]["pose_in"] for i in range(nf_po)])
+            ctx.pose_optimize_batch(obs_po, nobs_po, poses_po)
+            ctx.profile(True); ctx.profile_get(reset=True)
+            for _ in range(5):
+                _, _, sm_po = ctx.pose_optimize_batch(obs_po, nobs_po, poses_po, want_res=False)
+            st = ctx.profile_get(reset=True)
+            po_ms = st["pose_opt"][0] / max(st["pose_opt"][1], 1)
+            for _ in range(5):
+                ctx.pose_optimize(obs_po[0], poses_po[0])
+            ctx.profile_get(reset=True)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                _, _, s1_po = ctx.pose_optimize(obs_po[0], poses_po[0])
+            po_call_us = (time.perf_counter() - t0) / reps * 1e6
+            st = ctx.profile_get(reset=True)
+            import oracle as O_po                                   # cpu_baseline leg: the oracle port, one thread, bounded sample
+            t0 = time.perf_counter()
+            for i in range(16):
+                O_po.pose_optimization(base_po[i]["normals"], base_po[i]["levels"], base_po[i]["points_w"], base_po[i]["pose_in"])
+            po_cpu_us = (time.perf_counter() - t0) / 16 * 1e6
+            pose_opt = {"ms_per_launch": po_ms, "frames": nf_po, "observations": N_FEATS, "frames_per_s": nf_po / (po_ms * 1e-3),
+                        "lm_iterations_per_frame": float(sm_po["iterations"].mean()),
+                        "one_frame": {"kernel_us": st["pose_opt"][0] / max(st["pose_opt"][1], 1) * 1e3, "call_us": po_call_us,
+                                      "lm_iterations": int(s1_po["iterations"])},
+                        "cpu_port_us_per_frame": po_cpu_us,
+                        "note": "motion-only BA over 300 matches per frame (ceres::Solve configuration of the reference restated): sweep = one warp "
+                                "per frame, one frame = a CTA of eight warps; latency-bound dependent chain, not part of the step; cpu = oracle port, "
+                                "1 thread, 16 frames"}
+        finally:
+            ctx.profile(False)
+
     # ---------------- end-to-end through the C-ABI with host buffers
     h, w = cam["height"], cam["width"]
     pin = capi.pinned_empty
@@ -457,7 +501,8 @@ def run_ours(args):
                 "fast_cells": {"ms_per_launch": fast_ms, "frames": nfast, "GBps": fast_bytes / (fast_ms * 1e-3) / 1e9 if fast_ms else None,
                                "frac_hbm": fast_bytes / (fast_ms * 1e-3) / 1e9 / hbm_peak if fast_ms else None, "algorithmic_bytes": fast_bytes,
                                "note": "keyframe-only stage, not part of the step"},
-                "ingest": ingest},
+                "ingest": ingest,
+                "pose_opt": pose_opt},
             "cpu_baseline": cpu,
             "prep_s": prep_s,
         }

@@ -364,6 +364,11 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
+    if (std::strcmp(key, "pose_opt_solo_max") == 0) {
+        if (value < -1) return fail(c, DSDTM_E_ARG, "pose_opt_solo_max must be -1 (default: 2 x SM count), 0 (always one warp per frame) or a frame count");
+        c->po_solo_max = value;
+        return 0;
+    }
     if (std::strcmp(key, "depth_slots") == 0) {
         if (value < 1 || value > 65536) return fail(c, DSDTM_E_ARG, "depth_slots must be 1..65536");
         if (c->depth_d) return fail(c, DSDTM_E_ARG, "depth_slots must be set before the depth pool is first used");

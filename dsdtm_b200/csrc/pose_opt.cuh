@@ -15,10 +15,12 @@
 //   * accept when cost change / model change > 1e-3: radius /= max(1/3, 1 - (2q - 1)^3); otherwise radius /= 2, 4, 8, ...
 //
 // B200 mapping: the work per iteration is one pass over <= a few hundred observations producing 28 sums (cost, J'f, the 21
-// unique entries of J'J) followed by a 6 x 6 factorisation. One WARP owns a frame: observations are strided over the lanes
-// (staged once as structure-of-arrays in shared memory: observation, 2^-level, point), the 28 sums are reduced with xor-shuffle
-// butterflies (bitwise identical in all lanes, so every lane runs the scalar tail redundantly and no broadcast or barrier is
-// needed), and the candidate pass accumulates J'J and J'f speculatively so that an accepted step costs no second pass.
+// unique entries of J'J) followed by a 6 x 6 factorisation: a dependent chain, latency-bound. Observations are strided over the
+// threads that own the frame (staged once as structure-of-arrays in shared memory: observation, 2^-level, point), the 28 sums
+// are reduced with xor-shuffle butterflies (+ one shared-memory exchange when several warps own the frame) that leave identical
+// bits in every thread, so every thread runs the scalar tail redundantly and no broadcast is needed, and the candidate pass
+// accumulates J'J and J'f speculatively so that an accepted step costs no second pass. A sweep gives each frame ONE warp (the
+// other resident warps hide its chain); a lone frame gets a CTA of eight warps (the pass is eight times shorter).
 // Differences from Ceres' arithmetic are rounding only (documented in DESIGN.md): sums are per lane then tree instead of
 // sequential, J'J is accumulated unscaled and scaled afterwards, the system is solved by Cholesky substitution instead of
 // forming the inverse. The routine is __host__ __device__ (lane policy SerialLanes) so the CPU suite checks the same source
@@ -38,24 +40,66 @@
 
 namespace dsdtm {
 
+// Lane policies: how the observations of one frame are spread over threads and how the per-thread partial sums meet.
+// sum_n leaves the SAME bits in every participating thread, so the scalar tail runs redundantly and control flow stays uniform.
 struct SerialLanes {
     DSDTM_PO_HD int lane() const { return 0; }
     DSDTM_PO_HD int count() const { return 1; }
-    DSDTM_PO_HD double sum(double v) const { return v; }
+    template <int N> DSDTM_PO_HD void sum_n(double (&)[N]) const {}
     DSDTM_PO_HD void sync() const {}
 };
 
 #if defined(__CUDACC__)
+// one warp per frame (sweeps: the other resident warps hide this warp's dependent chain)
 struct WarpLanes {
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
     __device__ __forceinline__ int count() const { return 32; }
-    __device__ __forceinline__ double sum(double v) const
+    template <int N> __device__ __forceinline__ void sum_n(double (&v)[N]) const
     {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
     }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+// one CTA of kWarps warps per frame (a lone frame: the pass over the observations is kWarps times shorter). Per-warp butterflies,
+// then the warp sums meet in shared memory and every thread adds them in warp order; two buffers alternate so that one
+// __syncthreads per reduction suffices.
+template <int kWarps, int kMaxN>
+struct CtaLanes {
+    double* buf;            // 2 * kWarps * kMaxN doubles of shared memory
+    mutable int phase = 0;
+    __device__ __forceinline__ explicit CtaLanes(double* b) : buf(b) {}
+    __device__ __forceinline__ int lane() const { return threadIdx.x; }
+    __device__ __forceinline__ int count() const { return 32 * kWarps; }
+    template <int N> __device__ __forceinline__ void sum_n(double (&v)[N]) const
+    {
+        static_assert(N <= kMaxN && N <= 32, "reduction buffer too small");
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        double* b = buf + phase * (kWarps * kMaxN);
+        phase ^= 1;
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) b[w * kMaxN + i] = v[i];
+        }
+        __syncthreads();
+        // lane i of every warp adds the kWarps partial sums of value i in warp order, then hands the total to the whole warp
+        const int l = threadIdx.x & 31;
+        double tot = 0.0;
+        if (l < N) {
+            tot = b[l];
+#pragma unroll
+            for (int k = 1; k < kWarps; ++k) tot += b[k * kMaxN + l];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = __shfl_sync(0xffffffffu, tot, i);
+    }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 #endif
 
@@ -63,22 +107,41 @@ namespace po {
 
 static constexpr double kSmallEps = 1e-10;   // Sophus SMALL_EPS
 
+// The scalar tail is one dependent fp64 chain per iteration; a division costs ~10 dependent instructions, so denominators
+// shared by several quotients are inverted once (1 ulp away from the reference's quotients; covered by the stated tolerance).
+DSDTM_PO_HD double po_rsqrt(double v)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrt(v);
+#else
+    return 1.0 / sqrt(v);
+#endif
+}
+DSDTM_PO_HD void po_sincos(double a, double* s, double* c)
+{
+#if defined(__CUDA_ARCH__)
+    sincos(a, s, c);
+#else
+    *s = sin(a); *c = cos(a);
+#endif
+}
+
 // Sophus SO3::expAndTheta + the normalising SO3(Quaternion) constructor; q = {w, x, y, z}
 DSDTM_PO_HD void so3_exp(const double* om, double* q)
 {
     const double theta = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
     const double half = 0.5 * theta;
-    double imag;
-    const double real = cos(half);
+    double imag, real, sn;
+    po_sincos(half, &sn, &real);
     if (theta < kSmallEps) {
         const double t2 = theta * theta, t4 = t2 * t2;
         imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
     } else {
-        imag = sin(half) / theta;
+        imag = sn / theta;
     }
     double w = real, x = imag * om[0], y = imag * om[1], z = imag * om[2];
-    const double n = sqrt(x * x + y * y + z * z + w * w);
-    q[0] = w / n; q[1] = x / n; q[2] = y / n; q[3] = z / n;
+    const double rn = po_rsqrt(x * x + y * y + z * z + w * w);
+    q[0] = w * rn; q[1] = x * rn; q[2] = y * rn; q[3] = z * rn;
 }
 
 // Sophus SO3::logAndTheta (atan form)
@@ -104,10 +167,11 @@ DSDTM_PO_HD void qrot(const double* q, double v0, double v1, double v2, double& 
 }
 
 // PoseLocalParameterization::Plus: [t, log R] of SE3(exp(d.w), d.t) * SE3(exp(x.w), x.t)   (ref: include/Optimizer.h:220-236)
-DSDTM_PO_HD void pose_plus(const double* x, const double* d, double* out)
+// qo = so3_exp(x + 3), computed once per pose by the caller; q_out = the normalised product quaternion, which the evaluation of
+// the new pose uses directly: exp(log(q)) == +-q up to rounding, so re-deriving it from out[3..5] would only add a sincos.
+DSDTM_PO_HD void pose_plus(const double* x, const double* qo, const double* d, double* out, double* q_out)
 {
-    double qo[4], qd[4];
-    so3_exp(x + 3, qo);
+    double qd[4];
     so3_exp(d + 3, qd);
     double r0, r1, r2;
     qrot(qd, x[0], x[1], x[2], r0, r1, r2);
@@ -117,9 +181,10 @@ DSDTM_PO_HD void pose_plus(const double* x, const double* d, double* out)
     q[1] = qd[0] * qo[1] + qd[1] * qo[0] + qd[2] * qo[3] - qd[3] * qo[2];
     q[2] = qd[0] * qo[2] + qd[2] * qo[0] + qd[3] * qo[1] - qd[1] * qo[3];
     q[3] = qd[0] * qo[3] + qd[3] * qo[0] + qd[1] * qo[2] - qd[2] * qo[1];
-    const double n = sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3] + q[0] * q[0]);
-    q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+    const double rn = po_rsqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3] + q[0] * q[0]);
+    q[0] *= rn; q[1] *= rn; q[2] *= rn; q[3] *= rn;
     so3_log(q, out + 3);
+    q_out[0] = q[0]; q_out[1] = q[1]; q_out[2] = q[2]; q_out[3] = q[3];
 }
 
 struct Normal {     // cost, J'f and the upper triangle of J'J (loss-corrected, unscaled), row-major packed
@@ -131,25 +196,22 @@ struct Normal {     // cost, J'f and the upper triangle of J'J (loss-corrected, 
 DSDTM_PO_HD int hidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
 
 // One pass of ProgramEvaluator::Evaluate over the staged observations (soa = ox | oy | inv | px | py | pz, each n doubles).
+// q = so3_exp(x + 3)
 template <class Lanes>
-DSDTM_PO_HD void evaluate(const Lanes& ln, int n, const double* soa, const double* x, Normal& out)
+DSDTM_PO_HD void evaluate(const Lanes& ln, int n, const double* soa, const double* x, const double* q, Normal& out)
 {
-    double q[4];
-    so3_exp(x + 3, q);
-    double cost = 0.0;
-    double g[6] = { 0, 0, 0, 0, 0, 0 };
-    double H[21];
+    double acc[28];   // cost | J'f | upper triangle of J'J
 #pragma unroll
-    for (int i = 0; i < 21; ++i) H[i] = 0.0;
+    for (int i = 0; i < 28; ++i) acc[i] = 0.0;
     const double *ox = soa, *oy = soa + n, *inv = soa + 2 * n, *px = soa + 3 * n, *py = soa + 4 * n, *pz = soa + 5 * n;
     for (int k = ln.lane(); k < n; k += ln.count()) {
         double cx, cy, cz;
         qrot(q, px[k], py[k], pz[k], cx, cy, cz);
         cx += x[0]; cy += x[1]; cz += x[2];
         // FullBA_Problem::Evaluate (ref: include/Optimizer.h:141-205)
-        const double r0 = (ox[k] - cx / cz) * inv[k];
-        const double r1 = (oy[k] - cy / cz) * inv[k];
         const double z_inv = 1.0 / cz;
+        const double r0 = (ox[k] - cx * z_inv) * inv[k];
+        const double r1 = (oy[k] - cy * z_inv) * inv[k];
         const double z_inv2 = z_inv * z_inv;
         double j0[6], j1[6];
         j0[0] = -z_inv; j0[1] = 0.0; j0[2] = cx * z_inv2; j0[3] = cy * j0[2]; j0[4] = -(1.0 + cx * j0[2]); j0[5] = cy * z_inv;
@@ -158,43 +220,44 @@ DSDTM_PO_HD void evaluate(const Lanes& ln, int n, const double* soa, const doubl
         const double s = r0 * r0 + r1 * r1;
         const double sum = 1.0 + s;
         const double rho1 = fmax(DBL_MIN, 1.0 / sum);
-        cost += 0.5 * log(sum);
+        acc[0] += 0.5 * log(sum);
         const double w = sqrt(rho1);
         const double f0 = r0 * w, f1 = r1 * w;
 #pragma unroll
         for (int c = 0; c < 6; ++c) { j0[c] *= w; j1[c] *= w; }
 #pragma unroll
-        for (int c = 0; c < 6; ++c) g[c] += j0[c] * f0 + j1[c] * f1;
+        for (int c = 0; c < 6; ++c) acc[1 + c] += j0[c] * f0 + j1[c] * f1;
 #pragma unroll
         for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int b = a; b < 6; ++b) H[hidx(a, b)] += j0[a] * j0[b] + j1[a] * j1[b];
+            for (int b = a; b < 6; ++b) acc[7 + hidx(a, b)] += j0[a] * j0[b] + j1[a] * j1[b];
     }
-    out.cost = ln.sum(cost);
+    ln.sum_n(acc);
+    out.cost = acc[0];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) out.g[c] = ln.sum(g[c]);
+    for (int c = 0; c < 6; ++c) out.g[c] = acc[1 + c];
 #pragma unroll
-    for (int i = 0; i < 21; ++i) out.H[i] = ln.sum(H[i]);
+    for (int i = 0; i < 21; ++i) out.H[i] = acc[7 + i];
 }
 
 // Cholesky (lower) solve of the symmetric positive definite M (upper triangle packed) ; false when a pivot is not positive
 DSDTM_PO_HD bool chol6_solve(const double* Mu, const double* b, double* y)
 {
-    double L[6][6];
+    double L[6][6], rd[6];   // rd[k] = 1 / L[k][k]
+    bool ok = true;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         double d = Mu[hidx(k, k)];
 #pragma unroll
         for (int j = 0; j < k; ++j) d -= L[k][j] * L[k][j];
-        if (!(d > 0.0)) return false;
-        d = sqrt(d);
-        L[k][k] = d;
+        ok = ok && (d > 0.0);          // no early exit: the chain stays one basic block, NaNs of a failed pivot are discarded by the caller
+        rd[k] = po_rsqrt(d);
 #pragma unroll
         for (int i = k + 1; i < 6; ++i) {
             double s = Mu[hidx(k, i)];
 #pragma unroll
             for (int j = 0; j < k; ++j) s -= L[i][j] * L[k][j];
-            L[i][k] = s / d;
+            L[i][k] = s * rd[k];
         }
     }
     double v[6];
@@ -203,18 +266,18 @@ DSDTM_PO_HD bool chol6_solve(const double* Mu, const double* b, double* y)
         double s = b[i];
 #pragma unroll
         for (int j = 0; j < i; ++j) s -= L[i][j] * v[j];
-        v[i] = s / L[i][i];
+        v[i] = s * rd[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = v[i];
 #pragma unroll
         for (int j = i + 1; j < 6; ++j) s -= L[j][i] * v[j];
-        v[i] = s / L[i][i];
+        v[i] = s * rd[i];
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) y[i] = v[i];
-    return true;
+    return ok;
 }
 
 DSDTM_PO_HD bool finite_d(double v) { return fabs(v) <= DBL_MAX; }   // false for NaN and infinities
@@ -248,12 +311,14 @@ DSDTM_PO_HD void pose_optimize(const Lanes& ln, int n, const dsdtm_ba_obs* obs, 
     double x[6] = { pose_in[4], pose_in[5], pose_in[6], 0, 0, 0 };
     so3_log(pose_in, x + 3);
 
+    double qx[4] = { 1, 0, 0, 0 };   // so3_exp(x + 3) of the current pose
     int iterations = 0, n_successful = 0, term = DSDTM_BA_NO_RESIDUALS;
     double initial_cost = 0.0, final_cost = 0.0;
 
     if (n > 0) {
         Normal cur;
-        evaluate(ln, n, soa, x, cur);
+        so3_exp(x + 3, qx);
+        evaluate(ln, n, soa, x, qx, cur);
         initial_cost = final_cost = cur.cost;
         bool running = finite_d(cur.cost);
         if (!running) term = DSDTM_BA_FAILURE;
@@ -268,11 +333,19 @@ DSDTM_PO_HD void pose_optimize(const Lanes& ln, int n, const dsdtm_ba_obs* obs, 
         while (running) {
             // FinalizeIterationAndCheckIfMinimizerCanContinue
             if (iterations >= max_iters) { term = DSDTM_BA_NO_CONVERGENCE; break; }
-            if (last_successful) {
-                double ng[6], proj[6];
+            // GradientToleranceReached: max |x - Plus(x, -g)| <= 1e-10. The exact test costs a whole Plus (sincos, atan, rsqrt chain),
+            // so it is skipped when it cannot fire: with d = -g, the rotation part of x - Plus(x, d) is J_l^-1(x_w) d_w + O(d^2) and
+            // every singular value of J_l^-1 is >= 1, the translation part is -d_t + (I - R(d_w)) x_t with |(I - R) x_t| <= |d_w| |x_t|;
+            // for 1e-5 (1 + |x_t|) < max |g| < 1 at least one component therefore exceeds 1e-7.
+            double gabs = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) gabs = fmax(gabs, fabs(cur.g[c]));
+            const bool g_clear = gabs < 1.0 && gabs > 1e-5 * (1.0 + sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]));
+            if (last_successful && !g_clear) {
+                double ng[6], proj[6], qp[4];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) ng[c] = -cur.g[c];
-                pose_plus(x, ng, proj);
+                pose_plus(x, qx, ng, proj, qp);
                 double gmax = 0.0;
 #pragma unroll
                 for (int c = 0; c < 6; ++c) gmax = fmax(gmax, fabs(x[c] - proj[c]));
@@ -329,9 +402,10 @@ DSDTM_PO_HD void pose_optimize(const Lanes& ln, int n, const dsdtm_ba_obs* obs, 
             double delta[6], cand[6];
 #pragma unroll
             for (int c = 0; c < 6; ++c) delta[c] = step[c] * scale[c];
-            pose_plus(x, delta, cand);
+            double qc[4];
+            pose_plus(x, qx, delta, cand, qc);
             Normal nxt;
-            evaluate(ln, n, soa, cand, nxt);
+            evaluate(ln, n, soa, cand, qc, nxt);
             const bool cand_ok = finite_d(nxt.cost);
             const double cand_cost = cand_ok ? nxt.cost : DBL_MAX;
 
@@ -347,6 +421,8 @@ DSDTM_PO_HD void pose_optimize(const Lanes& ln, int n, const dsdtm_ba_obs* obs, 
             if (relative_decrease > kMinRelDecrease) {   // HandleSuccessfulStep
 #pragma unroll
                 for (int c = 0; c < 6; ++c) x[c] = cand[c];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) qx[c] = qc[c];
                 x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
                 cur = nxt;
                 final_cost = cur.cost;
@@ -365,7 +441,7 @@ DSDTM_PO_HD void pose_optimize(const Lanes& ln, int n, const dsdtm_ba_obs* obs, 
 
     // ref: src/Optimizer.cpp:79 and :298-318 (raw residual norm of every block at the final parameters)
     double q[4];
-    so3_exp(x + 3, q);
+    so3_exp(x + 3, q);   // ref: src/Optimizer.cpp:79 (also when n == 0: the pose handed back is exp(log(R)) as in the reference)
     if (res_norm) {
         const double *ox = soa, *oy = soa + n, *inv = soa + 2 * n, *px = soa + 3 * n, *py = soa + 4 * n, *pz = soa + 5 * n;
         for (int k = ln.lane(); k < n; k += ln.count()) {

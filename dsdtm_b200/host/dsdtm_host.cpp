@@ -434,6 +434,55 @@ void Feature_detector::detect(Frame* frame, const double detection_threshold, co
     frame->mImgMask.release();                                    // ref: :152-153
 }
 
+// ================================================================================================ Optimizer
+static dsdtm_ba_summary g_last_ba_summary = {};
+static std::vector<double> g_last_ba_residuals;
+const dsdtm_ba_summary& Optimizer::LastSummary() { return g_last_ba_summary; }
+const std::vector<double>& Optimizer::LastResiduals() { return g_last_ba_residuals; }
+
+void Optimizer::PoseOptimization(FramePtr tCurFrame, int /*tIterations: the reference ignores it and sets max_num_iterations = 100*/)
+{
+    double tReprojectThresh = Config::Get<float>("Optimization.LocalBAthreshhold");   // ref: src/Optimizer.cpp:22-24
+    tReprojectThresh = tReprojectThresh / tCurFrame->mCamera->mf;
+    const double tOutlineThres = tReprojectThresh;
+
+    // ref: :41-68 -- one residual block per feature with a good, initialised map point, in mvFeatures order; tvMpts is keyed by
+    // the FEATURE index (tNum advances on skipped features too)
+    std::vector<dsdtm_ba_obs> obs;
+    std::map<int, MapPoint*> tvMpts;
+    int tNum = 0;
+    for (auto iter = tCurFrame->mvFeatures.begin(); iter != tCurFrame->mvFeatures.end(); ++iter, ++tNum) {
+        if (!(*iter)->Mpt) continue;
+        if ((*iter)->Mpt->IsBad()) continue;
+        if (!((*iter)->mbInitial)) continue;
+        const Vector3d P = (*iter)->Mpt->Get_Pose();             // snapshot under the point's mutex (LocalMapping may move it)
+        tvMpts[tNum] = (*iter)->Mpt;
+        dsdtm_ba_obs o;
+        for (int k = 0; k < 3; ++k) { o.normal[k] = (*iter)->mNormal[k]; o.point_w[k] = P[k]; }
+        o.level = (*iter)->mlevel; o.reserved = 0;
+        obs.push_back(o);
+    }
+
+    dsdtm_ctx* ctx = GpuRuntime::Instance().ctx();
+    double pose_out[7];
+    g_last_ba_residuals.assign(obs.size(), 0.0);
+    const int rc = dsdtm_pose_optimize(ctx, obs.data(), (int)obs.size(), tCurFrame->Get_Pose().data(), 100, pose_out,
+                                       g_last_ba_residuals.data(), &g_last_ba_summary);
+    if (rc != 0) throw std::runtime_error(std::string("Optimizer::PoseOptimization: ") + dsdtm_last_error(ctx));
+    tCurFrame->Set_Pose(SE3(pose_out));                          // ref: :79
+
+    // ref: :81-94, literally: residual i is the i-th residual BLOCK, tvMpts[i] the map point of FEATURE i (std::map::operator[]
+    // inserts a null entry for a feature that was skipped) -- the two numberings agree only while no feature is skipped
+    const std::vector<double>& tvdResidual = g_last_ba_residuals;
+    for (int i = 0; i < (int)tvdResidual.size(); ++i) {
+        if (tvdResidual[i] > tOutlineThres) {
+            if (!tvMpts[i]) continue;
+            if (tvMpts[i]->IsBad()) continue;
+            tvMpts[i]->EraseFound();
+        }
+    }
+}
+
 // ================================================================================================ Sprase_ImgAlign
 Sprase_ImgAlign::Sprase_ImgAlign(int tMaxLevel, int tMinLevel, int tMaxIterators)
     : mnMaxLevel(tMaxLevel), mnMinLevel(tMinLevel), mnMaxIterators(tMaxIterators)

@@ -151,6 +151,9 @@ public:
     void SetBad(bool b) { mbBad = b; }
     int Get_FoundNums() const { return mnFound; }
     void IncreaseFound(int n = 1) { mnFound += n; }
+    // ref: src/MapPoint.cpp:183-197 (+ SetBadFlag :91-109: the outlier flag and the observation list; the Map / KeyFrame
+    // bookkeeping it also does lives outside the path)
+    void EraseFound(int n = 1) { mnFound -= n; if (mnFound <= 0) { mbBad = true; mObservations.clear(); } }
     void Add_Observation(KeyFrame* kf, size_t idx) { mObservations[kf] = idx; }
     bool Get_ClosetObs(const Frame* frame, Feature*& feature, KeyFrame*& kf) const;
     std::map<KeyFrame*, size_t> Get_Observations() const { return mObservations; }   // ref: src/MapPoint.cpp (copy under mMutexObs)
@@ -287,6 +290,15 @@ private:
     std::vector<Cell*> mCells;
     int mCell_size, mGrid_Cols, mGrid_Rows, mMax_pts, mPyr_levels;
     int mLastMatches = 0;
+};
+
+// ref: include/Optimizer.h:23-44, src/Optimizer.cpp:20-101 -- the entry Tracking calls right after SearchLocalPoints
+// (ref: src/Tracking.cpp:236). GPU: dsdtm_pose_optimize (the reference's ceres::Solve configuration, one launch).
+class Optimizer {
+public:
+    static void PoseOptimization(FramePtr tCurFrame, int tIterations = 100);
+    static const dsdtm_ba_summary& LastSummary();              // new: the reference only has Ceres' (commented-out) report
+    static const std::vector<double>& LastResiduals();         // new: GetReprojectReidual() of the last solve
 };
 
 // ------------------------------------------------------------------------------------------ GPU runtime

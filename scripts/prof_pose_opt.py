@@ -28,6 +28,17 @@ def main():
     for _ in range(50):
         ctx.pose_optimize(one, poses[1])
     ms1, k1 = ctx.profile_get()["pose_opt"]
+    ctx.set_option("pose_opt_solo_max", 0)
+    for _ in range(50):
+        ctx.pose_optimize(one, poses[1])
+    msw, kw = ctx.profile_get()["pose_opt"]
+    ctx.set_option("pose_opt_solo_max", -1)
+    print("one frame, one warp (sweep kernel): %.1f us; CTA of eight warps (solo kernel): %.1f us" % (1e3 * msw / kw, 1e3 * ms1 / k1))
+    for nb in (64, 296, 297, 1024):
+        for _ in range(5):
+            ctx.pose_optimize_batch(obs[:nb], n_obs[:nb], poses[:nb])
+        msb, kb = ctx.profile_get()["pose_opt"]
+        print("  %d frames: %.1f us per launch" % (nb, 1e3 * msb / kb))
     ctx.profile(False)
     t0 = time.perf_counter()
     for _ in range(200):

@@ -166,6 +166,29 @@ int hs_sparse_align_run(int maxl, int minl, int iters, void* cur, void* ref, dou
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// Optimizer::PoseOptimization (ref: src/Optimizer.cpp:20-101, called at src/Tracking.cpp:236). residuals: n_blocks doubles (cap entries max).
+int hs_pose_optimization(void* cur, double* pose_out, dsdtm_ba_summary* summary, double* residuals, int cap)
+{
+    try {
+        FramePtr c = static_cast<HsFrame*>(cur)->f;
+        Optimizer::PoseOptimization(c, 10);                     // Tracking passes 10; the reference ignores it
+        std::memcpy(pose_out, c->Get_Pose().data(), 7 * sizeof(double));
+        *summary = Optimizer::LastSummary();
+        const auto& r = Optimizer::LastResiduals();
+        for (int i = 0; i < (int)r.size() && i < cap; ++i) residuals[i] = r[i];
+        return (int)r.size();
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+// test set-up helpers: overwrite a feature's bearing / level, mark a map point bad
+void hs_frame_set_feature(void* f, int i, const double* normal3, int level)
+{
+    Feature* ft = static_cast<HsFrame*>(f)->f->mvFeatures[i];
+    ft->mNormal = Vector3d(normal3[0], normal3[1], normal3[2]);
+    ft->mlevel = level;
+}
+void hs_mappoint_set_bad(int id, int bad) { if (id >= 0 && id < (int)g_mps.size()) g_mps[id]->SetBad(bad != 0); }
+int hs_mappoint_is_bad(int id) { return (id >= 0 && id < (int)g_mps.size()) ? (g_mps[id]->IsBad() ? 1 : 0) : -1; }
+
 void* hs_keyframe_new(void* f)
 {
     Frame* fr = static_cast<HsFrame*>(f)->f.get();

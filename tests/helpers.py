@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 import oracle as O  # noqa: E402
 from dsdtm_b200 import synth as S  # noqa: E402
+from dsdtm_b200 import workload as W  # noqa: E402
 
 
 def ocam(cam):
@@ -103,37 +104,7 @@ def clahe_input(name, h, w):
     return np.clip(np.rint(v), 0, 255).astype(np.uint8)
 
 
-def _quat_from_rotvec(w):
-    th = float(np.linalg.norm(w))
-    if th < 1e-12:
-        return np.array([1.0, 0, 0, 0])
-    return np.r_[np.cos(th / 2), np.sin(th / 2) * np.asarray(w) / th]
-
-
-def _qmul(a, b):
-    w1, x1, y1, z1 = a; w2, x2, y2, z2 = b
-    return np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
-                     w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2, w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2])
-
-
-def make_ba_problem(seed, n=200, noise=1e-3, outliers=0.1, max_level=0, start_rot=0.01, start_trans=0.02):
-    """A frame after SearchLocalPoints for Optimizer::PoseOptimization (SURVEY 8f-2): n matched map points seen by a camera at a
-    seeded pose, observations = unit bearing vectors (Feature::mNormal) of the true projections + pixel noise / focal, a share of
-    gross outliers, pyramid levels U{0..max_level}, start pose = truth perturbed. Returns dict(normals, levels, points_w, pose_in, truth)."""
-    r = np.random.default_rng(seed)
-    q = _quat_from_rotvec(r.uniform(-0.2, 0.2, 3)); t = r.uniform(-0.3, 0.3, 3)
-    Pc = np.c_[r.uniform(-1.5, 1.5, n), r.uniform(-1, 1, n), r.uniform(1.5, 4, n)]
-    R = S.quat_to_R(q)
-    Pw = (Pc - t) @ R                                   # cam = R Pw + t
-    obs = np.c_[Pc[:, 0] / Pc[:, 2], Pc[:, 1] / Pc[:, 2]] + r.normal(0, noise, (n, 2))
-    k = r.random(n) < outliers
-    obs[k] += r.normal(0, 0.05, (int(k.sum()), 2))
-    nm = np.c_[obs, np.ones(n)]
-    nm /= np.linalg.norm(nm, axis=1)[:, None]
-    lv = r.integers(0, max_level + 1, n).astype(np.int32)
-    q0 = _qmul(_quat_from_rotvec(r.normal(0, start_rot, 3)), q)
-    pose0 = np.r_[q0, t + r.normal(0, start_trans, 3)]
-    return dict(normals=np.ascontiguousarray(nm), levels=lv, points_w=np.ascontiguousarray(Pw), pose_in=pose0, truth=np.r_[q, t])
+make_ba_problem = W.make_ba_problem   # the generator lives with the other synthetic workloads (bench.py uses it too)
 
 
 def ba_obs_records(pr, dtype, n_pad=None):

@@ -49,6 +49,8 @@ def lib():
         L.hs_sparse_align_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_keyframe_new.argtypes = [C.c_void_p]
         L.hs_search_local_points.argtypes = [C.c_void_p] * 5
+        L.hs_mappoint_found.argtypes = [C.c_int]
+        L.hs_mappoint_set_bad.argtypes = [C.c_int, C.c_int]
         L.hs_search_local_points_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_frame_attach_points_from.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hs_frame_feature_mp_ids.argtypes = [C.c_void_p, C.c_void_p]
@@ -56,6 +58,8 @@ def lib():
         L.hs_frame_keyframe_lift.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.hs_warp_affine_single.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hs_circle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.hs_pose_optimization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hs_frame_set_feature.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 

@@ -244,3 +244,59 @@ def test_single_candidate_warp_affine_and_patch_forms(built, scenario):
         want = O.warp_affine(A, O.pyr_level(packed, offs, ws, hs, L0), sc["feats"][idx]["px"], L0, 0)
         assert (p10 == want).all() and (p8 == O.patch_no_border(want)).all(), idx
     ref.free()
+
+
+@pytest.mark.gpu
+def test_optimizer_pose_optimization_after_search_local_points(built, scenario):
+    """Tracking's next call after SearchLocalPoints (ref: src/Tracking.cpp:236): Optimizer::PoseOptimization through the adapter
+    class against the oracle's restatement of ceres::Solve -- pose, stopping rule, residuals, and the reference's literal
+    EraseFound bookkeeping (residual BLOCK i is charged to the map point of FEATURE i, ref: src/Optimizer.cpp:81-94)."""
+    sc = scenario
+    cam_h = HL.configure(sc["cam"], max_fts=300)
+    L = HL.lib()
+    thr_px = 0.05
+    L.hs_config_set(b"Optimization.LocalBAthreshhold", repr(thr_px).encode())
+    ref = HL.HFrame(cam_h, sc["ref_img"], sc["T_ref"])
+    assert ref.detect(5.0) == 300
+    c = sc["corners"]
+    ref.attach_points(sc["ref_points"][c["y"], c["x"]], np.ones(len(c), np.uint8))
+    kf = L.hs_keyframe_new(ref.h)
+    cur = HL.HFrame(cam_h, sc["cur_img"], sc["T_cur"])
+    found0 = np.full(len(c), 3, np.int32)
+    m = L.hs_search_local_points(cam_h, cur.h, kf, HL._p(found0), None)
+    assert m > 100, L.hs_last_error()
+    px, lv, ini = cur.features()
+    ids = cur.mp_ids()
+    assert (ids >= 0).all() and ini.all()
+    # make the numbering of features and residual blocks differ: one matched map point goes bad before the solve
+    bad_feature = 7
+    L.hs_mappoint_set_bad(int(ids[bad_feature]), 1)
+    # start away from the optimum
+    start = O.se3_mul(O.se3_exp(np.array([0.01, -0.008, 0.012, 0.004, -0.003, 0.005])), sc["T_cur"])
+    cur.set_pose(start)
+    found_before = np.array([L.hs_mappoint_found(int(i)) for i in ids])
+    pose = np.empty(7); summ = np.zeros(1, O.BA_SUMMARY_DT); res = np.zeros(len(px))
+    nb = L.hs_pose_optimization(cur.h, HL._p(pose), HL._p(summ), HL._p(res), len(px))
+    assert nb == len(px) - 1, L.hs_last_error()
+    # the oracle on the same snapshot
+    oc = H.ocam(sc["cam"])
+    keep = np.arange(len(px)) != bad_feature
+    normals = np.array([O.feature_normal(oc, p) for p in px])
+    pts = sc["ref_points"][c["y"], c["x"]][ids]
+    a, ra, sa = O.pose_optimization(normals[keep], lv[keep], pts[keep], start)
+    s = summ[0]
+    assert (s["iterations"], s["termination"], s["n_successful"]) == (sa["iterations"], sa["termination"], sa["n_successful"])
+    assert np.abs(a - pose).max() < 1e-9 and np.abs(ra - res[:nb]).max() < 1e-9
+    assert np.abs(cur.pose() - pose).max() == 0
+    # back near the ground truth (sub-pixel matches): well inside the north_star pose budget of the front end
+    assert np.abs(pose - sc["T_cur"]).max() < 2e-4
+    # EraseFound, literally: block i -> feature i; feature `bad_feature` has no entry (skipped), later blocks are charged to the
+    # feature one position BEFORE their own
+    thr = float(np.float32(thr_px)) / float(np.float32(sc["cam"]["f"]))
+    expect = found_before.copy()
+    for i in range(nb):
+        if ra[i] > thr and i != bad_feature:
+            expect[i] -= 1
+    found_after = np.array([L.hs_mappoint_found(int(i)) for i in ids])
+    assert (found_after == expect).all()
+    assert 0 < (expect != found_before).sum() < nb            # the threshold splits the matches: both branches ran
