@@ -365,7 +365,7 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
         return 0;
     }
     if (std::strcmp(key, "pose_opt_solo_max") == 0) {
-        if (value < -1) return fail(c, DSDTM_E_ARG, "pose_opt_solo_max must be -1 (default: 2 x SM count), 0 (always one warp per frame) or a frame count");
+        if (value < -1) return fail(c, DSDTM_E_ARG, "pose_opt_solo_max must be -1 (default: the SM count), 0 (always one warp per frame) or a frame count");
         c->po_solo_max = value;
         return 0;
     }

@@ -114,7 +114,7 @@ struct dsdtm_ctx {
     double* po_pose_in_d = nullptr;      size_t po_pose_in_cap = 0;  // 7 per frame
     double* po_pose_out_d = nullptr;     size_t po_pose_out_cap = 0;
     dsdtm_ba_summary* po_sum_d = nullptr; size_t po_sum_cap = 0;
-    int po_solo_max = -1;                        // frames up to which a CTA of eight warps owns a frame (-1: 2 x SM count); 0 = always one warp per frame
+    int po_solo_max = -1;                        // frames up to which a CTA of eight warps owns a frame (-1: the SM count); 0 = always one warp per frame
 
     // pinned host staging for small synchronous calls
     uint8_t* pinned = nullptr;

@@ -8,11 +8,21 @@ namespace dsdtm {
 // independent frames: one warp per frame, kSweepWarps frames per CTA, each warp in its own shared-memory slice -- the chip is
 // filled by frames. A few frames (the per-frame call): one CTA of kSoloWarps warps per frame, so the pass over the observations
 // is kSoloWarps times shorter. Both kernels are single instantiations: a frame's result does not depend on its neighbours.
-static const int kSweepWarps = 4;
+#ifndef DSDTM_PO_SWEEP_WARPS
+#define DSDTM_PO_SWEEP_WARPS 4
+#endif
+// DSDTM_PO_SWEEP_MINB: CTAs per SM the sweep kernel is compiled for (a register cap); measured in scripts/po_variants.sh:
+// every cap spills and is slower than the uncapped 238 registers (0.674 ms per 4096 frames; 168 regs 0.739, 128 regs 0.818, 96 regs 0.926).
+#ifdef DSDTM_PO_SWEEP_MINB
+#define DSDTM_PO_SWEEP_BOUNDS __launch_bounds__(DSDTM_PO_SWEEP_WARPS * 32, DSDTM_PO_SWEEP_MINB)
+#else
+#define DSDTM_PO_SWEEP_BOUNDS __launch_bounds__(DSDTM_PO_SWEEP_WARPS * 32)
+#endif
+static const int kSweepWarps = DSDTM_PO_SWEEP_WARPS;
 static const int kSoloWarps = 8;
 static const int kPoseOptSmemLimit = 200 * 1024;
 
-__global__ void __launch_bounds__(kSweepWarps * 32)
+__global__ void DSDTM_PO_SWEEP_BOUNDS
 pose_opt_sweep_kernel(int n_frames, const dsdtm_ba_obs* __restrict__ obs, int obs_stride, const int* __restrict__ n_obs,
                       const double* __restrict__ poses_in, int max_iters, double* __restrict__ poses_out,
                       double* __restrict__ res_norm, dsdtm_ba_summary* __restrict__ summaries, int soa_stride)
@@ -56,7 +66,7 @@ cudaError_t launch_pose_opt(dsdtm_ctx* c, int n_frames, int obs_stride, int max_
     const size_t per_frame = (size_t)soa_stride * sizeof(double);
     double* rn = want_res ? c->po_res_d : nullptr;
     dsdtm_ba_summary* sm = want_sum ? c->po_sum_d : nullptr;
-    const int solo_max = c->po_solo_max >= 0 ? c->po_solo_max : 2 * c->sm_count;
+    const int solo_max = c->po_solo_max >= 0 ? c->po_solo_max : c->sm_count;   // one solo CTA per SM: 64 frames 108 us; two per SM (296 frames) 189 us vs 167 us for the sweep kernel
     if (n_frames <= solo_max) {
         pose_opt_solo_kernel<<<n_frames, kSoloWarps * 32, per_frame, s>>>(c->po_obs_d, obs_stride, c->po_nobs_d, c->po_pose_in_d, max_iters,
                                                                         c->po_pose_out_d, rn, sm);

@@ -61,7 +61,7 @@ def test_pose_optimize_batch_ragged_equals_single_and_is_deterministic(ctx):
     for nf in (2, 3):
         o, r, s = ctx.pose_optimize_batch(obs[:nf], n_obs[:nf], poses[:nf])
         assert (o == out[:nf]).all() and (s == sm[:nf]).all()
-    # the sweep kernel (one warp per frame; chosen automatically above 2 x SM count frames) on the same frames: another
+    # the sweep kernel (one warp per frame; chosen automatically above one frame per SM) on the same frames: another
     # reduction tree, so equal to rounding, with the same decisions; partial last CTA (21 frames, 4 per CTA)
     ctx.set_option("pose_opt_solo_max", 0)
     try:

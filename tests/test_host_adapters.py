@@ -254,8 +254,6 @@ def test_optimizer_pose_optimization_after_search_local_points(built, scenario):
     sc = scenario
     cam_h = HL.configure(sc["cam"], max_fts=300)
     L = HL.lib()
-    thr_px = 0.05
-    L.hs_config_set(b"Optimization.LocalBAthreshhold", repr(thr_px).encode())
     ref = HL.HFrame(cam_h, sc["ref_img"], sc["T_ref"])
     assert ref.detect(5.0) == 300
     c = sc["corners"]
@@ -275,15 +273,20 @@ def test_optimizer_pose_optimization_after_search_local_points(built, scenario):
     start = O.se3_mul(O.se3_exp(np.array([0.01, -0.008, 0.012, 0.004, -0.003, 0.005])), sc["T_cur"])
     cur.set_pose(start)
     found_before = np.array([L.hs_mappoint_found(int(i)) for i in ids])
-    pose = np.empty(7); summ = np.zeros(1, O.BA_SUMMARY_DT); res = np.zeros(len(px))
-    nb = L.hs_pose_optimization(cur.h, HL._p(pose), HL._p(summ), HL._p(res), len(px))
-    assert nb == len(px) - 1, L.hs_last_error()
     # the oracle on the same snapshot
     oc = H.ocam(sc["cam"])
     keep = np.arange(len(px)) != bad_feature
     normals = np.array([O.feature_normal(oc, p) for p in px])
     pts = sc["ref_points"][c["y"], c["x"]][ids]
     a, ra, sa = O.pose_optimization(normals[keep], lv[keep], pts[keep], start)
+    # Optimization.LocalBAthreshhold (pixels; 2.0 in the reference's configs) chosen between two residuals of this frame so that
+    # both branches of the outlier loop run
+    srt = np.sort(ra)
+    thr_px = float(np.float32(0.5 * (srt[len(srt) // 2] + srt[len(srt) // 2 + 1]) * float(np.float32(sc["cam"]["f"]))))
+    L.hs_config_set(b"Optimization.LocalBAthreshhold", repr(thr_px).encode())
+    pose = np.empty(7); summ = np.zeros(1, O.BA_SUMMARY_DT); res = np.zeros(len(px))
+    nb = L.hs_pose_optimization(cur.h, HL._p(pose), HL._p(summ), HL._p(res), len(px))
+    assert nb == len(px) - 1, L.hs_last_error()
     s = summ[0]
     assert (s["iterations"], s["termination"], s["n_successful"]) == (sa["iterations"], sa["termination"], sa["n_successful"])
     assert np.abs(a - pose).max() < 1e-9 and np.abs(ra - res[:nb]).max() < 1e-9
@@ -293,6 +296,7 @@ def test_optimizer_pose_optimization_after_search_local_points(built, scenario):
     # EraseFound, literally: block i -> feature i; feature `bad_feature` has no entry (skipped), later blocks are charged to the
     # feature one position BEFORE their own
     thr = float(np.float32(thr_px)) / float(np.float32(sc["cam"]["f"]))
+    assert np.abs(ra - thr).min() > 1e-8                      # no residual sits on the threshold
     expect = found_before.copy()
     for i in range(nb):
         if ra[i] > thr and i != bad_feature:
