@@ -132,6 +132,17 @@ class HFrame:
     def pose(self):
         p = np.empty(7); lib().hs_frame_get_pose(self.h, _p(p)); return p
 
+    def pose_optimization(self):
+        """Optimizer::PoseOptimization(frame, 10) as Tracking calls it -> (pose, summary record, residual norms)"""
+        n = lib().hs_frame_n_features(self.h)
+        pose = np.empty(7); res = np.zeros(max(n, 1))
+        summ = np.zeros(1, np.dtype([("iterations", "<i4"), ("termination", "<i4"), ("n_successful", "<i4"), ("n_obs", "<i4"),
+                                     ("initial_cost", "<f8"), ("final_cost", "<f8")]))
+        nb = lib().hs_pose_optimization(self.h, _p(pose), _p(summ), _p(res), n)
+        if nb < 0:
+            raise RuntimeError(lib().hs_last_error().decode())
+        return pose, summ[0], res[:nb]
+
     def set_pose(self, p):
         lib().hs_frame_set_pose(self.h, _p(np.ascontiguousarray(p, np.float64)))
 

@@ -426,3 +426,65 @@ def test_rgbd_sequence_with_device_keyframe_lift(built):
             n_kf += 1
         g_last = g_cur
     assert n_kf == 4
+
+
+# ------------------------------------------------------------------------------------------------ TrackWithLocalMap including the pose refinement
+@pytest.mark.gpu
+def test_sequence_with_pose_optimization_after_matching(built):
+    """Tracking::TrackWithLocalMap's order on a 25-frame RGB-D run (ref: src/Tracking.cpp:199-236): Sprase_ImgAlign::Run ->
+    SearchLocalPoints -> Optimizer::PoseOptimization (SURVEY 8f-2), the refined pose handed to the next frame as in the reference.
+    Functional end-to-end check against the ground-truth trajectory: the geometric refinement over the sub-pixel matches must not
+    lose what the photometric alignment found (and on average tightens it); with LocalBAthreshhold = 2 px (the value of every
+    reference config) no accurate match is charged. The per-call parity of the solve is in test_gpu_pose_opt.py and
+    test_host_adapters.py."""
+    cam = dict(S.KINECT)
+    scene = S.Scene(321)
+    n_frames, kf_every, scale = 25, 8, 5000.0
+    poses = _trajectory(n_frames, seed=33)
+    cam_h = HL.configure(cam, max_fts=300, max_frames=24, dist=(0.0, 0.0, 0.0, 0.0, 0.0))
+    L = HL.lib()
+    L.hs_config_set(b"Optimization.LocalBAthreshhold", b"2.0")
+    cfg = (5, 0, 8)
+
+    def lift(frame, z, start):
+        tab, _ = frame.keyframe_lift(np.clip(np.rint(z * scale), 0, 65535).astype(np.uint16), scale)
+        n = len(tab)
+        new = np.arange(start, n)
+        frame.attach_points_from(int(start), tab[new, 3:6], (tab[new, 2] > 0).astype(np.uint8))
+
+    img0, z0, _ = S.render(scene, cam, poses[0], want_points=True)
+    g_last = HL.HFrame(cam_h, img0, poses[0])
+    assert g_last.detect(5.0) == 300
+    lift(g_last, z0, 0)
+    kf_handles = [L.hs_keyframe_new(g_last.h)]
+    err_sa, err_po, its = [], [], []
+    for k in range(1, n_frames):
+        img, z, _ = S.render(scene, cam, poses[k], want_points=True)
+        g_cur = HL.HFrame(cam_h, img, g_last.pose())
+        n, pose_sa, _ = HL.sparse_align_run(*cfg, g_cur, g_last)
+        assert n >= 100, (k, n)
+        m, _ = HL.search_local_points_multi(cam_h, g_cur, kf_handles)
+        assert m >= 150, (k, m)
+        ids = g_cur.mp_ids()
+        found_before = np.array([L.hs_mappoint_found(int(i)) for i in ids])
+        pose_po, summ, res = g_cur.pose_optimization()
+        assert len(res) == m and summ["n_obs"] == m
+        assert summ["termination"] in (0, 1, 2) and summ["iterations"] <= 30, (k, summ)     # converged, not the iteration cap
+        assert summ["final_cost"] <= summ["initial_cost"]
+        assert res.max() < 2.0 / cam["f"]                                                     # every match within 2 px ...
+        assert (np.array([L.hs_mappoint_found(int(i)) for i in ids]) == found_before).all()    # ... so EraseFound never ran
+        assert np.abs(g_cur.pose() - pose_po).max() == 0                                      # Set_Pose happened
+        e0, e1 = S.pose_dist(pose_sa, poses[k]), S.pose_dist(pose_po, poses[k])
+        err_sa.append(e0); err_po.append(e1); its.append(int(summ["iterations"]))
+        assert e1[0] < 1.5e-3 and e1[1] < 4e-3, (k, e0, e1)
+        if k % kf_every == 0:
+            n_old = len(g_cur.features()[0])
+            assert g_cur.detect(5.0, use_existing=True) > n_old
+            lift(g_cur, z, n_old)
+            kf_handles.append(L.hs_keyframe_new(g_cur.h))
+        g_last = g_cur
+    err_sa, err_po = np.array(err_sa), np.array(err_po)
+    # the refinement over ~190 sub-pixel matches keeps (on average tightens) the photometric estimate
+    print("mean pose error (rad, m): sparse alignment", err_sa.mean(0), "after PoseOptimization", err_po.mean(0), "LM iterations", np.mean(its))
+    assert err_po[:, 0].mean() <= err_sa[:, 0].mean() and err_po[:, 1].mean() <= err_sa[:, 1].mean(),   # measured: 1.6e-5 rad / 3.4e-5 m after, 3.1e-5 / 7.1e-5 before
+        (err_sa.mean(0), err_po.mean(0))
