@@ -486,5 +486,5 @@ def test_sequence_with_pose_optimization_after_matching(built):
     err_sa, err_po = np.array(err_sa), np.array(err_po)
     # the refinement over ~190 sub-pixel matches keeps (on average tightens) the photometric estimate
     print("mean pose error (rad, m): sparse alignment", err_sa.mean(0), "after PoseOptimization", err_po.mean(0), "LM iterations", np.mean(its))
-    assert err_po[:, 0].mean() <= err_sa[:, 0].mean() and err_po[:, 1].mean() <= err_sa[:, 1].mean(),   # measured: 1.6e-5 rad / 3.4e-5 m after, 3.1e-5 / 7.1e-5 before
-        (err_sa.mean(0), err_po.mean(0))
+    # measured: 1.6e-5 rad / 3.4e-5 m after the refinement, 3.1e-5 / 7.1e-5 before
+    assert err_po[:, 0].mean() <= err_sa[:, 0].mean() and err_po[:, 1].mean() <= err_sa[:, 1].mean(), (err_sa.mean(0), err_po.mean(0))
