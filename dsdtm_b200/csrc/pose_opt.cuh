@@ -17,8 +17,8 @@
 // B200 mapping: the work per iteration is one pass over <= a few hundred observations producing 28 sums (cost, J'f, the 21
 // unique entries of J'J) followed by a 6 x 6 factorisation: a dependent chain, latency-bound. Observations are strided over the
 // threads that own the frame (staged once as structure-of-arrays in shared memory: observation, 2^-level, point), the 28 sums
-// are reduced with xor-shuffle butterflies (+ one shared-memory exchange when several warps own the frame) that leave identical
-// bits in every thread, so every thread runs the scalar tail redundantly and no broadcast is needed, and the candidate pass
+// are reduced with a transposed warp reduction + broadcast (+ one shared-memory exchange when several warps own the frame) that
+// leave identical bits in every thread, so every thread runs the scalar tail redundantly and no broadcast is needed, and the candidate pass
 // accumulates J'J and J'f speculatively so that an accepted step costs no second pass. A sweep gives each frame ONE warp (the
 // other resident warps hide its chain); a lone frame gets a CTA of eight warps (the pass is eight times shorter).
 // Differences from Ceres' arithmetic are rounding only (documented in DESIGN.md): sums are per lane then tree instead of
@@ -50,22 +50,48 @@ struct SerialLanes {
 };
 
 #if defined(__CUDACC__)
+// Sum N <= 32 per-lane values over the warp so that lane l ends up with the total of value l ("transposed" reduction): at the
+// stage with offset o a lane keeps the half of its values whose index has bit o equal to its own lane bit and hands the other
+// half to its partner, so 16 + 8 + 4 + 2 + 1 = 31 exchanges move everything -- instead of 5 exchanges for each of the N values
+// in a plain butterfly (140 for N = 28). Lanes >= N end with the total of a zero column.
+template <int N>
+__device__ __forceinline__ double warp_sum_transposed(const double (&v)[N])
+{
+    static_assert(N <= 32, "one value per lane");
+    const int lane = threadIdx.x & 31;
+    double w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = i < N ? v[i] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            if (i >= N) continue;                         // both halves are zero columns
+            const double lo = w[i], hi = w[i + o];
+            const double keep = up ? hi : lo;
+            const double send = up ? lo : hi;
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return w[0];
+}
+
 // one warp per frame (sweeps: the other resident warps hide this warp's dependent chain)
 struct WarpLanes {
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
     __device__ __forceinline__ int count() const { return 32; }
     template <int N> __device__ __forceinline__ void sum_n(double (&v)[N]) const
     {
+        const double tot = warp_sum_transposed(v);
 #pragma unroll
-        for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        for (int i = 0; i < N; ++i) v[i] = __shfl_sync(0xffffffffu, tot, i);
     }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
-// one CTA of kWarps warps per frame (a lone frame: the pass over the observations is kWarps times shorter). Per-warp butterflies,
-// then the warp sums meet in shared memory and every thread adds them in warp order; two buffers alternate so that one
-// __syncthreads per reduction suffices.
+// one CTA of kWarps warps per frame (a lone frame: the pass over the observations is kWarps times shorter). Per-warp transposed
+// reductions, then lane l of every warp adds the kWarps warp sums of value l from shared memory in warp order and hands the
+// total to its warp; two buffers alternate so that one __syncthreads per reduction suffices.
 template <int kWarps, int kMaxN>
 struct CtaLanes {
     double* buf;            // 2 * kWarps * kMaxN doubles of shared memory
@@ -76,21 +102,12 @@ struct CtaLanes {
     template <int N> __device__ __forceinline__ void sum_n(double (&v)[N]) const
     {
         static_assert(N <= kMaxN && N <= 32, "reduction buffer too small");
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        double tot = warp_sum_transposed(v);
         double* b = buf + phase * (kWarps * kMaxN);
         phase ^= 1;
-        const int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) b[w * kMaxN + i] = v[i];
-        }
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l < N) b[w * kMaxN + l] = tot;
         __syncthreads();
-        // lane i of every warp adds the kWarps partial sums of value i in warp order, then hands the total to the whole warp
-        const int l = threadIdx.x & 31;
-        double tot = 0.0;
         if (l < N) {
             tot = b[l];
 #pragma unroll
