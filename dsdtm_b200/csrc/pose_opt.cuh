@@ -333,126 +333,141 @@ DSDTM_PO_HD void pose_optimize(const Lanes& ln, int n, const dsdtm_ba_obs* obs, 
     double initial_cost = 0.0, final_cost = 0.0;
 
     if (n > 0) {
+        // One loop, rotated so that the pass over the observations appears ONCE in the code (iteration zero evaluates the start
+        // pose, every later trip the candidate): the pass is the bulk of the instructions and a second inlined copy costs
+        // instruction-cache misses on a lone CTA.
         Normal cur;
-        so3_exp(x + 3, qx);
-        evaluate(ln, n, soa, x, qx, cur);
-        initial_cost = final_cost = cur.cost;
-        bool running = finite_d(cur.cost);
-        if (!running) term = DSDTM_BA_FAILURE;
-        double scale[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) scale[c] = 1.0 / (1.0 + sqrt(cur.H[hidx(c, c)]));
+        double scale[6] = { 1, 1, 1, 1, 1, 1 };
         double radius = 1e4, decrease_factor = 2.0;
-        bool reuse_diagonal = false, last_successful = true;
+        bool reuse_diagonal = false, last_successful = true, first = true;
         double diagonal[6] = { 0, 0, 0, 0, 0, 0 };
         int n_invalid = 0;
         double x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
-        while (running) {
-            // FinalizeIterationAndCheckIfMinimizerCanContinue
-            if (iterations >= max_iters) { term = DSDTM_BA_NO_CONVERGENCE; break; }
-            // GradientToleranceReached: max |x - Plus(x, -g)| <= 1e-10. The exact test costs a whole Plus (sincos, atan, rsqrt chain),
-            // so it is skipped when it cannot fire: with d = -g, the rotation part of x - Plus(x, d) is J_l^-1(x_w) d_w + O(d^2) and
-            // every singular value of J_l^-1 is >= 1, the translation part is -d_t + (I - R(d_w)) x_t with |(I - R) x_t| <= |d_w| |x_t|;
-            // for 1e-5 (1 + |x_t|) < max |g| < 1 at least one component therefore exceeds 1e-7.
-            double gabs = 0.0;
+        double model_cost_change = 0.0;
+        double cand[6], qc[4];
+        so3_exp(x + 3, qx);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) gabs = fmax(gabs, fabs(cur.g[c]));
-            const bool g_clear = gabs < 1.0 && gabs > 1e-5 * (1.0 + sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]));
-            if (last_successful && !g_clear) {
-                double ng[6], proj[6], qp[4];
+        for (int c = 0; c < 6; ++c) cand[c] = x[c];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) ng[c] = -cur.g[c];
-                pose_plus(x, qx, ng, proj, qp);
-                double gmax = 0.0;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) gmax = fmax(gmax, fabs(x[c] - proj[c]));
-                if (gmax <= kGradientTol) { term = DSDTM_BA_GRADIENT_TOL; break; }
-            }
-            if (radius < kMinRadius) { term = DSDTM_BA_MIN_RADIUS; break; }
-            ++iterations;
-            last_successful = false;
-
-            // LevenbergMarquardtStrategy::ComputeStep on the column-scaled system
-            double M[21], gs[6];
-#pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                gs[a] = cur.g[a] * scale[a];
-#pragma unroll
-                for (int b = a; b < 6; ++b) M[hidx(a, b)] = cur.H[hidx(a, b)] * scale[a] * scale[b];
-            }
-            if (!reuse_diagonal) {
-#pragma unroll
-                for (int c = 0; c < 6; ++c) diagonal[c] = fmin(fmax(M[hidx(c, c)], kMinDiag), kMaxDiag);
-            }
-            reuse_diagonal = true;
-            double Hs_step_dot = 0.0;   // filled below
-            double A[21];
-#pragma unroll
-            for (int i = 0; i < 21; ++i) A[i] = M[i];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) A[hidx(c, c)] += diagonal[c] / radius;
-            double step[6];
-            bool valid = chol6_solve(A, gs, step);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) { valid = valid && finite_d(step[c]); step[c] = -step[c]; }
-            double model_cost_change = 0.0;
-            if (valid) {
-                // -(Js step)'(f + Js step / 2) = -(step'gs + step'(Js'Js)step / 2)
-                double sg = 0.0;
-#pragma unroll
-                for (int a = 0; a < 6; ++a) {
-                    sg += step[a] * gs[a];
-                    double row = 0.0;
-#pragma unroll
-                    for (int b = 0; b < 6; ++b) row += M[a <= b ? hidx(a, b) : hidx(b, a)] * step[b];
-                    Hs_step_dot += step[a] * row;
-                }
-                model_cost_change = -(sg + 0.5 * Hs_step_dot);
-                valid = model_cost_change > 0.0;
-            }
-            if (!valid) {   // HandleInvalidStep
-                if (++n_invalid >= kMaxInvalid) { term = DSDTM_BA_FAILURE; break; }
-                radius = radius / decrease_factor; decrease_factor *= 2.0;
-                continue;
-            }
-            n_invalid = 0;
-            double delta[6], cand[6];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) delta[c] = step[c] * scale[c];
-            double qc[4];
-            pose_plus(x, qx, delta, cand, qc);
+        for (int c = 0; c < 4; ++c) qc[c] = qx[c];
+        for (;;) {
             Normal nxt;
             evaluate(ln, n, soa, cand, qc, nxt);
-            const bool cand_ok = finite_d(nxt.cost);
-            const double cand_cost = cand_ok ? nxt.cost : DBL_MAX;
-
-            double step_norm = 0.0;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) step_norm += (x[c] - cand[c]) * (x[c] - cand[c]);
-            step_norm = sqrt(step_norm);
-            if (step_norm <= kParameterTol * (x_norm + kParameterTol)) { term = DSDTM_BA_PARAMETER_TOL; break; }
-            const double cost_change = cur.cost - cand_cost;
-            if (fabs(cost_change) <= kFunctionTol * cur.cost) { term = DSDTM_BA_FUNCTION_TOL; break; }
-
-            const double relative_decrease = cost_change / model_cost_change;
-            if (relative_decrease > kMinRelDecrease) {   // HandleSuccessfulStep
-#pragma unroll
-                for (int c = 0; c < 6; ++c) x[c] = cand[c];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) qx[c] = qc[c];
-                x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+            if (first) {
+                // IterationZero
+                first = false;
                 cur = nxt;
-                final_cost = cur.cost;
-                ++n_successful;
-                last_successful = true;
-                const double q = 2.0 * relative_decrease - 1.0;
-                radius = radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
-                radius = fmin(kMaxRadius, radius);
-                decrease_factor = 2.0;
-                reuse_diagonal = false;
+                initial_cost = final_cost = cur.cost;
+                if (!finite_d(cur.cost)) { term = DSDTM_BA_FAILURE; break; }
+#pragma unroll
+                for (int c = 0; c < 6; ++c) scale[c] = 1.0 / (1.0 + sqrt(cur.H[hidx(c, c)]));
             } else {
+                const bool cand_ok = finite_d(nxt.cost);
+                const double cand_cost = cand_ok ? nxt.cost : DBL_MAX;
+                // ParameterToleranceReached / FunctionToleranceReached: the candidate is NOT taken when they fire
+                double step_norm = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) step_norm += (x[c] - cand[c]) * (x[c] - cand[c]);
+                step_norm = sqrt(step_norm);
+                if (step_norm <= kParameterTol * (x_norm + kParameterTol)) { term = DSDTM_BA_PARAMETER_TOL; break; }
+                const double cost_change = cur.cost - cand_cost;
+                if (fabs(cost_change) <= kFunctionTol * cur.cost) { term = DSDTM_BA_FUNCTION_TOL; break; }
+
+                const double relative_decrease = cost_change / model_cost_change;
+                if (relative_decrease > kMinRelDecrease) {   // HandleSuccessfulStep
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) x[c] = cand[c];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) qx[c] = qc[c];
+                    x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+                    cur = nxt;
+                    final_cost = cur.cost;
+                    ++n_successful;
+                    last_successful = true;
+                    const double q = 2.0 * relative_decrease - 1.0;
+                    radius = radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+                    radius = fmin(kMaxRadius, radius);
+                    decrease_factor = 2.0;
+                    reuse_diagonal = false;
+                } else {
+                    radius = radius / decrease_factor; decrease_factor *= 2.0;
+                }
+            }
+
+            // the next trust-region step; invalid steps shrink the radius and try again without a pass over the observations
+            bool stop = false;
+            double step[6];
+            for (;;) {
+                // FinalizeIterationAndCheckIfMinimizerCanContinue
+                if (iterations >= max_iters) { term = DSDTM_BA_NO_CONVERGENCE; stop = true; break; }
+                // GradientToleranceReached: max |x - Plus(x, -g)| <= 1e-10. The exact test costs a whole Plus (sincos, atan, rsqrt chain),
+                // so it is skipped when it cannot fire: with d = -g, the rotation part of x - Plus(x, d) is J_l^-1(x_w) d_w + O(d^2) and
+                // every singular value of J_l^-1 is >= 1, the translation part is -d_t + (I - R(d_w)) x_t with |(I - R) x_t| <= |d_w| |x_t|;
+                // for 1e-5 (1 + |x_t|) < max |g| < 1 at least one component therefore exceeds 1e-7.
+                double gabs = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) gabs = fmax(gabs, fabs(cur.g[c]));
+                const bool g_clear = gabs < 1.0 && gabs > 1e-5 * (1.0 + sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]));
+                if (last_successful && !g_clear) {
+                    double ng[6], proj[6], qp[4];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) ng[c] = -cur.g[c];
+                    pose_plus(x, qx, ng, proj, qp);
+                    double gmax = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) gmax = fmax(gmax, fabs(x[c] - proj[c]));
+                    if (gmax <= kGradientTol) { term = DSDTM_BA_GRADIENT_TOL; stop = true; break; }
+                }
+                if (radius < kMinRadius) { term = DSDTM_BA_MIN_RADIUS; stop = true; break; }
+                ++iterations;
+                last_successful = false;
+
+                // LevenbergMarquardtStrategy::ComputeStep on the column-scaled system
+                double M[21], gs[6];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    gs[a] = cur.g[a] * scale[a];
+#pragma unroll
+                    for (int b = a; b < 6; ++b) M[hidx(a, b)] = cur.H[hidx(a, b)] * scale[a] * scale[b];
+                }
+                if (!reuse_diagonal) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) diagonal[c] = fmin(fmax(M[hidx(c, c)], kMinDiag), kMaxDiag);
+                }
+                reuse_diagonal = true;
+                double A[21];
+#pragma unroll
+                for (int i = 0; i < 21; ++i) A[i] = M[i];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) A[hidx(c, c)] += diagonal[c] / radius;
+                bool valid = chol6_solve(A, gs, step);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { valid = valid && finite_d(step[c]); step[c] = -step[c]; }
+                model_cost_change = 0.0;
+                if (valid) {
+                    // -(Js step)'(f + Js step / 2) = -(step'gs + step'(Js'Js)step / 2)
+                    double sg = 0.0, Hs_step_dot = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        sg += step[a] * gs[a];
+                        double row = 0.0;
+#pragma unroll
+                        for (int b = 0; b < 6; ++b) row += M[a <= b ? hidx(a, b) : hidx(b, a)] * step[b];
+                        Hs_step_dot += step[a] * row;
+                    }
+                    model_cost_change = -(sg + 0.5 * Hs_step_dot);
+                    valid = model_cost_change > 0.0;
+                }
+                if (valid) { n_invalid = 0; break; }
+                // HandleInvalidStep
+                if (++n_invalid >= kMaxInvalid) { term = DSDTM_BA_FAILURE; stop = true; break; }
                 radius = radius / decrease_factor; decrease_factor *= 2.0;
             }
+            if (stop) break;
+            double delta[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) delta[c] = step[c] * scale[c];
+            pose_plus(x, qx, delta, cand, qc);
         }
     }
 
