@@ -249,7 +249,7 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
     const size_t B = prm->max_batch, F = prm->max_feats, P = std::max(prm->max_patches, 1);
     const size_t pool = (size_t)prm->max_frames * g.frame_stride;
     if (dalloc(c, &c->frames_d, pool)) return bail("frame pool");
-    CK(cudaMemset(c->frames_d, 0, pool));
+    CK(cudaMemset(c->frames_d, 0, pool));   // ordered before any use: the synchronous cudaMemcpy below runs on the same (null) stream and blocks the host
     if (dalloc(c, &c->cells_d, B * c->n_cells) || dalloc(c, &c->occupied_d, B * c->n_cells) ||
         dalloc(c, &c->scoremap_d, 2 * (size_t)g.w[0] * g.h[0]) || dalloc(c, &c->ref_slots_d, B) || dalloc(c, &c->cur_slots_d, B) ||
         dalloc(c, &c->feats_d, B * F) || dalloc(c, &c->n_feats_d, B) || dalloc(c, &c->centers_d, B * 3) ||
@@ -271,6 +271,7 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
     CK(pose_opt_init(c));
     CK(cudaMallocHost((void**)&c->stage_pin, kStageBytes));
     CK(cudaMalloc((void**)&c->stage_dev, kStageBytes));
+    CK(cudaDeviceSynchronize());   // every initialisation above (null stream) is complete before the first call uses the non-blocking streams
 #undef CK
     return c;
 }
@@ -925,8 +926,10 @@ static int ensure_depth_pool(dsdtm_ctx* c)
     if (c->depth_d) return 0;
     const size_t px = (size_t)c->cam.width * c->cam.height;
     if (dalloc(c, &c->depth_d, px * c->depth_slots)) return DSDTM_E_NOMEM;
-    cudaError_t e = cudaMemset(c->depth_d, 0, px * c->depth_slots * sizeof(uint16_t));
-    if (e != cudaSuccess) return fail(c, DSDTM_E_CUDA, "cudaMemset(depth pool)", e);
+    // on the context's stream: it is a non-blocking stream, so a memset on the null stream is NOT ordered with the uploads that
+    // follow and could land after the first one (seen once as a zeroed slot 0 in test_depth_convert_bit_exact)
+    cudaError_t e = cudaMemsetAsync(c->depth_d, 0, px * c->depth_slots * sizeof(uint16_t), c->stream);
+    if (e != cudaSuccess) return fail(c, DSDTM_E_CUDA, "cudaMemsetAsync(depth pool)", e);
     return 0;
 }
 
