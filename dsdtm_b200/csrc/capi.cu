@@ -1019,6 +1019,29 @@ int dsdtm_pose_optimize_batch(dsdtm_ctx* c, int n_frames, const dsdtm_ba_obs* ob
             if (L < 0 || L > 30) return fail(c, DSDTM_E_ARG, "observation level outside [0, 30]");
         }
     const size_t n_rec = (size_t)n_frames * obs_stride;
+    {
+        // small calls (one frame, a few frames): everything in ONE copy each way through the pinned arena and its device mirror
+        const size_t nf = (size_t)n_frames;
+        Arena ar(c, n_rec * sizeof(dsdtm_ba_obs) + nf * (sizeof(int) + 7 * sizeof(double)),
+                 nf * (7 * sizeof(double) + sizeof(dsdtm_ba_summary)) + (res_norm ? n_rec * sizeof(double) : 0), 3, 3);
+        if (ar.active) {
+            cudaStream_t s = c->stream;
+            dsdtm_ba_obs* dummy_obs = nullptr;
+            PtrSwap<dsdtm_ba_obs> p0(c->po_obs_d, n_rec ? ar.in(obs, n_rec) : dummy_obs);
+            PtrSwap<int> p1(c->po_nobs_d, ar.in(n_obs, nf));
+            PtrSwap<double> p2(c->po_pose_in_d, ar.in(poses_in, 7 * nf)), q0(c->po_pose_out_d, ar.out(poses_out, 7 * nf));
+            PtrSwap<dsdtm_ba_summary> q1(c->po_sum_d, ar.out(summaries, nf));
+            PtrSwap<double> q2(c->po_res_d, (res_norm && n_rec) ? ar.out(res_norm, n_rec) : c->po_res_d);
+            DSDTM_CUDA(c, ar.upload(s));
+            stage_begin(c, DSDTM_STAGE_POSE_OPT);
+            DSDTM_CUDA(c, launch_pose_opt(c, n_frames, obs_stride, max_obs, max_iters, res_norm != nullptr && n_rec, summaries != nullptr, s));
+            stage_end(c, 1);
+            DSDTM_CUDA(c, ar.download(s));
+            DSDTM_CUDA(c, cudaStreamSynchronize(s));
+            ar.finish();
+            return 0;
+        }
+    }
     if (grow(c, &c->po_obs_d, &c->po_obs_cap, n_rec) || grow(c, &c->po_nobs_d, &c->po_nobs_cap, (size_t)n_frames) ||
         grow(c, &c->po_pose_in_d, &c->po_pose_in_cap, 7 * (size_t)n_frames) || grow(c, &c->po_pose_out_d, &c->po_pose_out_cap, 7 * (size_t)n_frames) ||
         grow(c, &c->po_sum_d, &c->po_sum_cap, (size_t)n_frames) || (res_norm && grow(c, &c->po_res_d, &c->po_res_cap, n_rec)))

@@ -448,8 +448,12 @@ void Optimizer::PoseOptimization(FramePtr tCurFrame, int /*tIterations: the refe
 
     // ref: :41-68 -- one residual block per feature with a good, initialised map point, in mvFeatures order; tvMpts is keyed by
     // the FEATURE index (tNum advances on skipped features too)
-    std::vector<dsdtm_ba_obs> obs;
-    std::map<int, MapPoint*> tvMpts;
+    // (std::map<int, MapPoint*> in the reference; a vector indexed by the feature number answers tvMpts[i] identically --
+    //  a missing key reads as null -- without 200 node allocations per frame)
+    static thread_local std::vector<dsdtm_ba_obs> obs;
+    static thread_local std::vector<MapPoint*> tvMpts;
+    obs.clear(); obs.reserve(tCurFrame->mvFeatures.size());
+    tvMpts.assign(tCurFrame->mvFeatures.size(), nullptr);
     int tNum = 0;
     for (auto iter = tCurFrame->mvFeatures.begin(); iter != tCurFrame->mvFeatures.end(); ++iter, ++tNum) {
         if (!(*iter)->Mpt) continue;
