@@ -3,6 +3,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../dsdtm_b200/host/dsdtm_host.h"
@@ -229,17 +230,14 @@ int hs_search_local_points_multi(void* cam, void* cur, void** kfs, int n_kfs, in
         Feature_Alignment& fa = feature_alignment(cam);
         FramePtr c = static_cast<HsFrame*>(cur)->f;
         fa.ResetGrid();
-        std::vector<MapPoint*> seen;
+        std::unordered_set<MapPoint*> seen;   // UpdateLocalMap's mvLocalMapPoints: each point once (ref: src/Tracking.cpp:258-313)
         int nr = 0;
         for (int q = 0; q < n_kfs; ++q) {
             KeyFrame* k = static_cast<HsKf*>(kfs[q])->kf;
             for (size_t i = 0; i < k->mvFeatures.size(); ++i) {
                 MapPoint* mp = k->mvFeatures[i]->Mpt;
                 if (!mp || mp->IsBad()) continue;
-                bool dup = false;
-                for (MapPoint* s : seen) if (s == mp) { dup = true; break; }
-                if (dup) continue;
-                seen.push_back(mp);
+                if (!seen.insert(mp).second) continue;
                 if (fa.ReprojectPoint(c, mp)) nr++;
             }
         }
