@@ -622,15 +622,23 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
     // of them in ONE call (dsdtm_local_map_align_batch), then replay the greedy selection in the reference's order.
     GpuRuntime& rt = GpuRuntime::Instance();
     struct Item { Candidate* cand; int index; };               // index into the point table, -1 = IsBad at snapshot time
-    std::vector<std::vector<Item>> items(mCells.size());
-    std::vector<dsdtm_kf_view> kfs;
-    std::map<KeyFrame*, int> kf_index;
-    std::vector<dsdtm_obs> obs;
-    std::vector<dsdtm_map_point> pts;
+    // flat, reused across frames: the items of cell ci are items[cell_begin[ci] .. cell_begin[ci + 1])
+    static thread_local std::vector<Item> items;
+    static thread_local std::vector<int> cell_begin;
+    static thread_local std::vector<dsdtm_kf_view> kfs;
+    static thread_local std::vector<dsdtm_obs> obs;
+    static thread_local std::vector<dsdtm_map_point> pts;
+    static thread_local unsigned long long snap_epoch = 0;
+    items.clear(); kfs.clear(); obs.clear(); pts.clear();
+    cell_begin.assign(mCells.size() + 1, 0);
+    ++snap_epoch;
     const int cur_slot_first = rt.Resident(frame->mGpu);     // touch the current frame first: it must stay resident as well
     for (size_t ci = 0; ci < mCells.size(); ++ci) {
         Cell* cell = mCells[ci];
-        cell->sort([](Candidate& a, Candidate& b) { return a.mMpPoint->Get_FoundNums() > b.mMpPoint->Get_FoundNums(); });   // ref: :88,123-126
+        cell_begin[ci] = (int)items.size();
+        if (cell->empty()) continue;
+        if (cell->size() > 1)
+            cell->sort([](Candidate& a, Candidate& b) { return a.mMpPoint->Get_FoundNums() > b.mMpPoint->Get_FoundNums(); });   // ref: :88,123-126
         for (Candidate& c : *cell) {
             Item it{ &c, -1 };
             if (!c.mMpPoint->IsBad()) {
@@ -638,35 +646,36 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
                 const Vector3d P = c.mMpPoint->Get_Pose();
                 for (int k = 0; k < 3; ++k) mp.point_w[k] = P[k];
                 mp.obs_begin = (int)obs.size();
-                for (const auto& o : c.mMpPoint->Get_Observations()) {          // std::map order = the reference's iteration order
-                    KeyFrame* kf = o.first;
-                    auto found = kf_index.find(kf);
-                    if (found == kf_index.end()) {
+                c.mMpPoint->ForEachObservation([&](KeyFrame* kf, size_t feat) {   // std::map order = the reference's iteration order
+                    if (kf->mSnapEpoch != snap_epoch) {
                         dsdtm_kf_view v{};
                         v.slot = rt.Resident(kf->mGpu);
                         const Vector3d O = kf->Get_CameraCnt();
                         const SE3 T = kf->Get_Pose();
                         for (int k = 0; k < 3; ++k) v.center[k] = O[k];
                         for (int k = 0; k < 7; ++k) v.pose_c2w[k] = T.data()[k];
-                        found = kf_index.emplace(kf, (int)kfs.size()).first;
+                        kf->mSnapEpoch = snap_epoch;
+                        kf->mSnapIndex = (int)kfs.size();
                         kfs.push_back(v);
                     }
-                    const Feature* f = kf->mvFeatures[o.second];
+                    const Feature* f = kf->mvFeatures[feat];
                     dsdtm_obs ob{};
-                    ob.kf = found->second; ob.level = f->mlevel; ob.px[0] = f->mpx.x; ob.px[1] = f->mpx.y;
-                    const Vector3d Pf = f->Mpt ? f->Mpt->Get_Pose() : P;         // ref: :167 rf->Mpt->Get_Pose()
+                    ob.kf = kf->mSnapIndex; ob.level = f->mlevel; ob.px[0] = f->mpx.x; ob.px[1] = f->mpx.y;
+                    const Vector3d Pf = (f->Mpt && f->Mpt != c.mMpPoint) ? f->Mpt->Get_Pose() : P;   // ref: :167 rf->Mpt->Get_Pose()
                     for (int k = 0; k < 3; ++k) { ob.normal[k] = f->mNormal[k]; ob.point_w[k] = Pf[k]; }
                     obs.push_back(ob);
-                }
+                });
                 mp.obs_count = (int)obs.size() - mp.obs_begin;
                 it.index = (int)pts.size();
                 pts.push_back(mp);
             }
-            items[ci].push_back(it);
+            items.push_back(it);
         }
     }
+    cell_begin[mCells.size()] = (int)items.size();
     const int n = (int)pts.size();
-    std::vector<dsdtm_reproj> res(n);
+    static thread_local std::vector<dsdtm_reproj> res;
+    res.resize(n);
     const auto T1 = std::chrono::steady_clock::now();
     if (n > 0) {
         const int cur_slot = rt.Resident(frame->mGpu);
@@ -688,7 +697,8 @@ void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref
     // replay (ref: :75-82, :91-118)
     int matches = 0;
     for (size_t ci = 0; ci < mCells.size(); ++ci) {
-        for (Item& it : items[ci]) {
+        for (int ii = cell_begin[ci]; ii < cell_begin[ci + 1]; ++ii) {
+            Item& it = items[ii];
             Candidate& c = *it.cand;
             if (c.mMpPoint->IsBad()) continue;
             if (frame->mImgMask.at(cvRound((float)c.mPx[1]), cvRound((float)c.mPx[0])) != 255) continue;

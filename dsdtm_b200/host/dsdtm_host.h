@@ -157,6 +157,8 @@ public:
     void Add_Observation(KeyFrame* kf, size_t idx) { mObservations[kf] = idx; }
     bool Get_ClosetObs(const Frame* frame, Feature*& feature, KeyFrame*& kf) const;
     std::map<KeyFrame*, size_t> Get_Observations() const { return mObservations; }   // ref: src/MapPoint.cpp (copy under mMutexObs)
+    // the adapters' snapshot walks the observations in place (same std::map order) instead of copying the map per candidate
+    template <class F> void ForEachObservation(F&& f) const { for (const auto& o : mObservations) f(o.first, o.second); }
 private:
     mutable std::mutex mMutexPos;
     Vector3d mPose;
@@ -214,6 +216,9 @@ public:
     std::vector<Mat8> mvImg_Pyr;
     Features mvFeatures;
     std::shared_ptr<GpuSlot> mGpu;
+    // position of this key frame in the table of the snapshot being built (valid while mSnapEpoch == the snapshot's number)
+    mutable unsigned long long mSnapEpoch = 0;
+    mutable int mSnapIndex = -1;
 private:
     SE3 mT_c2w;
     Vector3d mOw;
