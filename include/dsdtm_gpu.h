@@ -101,7 +101,9 @@ long long   dsdtm_launch_count(const dsdtm_ctx* ctx);
 /* tuning knobs (never change results): "sa_warps_per_pair" = 0 (auto) | 1 | 2 | 4 | 10;
  * "pyramid_kernel" = 0 (auto: register/DP4A strip kernel where the level shape allows) | 1 (shared-memory tile kernel);
  * "sa_variant" = 0 (shared-memory recompute kernel) | 1 (L2 workspace kernel); "step_chunks" = 1..8 concurrent streams
- * over which dsdtm_batch_run splits the pairs of a step (per-pair stage order unchanged) */
+ * over which dsdtm_batch_run splits the pairs of a step (per-pair stage order unchanged); "depth_slots" = size of the depth
+ * pool (before its first use); "pose_opt_solo_max" = frames per dsdtm_pose_optimize_batch call up to which a CTA of eight warps
+ * owns a frame (-1 = the SM count, 0 = always one warp per frame; the two kernels agree to rounding, not bitwise) */
 int         dsdtm_set_option(dsdtm_ctx* ctx, const char* key, int value);
 /* stage profiling: on != 0 brackets every stage with CUDA events; get returns accumulated ms and launch counts */
 int         dsdtm_profile(dsdtm_ctx* ctx, int on);
@@ -270,7 +272,10 @@ int dsdtm_frames_upload_clahe_pyramid(dsdtm_ctx* ctx, int first_slot, int n, con
  * ref: include/Optimizer.h:129-258): motion-only bundle adjustment of the current frame over its matched map points -- the
  * step Tracking runs right after SearchLocalPoints (ref: src/Tracking.cpp:236). The reference delegates to ceres::Solve
  * (trust-region Levenberg-Marquardt, DENSE_SCHUR, CauchyLoss(1.0), max_num_iterations = 100 -- its tIterations argument is
- * ignored; pass max_iters = 100 for the same behaviour); the device routine runs that algorithm, one warp per frame.
+ * ignored; pass max_iters = 100 for the same behaviour); the device routine runs that algorithm: a CTA of eight warps per frame
+ * for up to one frame per SM, one warp per frame for sweeps (option "pose_opt_solo_max" moves the switch). Floating point:
+ * results agree with a sequential evaluation to rounding; a frame's result does not depend on its neighbours
+ * in the batch, and is bit-reproducible from run to run for a given kernel choice.
  * One record per residual block, i.e. per feature of the frame with Mpt != NULL, !Mpt->IsBad() and mbInitial, in
  * mvFeatures order (ref: src/Optimizer.cpp:46-68). */
 typedef struct {
