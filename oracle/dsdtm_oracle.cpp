@@ -1038,7 +1038,7 @@ struct PoseBA {
             const double rho0 = 1.0 * std::log(sum);
             const double rho1 = std::max(std::numeric_limits<double>::min(), inv);
             c += 0.5 * rho0;
-            if (!std::isfinite(rho0)) return false;
+            if (!std::isfinite(rho0)) { *cost = c; return false; }
             if (want_jac) {
                 const double sqrt_rho1 = std::sqrt(rho1);   // Corrector: rho[2] = -inv*inv <= 0 => alpha = 0, scaling = sqrt(rho')
                 for (int i = 0; i < 12; ++i) jac[i] *= sqrt_rho1;

@@ -106,6 +106,12 @@ def test_pose_optimize_edge_cases_and_bad_arguments(ctx):
     bad["level"][3] = -1
     with pytest.raises(capi.DsdtmError):
         ctx.pose_optimize(bad, pr["pose_in"])
+    # a residual that cannot be evaluated: Ceres gives up at iteration zero, parameters untouched
+    nan = H.ba_obs_records(pr, capi.BA_OBS_DT); nan["normal"][5, 2] = 0.0
+    bn, rn, sn = ctx.pose_optimize(nan, pr["pose_in"])
+    an, _, san = O.pose_optimization(nan["normal"], nan["level"], nan["point_w"], pr["pose_in"])
+    assert sn["termination"] == capi.BA_FAILURE == san["termination"] and sn["iterations"] == 0 and np.abs(bn - pr["pose_in"]).max() < 1e-15
+    assert not np.isfinite(rn[5]) and np.isfinite(np.delete(rn, 5)).all()
     # the context stays usable
     b2, _, sb2 = ctx.pose_optimize(H.ba_obs_records(pr, capi.BA_OBS_DT), pr["pose_in"])
     a2, _, sa2 = _orc(pr)

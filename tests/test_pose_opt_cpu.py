@@ -128,3 +128,17 @@ def test_product_routine_many_seeds_and_caps(prod):
     e = dict(normals=np.zeros((0, 3)), levels=np.zeros(0, np.int32), points_w=np.zeros((0, 3)), pose_in=pr["pose_in"])
     b, rb, sb = prod(e)
     assert sb["termination"] == O.BA_NO_RESIDUALS and np.abs(b - pr["pose_in"]).max() < 1e-15
+
+
+def test_non_finite_input_fails_like_ceres(prod):
+    """A residual that cannot be evaluated (bearing with z = 0, map point in the camera centre plane) makes Ceres give up at iteration
+    zero with the parameters untouched; later non-finite candidates are rejected steps. Oracle and product agree."""
+    pr = H.make_ba_problem(31, n=40)
+    bad = dict(pr); bad["normals"] = pr["normals"].copy(); bad["normals"][5, 2] = 0.0
+    a, ra, sa = _orc(bad)
+    b, rb, sb = prod(bad)
+    assert sa["termination"] == O.BA_FAILURE and sb["termination"] == O.BA_FAILURE and sa["iterations"] == sb["iterations"] == 0
+    assert np.abs(a - pr["pose_in"]).max() < 1e-15 and np.abs(b - pr["pose_in"]).max() < 1e-15
+    assert not np.isfinite(sa["initial_cost"]) and not np.isfinite(sb["initial_cost"])
+    ok = np.arange(40) != 5
+    assert np.abs(ra[ok] - rb[ok]).max() < 1e-12 and not np.isfinite(rb[5]) and not np.isfinite(ra[5])
