@@ -27,6 +27,8 @@ LM_IN_IMAGE, LM_OBS_OK, LM_REF_OK, LM_CONVERGED = 1, 2, 4, 8
 LIFTED_DT = np.dtype([("px", "<f4", 2), ("depth", "<f4"), ("status", "<i4"), ("normal", "<f8", 3), ("point_w", "<f8", 3)])
 assert LIFTED_DT.itemsize == 64
 LIFT_SKIPPED, LIFT_OK, LIFT_NO_DEPTH = 0, 1, 2
+MAP_KF_DT = np.dtype([("pt_begin", "<i4"), ("pt_count", "<i4"), ("t", "<f8", 3)])
+assert MAP_KF_DT.itemsize == 32
 BA_OBS_DT = np.dtype([("normal", "<f8", 3), ("point_w", "<f8", 3), ("level", "<i4"), ("reserved", "<i4")])
 BA_SUMMARY_DT = np.dtype([("iterations", "<i4"), ("termination", "<i4"), ("n_successful", "<i4"), ("n_obs", "<i4"),
                           ("initial_cost", "<f8"), ("final_cost", "<f8")])
@@ -75,7 +77,7 @@ SYMBOLS = [
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
     "dsdtm_local_map_align_batch", "dsdtm_depth_upload", "dsdtm_depth_convert_f32", "dsdtm_keyframe_lift",
     "dsdtm_frame_upload_pyramid_host", "dsdtm_frames_upload_clahe_pyramid", "dsdtm_track_frame",
-    "dsdtm_pose_optimize", "dsdtm_pose_optimize_batch",
+    "dsdtm_pose_optimize", "dsdtm_pose_optimize_batch", "dsdtm_map_table_upload", "dsdtm_close_keyframes",
 ]
 
 
@@ -325,6 +327,19 @@ class Context:
         self._ck(self.L.dsdtm_keyframe_lift(self.hp, int(depth_slot), _p(np.ascontiguousarray(pose_c2w, np.float64)),
                                             _p(np.ascontiguousarray(dist, np.float32)), C.c_float(depth_scale), _p(px), _p(ini), len(px), _p(out)))
         return out
+
+    def map_table_upload(self, first_kf, kfs, first_point, points_w):
+        """dsdtm_map_table_upload: (re)write key-frame rows from first_kf and point rows from first_point."""
+        kfs = np.ascontiguousarray(kfs, MAP_KF_DT).reshape(-1)
+        pts = np.ascontiguousarray(points_w, np.float64).reshape(-1, 3)
+        self._ck(self.L.dsdtm_map_table_upload(self.hp, int(first_kf), len(kfs), _p(kfs), int(first_point), len(pts), _p(pts)))
+
+    def close_keyframes(self, pose_cur_c2w, n_kfs, max_local=10):
+        """dsdtm_close_keyframes -> (visible u8[n_kfs], dist f64[n_kfs], local key-frame rows in rank order)"""
+        vis = np.zeros(n_kfs, np.uint8); dist = np.zeros(n_kfs); local = np.zeros(max(max_local, 1), np.int32); n = C.c_int32(0)
+        self._ck(self.L.dsdtm_close_keyframes(self.hp, _p(np.ascontiguousarray(pose_cur_c2w, np.float64)), int(n_kfs), int(max_local),
+                                              _p(vis), _p(dist), _p(local), C.byref(n)))
+        return vis, dist, local[:n.value].copy()
 
     def pose_optimize_batch(self, obs, n_obs, poses_in, max_iters=100, want_res=True):
         """dsdtm_pose_optimize_batch: obs = (n_frames, obs_stride) BA_OBS_DT, n_obs per frame, poses (n_frames, 7).

@@ -63,6 +63,25 @@ static int grow(dsdtm_ctx* c, T** p, size_t* cap, size_t n)
     return 0;
 }
 
+// grow() for tables whose contents must survive: the first `keep` elements are copied to the new allocation
+template <class T>
+static int grow_keep(dsdtm_ctx* c, T** p, size_t* cap, size_t n, size_t keep)
+{
+    if (n <= *cap) return 0;
+    T* old = *p;
+    T* fresh = nullptr;
+    const size_t want = std::max<size_t>(2 * n, 1024);
+    if (dalloc(c, &fresh, want)) return DSDTM_E_NOMEM;
+    if (old && keep) {
+        cudaError_t e = cudaMemcpyAsync(fresh, old, keep * sizeof(T), cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { cudaFree(fresh); return fail(c, DSDTM_E_CUDA, "table copy", e); }
+    }
+    if (old) cudaFree(old);
+    *p = fresh; *cap = want;
+    return 0;
+}
+
 static int ensure_pinned(dsdtm_ctx* c, size_t bytes)
 {
     if (bytes <= c->pinned_bytes) return 0;
@@ -287,7 +306,8 @@ void dsdtm_destroy(dsdtm_ctx* c)
                      c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d, c->cand_d,
                      c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d,
                      c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d, c->clahe_src_d, c->clahe_lut_d,
-                     c->po_obs_d, c->po_res_d, c->po_nobs_d, c->po_pose_in_d, c->po_pose_out_d, c->po_sum_d };
+                     c->po_obs_d, c->po_res_d, c->po_nobs_d, c->po_pose_in_d, c->po_pose_out_d, c->po_sum_d,
+                     c->mt_kfs_d, c->mt_pts_d, c->mt_vis_d, c->mt_dist_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->stage_pin) cudaFreeHost(c->stage_pin);
@@ -994,6 +1014,60 @@ int dsdtm_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], 
     DSDTM_CUDA(c, cudaMemcpyAsync(st.out(out, (size_t)n * sizeof(dsdtm_lifted)), c->lift_out_d, (size_t)n * sizeof(dsdtm_lifted), cudaMemcpyDeviceToHost, s));
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
     st.finish();
+    return 0;
+}
+
+// Device-resident map table + Tracking::GetCloseKeyFrames / UpdateLocalMap ranking (ref: src/Tracking.cpp:261-277,315-345)
+int dsdtm_map_table_upload(dsdtm_ctx* c, int first_kf, int n_kfs, const dsdtm_map_kf* kfs, int first_point, int n_points, const double* points_w)
+{
+    if (!c) return DSDTM_E_ARG;
+    if (first_kf < 0 || n_kfs < 0 || first_point < 0 || n_points < 0) return fail(c, DSDTM_E_ARG, "negative range");
+    if ((n_kfs && !kfs) || (n_points && !points_w)) return fail(c, DSDTM_E_ARG, "null pointer");
+    if ((size_t)first_kf > c->mt_kfs_n || (size_t)first_point > c->mt_pts_n) return fail(c, DSDTM_E_ARG, "range starts past the end of the table (rows are appended or rewritten, never skipped)");
+    const size_t end_kf = (size_t)first_kf + n_kfs, end_pt = (size_t)first_point + n_points;
+    const size_t pts_after = std::max(c->mt_pts_n, end_pt);
+    for (int k = 0; k < n_kfs; ++k)
+        if (kfs[k].pt_begin < 0 || kfs[k].pt_count < 0 || (size_t)kfs[k].pt_begin + kfs[k].pt_count > pts_after)
+            return fail(c, DSDTM_E_ARG, "key-frame row points outside the point array");
+    if (grow_keep(c, &c->mt_kfs_d, &c->mt_kfs_cap, end_kf, c->mt_kfs_n) || grow_keep(c, &c->mt_pts_d, &c->mt_pts_cap, 3 * end_pt, 3 * c->mt_pts_n))
+        return DSDTM_E_NOMEM;
+    cudaStream_t s = c->stream;
+    Stager st(c, (size_t)n_kfs * sizeof(dsdtm_map_kf) + 3 * (size_t)n_points * sizeof(double));
+    if (n_kfs) DSDTM_CUDA(c, cudaMemcpyAsync(c->mt_kfs_d + first_kf, st.in(kfs, (size_t)n_kfs * sizeof(dsdtm_map_kf)), (size_t)n_kfs * sizeof(dsdtm_map_kf), cudaMemcpyHostToDevice, s));
+    if (n_points) DSDTM_CUDA(c, cudaMemcpyAsync(c->mt_pts_d + 3 * (size_t)first_point, st.in(points_w, 3 * (size_t)n_points * sizeof(double)), 3 * (size_t)n_points * sizeof(double), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));     // the caller's buffers may go away
+    c->mt_kfs_n = std::max(c->mt_kfs_n, end_kf);
+    c->mt_pts_n = pts_after;
+    return 0;
+}
+
+int dsdtm_close_keyframes(dsdtm_ctx* c, const double pose_cur_c2w[7], int n_kfs, int max_local, uint8_t* visible, double* dist,
+                          int32_t* local, int32_t* n_local)
+{
+    if (!c || !pose_cur_c2w || !n_local || n_kfs < 0 || max_local < 0 || (max_local && !local)) return DSDTM_E_ARG;
+    if ((size_t)n_kfs > c->mt_kfs_n) return fail(c, DSDTM_E_ARG, "n_kfs exceeds the uploaded map table");
+    *n_local = 0;
+    if (n_kfs == 0) return 0;
+    if (grow(c, &c->mt_vis_d, &c->mt_vis_cap, (size_t)n_kfs) || grow(c, &c->mt_dist_d, &c->mt_dist_cap, (size_t)n_kfs)) return DSDTM_E_NOMEM;
+    if (ensure_pinned(c, (size_t)n_kfs * (sizeof(double) + 1) + 16)) return DSDTM_E_NOMEM;
+    double* dist_h = reinterpret_cast<double*>(c->pinned);
+    uint8_t* vis_h = c->pinned + (size_t)n_kfs * sizeof(double);
+    cudaStream_t s = c->stream;
+    stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+    DSDTM_CUDA(c, launch_close_keyframes(c, pose_cur_c2w, n_kfs, s));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(dist_h, c->mt_dist_d, (size_t)n_kfs * sizeof(double), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaMemcpyAsync(vis_h, c->mt_vis_d, (size_t)n_kfs, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    if (visible) std::memcpy(visible, vis_h, (size_t)n_kfs);
+    if (dist) std::memcpy(dist, dist_h, (size_t)n_kfs * sizeof(double));
+    // UpdateLocalMap's ranking (ref: src/Tracking.cpp:266-277): stable sort of the close key frames by distance, first max_local
+    std::vector<int32_t> order;
+    for (int k = 0; k < n_kfs; ++k) if (vis_h[k]) order.push_back(k);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return dist_h[a] < dist_h[b]; });
+    const int n = std::min<int>((int)order.size(), max_local);
+    for (int i = 0; i < n; ++i) local[i] = order[i];
+    *n_local = n;
     return 0;
 }
 

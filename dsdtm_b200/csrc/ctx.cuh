@@ -107,6 +107,11 @@ struct dsdtm_ctx {
     dsdtm_lifted* lift_out_d = nullptr;
     uint8_t* clahe_src_d = nullptr;      size_t clahe_cap = 0;       // raw images waiting for CLAHE (frames)
     uint8_t* clahe_lut_d = nullptr;      size_t clahe_lut_cap = 0;   // per frame tiles * 256 bytes
+    // device-resident map table for the local-map selection (f-1, caller side), grown on demand
+    dsdtm_map_kf* mt_kfs_d = nullptr;    size_t mt_kfs_cap = 0;  size_t mt_kfs_n = 0;
+    double* mt_pts_d = nullptr;          size_t mt_pts_cap = 0;  size_t mt_pts_n = 0;     // 3 doubles per row
+    uint8_t* mt_vis_d = nullptr;         size_t mt_vis_cap = 0;
+    double* mt_dist_d = nullptr;         size_t mt_dist_cap = 0;
     // pose refinement (f-2), grown on demand
     dsdtm_ba_obs* po_obs_d = nullptr;    size_t po_obs_cap = 0;      // n_frames * obs_stride records
     double* po_res_d = nullptr;          size_t po_res_cap = 0;      // residual norms, same indexing
@@ -177,6 +182,7 @@ cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s);
 cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s,
                              const double* pose_dev = nullptr);
 cudaError_t launch_compose_pose(dsdtm_ctx* c, const double* t_c2r_d, const double pose_ref_c2w[7], double* out10_d, cudaStream_t s);
+cudaError_t launch_close_keyframes(dsdtm_ctx* c, const double pose_cur[7], int n_kfs, cudaStream_t s);
 cudaError_t pose_opt_init(dsdtm_ctx* c);
 cudaError_t launch_pose_opt(dsdtm_ctx* c, int n_frames, int obs_stride, int max_obs, int max_iters, bool want_res, bool want_sum,
                             cudaStream_t s);

@@ -181,4 +181,62 @@ cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const doubl
     return cudaGetLastError();
 }
 
+// ---- Tracking::GetCloseKeyFrames on the device-resident map table (ref: src/Tracking.cpp:315-345, src/Frame.cpp:300-311).
+// One warp per key frame: the lanes test 32 of its map points at a time (same non-contracted projection as above, boundary 0) and
+// the warp stops at the first chunk with a visible point -- the reference's early break, 32 points wide. The work is one read of
+// the point rows of the key frames that are NOT close (24 B per point) and one chunk of those that are.
+namespace {
+struct CkArgs {
+    const dsdtm_map_kf* kfs; const double* pts; int n_kfs;
+    double pose[7];
+    float fx, fy, cx, cy; int width, height;
+    uint8_t* visible; double* dist;
+};
+
+__global__ void __launch_bounds__(128) close_kf_kernel(const CkArgs a)
+{
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= a.n_kfs) return;
+    const int lane = threadIdx.x & 31;
+    const dsdtm_map_kf kf = a.kfs[k];
+    bool found = false;
+    for (int base = 0; base < kf.pt_count && !found; base += 32) {
+        const int i = base + lane;
+        bool vis = false;
+        if (i < kf.pt_count) {
+            const double* P = a.pts + 3 * (size_t)(kf.pt_begin + i);
+            const double P0 = P[0], P1 = P[1], P2 = P[2];
+            if (!(P0 == 0.0 && P1 == 0.0 && P2 == 0.0)) {                     // ref: :324-328
+                double q0, q1, q2;
+                qrot_exact(a.pose, P0, P1, P2, q0, q1, q2);
+                q0 = __dadd_rn(q0, a.pose[4]); q1 = __dadd_rn(q1, a.pose[5]); q2 = __dadd_rn(q2, a.pose[6]);
+                if (!(q2 < 0.0)) {                                              // ref: src/Frame.cpp:303
+                    const double u = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fx, q0), q2), (double)a.cx);
+                    const double v = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fy, q1), q2), (double)a.cy);
+                    vis = in_image(__double2float_rn(u), __double2float_rn(v), 0, 0, a.width, a.height);
+                }
+            }
+        }
+        found = __any_sync(0xffffffffu, vis);
+    }
+    if (lane == 0) {
+        a.visible[k] = found ? 1 : 0;
+        const double d0 = __dsub_rn(a.pose[4], kf.t[0]), d1 = __dsub_rn(a.pose[5], kf.t[1]), d2 = __dsub_rn(a.pose[6], kf.t[2]);
+        a.dist[k] = found ? sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2))) : 0.0;   // ref: :332
+    }
+}
+}  // namespace
+
+cudaError_t launch_close_keyframes(dsdtm_ctx* c, const double pose_cur[7], int n_kfs, cudaStream_t s)
+{
+    CkArgs a;
+    a.kfs = c->mt_kfs_d; a.pts = c->mt_pts_d; a.n_kfs = n_kfs;
+    for (int k = 0; k < 7; ++k) a.pose[k] = pose_cur[k];
+    a.fx = c->cam.fx; a.fy = c->cam.fy; a.cx = c->cam.cx; a.cy = c->cam.cy; a.width = c->cam.width; a.height = c->cam.height;
+    a.visible = c->mt_vis_d; a.dist = c->mt_dist_d;
+    close_kf_kernel<<<(n_kfs + 3) / 4, 128, 0, s>>>(a);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 }  // namespace dsdtm

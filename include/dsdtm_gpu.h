@@ -267,6 +267,26 @@ int dsdtm_keyframe_lift(dsdtm_ctx* ctx, int depth_slot, const double pose_c2w[7]
 int dsdtm_frames_upload_clahe_pyramid(dsdtm_ctx* ctx, int first_slot, int n, const uint8_t* imgs, double clip_limit,
                                       int tiles_x, int tiles_y, uint8_t* level0_out);
 
+/* ---------------------------------------------------------------- local-map selection (8f-1, the caller's half) ---- */
+/* Tracking::GetCloseKeyFrames (ref: src/Tracking.cpp:315-345) and the ranking at the top of Tracking::UpdateLocalMap
+ * (ref: :261-277). The reference walks EVERY key frame of the map and projects its map points into the current frame until one
+ * is visible (Frame::isVisible, ref: src/Frame.cpp:300-311) -- a key frame with no visible point costs all its points -- every
+ * frame, on the tracking thread. Here the map lives in a device-resident table that is updated incrementally (a new key frame
+ * appends its rows; a bundle adjustment re-uploads the ranges it moved) and one launch answers for the whole map.
+ * Point rows are KeyFrame::mvMapPoints in order; a null or exactly-zero map point is the row {0,0,0} (skipped as at :324-328). */
+typedef struct {
+    int32_t pt_begin, pt_count;   /* this key frame's rows of the point array */
+    double  t[3];                 /* KeyFrame::Get_Pose().translation() (the rank key of :332 is the distance of the translations) */
+} dsdtm_map_kf;                   /* 32 bytes */
+/* (re)write key-frame rows [first_kf, first_kf + n_kfs) and point rows [first_point, first_point + n_points); the table grows */
+int dsdtm_map_table_upload(dsdtm_ctx* ctx, int first_kf, int n_kfs, const dsdtm_map_kf* kfs, int first_point, int n_points,
+                           const double* points_w);
+/* over key-frame rows [0, n_kfs): visible[k] = the key frame has a map point visible in the current frame (it enters tClose_kfs),
+ * dist[k] = its rank key (0 when not visible); local[0 .. *n_local) = the first max_local (10 in the reference) visible key frames
+ * by ascending distance, ties in row order (std::list::sort is stable) = mvpLocalKeyFrames. visible / dist may be NULL. */
+int dsdtm_close_keyframes(dsdtm_ctx* ctx, const double pose_cur_c2w[7], int n_kfs, int max_local, uint8_t* visible, double* dist,
+                          int32_t* local, int32_t* n_local);
+
 /* ---------------------------------------------------------------- pose refinement after matching (8f-2) ---- */
 /* Optimizer::PoseOptimization(FramePtr, int) (ref: src/Optimizer.cpp:20-101; residual / Jacobian / parameterisation
  * ref: include/Optimizer.h:129-258): motion-only bundle adjustment of the current frame over its matched map points -- the

@@ -384,3 +384,15 @@ def pose_optimization(normals, levels, points_w, pose_in, max_iters=100):
     f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     f(len(lv), _p(nm), _p(lv), _p(pw), _p(np.ascontiguousarray(pose_in, np.float64)), int(max_iters), _p(out), _p(res), _p(summ))
     return out, res, summ[0]
+
+
+def close_keyframes(cam, pose_cur_c2w, pt_begin, pt_count, kf_t, points_w, max_local=10):
+    """Tracking::GetCloseKeyFrames + UpdateLocalMap's ranking -> (visible, dist, local rows)."""
+    pb = np.ascontiguousarray(pt_begin, np.int32); pc = np.ascontiguousarray(pt_count, np.int32)
+    kt = np.ascontiguousarray(kf_t, np.float64).reshape(-1, 3); pw = np.ascontiguousarray(points_w, np.float64).reshape(-1, 3)
+    n = len(pb)
+    vis = np.zeros(n, np.uint8); dist = np.zeros(n); local = np.zeros(max(max_local, 1), np.int32)
+    f = lib().orc_close_keyframes
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    k = f(C.byref(cam), _p(np.ascontiguousarray(pose_cur_c2w, np.float64)), _p(pb), _p(pc), _p(kt), n, _p(pw), int(max_local), _p(vis), _p(dist), _p(local))
+    return vis, dist, local[:k].copy()

@@ -943,6 +943,44 @@ int orc_align2d(const uint8_t* img, int w, int h, int stride, const uint8_t p10[
 }
 
 // ------------------------------------------------------------------------------------------
+// SURVEY 8f-1, the caller's half: Tracking::GetCloseKeyFrames (ref: src/Tracking.cpp:315-345) and the ranking at the top of
+// Tracking::UpdateLocalMap (ref: :261-277). A key frame is "close" when ANY of its map points is visible in the current frame
+// (Frame::isVisible, ref: src/Frame.cpp:300-311: in front of the camera and Camera::IsInImage of the float pixel, boundary 0);
+// null and exactly-zero points are skipped (:324-328); its rank key is the distance between the two poses' TRANSLATIONS (:332,
+// not the camera centres). UpdateLocalMap sorts the list (std::list::sort: stable) and keeps the first max_local (10).
+// kfs are visited in the caller's order (std::set<KeyFrame*> iteration order in the reference). PARITY UNPINNED (no golden).
+// ------------------------------------------------------------------------------------------
+extern "C" int orc_close_keyframes(const orc_cam* cam, const double pose_cur_c2w[7], const int* pt_begin, const int* pt_count,
+                                   const double* kf_t, int n_kfs, const double* points_w, int max_local, uint8_t* visible,
+                                   double* dist, int* local)
+{
+    const Se3 T = se3_from(pose_cur_c2w);
+    std::vector<std::pair<int, double>> close;
+    for (int k = 0; k < n_kfs; ++k) {
+        visible[k] = 0; dist[k] = 0.0;
+        for (int i = 0; i < pt_count[k]; ++i) {
+            const double* P = points_w + 3 * (size_t)(pt_begin[k] + i);
+            if (P[0] == 0.0 && P[1] == 0.0 && P[2] == 0.0) continue;          // null map point or isZero(0)
+            double c[3];
+            se3_act(T, P, c);
+            if (c[2] < 0.0) continue;                                           // ref: src/Frame.cpp:303
+            double px[2];
+            cam2pix(cam, c, px);
+            if (!orc_is_in_image(cam, (float)px[0], (float)px[1], 0, 0)) continue;
+            const double d0 = T.t[0] - kf_t[3 * k], d1 = T.t[1] - kf_t[3 * k + 1], d2 = T.t[2] - kf_t[3 * k + 2];
+            visible[k] = 1;
+            dist[k] = std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            close.emplace_back(k, dist[k]);
+            break;
+        }
+    }
+    std::stable_sort(close.begin(), close.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.second < b.second; });
+    int n = 0;
+    for (const auto& c : close) { if (n >= max_local) break; local[n++] = c.first; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
 // Optimizer::PoseOptimization. ref: src/Optimizer.cpp:20-101, include/Optimizer.h:129-258.
 //
 // The reference hands the problem to ceres::Solve (ceres-solver is a find_package dependency, CMakeLists.txt:23, version

@@ -148,6 +148,13 @@ void orc_unproject(const orc_cam* cam, const double pose_c2w[7], const float px[
  * PINNED against cv2 4.13 goldens (tests/golden/clahe_cv2.npz). */
 void orc_clahe(const uint8_t* src, int w, int h, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst);
 
+/* ---- SURVEY 8f-1 (caller side): Tracking::GetCloseKeyFrames + the ranking of UpdateLocalMap (ref: src/Tracking.cpp:315-345,261-277).
+ * Key frame k owns points_w[pt_begin[k] .. + pt_count[k]) (null / zero points = {0,0,0}); kf_t = Get_Pose().translation() per key frame.
+ * visible[k], dist[k] (0 when not visible); local[] = the first max_local visible key frames by distance (stable); returns their count. */
+int orc_close_keyframes(const orc_cam* cam, const double pose_cur_c2w[7], const int* pt_begin, const int* pt_count,
+                        const double* kf_t, int n_kfs, const double* points_w, int max_local, uint8_t* visible,
+                        double* dist, int* local);
+
 /* ---- Optimizer::PoseOptimization (ref: src/Optimizer.cpp:20-101, include/Optimizer.h:129-258) ----
  * ceres::Solve with the reference's configuration restated (trust-region Levenberg-Marquardt, DENSE_SCHUR on the single pose
  * block, CauchyLoss(1.0), PoseLocalParameterization, 100 iterations; see the .cpp). PARITY UNPINNED (Ceres is neither under

@@ -126,3 +126,31 @@ BA_CASES = [  # (seed, n, noise, outliers, max_level, start_rot, start_trans)
     (19, 33, 1e-3, 0.4, 3, 0.8, 0.5),    # ends on the parameter tolerance
     (3, 33, 1e-3, 0.4, 3, 0.8, 0.5),     # 65 iterations, 58 accepted
 ]
+
+
+def make_map_table(seed, n_kfs=60, pts_per_kf=(40, 300), cam=S.KINECT, spread=6.0):
+    """A map for Tracking::GetCloseKeyFrames (SURVEY 8f-1, caller side): key frames scattered over `spread` metres around the
+    origin, each with its own cloud of map points ~2 m in front of it (some null / zero rows, some behind the camera), and a current
+    pose near the origin. Returns dict(kfs MAP_KF-like arrays, points, pose_cur)."""
+    r = np.random.default_rng(seed)
+    pt_begin, pt_count, kf_t, pts = [], [], [], []
+    total = 0
+    for k in range(n_kfs):
+        n = int(r.integers(pts_per_kf[0], pts_per_kf[1] + 1)) if k % 11 else 0          # a few key frames without any point
+        q = _rotvec_quat(r.normal(0, 0.15, 3))
+        centre = np.r_[r.uniform(-spread, spread, 2), r.uniform(-0.5, 0.5)]
+        R = S.quat_to_R(q)
+        t = -R @ centre                                                                  # pose c2w: p_cam = R p_w + t
+        local = np.c_[r.uniform(-1.5, 1.5, n), r.uniform(-1.1, 1.1, n), r.uniform(1.0, 3.5, n)]
+        world = (local - t) @ R
+        if n:
+            world[r.random(n) < 0.08] = 0.0                                              # null map points / isZero(0)
+        pt_begin.append(total); pt_count.append(n); kf_t.append(t); pts.append(world); total += n
+    pose_cur = np.r_[_rotvec_quat(r.normal(0, 0.1, 3)), r.normal(0, 0.3, 3)]
+    return dict(pt_begin=np.array(pt_begin, np.int32), pt_count=np.array(pt_count, np.int32), kf_t=np.array(kf_t),
+                points=np.concatenate(pts) if total else np.zeros((0, 3)), pose_cur=pose_cur)
+
+
+def _rotvec_quat(w):
+    th = float(np.linalg.norm(w))
+    return np.array([1.0, 0, 0, 0]) if th < 1e-12 else np.r_[np.cos(th / 2), np.sin(th / 2) * np.asarray(w) / th]
