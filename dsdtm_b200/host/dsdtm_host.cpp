@@ -251,8 +251,11 @@ int GpuRuntime::Resident(const std::shared_ptr<GpuSlot>& s)
 GpuSlot::~GpuSlot() { if (g_runtime && slot >= 0) g_runtime->Release(slot); }
 
 // ================================================================================================ Frame / KeyFrame / MapPoint
+unsigned long Frame::mlNextId = 0;
+
 Frame::Frame(CameraPtr cam, const Mat8& gray, double ts) : mCamera(cam), mdCloTimestamp(ts), mColorImg(gray)
 {
+    mlId = mlNextId++;                                            // ref: src/Frame.cpp:30,39
     mPyra_levels = Config::Get<int>("Camera.MaxPyraLevels");      // ref: src/Frame.cpp:51-52
     mMin_Dist = Config::Get<int>("Camera.Min_dist");
     mvImg_Pyr.resize(mPyra_levels);
@@ -432,6 +435,108 @@ void Feature_detector::detect(Frame* frame, const double detection_threshold, co
     }
     ResetGrid();
     frame->mImgMask.release();                                    // ref: :152-153
+}
+
+// ================================================================================================ Map / Tracking (local-map selection)
+void Map::Pack(KeyFrame* kf, dsdtm_map_kf& row, std::vector<double>& pts) const
+{
+    const Vector3d t = kf->Get_Pose().translation();
+    for (int k = 0; k < 3; ++k) row.t[k] = t[k];
+    for (Feature* f : kf->mvFeatures) {                          // KeyFrame::mvMapPoints is parallel to the features (ref: src/Keyframe.cpp:11-19)
+        Vector3d P(0, 0, 0);                                     // null map point: the zero row the kernel skips (ref: src/Tracking.cpp:324-328)
+        if (f->Mpt) P = f->Mpt->Get_Pose();
+        pts.push_back(P[0]); pts.push_back(P[1]); pts.push_back(P[2]);
+    }
+}
+
+void Map::AddKeyFrame(KeyFrame* kf)
+{
+    if (mIndex.count(kf)) return;
+    mIndex[kf] = (int)mvKeyFrames.size();
+    mvKeyFrames.push_back(kf);
+    mRows.push_back(Rows{ mPoints, (int)kf->mvFeatures.size() });
+    mPoints += (int)kf->mvFeatures.size();
+}
+
+void Map::MarkMoved(KeyFrame* kf)
+{
+    auto it = mIndex.find(kf);
+    if (it != mIndex.end() && it->second < mUploadedKfs) mPending.push_back(it->second);
+}
+
+void Map::Sync()
+{
+    dsdtm_ctx* ctx = GpuRuntime::Instance().ctx();
+    std::vector<double> pts;
+    auto check = [&](int rc) { if (rc != 0) throw std::runtime_error(std::string("dsdtm_map_table_upload: ") + dsdtm_last_error(ctx)); };
+    for (int i : mPending) {                                     // rewritten rows: one key frame at a time (its rows are contiguous)
+        dsdtm_map_kf row{ mRows[i].pt_begin, mRows[i].pt_count, { 0, 0, 0 } };
+        pts.clear();
+        Pack(mvKeyFrames[i], row, pts);
+        check(dsdtm_map_table_upload(ctx, i, 1, &row, row.pt_begin, row.pt_count, pts.data()));
+    }
+    mPending.clear();
+    const int n = (int)mvKeyFrames.size();
+    if (mUploadedKfs < n) {                                      // appended key frames: one call for all of them
+        std::vector<dsdtm_map_kf> rows;
+        pts.clear();
+        for (int i = mUploadedKfs; i < n; ++i) {
+            dsdtm_map_kf row{ mRows[i].pt_begin, mRows[i].pt_count, { 0, 0, 0 } };
+            Pack(mvKeyFrames[i], row, pts);
+            rows.push_back(row);
+        }
+        check(dsdtm_map_table_upload(ctx, mUploadedKfs, n - mUploadedKfs, rows.data(), mRows[mUploadedKfs].pt_begin, (int)(pts.size() / 3), pts.data()));
+        mUploadedKfs = n;
+    }
+}
+
+Tracking::Tracking(CameraPtr cam, Map* map) : mMap(map), mFeature_Alignment(new Feature_Alignment(cam)), mCam(cam) {}
+Tracking::~Tracking() { delete mFeature_Alignment; }
+
+void Tracking::GetCloseKeyFrames(const Frame* tFrame, std::list<std::pair<KeyFrame*, double>>& tClose_kfs) const   // ref: src/Tracking.cpp:315-345
+{
+    mMap->Sync();
+    const int n = mMap->ReturnKeyFramesSize();
+    if (n == 0) return;
+    dsdtm_ctx* ctx = GpuRuntime::Instance().ctx();
+    static thread_local std::vector<uint8_t> visible;
+    static thread_local std::vector<double> dist;
+    visible.resize(n); dist.resize(n);
+    int32_t n_local = 0;
+    if (dsdtm_close_keyframes(ctx, tFrame->Get_Pose().data(), n, 0, visible.data(), dist.data(), nullptr, &n_local) != 0)
+        throw std::runtime_error(std::string("dsdtm_close_keyframes: ") + dsdtm_last_error(ctx));
+    for (int i = 0; i < n; ++i)
+        if (visible[i]) tClose_kfs.push_back(std::make_pair(mMap->Row(i), dist[i]));      // ref: :331-333, in GetAllKeyFrames order
+}
+
+void Tracking::UpdateLocalMap()                                   // ref: src/Tracking.cpp:257-313
+{
+    mFeature_Alignment->ResetGrid();
+    std::list<std::pair<KeyFrame*, double>> tClose_kfs;
+    GetCloseKeyFrames(mCurrentFrame.get(), tClose_kfs);
+    tClose_kfs.sort([](const std::pair<KeyFrame*, double>& a, const std::pair<KeyFrame*, double>& b) { return a.second < b.second; });   // ref: :266-267
+    mvpLocalKeyFrames.clear();
+    mvpLocalKeyFrames.reserve(10);
+    mvpLocalMapPoints.clear();
+    mLastReprojected = 0;
+    int tNum = 0;
+    for (auto iter = tClose_kfs.begin(); iter != tClose_kfs.end() && tNum < 10; iter++, tNum++) {   // ref: :276
+        KeyFrame* tKFrame = iter->first;
+        mvpLocalKeyFrames.push_back(tKFrame);
+        for (Feature* f : tKFrame->mvFeatures) {                  // KeyFrame::GetMapPoints()
+            MapPoint* tMp = f->Mpt;
+            if (tMp == nullptr) continue;
+            if (tMp->IsBad()) continue;
+            if (tMp->mLastProjectedFrameId == mCurrentFrame->mlId) continue;
+            tMp->mLastProjectedFrameId = mCurrentFrame->mlId;
+            if (mFeature_Alignment->ReprojectPoint(mCurrentFrame, tMp)) {
+                mvpLocalMapPoints[tMp] = tKFrame;
+                mLastReprojected++;
+                // ref: :299-300 IsinFrustum + IncreaseVisible feed MapPoint::Get_FoundRatio, which only LocalMapping's culling reads
+            }
+        }
+    }
+    // ref: :308-312 SetReferenceMapPoints is the viewer's copy
 }
 
 // ================================================================================================ Optimizer

@@ -159,6 +159,7 @@ public:
     std::map<KeyFrame*, size_t> Get_Observations() const { return mObservations; }   // ref: src/MapPoint.cpp (copy under mMutexObs)
     // the adapters' snapshot walks the observations in place (same std::map order) instead of copying the map per candidate
     template <class F> void ForEachObservation(F&& f) const { for (const auto& o : mObservations) f(o.first, o.second); }
+    unsigned long mLastProjectedFrameId = (unsigned long)-1;     // ref: include/MapPoint.h (UpdateLocalMap's per-frame dedupe)
 private:
     mutable std::mutex mMutexPos;
     Vector3d mPose;
@@ -190,6 +191,8 @@ public:
     const std::vector<dsdtm_lifted>& Lifted() const { return mLifted; }   // new: per-feature device results (depth, world point)
 
     CameraPtr mCamera;
+    unsigned long mlId;                // ref: include/Frame.h:106-107
+    static unsigned long mlNextId;
     double mdCloTimestamp;
     Mat8 mColorImg;
     std::vector<Mat8> mvImg_Pyr;
@@ -295,6 +298,47 @@ private:
     std::vector<Cell*> mCells;
     int mCell_size, mGrid_Cols, mGrid_Rows, mMax_pts, mPyr_levels;
     int mLastMatches = 0;
+};
+
+// ref: include/Map.h:23-66 -- the part Tracking::UpdateLocalMap reads, plus the bookkeeping of the device-resident map table
+// (one row per key frame, one row per entry of its mvMapPoints): a new key frame appends its rows, MarkMoved() queues the rows of
+// a key frame whose pose or points a bundle adjustment changed; Sync() uploads what is pending (called by GetCloseKeyFrames).
+class Map {
+public:
+    void AddKeyFrame(KeyFrame* kf);                              // ref: src/Map.cpp AddKeyFrame
+    std::vector<KeyFrame*> GetAllKeyFrames() const { return mvKeyFrames; }   // insertion order (the reference: std::set = address order)
+    int ReturnKeyFramesSize() const { return (int)mvKeyFrames.size(); }
+    void MarkMoved(KeyFrame* kf);                                // new: LocalBundleAdjustment's hook
+    void Sync();                                                 // new: pending rows -> dsdtm_map_table_upload
+    KeyFrame* Row(int i) const { return mvKeyFrames[i]; }
+private:
+    struct Rows { int pt_begin, pt_count; };
+    void Pack(KeyFrame* kf, dsdtm_map_kf& row, std::vector<double>& pts) const;
+    std::vector<KeyFrame*> mvKeyFrames;
+    std::vector<Rows> mRows;
+    std::map<KeyFrame*, int> mIndex;
+    std::vector<int> mPending;                                   // rows to (re)write
+    int mUploadedKfs = 0, mPoints = 0;
+};
+
+// ref: include/Tracking.h, src/Tracking.cpp:257-345 -- ONLY the local-map selection of the tracking thread: GetCloseKeyFrames and
+// UpdateLocalMap with the members they use. (The state machine around them is a caller of the path and stays the reference's.)
+class Tracking {
+public:
+    Tracking(CameraPtr cam, Map* map);
+    ~Tracking();
+    void SetCurrentFrame(FramePtr f) { mCurrentFrame = f; }
+    void GetCloseKeyFrames(const Frame* tFrame, std::list<std::pair<KeyFrame*, double>>& tClose_kfs) const;   // ref: :315-345
+    void UpdateLocalMap();                                                                                      // ref: :257-313
+    FramePtr mCurrentFrame;
+    Map* mMap;
+    Feature_Alignment* mFeature_Alignment;
+    std::vector<KeyFrame*> mvpLocalKeyFrames;
+    std::map<MapPoint*, KeyFrame*> mvpLocalMapPoints;
+    int LastReprojected() const { return mLastReprojected; }
+private:
+    CameraPtr mCam;
+    int mLastReprojected = 0;
 };
 
 // ref: include/Optimizer.h:23-44, src/Optimizer.cpp:20-101 -- the entry Tracking calls right after SearchLocalPoints

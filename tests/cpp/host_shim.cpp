@@ -27,7 +27,8 @@ static Feature_Alignment& feature_alignment(void* cam)
 extern "C" {
 
 const char* hs_last_error() { return g_err.c_str(); }
-void hs_reset() { g_fa.reset(); g_fa_cam = nullptr; GpuRuntime::Shutdown(); Config::Clear(); g_mps.clear(); }
+void hs_map_reset();
+void hs_reset() { hs_map_reset(); g_fa.reset(); g_fa_cam = nullptr; GpuRuntime::Shutdown(); Config::Clear(); g_mps.clear(); }
 void hs_config_set(const char* k, const char* v) { Config::Set(k, v); }
 int hs_config_load(const char* path) { try { Config::setParameterFile(path); return 0; } catch (std::exception& e) { g_err = e.what(); return -1; } }
 double hs_config_get(const char* k) { return Config::Get<double>(k); }
@@ -164,6 +165,34 @@ int hs_sparse_align_run(int maxl, int minl, int iters, void* cur, void* ref, dou
         *n_log = (int)l.size();
         for (int i = 0; i < (int)l.size() && i < cap; ++i) log[i] = l[i];
         return n;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// Tracking::UpdateLocalMap + SearchLocalPoints with the reference's own local-map selection (ref: src/Tracking.cpp:257-345):
+// a Map of all key frames, the 10 nearest close ones chosen on the device. local_out (optional): rows of mvpLocalKeyFrames.
+static std::unique_ptr<Map> g_map;
+static std::unique_ptr<Tracking> g_trk;
+static void* g_trk_cam = nullptr;
+void hs_map_reset() { g_trk.reset(); g_map.reset(); g_trk_cam = nullptr; }
+int hs_map_add_keyframe(void* kf) { if (!g_map) g_map.reset(new Map()); g_map->AddKeyFrame(static_cast<HsKf*>(kf)->kf); return g_map->ReturnKeyFramesSize(); }
+void hs_map_mark_moved(void* kf) { if (g_map) g_map->MarkMoved(static_cast<HsKf*>(kf)->kf); }
+void hs_keyframe_set_pose(void* kf, const double* pose7) { static_cast<HsKf*>(kf)->kf->Set_Pose(SE3(pose7)); }
+int hs_track_local_map(void* cam, void* cur, int* local_out, int* n_local, int* n_reprojected)
+{
+    try {
+        if (!g_map) g_map.reset(new Map());
+        if (!g_trk || g_trk_cam != cam) { g_trk.reset(new Tracking(*static_cast<CameraPtr*>(cam), g_map.get())); g_trk_cam = cam; }
+        FramePtr c = static_cast<HsFrame*>(cur)->f;
+        g_trk->SetCurrentFrame(c);
+        g_trk->UpdateLocalMap();
+        const std::vector<KeyFrame*> all = g_map->GetAllKeyFrames();
+        if (n_local) *n_local = (int)g_trk->mvpLocalKeyFrames.size();
+        if (local_out)
+            for (size_t i = 0; i < g_trk->mvpLocalKeyFrames.size(); ++i)
+                for (size_t k = 0; k < all.size(); ++k) if (all[k] == g_trk->mvpLocalKeyFrames[i]) local_out[i] = (int)k;
+        if (n_reprojected) *n_reprojected = g_trk->LastReprojected();
+        g_trk->mFeature_Alignment->SearchLocalPoints(c);
+        return g_trk->mFeature_Alignment->LastMatches();
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 

@@ -58,6 +58,10 @@ def lib():
         L.hs_frame_keyframe_lift.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.hs_warp_affine_single.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hs_circle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.hs_map_add_keyframe.argtypes = [C.c_void_p]
+        L.hs_map_mark_moved.argtypes = [C.c_void_p]
+        L.hs_keyframe_set_pose.argtypes = [C.c_void_p, C.c_void_p]
+        L.hs_track_local_map.argtypes = [C.c_void_p] * 5
         L.hs_pose_optimization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.hs_frame_set_feature.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _lib = L
@@ -161,6 +165,16 @@ def search_local_points_multi(cam_h, cur, kf_handles):
     if m < 0:
         raise RuntimeError(lib().hs_last_error().decode())
     return m, nrep.value
+
+
+def track_local_map(cam_h, cur):
+    """Tracking::UpdateLocalMap (device-side close-key-frame selection over the whole Map) + SearchLocalPoints
+    -> (matches, rows of mvpLocalKeyFrames in rank order, reprojected points)"""
+    local = np.full(16, -1, np.int32); n_local = C.c_int(0); nrep = C.c_int(0)
+    m = lib().hs_track_local_map(cam_h, cur.h, _p(local), C.byref(n_local), C.byref(nrep))
+    if m < 0:
+        raise RuntimeError(lib().hs_last_error().decode())
+    return m, local[:n_local.value].copy(), nrep.value
 
 
 def sparse_align_run(maxl, minl, iters, cur, ref):

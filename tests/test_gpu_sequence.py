@@ -488,3 +488,56 @@ def test_sequence_with_pose_optimization_after_matching(built):
     print("mean pose error (rad, m): sparse alignment", err_sa.mean(0), "after PoseOptimization", err_po.mean(0), "LM iterations", np.mean(its))
     # measured: 1.6e-5 rad / 3.4e-5 m after the refinement, 3.1e-5 / 7.1e-5 before
     assert err_po[:, 0].mean() <= err_sa[:, 0].mean() and err_po[:, 1].mean() <= err_sa[:, 1].mean(), (err_sa.mean(0), err_po.mean(0))
+
+
+# ------------------------------------------------------------------------------------------------ UpdateLocalMap with the device-side key-frame selection
+@pytest.mark.gpu
+def test_update_local_map_selects_the_oracles_keyframes(built):
+    """Tracking::UpdateLocalMap through the adapter (ref: src/Tracking.cpp:257-345): eight key frames strung along 4.2 m, the current
+    frame near the third. GetCloseKeyFrames runs on the device-resident map table; the close set, the distance ranking and the 10-nearest
+    cut must equal the oracle's, the map points of the chosen key frames are reprojected once each, and SearchLocalPoints matches
+    against them. Then a key frame is moved (bundle adjustment) and the table row is rewritten."""
+    cam = dict(S.KINECT)
+    scene = S.Scene(77)
+    cam_h = HL.configure(cam, max_fts=300, max_frames=24, dist=(0.0, 0.0, 0.0, 0.0, 0.0))
+    L = HL.lib()
+    oc = H.ocam(cam)
+    kf_poses = [S.pose_from_xi(np.array([0.6 * k, 0.05 * (k % 3), 0.02 * k, 0.0, 0.01 * k, 0.0])) for k in range(8)]
+    kfs, frames, tables = [], [], []
+    for k, pose in enumerate(kf_poses):
+        img, _, pts = S.render(scene, cam, pose, want_points=True)
+        g = HL.HFrame(cam_h, img, pose)
+        n = g.detect(5.0)
+        px, _, _ = g.features()
+        P = pts[px[:, 1].astype(int), px[:, 0].astype(int)]
+        has = np.ones(n, np.uint8); has[::9] = 0                      # some features without a map point: zero rows of the table
+        g.attach_points(P, has)
+        kf = L.hs_keyframe_new(g.h)
+        assert L.hs_map_add_keyframe(kf) == k + 1
+        kfs.append(kf); frames.append(g)
+        tables.append(np.where(has[:, None] > 0, P, 0.0))
+    pt_count = np.array([len(t) for t in tables], np.int32)
+    pt_begin = np.concatenate([[0], np.cumsum(pt_count)[:-1]]).astype(np.int32)
+    kf_t = np.array([p[4:] for p in kf_poses])
+    points = np.concatenate(tables)
+    pose_cur = S.pose_mul(S.pose_from_xi(np.array([0.012, -0.008, 0.006, 0.002, -0.003, 0.001])), kf_poses[2])
+    img, _ = S.render(scene, cam, pose_cur)
+    cur = HL.HFrame(cam_h, img, pose_cur)
+    m, local, nrep = HL.track_local_map(cam_h, cur)
+    vo, do, lo = O.close_keyframes(oc, pose_cur, pt_begin, pt_count, kf_t, points)
+    assert (local == lo).all() and 2 <= len(lo) < 8 and lo[0] == 2               # the far key frames see none of the current view
+    assert m >= 150 and nrep > 300
+    # every reprojected point belongs to a chosen key frame (the others were never walked)
+    ids = cur.mp_ids()
+    first_id = np.concatenate([[0], np.cumsum([int((np.abs(t).sum(1) > 0).sum()) for t in tables])])
+    owner = np.searchsorted(first_id, ids, side="right") - 1
+    assert set(owner.tolist()) <= set(lo.tolist())
+    # LocalBundleAdjustment moves the nearest key frame far away: its row is rewritten, it drops out of the ranking
+    moved = kf_poses[2].copy(); moved[4:] += np.array([50.0, 0.0, 0.0])
+    L.hs_keyframe_set_pose(kfs[2], HL._p(np.ascontiguousarray(moved)))
+    L.hs_map_mark_moved(kfs[2])
+    cur2 = HL.HFrame(cam_h, img, pose_cur)
+    m2, local2, _ = HL.track_local_map(cam_h, cur2)
+    kf_t2 = kf_t.copy(); kf_t2[2] = moved[4:]
+    _, _, lo2 = O.close_keyframes(oc, pose_cur, pt_begin, pt_count, kf_t2, points)
+    assert (local2 == lo2).all() and local2[-1] == 2 and m2 >= 100
