@@ -1,7 +1,7 @@
 """BASELINE configs[3]: the tracking front end on a synthetic 1000-frame RGB-D sequence at TUM shape (640x480, 16-bit depth,
 scale 5000), driven through the C++ adapter classes in Tracking's order (ref: src/Tracking.cpp:57,199-236,412-464):
-  new Frame (upload + pyramid) -> Sprase_ImgAlign(5,0,8)::Run(cur, last) -> UpdateLocalMap + SearchLocalPoints against the
-  last K key frames -> Optimizer::PoseOptimization -> every KF_EVERY frames CraeteKeyframe (detect on the free cells,
+  new Frame (upload + pyramid) -> Sprase_ImgAlign(5,0,8)::Run(cur, last) -> Tracking::UpdateLocalMap (GetCloseKeyFrames over the
+  WHOLE map on the device-resident table, the 10 nearest close key frames) + SearchLocalPoints -> Optimizer::PoseOptimization -> every KF_EVERY frames CraeteKeyframe (detect on the free cells,
   UndistortFeatures / depth lookup / UnProject on the device, new map points).
 Frames are ray-cast beforehand by a process pool (CPU work, not part of the loop). Reports the per-call wall clock, the matches,
 and the trajectory error against the ground truth."""
@@ -17,7 +17,6 @@ from dsdtm_b200 import synth as S
 
 SCALE = 5000.0
 KF_EVERY = 20
-LOCAL_KFS = 4
 SCENE_SEED = 1000
 
 
@@ -67,9 +66,10 @@ def main():
     assert g_last.detect(5.0) == 300
     lift(g_last, depth[0], 0)
     kfs = [L.hs_keyframe_new(g_last.h)]
+    L.hs_map_add_keyframe(kfs[-1])
     kf_frames = {0: g_last}
     T = {k: [] for k in ("frame", "run", "search", "opt", "keyframe")}
-    tracked, matches, iters, err_sa, err_po = [], [], [], [], []
+    tracked, matches, iters, err_sa, err_po, n_local, n_reproj = [], [], [], [], [], [], []
     lost = 0
     for k in range(1, n):
         t0 = time.perf_counter()
@@ -77,7 +77,8 @@ def main():
         t1 = time.perf_counter()
         nt, pose_sa, _ = HL.sparse_align_run(5, 0, 8, g_cur, g_last)
         t2 = time.perf_counter()
-        m, _ = HL.search_local_points_multi(cam_h, g_cur, kfs[-LOCAL_KFS:])
+        m, local, nrep = HL.track_local_map(cam_h, g_cur)
+        n_local.append(len(local)); n_reproj.append(nrep)
         t3 = time.perf_counter()
         pose_po, summ, _ = g_cur.pose_optimization()
         t4 = time.perf_counter()
@@ -92,6 +93,7 @@ def main():
             g_cur.detect(5.0, use_existing=True)
             lift(g_cur, depth[k], n_old)
             kfs.append(L.hs_keyframe_new(g_cur.h))
+            L.hs_map_add_keyframe(kfs[-1])
             kf_frames[k] = g_cur
             T["keyframe"].append(time.perf_counter() - t5)
         if g_last is not None and (k - 1) not in kf_frames:
@@ -102,6 +104,7 @@ def main():
     print("frames %d, key frames %d, lost %d" % (n, len(kfs), lost))
     print("tracked features (Run): median %d min %d; matches (SearchLocalPoints): median %d min %d; LM iterations: mean %.2f max %d"
           % (np.median(tracked), np.min(tracked), np.median(matches), np.min(matches), np.mean(iters), np.max(iters)))
+    print("local key frames per frame: median %d max %d; reprojected local map points: median %d max %d" % (np.median(n_local), np.max(n_local), np.median(n_reproj), np.max(n_reproj)))
     for key, name in (("frame", "Frame ctor (upload + pyramid)"), ("run", "Sprase_ImgAlign::Run"), ("search", "UpdateLocalMap + SearchLocalPoints"),
                       ("opt", "Optimizer::PoseOptimization"), ("keyframe", "CraeteKeyframe (detect + lift), per key frame")):
         print("%-46s: median %.1f us, p95 %.1f us" % ((name,) + us(T[key])))
