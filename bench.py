@@ -147,7 +147,7 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cam = dict(S.KINECT)
+    cam = dict(S.EUROC if args.cam == "euroc" else S.KINECT)
     B = args.pairs
     ctx = capi.Context(cam, levels=LEVELS, cell_size=15, max_feats=FEAT_STRIDE, max_patches=N_FEATS, max_frames=2 * B + 2, max_batch=B,
                        device=local)
@@ -472,12 +472,14 @@ def run_ours(args):
     if rank == 0:
         sa_gbs = sa_bytes / (sa_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC.replace("640x480", "%dx%d" % (cam["width"], cam["height"])), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic: %d ray-cast relief scenes tiled to %d pairs/GPU with per-pair start poses; every pair has its own frames, "
                     "features and patches in HBM" % (batch["n_scenes"], B),
-            "config": {"workload": "configs[0] shape batched: %d independent 640x480 kinect frame pairs per GPU, %d FAST/Shi-Tomasi features, "
-                                   "5-level pyramid(cur) + Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it)" % (B, N_FEATS, ppp),
+            "config": {"workload": "%s: %d independent %dx%d %s frame pairs per GPU, %d FAST/Shi-Tomasi features, "
+                                   "5-level pyramid(cur) + Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it)"
+                                   % ("configs[4] sweep" if args.cam == "euroc" else "configs[0] shape batched", B, cam["width"], cam["height"], args.cam, N_FEATS, ppp),
+                       "camera": args.cam,
                        "pairs_per_gpu": B, "features": N_FEATS, "levels": LEVELS, "sparse_align": ALIGN_CFG, "align2d_iters": ALIGN2D_ITERS,
                        "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (2 * B * ctx.L.dsdtm_frame_stride(ctx.hp) / 1e6)},
             "us_per_pair": ms_per_step * 1e3 / B,
@@ -549,7 +551,7 @@ def run_reference(args):
         return
     from dsdtm_b200 import synth as S, workload as W
     import oracle as O
-    cam = dict(S.KINECT)
+    cam = dict(S.EUROC if args.cam == "euroc" else S.KINECT)
     threads = os.cpu_count() or 1
     sample = args.cpu_sample
     # the same workload builder needs GPU FAST for feature selection; the reference arm uses the oracle's detector instead
@@ -582,11 +584,13 @@ def run_reference(args):
         O.pair_batch(*a)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+    line = {"impl": "reference", "metric": METRIC.replace("640x480", "%dx%d" % (cam["width"], cam["height"])), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
             "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic: %d ray-cast relief scenes tiled to a bounded sample of %d pairs per step" % (k, sample),
-            "config": {"workload": "configs[0] shape batched: independent 640x480 kinect frame pairs, %d features, 5-level pyramid(cur) + "
-                                   "Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it); CPU step = bounded sample of %d pairs" % (N_FEATS, N_FEATS, sample),
+            "config": {"workload": "%s: independent %dx%d %s frame pairs, %d features, 5-level pyramid(cur) + "
+                                   "Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it); CPU step = bounded sample of %d pairs"
+                                   % ("configs[4] sweep" if args.cam == "euroc" else "configs[0] shape batched", cam["width"], cam["height"], args.cam, N_FEATS, N_FEATS, sample),
+                       "camera": args.cam,
                        "features": N_FEATS, "levels": LEVELS, "sparse_align": ALIGN_CFG, "align2d_iters": ALIGN2D_ITERS},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d pairs per step, %d std::threads (the reference needs OpenCV/Eigen/Sophus/Ceres: not buildable here; "
@@ -605,6 +609,8 @@ def main():
     ap.add_argument("--scenes", type=int, default=16, help="distinct ray-cast scenes (tiled to --pairs)")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cam", default="kinect", choices=["kinect", "euroc"],
+                    help="kinect = 640x480 (the metric's configuration, default); euroc = 752x480, BASELINE configs[4]'s sweep geometry")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
