@@ -287,6 +287,7 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
         CK(cudaMemcpy(c->fast_tiles_d, tiles.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     }
     CK(sparse_align_init(c));
+    CK(pyramid_init(c));
     CK(pose_opt_init(c));
     CK(cudaMallocHost((void**)&c->stage_pin, kStageBytes));
     CK(cudaMalloc((void**)&c->stage_dev, kStageBytes));

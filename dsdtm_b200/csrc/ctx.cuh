@@ -162,6 +162,7 @@ void stage_end(dsdtm_ctx* c, int n_launches);
 int  stage_collect(dsdtm_ctx* c);
 
 // ---- kernel launchers (each returns cudaGetLastError()) ----
+cudaError_t pyramid_init(dsdtm_ctx* c);
 cudaError_t launch_pyramid(dsdtm_ctx* c, int first_slot, int n, cudaStream_t s);
 cudaError_t launch_pyramid_slots(dsdtm_ctx* c, const int* slots_d, int n, cudaStream_t s);
 cudaError_t launch_fast_cells(dsdtm_ctx* c, int first_slot, int n, int barrier, float seed_score, bool use_occupied,

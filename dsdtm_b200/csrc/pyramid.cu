@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128) pyrdown_strip_kernel(uint8_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Bulk-staged kernel (levels whose source width is a multiple of 16): level images are dense, so the 2*TH+3 source rows
+// Bulk-staged kernel (levels whose source width is a multiple of 8 and whose output width is a multiple of 4): level images are dense, so the 2*TH+3 source rows
 // of a tile of TH output rows are ONE contiguous byte range. One elected thread issues a single cp.async.bulk (TMA 1-D)
 // for it and everybody waits on the mbarrier; memory latency is covered by the other resident CTAs (a tile is ~12-22 KB,
 // 10-18 CTAs per SM), not by per-thread loads, and the arithmetic reads shared memory with immediate offsets: ~45
@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(1024) pyrdown_bulk_kernel(uint8_t* __restrict_
     uint8_t* __restrict__ dst = frames + (size_t)slot * frame_stride + dst_off;
     const int ty0 = blockIdx.x * tile_rows, ty1 = min(ty0 + tile_rows, dh);
     const int lo = max(2 * ty0 - 2, 0), hi = min(2 * ty1, h - 1);            // source rows lo..hi: one contiguous range
-    const uint32_t bytes = (uint32_t)(hi - lo + 1) * (uint32_t)w;
+    // the copy starts at an even row of a level whose width is a multiple of 8: 16-byte aligned; its size is rounded up to 16
+    // bytes (an odd number of rows of a width that is 8 mod 16 ends on an 8-byte boundary) -- the extra 8 bytes are the next
+    // row or, behind the last level, the zero padding of the slot
+    const uint32_t bytes = ((uint32_t)(hi - lo + 1) * (uint32_t)w + 15u) & ~15u;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -256,21 +259,116 @@ __global__ void __launch_bounds__(1024) pyrdown_bulk_kernel(uint8_t* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Whole-level kernel for the SMALL ragged levels (752x480: 188x120 -> 94x60 -> 47x30, widths that are not multiples of 8): one CTA
+// stages an entire source level in shared memory (one contiguous, 16-byte aligned range of <= 22.6 KB), does the horizontal pass into
+// a u16 plane and the vertical pass from it -- 5 + 5 shared-memory reads per output -- and keeps its output in shared memory as the
+// source of the NEXT level, so the whole tail of the pyramid is one launch and one read of its first level. (The tile kernel's 64x16
+// tiles carry a 2.6x halo overhead at this size: 0.38 TB/s on these two levels = 45 % of the 752x480 pyramid's time.)
+// Warps walk rows, lanes walk columns: no integer division in the loops.
+constexpr int SMALL_THREADS = 256;
+constexpr int SMALL_SMEM_LIMIT = 96 * 1024;
+struct SmallChain {
+    int n;                                   // levels produced by this launch
+    int w[DSDTM_MAX_LEVELS], h[DSDTM_MAX_LEVELS];      // [0] = the staged source level, [i + 1] = the i-th produced level
+    unsigned off[DSDTM_MAX_LEVELS];
+    int src_pad, h_bytes;                    // shared-memory plan: source plane | u16 sums | next source plane
+};
+
+__global__ void __launch_bounds__(SMALL_THREADS) pyrdown_small_kernel(uint8_t* __restrict__ frames, unsigned frame_stride, int first_slot,
+                                                                      const int* __restrict__ slots, const SmallChain ch)
+{
+    extern __shared__ __align__(16) uint8_t s_small[];
+    uint8_t* s_a = s_small;
+    uint16_t* s_h = reinterpret_cast<uint16_t*>(s_small + ch.src_pad);
+    uint8_t* s_b = s_small + ch.src_pad + ch.h_bytes;
+    const int slot = slots ? slots[blockIdx.x] : first_slot + blockIdx.x;
+    uint8_t* __restrict__ frame = frames + (size_t)slot * frame_stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = SMALL_THREADS / 32;
+    {
+        // the slot ends with >= 64 zero bytes, so rounding the last 16-byte word up never leaves the slot
+        const uint4* src = reinterpret_cast<const uint4*>(frame + ch.off[0]);            // level offsets are 16-byte aligned
+        for (int i = tid; i < (ch.src_pad >> 4); i += SMALL_THREADS) reinterpret_cast<uint4*>(s_a)[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    uint8_t* cur = s_a;
+    uint8_t* nxt = s_b;
+    for (int l = 0; l < ch.n; ++l) {
+        const int w = ch.w[l], h = ch.h[l], dw = ch.w[l + 1], dh = ch.h[l + 1];
+        for (int r = warp; r < h; r += NW) {
+            const uint8_t* row = cur + r * w;
+            for (int x = lane; x < dw; x += 32) {
+                const int c = 2 * x;
+                int sum;
+                if (c >= 2 && c + 2 < w) sum = row[c - 2] + 4 * row[c - 1] + 6 * row[c] + 4 * row[c + 1] + row[c + 2];
+                else sum = row[reflect101(c - 2, w)] + 4 * row[reflect101(c - 1, w)] + 6 * row[c] + 4 * row[reflect101(c + 1, w)] + row[reflect101(c + 2, w)];
+                s_h[r * dw + x] = (uint16_t)sum;
+            }
+        }
+        __syncthreads();
+        uint8_t* __restrict__ dst = frame + ch.off[l + 1];
+        const bool keep = l + 1 < ch.n;
+        for (int y = warp; y < dh; y += NW) {
+            const int r = 2 * y;
+            const uint16_t* p0 = s_h + reflect101(r - 2, h) * dw;
+            const uint16_t* p1 = s_h + reflect101(r - 1, h) * dw;
+            const uint16_t* p2 = s_h + r * dw;
+            const uint16_t* p3 = s_h + reflect101(r + 1, h) * dw;
+            const uint16_t* p4 = s_h + reflect101(r + 2, h) * dw;
+            for (int x = lane; x < dw; x += 32) {
+                const uint8_t v = (uint8_t)((p0[x] + 4 * p1[x] + 6 * p2[x] + 4 * p3[x] + p4[x] + 128) >> 8);
+                dst[y * dw + x] = v;
+                if (keep) nxt[y * dw + x] = v;
+            }
+        }
+        __syncthreads();
+        uint8_t* t = cur; cur = nxt; nxt = t;      // the produced level is the next source (it fits where the first one was, too)
+    }
+}
+
+// plans the chain of levels first .. that one CTA can produce from level first - 1; returns the number of levels (0: not eligible)
+int plan_small_chain(const LevelGeom& g, int first, SmallChain& ch, size_t& smem)
+{
+    const int w0 = g.w[first - 1], h0 = g.h[first - 1];
+    if (h0 < 3) return 0;
+    ch.n = 0;
+    ch.w[0] = w0; ch.h[0] = h0; ch.off[0] = g.off[first - 1];
+    ch.src_pad = (w0 * h0 + 15) & ~15;
+    ch.h_bytes = (2 * h0 * g.w[first] + 15) & ~15;
+    const int next_bytes = (g.w[first] * g.h[first] + 15) & ~15;       // every later plane is smaller than this one
+    smem = (size_t)ch.src_pad + ch.h_bytes + next_bytes;
+    if (smem > (size_t)SMALL_SMEM_LIMIT) return 0;
+    for (int l = first; l < g.levels; ++l) {
+        if (g.h[l - 1] < 3) break;
+        ch.w[ch.n + 1] = g.w[l]; ch.h[ch.n + 1] = g.h[l]; ch.off[ch.n + 1] = g.off[l];
+        ch.n++;
+    }
+    return ch.n;
+}
+
 cudaError_t launch_levels(dsdtm_ctx* c, int first_slot, const int* slots_d, int n, cudaStream_t s)
 {
     const LevelGeom& g = c->geo;
+    SmallChain chain;
+    size_t chain_smem = 0;
     for (int l = 1; l < g.levels; ++l) {
         const int w = g.w[l - 1], h = g.h[l - 1], dw = g.w[l], dh = g.h[l];
-        if ((w & 15) == 0 && h >= 3 && 2 * dw == w && (dw >> 2) <= 1024 && (size_t)(2 * BRPT + 3) * w + 2 * BULK_PAD <= 48 * 1024 && c->pyr_kernel == 0) {
+        if ((w & 7) == 0 && (dw & 3) == 0 && h >= 3 && 2 * dw == w && (dw >> 2) <= 1024 && (size_t)(2 * BRPT + 3) * w + 2 * BULK_PAD + 16 <= 48 * 1024 && c->pyr_kernel == 0) {
             const int xq = dw >> 2;
             int strips = std::max(1, DSDTM_PYR_BULK_THREADS / xq);
             strips = std::min(strips, (dh + BRPT - 1) / BRPT);
             while (xq * strips > 1024) --strips;
-            while (strips > 1 && (size_t)(2 * strips * BRPT + 3) * w + 2 * BULK_PAD > 48 * 1024) --strips;
+            while (strips > 1 && (size_t)(2 * strips * BRPT + 3) * w + 2 * BULK_PAD + 16 > 48 * 1024) --strips;
             const int tile_rows = strips * BRPT;
-            const size_t smem = (size_t)(2 * tile_rows + 3) * w + 2 * BULK_PAD;
+            const size_t smem = (size_t)(2 * tile_rows + 3) * w + 2 * BULK_PAD + 16;   // + the round-up of the copy to 16 bytes
             dim3 grid((dh + tile_rows - 1) / tile_rows, n);
             pyrdown_bulk_kernel<<<grid, xq * strips, smem, s>>>(c->frames_d, g.frame_stride, first_slot, slots_d, g.off[l - 1], g.off[l], w, h, dw, dh, tile_rows);
+        } else if (c->pyr_kernel == 0 && plan_small_chain(g, l, chain, chain_smem) > 0) {
+            pyrdown_small_kernel<<<n, SMALL_THREADS, chain_smem, s>>>(c->frames_d, g.frame_stride, first_slot, slots_d, chain);
+            c->launches++;
+            l += chain.n - 1;                     // the chain produced levels l .. l + n - 1
+            continue;
         } else if ((w & 7) == 0 && (dw & 3) == 0 && h >= 3 && 2 * dw == w && c->pyr_kernel != 1) {
             const int n_items = (dw >> 2) * ((dh + RPT - 1) / RPT);
             dim3 grid((n_items + 127) / 128, n);
@@ -286,6 +384,7 @@ cudaError_t launch_levels(dsdtm_ctx* c, int first_slot, const int* slots_d, int 
 
 }  // namespace
 
+cudaError_t pyramid_init(dsdtm_ctx*) { return cudaFuncSetAttribute(pyrdown_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM_LIMIT); }
 cudaError_t launch_pyramid(dsdtm_ctx* c, int first_slot, int n, cudaStream_t s) { return launch_levels(c, first_slot, nullptr, n, s); }
 cudaError_t launch_pyramid_slots(dsdtm_ctx* c, const int* slots_d, int n, cudaStream_t s) { return launch_levels(c, 0, slots_d, n, s); }
 

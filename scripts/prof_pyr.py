@@ -10,8 +10,9 @@ def main():
     ap.add_argument("--frames", type=int, default=2072)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--pyr", type=int, default=0)
+    ap.add_argument("--cam", default="kinect", choices=["kinect", "euroc"])
     a = ap.parse_args()
-    cam = dict(S.KINECT)
+    cam = dict(S.EUROC if a.cam == "euroc" else S.KINECT)
     ctx = capi.Context(cam, levels=5, cell_size=15, max_feats=64, max_patches=8, max_frames=a.frames, max_batch=1)
     ctx.set_option("pyramid_kernel", a.pyr)
     rng = np.random.default_rng(0)
