@@ -265,65 +265,103 @@ __global__ void __launch_bounds__(1024) pyrdown_bulk_kernel(uint8_t* __restrict_
 // a u16 plane and the vertical pass from it -- 5 + 5 shared-memory reads per output -- and keeps its output in shared memory as the
 // source of the NEXT level, so the whole tail of the pyramid is one launch and one read of its first level. (The tile kernel's 64x16
 // tiles carry a 2.6x halo overhead at this size: 0.38 TB/s on these two levels = 45 % of the 752x480 pyramid's time.)
-// Warps walk rows, lanes walk columns: no integer division in the loops.
+// Warps walk rows, lanes walk column groups: no integer division in the loops.
 constexpr int SMALL_THREADS = 256;
 constexpr int SMALL_SMEM_LIMIT = 96 * 1024;
+constexpr int SMALL_FP = 8;                  // bytes in front of column 0 of a staged row (columns -2, -1 live there)
+// A staged plane keeps every row at an 8-byte aligned pitch with the reflect-101 border MATERIALISED (columns -2, -1 and
+// w .. w + 10), so that every group of four outputs is the interior formula of the bulk kernel -- one aligned LDS.64 + two LDS.32 +
+// four DP4A -- whatever the width: no edge cases, no byte-wide arithmetic (the first version did 5 LDS.U8 + 4 multiply-adds per
+// sum and was issue-bound: 116 us per 2048 frames for 6 % of the pyramid's bytes).
+__host__ __device__ constexpr int small_pitch(int w) { return (SMALL_FP + w + 11 + 7) & ~7; }
+
 struct SmallChain {
     int n;                                   // levels produced by this launch
     int w[DSDTM_MAX_LEVELS], h[DSDTM_MAX_LEVELS];      // [0] = the staged source level, [i + 1] = the i-th produced level
     unsigned off[DSDTM_MAX_LEVELS];
-    int src_pad, h_bytes;                    // shared-memory plan: source plane | u16 sums | next source plane
+    int a_bytes, h_bytes;                    // shared-memory plan: plane A | packed horizontal sums | plane B
 };
+
+__device__ __forceinline__ void small_fill_border(uint8_t* plane, int w, int h, int pitch, int warp, int lane)
+{
+    // columns -2, -1 <- 2, 1 ; columns w + k <- reflect101(w + k), k = 0 .. 10
+    for (int r = warp; r < h; r += SMALL_THREADS / 32) {
+        uint8_t* row = plane + r * pitch + SMALL_FP;
+        if (lane < 13) {
+            const int col = lane < 2 ? lane - 2 : w + (lane - 2);
+            row[col] = row[reflect101(col, w)];
+        }
+    }
+}
 
 __global__ void __launch_bounds__(SMALL_THREADS) pyrdown_small_kernel(uint8_t* __restrict__ frames, unsigned frame_stride, int first_slot,
                                                                       const int* __restrict__ slots, const SmallChain ch)
 {
     extern __shared__ __align__(16) uint8_t s_small[];
     uint8_t* s_a = s_small;
-    uint16_t* s_h = reinterpret_cast<uint16_t*>(s_small + ch.src_pad);
-    uint8_t* s_b = s_small + ch.src_pad + ch.h_bytes;
+    uint2* s_h = reinterpret_cast<uint2*>(s_small + ch.a_bytes);
+    uint8_t* s_b = s_small + ch.a_bytes + ch.h_bytes;
     const int slot = slots ? slots[blockIdx.x] : first_slot + blockIdx.x;
     uint8_t* __restrict__ frame = frames + (size_t)slot * frame_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = SMALL_THREADS / 32;
     {
-        // the slot ends with >= 64 zero bytes, so rounding the last 16-byte word up never leaves the slot
-        const uint4* src = reinterpret_cast<const uint4*>(frame + ch.off[0]);            // level offsets are 16-byte aligned
-        for (int i = tid; i < (ch.src_pad >> 4); i += SMALL_THREADS) reinterpret_cast<uint4*>(s_a)[i] = __ldg(src + i);
+        const int w = ch.w[0], h = ch.h[0], pitch = small_pitch(w);
+        const uint8_t* __restrict__ src = frame + ch.off[0];
+        if ((w & 3) == 0) {                                              // rows start on 4-byte boundaries on both sides
+            for (int r = warp; r < h; r += NW)
+                for (int j = lane; j < (w >> 2); j += 32)
+                    *reinterpret_cast<uint32_t*>(s_a + r * pitch + SMALL_FP + 4 * j) = __ldg(reinterpret_cast<const uint32_t*>(src + r * w) + j);
+        } else {
+            for (int r = warp; r < h; r += NW)
+                for (int j = lane; j < w; j += 32) s_a[r * pitch + SMALL_FP + j] = __ldg(src + r * w + j);
+        }
+        __syncthreads();
+        small_fill_border(s_a, w, h, pitch, warp, lane);
+        __syncthreads();
     }
-    __syncthreads();
     uint8_t* cur = s_a;
     uint8_t* nxt = s_b;
     for (int l = 0; l < ch.n; ++l) {
         const int w = ch.w[l], h = ch.h[l], dw = ch.w[l + 1], dh = ch.h[l + 1];
+        const int pitch = small_pitch(w), G = (dw + 3) >> 2;             // G groups of four outputs per row
         for (int r = warp; r < h; r += NW) {
-            const uint8_t* row = cur + r * w;
-            for (int x = lane; x < dw; x += 32) {
-                const int c = 2 * x;
-                int sum;
-                if (c >= 2 && c + 2 < w) sum = row[c - 2] + 4 * row[c - 1] + 6 * row[c] + 4 * row[c + 1] + row[c + 2];
-                else sum = row[reflect101(c - 2, w)] + 4 * row[reflect101(c - 1, w)] + 6 * row[c] + 4 * row[reflect101(c + 1, w)] + row[reflect101(c + 2, w)];
-                s_h[r * dw + x] = (uint16_t)sum;
-            }
+            const uint8_t* row = cur + r * pitch + SMALL_FP;
+            for (int g = lane; g < G; g += 32) s_h[r * G + g] = hrow_s(row, 8 * g, false, false);
         }
         __syncthreads();
         uint8_t* __restrict__ dst = frame + ch.off[l + 1];
         const bool keep = l + 1 < ch.n;
+        const int npitch = small_pitch(dw);
         for (int y = warp; y < dh; y += NW) {
             const int r = 2 * y;
-            const uint16_t* p0 = s_h + reflect101(r - 2, h) * dw;
-            const uint16_t* p1 = s_h + reflect101(r - 1, h) * dw;
-            const uint16_t* p2 = s_h + r * dw;
-            const uint16_t* p3 = s_h + reflect101(r + 1, h) * dw;
-            const uint16_t* p4 = s_h + reflect101(r + 2, h) * dw;
-            for (int x = lane; x < dw; x += 32) {
-                const uint8_t v = (uint8_t)((p0[x] + 4 * p1[x] + 6 * p2[x] + 4 * p3[x] + p4[x] + 128) >> 8);
-                dst[y * dw + x] = v;
-                if (keep) nxt[y * dw + x] = v;
+            const uint2* p0 = s_h + reflect101(r - 2, h) * G;
+            const uint2* p1 = s_h + reflect101(r - 1, h) * G;
+            const uint2* p2 = s_h + r * G;
+            const uint2* p3 = s_h + reflect101(r + 1, h) * G;
+            const uint2* p4 = s_h + reflect101(r + 2, h) * G;
+            for (int g = lane; g < G; g += 32) {
+                const uint2 r0 = p0[g], r1 = p1[g], r2 = p2[g], r3 = p3[g], r4 = p4[g];
+                const uint32_t a = r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + 0x00800080u;
+                const uint32_t b = r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + 0x00800080u;
+                const uint32_t out = __byte_perm(a, b, 0x7531);
+                const int x = 4 * g;
+                if ((dw & 3) == 0) {
+                    *reinterpret_cast<uint32_t*>(dst + y * dw + x) = out;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (x + k < dw) dst[y * dw + x + k] = (uint8_t)(out >> (8 * k));
+                }
+                if (keep) *reinterpret_cast<uint32_t*>(nxt + y * npitch + SMALL_FP + x) = out;   // columns >= dw are rewritten by the border fill
             }
         }
         __syncthreads();
-        uint8_t* t = cur; cur = nxt; nxt = t;      // the produced level is the next source (it fits where the first one was, too)
+        if (keep) {
+            small_fill_border(nxt, dw, dh, npitch, warp, lane);
+            __syncthreads();
+        }
+        uint8_t* t = cur; cur = nxt; nxt = t;      // the produced level is the next source
     }
 }
 
@@ -331,16 +369,16 @@ __global__ void __launch_bounds__(SMALL_THREADS) pyrdown_small_kernel(uint8_t* _
 int plan_small_chain(const LevelGeom& g, int first, SmallChain& ch, size_t& smem)
 {
     const int w0 = g.w[first - 1], h0 = g.h[first - 1];
-    if (h0 < 3) return 0;
+    if (h0 < 3 || w0 < 3) return 0;
     ch.n = 0;
     ch.w[0] = w0; ch.h[0] = h0; ch.off[0] = g.off[first - 1];
-    ch.src_pad = (w0 * h0 + 15) & ~15;
-    ch.h_bytes = (2 * h0 * g.w[first] + 15) & ~15;
-    const int next_bytes = (g.w[first] * g.h[first] + 15) & ~15;       // every later plane is smaller than this one
-    smem = (size_t)ch.src_pad + ch.h_bytes + next_bytes;
+    ch.a_bytes = (h0 * small_pitch(w0) + 15) & ~15;                     // every later plane that lands here is smaller
+    ch.h_bytes = (h0 * ((g.w[first] + 3) >> 2) * 8 + 15) & ~15;
+    const int b_bytes = (g.h[first] * small_pitch(g.w[first]) + 15) & ~15;
+    smem = (size_t)ch.a_bytes + ch.h_bytes + b_bytes;
     if (smem > (size_t)SMALL_SMEM_LIMIT) return 0;
     for (int l = first; l < g.levels; ++l) {
-        if (g.h[l - 1] < 3) break;
+        if (g.h[l - 1] < 3 || g.w[l - 1] < 3) break;
         ch.w[ch.n + 1] = g.w[l]; ch.h[ch.n + 1] = g.h[l]; ch.off[ch.n + 1] = g.off[l];
         ch.n++;
     }
