@@ -490,8 +490,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"kernel": "sparse_align_kernel", "bound": "hbm", "achieved": sa_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": sa_gbs / hbm_peak, "traffic": measured_traffic("sparse_align_kernel", B), "peak_source": peak_src,
-                         "ms_per_launch": sa_ms, "algorithmic_bytes_per_launch": sa_bytes, "ncu": ncu_summary("sparse_align_kernel"),
+                         "frac": sa_gbs / hbm_peak, "traffic": measured_traffic("sparse_align_kernel", B) if args.cam == "kinect" else None, "peak_source": peak_src,
+                         "ms_per_launch": sa_ms, "algorithmic_bytes_per_launch": sa_bytes, "ncu": ncu_summary("sparse_align_kernel") if args.cam == "kinect" else None,   # the committed capture is the 640x480 step
                          "note": "dependent Gauss-Newton chain: latency/issue-bound, not bandwidth-bound (SURVEY 8d): ncu issue slots busy 38 %, "
                                  "fp64 pipe 38 %, DRAM 18 %, L1/TEX hit 74 % (profiles/r1_sa_bench_summary.txt); traffic is the ncu DRAM byte count "
                                  "(32-byte sectors for 5-byte window rows) scaled per pair; see stages for the HBM-bound kernels"},
