@@ -211,3 +211,44 @@ def test_clahe_matches_cv2_golden(golden):
     for name, h, w, clip, tiles in H.CLAHE_CASES:
         img = H.clahe_input(name, h, w)
         assert (O.clahe(img, clip, tiles) == g[name]).all(), name
+
+
+def test_se3_exp_matches_the_matrix_exponential_scipy_computes():
+    """An anchor outside this repository for the Sophus restatement (SE3::exp, translation-first twist; SE3 * SE3; SE3 * point):
+    scipy.linalg.expm of the 4x4 twist matrix and plain matrix products."""
+    from scipy.linalg import expm
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(3)
+
+    def mat(p):
+        M = np.eye(4)
+        M[:3, :3] = Rot.from_quat(np.r_[p[1:4], p[0]]).as_matrix(); M[:3, 3] = p[4:]
+        return M
+    for scale in (1e-12, 1e-6, 0.3, 2.5):
+        for _ in range(4):
+            x = rng.uniform(-scale, scale, 6)
+            W = np.array([[0, -x[5], x[4]], [x[5], 0, -x[3]], [-x[4], x[3], 0]])
+            T = np.zeros((4, 4)); T[:3, :3] = W; T[:3, 3] = x[:3]
+            a = O.se3_exp(x)
+            assert np.allclose(mat(a), expm(T), atol=1e-12)
+            b = O.se3_exp(rng.uniform(-0.5, 0.5, 6))
+            assert np.allclose(mat(O.se3_mul(a, b)), mat(a) @ mat(b), atol=1e-12)
+            assert np.allclose(mat(O.se3_inv(a)) @ mat(a), np.eye(4), atol=1e-12)
+            p = rng.uniform(-2, 2, 3)
+            assert np.allclose(O.se3_act(a, p), (mat(a) @ np.r_[p, 1.0])[:3], atol=1e-12)
+
+
+def test_pose_parameterisation_round_trip_and_plus_against_scipy():
+    """PoseLocalParameterization (ref: include/Optimizer.h:220-236) as the oracle's PoseOptimization uses it: with no residual the
+    solve hands back exp(log(R)) of the start pose (SO3::log / SO3::exp round trip); one capped iteration moves the pose by a left
+    multiplication -- checked through scipy's rotation vectors."""
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(4)
+    for _ in range(10):
+        w = rng.uniform(-1, 1, 3); w *= rng.uniform(0.0, 3.0) / np.linalg.norm(w)      # rotation angles up to 3 rad
+        q = Rot.from_rotvec(w).as_quat()
+        pose = np.r_[q[3], q[:3], rng.uniform(-1, 1, 3)]
+        out, res, sm = O.pose_optimization(np.zeros((0, 3)), np.zeros(0, np.int32), np.zeros((0, 3)), pose)
+        assert sm["termination"] == O.BA_NO_RESIDUALS and len(res) == 0
+        same = np.abs(out - pose).max() < 1e-14 or np.abs(out[:4] + pose[:4]).max() < 1e-14      # q and -q are the same rotation
+        assert same and np.abs(out[4:] - pose[4:]).max() == 0
