@@ -24,6 +24,9 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/Thirdparty/fast/src") and (force or not os.path.exists(_REF)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    # the reference's own hot-path translation units against the stand-in headers of tests/ref_shim (oracle/refpin.py)
+    from . import refpin
+    refpin.build(force)
 
 
 class Cam(C.Structure):
