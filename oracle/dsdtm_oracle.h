@@ -6,17 +6,18 @@
  * (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference leg).
  * Nothing under dsdtm_b200/ may include, link or call this file.
  *
- * Pinning status (see DESIGN.md "Oracle"):
- *   - FAST-10 detect/score/nonmax : PINNED against the reference's own Thirdparty/fast
- *     sources compiled into oracle/_ref/libfast_ref.so, and the 167-corner KAT of
- *     Thirdparty/fast/test/test.cpp:20,45,52.
+ * Pinning status:
+ *   - FAST-10 detect/score/nonmax : PINNED against the reference's own Thirdparty/fast sources (oracle/_ref/libfast_ref.so)
+ *     and the 167-corner KAT of Thirdparty/fast/test/test.cpp:20,45,52.
  *   - pyrDown, circle, undistortPoints, CLAHE : PINNED against cv2 4.13 goldens (tests/golden/).
- *   - Shi-Tomasi, grid selection, sparse alignment, WarpAffine, Align2D, ReprojectPoint / Get_ClosetObs, depth lookup, UnProject:
- *     PARITY UNPINNED -- the reference ships no golden vector for them and cannot be
- *     built here (needs OpenCV/Eigen/Sophus/Ceres/glog/Boost/Pangolin); restated line by
- *     line from the cited sources, Sophus/Eigen semantics restated from their published
- *     algorithms (Sophus non-templated 1.0 se3.cpp/so3.cpp, Eigen 3.2/3.3 Inverse_SSE-free
- *     3x3 cofactor inverse and pivoted LDLT).
+ *   - Shi-Tomasi, grid selection, sparse alignment, SolveAffine / WarpAffine / Align2D, ReprojectPoint / SearchLocalPoints /
+ *     Get_ClosetObs, GetCloseKeyFrames / UpdateLocalMap, depth lookup, UnProject : PINNED (round 2) against the reference's OWN
+ *     translation units, compiled unmodified from /root/reference into oracle/_ref/libdsdtm_ref.so against the stand-in
+ *     third-party headers of tests/ref_shim (recipe: oracle/Makefile target ref_dsdtm; comparisons: tests/test_ref_pin.py, bit
+ *     equality; travelling golden: tests/golden/refpin.npz).
+ *   - what happens INSIDE Eigen / Sophus calls (LDLT solve, reduction association, SE3::exp, quaternion product) and
+ *     ceres::Solve (PoseOptimization) : RESTATED FROM THE PUBLISHED ALGORITHMS, UNPINNED -- those libraries are neither under
+ *     /root/reference nor installed.
  *
  * All citations "ref:" are paths below /root/reference.
  */

@@ -12,9 +12,42 @@
 #include <cstring>
 #include <vector>
 
-#include "Feature_alignment.h"
-#include "Feature_detection.h"
-#include "Sprase_ImageAlign.h"
+#include <chrono>
+#include <ctime>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <iterator>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <utility>
+
+// every third-party stand-in (and through them every standard header) is parsed BEFORE access control is lifted below
+#include <Eigen/Dense>
+#include <opencv2/opencv.hpp>
+#include <sophus/se3.h>
+#include <glog/logging.h>
+#include <pangolin/pangolin.h>
+#include <ceres/ceres.h>
+#include "boost/bind.hpp"
+#include "MCDWrapper.h"
+#include "fast/fast.h"
+
+// Tracking::GetCloseKeyFrames / UpdateLocalMap and the members they fill are private / protected (ref: include/Tracking.h:76-160).
+// The reference's files are not touched: access control is lifted for THIS translation unit only, after the standard headers
+// above have been included (access specifiers change neither layout nor name mangling).
+#define private public
+#define protected public
+#include "Tracking.h"
+#undef private
+#undef protected
 
 using namespace DSDTM;
 
@@ -289,6 +322,36 @@ int ref_find_match_direct(int mp, int cur, double px[2], int* level)
 void ref_fa_reset_grid() { g_fa->ResetGrid(); }
 int ref_fa_reproject_point(int cur, int mp) { return g_fa->ReprojectPoint(g_frames[cur], g_mps[mp]) ? 1 : 0; }
 void ref_fa_search_local_points(int cur) { g_fa->SearchLocalPoints(g_frames[cur]); }
+
+// ---- Tracking (ref: src/Tracking.cpp:14-38,257-345): the caller's half of SURVEY 8f-1 ----
+static Tracking* g_tracker = nullptr;
+int ref_tracking_create()
+{
+    g_tracker = new Tracking(g_cam, g_map, nullptr);
+    return 0;
+}
+void ref_keyframe_add_mappoint(int kf, int idx, int mp) { g_kfs[kf]->Add_MapPoint(g_mps[mp], idx); }
+// GetCloseKeyFrames(frame, list): returns the list as (key-frame id, distance) in the order the reference produced it
+int ref_tracking_close_keyframes(int fr, int* kf_ids, double* dist, int cap)
+{
+    std::list<std::pair<KeyFrame*, double> > l;
+    g_tracker->GetCloseKeyFrames(g_frames[fr].get(), l);
+    int n = 0;
+    for (auto it = l.begin(); it != l.end() && n < cap; ++it, ++n) { kf_ids[n] = find_kf(it->first); dist[n] = it->second; }
+    return (int)l.size();
+}
+// UpdateLocalMap() on mCurrentFrame = frame: returns mvpLocalKeyFrames (ids, in order) and the number of local map points
+int ref_tracking_update_local_map(int fr, int* local_kfs, int cap, int* n_local_points)
+{
+    g_tracker->mCurrentFrame = g_frames[fr];
+    g_tracker->UpdateLocalMap();
+    int n = 0;
+    for (KeyFrame* k : g_tracker->mvpLocalKeyFrames) if (n < cap) local_kfs[n++] = find_kf(k);
+    *n_local_points = (int)g_tracker->mvpLocalMapPoints.size();
+    return (int)g_tracker->mvpLocalKeyFrames.size();
+}
+// the tracker's own Feature_Alignment instance, whose grid UpdateLocalMap has just filled (ref: src/Tracking.cpp:224)
+void ref_tracking_search_local_points() { g_tracker->mFeature_Alignment->SearchLocalPoints(g_tracker->mCurrentFrame); }
 
 // ---- SE3 stand-in, exposed so that the tests can state how far it is from the oracle's restatement ----
 void ref_se3_exp(const double x[6], double out[7])

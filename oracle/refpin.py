@@ -43,7 +43,10 @@ def write_config(cam, levels=5, cell=15, max_fts=300, min_fts=50, min_dist=15, m
           "Camera.k1": dist[0], "Camera.k2": dist[1], "Camera.p1": dist[2], "Camera.p2": dist[3], "Camera.k3": dist[4],
           "Camera.width": cam["width"], "Camera.height": cam["height"], "Camera.MaxPyraLevels": levels, "Camera.MinPyraLevels": 0,
           "Camera.CellSize": cell, "Camera.Max_fts": max_fts, "Camera.Min_fts": min_fts, "Camera.Min_dist": min_dist,
-          "Camera.Max_tkfts": max_tkfts}
+          "Camera.Max_tkfts": max_tkfts,
+          # read by the Tracking constructor (ref: src/Tracking.cpp:20-29); values of Config/kinect.yaml
+          "Camera.depth_scale": 1000.0, "Optimization.MaxIter": 8, "KeyFrame.min_rot": 0.08, "KeyFrame.min_trans": 0.08,
+          "KeyFrame.min_features": 25, "KeyFrame.min_dist": 0.12}
     fd, path = tempfile.mkstemp(suffix=".yaml", prefix="dsdtm_refpin_")
     with os.fdopen(fd, "w") as f:
         f.write("%YAML:1.0\n---\n")
@@ -248,6 +251,26 @@ class Ref:
 
     def search_local_points(self, cur):
         self.L.ref_fa_search_local_points(cur)
+
+    # ---- Tracking (caller side of f-1)
+    def tracking_create(self):
+        self.L.ref_tracking_create()
+
+    def keyframe_add_mappoint(self, kf, idx, mp):
+        self.L.ref_keyframe_add_mappoint(kf, idx, mp)
+
+    def close_keyframes(self, fr, cap=4096):
+        ids = np.empty(cap, np.int32); d = np.empty(cap)
+        n = self.L.ref_tracking_close_keyframes(fr, _p(ids), _p(d), cap)
+        return ids[:n].copy(), d[:n].copy()
+
+    def update_local_map(self, fr, cap=64):
+        ids = np.empty(cap, np.int32); npts = C.c_int(0)
+        n = self.L.ref_tracking_update_local_map(fr, _p(ids), cap, C.byref(npts))
+        return ids[:n].copy(), npts.value
+
+    def tracking_search_local_points(self):
+        self.L.ref_tracking_search_local_points()
 
     # ---- SE3 stand-in
     def se3_exp(self, x):

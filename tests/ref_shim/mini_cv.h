@@ -164,6 +164,18 @@ public:
         m.step.buf[1] = m.elemSize();
         return m;
     }
+    // CV_16U / CV_32F -> CV_32F with a scale, the only form the reference uses (ref: src/Tracking.cpp:56): one float multiply per pixel
+    // (a single correctly rounded product: nothing to restate)
+    void convertTo(Mat& dst, int rtype, double alpha = 1.0) const
+    {
+        if (rtype != CV_32F || channels() != 1 || (depth() != CV_16U && depth() != CV_32F)) std::abort();
+        Mat out(rows, cols, CV_32FC1);
+        const float a = (float)alpha;
+        for (int r = 0; r < rows; ++r) {
+            for (int c = 0; c < cols; ++c) out.ptr<float>(r)[c] = (depth() == CV_16U ? (float)ptr<ushort>(r)[c] : ptr<float>(r)[c]) * a;
+        }
+        dst = out;
+    }
     static Mat eye(int r, int c, int type)
     {
         Mat m(r, c, type, Scalar(0));

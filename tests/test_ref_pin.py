@@ -480,3 +480,86 @@ def test_sequence_against_reference_classes(kin):
             omap.kfs.append(o_cur)
         r_last, o_last = r_cur, o_cur
     assert min(n_matches) > 100
+
+
+# ---------------------------------------------------------------------------------------------- f-1, the caller's half
+def test_update_local_map_against_reference_tracking(kin):
+    """Tracking::GetCloseKeyFrames + Tracking::UpdateLocalMap of the reference (src/Tracking.cpp:257-345, compiled unmodified; the
+    private members are reached by lifting access control in the wrapper's translation unit only) on a 14-key-frame map: visible
+    flags, distances (bit-equal), the ten nearest in order, then SearchLocalPoints on the grid UpdateLocalMap filled -- against
+    orc_close_keyframes and the oracle-side search model with the same key-frame order."""
+    cam = dict(S.KINECT)
+    oc = H.ocam(cam)
+    scene = S.Scene(91)
+    R = kin
+    R.reset()
+    R.tracking_create()
+    rng = np.random.default_rng(4)
+    omap = OMap()
+    n_kf = 14
+    kf_poses = []
+    for k in range(n_kf):
+        xi = np.r_[rng.uniform(-0.5, 0.5), rng.uniform(-0.3, 0.3), rng.uniform(-0.1, 0.1), np.deg2rad(rng.uniform(-6, 6, 3))]
+        if k in (5, 9):
+            xi[:3] += (4.0, 3.0, 0.0)                               # far away: sees another part of the scene
+        kf_poses.append(S.pose_from_xi(xi))
+    rkf, rmp = [], {}
+    pt_begin, pt_count, kf_t, pts_all = [], [], [], []
+    for k, pose in enumerate(kf_poses):
+        img, _, pts = S.render(scene, cam, pose, want_points=True)
+        fr = R.frame(img, pose)
+        o = OracleFrame(img, pose)
+        corners, _ = H.detect_oracle(img, LEVELS, CELL, 80)
+        o.feats = H.ref_feats_from_corners(cam, corners, pts)
+        for f in o.feats:
+            R.add_feature(fr, f["px"], f["level"], True)
+        rkf.append(R.keyframe(fr))
+        o.feat_mp = []
+        rows = []
+        for i, f in enumerate(o.feats):
+            if i % 13 == 5:                                         # a feature without a map point: NULL in KeyFrame::mvMapPoints
+                o.feat_mp.append(-1); rows.append(np.zeros(3)); continue
+            P = np.zeros(3) if i % 29 == 7 else f["point_w"]        # a map point at the origin: the isZero(0) rule
+            mp = omap.new_mp(P)
+            omap.mp_obs[mp].append((k, i))
+            omap.mp_found[mp] = 1 + (i * 7 + k) % 4                 # uneven found counters: the per-cell sort matters
+            rmp[mp] = R.mappoint(P, rkf[k])
+            R.kf_feature_set_mappoint(rkf[k], i, rmp[mp]); R.keyframe_add_mappoint(rkf[k], i, rmp[mp]); R.add_observation(rmp[mp], rkf[k], i)
+            R.increase_found(rmp[mp], omap.mp_found[mp])
+            o.feat_mp.append(mp); rows.append(P)
+        if len(o.feats) == 0:
+            rows = []
+        omap.kfs.append(o)
+        pt_begin.append(sum(pt_count)); pt_count.append(len(rows)); kf_t.append(pose[4:]); pts_all += rows
+    inv_rmp = {v: k for k, v in rmp.items()}
+    pose_cur = S.pose_from_xi([0.05, -0.02, 0.01, 0.01, -0.02, 0.005])
+    imgc, _ = S.render(scene, cam, pose_cur)
+    cur = R.frame(imgc, pose_cur)
+    ocur = OracleFrame(imgc, pose_cur)
+
+    ids, dist = R.close_keyframes(cur)
+    vis, odist, local = O.close_keyframes(oc, pose_cur, pt_begin, pt_count, np.array(kf_t), np.array(pts_all), 10)
+    assert sorted(ids.tolist()) == np.nonzero(vis)[0].tolist() and 10 < len(ids) < n_kf        # Map iterates a std::set<KeyFrame*>: address order
+    assert 5 not in ids and 9 not in ids                            # the two far key frames share no visible point
+    for k, d in zip(ids, dist):
+        assert d == odist[k]
+    loc, n_local_pts = R.update_local_map(cur)
+    ds = [odist[k] for k in loc]
+    assert len(loc) == 10 and ds == sorted(ds) and set(loc.tolist()) == set(local.tolist())
+    assert len(set(ds)) == len(ds) and (loc == local).all()         # no ties in this map: the order is the oracle's
+    R.tracking_search_local_points()
+    want = _oracle_search_multi(oc, cam, ocur, omap, loc.tolist())
+    f = R.features(cur)
+    got_ids = [inv_rmp[m] for m in R.frame_mappoints(cur)]
+    assert len(want) == len(got_ids) and len(want) > 60, (len(want), len(got_ids))
+    for (mp, p, SL, _), gp, gl, gid in zip(want, f["px"], f["level"], got_ids):
+        assert gid == mp and gl == SL and (p == gp).all()
+    # the number of local map points = points that landed in the image (ref: src/Tracking.cpp:299-301)
+    n_in = 0
+    seen = set()
+    for q in loc:
+        for mp in omap.kfs[q].feat_mp:
+            if mp >= 0 and mp not in seen:
+                seen.add(mp)
+                n_in += O.reproject_point(oc, pose_cur, omap.mp_point[mp], CELL, 43)[0]
+    assert n_local_pts == n_in
