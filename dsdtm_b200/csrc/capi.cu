@@ -263,6 +263,7 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
         CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) { CK(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming)); }
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { CK(cudaEventCreate(&c->timer.ev0[i])); CK(cudaEventCreate(&c->timer.ev1[i])); }
 
     const size_t B = prm->max_batch, F = prm->max_feats, P = std::max(prm->max_patches, 1);
@@ -315,6 +316,7 @@ void dsdtm_destroy(dsdtm_ctx* c)
     if (c->stage_dev) cudaFree(c->stage_dev);
     for (int i = 0; i < StageTimer::kMaxEv; ++i) { if (c->timer.ev0[i]) cudaEventDestroy(c->timer.ev0[i]); if (c->timer.ev1[i]) cudaEventDestroy(c->timer.ev1[i]); }
     for (int i = 0; i < 4; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    for (int i = 0; i < 8; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); }
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -363,13 +365,14 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
 {
     if (!c || !key) return DSDTM_E_ARG;
     if (std::strcmp(key, "sa_warps_per_pair") == 0) {
-        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 5 && value != 10) return fail(c, DSDTM_E_ARG, "sa_warps_per_pair must be 0, 1, 2, 3, 4, 5 or 10");
+        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 5 && value != 6 && value != 8 && value != 10) return fail(c, DSDTM_E_ARG, "sa_warps_per_pair must be 0, 1, 2, 3, 4, 5, 6, 8 or 10");
         c->sa_wpp_override = value;
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
     if (std::strcmp(key, "sa_variant") == 0) {
-        if (value != 0 && value != 1) return fail(c, DSDTM_E_ARG, "sa_variant must be 0 (shared-memory recompute) or 1 (L2 workspace)");
+        if (value != 0 && value != 1 && value != 2) return fail(c, DSDTM_E_ARG, "sa_variant must be 0 (shared-memory recompute), 1 (L2 workspace) or 2 (parked grid)");
+        if (value == 2 && !c->sa_grid_ok) return fail(c, DSDTM_E_ARG, "sa_variant 2 needs 337 B of shared memory per feature: max_feats is too large for one CTA");
         c->sa_variant = value;
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
@@ -1233,18 +1236,19 @@ static int enqueue_step(dsdtm_ctx* c, int flags, cudaStream_t s, bool timed)
         }
         return 0;
     }
-    // Chunked step: the pairs are split into `chunks` groups, each running pyramid -> sparse align -> Align2D on its own
-    // stream (fork / join through events, captured into the same CUDA graph). The per-pair dependency order is unchanged;
-    // the issue-bound Align2D / pyramid kernels of one chunk fill the idle issue slots of the latency-bound sparse-alignment
-    // kernel of another (profiles/r1_step_chunks.md).
+    // Chunked step: ALL pyramids are built on the origin stream first (a pair's ref slot may be the cur slot of a pair in another
+    // chunk -- chained batches, ref[i] == cur[i-1] -- and its levels >= 1 must be complete before any alignment reads them, exactly
+    // as in the unchunked order); then the pairs are split into `chunks` groups, each running sparse align -> Align2D on its own
+    // stream (fork / join through events, captured into the same CUDA graph): the issue-bound Align2D kernel of one chunk fills the
+    // idle issue slots of the latency-bound sparse-alignment kernel of another.
     const int per = (b.n_pairs + chunks - 1) / chunks;
+    if (flags & 1) DSDTM_CUDA(c, launch_pyramid_slots(c, c->cur_slots_d, b.n_pairs, s));
     DSDTM_CUDA(c, cudaEventRecord(c->ev_fork, s));
     for (int k = 0; k < chunks; ++k) {
         const int p0 = k * per, n = std::min(per, b.n_pairs - p0);
         if (n <= 0) break;
         cudaStream_t sk = c->step_stream[k];
         DSDTM_CUDA(c, cudaStreamWaitEvent(sk, c->ev_fork, 0));
-        if (flags & 1) DSDTM_CUDA(c, launch_pyramid_slots(c, c->cur_slots_d + p0, n, sk));
         DSDTM_CUDA(c, launch_sparse_align(c, n, b.feat_stride, b.max_level, b.min_level, b.max_iters, false, sk, p0, b.n_pairs));
         if (b.patches_per_pair > 0) DSDTM_CUDA(c, launch_align2d(c, n * b.patches_per_pair, b.align_iters, sk, p0 * b.patches_per_pair));
         DSDTM_CUDA(c, cudaEventRecord(c->ev_join[k], sk));
@@ -1286,7 +1290,7 @@ int dsdtm_batch_run(dsdtm_ctx* c, int flags)
         DSDTM_CUDA(c, cudaGraphLaunch(b.graph[gi], c->stream));
         {
             const int chunks = (c->step_chunks <= 1 || b.n_pairs < 4 * c->sm_count) ? 1 : std::min(c->step_chunks, kMaxStepStreams);
-            c->launches += (long long)chunks * (((flags & 1) ? c->geo.levels - 1 : 0) + 1 + (b.patches_per_pair > 0 ? 1 : 0));
+            c->launches += ((flags & 1) ? c->geo.levels - 1 : 0) + (long long)chunks * (1 + (b.patches_per_pair > 0 ? 1 : 0));
         }
     }
     DSDTM_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
@@ -1345,61 +1349,68 @@ int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, con
     const LevelGeom& g = c->geo;
     const size_t img_bytes = (size_t)g.w[0] * g.h[0];
     // chunked pipeline: H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream) and the D2H of chunk k-1.
-    const int n_chunks = std::max(1, std::min(8, n_pairs / 64));
+    // Precondition for the overlap: no pair reads, as its reference, a slot that this call uploads as ANOTHER pair's current frame
+    // (chained batches, ref[i] == cur[i-1]); otherwise the upload / pyramid of one chunk would race the alignment of another.
+    // Such batches run as ONE chunk: upload all, build all pyramids, then align -- the order of dsdtm_batch_run.
+    bool chained = false;
+    {
+        std::vector<unsigned char> is_cur((size_t)c->prm.max_frames, 0);
+        for (int i = 0; i < n_pairs; ++i) is_cur[(size_t)cur_slots[i]] = 1;
+        for (int i = 0; i < n_pairs && !chained; ++i) chained = is_cur[(size_t)ref_slots[i]] != 0;
+    }
+    const int n_chunks = chained ? 1 : std::max(1, std::min(8, n_pairs / 64));
     const int per = (n_pairs + n_chunks - 1) / n_chunks;
     cudaStream_t cs = c->copy_stream[0], ds = c->copy_stream[1], ks = c->stream;
-    std::vector<cudaEvent_t> up(n_chunks), done(n_chunks);
-    for (int k = 0; k < n_chunks; ++k) { cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming); }
     int rc = 0;
+    cudaError_t ce = cudaSuccess;
+#define E2E_CK(call, what) do { if (!rc && (ce = (call)) != cudaSuccess) rc = fail(c, DSDTM_E_CUDA, what, ce); } while (0)
     DSDTM_CUDA(c, cudaEventRecord(c->ev_a, ks));
     DSDTM_CUDA(c, cudaStreamWaitEvent(cs, c->ev_a, 0));
     for (int k = 0; k < n_chunks && !rc; ++k) {
         const int p0 = k * per, n = std::min(per, n_pairs - p0);
         if (n <= 0) break;
         // cur images: scatter into their slots. Slots in arithmetic progression (the usual ref/cur interleaving gives
-        // stride 2) collapse into ONE strided 2-D copy; per-image copies cost ~2x in DMA setup (profiles/r1_e2e.md).
+        // stride 2) collapse into ONE strided 2-D copy; per-image copies cost ~2x in DMA setup.
         int sstride = (n > 1) ? cur_slots[p0 + 1] - cur_slots[p0] : 1;
         bool regular = sstride > 0;
         for (int i = 1; i < n && regular; ++i) if (cur_slots[p0 + i] != cur_slots[p0] + i * sstride) regular = false;
         if (regular) {
-            if (cudaMemcpy2DAsync(c->frames_d + (size_t)cur_slots[p0] * g.frame_stride, (size_t)sstride * g.frame_stride,
-                                  cur_imgs + (size_t)p0 * img_bytes, img_bytes, img_bytes, n, cudaMemcpyHostToDevice, cs) != cudaSuccess)
-                rc = fail(c, DSDTM_E_CUDA, "H2D images", cudaGetLastError());
+            E2E_CK(cudaMemcpy2DAsync(c->frames_d + (size_t)cur_slots[p0] * g.frame_stride, (size_t)sstride * g.frame_stride,
+                                     cur_imgs + (size_t)p0 * img_bytes, img_bytes, img_bytes, n, cudaMemcpyHostToDevice, cs), "H2D images");
         } else {
             for (int i = 0; i < n && !rc; ++i)
-                if (cudaMemcpyAsync(c->frames_d + (size_t)cur_slots[p0 + i] * g.frame_stride, cur_imgs + (size_t)(p0 + i) * img_bytes, img_bytes,
-                                    cudaMemcpyHostToDevice, cs) != cudaSuccess) rc = fail(c, DSDTM_E_CUDA, "H2D image", cudaGetLastError());
+                E2E_CK(cudaMemcpyAsync(c->frames_d + (size_t)cur_slots[p0 + i] * g.frame_stride, cur_imgs + (size_t)(p0 + i) * img_bytes, img_bytes,
+                                       cudaMemcpyHostToDevice, cs), "H2D image");
         }
         if (!rc) rc = stage_pairs(c, n, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, cs, p0);
         if (!rc) rc = stage_patches(c, n, cur_slots, patches10, patch_px, patch_level, ppp, cs, p0);
+        E2E_CK(cudaEventRecord(c->ev_up[k], cs), "e2e event");
+        E2E_CK(cudaStreamWaitEvent(ks, c->ev_up[k], 0), "e2e event");
         if (rc) break;
-        cudaEventRecord(up[k], cs);
-        cudaStreamWaitEvent(ks, up[k], 0);
-        if (ppp > 0) fill_patch_slots_kernel<<<(n * ppp + 255) / 256, 256, 0, ks>>>(c->cur_slots_d, c->patch_slot_d, ppp, n * ppp, p0 * ppp);
-        // pyramid for this chunk's cur frames
-        {
-            cudaError_t e = launch_pyramid_slots(c, c->cur_slots_d + p0, n, ks);
-            if (e == cudaSuccess) e = launch_sparse_align(c, n, feat_stride, max_level, min_level, max_iters, false, ks, p0, n_pairs);
-            if (e == cudaSuccess && ppp > 0) e = launch_align2d(c, n * ppp, align_iters, ks, p0 * ppp);
-            if (e != cudaSuccess) { rc = fail(c, DSDTM_E_CUDA, "e2e launch", e); break; }
-        }
-        cudaEventRecord(done[k], ks);
-        cudaStreamWaitEvent(ds, done[k], 0);
-        cudaMemcpyAsync(poses_out + 7 * (size_t)p0, c->poses_out_d + 7 * (size_t)p0, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ds);
-        cudaMemcpyAsync(n_tracked + p0, c->n_tracked_d + p0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ds);
         if (ppp > 0) {
-            cudaMemcpyAsync(patch_px_out + 2 * (size_t)p0 * ppp, c->patch_px_d + 2 * (size_t)p0 * ppp, (size_t)n * ppp * 2 * sizeof(double), cudaMemcpyDeviceToHost, ds);
-            cudaMemcpyAsync(patch_conv + (size_t)p0 * ppp, c->patch_conv_d + (size_t)p0 * ppp, (size_t)n * ppp, cudaMemcpyDeviceToHost, ds);
+            fill_patch_slots_kernel<<<(n * ppp + 255) / 256, 256, 0, ks>>>(c->cur_slots_d, c->patch_slot_d, ppp, n * ppp, p0 * ppp);
+            E2E_CK(cudaGetLastError(), "fill_patch_slots_kernel");
+        }
+        E2E_CK(launch_pyramid_slots(c, c->cur_slots_d + p0, n, ks), "e2e pyramid launch");
+        E2E_CK(launch_sparse_align(c, n, feat_stride, max_level, min_level, max_iters, false, ks, p0, n_pairs), "e2e sparse-align launch");
+        if (ppp > 0) E2E_CK(launch_align2d(c, n * ppp, align_iters, ks, p0 * ppp), "e2e align2d launch");
+        E2E_CK(cudaEventRecord(c->ev_done[k], ks), "e2e event");
+        E2E_CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0), "e2e event");
+        E2E_CK(cudaMemcpyAsync(poses_out + 7 * (size_t)p0, c->poses_out_d + 7 * (size_t)p0, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ds), "D2H poses");
+        E2E_CK(cudaMemcpyAsync(n_tracked + p0, c->n_tracked_d + p0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ds), "D2H tracked counts");
+        if (ppp > 0) {
+            E2E_CK(cudaMemcpyAsync(patch_px_out + 2 * (size_t)p0 * ppp, c->patch_px_d + 2 * (size_t)p0 * ppp, (size_t)n * ppp * 2 * sizeof(double), cudaMemcpyDeviceToHost, ds), "D2H patch positions");
+            E2E_CK(cudaMemcpyAsync(patch_conv + (size_t)p0 * ppp, c->patch_conv_d + (size_t)p0 * ppp, (size_t)n * ppp, cudaMemcpyDeviceToHost, ds), "D2H patch flags");
         }
     }
+#undef E2E_CK
     cudaEventRecord(c->ev_chunk[0], ds);
     cudaStreamWaitEvent(ks, c->ev_chunk[0], 0);
     cudaEventRecord(c->ev_b, ks);
     cudaError_t e = cudaStreamSynchronize(ks);
-    cudaStreamSynchronize(cs);
-    cudaStreamSynchronize(ds);
-    for (int k = 0; k < n_chunks; ++k) { cudaEventDestroy(up[k]); cudaEventDestroy(done[k]); }
+    const cudaError_t e2 = cudaStreamSynchronize(cs), e3 = cudaStreamSynchronize(ds);
     if (rc) return rc;
+    if (e == cudaSuccess) e = (e2 != cudaSuccess) ? e2 : e3;
     if (e != cudaSuccess) return fail(c, DSDTM_E_CUDA, "e2e sync", e);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) == cudaSuccess) c->last_run_ms = ms;

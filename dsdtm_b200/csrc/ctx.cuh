@@ -49,6 +49,7 @@ struct dsdtm_ctx {
     cudaStream_t copy_stream[2] = { nullptr, nullptr };
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_chunk[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev_up[8] = {}, ev_done[8] = {};   // dsdtm_pair_batch_e2e: upload / kernels-done of chunk k (created once)
     cudaStream_t step_stream[dsdtm::kMaxStepStreams] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[dsdtm::kMaxStepStreams] = {};
     int step_chunks = 1;                         // dsdtm_batch_run: pairs split over this many concurrent streams
@@ -58,7 +59,8 @@ struct dsdtm_ctx {
     dsdtm::StageTimer timer;
     float last_run_ms = 0.f;
     int pyr_kernel = 0;                          // 0 = auto (strip kernel where eligible), 1 = always the shared-memory tile kernel
-    int sa_variant = 0;                          // 0 = shared-memory recompute kernel, 1 = L2 workspace kernel
+    int sa_variant = 0;                          // 0 = shared-memory recompute kernel, 1 = L2 workspace kernel, 2 = parked-grid kernel
+    bool sa_grid_ok = false;                     // the parked-grid layout fits the shared memory of one CTA for this max_feats
     double* sa_ws_d = nullptr;                   // max_batch * 48 * nf doubles (variant 1)
     int sa_wpp_override = 0;                     // 0 = pick warps-per-pair from the batch size
 

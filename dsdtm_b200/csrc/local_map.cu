@@ -47,8 +47,11 @@ __global__ void __launch_bounds__(64) kf_pose_kernel(const LmArgs a)
 }
 
 // Camera::IsInImage (ref: src/Camera.cpp:187-193): cvRound(float) is round-half-even; integer division of the image size.
+// cvRound = cvtss2si: NaN (a map point at the camera centre projects to 0/0) gives INT_MIN and fails the test, whereas
+// __float2int_rn(NaN) is 0 -- hence the explicit guard (pinned against the compiled reference: test_is_in_image_and_nan).
 __device__ __forceinline__ bool in_image(float x, float y, int boundary, int level, int width, int height)
 {
+    if (!(x == x) || !(y == y)) return false;
     const int rx = __float2int_rn(x), ry = __float2int_rn(y);
     return rx >= boundary && rx < width / (1 << level) - boundary && ry >= boundary && ry < height / (1 << level) - boundary;
 }

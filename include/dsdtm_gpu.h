@@ -98,10 +98,13 @@ void*       dsdtm_host_alloc(size_t bytes);
 void        dsdtm_host_free(void* p);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 long long   dsdtm_launch_count(const dsdtm_ctx* ctx);
-/* tuning knobs (never change results): "sa_warps_per_pair" = 0 (auto) | 1 | 2 | 4 | 10;
- * "pyramid_kernel" = 0 (auto: register/DP4A strip kernel where the level shape allows) | 1 (shared-memory tile kernel);
+/* tuning knobs (never change results): "sa_warps_per_pair" = 0 (auto: 10 for a lone pair, 4, or 3 from four pairs per SM
+ * upwards) | 1 | 2 | 3 | 4 | 5 | 10 warps of one CTA per frame pair;
+ * "pyramid_kernel" = 0 (auto: TMA bulk-staged kernel where the level shape allows, whole-level kernel for the ragged tail, tile
+ * kernel otherwise) | 1 (shared-memory tile kernel everywhere) | 2 (register / DP4A strip kernel, the round-1 default);
  * "sa_variant" = 0 (shared-memory recompute kernel) | 1 (L2 workspace kernel); "step_chunks" = 1..8 concurrent streams
- * over which dsdtm_batch_run splits the pairs of a step (per-pair stage order unchanged); "depth_slots" = size of the depth
+ * over which dsdtm_batch_run splits the ALIGNMENT stages of a step (all pyramids of the step are built first on the origin
+ * stream, so a ref slot may be another pair's cur slot, as in the unchunked order); "depth_slots" = size of the depth
  * pool (before its first use); "pose_opt_solo_max" = frames per dsdtm_pose_optimize_batch call up to which a CTA of eight warps
  * owns a frame (-1 = the SM count, 0 = always one warp per frame; the two kernels agree to rounding, not bitwise) */
 int         dsdtm_set_option(dsdtm_ctx* ctx, const char* key, int value);

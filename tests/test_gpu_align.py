@@ -534,3 +534,77 @@ def test_large_batch_uses_the_throughput_kernel_and_matches_the_oracle(built):
         assert (pg == pb).all() and (tg == tb).all()
     finally:
         ctx.close()
+
+
+def test_chained_batch_is_safe_under_chunking_and_in_the_e2e_pipeline(built):
+    """in a chained batch (ref[i] == cur[i-1]) a pair's reference slot is another pair's current slot. With
+    step_chunks > 1 all pyramids are built before the fork, and dsdtm_pair_batch_e2e runs such a batch as one chunk: results must
+    equal the unchunked step bit for bit (before the fix another chunk's stream could still be writing levels >= 1 / uploading
+    level 0 of a slot while this chunk's alignment read it)."""
+    from dsdtm_b200 import capi
+    cam = dict(S.KINECT)
+    scene = S.Scene(5)
+    poses3 = [S.IDENTITY, S.pose_from_xi([0.01, 0.004, -0.003, 0.002, -0.003, 0.001]), S.pose_from_xi([0.018, -0.006, 0.004, -0.003, 0.004, 0.002])]
+    imgs, feats3, centers3 = [], [], []
+    for p in poses3:
+        img, _, pts = S.render(scene, cam, p, want_points=True)
+        corners, _ = H.detect_oracle(img, 5, 15, 60)
+        imgs.append(img); feats3.append(H.ref_feats_from_corners(cam, corners, pts)); centers3.append(O.se3_inv(p)[4:])
+    n, stride = 640, 64                                              # >= 4 pairs per SM: the chunked path is taken
+    c = capi.Context(cam, levels=5, cell_size=15, max_feats=stride, max_patches=1, max_frames=n + 1, max_batch=n)
+    try:
+        c.upload_batch(0, np.stack([imgs[i % 3] for i in range(n + 1)]))
+        ref_slots = np.arange(n, dtype=np.int32); cur_slots = ref_slots + 1
+        feats = np.zeros((n, stride), O.REF_FEAT_DT); nf = np.zeros(n, np.int32); centers = np.zeros((n, 3)); poses = np.zeros((n, 7))
+        for i in range(n):
+            f = feats3[i % 3]
+            nf[i] = len(f); feats[i, :nf[i]] = f; centers[i] = centers3[i % 3]
+            poses[i] = O.se3_mul(poses3[i % 3], O.se3_inv(poses3[i % 3]))          # start at the reference pose: T_c2r = identity
+        pt = np.zeros((n, 0, 100), np.uint8); st = np.zeros((n, 0, 2)); lv = np.zeros((n, 0), np.int32)
+        c.set_option("sa_warps_per_pair", 4)                          # singles and batches reduce in the same order
+        singles = [c.sparse_align(int(ref_slots[i]), int(cur_slots[i]), feats[i, :nf[i]], centers[i], poses[i], 5, 0, 8) for i in (0, 1, 2, 317, 639)]
+        c.batch_stage(ref_slots, cur_slots, feats, nf, centers, poses, 5, 0, 8, None, None, None, 10)
+        c.set_option("step_chunks", 1)
+        c.batch_run(1); base = c.batch_fetch()
+        for (p, k, _), i in zip(singles, (0, 1, 2, 317, 639)):
+            assert (p == base[0][i]).all() and k == base[1][i]
+        c.set_option("step_chunks", 4)
+        for rep in range(3):
+            c.upload_batch(0, np.stack([imgs[i % 3] for i in range(n + 1)]))          # level 0 again; run() rebuilds levels >= 1
+            c.batch_run(1); got = c.batch_fetch()
+            assert (got[0] == base[0]).all() and (got[1] == base[1]).all()
+        c.set_option("step_chunks", 1)
+        cur_imgs = np.ascontiguousarray(np.stack([imgs[(i + 1) % 3] for i in range(n)]))
+        out = dict(poses=np.empty((n, 7)), n_tracked=np.empty(n, np.int32))
+        for rep in range(2):
+            c.pair_batch_e2e(cur_imgs, ref_slots, cur_slots, feats, stride, nf, centers, poses, 5, 0, 8, None, None, None, 0, 10, out)
+            assert (out["poses"] == base[0]).all() and (out["n_tracked"] == base[1]).all()
+    finally:
+        c.close()
+
+
+def test_sparse_align_variants_agree_bitwise(ctx, scenario):
+    """The parked-grid kernel (sa_variant 2) parks the 6x6 bilinear reference grid per level instead of re-deriving it every
+    iteration: same values, same operation order => bit-identical poses, counts and iteration logs at equal warps-per-pair."""
+    sc = scenario
+    ctx.upload(0, sc["ref_img"]); ctx.upload(1, sc["cur_img"])
+    try:
+        for cfg in [(4, 0, 30), (5, 0, 8), (3, 1, 4)]:
+            for wpp in (3, 4, 5, 10):
+                ctx.set_option("sa_warps_per_pair", wpp)
+                ctx.set_option("sa_variant", 0)
+                p0, n0, l0 = ctx.sparse_align(0, 1, sc["feats"], sc["ref_center"], S.IDENTITY, *cfg)
+                ctx.set_option("sa_variant", 2)
+                p2, n2, l2 = ctx.sparse_align(0, 1, sc["feats"], sc["ref_center"], S.IDENTITY, *cfg)
+                assert (p0 == p2).all() and n0 == n2 and len(l0) == len(l2)
+                assert (l0["chi2"] == l2["chi2"]).all() and (l0["x"] == l2["x"]).all() and (l0["flags"] == l2["flags"]).all()
+            for wpp in (6, 8):                                        # widths only the parked-grid kernel has: against the oracle
+                ctx.set_option("sa_warps_per_pair", wpp)
+                p2, n2, l2 = ctx.sparse_align(0, 1, sc["feats"], sc["ref_center"], S.IDENTITY, *cfg)
+                packed, offs, ws, hs = sc["ref_pyr"]
+                po, no, lo = O.sparse_align(H.ocam(sc["cam"]), packed, sc["cur_pyr"][0], offs, ws, hs, sc["feats"], sc["ref_center"], S.IDENTITY, *cfg)
+                d = S.pose_dist(po, p2)
+                assert d[0] < 1e-5 and d[1] < 1e-5 and no == n2 and len(lo) == len(l2)
+                assert all(abs(a["chi2"] - b["chi2"]) <= 1e-4 * abs(a["chi2"]) for a, b in zip(lo, l2))
+    finally:
+        ctx.set_option("sa_variant", 0); ctx.set_option("sa_warps_per_pair", 0)
