@@ -365,14 +365,13 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
 {
     if (!c || !key) return DSDTM_E_ARG;
     if (std::strcmp(key, "sa_warps_per_pair") == 0) {
-        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 5 && value != 6 && value != 8 && value != 10) return fail(c, DSDTM_E_ARG, "sa_warps_per_pair must be 0, 1, 2, 3, 4, 5, 6, 8 or 10");
+        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 5 && value != 6 && value != 10) return fail(c, DSDTM_E_ARG, "sa_warps_per_pair must be 0, 1, 2, 3, 4, 5, 6 or 10");
         c->sa_wpp_override = value;
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
     if (std::strcmp(key, "sa_variant") == 0) {
-        if (value != 0 && value != 1 && value != 2) return fail(c, DSDTM_E_ARG, "sa_variant must be 0 (shared-memory recompute), 1 (L2 workspace) or 2 (parked grid)");
-        if (value == 2 && !c->sa_grid_ok) return fail(c, DSDTM_E_ARG, "sa_variant 2 needs 337 B of shared memory per feature: max_feats is too large for one CTA");
+        if (value != 0 && value != 1) return fail(c, DSDTM_E_ARG, "sa_variant must be 0 (shared-memory recompute) or 1 (L2 workspace)");
         c->sa_variant = value;
         for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;

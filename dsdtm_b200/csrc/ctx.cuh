@@ -59,8 +59,7 @@ struct dsdtm_ctx {
     dsdtm::StageTimer timer;
     float last_run_ms = 0.f;
     int pyr_kernel = 0;                          // 0 = auto (strip kernel where eligible), 1 = always the shared-memory tile kernel
-    int sa_variant = 0;                          // 0 = shared-memory recompute kernel, 1 = L2 workspace kernel, 2 = parked-grid kernel
-    bool sa_grid_ok = false;                     // the parked-grid layout fits the shared memory of one CTA for this max_feats
+    int sa_variant = 0;                          // 0 = shared-memory recompute kernel, 1 = L2 workspace kernel
     double* sa_ws_d = nullptr;                   // max_batch * 48 * nf doubles (variant 1)
     int sa_wpp_override = 0;                     // 0 = pick warps-per-pair from the batch size
 

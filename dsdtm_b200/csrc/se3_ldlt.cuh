@@ -243,29 +243,57 @@ DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&o
     const double SMALL_EPS = 1e-10;
     const double u0 = x[0], u1 = x[1], u2 = x[2], o0 = x[3], o1 = x[4], o2 = x[5];
     const double t2 = o0 * o0 + o1 * o1 + o2 * o2;
-    const double theta = sqrt(t2);
-    const double half = 0.5 * theta;
-    double sh, ch;
-#if defined(__CUDA_ARCH__)
-    sincos(half, &sh, &ch);
-#else
-    sh = sin(half); ch = cos(half);
+    double theta, ch, imag, a, b;
+    double ew, ex, ey, ez;
+#ifndef DSDTM_SE3_SERIES
+#define DSDTM_SE3_SERIES 1
 #endif
-    double imag, a, b;
-    if (theta < SMALL_EPS) {
-        const double t4 = t2 * t2;
-        imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
-        a = 0.0; b = 0.0;
+    const bool series = DSDTM_SE3_SERIES && t2 < 0.25;
+    if (series) {
+        // |theta| < 0.5 rad (every Gauss-Newton step of a tracker; larger updates take the generic branch below): the four scalar
+        // functions of Sophus' exp are even power series in theta,
+        //   cos(theta/2), sin(theta/2)/theta, (1 - cos theta)/theta^2, (theta - sin theta)/theta^3,
+        // so neither the square root, nor sincos, nor the division by theta is needed: four independent Horner chains of eight terms
+        // (truncation < 1e-18 relative at theta = 0.5) instead of a dependent sqrt -> sincos -> 1/theta sequence of several hundred
+        // cycles on the one lane the whole CTA waits for. (Sophus' own Taylor terms for theta < 1e-10 vanish in fp64: same imag.)
+        const double h2 = 0.25 * t2;                                     // (theta/2)^2
+        ch = fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, -1.0 / 87178291200.0, 1.0 / 479001600.0), -1.0 / 3628800.0), 1.0 / 40320.0),
+                                             -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
+        imag = 0.5 * fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0), -1.0 / 39916800.0), 1.0 / 362880.0),
+                                                 -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+        a = fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, -1.0 / 20922789888000.0, 1.0 / 87178291200.0), -1.0 / 479001600.0), 1.0 / 3628800.0),
+                                        -1.0 / 40320.0), 1.0 / 720.0), -1.0 / 24.0), 0.5);
+        b = fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, -1.0 / 355687428096000.0, 1.0 / 1307674368000.0), -1.0 / 6227020800.0), 1.0 / 39916800.0),
+                                        -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
+        // only tested against SMALL_EPS below. Sophus switches to V = R(q) for theta < 1e-10 (first-order different from the series:
+        // R u = u + w x u, V u = u + w x u / 2); reproduced, the reference's step is what counts
+        theta = (t2 < SMALL_EPS * SMALL_EPS) ? 0.0 : 1.0;
+        ew = ch; ex = imag * o0; ey = imag * o1; ez = imag * o2;
+        // Sophus' SO3(Quaternion) constructor normalises; |q|^2 is within a few ulp of 1 here, where 1/sqrt(n) = 1.5 - 0.5 n to O((n-1)^2)
+        const double rn = fma(-0.5, ex * ex + ey * ey + ez * ez + ew * ew, 1.5);
+        ex *= rn; ey *= rn; ez *= rn; ew *= rn;
     } else {
-        const double it = 1.0 / theta;
-        imag = sh * it;
-        const double ct = 2.0 * ch * ch - 1.0, st = 2.0 * sh * ch;     // cos(theta), sin(theta)
-        const double it2 = it * it;
-        a = (1 - ct) * it2;                                            // (1 - cos theta) / theta^2
-        b = (theta - st) * (it2 * it);                                 // (theta - sin theta) / theta^3
-    }
-    double ew = ch, ex = imag * o0, ey = imag * o1, ez = imag * o2;
-    {
+        theta = sqrt(t2);
+        const double half = 0.5 * theta;
+        double sh;
+#if defined(__CUDA_ARCH__)
+        sincos(half, &sh, &ch);
+#else
+        sh = sin(half); ch = cos(half);
+#endif
+        if (theta < SMALL_EPS) {
+            const double t4 = t2 * t2;
+            imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
+            a = 0.0; b = 0.0;
+        } else {
+            const double it = 1.0 / theta;
+            imag = sh * it;
+            const double ct = 2.0 * ch * ch - 1.0, st = 2.0 * sh * ch;     // cos(theta), sin(theta)
+            const double it2 = it * it;
+            a = (1 - ct) * it2;                                            // (1 - cos theta) / theta^2
+            b = (theta - st) * (it2 * it);                                 // (theta - sin theta) / theta^3
+        }
+        ew = ch; ex = imag * o0; ey = imag * o1; ez = imag * o2;
         const double rn = dsdtm_rsqrt(ex * ex + ey * ey + ez * ez + ew * ew);
         ex *= rn; ey *= rn; ez *= rn; ew *= rn;
     }
@@ -300,7 +328,11 @@ DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&o
     const double rx = aw * ex + ax * ew + ay * ez - az * ey;
     const double ry = aw * ey + ay * ew + az * ex - ax * ez;
     const double rz = aw * ez + az * ew + ax * ey - ay * ex;
-    const double rn = dsdtm_rsqrt(rx * rx + ry * ry + rz * rz + rw * rw);
+    // |q_T q_E|^2 = |q_T|^2 |q_E|^2: within rounding of 1 whenever the pose handed in is a unit quaternion (every pose this library
+    // produces); then 1/sqrt(n) = 1 - d/2 + 3 d^2/8 with d = n - 1 is exact to O(d^3) < 1e-24. A pose that is not normalised takes rsqrt.
+    const double n2 = rx * rx + ry * ry + rz * rz + rw * rw;
+    const double dn = n2 - 1.0;
+    const double rn = (fabs(dn) < 1e-8) ? fma(dn, fma(dn, 0.375, -0.5), 1.0) : dsdtm_rsqrt(n2);
     out[0] = rw * rn; out[1] = rx * rn; out[2] = ry * rn; out[3] = rz * rn;
     out[4] = T[4] + (et0 + aw * uv0 + c0);
     out[5] = T[5] + (et1 + aw * uv1 + c1);

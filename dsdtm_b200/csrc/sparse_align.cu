@@ -9,7 +9,7 @@
 //     WPP = 1 packs 6 independent pairs on one SM (throughput: other pairs fill the serial solve of this one),
 //     WPP = 10 gives one feature per lane (single-pair latency);
 //   * per level the 7x7 u8 neighbourhood of every reference feature (49 B), its 3-D point and sub-pixel offsets are
-//     staged ONCE in shared memory (113 B / feature incl. the parked second moments, instead of the 384 B of precomputed
+//     staged ONCE in shared memory (121 B / feature incl. the parked second moments and 1 / z, instead of the 384 B of precomputed
 //     fp64 patches which limited v1 to one pair per SM); the bilinear reference samples and their central differences are re-derived from the bytes
 //     with the reference's expressions each iteration (2x the flops, 1/3 the shared memory, 6x the residency);
 //   * inverse-compositional structure: the Jacobian row of pixel p of feature j is
@@ -43,7 +43,7 @@ struct SaArgs {
     double* ws;  // variant 1: per-pair workspace [48][nf] doubles (ref, 2dx, 2dy per patch pixel), L2-resident
     int nf;      // shared-memory column count (multiple of 16, >= every n_feats)
     int pair0;
-    int variant;   // 0 recompute, 1 L2 workspace, 2 parked grid
+    int variant;   // 0 recompute, 1 L2 workspace
 };
 
 constexpr int NB_WORDS = 14;   // 7 rows x 2 words (7 bytes) of the reference neighbourhood
@@ -198,20 +198,24 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 #ifndef DSDTM_SA_MINB3
 #define DSDTM_SA_MINB3 4         // resident CTAs per SM the 3-warp variant is compiled for (5 -> 128 regs, 60 B spills: 1.79 vs 1.52 ms; 6 -> 96 regs: 2.89 ms)
 #endif
+#ifndef DSDTM_SA_MINB5
+#define DSDTM_SA_MINB5 3         // resident CTAs per SM the 5-warp variant is compiled for (3 -> 128 registers, 56 B of spills; 2 -> 168, none)
+#endif
 #ifndef DSDTM_SA_MINB4
 #define DSDTM_SA_MINB4 3         // resident CTAs per SM the 4-warp variant is compiled for (register cap 65536 / (128 * MINB4))
 #endif
 
 template <int WPP>
-__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_SA_MINB3 : (WPP == 4 ? DSDTM_SA_MINB4 : (WPP == 5 ? 3 : 1)))) sparse_align_kernel(const SaArgs a)
+__global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_SA_MINB3 : (WPP == 4 ? DSDTM_SA_MINB4 : (WPP == 5 ? DSDTM_SA_MINB5 : (WPP == 6 ? 2 : 1))))) sparse_align_kernel(const SaArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int NF = a.nf;
     double* s_P = reinterpret_cast<double*>(s_raw);                                        // [3][NF] point in the ref camera
     double* s_S = reinterpret_cast<double*>(s_raw + (size_t)24 * NF);                      // [3][NF] Sxx, Sxy, Syy of the ref patch
-    uint32_t* s_nb = reinterpret_cast<uint32_t*>(s_raw + (size_t)48 * NF);                 // [14][NF] 7x7 u8 neighbourhood
-    float2* s_sub = reinterpret_cast<float2*>(s_raw + (size_t)(48 + 4 * NB_WORDS) * NF);   // [NF] sub-pixel offsets
-    uint8_t* s_valid = s_raw + (size_t)(48 + 4 * NB_WORDS + 8) * NF;                       // [NF]
+    double* s_zi = reinterpret_cast<double*>(s_raw + (size_t)48 * NF);                     // [NF] 1 / P.z (pose-independent: one division per level instead of one per iteration)
+    uint32_t* s_nb = reinterpret_cast<uint32_t*>(s_raw + (size_t)56 * NF);                 // [14][NF] 7x7 u8 neighbourhood
+    float2* s_sub = reinterpret_cast<float2*>(s_raw + (size_t)(56 + 4 * NB_WORDS) * NF);   // [NF] sub-pixel offsets
+    uint8_t* s_valid = s_raw + (size_t)(56 + 4 * NB_WORDS + 8) * NF;                       // [NF]
     __shared__ double s_red[WPP][8];
     __shared__ int s_cnt[WPP];
     __shared__ double s_redH[WPP][22];
@@ -258,6 +262,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                         s_P[f] = __dmul_rn(ft.normal[0], depth);                                      // ref: :119
                         s_P[NF + f] = __dmul_rn(ft.normal[1], depth);
                         s_P[2 * NF + f] = __dmul_rn(ft.normal[2], depth);
+                        s_zi[f] = 1.0 / __dmul_rn(ft.normal[2], depth);
                         const int fxi = __double2int_rd(px), fyi = __double2int_rd(py);
                         s_sub[f] = make_float2((float)(px - fxi), (float)(py - fyi));                 // exact: px is a float scaled by 2^-level
                         // rows fyi-3 .. fyi+3, cols fxi-3 .. fxi+3 : three aligned 32-bit loads + funnel shifts per row
@@ -293,8 +298,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
             static_assert(DSDTM_MAX_FEATS_LIMIT <= 32 * 32, "vis_mask holds one bit per feature of a lane: at most 32 features per lane at WPP = 1");
             unsigned vis_mask = 0;
 
-            // stage 1 of a feature: projection, bounds test and the ten aligned 32-bit loads of its 5x5 current-image window.
-            // It is issued one feature AHEAD of the fp64 arithmetic (software pipeline) so the gather latency is covered.
+            // stage 1 of a feature: projection, bounds test and the ten aligned 32-bit loads of its 5x5 current-image window
             auto stage1 = [&](int f, Pre& p) {
                 p.valid = false; p.vis = false;
                 if (f >= nfeat) return;
@@ -334,11 +338,12 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 }
             };
 
-            // stage 2: the fp64 arithmetic of one feature. FIRST (iteration 0 of a level) also derives the pose-independent
-            // second moments Sxx, Sxy, Syy of every VALID feature (visible or not) and parks them in shared memory for H.
-            auto stage2 = [&](auto first_tag, int f, int k, const Pre& me) {
-                constexpr bool FIRST = decltype(first_tag)::value;
-                if (!(FIRST ? me.valid : me.vis)) return;
+            // stage 2: the fp64 arithmetic of one feature. `first` (iteration 0 of a level, uniform over the CTA) also derives the
+            // pose-independent second moments Sxx, Sxy, Syy of every VALID feature (visible or not) and parks them in shared memory for
+            // H. One instantiation serves both cases (round 1 compiled the pass twice: half of the 120 KB of SASS, and the first
+            // iteration of every level ran cold code -- profiles/r2_sparse_align.md).
+            auto stage2 = [&](bool first, int f, int k, const Pre& me) {
+                if (!(first ? me.valid : me.vis)) return;
                 const bool vis = me.vis;
                 if (vis) { vis_mask |= 1u << k; ++cnt; }
                 RefRows R;
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                         // 2*dx, 2*dy: the reference's 0.5 factor (ref: :150-158) is applied once to the sums below (exact: power of two)
                         const double dx2 = __dsub_rn(R.G[g1][c + 2], R.G[g1][c]);
                         const double dy2 = __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]);
-                        if (FIRST) { Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy); }
+                        if (first) { Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy); }
                         const double cur = bil(me.tl, me.tr, me.bl, me.br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
                         const double res = __dsub_rn(cur, refv);                                          // ref: :282
 #if DSDTM_SA_STRICT
@@ -388,12 +393,12 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                         Sy = fma(dy2, res, Sy);
                     }
                 }
-                if (FIRST) { s_S[f] = 0.25 * Sxx; s_S[NF + f] = 0.25 * Sxy; s_S[2 * NF + f] = 0.25 * Syy; }   // (0.5 d2)^2, exact scaling
-                if (FIRST && !vis) return;
+                if (first) { s_S[f] = 0.25 * Sxx; s_S[NF + f] = 0.25 * Sxy; s_S[2 * NF + f] = 0.25 * Syy; }   // (0.5 d2)^2, exact scaling
+                if (first && !vis) return;
                 Sx *= 0.5; Sy *= 0.5;
                 // GetJocabianBA(P) rows (ref: :169-193); a1 = b0 = 0.   b_j = fs * (a * Sx + b * Sy)
-                const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
-                const double zi = 1.0 / P2, zi2 = zi * zi;
+                const double P0 = s_P[f], P1 = s_P[NF + f];
+                const double zi = s_zi[f], zi2 = zi * zi;
                 const double a0 = -zi, a2 = P0 * zi2, a3 = P1 * a2, a4 = -(1.0 + P0 * a2), a5 = P1 * zi;
                 const double b1 = -zi, b2 = P1 * zi2, b3 = 1.0 + P1 * b2, b4 = -P0 * b2, b5 = -P0 * zi;
                 acc0 += fs * (a0 * Sx); acc1 += fs * (b1 * Sy); acc2 += fs * (a2 * Sx + b2 * Sy);
@@ -401,32 +406,18 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 accc += c2;
             };
 
-            auto run_pass = [&](auto first_tag) {
-#if !DSDTM_SA_PIPELINE
+            {
+                const bool first = (it == 0);
                 int kq = 0;
                 for (int f = tid; f < nfeat; f += NT, ++kq) {
                     Pre me;
                     stage1(f, me);
-                    stage2(first_tag, f, kq, me);
+                    stage2(first, f, kq, me);
                 }
-                return;
-#endif
-                Pre cur;
-                cur.valid = false; cur.vis = false;
-                int k = -1;
-                for (int f = tid; f < nfeat + NT; f += NT, ++k) {
-                    Pre nxt;
-                    stage1(f, nxt);
-                    const Pre me = cur;
-                    cur = nxt;
-                    stage2(first_tag, f - NT, k, me);
-                }
-            };
-            if (it == 0) run_pass(std::true_type{}); else run_pass(std::false_type{});
+            }
 #ifdef DSDTM_SA_TIMING
             const long long tk1 = clock64();
 #endif
-
             acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2); acc3 = warp_sum(acc3);
             acc4 = warp_sum(acc4); acc5 = warp_sum(acc5); accc = warp_sum(accc);
             cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -438,25 +429,34 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
             const int need_H = __syncthreads_or((it == 0) || (vis_mask != prev_vis));
             prev_vis = vis_mask;
             if (need_H) {
-                // H = fs^2 sum_visible (Sxx a a^T + Sxy (a b^T + b a^T) + Syy b b^T), lower triangle packed row-major,
-                // assembled from the parked second moments (no image arithmetic here)
+                // H = fs^2 sum_visible (Sxx a a^T + Sxy (a b^T + b a^T) + Syy b b^T), lower triangle packed row-major, assembled from
+                // the parked second moments (no image arithmetic here):  H += a u^T + b w^T  with  u = cxx a + cxy b,  w = cxy a + cyy b
                 double hacc[21];
 #pragma unroll
                 for (int i = 0; i < 21; ++i) hacc[i] = 0.0;
-                int kk = 0;
-                for (int f = tid; f < nfeat; f += NT, ++kk) {
-                    if (!((vis_mask >> kk) & 1u)) continue;
-                    const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
-                    const double zi = 1.0 / P2, zi2 = zi * zi;
+                auto add_H = [&](int f) {
+                    const double P0 = s_P[f], P1 = s_P[NF + f];
+                    const double zi = s_zi[f], zi2 = zi * zi;
                     const double av[6] = { -zi, 0.0, P0 * zi2, P1 * (P0 * zi2), -(1.0 + P0 * (P0 * zi2)), P1 * zi };
                     const double bv[6] = { 0.0, -zi, P1 * zi2, 1.0 + P1 * (P1 * zi2), -P0 * (P1 * zi2), -P0 * zi };
                     const double cxx = fs2 * s_S[f], cxy = fs2 * s_S[NF + f], cyy = fs2 * s_S[2 * NF + f];
+                    double u[6], w[6];
+                    u[0] = cxx * av[0]; w[0] = cxy * av[0];             // bv[0] == 0
+                    u[1] = cxy * bv[1]; w[1] = cyy * bv[1];             // av[1] == 0
+#pragma unroll
+                    for (int c = 2; c < 6; ++c) { u[c] = fma(cxy, bv[c], cxx * av[c]); w[c] = fma(cyy, bv[c], cxy * av[c]); }
 #pragma unroll
                     for (int r = 0; r < 6; ++r)
 #pragma unroll
-                        for (int c = 0; c <= r; ++c)
-                            hacc[r * (r + 1) / 2 + c] += cxx * (av[r] * av[c]) + cxy * (av[r] * bv[c] + bv[r] * av[c]) + cyy * (bv[r] * bv[c]);
-                }
+                        for (int c = 0; c <= r; ++c) {
+                            if (r == 0) hacc[0] = fma(av[0], u[0], hacc[0]);
+                            else if (r == 1) hacc[r * (r + 1) / 2 + c] = fma(bv[1], w[c], hacc[r * (r + 1) / 2 + c]);
+                            else hacc[r * (r + 1) / 2 + c] = fma(bv[r], w[c], fma(av[r], u[c], hacc[r * (r + 1) / 2 + c]));
+                        }
+                };
+                int kk = 0;
+                for (int f = tid; f < nfeat; f += NT, ++kk)
+                    if ((vis_mask >> kk) & 1u) add_H(f);
 #pragma unroll
                 for (int i = 0; i < 21; ++i) {
                     const double h = warp_sum(hacc[i]);
@@ -858,363 +858,10 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 8 : (WPP == 3 ? 4 : (WP
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Variant 2 ("parked grid", round 2): the pose-independent 6x6 grid of bilinear reference samples G (ref: :141-158, the 36
-// values every ref / dx / dy of the 4x4 patch is a difference of) is computed ONCE per level -- with exactly the expressions
-// and operation order of variant 0 -- and parked in shared memory as fp64, [36][NF] so that consecutive lanes read consecutive
-// doubles. An iteration then only does the current-image side: 16 bilinear samples + 6 fp64 operations per patch pixel instead
-// of re-deriving the grid from bytes (36 bilinear samples + 49 conversions per feature and iteration, ~45 % of the fp64
-// instructions of variant 0), and the second moments Sxx / Sxy / Syy are taken at staging time, which removes the separate
-// "first iteration" instantiation of the pass (half the code: the kernel fits the instruction cache much better).
-// Cost: 337 instead of 113 B of shared memory per feature => two resident pairs per SM at 300 features (variant 0: four),
-// which is why the CTA is wider here (WPP = 5 ... 10). Results are BIT-IDENTICAL to variant 0 at the same WPP: same values,
-// same order of every floating-point operation (tests/test_gpu_align.py::test_sparse_align_variants_agree_bitwise).
-#ifndef DSDTM_SAG_WPP
-#define DSDTM_SAG_WPP 5      // warps per pair of the parked-grid kernel when the batch fills the chip
-#endif
-#ifndef DSDTM_SAG_PIPELINE
-#define DSDTM_SAG_PIPELINE 0
-#endif
-template <int WPP>
-__global__ void __launch_bounds__(32 * WPP, (WPP <= 8) ? 2 : 1) sparse_align_g_kernel(const SaArgs a)
-{
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const int NF = a.nf;
-    double* s_P = reinterpret_cast<double*>(s_raw);                                        // [3][NF] point in the ref camera
-    double* s_S = s_P + (size_t)3 * NF;                                                    // [3][NF] Sxx, Sxy, Syy of the ref patch
-    double* s_G = s_S + (size_t)3 * NF;                                                    // [36][NF] bilinear grid G[y][x], y, x in 0..5
-    uint8_t* s_valid = reinterpret_cast<uint8_t*>(s_G + (size_t)36 * NF);                  // [NF]
-    __shared__ double s_red[WPP][8];
-    __shared__ int s_cnt[WPP];
-    __shared__ double s_redH[WPP][22];
-    __shared__ double s_H[21];
-    __shared__ double s_F[22];
-    __shared__ double s_T[7], s_Told[7];
-    __shared__ double s_chi2prev;
-    __shared__ int s_stop, s_npts, s_nlog;
-
-    constexpr int NT = 32 * WPP;
-    const int pair = blockIdx.x + a.pair0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nfeat = min(a.n_feats[pair], NF);
-    const uint8_t* __restrict__ ref_frame = a.frames + (size_t)a.ref_slots[pair] * a.frame_stride;
-    const uint8_t* __restrict__ cur_frame = a.frames + (size_t)a.cur_slots[pair] * a.frame_stride;
-    const double cen0 = a.centers[3 * pair], cen1 = a.centers[3 * pair + 1], cen2 = a.centers[3 * pair + 2];
-    const double fx = (double)a.fx, fy = (double)a.fy, cx = (double)a.cx, cy = (double)a.cy;
-
-    if (tid < 7) { s_T[tid] = a.poses_in[7 * pair + tid]; s_Told[tid] = s_T[tid]; }
-    if (tid == 0) { s_npts = 0; s_nlog = 0; s_stop = 0; s_chi2prev = 0.0; }
-    __syncthreads();
-
-    for (int level = a.max_level - 1; level >= a.min_level; --level) {
-        const int cols = a.geo.w[level], rows = a.geo.h[level];
-        const float tScale = 1.0f / (float)(1 << level);
-        const double scale = (double)tScale;
-        const double fs = (double)a.f * scale;     // == (v * f) * scale bit-exactly, scale being a power of two
-        const double fs2 = fs * fs;
-
-        // ------------------------------------------------ GetJocabianMat (ref: :62-166), pose-independent: once per level
-        {
-            const uint8_t* __restrict__ img = ref_frame + a.geo.off[level];
-            for (int f = tid; f < nfeat; f += NT) {
-                const dsdtm_ref_feat ft = a.feats[(size_t)pair * a.feat_stride + f];
-                bool valid = false;
-                if (ft.initial) {                                                                      // ref: :86
-                    const double px = (double)ft.px[0] * scale, py = (double)ft.px[1] * scale;       // ref: :89-91
-                    const bool zero = (ft.point_w[0] == 0.0 && ft.point_w[1] == 0.0 && ft.point_w[2] == 0.0);
-                    const int boarder = 3;                                                             // ref: :67
-                    if (!(zero || px - boarder < 0 || py - boarder < 0 || px + boarder >= cols || py + boarder >= rows)) {   // ref: :95-96
-                        valid = true;
-                        const double d0 = __dsub_rn(ft.point_w[0], cen0), d1 = __dsub_rn(ft.point_w[1], cen1), d2 = __dsub_rn(ft.point_w[2], cen2);
-                        const double depth = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));   // ref: :117-118
-                        s_P[f] = __dmul_rn(ft.normal[0], depth);                                      // ref: :119
-                        s_P[NF + f] = __dmul_rn(ft.normal[1], depth);
-                        s_P[2 * NF + f] = __dmul_rn(ft.normal[2], depth);
-                        const int fxi = __double2int_rd(px), fyi = __double2int_rd(py);
-                        const double sx = (double)(float)(px - fxi), sy = (double)(float)(py - fyi);   // exact (variant 0 parks them as float)
-                        const double w00 = __dmul_rn(1.0 - sx, 1.0 - sy), w01 = __dmul_rn(sx, 1.0 - sy);
-                        const double w10 = __dmul_rn(1.0 - sx, sy), w11 = __dmul_rn(sx, sy);          // ref: :129-132
-                        // rows fyi-3 .. fyi+3, cols fxi-3 .. fxi+3 : three aligned 32-bit loads + funnel shifts per row; the grid row
-                        // y needs neighbourhood rows y and y+1, so two converted rows are alive at a time
-                        const unsigned a0 = (unsigned)(fyi - 3) * (unsigned)cols + (unsigned)(fxi - 3);
-                        double Na[7], Nb[7];
-                        auto load_row = [&](int r, double (&N)[7]) {
-                            const unsigned ad = a0 + (unsigned)r * (unsigned)cols;
-                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (ad & ~3u));
-                            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-                            const int sh = 8 * (ad & 3u);
-                            const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) N[c] = u8_to_f64(lo, c);
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) N[4 + c] = u8_to_f64(hi, c);
-                        };
-                        load_row(0, Na);
-#pragma unroll
-                        for (int y = 0; y < 6; ++y) {
-                            if (y & 1) {
-                                load_row(y + 1, Na);
-#pragma unroll
-                                for (int x = 0; x < 6; ++x) s_G[(size_t)(6 * y + x) * NF + f] = bil(w00, w01, w10, w11, Nb[x], Nb[x + 1], Na[x], Na[x + 1]);
-                            } else {
-                                load_row(y + 1, Nb);
-#pragma unroll
-                                for (int x = 0; x < 6; ++x) s_G[(size_t)(6 * y + x) * NF + f] = bil(w00, w01, w10, w11, Na[x], Na[x + 1], Nb[x], Nb[x + 1]);
-                            }
-                        }
-                        // second moments of the 16 patch gradients, in the pixel order of variant 0's first pass
-                        double Sxx = 0, Sxy = 0, Syy = 0;
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const double dx2 = __dsub_rn(s_G[(size_t)(6 * (r + 1) + c + 2) * NF + f], s_G[(size_t)(6 * (r + 1) + c) * NF + f]);
-                                const double dy2 = __dsub_rn(s_G[(size_t)(6 * (r + 2) + c + 1) * NF + f], s_G[(size_t)(6 * r + c + 1) * NF + f]);
-                                Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy);
-                            }
-                        s_S[f] = 0.25 * Sxx; s_S[NF + f] = 0.25 * Sxy; s_S[2 * NF + f] = 0.25 * Syy;   // (0.5 d2)^2, exact scaling
-                    }
-                }
-                s_valid[f] = valid ? 1 : 0;
-            }
-        }
-        __syncthreads();
-
-        unsigned prev_vis = 0;
-        const uint8_t* __restrict__ cimg = cur_frame + a.geo.off[level];
-
-        // ------------------------------------------------ GaussNewtonSolver (ref: :301-344)
-        for (int it = 0; it < a.max_iters; ++it) {
-            const double qw = s_T[0], qx = s_T[1], qy = s_T[2], qz = s_T[3];
-            const double t0 = s_T[4], t1 = s_T[5], t2 = s_T[6];
-            double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0, accc = 0;
-            int cnt = 0;
-            unsigned vis_mask = 0;
-
-            auto stage1 = [&](int f, Pre& p) {
-                p.valid = false; p.vis = false;
-                if (f >= nfeat) return;
-                if (!s_valid[f]) return;
-                p.valid = true;
-                const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
-                double Q0, Q1, Q2;
-                qrot(qw, qx, qy, qz, P0, P1, P2, Q0, Q1, Q2);                                  // ref: :254
-                Q0 = __dadd_rn(Q0, t0); Q1 = __dadd_rn(Q1, t1); Q2 = __dadd_rn(Q2, t2);
-#if DSDTM_SA_STRICT
-                const double u = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fx, Q0), Q2), cx), scale);
-                const double v = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fy, Q1), Q2), cy), scale);
-#else
-                const double iz = 1.0 / Q2;
-                const double u = __dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(fx, Q0), iz), cx), scale);
-                const double v = __dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(fy, Q1), iz), cy), scale);
-#endif
-                const double uf = floor(u), vf = floor(v);
-                if (!(uf >= 3.0 && vf >= 3.0 && uf < (double)(cols - 3) && vf < (double)(rows - 3))) return;   // ref: :262
-                p.vis = true;
-                const int ui = (int)uf, vi = (int)vf;
-                const double su = u - uf, sv = v - vf;
-                p.tl = __dmul_rn(1.0 - su, 1.0 - sv); p.tr = __dmul_rn(su, 1.0 - sv);
-                p.bl = __dmul_rn(1.0 - su, sv); p.br = __dmul_rn(su, sv);                     // ref: :267-270
-                const unsigned c0w = (unsigned)(vi - 2) * (unsigned)cols + (unsigned)(ui - 2);
-#pragma unroll
-                for (int r = 0; r < 5; ++r) {
-                    const unsigned ad = c0w + (unsigned)r * (unsigned)cols;
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(cimg + (ad & ~3u));
-                    const uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
-                    const int sh = 8 * (ad & 3u);
-                    p.cw0[r] = __funnelshift_r(lo, hi, sh);
-                    p.cw1[r] = hi >> sh;
-                }
-            };
-            auto stage2 = [&](int f, int k, const Pre& me) {
-                if (!me.vis) return;
-                vis_mask |= 1u << k; ++cnt;
-                const double* __restrict__ gf = s_G + f;
-                double G[3][6];
-#pragma unroll
-                for (int x = 0; x < 6; ++x) { G[0][x] = gf[(size_t)x * NF]; G[1][x] = gf[(size_t)(6 + x) * NF]; }
-                double Cw[2][5];
-                auto cvt_cur = [&](int slot, int r) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) Cw[slot][c] = u8_to_f64(me.cw0[r], c);
-                    Cw[slot][4] = u8_to_f64(me.cw1[r], 0);
-                };
-                cvt_cur(0, 0);
-                double Sx = 0, Sy = 0, c2 = 0;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int g0 = r % 3, g1 = (r + 1) % 3, g2 = (r + 2) % 3;   // G rows r, r+1, r+2
-#pragma unroll
-                    for (int x = 0; x < 6; ++x) G[g2][x] = gf[(size_t)(6 * (r + 2) + x) * NF];
-                    cvt_cur((r + 1) & 1, r + 1);
-                    const int ca = r & 1, cb = ca ^ 1;                          // Cw rows r, r+1
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const double refv = G[g1][c + 1];
-                        const double dx2 = __dsub_rn(G[g1][c + 2], G[g1][c]);
-                        const double dy2 = __dsub_rn(G[g2][c + 1], G[g0][c + 1]);
-                        const double cur = bil(me.tl, me.tr, me.bl, me.br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
-                        const double res = __dsub_rn(cur, refv);                                          // ref: :282
-#if DSDTM_SA_STRICT
-                        c2 = __dadd_rn(c2, __dmul_rn(res, res));                                          // ref: :284
-#else
-                        c2 = fma(res, res, c2);
-#endif
-                        Sx = fma(dx2, res, Sx);
-                        Sy = fma(dy2, res, Sy);
-                    }
-                }
-                Sx *= 0.5; Sy *= 0.5;
-                const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
-                const double zi = 1.0 / P2, zi2 = zi * zi;
-                const double a0 = -zi, a2 = P0 * zi2, a3 = P1 * a2, a4 = -(1.0 + P0 * a2), a5 = P1 * zi;
-                const double b1 = -zi, b2 = P1 * zi2, b3 = 1.0 + P1 * b2, b4 = -P0 * b2, b5 = -P0 * zi;
-                acc0 += fs * (a0 * Sx); acc1 += fs * (b1 * Sy); acc2 += fs * (a2 * Sx + b2 * Sy);
-                acc3 += fs * (a3 * Sx + b3 * Sy); acc4 += fs * (a4 * Sx + b4 * Sy); acc5 += fs * (a5 * Sx + b5 * Sy);
-                accc += c2;
-            };
-#if !DSDTM_SAG_PIPELINE
-            {
-                int kq = 0;
-                for (int f = tid; f < nfeat; f += NT, ++kq) {
-                    Pre me;
-                    stage1(f, me);
-                    stage2(f, kq, me);
-                }
-            }
-#else
-            {
-                Pre cur;
-                cur.valid = false; cur.vis = false;
-                int k = -1;
-                for (int f = tid; f < nfeat + NT; f += NT, ++k) {
-                    Pre nxt;
-                    stage1(f, nxt);
-                    const Pre me = cur;
-                    cur = nxt;
-                    stage2(f - NT, k, me);
-                }
-            }
-#endif
-            acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2); acc3 = warp_sum(acc3);
-            acc4 = warp_sum(acc4); acc5 = warp_sum(acc5); accc = warp_sum(accc);
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) {
-                s_red[warp][0] = acc0; s_red[warp][1] = acc1; s_red[warp][2] = acc2; s_red[warp][3] = acc3;
-                s_red[warp][4] = acc4; s_red[warp][5] = acc5; s_red[warp][6] = accc;
-                s_cnt[warp] = cnt;
-            }
-            const int need_H = __syncthreads_or((it == 0) || (vis_mask != prev_vis));
-            prev_vis = vis_mask;
-            if (need_H) {
-                double hacc[21];
-#pragma unroll
-                for (int i = 0; i < 21; ++i) hacc[i] = 0.0;
-                int kk = 0;
-                for (int f = tid; f < nfeat; f += NT, ++kk) {
-                    if (!((vis_mask >> kk) & 1u)) continue;
-                    const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
-                    const double zi = 1.0 / P2, zi2 = zi * zi;
-                    const double av[6] = { -zi, 0.0, P0 * zi2, P1 * (P0 * zi2), -(1.0 + P0 * (P0 * zi2)), P1 * zi };
-                    const double bv[6] = { 0.0, -zi, P1 * zi2, 1.0 + P1 * (P1 * zi2), -P0 * (P1 * zi2), -P0 * zi };
-                    const double cxx = fs2 * s_S[f], cxy = fs2 * s_S[NF + f], cyy = fs2 * s_S[2 * NF + f];
-#pragma unroll
-                    for (int r = 0; r < 6; ++r)
-#pragma unroll
-                        for (int c = 0; c <= r; ++c)
-                            hacc[r * (r + 1) / 2 + c] += cxx * (av[r] * av[c]) + cxy * (av[r] * bv[c] + bv[r] * av[c]) + cyy * (bv[r] * bv[c]);
-                }
-#pragma unroll
-                for (int i = 0; i < 21; ++i) {
-                    const double h = warp_sum(hacc[i]);
-                    if (lane == 0) s_redH[warp][i] = h;
-                }
-                __syncthreads();
-            }
-            if (warp == 0) {
-                if (need_H && lane < 21) {
-                    double h = 0;
-                    for (int w = 0; w < WPP; ++w) h += s_redH[w][lane];
-                    s_H[lane] = h;
-                }
-                double red = 0;
-                if (lane < 7) for (int w = 0; w < WPP; ++w) red += s_red[w][lane];
-                int npts = 0;
-                for (int w = 0; w < WPP; ++w) npts += s_cnt[w];
-                acc0 = __shfl_sync(0xffffffffu, red, 0); acc1 = __shfl_sync(0xffffffffu, red, 1);
-                acc2 = __shfl_sync(0xffffffffu, red, 2); acc3 = __shfl_sync(0xffffffffu, red, 3);
-                acc4 = __shfl_sync(0xffffffffu, red, 4); acc5 = __shfl_sync(0xffffffffu, red, 5);
-                accc = __shfl_sync(0xffffffffu, red, 6);
-                cnt = npts;
-                __syncwarp();
-                if (lane == 0) {
-                    const double chi2New = accc / (double)(16 * cnt);                      // ref: :298 (NaN if nothing visible)
-                    const double bvec[6] = { acc0, acc1, acc2, acc3, acc4, acc5 };
-                    double x[6];
-                    solve_and_update(s_H, s_F, need_H != 0, bvec, x);                      // ref: :318
-                    int flags = 0;
-                    bool stop = false;
-                    if (isnan(x[0])) { stop = true; flags |= 4; }                          // ref: :321-326
-                    if ((it > 0 && chi2New > s_chi2prev) || stop) {                        // ref: :328-332
-#pragma unroll
-                        for (int q = 0; q < 7; ++q) s_T[q] = s_Told[q];
-                        flags |= 2;
-                        stop = true;
-                    } else {
-                        double Tn[7];
-                        pose_update(s_T, x, Tn);                                           // ref: :335
-#pragma unroll
-                        for (int q = 0; q < 7; ++q) { s_Told[q] = s_T[q]; s_T[q] = Tn[q]; } // ref: :336-337
-                        s_chi2prev = chi2New;                                              // ref: :339
-                        flags |= 1;
-                        double mx = 0;
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) mx = fmax(mx, fabs(x[q]));
-                        if (mx <= 1e-8) { stop = true; flags |= 8; }                       // ref: :341
-                    }
-                    s_npts = cnt;
-                    s_stop = stop ? 1 : 0;
-                    if (a.log) {
-                        const int n = s_nlog;
-                        if (n < a.log_cap) {
-                            dsdtm_iter_log* e = a.log + (size_t)pair * a.log_cap + n;
-                            e->level = level; e->iter = it; e->n_pts = cnt; e->flags = flags; e->chi2 = chi2New;
-#pragma unroll
-                            for (int q = 0; q < 6; ++q) e->x[q] = x[q];
-                        }
-                        s_nlog = n + 1;
-                    }
-                }
-            }
-            __syncthreads();
-            if (s_stop) break;
-        }
-        // ref: :308 tT_c2rOld(tT_c2r) and chi2 = 0 at the start of every level
-        __syncthreads();
-        if (tid < 7) s_Told[tid] = s_T[tid];
-        if (tid == 0) { s_stop = 0; s_chi2prev = 0.0; }
-        __syncthreads();
-    }
-    if (tid < 7) a.poses_out[7 * pair + tid] = s_T[tid];
-    if (tid == 0) {
-        a.n_tracked[pair] = s_npts;
-        if (a.n_log) a.n_log[pair] = s_nlog;
-    }
-}
-
-int smem_bytes_g(int nf) { return (48 + 36 * 8 + 1) * nf; }
-
-int smem_bytes(int nf) { return (48 + 4 * NB_WORDS + 8 + 1) * nf; }
+int smem_bytes(int nf) { return (56 + 4 * NB_WORDS + 8 + 1) * nf; }
 int round_nf(int max_feats) { return (max_feats + 15) / 16 * 16; }
 
 int smem_bytes_ws(int nf) { return (48 + 1) * nf; }
-
-template <int WPP>
-cudaError_t launch_g(const SaArgs& a, int n_pairs, cudaStream_t s)
-{
-    sparse_align_g_kernel<WPP><<<n_pairs, 32 * WPP, smem_bytes_g(a.nf), s>>>(a);
-    return cudaGetLastError();
-}
 
 template <int WPP>
 cudaError_t launch(const SaArgs& a, int n_pairs, cudaStream_t s)
@@ -1238,26 +885,11 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 #ifdef DSDTM_SA_CARVEOUT
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, DSDTM_SA_CARVEOUT);
 #endif
-    {
-        // parked-grid variant: usable when its layout fits one CTA (227 KB opt-in)
-        const int bg = smem_bytes_g(nf);
-        int dev = 0, max_optin = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        c->sa_grid_ok = bg + 4096 <= max_optin;
-        if (c->sa_grid_ok) {
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_g_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bg);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_g_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bg);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_g_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bg);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_g_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bg);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_g_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bg);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_g_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, bg);
-        }
-    }
     const int bw = smem_bytes_ws(nf);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
@@ -1275,7 +907,6 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
 int sparse_align_pick_wpp(const dsdtm_ctx* c, int n_pairs)
 {
     if (c->sa_wpp_override > 0) return c->sa_wpp_override;
-    if (c->sa_variant == 2) return (n_pairs >= c->sm_count) ? DSDTM_SAG_WPP : 10;
     // >= 4 pairs per SM: three warps per pair, four CTAs per SM (same 12 warps per SM, one more pair overlapping the others' serial
     // tails): 1.524 vs 1.553 ms per 4096 pairs, 2.470 vs 2.499 ms per step (CUDA events, alternating runs)
     if (n_pairs >= 4 * c->sm_count) return 3;
@@ -1300,22 +931,13 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
     c->launches++;
     // warps-per-pair is chosen from the size of the WHOLE batch so that chunked (e2e) and single-launch runs reduce in the same order
     const int wpp = sparse_align_pick_wpp(c, n_pairs_total > 0 ? n_pairs_total : n_pairs);
-    if (a.variant == 2) {
-        switch (wpp) {
-        case 3: return launch_g<3>(a, n_pairs, s);
-        case 4: return launch_g<4>(a, n_pairs, s);
-        case 5: return launch_g<5>(a, n_pairs, s);
-        case 6: return launch_g<6>(a, n_pairs, s);
-        case 8: return launch_g<8>(a, n_pairs, s);
-        default: return launch_g<10>(a, n_pairs, s);
-        }
-    }
     switch (wpp) {
     case 1: return launch<1>(a, n_pairs, s);
     case 2: return launch<2>(a, n_pairs, s);
     case 3: return launch<3>(a, n_pairs, s);
     case 4: return launch<4>(a, n_pairs, s);
     case 5: return launch<5>(a, n_pairs, s);
+    case 6: if (!a.ws) { sparse_align_kernel<6><<<n_pairs, 192, smem_bytes(a.nf), s>>>(a); return cudaGetLastError(); } return launch<5>(a, n_pairs, s);
     default: return launch<10>(a, n_pairs, s);
     }
 }

@@ -11,7 +11,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--combos", default="0:3,0:4,0:5,2:3,2:4,2:5,2:6,2:8,2:10")
+    ap.add_argument("--combos", default="0:3,0:4,0:5,0:10")
     a = ap.parse_args()
     cam = dict(S.KINECT)
     B = a.pairs
