@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdsdtm_gpu.so")
-SOURCES = ["capi.cu", "pyramid.cu", "fast.cu", "sparse_align.cu", "align2d.cu", "local_map.cu", "ingest.cu", "clahe.cu", "pose_opt.cu"]
+SOURCES = ["capi.cu", "pyramid.cu", "fast.cu", "sparse_align.cu", "align2d.cu", "local_map.cu", "ingest.cu", "clahe.cu", "pose_opt.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
 

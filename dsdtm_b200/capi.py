@@ -77,7 +77,7 @@ SYMBOLS = [
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
     "dsdtm_local_map_align_batch", "dsdtm_depth_upload", "dsdtm_depth_convert_f32", "dsdtm_keyframe_lift",
     "dsdtm_frame_upload_pyramid_host", "dsdtm_frames_upload_clahe_pyramid", "dsdtm_track_frame",
-    "dsdtm_pose_optimize", "dsdtm_pose_optimize_batch", "dsdtm_map_table_upload", "dsdtm_close_keyframes",
+    "dsdtm_pose_optimize", "dsdtm_pose_optimize_batch", "dsdtm_map_table_upload", "dsdtm_close_keyframes", "dsdtm_probe_fp64", "dsdtm_batch_stage_map", "dsdtm_batch_fetch_map", "dsdtm_track_batch_e2e",
 ]
 
 
@@ -183,6 +183,12 @@ class Context:
 
     def set_option(self, key, value):
         self._ck(self.L.dsdtm_set_option(self.hp, key.encode(), int(value)))
+
+    def probe_fp64(self):
+        """-> (TFLOP/s of dependency-free DFMA streams, DFMA warp instructions per clock and SM at the nominal max clock)"""
+        t = C.c_double(0); w = C.c_double(0)
+        self._ck(self.L.dsdtm_probe_fp64(self.hp, C.byref(t), C.byref(w)))
+        return t.value, w.value
 
     def profile(self, on):
         self._ck(self.L.dsdtm_profile(self.hp, int(on)))
@@ -398,6 +404,26 @@ class Context:
             _p(np.ascontiguousarray(patches10, np.uint8)) if ppp else None,
             _p(np.ascontiguousarray(patch_px, np.float64)) if ppp else None,
             _p(np.ascontiguousarray(patch_level, np.int32)) if ppp else None, ppp, int(align_iters)))
+
+    def batch_stage_map(self, poses_ref_c2w, points_per_pair, max_search_level, align_iters=10):
+        """after batch_stage: the refinement chain's inputs (reference poses); batch_run(flags | 2) then runs the chain"""
+        pr = np.ascontiguousarray(poses_ref_c2w, np.float64).reshape(self._n, 7)
+        self._map_ppp = int(points_per_pair)
+        self._ck(self.L.dsdtm_batch_stage_map(self.hp, _p(pr), int(points_per_pair), int(max_search_level), int(align_iters)))
+
+    def batch_fetch_map(self):
+        out = np.zeros((self._n, self._map_ppp), REPROJ_DT)
+        self._ck(self.L.dsdtm_batch_fetch_map(self.hp, _p(out)))
+        return out
+
+    def track_batch_e2e(self, cur_imgs, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_ref, poses_in, max_level, min_level,
+                        max_iters, points_per_pair, max_search_level, align_iters, out):
+        """All arrays contiguous with the right dtype (pinned for async copies); out = dict(poses, n_tracked, reproj)."""
+        n = len(ref_slots)
+        self._ck(self.L.dsdtm_track_batch_e2e(
+            self.hp, n, _p(cur_imgs), _p(ref_slots), _p(cur_slots), _p(feats), int(feat_stride), _p(n_feats), _p(ref_centers), _p(poses_ref),
+            _p(poses_in), int(max_level), int(min_level), int(max_iters), int(points_per_pair), int(max_search_level), int(align_iters),
+            _p(out["poses"]), _p(out["n_tracked"]), _p(out["reproj"])))
 
     def batch_run(self, flags=0):
         self._ck(self.L.dsdtm_batch_run(self.hp, int(flags)))

@@ -182,13 +182,14 @@ struct WaArgs {
     const int* meta;       // n x 3 : slot, ref_level, search_level
     uint8_t* out;          // n x 100
     int n;
+    int i0;
 };
 
 __global__ void __launch_bounds__(256) warp_affine_kernel(const WaArgs a)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + warp;
-    if (i >= a.n) return;
+    const int i = a.i0 + blockIdx.x * 8 + warp;
+    if (i >= a.i0 + a.n) return;
     const int slot = a.meta[3 * i], rl = a.meta[3 * i + 1], sl = a.meta[3 * i + 2];
     if (slot < 0) return;                                           // candidate skipped by candidate_prep_kernel
     const double A00 = a.A[4 * i], A01 = a.A[4 * i + 1], A10 = a.A[4 * i + 2], A11 = a.A[4 * i + 3];
@@ -232,6 +233,8 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const WaArgs a)
 // inputs of warp_affine_kernel and align2d_kernel directly, so the three stages chain on the device.
 struct CpArgs {
     const dsdtm_candidate* cand; int n; int cur_slot; int max_search_level;
+    int i0;                      // first candidate of this launch (chunked batches)
+    const int* cur_slots; int ppp;   // batched chain: candidate i belongs to pair i / ppp, whose current frame is cur_slots[pair]
     float fx, fy, cx, cy;
     double* A; float* ref_px; int* meta; int* patch_level; int* patch_slot; double* px_in;
 };
@@ -252,12 +255,13 @@ __device__ __forceinline__ void cp_qrot(const double* q, double v0, double v1, d
 
 __global__ void __launch_bounds__(128) candidate_prep_kernel(const CpArgs a)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    const int i = a.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.i0 + a.n) return;
     const dsdtm_candidate c = a.cand[i];
+    const int cur_slot = a.cur_slots ? a.cur_slots[i / a.ppp] : a.cur_slot;
     if (c.ref_slot < 0) {                                           // rejected before FindMatchDirect's arithmetic (local_map.cu)
         a.meta[3 * i] = -1; a.meta[3 * i + 1] = 0; a.meta[3 * i + 2] = 0;
-        a.patch_level[i] = -1; a.patch_slot[i] = a.cur_slot;
+        a.patch_level[i] = -1; a.patch_slot[i] = cur_slot;
         a.px_in[2 * i] = c.px[0]; a.px_in[2 * i + 1] = c.px[1];
         return;
     }
@@ -301,17 +305,18 @@ __global__ void __launch_bounds__(128) candidate_prep_kernel(const CpArgs a)
     a.A[4 * i] = A00; a.A[4 * i + 1] = A01; a.A[4 * i + 2] = A10; a.A[4 * i + 3] = A11;
     a.ref_px[2 * i] = c.ref_px[0]; a.ref_px[2 * i + 1] = c.ref_px[1];
     a.meta[3 * i] = c.ref_slot; a.meta[3 * i + 1] = c.ref_level; a.meta[3 * i + 2] = L;
-    a.patch_level[i] = L; a.patch_slot[i] = a.cur_slot;
+    a.patch_level[i] = L; a.patch_slot[i] = cur_slot;
     const double inv = 1.0 / (double)(1 << L);                      // ref: :150 tPt / (1 << level): exact power of two
     a.px_in[2 * i] = __dmul_rn(c.px[0], inv); a.px_in[2 * i + 1] = __dmul_rn(c.px[1], inv);
 }
 
 }  // namespace
 
-cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s)
+cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s, int i0, const int* cur_slots_d, int ppp)
 {
     CpArgs a;
     a.cand = c->cand_d; a.n = n; a.cur_slot = cur_slot; a.max_search_level = max_search_level;
+    a.i0 = i0; a.cur_slots = cur_slots_d; a.ppp = ppp > 0 ? ppp : 1;
     a.fx = c->cam.fx; a.fy = c->cam.fy; a.cx = c->cam.cx; a.cy = c->cam.cy;
     a.A = c->wa_A_d; a.ref_px = c->wa_px_d; a.meta = c->wa_meta_d; a.patch_level = c->patch_level_d; a.patch_slot = c->patch_slot_d;
     a.px_in = c->patch_px_in_d;
@@ -331,9 +336,10 @@ cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStrea
     return cudaGetLastError();
 }
 
-cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s)
+cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s, int i0)
 {
     WaArgs a;
+    a.i0 = i0;
     a.frames = c->frames_d; a.frame_stride = c->geo.frame_stride; a.geo = c->geo;
     a.A = c->wa_A_d; a.ref_px = c->wa_px_d; a.meta = c->wa_meta_d; a.out = out_d; a.n = n;
     warp_affine_kernel<<<(n + 7) / 8, 256, 0, s>>>(a);

@@ -277,7 +277,7 @@ dsdtm_ctx* dsdtm_create(int device, const dsdtm_cam* cam, const dsdtm_params* pr
         dalloc(c, &c->log_d, B * kLogCap) || dalloc(c, &c->n_log_d, B) || dalloc(c, &c->patches_d, B * P * 100) ||
         dalloc(c, &c->patch_px_d, B * P * 2) || dalloc(c, &c->patch_px_in_d, B * P * 2) || dalloc(c, &c->patch_level_d, B * P) || dalloc(c, &c->patch_slot_d, B * P) ||
         dalloc(c, &c->patch_conv_d, B * P) || dalloc(c, &c->wa_A_d, B * P * 4) || dalloc(c, &c->wa_px_d, B * P * 2) ||
-        dalloc(c, &c->wa_meta_d, B * P * 3) || dalloc(c, &c->cand_d, B * P) || dalloc(c, &c->sa_ws_d, B * sparse_align_ws_doubles(prm->max_feats)))
+        dalloc(c, &c->wa_meta_d, B * P * 3) || dalloc(c, &c->cand_d, B * P) || dalloc(c, &c->poses_ref_d, B * 7) || dalloc(c, &c->pair_reproj_d, B * P) || dalloc(c, &c->sa_ws_d, B * sparse_align_ws_doubles(prm->max_feats)))
         return bail("device buffers");
     {
         const int n = build_fast_tiles(g, nullptr, nullptr);
@@ -302,11 +302,11 @@ void dsdtm_destroy(dsdtm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) cudaGraphExecDestroy(c->batch.graph[k]);
+    for (int k = 0; k < 4; ++k) if (c->batch.graph[k]) cudaGraphExecDestroy(c->batch.graph[k]);
     void* bufs[] = { c->frames_d, c->cells_d, c->occupied_d, c->scoremap_d, c->fast_tiles_d, c->ref_slots_d, c->cur_slots_d,
                      c->feats_d, c->n_feats_d, c->centers_d, c->poses_in_d, c->poses_out_d, c->n_tracked_d, c->log_d, c->n_log_d,
                      c->patches_d, c->patch_px_d, c->patch_px_in_d, c->patch_level_d, c->patch_slot_d, c->patch_conv_d, c->wa_A_d, c->wa_px_d, c->wa_meta_d, c->sa_ws_d, c->cand_d,
-                     c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d,
+                     c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d, c->poses_ref_d, c->pair_reproj_d,
                      c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d, c->clahe_src_d, c->clahe_lut_d,
                      c->po_obs_d, c->po_res_d, c->po_nobs_d, c->po_pose_in_d, c->po_pose_out_d, c->po_sum_d,
                      c->mt_kfs_d, c->mt_pts_d, c->mt_vis_d, c->mt_dist_d };
@@ -367,25 +367,25 @@ int dsdtm_set_option(dsdtm_ctx* c, const char* key, int value)
     if (std::strcmp(key, "sa_warps_per_pair") == 0) {
         if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 5 && value != 6 && value != 10) return fail(c, DSDTM_E_ARG, "sa_warps_per_pair must be 0, 1, 2, 3, 4, 5, 6 or 10");
         c->sa_wpp_override = value;
-        for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
+        for (int k = 0; k < 4; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
     if (std::strcmp(key, "sa_variant") == 0) {
         if (value != 0 && value != 1) return fail(c, DSDTM_E_ARG, "sa_variant must be 0 (shared-memory recompute) or 1 (L2 workspace)");
         c->sa_variant = value;
-        for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
+        for (int k = 0; k < 4; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
     if (std::strcmp(key, "step_chunks") == 0) {
         if (value < 1 || value > kMaxStepStreams) return fail(c, DSDTM_E_ARG, "step_chunks must be 1..8");
         c->step_chunks = value;
-        for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
+        for (int k = 0; k < 4; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
     if (std::strcmp(key, "pyramid_kernel") == 0) {
         if (value != 0 && value != 1 && value != 2) return fail(c, DSDTM_E_ARG, "pyramid_kernel must be 0 (auto: bulk-staged where eligible), 1 (tile) or 2 (register strip)");
         c->pyr_kernel = value;
-        for (int k = 0; k < 2; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
+        for (int k = 0; k < 4; ++k) if (c->batch.graph[k]) { cudaGraphExecDestroy(c->batch.graph[k]); c->batch.graph[k] = nullptr; }
         return 0;
     }
     if (std::strcmp(key, "pose_opt_solo_max") == 0) {
@@ -1211,14 +1211,42 @@ int dsdtm_batch_stage(dsdtm_ctx* c, int n_pairs, const int* ref_slots, const int
     auto& b = c->batch;
     b.staged = true; b.n_pairs = n_pairs; b.feat_stride = feat_stride; b.max_level = max_level; b.min_level = min_level;
     b.max_iters = max_iters; b.patches_per_pair = ppp; b.align_iters = align_iters;
+    b.map_staged = false;
     return 0;
+}
+
+int dsdtm_batch_stage_map(dsdtm_ctx* c, const double* poses_ref_c2w, int points_per_pair, int max_search_level, int align_iters)
+{
+    if (!c || !poses_ref_c2w) return DSDTM_E_ARG;
+    auto& b = c->batch;
+    if (!b.staged) return fail(c, DSDTM_E_STATE, "dsdtm_batch_stage_map: call dsdtm_batch_stage first");
+    if (points_per_pair < 1 || points_per_pair > c->prm.max_patches || points_per_pair > b.feat_stride)
+        return fail(c, DSDTM_E_ARG, "points_per_pair must be 1..min(max_patches, feat_stride)");
+    if (max_search_level < 0 || max_search_level >= c->geo.levels || align_iters < 0) return fail(c, DSDTM_E_ARG, "bad max_search_level / align_iters");
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->poses_ref_d, poses_ref_c2w, (size_t)b.n_pairs * 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    b.map_staged = true; b.map_ppp = points_per_pair; b.max_search_level = max_search_level; b.map_align_iters = align_iters;
+    for (int k = 0; k < 4; ++k) if (b.graph[k]) { cudaGraphExecDestroy(b.graph[k]); b.graph[k] = nullptr; }
+    return 0;
+}
+
+// the refinement chain of pairs [p0, p0 + n) on stream s: candidates from the aligned pose -> affine + search level -> warp -> Align2D -> records
+static cudaError_t enqueue_chain(dsdtm_ctx* c, int p0, int n, int feat_stride, int ppp, int max_search_level, int align_iters, cudaStream_t s)
+{
+    cudaError_t e = launch_pair_candidates(c, p0, n, feat_stride, ppp, s);
+    if (e == cudaSuccess) e = launch_candidate_prep(c, n * ppp, 0, max_search_level, s, p0 * ppp, c->cur_slots_d, ppp);
+    if (e == cudaSuccess) e = launch_warp_affine(c, n * ppp, c->patches_d, s, p0 * ppp);
+    if (e == cudaSuccess) e = launch_align2d(c, n * ppp, align_iters, s, p0 * ppp);
+    if (e == cudaSuccess) e = launch_local_map_finalize(c, n * ppp, s, c->pair_reproj_d, p0 * ppp);
+    return e;
 }
 
 // the kernels of one step, enqueued on stream s (captured into a CUDA graph by dsdtm_batch_run)
 static int enqueue_step(dsdtm_ctx* c, int flags, cudaStream_t s, bool timed)
 {
     auto& b = c->batch;
-    const int chunks = (timed || c->step_chunks <= 1 || b.n_pairs < 4 * c->sm_count) ? 1 : std::min(c->step_chunks, kMaxStepStreams);
+    const bool chain = (flags & 2) != 0;
+    const int chunks = (timed || chain || c->step_chunks <= 1 || b.n_pairs < 4 * c->sm_count) ? 1 : std::min(c->step_chunks, kMaxStepStreams);
     if (chunks == 1) {
         if (flags & 1) {
             if (timed) stage_begin(c, DSDTM_STAGE_PYRAMID);
@@ -1228,7 +1256,20 @@ static int enqueue_step(dsdtm_ctx* c, int flags, cudaStream_t s, bool timed)
         if (timed) stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
         DSDTM_CUDA(c, launch_sparse_align(c, b.n_pairs, b.feat_stride, b.max_level, b.min_level, b.max_iters, false, s));
         if (timed) stage_end(c, 1);
-        if (b.patches_per_pair > 0) {
+        if (chain) {
+            // TrackWithLocalMap right after Run: the patches come from the reference frame through the aligned pose, nothing from the host
+            if (timed) stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+            DSDTM_CUDA(c, launch_pair_candidates(c, 0, b.n_pairs, b.feat_stride, b.map_ppp, s));
+            DSDTM_CUDA(c, launch_candidate_prep(c, b.n_pairs * b.map_ppp, 0, b.max_search_level, s, 0, c->cur_slots_d, b.map_ppp));
+            if (timed) stage_end(c, 2);
+            if (timed) stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
+            DSDTM_CUDA(c, launch_warp_affine(c, b.n_pairs * b.map_ppp, c->patches_d, s));
+            if (timed) stage_end(c, 1);
+            if (timed) stage_begin(c, DSDTM_STAGE_ALIGN2D);
+            DSDTM_CUDA(c, launch_align2d(c, b.n_pairs * b.map_ppp, b.map_align_iters, s));
+            DSDTM_CUDA(c, launch_local_map_finalize(c, b.n_pairs * b.map_ppp, s, c->pair_reproj_d, 0));
+            if (timed) stage_end(c, 2);
+        } else if (b.patches_per_pair > 0) {
             if (timed) stage_begin(c, DSDTM_STAGE_ALIGN2D);
             DSDTM_CUDA(c, launch_align2d(c, b.n_pairs * b.patches_per_pair, b.align_iters, s));
             if (timed) stage_end(c, 1);
@@ -1261,7 +1302,8 @@ int dsdtm_batch_run(dsdtm_ctx* c, int flags)
     if (!c) return DSDTM_E_ARG;
     auto& b = c->batch;
     if (!b.staged) return fail(c, DSDTM_E_STATE, "dsdtm_batch_run: no staged batch");
-    const int gi = flags & 1;
+    if ((flags & 2) && !b.map_staged) return fail(c, DSDTM_E_STATE, "dsdtm_batch_run: flags bit 1 needs dsdtm_batch_stage_map");
+    const int gi = flags & 3;
     DSDTM_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
     if (c->profiling) {
         // per-stage events cannot be recorded inside a captured graph: launch directly
@@ -1289,7 +1331,8 @@ int dsdtm_batch_run(dsdtm_ctx* c, int flags)
         DSDTM_CUDA(c, cudaGraphLaunch(b.graph[gi], c->stream));
         {
             const int chunks = (c->step_chunks <= 1 || b.n_pairs < 4 * c->sm_count) ? 1 : std::min(c->step_chunks, kMaxStepStreams);
-            c->launches += ((flags & 1) ? c->geo.levels - 1 : 0) + (long long)chunks * (1 + (b.patches_per_pair > 0 ? 1 : 0));
+            if (flags & 2) c->launches += ((flags & 1) ? c->geo.levels - 1 : 0) + 1 + 5;
+            else c->launches += ((flags & 1) ? c->geo.levels - 1 : 0) + (long long)chunks * (1 + (b.patches_per_pair > 0 ? 1 : 0));
         }
     }
     DSDTM_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
@@ -1310,6 +1353,16 @@ int dsdtm_batch_fetch(dsdtm_ctx* c, double* poses_out, int* n_tracked, double* p
     DSDTM_CUDA(c, cudaStreamSynchronize(s));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) == cudaSuccess) c->last_run_ms = ms;
+    return 0;
+}
+
+int dsdtm_batch_fetch_map(dsdtm_ctx* c, dsdtm_reproj* reproj_out)
+{
+    if (!c || !reproj_out) return DSDTM_E_ARG;
+    auto& b = c->batch;
+    if (!b.staged || !b.map_staged) return fail(c, DSDTM_E_STATE, "dsdtm_batch_fetch_map: no staged map batch");
+    DSDTM_CUDA(c, cudaMemcpyAsync(reproj_out, c->pair_reproj_d, (size_t)b.n_pairs * b.map_ppp * sizeof(dsdtm_reproj), cudaMemcpyDeviceToHost, c->stream));
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -1334,11 +1387,14 @@ float dsdtm_timer_stop(dsdtm_ctx* c)
     return ms;
 }
 
-int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots, const int* cur_slots,
+// chain != nullptr: the refinement inputs come from the reference frames on the device (dsdtm_track_batch_e2e) instead of host patches
+struct E2eChain { const double* poses_ref; int ppp; int max_search_level; dsdtm_reproj* reproj_out; };
+
+static int pair_batch_e2e_impl(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots, const int* cur_slots,
                          const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats, const double* ref_centers,
                          const double* poses_in, int max_level, int min_level, int max_iters, const uint8_t* patches10,
                          const double* patch_px, const int* patch_level, int ppp, int align_iters, double* poses_out,
-                         int* n_tracked, double* patch_px_out, uint8_t* patch_conv)
+                         int* n_tracked, double* patch_px_out, uint8_t* patch_conv, const E2eChain* chain)
 {
     if (!c || !cur_imgs || !ref_slots || !cur_slots || !feats || !n_feats || !ref_centers || !poses_in || !poses_out || !n_tracked) return DSDTM_E_ARG;
     if (check_pairs(c, n_pairs, ref_slots, cur_slots, feat_stride, n_feats, max_level, min_level, max_iters)) return DSDTM_E_ARG;
@@ -1383,6 +1439,7 @@ int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, con
         }
         if (!rc) rc = stage_pairs(c, n, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, cs, p0);
         if (!rc) rc = stage_patches(c, n, cur_slots, patches10, patch_px, patch_level, ppp, cs, p0);
+        if (chain) E2E_CK(cudaMemcpyAsync(c->poses_ref_d + 7 * (size_t)p0, chain->poses_ref + 7 * (size_t)p0, (size_t)n * 7 * sizeof(double), cudaMemcpyHostToDevice, cs), "H2D reference poses");
         E2E_CK(cudaEventRecord(c->ev_up[k], cs), "e2e event");
         E2E_CK(cudaStreamWaitEvent(ks, c->ev_up[k], 0), "e2e event");
         if (rc) break;
@@ -1393,6 +1450,7 @@ int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, con
         E2E_CK(launch_pyramid_slots(c, c->cur_slots_d + p0, n, ks), "e2e pyramid launch");
         E2E_CK(launch_sparse_align(c, n, feat_stride, max_level, min_level, max_iters, false, ks, p0, n_pairs), "e2e sparse-align launch");
         if (ppp > 0) E2E_CK(launch_align2d(c, n * ppp, align_iters, ks, p0 * ppp), "e2e align2d launch");
+        if (chain) E2E_CK(enqueue_chain(c, p0, n, feat_stride, chain->ppp, chain->max_search_level, align_iters, ks), "e2e refinement chain launch");
         E2E_CK(cudaEventRecord(c->ev_done[k], ks), "e2e event");
         E2E_CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0), "e2e event");
         E2E_CK(cudaMemcpyAsync(poses_out + 7 * (size_t)p0, c->poses_out_d + 7 * (size_t)p0, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ds), "D2H poses");
@@ -1401,6 +1459,8 @@ int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, con
             E2E_CK(cudaMemcpyAsync(patch_px_out + 2 * (size_t)p0 * ppp, c->patch_px_d + 2 * (size_t)p0 * ppp, (size_t)n * ppp * 2 * sizeof(double), cudaMemcpyDeviceToHost, ds), "D2H patch positions");
             E2E_CK(cudaMemcpyAsync(patch_conv + (size_t)p0 * ppp, c->patch_conv_d + (size_t)p0 * ppp, (size_t)n * ppp, cudaMemcpyDeviceToHost, ds), "D2H patch flags");
         }
+        if (chain) E2E_CK(cudaMemcpyAsync(chain->reproj_out + (size_t)p0 * chain->ppp, c->pair_reproj_d + (size_t)p0 * chain->ppp,
+                                          (size_t)n * chain->ppp * sizeof(dsdtm_reproj), cudaMemcpyDeviceToHost, ds), "D2H refinement records");
     }
 #undef E2E_CK
     cudaEventRecord(c->ev_chunk[0], ds);
@@ -1414,6 +1474,31 @@ int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, con
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) == cudaSuccess) c->last_run_ms = ms;
     return 0;
+}
+
+int dsdtm_pair_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots, const int* cur_slots,
+                         const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats, const double* ref_centers,
+                         const double* poses_in, int max_level, int min_level, int max_iters, const uint8_t* patches10,
+                         const double* patch_px, const int* patch_level, int ppp, int align_iters, double* poses_out,
+                         int* n_tracked, double* patch_px_out, uint8_t* patch_conv)
+{
+    return pair_batch_e2e_impl(c, n_pairs, cur_imgs, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_in, max_level, min_level,
+                               max_iters, patches10, patch_px, patch_level, ppp, align_iters, poses_out, n_tracked, patch_px_out, patch_conv, nullptr);
+}
+
+int dsdtm_track_batch_e2e(dsdtm_ctx* c, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots, const int* cur_slots,
+                          const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats, const double* ref_centers,
+                          const double* poses_ref_c2w, const double* poses_c2r_in, int max_level, int min_level, int max_iters,
+                          int points_per_pair, int max_search_level, int align_iters, double* poses_c2r_out, int* n_tracked,
+                          dsdtm_reproj* reproj_out)
+{
+    if (!c || !poses_ref_c2w || !reproj_out) return DSDTM_E_ARG;
+    if (points_per_pair < 1 || points_per_pair > c->prm.max_patches || points_per_pair > feat_stride)
+        return fail(c, DSDTM_E_ARG, "points_per_pair must be 1..min(max_patches, feat_stride)");
+    if (max_search_level < 0 || max_search_level >= c->geo.levels) return fail(c, DSDTM_E_ARG, "bad max_search_level");
+    const E2eChain ch = { poses_ref_c2w, points_per_pair, max_search_level, reproj_out };
+    return pair_batch_e2e_impl(c, n_pairs, cur_imgs, ref_slots, cur_slots, feats, feat_stride, n_feats, ref_centers, poses_c2r_in, max_level, min_level,
+                               max_iters, nullptr, nullptr, nullptr, 0, align_iters, poses_c2r_out, n_tracked, nullptr, nullptr, &ch);
 }
 
 }  // extern "C"

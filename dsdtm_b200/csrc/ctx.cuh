@@ -78,6 +78,8 @@ struct dsdtm_ctx {
     int* n_feats_d = nullptr;
     double* centers_d = nullptr;                 // max_batch * 3
     double* poses_in_d = nullptr;                // max_batch * 7
+    double* poses_ref_d = nullptr;               // max_batch * 7: reference-frame poses of the batched refinement chain
+    dsdtm_reproj* pair_reproj_d = nullptr;       // max_batch * max_patches: per-candidate records of the batched chain
     double* poses_out_d = nullptr;               // max_batch * 7
     int* n_tracked_d = nullptr;
     dsdtm_iter_log* log_d = nullptr;             // max_batch * kLogCap
@@ -133,8 +135,10 @@ struct dsdtm_ctx {
         bool staged = false;
         int n_pairs = 0, feat_stride = 0, max_level = 0, min_level = 0, max_iters = 0;
         int patches_per_pair = 0, align_iters = 0;
-        cudaGraphExec_t graph[2] = { nullptr, nullptr };   // [flags & 1]
-        int graph_key[2][8];
+        bool map_staged = false;                           // dsdtm_batch_stage_map: the refinement chain's inputs are on the device
+        int map_ppp = 0, max_search_level = 0, map_align_iters = 0;
+        cudaGraphExec_t graph[4] = { nullptr, nullptr, nullptr, nullptr };   // [flags & 3]
+        int graph_key[4][8];
     } batch;
 };
 
@@ -172,15 +176,17 @@ cudaError_t launch_fast_score_map(dsdtm_ctx* c, int slot, int level, int barrier
 cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int max_level, int min_level, int max_iters,
                                 bool want_log, cudaStream_t s, int pair0 = 0, int n_pairs_total = 0);
 cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
-cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s);
-cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s);
+cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s, int i0 = 0);
+cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s, int i0 = 0, const int* cur_slots_d = nullptr, int ppp = 0);
 cudaError_t launch_clahe(dsdtm_ctx* c, int first_slot, int n, double clip_limit, int tiles_x, int tiles_y, cudaStream_t s);
 int clahe_max_tiles_x();
 int clahe_rows_per_cta();
 cudaError_t launch_depth_convert(dsdtm_ctx* c, int first_slot, int n, float depth_scale, cudaStream_t s);
 cudaError_t launch_keyframe_lift(dsdtm_ctx* c, int depth_slot, const double pose_c2w[7], const float dist[5], float depth_scale,
                                  bool have_initial, int n, cudaStream_t s);
-cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s);
+cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s, dsdtm_reproj* out_d = nullptr, int i0 = 0);
+// batched chain (one-key-frame local map per pair = its reference frame): reproject / closest observation / gates for pairs [pair0, pair0 + n_pairs)
+cudaError_t launch_pair_candidates(dsdtm_ctx* c, int pair0, int n_pairs, int feat_stride, int ppp, cudaStream_t s);
 cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s,
                              const double* pose_dev = nullptr);
 cudaError_t launch_compose_pose(dsdtm_ctx* c, const double* t_c2r_d, const double pose_ref_c2w[7], double* out10_d, cudaStream_t s);

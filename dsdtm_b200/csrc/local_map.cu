@@ -134,12 +134,92 @@ __global__ void compose_pose_kernel(const ComposeArgs a)
     a.out[7] = inv[4]; a.out[8] = inv[5]; a.out[9] = inv[6];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The refinement chain of a BATCH of independent frame pairs (bench / sweep: dsdtm_batch_run flags bit 1, dsdtm_track_batch_e2e):
+// every pair's local map is its reference frame seen as ONE key frame, whose features with map points are the candidates --
+// Tracking::TrackWithLocalMap right after a key frame (ref: src/Tracking.cpp:219-224,257-313). One thread per (pair, feature):
+//   cur.Set_Pose(T_c2r * ref.Get_Pose())                       ref: src/Sprase_ImageAlign.cpp:57, src/Frame.cpp:167-174
+//   ReprojectPoint: World2Pixel + IsInImage(px, 8) + cell      ref: src/Feature_alignment.cpp:54-69
+//   Get_ClosetObs with the single observation (cos >= 0.5)     ref: src/MapPoint.cpp:133-174
+//   IsInImage(ref px / 2^level, 5, level)                      ref: src/Feature_alignment.cpp:138
+//   T_c2r' = cur.Get_Pose() * kf.Get_Pose().inverse()          ref: src/Feature_alignment.cpp:181
+// and the dsdtm_candidate that candidate_prep_kernel consumes. Same non-contracted arithmetic as local_map_kernel / kf_pose_kernel /
+// compose_pose_kernel (the pose composition is repeated per thread: ~150 flops, no extra launch, no extra pass over the poses).
+struct PcArgs {
+    const int* ref_slots; const dsdtm_ref_feat* feats; int feat_stride; const int* n_feats;
+    const double* centers; const double* poses_ref; const double* poses_c2r;
+    int pair0, n_pairs, ppp;
+    float fx, fy, cx, cy;
+    int width, height, cell_size, grid_cols;
+    dsdtm_candidate* cand; dsdtm_reproj* out;
+};
+
+__global__ void __launch_bounds__(128) pair_candidates_kernel(const PcArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_pairs * a.ppp) return;
+    const int pair = a.pair0 + t / a.ppp, j = t % a.ppp;
+    const size_t i = (size_t)pair * a.ppp + j;
+    dsdtm_candidate cd;
+    cd.ref_slot = -1; cd.ref_level = 0; cd.px[0] = 0.0; cd.px[1] = 0.0;
+    dsdtm_reproj r;
+    r.px_proj[0] = r.px_proj[1] = r.px[0] = r.px[1] = 0.0; r.cell = -1; r.obs = -1; r.flags = 0; r.level = -1;
+    const dsdtm_ref_feat ft = (j < a.n_feats[pair]) ? a.feats[(size_t)pair * a.feat_stride + j] : dsdtm_ref_feat{};
+    if (j < a.n_feats[pair] && ft.initial) {                         // features without a map point are not in KeyFrame::GetMapPoints()
+        double Tr[7], Tc2r[7], pc[7], inv[7], Tck[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { Tr[k] = a.poses_ref[7 * pair + k]; Tc2r[k] = a.poses_c2r[7 * pair + k]; }
+        se3_mul_exact(Tc2r, Tr, pc);                                 // cur pose (c2w)
+        se3_inv_exact(pc, inv);                                      // cur centre = inverse().translation()
+        const double cc0 = inv[4], cc1 = inv[5], cc2 = inv[6];
+        se3_inv_exact(Tr, inv);
+        se3_mul_exact(pc, inv, Tck);                                 // T_cur * T_kf^-1
+        const double P0 = ft.point_w[0], P1 = ft.point_w[1], P2 = ft.point_w[2];
+        double q0, q1, q2;
+        qrot_exact(pc, P0, P1, P2, q0, q1, q2);
+        q0 = __dadd_rn(q0, pc[4]); q1 = __dadd_rn(q1, pc[5]); q2 = __dadd_rn(q2, pc[6]);
+        const double u = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fx, q0), q2), (double)a.cx);
+        const double v = __dadd_rn(__ddiv_rn(__dmul_rn((double)a.fy, q1), q2), (double)a.cy);
+        int flags = 0, cell = -1;
+        if (in_image(__double2float_rn(u), __double2float_rn(v), 8, 0, a.width, a.height)) {
+            flags |= DSDTM_LM_IN_IMAGE;
+            cell = (int)__ddiv_rn(v, (double)a.cell_size) * a.grid_cols + (int)__ddiv_rn(u, (double)a.cell_size);
+        }
+        const double* O = a.centers + 3 * (size_t)pair;
+        double f0 = __dsub_rn(cc0, P0), f1 = __dsub_rn(cc1, P1), f2 = __dsub_rn(cc2, P2);
+        double n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1)), __dmul_rn(f2, f2)));
+        f0 = __ddiv_rn(f0, n); f1 = __ddiv_rn(f1, n); f2 = __ddiv_rn(f2, n);
+        double r0 = __dsub_rn(O[0], P0), r1 = __dsub_rn(O[1], P1), r2 = __dsub_rn(O[2], P2);
+        const double rn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2)));
+        r0 = __ddiv_rn(r0, rn); r1 = __ddiv_rn(r1, rn); r2 = __ddiv_rn(r2, rn);
+        const double cosv = __dadd_rn(__dadd_rn(__dmul_rn(r0, f0), __dmul_rn(r1, f1)), __dmul_rn(r2, f2));
+        const double best_cos = (cosv > 0.0) ? cosv : 0.0;                                               // tMin_angle starts at 0, strict >
+        if (!(best_cos < 0.5)) flags |= DSDTM_LM_OBS_OK;
+        const float sc = (float)(1 << ft.level);
+        if (in_image(__fdiv_rn(ft.px[0], sc), __fdiv_rn(ft.px[1], sc), 5, ft.level, a.width, a.height)) flags |= DSDTM_LM_REF_OK;
+        cd.px[0] = u; cd.px[1] = v;
+        const int all = DSDTM_LM_IN_IMAGE | DSDTM_LM_OBS_OK | DSDTM_LM_REF_OK;
+        if ((flags & all) == all) {
+            cd.ref_slot = a.ref_slots[pair]; cd.ref_level = ft.level;
+            cd.ref_px[0] = ft.px[0]; cd.ref_px[1] = ft.px[1];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { cd.ref_normal[k] = ft.normal[k]; cd.ref_point_w[k] = ft.point_w[k]; cd.kf_center[k] = O[k]; }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) cd.pose_c2r[k] = Tck[k];
+        }
+        r.px_proj[0] = u; r.px_proj[1] = v; r.px[0] = u; r.px[1] = v;
+        r.cell = cell; r.obs = j; r.flags = flags;
+    }
+    a.cand[i] = cd;
+    a.out[i] = r;
+}
+
 // After Align2D: fold (refined px * 2^level, level, converged) into the per-point records so that ONE copy returns everything.
 __global__ void __launch_bounds__(128) local_map_finalize_kernel(dsdtm_reproj* __restrict__ out, const double* __restrict__ px,
-                                                                 const int* __restrict__ level, const uint8_t* __restrict__ conv, int n)
+                                                                 const int* __restrict__ level, const uint8_t* __restrict__ conv, int n, int i0)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i0 + n) return;
     const int L = level[i];
     if (L < 0) return;                                              // not aligned: px stays the projection, level -1
     const double sc = (double)(1 << L);                             // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
@@ -150,9 +230,24 @@ __global__ void __launch_bounds__(128) local_map_finalize_kernel(dsdtm_reproj* _
 
 }  // namespace
 
-cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s)
+cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s, dsdtm_reproj* out_d, int i0)
 {
-    local_map_finalize_kernel<<<(n_pts + 127) / 128, 128, 0, s>>>(c->lm_reproj_d, c->patch_px_d, c->patch_level_d, c->patch_conv_d, n_pts);
+    local_map_finalize_kernel<<<(n_pts + 127) / 128, 128, 0, s>>>(out_d ? out_d : c->lm_reproj_d, c->patch_px_d, c->patch_level_d, c->patch_conv_d, n_pts, i0);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pair_candidates(dsdtm_ctx* c, int pair0, int n_pairs, int feat_stride, int ppp, cudaStream_t s)
+{
+    PcArgs a;
+    a.ref_slots = c->ref_slots_d; a.feats = c->feats_d; a.feat_stride = feat_stride; a.n_feats = c->n_feats_d;
+    a.centers = c->centers_d; a.poses_ref = c->poses_ref_d; a.poses_c2r = c->poses_out_d;
+    a.pair0 = pair0; a.n_pairs = n_pairs; a.ppp = ppp;
+    a.fx = c->cam.fx; a.fy = c->cam.fy; a.cx = c->cam.cx; a.cy = c->cam.cy;
+    a.width = c->cam.width; a.height = c->cam.height; a.cell_size = c->prm.cell_size; a.grid_cols = c->grid_cols;
+    a.cand = c->cand_d; a.out = c->pair_reproj_d;
+    const long long n = (long long)n_pairs * ppp;
+    pair_candidates_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
     c->launches++;
     return cudaGetLastError();
 }

@@ -98,6 +98,10 @@ void*       dsdtm_host_alloc(size_t bytes);
 void        dsdtm_host_free(void* p);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 long long   dsdtm_launch_count(const dsdtm_ctx* ctx);
+/* measurement aid (no reference counterpart): the DFMA throughput this GPU sustains on dependency-free streams, in TFLOP/s (2 flops
+ * per DFMA) and in warp instructions per clock and SM at the nominal maximum clock -- the ceiling bench.py puts the fp64
+ * sparse-alignment kernel against. Runs a ~10 ms kernel on the context's stream and synchronises. */
+int         dsdtm_probe_fp64(dsdtm_ctx* ctx, double* tflops, double* dfma_warp_insts_per_clk_per_sm);
 /* tuning knobs (never change results): "sa_warps_per_pair" = 0 (auto: 10 for a lone pair, 4, or 3 from four pairs per SM
  * upwards) | 1 | 2 | 3 | 4 | 5 | 10 warps of one CTA per frame pair;
  * "pyramid_kernel" = 0 (auto: TMA bulk-staged kernel where the level shape allows, whole-level kernel for the ragged tail, tile
@@ -369,9 +373,26 @@ int dsdtm_batch_stage(dsdtm_ctx* ctx, int n_pairs, const int* ref_slots, const i
                       const uint8_t* patches10, const double* patch_px, const int* patch_level,
                       int patches_per_pair, int align_iters);
 int dsdtm_batch_run(dsdtm_ctx* ctx, int flags);
+/* The refinement chain of the reference as a batched stage (ref: src/Tracking.cpp:219-224,257-313 TrackWithLocalMap right after
+ * Sprase_ImgAlign::Run; src/Feature_alignment.cpp:54-69,128-158): every pair's local map is its reference frame seen as one key
+ * frame, whose features with map points (the staged dsdtm_ref_feat records, indices < points_per_pair) are the candidates. After
+ * dsdtm_batch_stage, stage_map uploads the reference poses (n_pairs x 7, Frame::Get_Pose of the reference frames); then
+ * dsdtm_batch_run(flags | 2) runs pyramid -> sparse alignment -> pose composition + reprojection + closest observation + gates ->
+ * SolveAffineMatrix / GetBestSearchLevel -> WarpAffine -> Align2DGaussNewton for every candidate, all on the device, and
+ * fetch_map returns n_pairs x points_per_pair records (obs = feature index; cell, flags, level, refined px as in
+ * dsdtm_local_map_align_batch). The greedy per-cell selection of SearchLocalPoints stays with the caller. */
+int dsdtm_batch_stage_map(dsdtm_ctx* ctx, const double* poses_ref_c2w, int points_per_pair, int max_search_level, int align_iters);
+int dsdtm_batch_fetch_map(dsdtm_ctx* ctx, dsdtm_reproj* reproj_out /* n_pairs x points_per_pair */);
 int dsdtm_batch_fetch(dsdtm_ctx* ctx, double* poses_out, int* n_tracked, double* patch_px_out, uint8_t* patch_conv);
 /* end-to-end step with HOST buffers: uploads the n_pairs cur images (dense, pinned recommended) into their cur slots,
  * stages the per-pair inputs, runs, and fetches -- copies overlapped with compute in chunks on internal streams. */
+/* the same with the refinement chain of dsdtm_batch_stage_map instead of host patches: per pair only the current image, the
+ * reference features and three small arrays go up, the poses / counts / per-candidate records come back */
+int dsdtm_track_batch_e2e(dsdtm_ctx* ctx, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots, const int* cur_slots,
+                          const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats, const double* ref_centers,
+                          const double* poses_ref_c2w, const double* poses_c2r_in, int max_level, int min_level, int max_iters,
+                          int points_per_pair, int max_search_level, int align_iters, double* poses_c2r_out, int* n_tracked,
+                          dsdtm_reproj* reproj_out);
 int dsdtm_pair_batch_e2e(dsdtm_ctx* ctx, int n_pairs, const uint8_t* cur_imgs, const int* ref_slots,
                          const int* cur_slots, const dsdtm_ref_feat* feats, int feat_stride, const int* n_feats,
                          const double* ref_centers, const double* poses_in, int max_level, int min_level,

@@ -371,6 +371,25 @@ def pair_batch(cam, levels, ref_pyrs, cur_imgs, feats, n_feats, ref_centers, pos
     return poses_out, n_tracked, px_out, conv
 
 
+REPROJ_DT = np.dtype([("px_proj", "<f8", 2), ("px", "<f8", 2), ("cell", "<i4"), ("obs", "<i4"), ("flags", "<i4"), ("level", "<i4")])
+
+
+def pair_batch_map(cam, levels, cell_size, ref_pyrs, cur_imgs, feats, n_feats, ref_centers, poses_ref, poses_in, max_level, min_level,
+                   max_iters, points_per_pair, max_search_level, align_iters, n_threads):
+    """CPU restatement of one bench step with the reference's refinement chain (pyramid(cur) + Run + per-feature FindMatchDirect)."""
+    n_pairs = len(n_feats)
+    feats = np.ascontiguousarray(feats, REF_FEAT_DT)
+    fpp = feats.size // n_pairs
+    poses_out = np.empty((n_pairs, 7)); n_tracked = np.empty(n_pairs, np.int32)
+    rep = np.zeros((n_pairs, points_per_pair), REPROJ_DT)
+    lib().orc_pair_batch_map(C.byref(cam), int(levels), int(cell_size), _p(u8(ref_pyrs)), _p(u8(cur_imgs)), n_pairs, _p(feats), fpp,
+                             _p(np.ascontiguousarray(n_feats, np.int32)), _p(np.ascontiguousarray(ref_centers, np.float64)),
+                             _p(np.ascontiguousarray(poses_ref, np.float64)), _p(np.ascontiguousarray(poses_in, np.float64)),
+                             int(max_level), int(min_level), int(max_iters), int(points_per_pair), int(max_search_level), int(align_iters),
+                             int(n_threads), _p(poses_out), _p(n_tracked), _p(rep))
+    return poses_out, n_tracked, rep
+
+
 BA_SUMMARY_DT = np.dtype([("iterations", "<i4"), ("termination", "<i4"), ("n_successful", "<i4"), ("pad", "<i4"),
                           ("initial_cost", "<f8"), ("final_cost", "<f8")])
 BA_FUNCTION_TOL, BA_PARAMETER_TOL, BA_GRADIENT_TOL, BA_NO_CONVERGENCE, BA_FAILURE, BA_MIN_RADIUS, BA_NO_RESIDUALS = range(7)

@@ -1351,4 +1351,78 @@ int orc_pair_batch(const orc_cam* cam, int levels, const uint8_t* ref_pyrs, cons
     return 0;
 }
 
+// The same step with the reference's own refinement chain instead of host-provided patches (ref: src/Tracking.cpp:219-224,257-313
+// TrackWithLocalMap right after Run, with the reference frame as the one key frame of the local map; src/Feature_alignment.cpp:54-69,
+// 128-158; src/MapPoint.cpp:133-174): per feature with a map point -> ReprojectPoint, Get_ClosetObs (single observation), the IsInImage
+// gate, SolveAffineMatrix, GetBestSearchLevel, WarpAffine, GetPatchNoBoarder, Align2DGaussNewton. Records as dsdtm_reproj.
+int orc_pair_batch_map(const orc_cam* cam, int levels, int cell_size, const uint8_t* ref_pyrs, const uint8_t* cur_imgs, int n_pairs,
+                       const orc_ref_feat* feats, int feats_per_pair, const int* n_feats, const double* ref_centers,
+                       const double* poses_ref, const double* poses_in, int max_level, int min_level, int max_iters,
+                       int points_per_pair, int max_search_level, int align_iters, int n_threads,
+                       double* poses_out, int* n_tracked, orc_reproj* reproj)
+{
+    std::vector<int> offs(levels), ws(levels), hs(levels);
+    {
+        int off = 0;
+        for (int l = 0; l < levels; ++l) {
+            ws[l] = l ? (ws[l - 1] + 1) / 2 : cam->width;
+            hs[l] = l ? (hs[l - 1] + 1) / 2 : cam->height;
+            offs[l] = off; off += ws[l] * hs[l];
+        }
+    }
+    const size_t pyr_bytes = (size_t)offs[levels - 1] + (size_t)ws[levels - 1] * hs[levels - 1];
+    const size_t img_bytes = (size_t)cam->width * cam->height;
+    const int grid_cols = (cam->width + cell_size - 1) / cell_size;
+    auto work = [&](int t) {
+        std::vector<uint8_t> cur(pyr_bytes);
+        std::vector<int> o(levels), w(levels), h(levels);
+        for (int i = t; i < n_pairs; i += n_threads) {
+            orc_pyramid(cur_imgs + (size_t)i * img_bytes, cam->width, cam->height, levels, cur.data(), o.data(), w.data(), h.data());
+            int nl = 0;
+            const uint8_t* ref = ref_pyrs + (size_t)i * pyr_bytes;
+            n_tracked[i] = orc_sparse_align(cam, ref, cur.data(), offs.data(), ws.data(), hs.data(),
+                                            feats + (size_t)i * feats_per_pair, n_feats[i], ref_centers + 3 * (size_t)i,
+                                            poses_in + 7 * (size_t)i, max_level, min_level, max_iters, poses_out + 7 * (size_t)i,
+                                            nullptr, 0, &nl);
+            // cur.Set_Pose(T_c2r * ref.Get_Pose()) (ref: src/Sprase_ImageAlign.cpp:57); mOw (ref: src/Frame.cpp:167-174)
+            double pose_cur[7], inv[7], Tck[7];
+            orc_se3_mul(poses_out + 7 * (size_t)i, poses_ref + 7 * (size_t)i, pose_cur);
+            orc_se3_inv(pose_cur, inv);
+            const double cur_center[3] = { inv[4], inv[5], inv[6] };
+            orc_se3_inv(poses_ref + 7 * (size_t)i, inv);
+            orc_se3_mul(pose_cur, inv, Tck);                                          // ref: src/Feature_alignment.cpp:181
+            const double* kfc = ref_centers + 3 * (size_t)i;
+            for (int j = 0; j < points_per_pair; ++j) {
+                orc_reproj& r = reproj[(size_t)i * points_per_pair + j];
+                r.px_proj[0] = r.px_proj[1] = r.px[0] = r.px[1] = 0.0; r.cell = -1; r.obs = -1; r.flags = 0; r.level = -1;
+                if (j >= n_feats[i]) continue;
+                const orc_ref_feat& f = feats[(size_t)i * feats_per_pair + j];
+                if (!f.initial) continue;
+                double px[2]; int cell = -1;
+                if (orc_reproject_point(cam, pose_cur, f.point_w, cell_size, grid_cols, px, &cell)) { r.flags |= 1; r.cell = cell; }
+                r.px_proj[0] = r.px[0] = px[0]; r.px_proj[1] = r.px[1] = px[1]; r.obs = j;
+                int best = -1;
+                if (orc_closest_obs(cur_center, f.point_w, kfc, 1, &best)) r.flags |= 2;
+                const float sc = (float)(1 << f.level);
+                if (orc_is_in_image(cam, f.px[0] / sc, f.px[1] / sc, 5, f.level)) r.flags |= 4;
+                if ((r.flags & 7) != 7) continue;
+                double A[4];
+                orc_solve_affine(cam, kfc, f.point_w, f.normal, f.px, f.level, Tck, A);
+                const int L = orc_best_search_level(A, max_search_level);
+                uint8_t p10[100], p8[64];
+                orc_warp_affine(A, ref + offs[f.level], ws[f.level], hs[f.level], ws[f.level], f.px, f.level, L, p10);
+                orc_patch_no_border(p10, p8);
+                double q[2] = { px[0] / (double)(1 << L), px[1] / (double)(1 << L) };
+                if (orc_align2d(cur.data() + offs[L], ws[L], hs[L], ws[L], p10, p8, align_iters, q, nullptr)) r.flags |= 8;
+                r.px[0] = q[0] * (double)(1 << L); r.px[1] = q[1] * (double)(1 << L); r.level = L;
+            }
+        }
+    };
+    if (n_threads <= 1) { n_threads = 1; work(0); return 0; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+    return 0;
+}
+
 }  // extern "C"

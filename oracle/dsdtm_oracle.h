@@ -184,6 +184,18 @@ int orc_pair_batch(const orc_cam* cam, int levels, const uint8_t* ref_pyrs, cons
                    int align_iters, int n_threads,
                    double* poses_out, int* n_tracked, double* patch_px_out, uint8_t* patch_conv);
 
+/* per-candidate record of the batched refinement chain (layout of dsdtm_reproj in include/dsdtm_gpu.h) */
+typedef struct {
+    double  px_proj[2];
+    double  px[2];
+    int32_t cell, obs, flags, level;
+} orc_reproj;
+int orc_pair_batch_map(const orc_cam* cam, int levels, int cell_size, const uint8_t* ref_pyrs, const uint8_t* cur_imgs, int n_pairs,
+                       const orc_ref_feat* feats, int feats_per_pair, const int* n_feats, const double* ref_centers,
+                       const double* poses_ref, const double* poses_in, int max_level, int min_level, int max_iters,
+                       int points_per_pair, int max_search_level, int align_iters, int n_threads,
+                       double* poses_out, int* n_tracked, orc_reproj* reproj);
+
 #ifdef __cplusplus
 }
 #endif

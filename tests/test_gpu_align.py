@@ -581,3 +581,58 @@ def test_chained_batch_is_safe_under_chunking_and_in_the_e2e_pipeline(built):
             assert (out["poses"] == base[0]).all() and (out["n_tracked"] == base[1]).all()
     finally:
         c.close()
+
+
+def test_batched_refinement_chain_matches_oracle(built):
+    """dsdtm_batch_run(flags | 2) / dsdtm_track_batch_e2e: pyramid -> Run -> pose composition -> ReprojectPoint / Get_ClosetObs / gates ->
+    SolveAffineMatrix -> WarpAffine -> Align2D for every reference feature of every pair, against the same chain restated with the
+    oracle (orc_pair_batch_map): flags, cells, search levels exact, refined pixels within 1e-3 px, poses within 1e-5."""
+    from dsdtm_b200 import capi
+    cam = dict(S.KINECT)
+    oc = H.ocam(cam)
+    T_ref = S.pose_from_xi(np.r_[0.2, -0.1, 0.05, 0.03, -0.02, 0.04])
+    prs = [S.make_pair(61 + k, cam, trans=0.03, rot_deg=0.8, ref_pose=(T_ref if k % 2 else None)) for k in range(3)]
+    n, stride, ppp = 6, 320, 300
+    c = capi.Context(cam, levels=5, cell_size=15, max_feats=stride, max_patches=ppp, max_frames=2 * n, max_batch=n)
+    try:
+        feats = np.zeros((n, stride), O.REF_FEAT_DT); nf = np.zeros(n, np.int32); centers = np.zeros((n, 3))
+        poses_ref = np.zeros((n, 7)); poses_in = np.tile(S.IDENTITY, (n, 1))
+        ref_pyrs = []; cur_imgs = []
+        for i in range(n):
+            pr = prs[i % 3]
+            c.upload(2 * i, pr["ref_img"]); c.upload(2 * i + 1, pr["cur_img"])
+            corners, pyr = H.detect_oracle(pr["ref_img"], 5, 15, 300)
+            F = H.ref_feats_from_corners(cam, corners, pr["ref_points"])
+            if i >= 3:
+                F["initial"][::11] = 0                                   # features without a map point are no candidates
+                F["px"][3] = (2.0, 2.0)                                  # a reference feature too close to the border: REF_OK fails
+            nf[i] = len(F); feats[i, :nf[i]] = F; centers[i] = O.se3_inv(pr["T_ref"])[4:]; poses_ref[i] = pr["T_ref"]
+            ref_pyrs.append(pyr[0]); cur_imgs.append(pr["cur_img"])
+        ref_slots = 2 * np.arange(n, dtype=np.int32); cur_slots = ref_slots + 1
+        c.batch_stage(ref_slots, cur_slots, feats, nf, centers, poses_in, 5, 0, 8, None, None, None, 10)
+        c.batch_stage_map(poses_ref, ppp, 2, 10)
+        c.batch_run(3)
+        poses_g, nt_g, _, _ = c.batch_fetch()
+        rep_g = c.batch_fetch_map()
+        poses_o, nt_o, rep_o = O.pair_batch_map(oc, 5, 15, np.stack(ref_pyrs), np.stack(cur_imgs), feats, nf, centers, poses_ref, poses_in,
+                                                5, 0, 8, ppp, 2, 10, 4)
+        for i in range(n):
+            d = S.pose_dist(poses_o[i], poses_g[i])
+            assert d[0] < 1e-5 and d[1] < 1e-5 and nt_g[i] == nt_o[i]
+        assert (rep_g["flags"] == rep_o["flags"]).all() and (rep_g["cell"] == rep_o["cell"]).all()
+        assert (rep_g["level"] == rep_o["level"]).all() and (rep_g["obs"] == rep_o["obs"]).all()
+        assert np.abs(rep_g["px_proj"] - rep_o["px_proj"]).max() < 1e-6        # the aligned poses differ by ~1e-15; projections follow
+        ok = (rep_g["flags"] & capi.LM_CONVERGED) != 0
+        assert ok.sum() > 0.8 * nf.sum() * 0.9 and np.abs(rep_g["px"][ok] - rep_o["px"][ok]).max() <= 1e-3
+        assert (rep_g["level"][:, :][rep_g["flags"] & 7 != 7] == -1).all()
+        # replay + the host-buffer entry give the same bits
+        c.batch_run(3)
+        assert c.batch_fetch_map().tobytes() == rep_g.tobytes()           # byte-wise: Q3 candidates carry NaN positions
+        out = dict(poses=np.empty((n, 7)), n_tracked=np.empty(n, np.int32), reproj=np.zeros((n, ppp), capi.REPROJ_DT))
+        c.track_batch_e2e(np.ascontiguousarray(np.stack(cur_imgs)), ref_slots, cur_slots, feats, stride, nf, centers, poses_ref, poses_in, 5, 0, 8, ppp, 2, 10, out)
+        assert (out["poses"] == poses_g).all() and (out["n_tracked"] == nt_g).all() and out["reproj"].tobytes() == rep_g.tobytes()
+        with pytest.raises(capi.DsdtmError):
+            c.batch_stage(ref_slots, cur_slots, feats, nf, centers, poses_in, 5, 0, 8, None, None, None, 10)
+            c.batch_run(2)                                             # chain requested without dsdtm_batch_stage_map
+    finally:
+        c.close()
