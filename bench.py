@@ -12,6 +12,9 @@ One "step" = one pass of the hot path over one batch of B frame pairs per GPU, a
 The reference arm (--impl reference) times the CPU restatement of the reference (oracle/, kind "port": the reference itself
 needs OpenCV/Eigen/Sophus/Ceres and cannot be built here) on all host threads.
 No pair shards across GPUs: N > 1 = N independent replicas of the batch (weak scaling), no collective on the data path.
+Extra keys on the same line: `refine_chain` = the step with the reference's own refinement chain (reprojection -> closest observation ->
+affine -> warp -> Align2D on the device) instead of host patches; `strong_scaling` = BASELINE configs[4] as written: ONE batch of 4096
+EuRoC 752x480 pairs partitioned over the ranks (contiguous blocks).
 """
 import argparse
 import json
@@ -34,6 +37,20 @@ LEVELS = 5                                                      # Camera.MaxPyra
 ALIGN2D_ITERS = 10                                              # src/Feature_alignment.cpp:152
 N_FEATS = 300
 FEAT_STRIDE = 320
+
+
+def make_config(cam_name, cam, B):
+    """The `config` object: identical in the GPU arm and in the reference arm (the driver compares them)."""
+    w, h = cam["width"], cam["height"]
+    pyr = 0
+    for _ in range(LEVELS):
+        pyr += w * h
+        w, h = (w + 1) // 2, (h + 1) // 2
+    return {"workload": "%s: %d independent %dx%d %s frame pairs per GPU, %d FAST/Shi-Tomasi features, 5-level pyramid(cur) + "
+                        "Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it)"
+                        % ("configs[4] sweep" if cam_name == "euroc" else "configs[0] shape batched", B, cam["width"], cam["height"], cam_name, N_FEATS, N_FEATS),
+            "camera": cam_name, "pairs_per_gpu": B, "features": N_FEATS, "levels": LEVELS, "sparse_align": ALIGN_CFG, "align2d_iters": ALIGN2D_ITERS,
+            "l2": "inputs larger than L2 (%.0f MB of pyramids per step)" % (2 * B * pyr / 1e6)}
 
 
 def shard(n_total, world, rank):
@@ -101,6 +118,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank to the CPUs of its GPU's NUMA node BEFORE any pinned host buffer is allocated (cudaHostAlloc places pages by the
+    calling thread's policy = local node): with 4-8 ranks on one box the H2D streams otherwise share one socket's memory controllers and
+    cross the inter-socket link (r1: e2e efficiency 0.43 at 8 GPUs)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True,
+                             timeout=10).stdout.strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # 00000000:1b:00.0 -> 0000:1b:00.0
+        d = "/sys/bus/pci/devices/" + bus
+        node = int(open(d + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(d + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"node": node, "cpus": len(cpus), "bound": True}
+        return {"node": node, "cpus": len(os.sched_getaffinity(0)), "bound": False}
+    except Exception as e:                                   # no sysfs / single-node box: nothing to bind
+        return {"node": None, "cpus": len(os.sched_getaffinity(0)), "bound": False, "note": str(e)[:80]}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -108,19 +149,37 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_file():
+    """the newest committed ncu --set full capture of the dominant kernel"""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return p
+    return os.path.join(ROOT, "profiles", "r2_traffic.json")
+
+
+def fp64_insts_per_pair(kernel):
+    """smsp__inst_executed_pipe_fp64.sum (warp instructions on the FP64 pipe) per pair from the committed capture, or None"""
+    p = traffic_file()
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p)).get(kernel) or {}
+    return t.get("fp64_warp_insts_per_pair")
+
+
 def ncu_summary(kernel):
     """Pipe / issue figures of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json); {} if absent."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = traffic_file()
     if not os.path.exists(p):
         return {}
     t = json.load(open(p)).get(kernel) or {}
-    return {k: t[k] for k in ("issue_slots_busy_pct", "fp64_pipe_pct", "dram_throughput_pct", "l1tex_hit_pct", "l2_hit_pct", "source") if k in t}
+    return {k: t[k] for k in ("issue_slots_busy_pct", "fp64_pipe_pct", "dram_throughput_pct", "l1tex_hit_pct", "l2_hit_pct", "warp_instructions", "fp64_warp_insts_per_pair", "source") if k in t}
 
 
 def measured_traffic(kernel, pairs):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
     (profiles/r1_traffic.json, taken at 4096 pairs), scaled per pair. None if the capture is absent."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = traffic_file()
     if not os.path.exists(p):
         return None
     t = json.load(open(p)).get(kernel)
@@ -143,6 +202,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
@@ -222,6 +283,7 @@ def run_ours(args):
     n_levels = ALIGN_CFG["max_level"] - ALIGN_CFG["min_level"]
     restage()
     hbm_peak, peak_src = peaks()
+    fp64_tflops, dfma_per_clk_sm = ctx.probe_fp64()          # measured live: dependency-free DFMA streams on this GPU
     sa_bytes = B * (int(np.mean(batch["n_feats"])) * (64 + 49 * n_levels + 25 * iters) + 112)
     g = ctx
     pyr_bytes = B * sum(g.ws[l - 1] * g.hs[l - 1] + g.ws[l] * g.hs[l] for l in range(1, LEVELS))
@@ -239,6 +301,36 @@ def run_ours(args):
     finally:
         ctx.profile(False)
     fast_bytes = nfast * (sum(g.ws[l] * g.hs[l] for l in range(LEVELS)) + ctx.n_cells * 16)
+
+    # ---------------- the step with the reference's own refinement chain: patches are NOT host inputs; every
+    # reference feature with a map point is reprojected through the aligned pose, gated, affine-warped from the reference frame and
+    # refined by Align2D on the device (dsdtm_batch_stage_map / dsdtm_batch_run(flags | 2)) -- dsdtm_track_frame, batched
+    ctx.batch_stage_map(batch["poses_ref"], N_FEATS, LEVELS - 3, ALIGN2D_ITERS)
+    for _ in range(max(args.warmup, 3)):
+        ctx.batch_run(3)
+    ctx.sync()
+    rep = ctx.batch_fetch_map()
+    chain_conv = float(((rep["flags"] & capi.LM_CONVERGED) != 0).sum() / max(int(batch["n_feats"].sum()), 1))
+    if chain_conv < 0.5:
+        raise SystemExit("bench.py: refinement chain converged on %.0f %% of the features only" % (100 * chain_conv))
+    barrier()
+    lc0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        ctx.batch_run(3)
+    chain_ms = ctx.timer_stop()
+    chain_launches = ctx.launch_count() - lc0
+    barrier()
+    tc = torch.tensor([chain_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    chain_ms_per_step = float(tc.item()) / args.steps
+    ctx.profile(True); ctx.profile_get(reset=True)
+    for _ in range(args.steps):
+        ctx.batch_run(3)
+    cst = ctx.profile_get(reset=True)
+    ctx.profile(False)
+    chain_stages = {k_: cst[k_][0] / args.steps for k_ in ("pyramid", "sparse_align", "local_map", "warp_affine", "align2d")}
 
     # ---------------- single-pair latency (BASELINE target: < 200 us sparse alignment + feature refinement per 640x480 frame)
     def stage_n(n):
@@ -443,6 +535,39 @@ def run_ours(args):
     h2d = int(cur_imgs.nbytes + sum(hb[k_].nbytes for k_ in hb))
     d2h = int(sum(out[k_].nbytes for k_ in out))
 
+    # ---------------- the chain variant end to end: per pair only the cur image, the reference features and four small arrays go up
+    hb["poses_ref"] = pin((B, 7), np.float64); hb["poses_ref"][...] = batch["poses_ref"]
+    cout = dict(poses=pin((B, 7), np.float64), n_tracked=pin((B,), np.int32), reproj=pin((B, N_FEATS), capi.REPROJ_DT))
+
+    def chain_e2e_step():
+        ctx.track_batch_e2e(cur_imgs, hb["ref_slots"], hb["cur_slots"], hb["feats"], FEAT_STRIDE, hb["n_feats"], hb["centers"], hb["poses_ref"],
+                            hb["poses_in"], ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], N_FEATS, LEVELS - 3,
+                            ALIGN2D_ITERS, cout)
+
+    for _ in range(max(args.warmup, 3)):
+        chain_e2e_step()
+    if cout["reproj"].tobytes() != rep.tobytes():
+        raise SystemExit("bench.py: chain e2e results differ from the device-resident run")
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(args.steps):
+        chain_e2e_step()
+    chain_e2e_wall = time.perf_counter() - t2
+    barrier()
+    tce = torch.tensor([chain_e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tce, op=dist.ReduceOp.MAX)
+    chain_h2d = int(cur_imgs.nbytes + sum(hb[k_].nbytes for k_ in ("ref_slots", "cur_slots", "feats", "n_feats", "centers", "poses_in", "poses_ref")))
+    chain_d2h = int(sum(cout[k_].nbytes for k_ in cout))
+    refine_chain = {
+        "value": world * B / (chain_ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": chain_ms_per_step, "gpu_launches": int(chain_launches),
+        "stages_ms_per_step": chain_stages, "converged_fraction": chain_conv,
+        "e2e": {"value": world * B * args.steps / float(tce.item()), "unit": UNIT, "h2d_bytes_per_step": chain_h2d, "d2h_bytes_per_step": chain_d2h,
+                "ms_per_step": float(tce.item()) * 1e3 / args.steps},
+        "workload": "pyramid(cur) -> Sprase_ImgAlign(4,0,30) -> cur.Set_Pose -> ReprojectPoint + Get_ClosetObs + IsInImage gates -> SolveAffineMatrix + "
+                    "GetBestSearchLevel -> WarpAffine -> Align2DGaussNewton(10) for the %d map points of the pair's reference key frame "
+                    "(ref: src/Tracking.cpp:219-224,257-313; src/Feature_alignment.cpp:54-69,128-158), all on the device" % N_FEATS}
+
     # ---------------- CLAHE ingest stage (overwrites frame slots, therefore after everything that uses them)
     if ingest is not None and rank == 0:
         try:
@@ -463,25 +588,53 @@ def run_ours(args):
     # ---------------- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample, all host threads
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, full_affinity)          # the CPU baseline uses every host core, not only the GPU's NUMA node
         cpu = cpu_baseline(batch, cam, sample=min(B, args.cpu_sample))
         # the checker beside the number: CPU port and CUDA path agree on the sampled pairs (tolerances of tests/)
         cp = cpu.pop("_poses")
         d = np.array([S.pose_dist(cp[i], poses[i]) for i in range(len(cp))])
         cpu["max_pose_diff_vs_gpu"] = [float(d[:, 0].max()), float(d[:, 1].max())]
+        ccpu = cpu_baseline(batch, cam, sample=min(B, args.cpu_sample), chain=True)
+        crep = ccpu.pop("_reproj"); ccpu.pop("_poses")
+        nchk = len(crep)
+        same = bool((crep["flags"] == rep[:nchk]["flags"]).all() and (crep["level"] == rep[:nchk]["level"]).all())
+        okc = (crep["flags"] & capi.LM_CONVERGED) != 0
+        ccpu["decisions_equal_gpu"] = same
+        ccpu["max_px_diff_vs_gpu"] = float(np.abs(crep["px"][okc] - rep[:nchk]["px"][okc]).max()) if okc.any() else None
+        refine_chain["cpu_baseline"] = ccpu
+
+    ctx.close()
+    strong = None
+    if not args.no_strong:
+        bind_to_gpu_numa(local)                         # (the CPU baseline above ran on every core)
+        strong = run_strong(args, torch, dist, rank, world, local)
 
     if rank == 0:
         sa_gbs = sa_bytes / (sa_ms * 1e-3) / 1e9
+        traffic = measured_traffic("sparse_align_kernel", B) if args.cam == "kinect" else None
+        fpi = fp64_insts_per_pair("sparse_align_kernel") if args.cam == "kinect" else None
+        # The dominant kernel is an fp64 Gauss-Newton chain: its pipe is the FP64 pipe, its memory side is far from the HBM roof.
+        # achieved = warp instructions on the FP64 pipe (ncu smsp__inst_executed_pipe_fp64.sum of the committed capture, per pair) x 32 lanes
+        # x 2 flop / measured kernel time; peak = the DFMA rate dsdtm_probe_fp64 measured on this GPU in this run.
+        fp64_achieved = (fpi * B * 64.0 / (sa_ms * 1e-3) / 1e12) if fpi else None
+        roofline = {"kernel": "sparse_align_kernel", "bound": "fp64", "achieved": fp64_achieved, "peak": fp64_tflops, "unit": "TFLOP/s",
+                    "frac": (fp64_achieved / fp64_tflops) if fp64_achieved else None, "traffic": traffic,
+                    "peak_source": "measured live: dsdtm_probe_fp64 (16 independent DFMA chains per thread, 8 CTAs of 256 threads per SM, best of 4); "
+                                   "%.2f DFMA warp instructions per clock and SM at the nominal max clock" % dfma_per_clk_sm,
+                    "ms_per_launch": sa_ms, "fp64_warp_insts_per_launch": (fpi * B) if fpi else None,
+                    "hbm": {"achieved": sa_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sa_gbs / hbm_peak, "traffic": traffic,
+                            "algorithmic_bytes_per_launch": sa_bytes, "sector_waste": (traffic / sa_bytes) if traffic else None,
+                            "peak_source": peak_src},
+                    "ncu": ncu_summary("sparse_align_kernel") if args.cam == "kinect" else None,   # the committed capture is the 640x480 step
+                    "note": "dependent Gauss-Newton chain on the FP64 pipe: latency/issue-bound (profiles/r2_sparse_align.md: a round of the feature "
+                            "pass is a 3.4-4.5 k-cycle dependent chain at 2.9 warps per scheduler); the HBM side is reported under `hbm` (DRAM traffic "
+                            "= 32-byte sectors for 5- and 7-byte window rows); see stages for the HBM-bound kernels"}
         line = {
             "metric": METRIC.replace("640x480", "%dx%d" % (cam["width"], cam["height"])), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic: %d ray-cast relief scenes tiled to %d pairs/GPU with per-pair start poses; every pair has its own frames, "
                     "features and patches in HBM" % (batch["n_scenes"], B),
-            "config": {"workload": "%s: %d independent %dx%d %s frame pairs per GPU, %d FAST/Shi-Tomasi features, "
-                                   "5-level pyramid(cur) + Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it)"
-                                   % ("configs[4] sweep" if args.cam == "euroc" else "configs[0] shape batched", B, cam["width"], cam["height"], args.cam, N_FEATS, ppp),
-                       "camera": args.cam,
-                       "pairs_per_gpu": B, "features": N_FEATS, "levels": LEVELS, "sparse_align": ALIGN_CFG, "align2d_iters": ALIGN2D_ITERS,
-                       "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (2 * B * ctx.L.dsdtm_frame_stride(ctx.hp) / 1e6)},
+            "config": make_config(args.cam, cam, B),
             "us_per_pair": ms_per_step * 1e3 / B,
             "gn_iterations_per_pair": iters,
             "latency": latency,
@@ -489,12 +642,7 @@ def run_ours(args):
                     "ms_per_step": float(t.item()) * 1e3 / args.steps, "timer": "host wall clock around the C-ABI call"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "sparse_align_kernel", "bound": "hbm", "achieved": sa_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": sa_gbs / hbm_peak, "traffic": measured_traffic("sparse_align_kernel", B) if args.cam == "kinect" else None, "peak_source": peak_src,
-                         "ms_per_launch": sa_ms, "algorithmic_bytes_per_launch": sa_bytes, "ncu": ncu_summary("sparse_align_kernel") if args.cam == "kinect" else None,   # the committed capture is the 640x480 step
-                         "note": "dependent Gauss-Newton chain: latency/issue-bound, not bandwidth-bound (SURVEY 8d): ncu issue slots busy 38 %, "
-                                 "fp64 pipe 38 %, DRAM 18 %, L1/TEX hit 74 % (profiles/r1_sa_bench_summary.txt); traffic is the ncu DRAM byte count "
-                                 "(32-byte sectors for 5-byte window rows) scaled per pair; see stages for the HBM-bound kernels"},
+            "roofline": roofline,
             "stages": {
                 "pyramid": {"ms_per_step": pyr_ms, "GBps": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "frac_hbm": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak,
                             "algorithmic_bytes": pyr_bytes},
@@ -506,16 +654,113 @@ def run_ours(args):
                 "ingest": ingest,
                 "pose_opt": pose_opt},
             "cpu_baseline": cpu,
+            "refine_chain": refine_chain,
+            "strong_scaling": strong,
+            "numa": numa,
             "prep_s": prep_s,
         }
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(batch, cam, sample, threads=None, reps=1):
-    """The oracle (CPU restatement of the reference, kind 'port') on `sample` pairs of the same workload, all host threads."""
+def run_strong(args, torch, dist, rank, world, local):
+    """BASELINE configs[4] as written: ONE batch of `--total-pairs` EuRoC 752x480 pairs, partitioned into contiguous blocks
+    over the ranks (shard()); every rank builds the same global batch description (same seeds) and owns its block. Strong scaling:
+    value = total pairs / max-over-ranks time of a step. No collective on the data path."""
+    from dsdtm_b200 import capi, synth as S, workload as W
+    total = args.total_pairs
+    lo, hi = shard(total, world, rank)
+    n = hi - lo
+    cam = dict(S.EUROC)
+    ctx = capi.Context(cam, levels=LEVELS, cell_size=15, max_feats=FEAT_STRIDE, max_patches=N_FEATS, max_frames=2 * n + 2, max_batch=max(n, 1), device=local)
+    nsc = min(args.scenes, 8)
+    scenes = W.render_scenes(nsc, cam, seed0=W.BASE_SEED + 500000, procs=max(1, min(nsc, (os.cpu_count() or 2) // (2 * world))))
+    batch = W.build_batch(ctx, cam, total, n_feats=N_FEATS, feat_stride=FEAT_STRIDE, patches_per_pair=N_FEATS, seed0=W.BASE_SEED + 500000,
+                          scenes=scenes, lo=lo, hi=hi)
+    ppp = batch["patches_per_pair"]
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx.batch_stage(batch["ref_slots"], batch["cur_slots"], batch["feats"], batch["n_feats"], batch["centers"], batch["poses_in"],
+                    ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], batch["patches"], batch["patch_px"],
+                    batch["patch_level"], ALIGN2D_ITERS)
+    for _ in range(max(args.warmup, 3)):
+        ctx.batch_run(1)
+    poses, nt, px, conv = ctx.batch_fetch()
+    err = np.array([S.pose_dist(poses[i], batch["truth"][i]) for i in range(min(n, 64))])
+    if n and not (np.median(err[:, 0]) < 5e-4 and np.median(err[:, 1]) < 1e-3):
+        raise SystemExit("bench.py: strong-scaling batch did not converge to the synthetic ground truth: %s" % np.median(err, 0))
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        ctx.batch_run(1)
+    ms = allmax(ctx.timer_stop()) / args.steps
+    ctx.profile(True); ctx.profile_get(reset=True)
+    for _ in range(args.steps):
+        ctx.batch_run(1)
+    st = ctx.profile_get(reset=True)
+    ctx.profile(False)
+    # end to end with host buffers
+    h, w = cam["height"], cam["width"]
+    pin = capi.pinned_empty
+    cur_imgs = pin((n, h, w), np.uint8)
+    k = batch["n_scenes"]
+    for i in range(n):
+        cur_imgs[i] = batch["scenes"][(lo + i) % k]["cur_img"]
+    hb = dict(ref_slots=pin((n,), np.int32), cur_slots=pin((n,), np.int32), feats=pin((n, FEAT_STRIDE), capi.REF_FEAT_DT),
+              n_feats=pin((n,), np.int32), centers=pin((n, 3), np.float64), poses_in=pin((n, 7), np.float64),
+              patches=pin((n, ppp, 100), np.uint8), patch_px=pin((n, ppp, 2), np.float64), patch_level=pin((n, ppp), np.int32))
+    for k_, src in (("ref_slots", batch["ref_slots"]), ("cur_slots", batch["cur_slots"]), ("feats", batch["feats"]), ("n_feats", batch["n_feats"]),
+                    ("centers", batch["centers"]), ("poses_in", batch["poses_in"]), ("patches", batch["patches"]), ("patch_px", batch["patch_px"]),
+                    ("patch_level", batch["patch_level"])):
+        hb[k_][...] = src
+    out = dict(poses=pin((n, 7), np.float64), n_tracked=pin((n,), np.int32), px=pin((n, ppp, 2), np.float64), conv=pin((n, ppp), np.uint8))
+
+    def e2e_step():
+        ctx.pair_batch_e2e(cur_imgs, hb["ref_slots"], hb["cur_slots"], hb["feats"], FEAT_STRIDE, hb["n_feats"], hb["centers"], hb["poses_in"],
+                           ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], hb["patches"], hb["patch_px"],
+                           hb["patch_level"], ppp, ALIGN2D_ITERS, out)
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    if not np.array_equal(out["poses"], poses):
+        raise SystemExit("bench.py: strong-scaling e2e results differ from the device-resident run")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    wall = allmax(time.perf_counter() - t0)
+    barrier()
+    g = ctx
+    pyr_bytes = n * sum(g.ws[l - 1] * g.hs[l - 1] + g.ws[l] * g.hs[l] for l in range(1, LEVELS))
+    hbm_peak, _ = peaks()
+    pyr_ms = st["pyramid"][0] / args.steps
+    res = {"config": "BASELINE configs[4]: %d independent 752x480 EuRoC pairs partitioned over %d GPU(s) in contiguous blocks" % (total, world),
+           "scaling": "strong", "total_pairs": total, "pairs_per_gpu": n, "value": total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+           "e2e": {"value": total * args.steps / wall, "unit": UNIT, "ms_per_step": wall * 1e3 / args.steps,
+                   "h2d_bytes_per_step_per_gpu": int(cur_imgs.nbytes + sum(hb[k_].nbytes for k_ in hb)),
+                   "d2h_bytes_per_step_per_gpu": int(sum(out[k_].nbytes for k_ in out))},
+           "stages_ms_per_step_rank0": {"pyramid": pyr_ms, "sparse_align": st["sparse_align"][0] / args.steps, "align2d": st["align2d"][0] / args.steps},
+           "pyramid_frac_hbm_rank0": (pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak) if pyr_ms > 0 else None,
+           "resident_ctas_note": "%d pairs per GPU against %d resident sparse-alignment CTAs (4 per SM)" % (n, 4 * 148)}
+    ctx.close()
+    return res
+
+
+def cpu_baseline(batch, cam, sample, threads=None, reps=1, chain=False):
+    """The oracle (CPU restatement of the reference, kind 'port') on `sample` pairs of the same workload, all host threads.
+    chain: the step with the reference's refinement chain (orc_pair_batch_map) instead of host patches."""
     import oracle as O
     from dsdtm_b200 import synth as S
     threads = threads or (os.cpu_count() or 1)
@@ -526,22 +771,50 @@ def cpu_baseline(batch, cam, sample, threads=None, reps=1):
     n = sample
     ref_pyrs = np.empty((n, pyr_bytes), np.uint8)
     cur_imgs = np.empty((n, cam["height"], cam["width"]), np.uint8)
+    lo = batch.get("lo", 0)
     for i in range(n):
-        ref_pyrs[i] = ref_pyr[i % k]
-        cur_imgs[i] = batch["scenes"][i % k]["cur_img"]
+        ref_pyrs[i] = ref_pyr[(lo + i) % k]
+        cur_imgs[i] = batch["scenes"][(lo + i) % k]["cur_img"]
     feats = batch["feats"][:n].astype(O.REF_FEAT_DT)
-    args = (oc, LEVELS, ref_pyrs, cur_imgs, feats, batch["n_feats"][:n], batch["centers"][:n], batch["poses_in"][:n],
-            ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], batch["patches"][:n], batch["patch_px"][:n],
-            batch["patch_level"][:n], ALIGN2D_ITERS, threads)
-    O.pair_batch(*args)     # warm-up (page in, thread start)
+    if chain:
+        args = (oc, LEVELS, 15, ref_pyrs, cur_imgs, feats, batch["n_feats"][:n], batch["centers"][:n], batch["poses_ref"][:n], batch["poses_in"][:n],
+                ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], N_FEATS, LEVELS - 3, ALIGN2D_ITERS, threads)
+        fn = O.pair_batch_map
+        what = "pyramid(cur)+sparse align+reproject/affine/warp/align2d of %d map points" % N_FEATS
+    else:
+        args = (oc, LEVELS, ref_pyrs, cur_imgs, feats, batch["n_feats"][:n], batch["centers"][:n], batch["poses_in"][:n],
+                ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], batch["patches"][:n], batch["patch_px"][:n],
+                batch["patch_level"][:n], ALIGN2D_ITERS, threads)
+        fn = O.pair_batch
+        what = "pyramid(cur)+sparse align+align2d"
+    fn(*args)     # warm-up (page in, thread start)
     t0 = time.perf_counter()
     for _ in range(reps):
-        poses, nt, px, conv = O.pair_batch(*args)
+        res = fn(*args)
     dt = (time.perf_counter() - t0) / reps
-    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d pairs of the same workload (pyramid(cur)+sparse align+align2d), %d std::threads, %.2f s" % (n, threads, dt),
-            "us_per_pair_per_core": dt / n * threads * 1e6,
-            "_poses": poses}
+    out = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": "%d pairs of the same workload (%s), %d std::threads, %.2f s" % (n, what, threads, dt),
+           "us_per_pair_per_core": dt / n * threads * 1e6, "_poses": res[0]}
+    if chain:
+        out["_reproj"] = res[2]
+    return out
+
+
+def host_batch_with_oracle_detector(cam, scenes, n_pairs, seed0):
+    """The SAME batch the GPU arm stages (dsdtm_b200.workload: same scenes, same selection code, same per-pair start poses, centres and
+    patches), with the per-cell corner records coming from the oracle's detector instead of dsdtm_fast_cells -- the two are bit-equal
+    (tests/test_gpu_pyramid_fast.py, tests/test_ref_pin.py), so the reference arm needs no GPU to build the GPU arm's inputs."""
+    import oracle as O
+    from dsdtm_b200 import workload as W
+    per_scene = []
+    for sc in scenes:
+        packed, offs, ws, hs = O.pyramid(sc["ref_img"], LEVELS)
+        oc = O.detect_cells(packed, offs, ws, hs, 15, None, 5.0)
+        cells = np.zeros(len(oc), W.CORNER_DT)
+        for f in ("x", "y", "level", "score"):
+            cells[f] = oc[f]
+        per_scene.append(W.scene_inputs(sc, cam, cells, 15, N_FEATS, FEAT_STRIDE, N_FEATS))
+    return W.assemble_batch(scenes, per_scene, n_pairs, FEAT_STRIDE, N_FEATS, seed0)
 
 
 def run_reference(args):
@@ -554,29 +827,19 @@ def run_reference(args):
     cam = dict(S.EUROC if args.cam == "euroc" else S.KINECT)
     threads = os.cpu_count() or 1
     sample = args.cpu_sample
-    # the same workload builder needs GPU FAST for feature selection; the reference arm uses the oracle's detector instead
+    # the GPU arm's own batch (same scenes, features, start poses, centres, patches: host_batch_with_oracle_detector), bounded to the
+    # first `sample` pairs per step
     scenes = W.render_scenes(args.scenes, cam, seed0=W.BASE_SEED)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import helpers as H
-    feats = np.zeros((sample, FEAT_STRIDE), O.REF_FEAT_DT); nf = np.zeros(sample, np.int32)
-    centers = np.zeros((sample, 3)); poses = np.tile(S.IDENTITY, (sample, 1))
-    patches = np.zeros((sample, N_FEATS, 100), np.uint8); ppx = np.zeros((sample, N_FEATS, 2)); plv = np.full((sample, N_FEATS), -1, np.int32)
-    per = []
-    for sc in scenes:
-        corners, pyr = H.detect_oracle(sc["ref_img"], LEVELS, 15, N_FEATS)
-        F = H.ref_feats_from_corners(cam, corners, sc["ref_points"], n_pad=FEAT_STRIDE)
-        cur_pyr = O.pyramid(sc["cur_img"], LEVELS)
-        lv, pt, truth, st = H.make_patches(cur_pyr, N_FEATS, sc["seed"], max_level=0, pert=1.0)
-        per.append((F, len(corners), pyr[0], lv, pt, st))
+    batch = host_batch_with_oracle_detector(cam, scenes, args.pairs, W.BASE_SEED)
     k = len(scenes)
-    ref_pyrs = np.empty((sample, len(per[0][2])), np.uint8); cur_imgs = np.empty((sample, cam["height"], cam["width"]), np.uint8)
+    ref_pyr = [O.pyramid(sc["ref_img"], LEVELS)[0] for sc in scenes]
+    ref_pyrs = np.empty((sample, len(ref_pyr[0])), np.uint8); cur_imgs = np.empty((sample, cam["height"], cam["width"]), np.uint8)
     for i in range(sample):
-        F, n, rp, lv, pt, st = per[i % k]
-        feats[i] = F; nf[i] = n; ref_pyrs[i] = rp; cur_imgs[i] = scenes[i % k]["cur_img"]
-        patches[i] = pt; ppx[i] = st; plv[i] = lv
+        ref_pyrs[i] = ref_pyr[i % k]; cur_imgs[i] = scenes[i % k]["cur_img"]
     oc = O.make_cam(cam["width"], cam["height"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["f"])
-    a = (oc, LEVELS, ref_pyrs, cur_imgs, feats, nf, centers, poses, ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"],
-         patches, ppx, plv, ALIGN2D_ITERS, threads)
+    a = (oc, LEVELS, ref_pyrs, cur_imgs, batch["feats"][:sample].astype(O.REF_FEAT_DT), batch["n_feats"][:sample], batch["centers"][:sample],
+         batch["poses_in"][:sample], ALIGN_CFG["max_level"], ALIGN_CFG["min_level"], ALIGN_CFG["max_iters"], batch["patches"][:sample],
+         batch["patch_px"][:sample], batch["patch_level"][:sample], ALIGN2D_ITERS, threads)
     for _ in range(max(args.warmup, 1)):
         O.pair_batch(*a)
     t0 = time.perf_counter()
@@ -586,12 +849,8 @@ def run_reference(args):
     value = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC.replace("640x480", "%dx%d" % (cam["width"], cam["height"])), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
             "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic: %d ray-cast relief scenes tiled to a bounded sample of %d pairs per step" % (k, sample),
-            "config": {"workload": "%s: independent %dx%d %s frame pairs, %d features, 5-level pyramid(cur) + "
-                                   "Sprase_ImgAlign(4,0,30) + Align2D(%d patches, 10 it); CPU step = bounded sample of %d pairs"
-                                   % ("configs[4] sweep" if args.cam == "euroc" else "configs[0] shape batched", cam["width"], cam["height"], args.cam, N_FEATS, N_FEATS, sample),
-                       "camera": args.cam,
-                       "features": N_FEATS, "levels": LEVELS, "sparse_align": ALIGN_CFG, "align2d_iters": ALIGN2D_ITERS},
+            "data": "synthetic: %d ray-cast relief scenes tiled to %d pairs (the GPU arm's batch); each CPU step runs the first %d of them (bounded sample)" % (k, args.pairs, sample),
+            "config": make_config(args.cam, cam, args.pairs),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d pairs per step, %d std::threads (the reference needs OpenCV/Eigen/Sophus/Ceres: not buildable here; "
                                        "oracle/ restates it line by line)" % (sample, threads)},
@@ -609,6 +868,8 @@ def main():
     ap.add_argument("--scenes", type=int, default=16, help="distinct ray-cast scenes (tiled to --pairs)")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--total-pairs", type=int, default=4096, help="strong-scaling extra (configs[4]): EuRoC pairs partitioned over the ranks")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling extra")
     ap.add_argument("--cam", default="kinect", choices=["kinect", "euroc"],
                     help="kinect = 640x480 (the metric's configuration, default); euroc = 752x480, BASELINE configs[4]'s sweep geometry")
     args = ap.parse_args()

@@ -78,76 +78,101 @@ def feature_normals(cam, px):
     return n / np.linalg.norm(n, axis=1, keepdims=True)
 
 
-def build_batch(ctx, cam, n_pairs, n_scenes=8, n_feats=300, feat_stride=320, patches_per_pair=300, seed0=BASE_SEED, scenes=None,
-                first_slot=0):
-    """Uploads 2*n_pairs frames (ref slots first_slot + 2i, cur slots first_slot + 2i + 1) and returns the host-side batch dict."""
-    scenes = scenes or render_scenes(n_scenes, cam, seed0=seed0)
-    k = len(scenes)
+def scene_inputs(sc, cam, cells, cell_size, n_feats, feat_stride, patches_per_pair):
+    """Per-scene inputs of a pair from the per-cell corner records of its reference frame (`cells`: the FAST / Shi-Tomasi stage's
+    output, from the GPU -- dsdtm_fast_cells -- or from any implementation with the same contract): selected features with their
+    bearings and map points, and the host-patch variant of the refinement inputs."""
     w, h = cam["width"], cam["height"]
-    per_scene = []
-    for s, sc in enumerate(scenes):
-        ctx.upload(first_slot, sc["ref_img"])
-        cells = ctx.fast_cells(first_slot, 20, 5.0)
-        feats_c = select_features(cells, w, h, ctx.prm.cell_size, n_feats)
-        nf = len(feats_c)
-        F = np.zeros(feat_stride, REF_FEAT_DT)
-        px = np.stack([feats_c["x"], feats_c["y"]], 1).astype(np.float32)
-        F["px"][:nf] = px
-        F["level"][:nf] = feats_c["level"]
-        F["initial"][:nf] = 1
-        F["normal"][:nf] = feature_normals(cam, px)
-        F["point_w"][:nf] = sc["ref_points"][feats_c["y"], feats_c["x"]]
-        # feature-alignment inputs: 10x10 reference patches around the ref features (level 0, identity warp) and start
-        # positions = true reprojection into cur + U(+-1) px
-        P = S.pose_act(S.pose_mul(sc["T_c2r"], sc["T_ref"]), F["point_w"][:nf])
-        fxd, fyd, cxd, cyd = (float(np.float32(cam[q])) for q in ("fx", "fy", "cx", "cy"))
-        proj = np.stack([fxd * P[:, 0] / P[:, 2] + cxd, fyd * P[:, 1] / P[:, 2] + cyd], 1)
-        rng = np.random.default_rng(sc["seed"] + 777)
-        npatch = min(patches_per_pair, nf)
-        patches = np.zeros((patches_per_pair, 100), np.uint8)
-        ppx = np.zeros((patches_per_pair, 2))
-        plv = np.full(patches_per_pair, -1, np.int32)
-        for j in range(npatch):
-            x, y = int(feats_c["x"][j]), int(feats_c["y"][j])
-            if 6 <= x < w - 6 and 6 <= y < h - 6 and 8 <= proj[j, 0] < w - 8 and 8 <= proj[j, 1] < h - 8:
-                patches[j] = sc["ref_img"][y - 5:y + 5, x - 5:x + 5].reshape(-1)
-                ppx[j] = proj[j] + rng.uniform(-1, 1, 2)
-                plv[j] = 0
-        per_scene.append(dict(F=F, nf=nf, patches=patches, ppx=ppx, plv=plv, truth_px=proj))
-    B = n_pairs
+    feats_c = select_features(cells, w, h, cell_size, n_feats)
+    nf = len(feats_c)
+    F = np.zeros(feat_stride, REF_FEAT_DT)
+    px = np.stack([feats_c["x"], feats_c["y"]], 1).astype(np.float32)
+    F["px"][:nf] = px
+    F["level"][:nf] = feats_c["level"]
+    F["initial"][:nf] = 1
+    F["normal"][:nf] = feature_normals(cam, px)
+    F["point_w"][:nf] = sc["ref_points"][feats_c["y"], feats_c["x"]]
+    # feature-alignment inputs: 10x10 reference patches around the ref features (level 0, identity warp) and start
+    # positions = true reprojection into cur + U(+-1) px
+    P = S.pose_act(S.pose_mul(sc["T_c2r"], sc["T_ref"]), F["point_w"][:nf])
+    fxd, fyd, cxd, cyd = (float(np.float32(cam[q])) for q in ("fx", "fy", "cx", "cy"))
+    proj = np.stack([fxd * P[:, 0] / P[:, 2] + cxd, fyd * P[:, 1] / P[:, 2] + cyd], 1)
+    rng = np.random.default_rng(sc["seed"] + 777)
+    npatch = min(patches_per_pair, nf)
+    patches = np.zeros((patches_per_pair, 100), np.uint8)
+    ppx = np.zeros((patches_per_pair, 2))
+    plv = np.full(patches_per_pair, -1, np.int32)
+    for j in range(npatch):
+        x, y = int(feats_c["x"][j]), int(feats_c["y"][j])
+        if 6 <= x < w - 6 and 6 <= y < h - 6 and 8 <= proj[j, 0] < w - 8 and 8 <= proj[j, 1] < h - 8:
+            patches[j] = sc["ref_img"][y - 5:y + 5, x - 5:x + 5].reshape(-1)
+            ppx[j] = proj[j] + rng.uniform(-1, 1, 2)
+            plv[j] = 0
+    return dict(F=F, nf=nf, patches=patches, ppx=ppx, plv=plv, truth_px=proj)
+
+
+def assemble_batch(scenes, per_scene, n_pairs, feat_stride, patches_per_pair, seed0=BASE_SEED, first_slot=0, lo=0, hi=None):
+    """Host arrays of pairs [lo, hi) of a GLOBAL batch of n_pairs pairs (pair g uses scene g % k; start poses come from one seeded
+    stream over the global index, so a shard of the batch is the same data whichever rank builds it). Slots are local to the shard."""
+    k = len(scenes)
+    hi = n_pairs if hi is None else hi
+    B = hi - lo
     feats = np.zeros((B, feat_stride), REF_FEAT_DT)
     nfe = np.zeros(B, np.int32)
     centers = np.zeros((B, 3))
     poses = np.zeros((B, 7))
+    poses_ref = np.zeros((B, 7))
     patches = np.zeros((B, patches_per_pair, 100), np.uint8)
     ppx = np.zeros((B, patches_per_pair, 2))
     plv = np.zeros((B, patches_per_pair), np.int32)
-    ref_imgs = np.empty((min(B, k), h, w), np.uint8)
     rng = np.random.default_rng(seed0 + 4242)
+    start = np.concatenate([rng.uniform(-0.004, 0.004, (n_pairs, 3)), rng.uniform(-0.002, 0.002, (n_pairs, 3))], 1)
     for i in range(B):
-        s = i % k
+        g = lo + i
+        s = g % k
         ps = per_scene[s]
         feats[i] = ps["F"]; nfe[i] = ps["nf"]
         T_ref = scenes[s]["T_ref"]
         centers[i] = -(S.quat_to_R(T_ref[:4]).T @ T_ref[4:])
+        poses_ref[i] = T_ref
         # start pose: identity (cur.Set_Pose(last.Get_Pose()), ref: src/Tracking.cpp:201) perturbed per replica
-        poses[i] = S.IDENTITY if i < k else S.pose_from_xi(np.concatenate([rng.uniform(-0.004, 0.004, 3), rng.uniform(-0.002, 0.002, 3)]))
+        poses[i] = S.IDENTITY if g < k else S.pose_from_xi(start[g])
         patches[i] = ps["patches"]; ppx[i] = ps["ppx"]; plv[i] = ps["plv"]
-    # frames: upload in chunks of <= 64 images
     ref_slots = first_slot + 2 * np.arange(B, dtype=np.int32)
     cur_slots = ref_slots + 1
+    truth = np.stack([scenes[(lo + i) % k]["T_c2r"] for i in range(B)]) if B else np.zeros((0, 7))
+    return dict(n_pairs=B, n_scenes=k, ref_slots=ref_slots, cur_slots=cur_slots, feats=feats, n_feats=nfe, centers=centers,
+                poses_in=poses, poses_ref=poses_ref, patches=patches, patch_px=ppx, patch_level=plv, truth=truth, scenes=scenes,
+                per_scene=per_scene, feat_stride=feat_stride, patches_per_pair=patches_per_pair, lo=lo)
+
+
+def upload_frames(ctx, batch, first_slot=0):
+    """ref / cur frames of the shard into slots first_slot + 2i / + 2i + 1 (level 0 + pyramid), in chunks of 32 pairs"""
+    scenes = batch["scenes"]; k = len(scenes); B = batch["n_pairs"]; lo = batch["lo"]
+    h, w = scenes[0]["ref_img"].shape
     chunk = 32
     for i0 in range(0, B, chunk):
         n = min(chunk, B - i0)
         buf = np.empty((2 * n, h, w), np.uint8)
         for j in range(n):
-            s = (i0 + j) % k
+            s = (lo + i0 + j) % k
             buf[2 * j] = scenes[s]["ref_img"]; buf[2 * j + 1] = scenes[s]["cur_img"]
         ctx.upload_batch(first_slot + 2 * i0, buf)
-    truth = np.stack([scenes[i % k]["T_c2r"] for i in range(B)])
-    return dict(n_pairs=B, n_scenes=k, ref_slots=ref_slots, cur_slots=cur_slots, feats=feats, n_feats=nfe, centers=centers,
-                poses_in=poses, patches=patches, patch_px=ppx, patch_level=plv, truth=truth, scenes=scenes, per_scene=per_scene,
-                feat_stride=feat_stride, patches_per_pair=patches_per_pair)
+
+
+def build_batch(ctx, cam, n_pairs, n_scenes=8, n_feats=300, feat_stride=320, patches_per_pair=300, seed0=BASE_SEED, scenes=None,
+                first_slot=0, lo=0, hi=None):
+    """Uploads the frames of pairs [lo, hi) of a global batch of n_pairs pairs (default: all of it; ref slots first_slot + 2i, cur
+    slots first_slot + 2i + 1) and returns the host-side batch dict. Reference features come from the GPU FAST stage."""
+    scenes = scenes or render_scenes(n_scenes, cam, seed0=seed0)
+    per_scene = []
+    for sc in scenes:
+        ctx.upload(first_slot, sc["ref_img"])
+        cells = ctx.fast_cells(first_slot, 20, 5.0)
+        per_scene.append(scene_inputs(sc, cam, cells, ctx.prm.cell_size, n_feats, feat_stride, patches_per_pair))
+    batch = assemble_batch(scenes, per_scene, n_pairs, feat_stride, patches_per_pair, seed0, first_slot, lo, hi)
+    upload_frames(ctx, batch, first_slot)
+    return batch
 
 
 # ---------------------------------------------------------------- pose refinement after matching (SURVEY 8f-2)
