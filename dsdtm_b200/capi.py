@@ -77,7 +77,7 @@ SYMBOLS = [
     "dsdtm_pair_batch_e2e", "dsdtm_last_run_ms", "dsdtm_timer_start", "dsdtm_timer_stop", "dsdtm_set_option", "dsdtm_feature_align_batch",
     "dsdtm_local_map_align_batch", "dsdtm_depth_upload", "dsdtm_depth_convert_f32", "dsdtm_keyframe_lift",
     "dsdtm_frame_upload_pyramid_host", "dsdtm_frames_upload_clahe_pyramid", "dsdtm_track_frame",
-    "dsdtm_pose_optimize", "dsdtm_pose_optimize_batch", "dsdtm_map_table_upload", "dsdtm_close_keyframes", "dsdtm_probe_fp64", "dsdtm_batch_stage_map", "dsdtm_batch_fetch_map", "dsdtm_track_batch_e2e",
+    "dsdtm_pose_optimize", "dsdtm_pose_optimize_batch", "dsdtm_map_table_upload", "dsdtm_close_keyframes", "dsdtm_probe_fp64", "dsdtm_frame_upload_level", "dsdtm_batch_stage_map", "dsdtm_batch_fetch_map", "dsdtm_track_batch_e2e",
 ]
 
 
@@ -204,6 +204,11 @@ class Context:
         img = np.ascontiguousarray(img, np.uint8)
         assert img.shape == (self.height, self.width)
         self._ck(self.L.dsdtm_frame_upload_pyramid(self.hp, int(slot), _p(img), img.shape[1]))
+
+    def upload_level(self, slot, level, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        assert img.shape == (self.hs[level], self.ws[level])
+        self._ck(self.L.dsdtm_frame_upload_level(self.hp, int(slot), int(level), _p(img), img.shape[1]))
 
     def upload_with_levels(self, slot, img):
         """upload + pyramid + host copies of levels 1.. in one call -> list of level images (level 0 is img itself)"""

@@ -494,6 +494,18 @@ int dsdtm_frames_build_pyramid(dsdtm_ctx* c, int first_slot, int n)
     return 0;
 }
 
+int dsdtm_frame_upload_level(dsdtm_ctx* c, int slot, int level, const uint8_t* img, int stride)
+{
+    if (!c || !img || level < 0 || level >= c->geo.levels) return c ? fail(c, DSDTM_E_ARG, "dsdtm_frame_upload_level: bad level / null image") : DSDTM_E_ARG;
+    if (check_slot(c, slot)) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    if (stride < g.w[level]) return fail(c, DSDTM_E_ARG, "dsdtm_frame_upload_level: stride < level width");
+    DSDTM_CUDA(c, cudaMemcpy2DAsync(c->frames_d + (size_t)slot * g.frame_stride + g.off[level], (size_t)g.w[level], img, (size_t)stride,
+                                    (size_t)g.w[level], (size_t)g.h[level], cudaMemcpyHostToDevice, c->stream));
+    DSDTM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int dsdtm_frame_download_level(dsdtm_ctx* c, int slot, int level, uint8_t* out)
 {
     if (!c || !out || level < 0 || level >= c->geo.levels) return DSDTM_E_ARG;

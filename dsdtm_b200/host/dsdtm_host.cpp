@@ -239,6 +239,15 @@ std::shared_ptr<GpuSlot> GpuRuntime::Upload(const Mat8& img, uint8_t* levels_out
     return s;
 }
 
+std::shared_ptr<GpuSlot> GpuRuntime::UploadLevel(const Mat8& img, int level)
+{
+    auto s = std::make_shared<GpuSlot>(Mat8());                   // no host copy: the handle lives for one call and is never re-uploaded
+    s->slot = Acquire(s.get());
+    if (dsdtm_frame_upload_level(mCtx, s->slot, level, img.data, img.step) != 0)
+        throw std::runtime_error(std::string("dsdtm_frame_upload_level: ") + dsdtm_last_error(mCtx));
+    return s;
+}
+
 int GpuRuntime::Resident(const std::shared_ptr<GpuSlot>& s)
 {
     if (s->slot >= 0) { mStamp[s->slot] = ++mClock; return s->slot; }
@@ -872,6 +881,25 @@ bool Feature_Alignment::Align2DGaussNewton(const FramePtr cur, int level, uchar*
     uint8_t conv = 0;
     double p[2] = { px[0], px[1] };
     if (dsdtm_align2d_batch(rt.ctx(), rt.Resident(cur->mGpu), &level, patch10, p, 1, MaxIters, &conv) != 0)
+        throw std::runtime_error(std::string("dsdtm_align2d_batch: ") + dsdtm_last_error(rt.ctx()));
+    px = Vector2d(p[0], p[1]);
+    return conv != 0;
+}
+
+bool Feature_Alignment::Align2DGaussNewton(const Mat8& img, uchar* patch10, uchar*, int MaxIters, Vector2d& px)   // ref: include/Feature_alignment.h:85
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    int level = -1;
+    for (int l = 0; l < rt.levels() && level < 0; ++l) {
+        int w = 0, h = 0; size_t off = 0;
+        if (dsdtm_level_info(rt.ctx(), l, &w, &h, &off) == 0 && w == img.cols && h == img.rows) level = l;
+    }
+    if (level < 0 || img.empty())
+        throw std::invalid_argument("Feature_Alignment::Align2DGaussNewton(image, ...): the image must have the size of a pyramid level of the configured camera");
+    const std::shared_ptr<GpuSlot> slot = rt.UploadLevel(img, level);
+    uint8_t conv = 0;
+    double p[2] = { px[0], px[1] };
+    if (dsdtm_align2d_batch(rt.ctx(), slot->slot, &level, patch10, p, 1, MaxIters, &conv) != 0)
         throw std::runtime_error(std::string("dsdtm_align2d_batch: ") + dsdtm_last_error(rt.ctx()));
     px = Vector2d(p[0], p[1]);
     return conv != 0;

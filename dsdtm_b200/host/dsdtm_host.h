@@ -290,6 +290,10 @@ public:
     uchar mPatch[2 * mHalf_PatchSize * 2 * mHalf_PatchSize];
     uchar mPatch_WithBoarder[(2 * mHalf_PatchSize + 2) * (2 * mHalf_PatchSize + 2)];
     static bool Align2DGaussNewton(const FramePtr tCurFrame, int tLevel, uchar* tPatch_WithBoarder, uchar* tPatch, int MaxIters, Vector2d& tCurPx);
+    // the reference's own static signature (ref: include/Feature_alignment.h:85; Test/test_Feature_alignment.cpp:72 hands it an arbitrary
+    // image): tCurImg must have the size of one pyramid level of the configured camera (the device frame pool is geometry-fixed); it is
+    // uploaded into a scratch slot for the call. Throws std::invalid_argument for any other size.
+    static bool Align2DGaussNewton(const Mat8& tCurImg, uchar* tPatch_WithBoarder, uchar* tPatch, int MaxIters, Vector2d& tCurPx);
     int LastMatches() const { return mLastMatches; }
 private:
     struct Prepared;   // one candidate after the host-side map walk
@@ -360,6 +364,8 @@ public:
     // uploads + builds the pyramid, returns the residency handle; levels_out (optional) receives the host copies of levels 1..
     std::shared_ptr<GpuSlot> Upload(const Mat8& level0, uint8_t* levels_out = nullptr);
     int Resident(const std::shared_ptr<GpuSlot>& s);             // slot index, re-uploading from the host copy if it was evicted
+    // a slot holding ONE level image (no pyramid), for single calls on images that are not frames; released with the handle
+    std::shared_ptr<GpuSlot> UploadLevel(const Mat8& img, int level);
     int levels() const { return mLevels; }
     void Release(int slot);
     // epoch = one batched call that resolves several slots before using them: detects a slot being recycled in between

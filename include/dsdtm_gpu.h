@@ -129,6 +129,10 @@ int dsdtm_frames_upload_pyramid(dsdtm_ctx* ctx, int first_slot, int n, const uin
 /* device-resident variant: level 0 of the n slots is already in HBM (e.g. written by a previous upload); rebuild levels */
 int dsdtm_frames_build_pyramid(dsdtm_ctx* ctx, int first_slot, int n);
 /* parity helper: copy one level of a slot back (dense w*h bytes) */
+/* Raw upload of ONE level image (w_level x h_level) into a slot, no pyramid: for callers that hold an image that is not a level-0
+ * frame, e.g. the static Feature_Alignment::Align2DGaussNewton(const cv::Mat&, ...) (ref: include/Feature_alignment.h:85), which may
+ * be handed any level of any pyramid. The other levels of the slot are left as they are. */
+int dsdtm_frame_upload_level(dsdtm_ctx* ctx, int slot, int level, const uint8_t* img, int stride);
 int dsdtm_frame_download_level(dsdtm_ctx* ctx, int slot, int level, uint8_t* out);
 
 /* ---------------------------------------------------------------- (b) FAST + grid cells -------------------- */

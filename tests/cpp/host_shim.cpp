@@ -288,6 +288,21 @@ int hs_align2d_single(void* cur, int level, const uint8_t* patch10, int iters, d
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// the reference's static signature Align2DGaussNewton(const cv::Mat&, uchar*, uchar*, int, Vector2d&) on an arbitrary image
+// (ref: include/Feature_alignment.h:85, Test/test_Feature_alignment.cpp:72)
+int hs_align2d_image(const uint8_t* img, int w, int h, const uint8_t* patch10, const uint8_t* patch8, int iters, double* px)
+{
+    try {
+        uint8_t p10[100], p8[64];
+        std::memcpy(p10, patch10, 100); std::memcpy(p8, patch8, 64);
+        const Mat8 m(h, w, img, w);
+        Vector2d v(px[0], px[1]);
+        const bool ok = Feature_Alignment::Align2DGaussNewton(m, p10, p8, iters, v);
+        px[0] = v[0]; px[1] = v[1];
+        return ok ? 1 : 0;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // Feature_Alignment::WarpAffine + GetPatchNoBoarder for feature `idx` of a key frame (single-candidate forms, ref: :206-275)
 int hs_warp_affine_single(void* cam, void* kf, int idx, const double* A4, int search_level, uint8_t* patch10, uint8_t* patch8)
 {

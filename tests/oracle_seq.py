@@ -9,12 +9,12 @@ from dsdtm_b200 import synth as S
 LEVELS, CELL = 5, 15
 
 
-def _trajectory(n, seed=3):
+def _trajectory(n, seed=3, scale=1.0):
     rng = np.random.default_rng(seed)
     v = np.concatenate([rng.uniform(-0.012, 0.012, 3), np.deg2rad(rng.uniform(-0.3, 0.3, 3))])
     poses = [S.IDENTITY.copy()]
     for k in range(1, n):
-        step = v * (1.0 + 0.2 * np.sin(0.7 * k))
+        step = scale * v * (1.0 + 0.2 * np.sin(0.7 * k))
         poses.append(S.pose_mul(S.pose_from_xi(step), poses[-1]))
     return poses
 

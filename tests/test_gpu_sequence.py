@@ -126,12 +126,24 @@ def test_front_end_sequence_with_second_keyframe(built):
     detect on a frame that already carries matched features (occupancy grid, Frame::Set_Mask with Min_dist circles), new map
     points, a second keyframe, and afterwards a local map of two keyframes where MapPoint::Get_ClosetObs picks the
     observation by viewing angle."""
+    _run_keyframe_sequence(8, (4,), seed=9)
+
+
+@pytest.mark.slow
+def test_front_end_sequence_100_frames_five_keyframes(built):
+    """BASELINE configs[3] at a length where the map matters: 100 frames, a new key frame every 20 frames (five
+    besides the initial one), every frame compared with the oracle-side model: pose after Run, match list of SearchLocalPoints over
+    the growing local map (ids, levels, refined pixels), new corners at every key frame."""
+    _run_keyframe_sequence(100, (20, 40, 60, 80, 95), seed=9, step_scale=0.25)
+
+
+def _run_keyframe_sequence(n_frames, kf_frames, seed, step_scale=1.0):
     cam = dict(S.KINECT)
     oc = H.ocam(cam)
     scene = S.Scene(91)
-    n_frames, kf_at = 8, 4
-    poses = _trajectory(n_frames, seed=9)
-    cam_h = HL.configure(cam, max_fts=300, max_frames=24)
+    kf_at = kf_frames[0]
+    poses = _trajectory(n_frames, seed=seed, scale=step_scale)
+    cam_h = HL.configure(cam, max_fts=300, max_frames=max(24, 2 * len(kf_frames) + 8))
     cfg = (5, 0, 8)
     omap = OMap()
 
@@ -170,10 +182,10 @@ def test_front_end_sequence_with_second_keyframe(built):
             F[j]["normal"] = O.feature_normal(oc, px[j]); F[j]["point_w"] = omap.mp_point[mp]
         o_cur.feats = F
         o_cur.feat_mp = [w_[0] for w_ in want]
-        if k >= kf_at + 1:
+        if k >= kf_at + 1 and len(kf_frames) == 1:
             assert len({w_[3] for w_ in want}) == 2, "both keyframes should serve as closest observation somewhere"
 
-        if k == kf_at:
+        if k in kf_frames:
             # ---- CraeteKeyframe: Set_ExistingFeatures(cur features) + detect(cur, 5.0), then map points for the new features
             n_old = len(px)
             n_all = g_cur.detect(5.0, use_existing=True)

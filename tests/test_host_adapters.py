@@ -247,6 +247,41 @@ def test_single_candidate_warp_affine_and_patch_forms(built, scenario):
 
 
 @pytest.mark.gpu
+def test_align2d_static_signature_on_an_arbitrary_image(built, scenario):
+    """Feature_Alignment::Align2DGaussNewton(const Mat&, uchar*, uchar*, int, Vector2d&) -- the reference's own static signature
+    (ref: include/Feature_alignment.h:85) -- with the recipe of ref Test/test_Feature_alignment.cpp:56-81: reference patch interpolated
+    at px_true = (130.2, 120.3), start offset (+1.1, +0.8), 3 iterations; the image is NOT a Frame (here: level 0 and level 1 of the
+    scenario pyramid handed in as plain images). Against the oracle and the pinned reference value."""
+    sc = scenario
+    HL.configure(sc["cam"], max_fts=300)
+    packed, offs, ws, hs = sc["cur_pyr"]
+    px_true = np.array([130.2, 120.3])
+    for L in (0, 1):
+        img = np.ascontiguousarray(O.pyr_level(packed, offs, ws, hs, L))
+        # generateRefPatchNoWarpInterpolate (ref: Test/test_Feature_alignment.cpp:22-45): bilinear 10x10 around px_true, truncated to u8
+        u_r, v_r = int(np.floor(px_true[0])), int(np.floor(px_true[1]))
+        sx, sy = px_true[0] - u_r, px_true[1] - v_r
+        wTL, wTR, wBL, wBR = (1 - sx) * (1 - sy), sx * (1 - sy), (1 - sx) * sy, sx * sy
+        I = img.astype(np.float64)
+        p10 = np.zeros((10, 10), np.uint8)
+        for y in range(10):
+            for x in range(10):
+                yy, xx = v_r + y - 5, u_r + x - 5
+                p10[y, x] = np.uint8(wTL * I[yy, xx] + wTR * I[yy, xx + 1] + wBL * I[yy + 1, xx] + wBR * I[yy + 1, xx + 1])
+        p8 = O.patch_no_border(p10)
+        px = px_true + (1.1, 0.8)
+        got = px.copy()
+        rc = HL.lib().hs_align2d_image(HL._p(img), img.shape[1], img.shape[0], HL._p(np.ascontiguousarray(p10.reshape(-1))), HL._p(p8), 3, HL._p(got))
+        assert rc >= 0, HL.lib().hs_last_error()
+        want, conv, _ = O.align2d(img, p10, 3, px)
+        assert bool(rc) == conv and np.abs(got - want).max() <= 1e-3
+        assert np.linalg.norm(got - px_true) < 0.5                   # three iterations from 1.36 px away (the reference prints 0.015 px on its own, not shipped, image)
+    bad = np.zeros((100, 123), np.uint8)
+    assert HL.lib().hs_align2d_image(HL._p(bad), 123, 100, HL._p(np.zeros(100, np.uint8)), HL._p(np.zeros(64, np.uint8)), 3, HL._p(np.zeros(2))) == -1
+    assert b"pyramid level" in HL.lib().hs_last_error()
+
+
+@pytest.mark.gpu
 def test_optimizer_pose_optimization_after_search_local_points(built, scenario):
     """Tracking's next call after SearchLocalPoints (ref: src/Tracking.cpp:236): Optimizer::PoseOptimization through the adapter
     class against the oracle's restatement of ceres::Solve -- pose, stopping rule, residuals, and the reference's literal
