@@ -4,7 +4,8 @@ scale 5000), driven through the C++ adapter classes in Tracking's order (ref: sr
   WHOLE map on the device-resident table, the 10 nearest close key frames) + SearchLocalPoints -> Optimizer::PoseOptimization -> every KF_EVERY frames CraeteKeyframe (detect on the free cells,
   UndistortFeatures / depth lookup / UnProject on the device, new map points).
 Frames are ray-cast beforehand by a process pool (CPU work, not part of the loop). Reports the per-call wall clock, the matches,
-and the trajectory error against the ground truth."""
+and the trajectory error against the ground truth. Every CHECK_EVERY-th frame the pose Run returns is compared with the oracle's
+Sprase_ImgAlign::Run on the same two images, features, map points and start pose (1e-5 rad / 1e-5 m, tracked counts equal)."""
 import multiprocessing as mp
 import os
 import sys
@@ -18,6 +19,7 @@ from dsdtm_b200 import synth as S
 SCALE = 5000.0
 KF_EVERY = 20
 SCENE_SEED = 1000
+CHECK_EVERY = 50
 
 
 def ground_truth(n):
@@ -71,12 +73,34 @@ def main():
     T = {k: [] for k in ("frame", "run", "search", "opt", "keyframe")}
     tracked, matches, iters, err_sa, err_po, n_local, n_reproj = [], [], [], [], [], [], []
     lost = 0
+    checked = []
     for k in range(1, n):
         t0 = time.perf_counter()
         g_cur = HL.HFrame(cam_h, imgs[k], g_last.pose())
         t1 = time.perf_counter()
+        if k % CHECK_EVERY == 0:                                # snapshot Run's inputs for the oracle (outside the timed calls)
+            import oracle as O
+            pxl, lvl, inil = g_last.features()
+            idl = g_last.mp_ids()
+            Fo = np.zeros(len(pxl), O.REF_FEAT_DT)
+            oc = O.make_cam(cam["width"], cam["height"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["f"])
+            for j in range(len(pxl)):
+                Fo[j]["px"] = pxl[j]; Fo[j]["level"] = lvl[j]; Fo[j]["initial"] = inil[j]
+                Fo[j]["normal"] = O.feature_normal(oc, pxl[j])
+                if idl[j] >= 0:
+                    P = np.zeros(3); L.hs_mappoint_pose(int(idl[j]), HL._p(P)); Fo[j]["point_w"] = P
+            last_pose = g_last.pose()
+            t1 = time.perf_counter()
         nt, pose_sa, _ = HL.sparse_align_run(5, 0, 8, g_cur, g_last)
         t2 = time.perf_counter()
+        if k % CHECK_EVERY == 0:
+            rp, offs, ws, hs = O.pyramid(imgs[k - 1], 5)
+            cp = O.pyramid(imgs[k], 5)[0]
+            T0 = O.se3_mul(last_pose, O.se3_inv(last_pose))         # cur starts at the last pose (ref: src/Tracking.cpp:201)
+            po, no, _ = O.sparse_align(oc, rp, cp, offs, ws, hs, Fo, O.se3_inv(last_pose)[4:], T0, 5, 0, 8)
+            dd = S.pose_dist(O.se3_mul(po, last_pose), pose_sa)
+            assert no == nt and dd[0] < 1e-5 and dd[1] < 1e-5, ("oracle check failed at frame %d" % k, dd, no, nt)
+            checked.append(max(dd))
         m, local, nrep = HL.track_local_map(cam_h, g_cur)
         n_local.append(len(local)); n_reproj.append(nrep)
         t3 = time.perf_counter()
@@ -112,6 +136,7 @@ def main():
     print("%-46s: median %.1f us, p95 %.1f us  (%.0f frames/s)" % (("front end per frame",) + us(tot) + (1.0 / np.mean(tot),)))
     print("pose error vs ground truth after Run              : mean %.2e rad %.2e m, max %.2e rad %.2e m" % (*err_sa.mean(0), *err_sa.max(0)))
     print("pose error vs ground truth after PoseOptimization : mean %.2e rad %.2e m, max %.2e rad %.2e m" % (*err_po.mean(0), *err_po.max(0)))
+    print("oracle checks of Run (every %d frames): %d frames, max pose difference %.1e (tolerance 1e-5)" % (CHECK_EVERY, len(checked), max(checked) if checked else 0.0))
     q = [n // 4, n // 2, 3 * n // 4, n - 2]
     print("error along the sequence (rad, m) at frames %s: %s" % (q, ["%.1e/%.1e" % tuple(err_po[i]) for i in q]))
 

@@ -153,6 +153,7 @@ void hs_frame_feature_mp_ids(void* f, int* ids)
         for (size_t k = 0; k < g_mps.size(); ++k) if (g_mps[k] == fs[i]->Mpt) { ids[i] = (int)k; break; }
     }
 }
+void hs_mappoint_pose(int id, double* out3) { const Vector3d P = g_mps[id]->Get_Pose(); out3[0] = P[0]; out3[1] = P[1]; out3[2] = P[2]; }
 int hs_mappoint_found(int id) { return (id >= 0 && id < (int)g_mps.size()) ? g_mps[id]->Get_FoundNums() : -1; }
 
 int hs_sparse_align_run(int maxl, int minl, int iters, void* cur, void* ref, double* pose_out, dsdtm_iter_log* log, int cap, int* n_log)

@@ -50,6 +50,7 @@ def lib():
         L.hs_keyframe_new.argtypes = [C.c_void_p]
         L.hs_search_local_points.argtypes = [C.c_void_p] * 5
         L.hs_mappoint_found.argtypes = [C.c_int]
+        L.hs_mappoint_pose.argtypes = [C.c_int, C.c_void_p]
         L.hs_mappoint_set_bad.argtypes = [C.c_int, C.c_int]
         L.hs_search_local_points_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_frame_attach_points_from.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
