@@ -61,6 +61,7 @@ struct dsdtm_ctx {
     int pyr_kernel = 0;                          // 0 = auto (strip kernel where eligible), 1 = always the shared-memory tile kernel
     int sa_variant = 0;                          // 0 = shared-memory recompute kernel, 1 = L2 workspace kernel
     double* sa_ws_d = nullptr;                   // max_batch * 48 * nf doubles (variant 1)
+    int sa_ctas_per_sm[11] = {};                 // resident CTAs per SM of sparse_align_kernel<WPP> for this max_feats (occupancy API), index = WPP
     int sa_wpp_override = 0;                     // 0 = pick warps-per-pair from the batch size
 
     // device memory

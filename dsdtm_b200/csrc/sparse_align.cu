@@ -890,6 +890,14 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
 #ifdef DSDTM_SA_CARVEOUT
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, DSDTM_SA_CARVEOUT);
 #endif
+    if (e == cudaSuccess) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sparse_align_kernel<3>, 96, bytes) == cudaSuccess) c->sa_ctas_per_sm[3] = n;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sparse_align_kernel<4>, 128, bytes) == cudaSuccess) c->sa_ctas_per_sm[4] = n;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sparse_align_kernel<5>, 160, bytes) == cudaSuccess) c->sa_ctas_per_sm[5] = n;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sparse_align_kernel<10>, 320, bytes) == cudaSuccess) c->sa_ctas_per_sm[10] = n;
+        (void)cudaGetLastError();
+    }
     const int bw = smem_bytes_ws(nf);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
@@ -900,17 +908,27 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
     return e;
 }
 
-// warps per pair, measured on B200 (profiles/r1_sparse_align_v3.md, 2072 pairs, ms per launch): 1 -> 1.71, 2 -> 1.70,
-// 4 -> 1.22, 10 -> one pair per SM. Four warps per pair keeps the warps of a CTA on the same code (instruction-cache
-// locality: the kernel is ~120 KB of SASS) while three CTAs per SM overlap each other's serial solve; a lone pair gets
-// ten warps (one feature per lane) for latency.
+// Warps per pair. A CTA owns a pair, so the choice trades the latency of one pair (more warps: fewer rounds of the feature pass per
+// iteration) against the pairs resident per SM (registers: 168 per thread). Measured per-pair latencies at full residency on B200
+// (profiles/r2_sparse_align.md, 4096 pairs: time / waves): 3 warps (4 CTAs per SM) 195 us, 4 warps (3 per SM) 156 us, 5 warps (3 per
+// SM) 152 us, 10 warps (1 per SM) 88 us. The batch runs in ceil(n / resident CTAs) waves, so the pick is the width with the smallest
+// waves x latency: a lone pair gets ten warps, batches that fill the chip many times get three (highest throughput), and a batch of
+// 512 pairs on 148 SMs -- one eighth of BASELINE configs[4] -- gets three as well (ONE wave of 592 slots; the round-1 rule picked four
+// warps = 444 slots = two waves, 0.29 instead of 0.20 ms).
 int sparse_align_pick_wpp(const dsdtm_ctx* c, int n_pairs)
 {
     if (c->sa_wpp_override > 0) return c->sa_wpp_override;
-    // >= 4 pairs per SM: three warps per pair, four CTAs per SM (same 12 warps per SM, one more pair overlapping the others' serial
-    // tails): 1.524 vs 1.553 ms per 4096 pairs, 2.470 vs 2.499 ms per step (CUDA events, alternating runs)
-    if (n_pairs >= 4 * c->sm_count) return 3;
-    return (n_pairs >= c->sm_count) ? 4 : 10;
+    static const int widths[4] = { 3, 4, 5, 10 };
+    static const double latency_us[4] = { 195.0, 156.0, 152.0, 88.0 };
+    int best = 3;
+    double best_cost = 1e300;
+    for (int k = 0; k < 4; ++k) {
+        const int per_sm = c->sa_ctas_per_sm[widths[k]] > 0 ? c->sa_ctas_per_sm[widths[k]] : 1;
+        const long long slots = (long long)per_sm * c->sm_count;
+        const double cost = (double)((n_pairs + slots - 1) / slots) * latency_us[k];
+        if (cost < best_cost) { best_cost = cost; best = widths[k]; }
+    }
+    return best;
 }
 
 cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int max_level, int min_level, int max_iters,
