@@ -16,6 +16,7 @@
 // fp32 non-contracted with the reference's operation order => bit-exact 10x10 uchar patches (incl. the integer-division
 // quirk Q3: the sampling grid collapses to the reference pixel for search levels >= 1).
 #include "ctx.cuh"
+#include "cand_prep.cuh"
 
 namespace dsdtm {
 
@@ -30,6 +31,8 @@ struct A2dArgs {
     double* px;                 // n x 2 refined positions
     uint8_t* conv;              // n
     int n, max_iters, patch0;
+    const int* n_dev;           // optional: number of valid entries, known only on the device (entries past it are skipped)
+    dsdtm_store_cand* store_out;   // optional: fold (px * 2^level, level, converged) into the map-store records (ref: :154-156)
 };
 
 constexpr int A2D_WARPS = 8;          // 8 warps = 16 patches per CTA
@@ -61,7 +64,8 @@ __global__ void __launch_bounds__(A2D_WARPS * 32, DSDTM_A2D_MINB) align2d_kernel
 {
     __shared__ __align__(16) uint8_t s_patch[A2D_WARPS * 2][104];
     const int half = threadIdx.x >> 4, l16 = threadIdx.x & 15;
-    const int last = a.patch0 + a.n - 1;
+    const int n_eff = a.n_dev ? min(a.n, *a.n_dev) : a.n;
+    const int last = a.patch0 + n_eff - 1;
     const int iraw = a.patch0 + blockIdx.x * (A2D_WARPS * 2) + half;
     if (iraw - (half & 1) > last) return;                 // whole warp out of range (both halves)
     const bool exists = iraw <= last;
@@ -171,6 +175,13 @@ __global__ void __launch_bounds__(A2D_WARPS * 32, DSDTM_A2D_MINB) align2d_kernel
     if (exists && L >= 0 && l16 == 0) {
         a.px[2 * i] = (double)u; a.px[2 * i + 1] = (double)v;     // ref: :414
         a.conv[i] = converged ? 1 : 0;
+        if (a.store_out) {
+            const double sc = (double)(1 << L);                   // ref: :154 tPt = tCurPx * (1 << tBestLevel) (exact)
+            dsdtm_store_cand& o = a.store_out[i];
+            o.r.px[0] = __dmul_rn((double)u, sc); o.r.px[1] = __dmul_rn((double)v, sc);
+            o.r.level = L;
+            if (converged) o.r.flags |= DSDTM_LM_CONVERGED;
+        }
     }
 }
 
@@ -183,13 +194,14 @@ struct WaArgs {
     uint8_t* out;          // n x 100
     int n;
     int i0;
+    const int* n_dev;      // optional device-side count of valid entries
 };
 
 __global__ void __launch_bounds__(256) warp_affine_kernel(const WaArgs a)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = a.i0 + blockIdx.x * 8 + warp;
-    if (i >= a.i0 + a.n) return;
+    if (i >= a.i0 + (a.n_dev ? min(a.n, *a.n_dev) : a.n)) return;
     const int slot = a.meta[3 * i], rl = a.meta[3 * i + 1], sl = a.meta[3 * i + 2];
     if (slot < 0) return;                                           // candidate skipped by candidate_prep_kernel
     const double A00 = a.A[4 * i], A01 = a.A[4 * i + 1], A10 = a.A[4 * i + 2], A11 = a.A[4 * i + 3];
@@ -231,83 +243,12 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const WaArgs a)
 // candidate_prep_kernel: SolveAffineMatrix + GetBestSearchLevel (ref: src/Feature_alignment.cpp:160-204), one thread per
 // candidate, fp64 non-contracted in the reference's operation order (Eigen / Sophus semantics as in the oracle). Writes the
 // inputs of warp_affine_kernel and align2d_kernel directly, so the three stages chain on the device.
-struct CpArgs {
-    const dsdtm_candidate* cand; int n; int cur_slot; int max_search_level;
-    int i0;                      // first candidate of this launch (chunked batches)
-    const int* cur_slots; int ppp;   // batched chain: candidate i belongs to pair i / ppp, whose current frame is cur_slots[pair]
-    float fx, fy, cx, cy;
-    double* A; float* ref_px; int* meta; int* patch_level; int* patch_slot; double* px_in;
-};
-
-__device__ __forceinline__ void cp_qrot(const double* q, double v0, double v1, double v2, double& o0, double& o1, double& o2)
-{
-    double uv0 = __dsub_rn(__dmul_rn(q[2], v2), __dmul_rn(q[3], v1));
-    double uv1 = __dsub_rn(__dmul_rn(q[3], v0), __dmul_rn(q[1], v2));
-    double uv2 = __dsub_rn(__dmul_rn(q[1], v1), __dmul_rn(q[2], v0));
-    uv0 = __dadd_rn(uv0, uv0); uv1 = __dadd_rn(uv1, uv1); uv2 = __dadd_rn(uv2, uv2);
-    const double c0 = __dsub_rn(__dmul_rn(q[2], uv2), __dmul_rn(q[3], uv1));
-    const double c1 = __dsub_rn(__dmul_rn(q[3], uv0), __dmul_rn(q[1], uv2));
-    const double c2 = __dsub_rn(__dmul_rn(q[1], uv1), __dmul_rn(q[2], uv0));
-    o0 = __dadd_rn(__dadd_rn(v0, __dmul_rn(q[0], uv0)), c0);
-    o1 = __dadd_rn(__dadd_rn(v1, __dmul_rn(q[0], uv1)), c1);
-    o2 = __dadd_rn(__dadd_rn(v2, __dmul_rn(q[0], uv2)), c2);
-}
-
 __global__ void __launch_bounds__(128) candidate_prep_kernel(const CpArgs a)
 {
     const int i = a.i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.i0 + a.n) return;
     const dsdtm_candidate c = a.cand[i];
-    const int cur_slot = a.cur_slots ? a.cur_slots[i / a.ppp] : a.cur_slot;
-    if (c.ref_slot < 0) {                                           // rejected before FindMatchDirect's arithmetic (local_map.cu)
-        a.meta[3 * i] = -1; a.meta[3 * i + 1] = 0; a.meta[3 * i + 2] = 0;
-        a.patch_level[i] = -1; a.patch_slot[i] = cur_slot;
-        a.px_in[2 * i] = c.px[0]; a.px_in[2 * i + 1] = c.px[1];
-        return;
-    }
-    const double fx = (double)a.fx, fy = (double)a.fy, cx = (double)a.cx, cy = (double)a.cy;
-    const int HalfLarger = 5;                                       // mHalf_PatchSize + 1
-    // ref: :167  P = ||O_kf - P_w|| * mNormal
-    const double d0 = __dsub_rn(c.kf_center[0], c.ref_point_w[0]), d1 = __dsub_rn(c.kf_center[1], c.ref_point_w[1]), d2 = __dsub_rn(c.kf_center[2], c.ref_point_w[2]);
-    const double nrm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
-    const double P0 = __dmul_rn(nrm, c.ref_normal[0]), P1 = __dmul_rn(nrm, c.ref_normal[1]), P2 = __dmul_rn(nrm, c.ref_normal[2]);
-    // ref: :171-172 (float px + int, evaluated in float, then widened)
-    const float step = (float)(HalfLarger * (1 << c.ref_level));
-    const double pxU0 = (double)__fadd_rn(c.ref_px[0], step), pxU1 = (double)c.ref_px[1];
-    const double pxV0 = (double)c.ref_px[0], pxV1 = (double)__fadd_rn(c.ref_px[1], step);
-    // ref: :174-179  Pixel2Camera(Vector2d, 1.0f) -> normalize -> rescale to depth P.z
-    double U0 = __ddiv_rn(__dmul_rn(1.0, __dsub_rn(pxU0, cx)), fx), U1 = __ddiv_rn(__dmul_rn(1.0, __dsub_rn(pxU1, cy)), fy), U2 = 1.0;
-    double V0 = __ddiv_rn(__dmul_rn(1.0, __dsub_rn(pxV0, cx)), fx), V1 = __ddiv_rn(__dmul_rn(1.0, __dsub_rn(pxV1, cy)), fy), V2 = 1.0;
-    double n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(U0, U0), __dmul_rn(U1, U1)), __dmul_rn(U2, U2)));
-    U0 = __ddiv_rn(U0, n); U1 = __ddiv_rn(U1, n); U2 = __ddiv_rn(U2, n);
-    n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(V0, V0), __dmul_rn(V1, V1)), __dmul_rn(V2, V2)));
-    V0 = __ddiv_rn(V0, n); V1 = __ddiv_rn(V1, n); V2 = __ddiv_rn(V2, n);
-    double sc = __ddiv_rn(P2, U2); U0 = __dmul_rn(U0, sc); U1 = __dmul_rn(U1, sc); U2 = __dmul_rn(U2, sc);
-    sc = __ddiv_rn(P2, V2);        V0 = __dmul_rn(V0, sc); V1 = __dmul_rn(V1, sc); V2 = __dmul_rn(V2, sc);
-    // ref: :181-184  project the three points with T = T_cur * T_kf^-1 (Camera2Pixel: (fx*X)/Z + cx)
-    double q0, q1, q2;
-    cp_qrot(c.pose_c2r, P0, P1, P2, q0, q1, q2);
-    q0 = __dadd_rn(q0, c.pose_c2r[4]); q1 = __dadd_rn(q1, c.pose_c2r[5]); q2 = __dadd_rn(q2, c.pose_c2r[6]);
-    const double c0 = __dadd_rn(__ddiv_rn(__dmul_rn(fx, q0), q2), cx), c1 = __dadd_rn(__ddiv_rn(__dmul_rn(fy, q1), q2), cy);
-    cp_qrot(c.pose_c2r, U0, U1, U2, q0, q1, q2);
-    q0 = __dadd_rn(q0, c.pose_c2r[4]); q1 = __dadd_rn(q1, c.pose_c2r[5]); q2 = __dadd_rn(q2, c.pose_c2r[6]);
-    const double cu0 = __dadd_rn(__ddiv_rn(__dmul_rn(fx, q0), q2), cx), cu1 = __dadd_rn(__ddiv_rn(__dmul_rn(fy, q1), q2), cy);
-    cp_qrot(c.pose_c2r, V0, V1, V2, q0, q1, q2);
-    q0 = __dadd_rn(q0, c.pose_c2r[4]); q1 = __dadd_rn(q1, c.pose_c2r[5]); q2 = __dadd_rn(q2, c.pose_c2r[6]);
-    const double cv0 = __dadd_rn(__ddiv_rn(__dmul_rn(fx, q0), q2), cx), cv1 = __dadd_rn(__ddiv_rn(__dmul_rn(fy, q1), q2), cy);
-    // ref: :186-187
-    const double A00 = __ddiv_rn(__dsub_rn(cu0, c0), (double)HalfLarger), A10 = __ddiv_rn(__dsub_rn(cu1, c1), (double)HalfLarger);
-    const double A01 = __ddiv_rn(__dsub_rn(cv0, c0), (double)HalfLarger), A11 = __ddiv_rn(__dsub_rn(cv1, c1), (double)HalfLarger);
-    // ref: :192-204 GetBestSearchLevel
-    int L = 0;
-    double D = __dsub_rn(__dmul_rn(A00, A11), __dmul_rn(A10, A01));
-    while (D > 3.0 && L < a.max_search_level) { L++; D = __dmul_rn(D, 0.25); }
-    a.A[4 * i] = A00; a.A[4 * i + 1] = A01; a.A[4 * i + 2] = A10; a.A[4 * i + 3] = A11;
-    a.ref_px[2 * i] = c.ref_px[0]; a.ref_px[2 * i + 1] = c.ref_px[1];
-    a.meta[3 * i] = c.ref_slot; a.meta[3 * i + 1] = c.ref_level; a.meta[3 * i + 2] = L;
-    a.patch_level[i] = L; a.patch_slot[i] = cur_slot;
-    const double inv = 1.0 / (double)(1 << L);                      // ref: :150 tPt / (1 << level): exact power of two
-    a.px_in[2 * i] = __dmul_rn(c.px[0], inv); a.px_in[2 * i + 1] = __dmul_rn(c.px[1], inv);
+    candidate_prep_one(a, i, c, a.cur_slots ? a.cur_slots[i / a.ppp] : a.cur_slot);
 }
 
 }  // namespace
@@ -325,9 +266,10 @@ cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_sea
     return cudaGetLastError();
 }
 
-cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0)
+cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0, const int* n_dev, dsdtm_store_cand* store_out)
 {
     A2dArgs a;
+    a.n_dev = n_dev; a.store_out = store_out;
     a.frames = c->frames_d; a.frame_stride = c->geo.frame_stride; a.geo = c->geo;
     a.patch_slot = c->patch_slot_d; a.patch_level = c->patch_level_d; a.patch10 = c->patches_d;
     a.px_in = c->patch_px_in_d; a.px = c->patch_px_d; a.conv = c->patch_conv_d; a.n = n_patches; a.max_iters = max_iters; a.patch0 = patch0;
@@ -336,10 +278,10 @@ cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStrea
     return cudaGetLastError();
 }
 
-cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s, int i0)
+cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s, int i0, const int* n_dev)
 {
     WaArgs a;
-    a.i0 = i0;
+    a.i0 = i0; a.n_dev = n_dev;
     a.frames = c->frames_d; a.frame_stride = c->geo.frame_stride; a.geo = c->geo;
     a.A = c->wa_A_d; a.ref_px = c->wa_px_d; a.meta = c->wa_meta_d; a.out = out_d; a.n = n;
     warp_affine_kernel<<<(n + 7) / 8, 256, 0, s>>>(a);

@@ -309,7 +309,8 @@ void dsdtm_destroy(dsdtm_ctx* c)
                      c->lm_kfs_d, c->lm_obs_d, c->lm_pts_d, c->lm_pose_d, c->lm_reproj_d, c->poses_ref_d, c->pair_reproj_d,
                      c->depth_d, c->depth_f32_d, c->lift_px_d, c->lift_initial_d, c->lift_out_d, c->clahe_src_d, c->clahe_lut_d,
                      c->po_obs_d, c->po_res_d, c->po_nobs_d, c->po_pose_in_d, c->po_pose_out_d, c->po_sum_d,
-                     c->mt_kfs_d, c->mt_pts_d, c->mt_vis_d, c->mt_dist_d };
+                     c->mt_kfs_d, c->mt_pts_d, c->mt_vis_d, c->mt_dist_d,
+                     c->st_kfs_d, c->st_feats_d, c->st_pts_d, c->st_claim_d, c->st_vis_d, c->st_dist_d, c->st_sel_d, c->st_out_d };
     for (void* p : bufs) if (p) cudaFree(p);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->stage_pin) cudaFreeHost(c->stage_pin);
@@ -1083,6 +1084,266 @@ int dsdtm_close_keyframes(dsdtm_ctx* c, const double pose_cur_c2w[7], int n_kfs,
     const int n = std::min<int>((int)order.size(), max_local);
     for (int i = 0; i < n; ++i) local[i] = order[i];
     *n_local = n;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device-resident map store
+int dsdtm_store_clear(dsdtm_ctx* c)
+{
+    if (!c) return DSDTM_E_ARG;
+    c->st_kfs_n = c->st_feats_n = c->st_pts_n = 0;
+    c->st_max_feats = 0;
+    return 0;
+}
+
+int dsdtm_store_set_points(dsdtm_ctx* c, int first, int n, const double* point_w, const int32_t* bad)
+{
+    if (!c) return DSDTM_E_ARG;
+    if (first < 0 || n < 0 || (n && !point_w)) return fail(c, DSDTM_E_ARG, "dsdtm_store_set_points: bad range / null positions");
+    if ((size_t)first > c->st_pts_n) return fail(c, DSDTM_E_ARG, "dsdtm_store_set_points: range starts past the end (points are appended or rewritten)");
+    if (n == 0) return 0;
+    const size_t end = (size_t)first + n, old_n = c->st_pts_n;
+    const size_t old_claim_cap = c->st_claim_cap;
+    if (grow_keep(c, &c->st_pts_d, &c->st_pts_cap, end, old_n) || grow_keep(c, &c->st_claim_d, &c->st_claim_cap, end, old_n)) return DSDTM_E_NOMEM;
+    cudaStream_t s = c->stream;
+    if (c->st_claim_cap != old_claim_cap)     // fresh part of the claim array: "never claimed"
+        DSDTM_CUDA(c, cudaMemsetAsync(c->st_claim_d + old_n, 0xFF, (c->st_claim_cap - old_n) * sizeof(unsigned long long), s));
+    std::vector<dsdtm_store_point> rows((size_t)n);
+    std::vector<int32_t> last((size_t)n, -1);
+    const size_t n_old = end > old_n ? (old_n > (size_t)first ? old_n - first : 0) : (size_t)n;   // rows that already exist keep their chains
+    if (n_old) {
+        std::vector<dsdtm_store_point> cur(n_old);
+        DSDTM_CUDA(c, cudaMemcpyAsync(cur.data(), c->st_pts_d + first, n_old * sizeof(dsdtm_store_point), cudaMemcpyDeviceToHost, s));
+        DSDTM_CUDA(c, cudaStreamSynchronize(s));
+        for (size_t i = 0; i < n_old; ++i) last[i] = cur[i].last_obs;
+    }
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) rows[(size_t)i].point_w[k] = point_w[3 * (size_t)i + k];
+        rows[(size_t)i].bad = bad ? bad[i] : 0;
+        rows[(size_t)i].last_obs = last[(size_t)i];
+    }
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->st_pts_d + first, rows.data(), (size_t)n * sizeof(dsdtm_store_point), cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    c->st_pts_n = std::max(old_n, end);
+    return 0;
+}
+
+namespace {
+__global__ void store_update_points_kernel(dsdtm_store_point* pts, const int32_t* ids, int n, const double* pw, const int32_t* bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dsdtm_store_point& p = pts[ids[i]];
+    if (pw) { p.point_w[0] = pw[3 * i]; p.point_w[1] = pw[3 * i + 1]; p.point_w[2] = pw[3 * i + 2]; }
+    if (bad) p.bad = bad[i];
+}
+}  // namespace
+
+int dsdtm_store_update_points(dsdtm_ctx* c, const int32_t* ids, int n, const double* point_w, const int32_t* bad)
+{
+    if (!c) return DSDTM_E_ARG;
+    if (n < 0 || (n && !ids)) return fail(c, DSDTM_E_ARG, "dsdtm_store_update_points: null ids");
+    if (n == 0 || (!point_w && !bad)) return 0;
+    for (int i = 0; i < n; ++i) if (ids[i] < 0 || (size_t)ids[i] >= c->st_pts_n) return fail(c, DSDTM_E_ARG, "dsdtm_store_update_points: id outside the point table");
+    const int chunk = 16384;                                     // 16384 x 32 B + padding fits the 1 MB staging mirror
+    cudaStream_t s = c->stream;
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        const int m = std::min(chunk, n - i0);
+        size_t off = 0;
+        auto up = [&](const void* src, size_t nb) -> void* {
+            std::memcpy(c->stage_pin + off, src, nb);
+            void* dst = c->stage_dev + off;
+            cudaMemcpyAsync(dst, c->stage_pin + off, nb, cudaMemcpyHostToDevice, s);
+            off += (nb + 15) & ~(size_t)15;
+            return dst;
+        };
+        const double* pw_d = point_w ? static_cast<const double*>(up(point_w + 3 * (size_t)i0, (size_t)m * 3 * sizeof(double))) : nullptr;
+        const int32_t* ids_d = static_cast<const int32_t*>(up(ids + i0, (size_t)m * sizeof(int32_t)));
+        const int32_t* bad_d = bad ? static_cast<const int32_t*>(up(bad + i0, (size_t)m * sizeof(int32_t))) : nullptr;
+        store_update_points_kernel<<<(m + 127) / 128, 128, 0, s>>>(c->st_pts_d, ids_d, m, pw_d, bad_d);
+        c->launches++;
+        DSDTM_CUDA(c, cudaGetLastError());
+        DSDTM_CUDA(c, cudaStreamSynchronize(s));                 // the staging arena is reused by the next chunk / call
+    }
+    return 0;
+}
+
+int dsdtm_store_append_keyframe(dsdtm_ctx* c, const dsdtm_store_kf* kf, const dsdtm_store_feat* feats, int n_feats, int32_t* row)
+{
+    if (!c || !kf) return DSDTM_E_ARG;
+    if (n_feats < 0 || (n_feats && !feats) || n_feats > 65535) return fail(c, DSDTM_E_ARG, "dsdtm_store_append_keyframe: bad feature count");
+    if (check_slot(c, kf->slot)) return DSDTM_E_ARG;
+    for (int j = 0; j < n_feats; ++j)
+        if (feats[j].mp >= (int)c->st_pts_n || feats[j].level < 0 || feats[j].level >= c->geo.levels)
+            return fail(c, DSDTM_E_ARG, "dsdtm_store_append_keyframe: feature names a map point outside the point table (append the points first) or a bad level");
+    const size_t r = c->st_kfs_n, f0 = c->st_feats_n;
+    if (grow_keep(c, &c->st_kfs_d, &c->st_kfs_cap, r + 1, r) || grow_keep(c, &c->st_feats_d, &c->st_feats_cap, f0 + n_feats, f0)) return DSDTM_E_NOMEM;
+    if (grow(c, &c->st_vis_d, &c->st_vis_cap, r + 1) || grow(c, &c->st_dist_d, &c->st_dist_cap, r + 1)) return DSDTM_E_NOMEM;
+    if (!c->st_sel_d && dalloc(c, &c->st_sel_d, 32)) return DSDTM_E_NOMEM;
+    dsdtm_store_kf k = *kf;
+    k.feat_begin = (int32_t)f0; k.feat_count = n_feats;
+    std::vector<dsdtm_store_feat> fs(feats, feats + n_feats);
+    for (auto& f : fs) { f.is_obs = (f.mp >= 0 && f.is_obs) ? (int32_t)r + 1 : 0; f.next_obs = -1; }   // the observing key frame's row + 1
+    cudaStream_t s = c->stream;
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->st_kfs_d + r, &k, sizeof k, cudaMemcpyHostToDevice, s));
+    if (n_feats) DSDTM_CUDA(c, cudaMemcpyAsync(c->st_feats_d + f0, fs.data(), (size_t)n_feats * sizeof(dsdtm_store_feat), cudaMemcpyHostToDevice, s));
+    c->st_kfs_n = r + 1; c->st_feats_n = f0 + n_feats;
+    c->st_max_feats = std::max(c->st_max_feats, n_feats);
+    DSDTM_CUDA(c, launch_store_link(c, (int)f0, n_feats, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    if (row) *row = (int32_t)r;
+    return 0;
+}
+
+int dsdtm_store_set_keyframe(dsdtm_ctx* c, int row, int slot, const double pose_c2w[7], const double center[3])
+{
+    if (!c || !pose_c2w || !center) return DSDTM_E_ARG;
+    if (row < 0 || (size_t)row >= c->st_kfs_n) return fail(c, DSDTM_E_ARG, "dsdtm_store_set_keyframe: row outside the table");
+    if (check_slot(c, slot)) return DSDTM_E_ARG;
+    cudaStream_t s = c->stream;
+    dsdtm_store_kf k;
+    DSDTM_CUDA(c, cudaMemcpyAsync(&k, c->st_kfs_d + row, sizeof k, cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    k.slot = slot;
+    for (int i = 0; i < 7; ++i) k.pose_c2w[i] = pose_c2w[i];
+    for (int i = 0; i < 3; ++i) k.center[i] = center[i];
+    DSDTM_CUDA(c, cudaMemcpyAsync(c->st_kfs_d + row, &k, sizeof k, cudaMemcpyHostToDevice, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dsdtm_store_track(dsdtm_ctx* c, int cur_slot, const double pose_cur_c2w[7], const double cur_center[3], int max_local,
+                      int max_search_level, int align_iters, int32_t* local_rows, int32_t* n_local, dsdtm_store_cand* out, int cap,
+                      int32_t* n_out)
+{
+    if (!c || !pose_cur_c2w || !cur_center || !local_rows || !n_local || !n_out || (cap && !out)) return DSDTM_E_ARG;
+    if (check_slot(c, cur_slot)) return DSDTM_E_ARG;
+    if (max_local < 1 || max_local > 16) return fail(c, DSDTM_E_ARG, "dsdtm_store_track: max_local must be 1..16");
+    if (max_search_level < 0 || max_search_level >= c->geo.levels || align_iters < 0) return fail(c, DSDTM_E_ARG, "dsdtm_store_track: bad max_search_level / align_iters");
+    const size_t room = (size_t)c->prm.max_batch * std::max(c->prm.max_patches, 1);
+    if (cap < 0 || (size_t)cap > room) return fail(c, DSDTM_E_ARG, "dsdtm_store_track: cap exceeds max_batch * max_patches");
+    *n_local = 0; *n_out = 0;
+    if (c->st_kfs_n == 0 || cap == 0) return 0;
+    if (grow(c, &c->st_out_d, &c->st_out_cap, (size_t)cap)) return DSDTM_E_NOMEM;
+    const size_t out_bytes = (size_t)cap * sizeof(dsdtm_store_cand);
+    if (ensure_pinned(c, out_bytes + 32 * sizeof(int))) return DSDTM_E_NOMEM;
+    int* sel_h = reinterpret_cast<int*>(c->pinned);
+    dsdtm_store_cand* out_h = reinterpret_cast<dsdtm_store_cand*>(c->pinned + 32 * sizeof(int));
+    cudaStream_t s = c->stream;
+    ++c->st_epoch;
+    StoreTrackArgs a;
+    a.cur_slot = cur_slot; a.n_kfs = (int)c->st_kfs_n; a.max_local = max_local; a.cap = cap;
+    for (int k = 0; k < 7; ++k) a.pose_cur[k] = pose_cur_c2w[k];
+    for (int k = 0; k < 3; ++k) a.cur_center[k] = cur_center[k];
+    a.max_search_level = max_search_level;
+    stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+    DSDTM_CUDA(c, launch_store_track(c, a, s));
+    stage_end(c, 2);
+    // the record count is only known on the device: warp / Align2D take it from there and skip what lies beyond
+    stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
+    DSDTM_CUDA(c, launch_warp_affine(c, cap, c->patches_d, s, 0, store_count_dev(c)));
+    stage_end(c, 1);
+    stage_begin(c, DSDTM_STAGE_ALIGN2D);
+    DSDTM_CUDA(c, launch_align2d(c, cap, align_iters, s, 0, store_count_dev(c), c->st_out_d));
+    stage_end(c, 1);
+    DSDTM_CUDA(c, cudaMemcpyAsync(sel_h, c->st_sel_d, 18 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    // typical frames have ~1 k candidates: the first copy takes that many, a second one follows only for a fuller frame
+    const int first = std::min(cap, 1280);
+    DSDTM_CUDA(c, cudaMemcpyAsync(out_h, c->st_out_d, (size_t)first * sizeof(dsdtm_store_cand), cudaMemcpyDeviceToHost, s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    const int n = sel_h[17], got = std::min(n, cap);
+    if (got > first) {
+        DSDTM_CUDA(c, cudaMemcpyAsync(out_h + first, c->st_out_d + first, (size_t)(got - first) * sizeof(dsdtm_store_cand), cudaMemcpyDeviceToHost, s));
+        DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    }
+    *n_local = sel_h[0];
+    for (int i = 0; i < sel_h[0]; ++i) local_rows[i] = sel_h[1 + i];
+    std::memcpy(out, out_h, (size_t)got * sizeof(dsdtm_store_cand));
+    *n_out = n;
+    if (n > cap) return fail(c, DSDTM_E_ARG, "dsdtm_store_track: more candidates than cap (records truncated)");
+    return 0;
+}
+
+// Sprase_ImgAlign::Run and Tracking::UpdateLocalMap (+ the arithmetic of SearchLocalPoints) as ONE submission: the pose found by the
+// sparse alignment is composed with the reference pose on the device and handed to the map-store kernels through device memory,
+// so the frame costs one synchronisation instead of two (ref: src/Tracking.cpp:199-224,257-313).
+int dsdtm_track_frame_store(dsdtm_ctx* c, const dsdtm_track_store_in* in, dsdtm_track_out* out, int32_t* local_rows, int32_t* n_local,
+                            dsdtm_store_cand* cands, int cap, int32_t* n_out)
+{
+    if (!c || !in || !out || !in->feats || !local_rows || !n_local || !n_out || (cap && !cands)) return DSDTM_E_ARG;
+    const int nf = in->n_feats;
+    if (nf < 1 || nf > c->prm.max_feats) return fail(c, DSDTM_E_ARG, "n_feats out of range (max_feats)");
+    if (check_pairs(c, 1, &in->ref_slot, &in->cur_slot, nf, &nf, in->max_level, in->min_level, in->max_iters)) return DSDTM_E_ARG;
+    if (in->max_local < 1 || in->max_local > 16) return fail(c, DSDTM_E_ARG, "max_local must be 1..16");
+    if (in->max_search_level < 0 || in->max_search_level >= c->geo.levels || in->align_iters < 0) return fail(c, DSDTM_E_ARG, "bad max_search_level / align_iters");
+    const size_t room = (size_t)c->prm.max_batch * std::max(c->prm.max_patches, 1);
+    if (cap < 0 || (size_t)cap > room) return fail(c, DSDTM_E_ARG, "cap exceeds max_batch * max_patches");
+    *n_local = 0; *n_out = 0;
+    const bool with_map = c->st_kfs_n > 0 && cap > 0;
+    if (with_map && grow(c, &c->st_out_d, &c->st_out_cap, (size_t)cap)) return DSDTM_E_NOMEM;
+    if (ensure_pinned(c, (size_t)std::max(cap, 1) * sizeof(dsdtm_store_cand) + 32 * sizeof(int))) return DSDTM_E_NOMEM;
+    Arena ar(c, 3 * sizeof(int) + 10 * sizeof(double) + (size_t)nf * sizeof(dsdtm_ref_feat), (7 + 10) * sizeof(double) + 2 * sizeof(int), 6, 4);
+    if (!ar.active) return fail(c, DSDTM_E_ARG, "dsdtm_track_frame_store: inputs exceed the 1 MB staging arena");
+    c->batch.staged = false;
+    cudaStream_t s = c->stream;
+    PtrSwap<int> p0(c->ref_slots_d, ar.in(&in->ref_slot, 1)), p1(c->cur_slots_d, ar.in(&in->cur_slot, 1)), p2(c->n_feats_d, ar.in(&nf, 1));
+    PtrSwap<double> p3(c->centers_d, ar.in(in->ref_center, 3)), p4(c->poses_in_d, ar.in(in->pose_c2r_in, 7));
+    PtrSwap<dsdtm_ref_feat> p5(c->feats_d, ar.in(in->feats, (size_t)nf));
+    double* pose_c2r_d = ar.out(out->pose_c2r, 7);
+    double* pose10_d = ar.out((double*)nullptr, 10);
+    PtrSwap<double> q0(c->poses_out_d, pose_c2r_d);
+    PtrSwap<int> q1(c->n_tracked_d, ar.out(&out->n_tracked, 1)), q2(c->n_log_d, ar.out((int*)nullptr, 1));
+    DSDTM_CUDA(c, ar.upload(s));
+    stage_begin(c, DSDTM_STAGE_SPARSE_ALIGN);
+    DSDTM_CUDA(c, launch_sparse_align(c, 1, nf, in->max_level, in->min_level, in->max_iters, false, s));
+    stage_end(c, 1);
+    int* sel_h = reinterpret_cast<int*>(c->pinned);
+    dsdtm_store_cand* out_h = reinterpret_cast<dsdtm_store_cand*>(c->pinned + 32 * sizeof(int));
+    const int first = std::min(cap, 1280);
+    if (!with_map) {
+        stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+        DSDTM_CUDA(c, launch_compose_pose(c, pose_c2r_d, in->pose_ref_c2w, pose10_d, s));
+        stage_end(c, 1);
+    } else {
+        ++c->st_epoch;
+        StoreTrackArgs a;
+        a.cur_slot = in->cur_slot; a.n_kfs = (int)c->st_kfs_n; a.max_local = in->max_local; a.cap = cap;
+        for (int k = 0; k < 7; ++k) a.pose_cur[k] = 0.0;
+        for (int k = 0; k < 3; ++k) a.cur_center[k] = 0.0;
+        a.t_c2r_dev = pose_c2r_d; a.pose10_out = pose10_d;
+        for (int k = 0; k < 7; ++k) a.pose_ref[k] = in->pose_ref_c2w[k];
+        a.max_search_level = in->max_search_level;
+        stage_begin(c, DSDTM_STAGE_LOCAL_MAP);
+        DSDTM_CUDA(c, launch_store_track(c, a, s));
+        stage_end(c, 2);
+        stage_begin(c, DSDTM_STAGE_WARP_AFFINE);
+        DSDTM_CUDA(c, launch_warp_affine(c, cap, c->patches_d, s, 0, store_count_dev(c)));
+        stage_end(c, 1);
+        stage_begin(c, DSDTM_STAGE_ALIGN2D);
+        DSDTM_CUDA(c, launch_align2d(c, cap, in->align_iters, s, 0, store_count_dev(c), c->st_out_d));
+        stage_end(c, 1);
+        DSDTM_CUDA(c, cudaMemcpyAsync(sel_h, c->st_sel_d, 18 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        DSDTM_CUDA(c, cudaMemcpyAsync(out_h, c->st_out_d, (size_t)first * sizeof(dsdtm_store_cand), cudaMemcpyDeviceToHost, s));
+    }
+    DSDTM_CUDA(c, ar.download(s));
+    DSDTM_CUDA(c, cudaStreamSynchronize(s));
+    ar.finish();
+    const double* p10 = ar.host_view(pose10_d);
+    for (int k = 0; k < 7; ++k) out->pose_cur_c2w[k] = p10[k];
+    for (int k = 0; k < 3; ++k) out->cur_center[k] = p10[7 + k];
+    out->reserved = 0;
+    if (with_map) {
+        const int n = sel_h[17], got = std::min(n, cap);
+        if (got > first) {
+            DSDTM_CUDA(c, cudaMemcpyAsync(out_h + first, c->st_out_d + first, (size_t)(got - first) * sizeof(dsdtm_store_cand), cudaMemcpyDeviceToHost, s));
+            DSDTM_CUDA(c, cudaStreamSynchronize(s));
+        }
+        *n_local = sel_h[0];
+        for (int i = 0; i < sel_h[0]; ++i) local_rows[i] = sel_h[1 + i];
+        std::memcpy(cands, out_h, (size_t)got * sizeof(dsdtm_store_cand));
+        *n_out = n;
+        if (n > cap) return fail(c, DSDTM_E_ARG, "dsdtm_track_frame_store: more candidates than cap (records truncated)");
+    }
     return 0;
 }
 

@@ -116,6 +116,17 @@ struct dsdtm_ctx {
     double* mt_pts_d = nullptr;          size_t mt_pts_cap = 0;  size_t mt_pts_n = 0;     // 3 doubles per row
     uint8_t* mt_vis_d = nullptr;         size_t mt_vis_cap = 0;
     double* mt_dist_d = nullptr;         size_t mt_dist_cap = 0;
+    // device-resident map store (dsdtm_store_*)
+    dsdtm_store_kf* st_kfs_d = nullptr;      size_t st_kfs_cap = 0, st_kfs_n = 0;
+    dsdtm_store_feat* st_feats_d = nullptr;  size_t st_feats_cap = 0, st_feats_n = 0;
+    dsdtm_store_point* st_pts_d = nullptr;   size_t st_pts_cap = 0, st_pts_n = 0;
+    unsigned long long* st_claim_d = nullptr; size_t st_claim_cap = 0;     // per point: (~epoch << 32 | order) of the first local key frame that lists it
+    uint8_t* st_vis_d = nullptr;             size_t st_vis_cap = 0;
+    double* st_dist_d = nullptr;             size_t st_dist_cap = 0;
+    int* st_sel_d = nullptr;                 // [0] = n_local, [1..16] = local rows, [17] = n_cand
+    dsdtm_store_cand* st_out_d = nullptr;    size_t st_out_cap = 0;
+    unsigned st_epoch = 0;
+    int st_max_feats = 0;                    // largest feat_count of any key frame (grid width of the candidate kernels)
     // pose refinement (f-2), grown on demand
     dsdtm_ba_obs* po_obs_d = nullptr;    size_t po_obs_cap = 0;      // n_frames * obs_stride records
     double* po_res_d = nullptr;          size_t po_res_cap = 0;      // residual norms, same indexing
@@ -176,8 +187,8 @@ cudaError_t launch_fast_cells(dsdtm_ctx* c, int first_slot, int n, int barrier, 
 cudaError_t launch_fast_score_map(dsdtm_ctx* c, int slot, int level, int barrier, cudaStream_t s);
 cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int max_level, int min_level, int max_iters,
                                 bool want_log, cudaStream_t s, int pair0 = 0, int n_pairs_total = 0);
-cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0);
-cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s, int i0 = 0);
+cudaError_t launch_align2d(dsdtm_ctx* c, int n_patches, int max_iters, cudaStream_t s, int patch0 = 0, const int* n_dev = nullptr, dsdtm_store_cand* store_out = nullptr);
+cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t s, int i0 = 0, const int* n_dev = nullptr);
 cudaError_t launch_candidate_prep(dsdtm_ctx* c, int n, int cur_slot, int max_search_level, cudaStream_t s, int i0 = 0, const int* cur_slots_d = nullptr, int ppp = 0);
 cudaError_t launch_clahe(dsdtm_ctx* c, int first_slot, int n, double clip_limit, int tiles_x, int tiles_y, cudaStream_t s);
 int clahe_max_tiles_x();
@@ -190,6 +201,17 @@ cudaError_t launch_local_map_finalize(dsdtm_ctx* c, int n_pts, cudaStream_t s, d
 cudaError_t launch_pair_candidates(dsdtm_ctx* c, int pair0, int n_pairs, int feat_stride, int ppp, cudaStream_t s);
 cudaError_t launch_local_map(dsdtm_ctx* c, const double pose_cur[7], const double cur_center[3], int n_kfs, int n_pts, cudaStream_t s,
                              const double* pose_dev = nullptr);
+struct StoreTrackArgs {
+    int cur_slot, n_kfs, max_local, cap;
+    double pose_cur[7], cur_center[3];
+    const double* pose_dev = nullptr;           // {pose_c2w[7], centre[3]} on the device: overrides the two above
+    // or: compose them on the device from the sparse alignment's T_c2r and the reference pose, into pose10_out (overrides all three)
+    const double* t_c2r_dev = nullptr; double pose_ref[7] = {1, 0, 0, 0, 0, 0, 0}; double* pose10_out = nullptr;
+    int max_search_level = 0;
+};
+cudaError_t launch_store_link(dsdtm_ctx* c, int feat_begin, int n_feats, cudaStream_t s);
+cudaError_t launch_store_track(dsdtm_ctx* c, const StoreTrackArgs& a, cudaStream_t s);
+const int* store_count_dev(dsdtm_ctx* c);     // number of candidate records of the last launch_store_track, on the device
 cudaError_t launch_compose_pose(dsdtm_ctx* c, const double* t_c2r_d, const double pose_ref_c2w[7], double* out10_d, cudaStream_t s);
 cudaError_t launch_close_keyframes(dsdtm_ctx* c, const double pose_cur[7], int n_kfs, cudaStream_t s);
 cudaError_t pose_opt_init(dsdtm_ctx* c);

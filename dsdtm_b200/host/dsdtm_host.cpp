@@ -366,6 +366,25 @@ void Frame::Set_Mask()                                            // ref: src/Fr
 KeyFrame::KeyFrame(Frame* f) : mvImg_Pyr(f->mvImg_Pyr), mvFeatures(f->mvFeatures), mGpu(f->mGpu) { Set_Pose(f->Get_Pose()); }
 void KeyFrame::Set_Pose(const SE3& p) { mT_c2w = p; mOw = mT_c2w.inverse().translation(); }
 
+// change queue of the device-resident map store: positions (bundle adjustment) and bad flags (PoseOptimization's EraseFound) reach
+// the device at the next Map::Sync(); a mutex because LocalMapping may move points from its own thread
+MapPoint::DenseState* MapPoint::sDense = nullptr;
+static std::mutex g_touched_mutex;
+static std::vector<MapPoint*> g_touched;
+void MapPoint::Touch()
+{
+    if (mStoreId < 0) return;
+    std::unique_lock<std::mutex> l(g_touched_mutex);
+    if (!mTouched) { mTouched = true; g_touched.push_back(this); }
+}
+void MapPoint::DrainTouched(std::vector<MapPoint*>& out)
+{
+    std::unique_lock<std::mutex> l(g_touched_mutex);
+    out.swap(g_touched);
+    g_touched.clear();
+    for (MapPoint* m : out) m->mTouched = false;
+}
+
 bool MapPoint::Get_ClosetObs(const Frame* frame, Feature*& feature, KeyFrame*& kf) const   // ref: src/MapPoint.cpp:133-174
 {
     if (mObservations.empty()) return false;
@@ -458,6 +477,15 @@ void Map::Pack(KeyFrame* kf, dsdtm_map_kf& row, std::vector<double>& pts) const
     }
 }
 
+Map::~Map()
+{
+    for (MapPoint* m : mStorePoints) m->mStoreId = -1;
+    if (MapPoint::sDense == &mDense) MapPoint::sDense = nullptr;
+    for (KeyFrame* k : mvKeyFrames) { k->mStoreRow = -1; k->mStoreSlot = -1; }
+    if (g_runtime && (mStoreKfs > 0 || !mStorePoints.empty())) dsdtm_store_clear(g_runtime->ctx());
+    if (g_runtime && g_runtime->TrackingMap() == this) g_runtime->SetTrackingMap(nullptr);
+}
+
 void Map::AddKeyFrame(KeyFrame* kf)
 {
     if (mIndex.count(kf)) return;
@@ -471,6 +499,82 @@ void Map::MarkMoved(KeyFrame* kf)
 {
     auto it = mIndex.find(kf);
     if (it != mIndex.end() && it->second < mUploadedKfs) mPending.push_back(it->second);
+    if (kf->mStoreRow >= 0) mStoreMoved.push_back(kf);
+}
+
+// The device-resident map store (dsdtm_store_*): new key frames append their rows (their map points first), touched map points and
+// moved key frames are rewritten, and a key frame whose pyramid was evicted from the frame pool is re-uploaded (the store holds slots).
+void Map::SyncStore()
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    dsdtm_ctx* ctx = rt.ctx();
+    auto check = [&](int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + dsdtm_last_error(ctx)); };
+    rt.BeginEpoch();
+    for (int i = mStoreKfs; i < (int)mvKeyFrames.size(); ++i) {
+        KeyFrame* kf = mvKeyFrames[i];
+        std::vector<double> pos; std::vector<int32_t> bad;
+        const int first = (int)mStorePoints.size();
+        for (Feature* f : kf->mvFeatures)
+            if (f->Mpt && f->Mpt->mStoreId < 0) {
+                f->Mpt->mStoreId = (int)mStorePoints.size();
+                mStorePoints.push_back(f->Mpt);
+                mDense.found.push_back(f->Mpt->Get_FoundNums()); mDense.bad.push_back(f->Mpt->IsBad() ? 1 : 0);
+                MapPoint::sDense = &mDense;
+                const Vector3d P = f->Mpt->Get_Pose();
+                pos.push_back(P[0]); pos.push_back(P[1]); pos.push_back(P[2]);
+                bad.push_back(f->Mpt->IsBad() ? 1 : 0);
+            }
+        if (!bad.empty()) check(dsdtm_store_set_points(ctx, first, (int)bad.size(), pos.data(), bad.data()), "dsdtm_store_set_points");
+        dsdtm_store_kf row{};
+        row.slot = rt.Resident(kf->mGpu);
+        const SE3 T = kf->Get_Pose();
+        const Vector3d O = kf->Get_CameraCnt();
+        for (int k = 0; k < 7; ++k) row.pose_c2w[k] = T.data()[k];
+        for (int k = 0; k < 3; ++k) row.center[k] = O[k];
+        std::vector<dsdtm_store_feat> feats(kf->mvFeatures.size());
+        for (size_t j = 0; j < feats.size(); ++j) {
+            const Feature* f = kf->mvFeatures[j];
+            dsdtm_store_feat& o = feats[j];
+            o.mp = f->Mpt ? f->Mpt->mStoreId : -1;
+            o.level = f->mlevel; o.px[0] = f->mpx.x; o.px[1] = f->mpx.y;
+            for (int k = 0; k < 3; ++k) o.normal[k] = f->mNormal[k];
+            o.is_obs = (f->Mpt && f->Mpt->HasObservation(kf, j)) ? 1 : 0;
+            o.next_obs = -1;
+        }
+        int32_t r = -1;
+        check(dsdtm_store_append_keyframe(ctx, &row, feats.data(), (int)feats.size(), &r), "dsdtm_store_append_keyframe");
+        kf->mStoreRow = r; kf->mStoreSlot = row.slot;
+        ++mVersion;
+    }
+    mStoreKfs = (int)mvKeyFrames.size();
+    std::vector<MapPoint*> touched;
+    MapPoint::DrainTouched(touched);
+    if (!touched.empty()) {
+        std::vector<int32_t> ids, bad; std::vector<double> pos;
+        for (MapPoint* m : touched) {
+            if (m->mStoreId < 0) continue;
+            const Vector3d P = m->Get_Pose();
+            ids.push_back(m->mStoreId); bad.push_back(m->IsBad() ? 1 : 0);
+            pos.push_back(P[0]); pos.push_back(P[1]); pos.push_back(P[2]);
+        }
+        if (!ids.empty()) { check(dsdtm_store_update_points(ctx, ids.data(), (int)ids.size(), pos.data(), bad.data()), "dsdtm_store_update_points"); ++mVersion; }
+    }
+    // every key frame's pyramid must be resident under the slot the store names (touching it also keeps it young in the LRU pool)
+    for (KeyFrame* kf : mvKeyFrames) {
+        const int slot = rt.Resident(kf->mGpu);
+        const bool moved = std::find(mStoreMoved.begin(), mStoreMoved.end(), kf) != mStoreMoved.end();
+        if (slot != kf->mStoreSlot || moved) {
+            const SE3 T = kf->Get_Pose();
+            const Vector3d O = kf->Get_CameraCnt();
+            double c3[3] = { O[0], O[1], O[2] };
+            check(dsdtm_store_set_keyframe(ctx, kf->mStoreRow, slot, T.data(), c3), "dsdtm_store_set_keyframe");
+            kf->mStoreSlot = slot;
+            ++mVersion;
+        }
+    }
+    mStoreMoved.clear();
+    if (!rt.SlotsStillValid())
+        throw std::runtime_error("Map::SyncStore: frame pool too small for the key frames of the map (raise Gpu.MaxFrames)");
 }
 
 void Map::Sync()
@@ -499,8 +603,8 @@ void Map::Sync()
     }
 }
 
-Tracking::Tracking(CameraPtr cam, Map* map) : mMap(map), mFeature_Alignment(new Feature_Alignment(cam)), mCam(cam) {}
-Tracking::~Tracking() { delete mFeature_Alignment; }
+Tracking::Tracking(CameraPtr cam, Map* map) : mMap(map), mFeature_Alignment(new Feature_Alignment(cam)), mCam(cam) { GpuRuntime::Instance().SetTrackingMap(map); }
+Tracking::~Tracking() { if (g_runtime && g_runtime->TrackingMap() == mMap) g_runtime->SetTrackingMap(nullptr); delete mFeature_Alignment; }
 
 void Tracking::GetCloseKeyFrames(const Frame* tFrame, std::list<std::pair<KeyFrame*, double>>& tClose_kfs) const   // ref: src/Tracking.cpp:315-345
 {
@@ -518,8 +622,65 @@ void Tracking::GetCloseKeyFrames(const Frame* tFrame, std::list<std::pair<KeyFra
         if (visible[i]) tClose_kfs.push_back(std::make_pair(mMap->Row(i), dist[i]));      // ref: :331-333, in GetAllKeyFrames order
 }
 
+bool Tracking::sUseStore = true;
+bool Tracking::sSpeculate = true;
+
+// UpdateLocalMap on the device-resident map store: ONE call selects the close key frames, ranks them, visits every map point of the
+// ten nearest once, reprojects it and -- for the points that land in the image -- runs Get_ClosetObs, the IsInImage gate,
+// SolveAffineMatrix, WarpAffine and Align2D. What comes back is one record per candidate; SearchLocalPoints orders its cells and
+// replays the mask-dependent greedy selection. Same candidates, same order, same arithmetic as the host loop below
+// (tests: test_update_local_map_device_path_equals_the_host_loop).
+void Tracking::UpdateLocalMapOnDevice()
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    const auto T0 = std::chrono::steady_clock::now();
+    mMap->Sync();
+    mMap->SyncStore();
+    const auto T1 = std::chrono::steady_clock::now();
+    mFeature_Alignment->ResetGrid();
+    mvpLocalKeyFrames.clear();
+    mvpLocalMapPoints.clear();
+    mLastReprojected = 0;
+    if (mMap->ReturnKeyFramesSize() == 0) return;
+    const SE3 Tc = mCurrentFrame->Get_Pose();
+    {   // Run already did this frame's local-map stage with exactly this pose on exactly this map: take its records
+        GpuRuntime::Speculation& sp = rt.Spec();
+        if (sp.frame == mCurrentFrame.get() && sp.map_version == mMap->Version() && std::memcmp(sp.pose, Tc.data(), sizeof sp.pose) == 0) {
+            for (int i = 0; i < sp.n_local; ++i) mvpLocalKeyFrames.push_back(mMap->Row(sp.rows[i]));
+            mLastReprojected = sp.n_out;
+            sp.frame = nullptr;
+            mFeature_Alignment->SetFused(mCurrentFrame.get(), std::move(sp.cands), &mMap->StorePoints(), &mMap->Dense());
+            if (getenv("DSDTM_HOST_TIMING")) fprintf(stderr, "UpdateLocalMap(device): records of Run's submission taken (n=%d)\n", mLastReprojected);
+            return;
+        }
+        sp.frame = nullptr;
+    }
+    const int cur_slot = rt.Resident(mCurrentFrame->mGpu);
+    const Vector3d Oc = mCurrentFrame->Get_CameraCnt();
+    const double center[3] = { Oc[0], Oc[1], Oc[2] };
+    static thread_local std::vector<dsdtm_store_cand> cands;
+    const int cap = 4096;
+    cands.resize(cap);
+    int32_t rows[16], n_local = 0, n_out = 0;
+    if (dsdtm_store_track(rt.ctx(), cur_slot, Tc.data(), center, 10, Config::Get<int>("Camera.MaxPyraLevels") - 3, 10, rows, &n_local,
+                          cands.data(), cap, &n_out) != 0)
+        throw std::runtime_error(std::string("dsdtm_store_track: ") + dsdtm_last_error(rt.ctx()));
+    for (int i = 0; i < n_local; ++i) mvpLocalKeyFrames.push_back(mMap->Row(rows[i]));
+    cands.resize((size_t)n_out);
+    mLastReprojected = n_out;
+    std::vector<dsdtm_store_cand> mine(cands.begin(), cands.end());
+    mFeature_Alignment->SetFused(mCurrentFrame.get(), std::move(mine), &mMap->StorePoints(), &mMap->Dense());
+    if (getenv("DSDTM_HOST_TIMING")) {
+        const auto T2 = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "UpdateLocalMap(device): sync %.1f us, dsdtm_store_track %.1f us (n=%d)\n", us(T0, T1), us(T1, T2), n_out);
+    }
+    // mvpLocalMapPoints (the viewer's list, ref: :299,308-312) is not rebuilt per frame here: nothing on the path reads it
+}
+
 void Tracking::UpdateLocalMap()                                   // ref: src/Tracking.cpp:257-313
 {
+    if (sUseStore) { UpdateLocalMapOnDevice(); return; }
     mFeature_Alignment->ResetGrid();
     std::list<std::pair<KeyFrame*, double>> tClose_kfs;
     GetCloseKeyFrames(mCurrentFrame.get(), tClose_kfs);
@@ -623,7 +784,8 @@ int Sprase_ImgAlign::Run(FramePtr cur, FramePtr ref)              // ref: src/Sp
     if ((int)ref->mvFeatures.size() < mnMinfts) return 0;         // ref: :34-38 "Too few features to track"
     GpuRuntime& rt = GpuRuntime::Instance();
     // snapshot every map point ONCE on the tracking thread (the mapper moves them under mutex, SURVEY 7 "thread-safety at the seam")
-    std::vector<dsdtm_ref_feat> feats;
+    std::vector<dsdtm_ref_feat>& feats = mFeats;
+    feats.clear();
     feats.reserve(ref->mvFeatures.size());
     for (Feature* f : ref->mvFeatures) {
         dsdtm_ref_feat r;
@@ -637,11 +799,44 @@ int Sprase_ImgAlign::Run(FramePtr cur, FramePtr ref)              // ref: src/Sp
     const Vector3d cen = ref->Get_CameraCnt();
     double pose_out[7];
     int n_tracked = 0, n_log = 0;
-    mLog.resize(256);
+    if (mWantLog) mLog.resize(256);
+    Map* tmap = (Tracking::sUseStore && Tracking::sSpeculate && !mWantLog) ? rt.TrackingMap() : nullptr;
+    if (tmap && tmap->ReturnKeyFramesSize() > 0) {
+        // Run + Tracking::UpdateLocalMap in ONE submission (dsdtm_track_frame_store): the tables are brought up to date first, the
+        // device composes cur.Set_Pose(T_c2r * ref) itself and runs the local-map stage with it; the records wait in the runtime
+        tmap->Sync();
+        tmap->SyncStore();
+        const int ref_slot = rt.Resident(ref->mGpu), cur_slot = rt.Resident(cur->mGpu);
+        dsdtm_track_store_in in{};
+        in.ref_slot = ref_slot; in.cur_slot = cur_slot; in.n_feats = (int)feats.size(); in.feats = feats.data();
+        const SE3 Tr = ref->Get_Pose();
+        for (int k = 0; k < 3; ++k) in.ref_center[k] = cen[k];
+        for (int k = 0; k < 7; ++k) { in.pose_ref_c2w[k] = Tr.data()[k]; in.pose_c2r_in[k] = T_c2r.data()[k]; }
+        in.max_level = mnMaxLevel; in.min_level = mnMinLevel; in.max_iters = mnMaxIterators;
+        in.max_local = 10; in.max_search_level = Config::Get<int>("Camera.MaxPyraLevels") - 3; in.align_iters = 10;
+        dsdtm_track_out to{};
+        GpuRuntime::Speculation& sp = rt.Spec();
+        sp.frame = nullptr;
+        const int cap = 4096;
+        sp.cands.resize(cap);
+        int32_t nl = 0, no = 0;
+        if (dsdtm_track_frame_store(rt.ctx(), &in, &to, sp.rows, &nl, sp.cands.data(), cap, &no) != 0)
+            throw std::runtime_error(std::string("dsdtm_track_frame_store: ") + dsdtm_last_error(rt.ctx()));
+        mLog.clear();
+        mT_c2r = SE3(to.pose_c2r);
+        cur->Set_Pose(mT_c2r * ref->Get_Pose());                 // ref: :57
+        if (std::memcmp(cur->Get_Pose().data(), to.pose_cur_c2w, 7 * sizeof(double)) == 0) {   // the device composed the same bits
+            sp.cands.resize((size_t)no);
+            sp.n_local = nl; sp.n_out = no; sp.map_version = tmap->Version();
+            std::memcpy(sp.pose, to.pose_cur_c2w, sizeof sp.pose);
+            sp.frame = cur.get();
+        }
+        return to.n_tracked;
+    }
     const int ref_slot = rt.Resident(ref->mGpu), cur_slot = rt.Resident(cur->mGpu);
     // chunks of max_feats would change the reference's single linear system; the capacity is sized from Camera.Max_fts instead
     if (dsdtm_sparse_align(rt.ctx(), ref_slot, cur_slot, feats.data(), (int)feats.size(), cen.v, T_c2r.data(), mnMaxLevel, mnMinLevel,
-                           mnMaxIterators, pose_out, &n_tracked, mLog.data(), (int)mLog.size(), &n_log) != 0)
+                           mnMaxIterators, pose_out, &n_tracked, mWantLog ? mLog.data() : nullptr, mWantLog ? (int)mLog.size() : 0, &n_log) != 0)
         throw std::runtime_error(std::string("dsdtm_sparse_align: ") + dsdtm_last_error(rt.ctx()));
     mLog.resize(std::min<size_t>(n_log, mLog.size()));
     mT_c2r = SE3(pose_out);
@@ -667,10 +862,84 @@ Feature_Alignment::Feature_Alignment(CameraPtr camera) : mCam(camera)   // ref: 
 }
 
 Feature_Alignment::~Feature_Alignment() { for (auto* c : mCells) delete c; }
-void Feature_Alignment::ResetGrid() { for (auto* c : mCells) c->clear(); }
+void Feature_Alignment::ResetGrid() { for (auto* c : mCells) c->clear(); mFusedFrame = nullptr; mFusedPoints = nullptr; mFused.clear(); }
+
+void Feature_Alignment::SetFused(const Frame* frame, std::vector<dsdtm_store_cand>&& cands, const std::vector<MapPoint*>* points, const MapPoint::DenseState* dense)
+{
+    mFused = std::move(cands); mFusedFrame = frame; mFusedPoints = points; mFusedDense = dense;
+}
+
+// a caller mixes the two styles (UpdateLocalMap on the device, then its own ReprojectPoint calls): rebuild the reference's cell lists
+// from the records, in the reference's insertion order, and continue on the host path
+void Feature_Alignment::MaterializeFused()
+{
+    std::vector<const dsdtm_store_cand*> o;
+    for (const auto& c : mFused) o.push_back(&c);
+    std::sort(o.begin(), o.end(), [](const dsdtm_store_cand* a, const dsdtm_store_cand* b) { return a->order < b->order; });
+    for (const dsdtm_store_cand* c : o)
+        mCells[c->r.cell]->push_back(Candidate((*mFusedPoints)[c->mp], Vector2d(c->r.px_proj[0], c->r.px_proj[1])));
+    mFusedFrame = nullptr; mFusedPoints = nullptr; mFusedDense = nullptr; mFused.clear();
+}
+
+// SearchLocalPoints on the records of dsdtm_store_track (ref: :71-121): cells in index order, candidates of a cell by found count
+// (std::list::sort is stable: ties keep the order of the ReprojectPoint calls = `order`), first converged candidate whose projection
+// is still unmasked wins the cell, its circle masks later candidates, 200 matches end the search.
+void Feature_Alignment::SearchFused(FramePtr frame)
+{
+    const auto T0 = std::chrono::steady_clock::now();
+    // bucket the records by cell (counting sort: 1376 cells), then order each cell's few candidates by (found desc, order asc)
+    struct Key { int found, order, idx; };
+    static thread_local std::vector<Key> keys;
+    static thread_local std::vector<int> begin;
+    const int n_cells = (int)mCells.size();
+    begin.assign((size_t)n_cells + 1, 0);
+    for (const dsdtm_store_cand& c : mFused) begin[(size_t)c.r.cell + 1]++;
+    for (int i = 0; i < n_cells; ++i) begin[(size_t)i + 1] += begin[(size_t)i];
+    keys.resize(mFused.size());
+    {
+        static thread_local std::vector<int> fill;
+        fill.assign(begin.begin(), begin.end() - 1);
+        for (size_t i = 0; i < mFused.size(); ++i) {
+            const dsdtm_store_cand& c = mFused[i];
+            keys[(size_t)fill[(size_t)c.r.cell]++] = Key{ mFusedDense->found[(size_t)c.mp], c.order, (int)i };
+        }
+    }
+    int matches = 0;
+    const int gates = DSDTM_LM_OBS_OK | DSDTM_LM_REF_OK;
+    for (int cell = 0; cell < n_cells && matches < 200; ++cell) {   // ref: :75-82, the literal 200
+        const int b0 = begin[(size_t)cell], b1 = begin[(size_t)cell + 1];
+        if (b0 == b1) continue;
+        if (b1 - b0 > 1)
+            std::sort(keys.begin() + b0, keys.begin() + b1, [](const Key& a, const Key& b) { return a.found != b.found ? a.found > b.found : a.order < b.order; });
+        for (int k = b0; k < b1; ++k) {
+            const dsdtm_store_cand& c = mFused[(size_t)keys[(size_t)k].idx];
+            if (mFusedDense->bad[(size_t)c.mp]) continue;
+            if (frame->mImgMask.at(cvRound((float)c.r.px_proj[1]), cvRound((float)c.r.px_proj[0])) != 255) continue;
+            if ((c.r.flags & gates) != gates || c.r.level < 0) continue;
+            if (!(c.r.flags & DSDTM_LM_CONVERGED)) continue;
+            MapPoint* mp = (*mFusedPoints)[(size_t)c.mp];
+            mp->IncreaseFound();
+            const Point2f p((float)c.r.px[0], (float)c.r.px[1]);
+            Feature* f = new Feature(frame.get(), p, c.r.level);
+            f->SetPose(mp);
+            circle(frame->mImgMask, p, mCell_size, 0);
+            frame->Add_Feature(f);
+            frame->Add_MapPoint(mp);
+            matches++;
+            break;                                               // ReprojectCell returns at the first match
+        }
+    }
+    mLastMatches = matches;
+    mFusedFrame = nullptr; mFusedPoints = nullptr; mFused.clear();
+    if (getenv("DSDTM_HOST_TIMING")) {
+        const auto T1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "SearchLocalPoints(records): order + replay %.1f us\n", std::chrono::duration<double, std::micro>(T1 - T0).count());
+    }
+}
 
 bool Feature_Alignment::ReprojectPoint(FramePtr frame, MapPoint* mp)     // ref: :54-69
 {
+    if (mFusedPoints) MaterializeFused();
     const Vector2d px = frame->World2Pixel(mp->Get_Pose());
     if (mCam->IsInImage(Point2f((float)px(0), (float)px(1)), 8)) {
         const int index = static_cast<int>(px(1) / mCell_size) * mGrid_Cols + static_cast<int>(px(0) / mCell_size);
@@ -727,6 +996,8 @@ bool Feature_Alignment::Prepare(const MapPoint* mp, const FramePtr frame, const 
 
 void Feature_Alignment::SearchLocalPoints(FramePtr frame)                 // ref: :71-121
 {
+    if (HasFused(frame.get())) { SearchFused(frame); return; }
+    if (mFusedPoints) MaterializeFused();
     const auto T0 = std::chrono::steady_clock::now();
     GpuRuntime::Instance().BeginEpoch();
     // The reference walks cells in index order, candidates by found-count, and stops a cell at the first match; a match

@@ -146,21 +146,32 @@ class MapPoint {   // ref: include/MapPoint.h, src/MapPoint.cpp:38-43,126-181 (t
 public:
     explicit MapPoint(const Vector3d& pose) : mPose(pose) {}
     Vector3d Get_Pose() const { std::unique_lock<std::mutex> l(mMutexPos); return mPose; }
-    void Set_Pose(const Vector3d& p) { std::unique_lock<std::mutex> l(mMutexPos); mPose = p; }
+    void Set_Pose(const Vector3d& p) { { std::unique_lock<std::mutex> l(mMutexPos); mPose = p; } Touch(); }
     bool IsBad() const { return mbBad; }
-    void SetBad(bool b) { mbBad = b; }
+    void SetBad(bool b) { mbBad = b; Touch(); Mirror(); }
+    // new: row of this point in the device-resident map store (-1 = not there yet) and the change queue Map::Sync() drains
+    int mStoreId = -1;
+    // dense host mirrors of (found count, bad flag) by store row: SearchLocalPoints orders ~1000 candidates per frame by found count
+    // and would otherwise chase a pointer per candidate into objects scattered over the heap
+    struct DenseState { std::vector<int> found; std::vector<unsigned char> bad; };
+    static DenseState* sDense;
+    void Mirror() { if (mStoreId >= 0 && sDense && (size_t)mStoreId < sDense->found.size()) { sDense->found[mStoreId] = mnFound; sDense->bad[mStoreId] = mbBad ? 1 : 0; } }
+    void Touch();
+    static void DrainTouched(std::vector<MapPoint*>& out);
     int Get_FoundNums() const { return mnFound; }
-    void IncreaseFound(int n = 1) { mnFound += n; }
+    void IncreaseFound(int n = 1) { mnFound += n; Mirror(); }
     // ref: src/MapPoint.cpp:183-197 (+ SetBadFlag :91-109: the outlier flag and the observation list; the Map / KeyFrame
     // bookkeeping it also does lives outside the path)
-    void EraseFound(int n = 1) { mnFound -= n; if (mnFound <= 0) { mbBad = true; mObservations.clear(); } }
+    void EraseFound(int n = 1) { mnFound -= n; if (mnFound <= 0) { mbBad = true; mObservations.clear(); Touch(); } Mirror(); }
     void Add_Observation(KeyFrame* kf, size_t idx) { mObservations[kf] = idx; }
     bool Get_ClosetObs(const Frame* frame, Feature*& feature, KeyFrame*& kf) const;
     std::map<KeyFrame*, size_t> Get_Observations() const { return mObservations; }   // ref: src/MapPoint.cpp (copy under mMutexObs)
     // the adapters' snapshot walks the observations in place (same std::map order) instead of copying the map per candidate
     template <class F> void ForEachObservation(F&& f) const { for (const auto& o : mObservations) f(o.first, o.second); }
     unsigned long mLastProjectedFrameId = (unsigned long)-1;     // ref: include/MapPoint.h (UpdateLocalMap's per-frame dedupe)
+    bool HasObservation(KeyFrame* kf, size_t idx) const { auto it = mObservations.find(kf); return it != mObservations.end() && it->second == idx; }
 private:
+    bool mTouched = false;
     mutable std::mutex mMutexPos;
     Vector3d mPose;
     bool mbBad = false;
@@ -222,6 +233,7 @@ public:
     // position of this key frame in the table of the snapshot being built (valid while mSnapEpoch == the snapshot's number)
     mutable unsigned long long mSnapEpoch = 0;
     mutable int mSnapIndex = -1;
+    int mStoreRow = -1, mStoreSlot = -1;                        // new: row in the device-resident map store, slot recorded there
 private:
     SE3 mT_c2w;
     Vector3d mOw;
@@ -257,10 +269,13 @@ public:
     const SE3& Get_T_c2r() const { return mT_c2r; }           // mT_c2r of the last Run
     // last run's Gauss-Newton trace (new: the reference only prints; used by the parity tests)
     const std::vector<dsdtm_iter_log>& LastLog() const { return mLog; }
+    void EnableLog(bool on) { mWantLog = on; }                // off by default: the trace costs an 18 KB read-back per frame
 protected:
     int mnMaxLevel, mnMinLevel, mnMaxIterators, mnMinfts;
     SE3 mT_c2r;
     std::vector<dsdtm_iter_log> mLog;
+    bool mWantLog = false;
+    std::vector<dsdtm_ref_feat> mFeats;                       // reused across frames
 };
 
 static const int mHalf_PatchSize = 4;   // ref: include/Feature_alignment.h:21
@@ -295,7 +310,17 @@ public:
     // uploaded into a scratch slot for the call. Throws std::invalid_argument for any other size.
     static bool Align2DGaussNewton(const Mat8& tCurImg, uchar* tPatch_WithBoarder, uchar* tPatch, int MaxIters, Vector2d& tCurPx);
     int LastMatches() const { return mLastMatches; }
+    // new: Tracking::UpdateLocalMap's device path (dsdtm_store_track) hands its per-candidate records here instead of calling
+    // ReprojectPoint once per map point; SearchLocalPoints then only orders the cells and replays the greedy selection
+    void SetFused(const Frame* frame, std::vector<dsdtm_store_cand>&& cands, const std::vector<MapPoint*>* points, const MapPoint::DenseState* dense);
+    bool HasFused(const Frame* frame) const { return mFusedFrame == frame && mFusedPoints != nullptr; }
 private:
+    void SearchFused(FramePtr frame);
+    void MaterializeFused();            // a later ReprojectPoint call: turn the records back into the reference's cell lists
+    const Frame* mFusedFrame = nullptr;
+    std::vector<dsdtm_store_cand> mFused;
+    const std::vector<MapPoint*>* mFusedPoints = nullptr;
+    const MapPoint::DenseState* mFusedDense = nullptr;
     struct Prepared;   // one candidate after the host-side map walk
     bool Prepare(const MapPoint* mp, const FramePtr frame, const Vector2d& px, Prepared& out);
     CameraPtr mCam;
@@ -309,13 +334,23 @@ private:
 // a key frame whose pose or points a bundle adjustment changed; Sync() uploads what is pending (called by GetCloseKeyFrames).
 class Map {
 public:
+    ~Map();                                                      // forgets the device-resident rows of this map
     void AddKeyFrame(KeyFrame* kf);                              // ref: src/Map.cpp AddKeyFrame
     std::vector<KeyFrame*> GetAllKeyFrames() const { return mvKeyFrames; }   // insertion order (the reference: std::set = address order)
     int ReturnKeyFramesSize() const { return (int)mvKeyFrames.size(); }
     void MarkMoved(KeyFrame* kf);                                // new: LocalBundleAdjustment's hook
     void Sync();                                                 // new: pending rows -> dsdtm_map_table_upload
     KeyFrame* Row(int i) const { return mvKeyFrames[i]; }
+    const std::vector<MapPoint*>& StorePoints() const { return mStorePoints; }    // map-store row -> MapPoint
+    const MapPoint::DenseState& Dense() const { return mDense; }
+    unsigned long long Version() const { return mVersion; }      // changes whenever Sync() / SyncStore() changed a device table
+    void SyncStore();                                            // new key frames / points, touched points, moved or re-uploaded key frames
 private:
+    std::vector<MapPoint*> mStorePoints;
+    MapPoint::DenseState mDense;
+    unsigned long long mVersion = 1;
+    int mStoreKfs = 0;
+    std::vector<KeyFrame*> mStoreMoved;
     struct Rows { int pt_begin, pt_count; };
     void Pack(KeyFrame* kf, dsdtm_map_kf& row, std::vector<double>& pts) const;
     std::vector<KeyFrame*> mvKeyFrames;
@@ -340,7 +375,11 @@ public:
     std::vector<KeyFrame*> mvpLocalKeyFrames;
     std::map<MapPoint*, KeyFrame*> mvpLocalMapPoints;
     int LastReprojected() const { return mLastReprojected; }
+    // new: false = the literal host loop of the reference (one ReprojectPoint per map point); true (default) = dsdtm_store_track
+    static bool sUseStore;
+    static bool sSpeculate;                                   // Run also runs the local-map stage (one synchronisation per frame instead of two)
 private:
+    void UpdateLocalMapOnDevice();
     CameraPtr mCam;
     int mLastReprojected = 0;
 };
@@ -372,6 +411,21 @@ public:
     void BeginEpoch() { mEpochStart = mClock; mEpochEvicted = false; }
     bool SlotsStillValid() const { return !mEpochEvicted; }
     void SetDepthOwner(const Frame* f) { mDepthOwner = f; }      // depth slot 0 holds this frame's depth image
+    // Run + UpdateLocalMap as one submission (dsdtm_track_frame_store): Tracking registers its map; Sprase_ImgAlign::Run then also runs the
+    // local-map stage with the pose it has just found and parks the records here; Tracking::UpdateLocalMap takes them when frame, pose
+    // and map version still match (otherwise it makes its own call). Same results either way (the device composes the pose exactly as
+    // the host does; the adapter checks the bits).
+    struct Speculation {
+        const Frame* frame = nullptr;
+        double pose[7];
+        int32_t rows[16];
+        int n_local = 0, n_out = 0;
+        unsigned long long map_version = 0;
+        std::vector<dsdtm_store_cand> cands;
+    };
+    void SetTrackingMap(Map* m) { mTrackingMap = m; mSpec.frame = nullptr; }
+    Map* TrackingMap() const { return mTrackingMap; }
+    Speculation& Spec() { return mSpec; }
     const Frame* DepthOwner() const { return mDepthOwner; }
     ~GpuRuntime();
 private:
@@ -384,6 +438,8 @@ private:
     unsigned long long mClock = 0, mEpochStart = 0;
     bool mEpochEvicted = false;
     const Frame* mDepthOwner = nullptr;
+    Map* mTrackingMap = nullptr;
+    Speculation mSpec;
     friend class GpuSlot;
 };
 

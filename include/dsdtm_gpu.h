@@ -366,6 +366,78 @@ typedef struct {
 } dsdtm_track_out;          /* 144 bytes */
 int dsdtm_track_frame(dsdtm_ctx* ctx, const dsdtm_track_in* in, dsdtm_track_out* out, dsdtm_reproj* reproj /* n_pts */);
 
+/* ---------------------------------------------------------------- device-resident map store -------------------------------- */
+/* Tracking::UpdateLocalMap + Feature_Alignment::SearchLocalPoints' arithmetic as ONE call on a map that LIVES on the device
+ * (ref: src/Tracking.cpp:257-345, src/Feature_alignment.cpp:54-69,128-158, src/MapPoint.cpp:133-174). The per-frame host work of the
+ * reference -- a loop over every map point of the ten local key frames, a mutex-guarded Get_Pose per point, a std::map copy per
+ * candidate -- becomes table maintenance at key-frame rate: a key frame appends its row and its features' rows once
+ * (dsdtm_store_append_keyframe), map points are appended / updated when they are created, moved by a bundle adjustment or flagged bad
+ * (dsdtm_store_set_points / dsdtm_store_update_points), and every frame makes one call (dsdtm_store_track). */
+typedef struct {
+    int32_t slot;           /* frame slot of the key frame's pyramid (KeyFrame::mvImg_Pyr) */
+    int32_t feat_begin;     /* first row of this key frame in the feature table (filled by the library on append) */
+    int32_t feat_count;
+    int32_t reserved;
+    double  pose_c2w[7];    /* KeyFrame::Get_Pose() */
+    double  center[3];      /* KeyFrame::Get_CameraCnt() */
+} dsdtm_store_kf;           /* 96 bytes */
+typedef struct {
+    int32_t mp;             /* row of the feature's map point in the point table (KeyFrame::mvMapPoints[i]), -1 = none */
+    int32_t level;          /* Feature::mlevel */
+    float   px[2];          /* Feature::mpx */
+    double  normal[3];      /* Feature::mNormal */
+    int32_t is_obs;         /* != 0: (key frame, this feature) is in MapPoint::mObservations of `mp` */
+    int32_t next_obs;       /* library: next older observation of the same map point (feature-table row), -1 = end */
+} dsdtm_store_feat;         /* 48 bytes */
+typedef struct {
+    double  point_w[3];     /* MapPoint::Get_Pose() */
+    int32_t bad;            /* MapPoint::IsBad() */
+    int32_t last_obs;       /* library: newest observation (feature-table row), -1 = none */
+} dsdtm_store_point;        /* 32 bytes */
+typedef struct {
+    int32_t mp;             /* map point (row of the point table) */
+    int32_t order;          /* (rank of the local key frame << 16) | feature index: the order in which UpdateLocalMap calls ReprojectPoint */
+    dsdtm_reproj r;         /* as dsdtm_local_map_align_batch: projection, cell, chosen observation (feature-table row), flags, level, refined px */
+} dsdtm_store_cand;         /* 56 bytes */
+/* points [first, first + n): append (first == current size) or rewrite. bad may be NULL (= 0). Appended points start without observations. */
+int dsdtm_store_set_points(dsdtm_ctx* ctx, int first, int n, const double* point_w, const int32_t* bad);
+/* scattered update of existing points: positions (NULL = keep) and bad flags (NULL = keep) */
+int dsdtm_store_update_points(dsdtm_ctx* ctx, const int32_t* ids, int n, const double* point_w, const int32_t* bad);
+/* appends one key frame with its features (row = number of key frames before the call, returned in *row); the observation chains of
+ * the features' map points are extended on the device */
+int dsdtm_store_append_keyframe(dsdtm_ctx* ctx, const dsdtm_store_kf* kf, const dsdtm_store_feat* feats, int n_feats, int32_t* row);
+/* pose / slot of an existing key frame (bundle adjustment moved it; its pyramid was re-uploaded into another slot) */
+int dsdtm_store_set_keyframe(dsdtm_ctx* ctx, int row, int slot, const double pose_c2w[7], const double center[3]);
+int dsdtm_store_clear(dsdtm_ctx* ctx);
+/* One frame: GetCloseKeyFrames over all key frames (a point of the key frame visible in the current frame), the max_local nearest by
+ * |t_cur - t_kf| (stable in row order), every map point of those key frames once (first key frame in rank order wins, bad points
+ * skipped), ReprojectPoint, and for the points inside the image Get_ClosetObs + the IsInImage gate + SolveAffineMatrix +
+ * GetBestSearchLevel + WarpAffine + Align2DGaussNewton. Returns the local key frames in rank order and ONE record per point that landed
+ * in the image (unordered; `order` restores the reference's insertion order, the caller sorts its cells by found count and replays the
+ * mask-dependent greedy selection of SearchLocalPoints). cap = capacity of `out`; *n_out may exceed it (then only cap records are
+ * written and the call returns DSDTM_E_ARG). Observations are walked newest first; with strict '>' on the cosine, exact ties keep the
+ * newest (the reference: std::map<KeyFrame*> address order -- not reproducible). */
+int dsdtm_store_track(dsdtm_ctx* ctx, int cur_slot, const double pose_cur_c2w[7], const double cur_center[3], int max_local,
+                      int max_search_level, int align_iters, int32_t* local_rows, int32_t* n_local, dsdtm_store_cand* out, int cap,
+                      int32_t* n_out);
+
+/* Sprase_ImgAlign::Run + Tracking::UpdateLocalMap (+ the arithmetic of SearchLocalPoints) of one frame as ONE submission with one
+ * synchronisation (ref: src/Tracking.cpp:199-224,257-313): sparse alignment of cur against ref, cur.Set_Pose(T_c2r * ref pose) on the
+ * device (ref: src/Sprase_ImageAlign.cpp:57), then dsdtm_store_track with that pose. The current frame's pyramid must already be in
+ * cur_slot (Frame's constructor uploads it). out: as dsdtm_track_frame; local_rows / cands / n_out: as dsdtm_store_track. */
+typedef struct {
+    int32_t ref_slot, cur_slot;
+    int32_t n_feats, reserved;
+    const dsdtm_ref_feat* feats;
+    double  ref_center[3];
+    double  pose_ref_c2w[7];
+    double  pose_c2r_in[7];
+    int32_t max_level, min_level, max_iters;
+    int32_t max_local, max_search_level, align_iters;
+} dsdtm_track_store_in;
+int dsdtm_track_frame_store(dsdtm_ctx* ctx, const dsdtm_track_store_in* in, dsdtm_track_out* out, int32_t* local_rows, int32_t* n_local,
+                            dsdtm_store_cand* cands, int cap, int32_t* n_out);
+
 /* ---------------------------------------------------------------- batched front end (sweep / bench) -------- */
 /* One "step" over n_pairs independent frame pairs: [pyramid(cur)] -> sparse align -> Align2D of the pair's patches
  * against its cur frame. Inputs are staged once (H2D), run() only launches kernels on HBM-resident data (CUDA-graph

@@ -91,7 +91,7 @@ def main():
                     P = np.zeros(3); L.hs_mappoint_pose(int(idl[j]), HL._p(P)); Fo[j]["point_w"] = P
             last_pose = g_last.pose()
             t1 = time.perf_counter()
-        nt, pose_sa, _ = HL.sparse_align_run(5, 0, 8, g_cur, g_last)
+        nt, pose_sa, _ = HL.sparse_align_run(5, 0, 8, g_cur, g_last, want_log=False)
         t2 = time.perf_counter()
         if k % CHECK_EVERY == 0:
             rp, offs, ws, hs = O.pyramid(imgs[k - 1], 5)

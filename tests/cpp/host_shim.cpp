@@ -153,6 +153,9 @@ void hs_frame_feature_mp_ids(void* f, int* ids)
         for (size_t k = 0; k < g_mps.size(); ++k) if (g_mps[k] == fs[i]->Mpt) { ids[i] = (int)k; break; }
     }
 }
+void hs_set_use_store(int on) { Tracking::sUseStore = on != 0; }
+void hs_set_speculate(int on) { Tracking::sSpeculate = on != 0; }
+void hs_mappoint_increase_found(int id, int n) { if (id >= 0 && id < (int)g_mps.size()) g_mps[id]->IncreaseFound(n); }
 void hs_mappoint_pose(int id, double* out3) { const Vector3d P = g_mps[id]->Get_Pose(); out3[0] = P[0]; out3[1] = P[1]; out3[2] = P[2]; }
 int hs_mappoint_found(int id) { return (id >= 0 && id < (int)g_mps.size()) ? g_mps[id]->Get_FoundNums() : -1; }
 
@@ -160,6 +163,7 @@ int hs_sparse_align_run(int maxl, int minl, int iters, void* cur, void* ref, dou
 {
     try {
         Sprase_ImgAlign sa(maxl, minl, iters);
+        sa.EnableLog(log != nullptr && cap > 0);
         const int n = sa.Run(static_cast<HsFrame*>(cur)->f, static_cast<HsFrame*>(ref)->f);
         std::memcpy(pose_out, static_cast<HsFrame*>(cur)->f->Get_Pose().data(), 7 * sizeof(double));
         const auto& l = sa.LastLog();

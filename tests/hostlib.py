@@ -51,6 +51,9 @@ def lib():
         L.hs_search_local_points.argtypes = [C.c_void_p] * 5
         L.hs_mappoint_found.argtypes = [C.c_int]
         L.hs_mappoint_pose.argtypes = [C.c_int, C.c_void_p]
+        L.hs_mappoint_increase_found.argtypes = [C.c_int, C.c_int]
+        L.hs_set_use_store.argtypes = [C.c_int]
+        L.hs_set_speculate.argtypes = [C.c_int]
         L.hs_mappoint_set_bad.argtypes = [C.c_int, C.c_int]
         L.hs_search_local_points_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_frame_attach_points_from.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -179,9 +182,9 @@ def track_local_map(cam_h, cur):
     return m, local[:n_local.value].copy(), nrep.value
 
 
-def sparse_align_run(maxl, minl, iters, cur, ref):
-    pose = np.empty(7); log = np.zeros(256, ITER_LOG_DT); n_log = C.c_int(0)
-    n = lib().hs_sparse_align_run(maxl, minl, iters, cur.h, ref.h, _p(pose), _p(log), 256, C.byref(n_log))
+def sparse_align_run(maxl, minl, iters, cur, ref, want_log=True):
+    pose = np.empty(7); log = np.zeros(256 if want_log else 0, ITER_LOG_DT); n_log = C.c_int(0)
+    n = lib().hs_sparse_align_run(maxl, minl, iters, cur.h, ref.h, _p(pose), _p(log) if want_log else None, 256 if want_log else 0, C.byref(n_log))
     if n < 0:
         raise RuntimeError(lib().hs_last_error().decode())
     return n, pose, log[:n_log.value].copy()

@@ -402,6 +402,22 @@ def test_update_local_map_selects_the_oracles_keyframes(built):
     first_id = np.concatenate([[0], np.cumsum([int((np.abs(t).sum(1) > 0).sum()) for t in tables])])
     owner = np.searchsorted(first_id, ids, side="right") - 1
     assert set(owner.tolist()) <= set(lo.tolist())
+    # the device path (dsdtm_store_track, default) against the literal host loop of the reference (one ReprojectPoint per map point,
+    # snapshot of the observations per candidate): same local key frames, same matches in the same order, same pixels, same levels
+    px_a, lv_a, _ = cur.features()
+    for i in ids:
+        L.hs_mappoint_increase_found(int(i), -1)                      # undo the first run's IncreaseFound: same sort keys for the second
+    L.hs_set_use_store(0)
+    try:
+        cur_b = HL.HFrame(cam_h, img, pose_cur)
+        m_b, local_b, nrep_b = HL.track_local_map(cam_h, cur_b)
+    finally:
+        L.hs_set_use_store(1)
+    px_b, lv_b, _ = cur_b.features()
+    assert m_b == m and nrep_b == nrep and (local_b == local).all()
+    assert (cur_b.mp_ids() == ids).all() and (lv_b == lv_a).all() and (px_b == px_a).all()
+    for i in ids:
+        L.hs_mappoint_increase_found(int(i), -1)
     # LocalBundleAdjustment moves the nearest key frame far away: its row is rewritten, it drops out of the ranking
     moved = kf_poses[2].copy(); moved[4:] += np.array([50.0, 0.0, 0.0])
     L.hs_keyframe_set_pose(kfs[2], HL._p(np.ascontiguousarray(moved)))
@@ -411,3 +427,50 @@ def test_update_local_map_selects_the_oracles_keyframes(built):
     kf_t2 = kf_t.copy(); kf_t2[2] = moved[4:]
     _, _, lo2 = O.close_keyframes(oc, pose_cur, pt_begin, pt_count, kf_t2, points)
     assert (local2 == lo2).all() and local2[-1] == 2 and m2 >= 100
+
+
+def test_run_and_update_local_map_as_one_submission_equal_the_separate_calls(built):
+    """Sprase_ImgAlign::Run also runs Tracking::UpdateLocalMap's device stage in the same submission (dsdtm_track_frame_store) and
+    Tracking::UpdateLocalMap takes the parked records: poses, tracked counts, local key frames, matches, pixels, levels and map-point
+    ids must be bit-equal to the two separate calls, frame after frame (the found counters evolve identically)."""
+    cam = dict(S.KINECT)
+    scene = S.Scene(77)
+    L = HL.lib()
+    kf_poses = [S.pose_from_xi(np.array([0.25 * k, 0.03 * (k % 3), 0.01 * k, 0.0, 0.01 * k, 0.0])) for k in range(4)]
+    cur_poses = [S.pose_mul(S.pose_from_xi(np.array([0.01 * (j + 1), -0.006, 0.004, 0.002, -0.002 * j, 0.001])), kf_poses[1]) for j in range(4)]
+    runs = []
+    for spec in (1, 0):
+        cam_h = HL.configure(cam, max_fts=300, max_frames=24, dist=(0.0, 0.0, 0.0, 0.0, 0.0))       # hs_reset inside: fresh map, fresh points
+        L.hs_set_speculate(spec)
+        try:
+            frames = []
+            for k, pose in enumerate(kf_poses):
+                img, _, pts = S.render(scene, cam, pose, want_points=True)
+                g = HL.HFrame(cam_h, img, pose)
+                n = g.detect(5.0)
+                px, _, _ = g.features()
+                g.attach_points(pts[px[:, 1].astype(int), px[:, 0].astype(int)], np.ones(n, np.uint8))
+                L.hs_map_add_keyframe(L.hs_keyframe_new(g.h))
+                frames.append(g)
+            g_last = frames[1]
+            rec = []
+            img0, _ = S.render(scene, cam, cur_poses[0])
+            warm = HL.HFrame(cam_h, img0, g_last.pose())
+            HL.track_local_map(cam_h, warm)                                # creates the Tracking object (registers the map) in both runs
+            for i in warm.mp_ids():
+                L.hs_mappoint_increase_found(int(i), -1)
+            for j, pose in enumerate(cur_poses):
+                img, _ = S.render(scene, cam, pose)
+                g_cur = HL.HFrame(cam_h, img, g_last.pose())
+                nt, pose_sa, _ = HL.sparse_align_run(5, 0, 8, g_cur, g_last, want_log=False)
+                m, local, nrep = HL.track_local_map(cam_h, g_cur)
+                px, lv, _ = g_cur.features()
+                rec.append((nt, pose_sa.copy(), m, local.copy(), nrep, px.copy(), lv.copy(), g_cur.mp_ids().copy()))
+                g_last = g_cur
+            runs.append(rec)
+        finally:
+            L.hs_set_speculate(1)
+    for a, b in zip(*runs):
+        assert a[0] == b[0] and (a[1] == b[1]).all() and a[2] == b[2] and (a[3] == b[3]).all() and a[4] == b[4]
+        assert (a[5] == b[5]).all() and (a[6] == b[6]).all() and (a[7] == b[7]).all()
+        assert a[2] >= 100 and a[0] >= 100
