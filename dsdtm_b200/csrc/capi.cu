@@ -448,6 +448,20 @@ int dsdtm_frame_upload_pyramid(dsdtm_ctx* c, int slot, const uint8_t* img, int s
     return 0;
 }
 
+int dsdtm_frame_upload_pyramid_async(dsdtm_ctx* c, int slot, const uint8_t* img, int stride)
+{
+    if (!c || !img) return DSDTM_E_ARG;
+    if (check_slot(c, slot)) return DSDTM_E_ARG;
+    const LevelGeom& g = c->geo;
+    if (stride < g.w[0]) return fail(c, DSDTM_E_ARG, "stride < width");
+    DSDTM_CUDA(c, cudaMemcpy2DAsync(c->frames_d + (size_t)slot * g.frame_stride, g.w[0], img, stride, g.w[0], g.h[0],
+                                    cudaMemcpyHostToDevice, c->stream));
+    stage_begin(c, DSDTM_STAGE_PYRAMID);
+    DSDTM_CUDA(c, launch_pyramid(c, slot, 1, c->stream));
+    stage_end(c, g.levels - 1);
+    return 0;
+}
+
 int dsdtm_frame_upload_pyramid_host(dsdtm_ctx* c, int slot, const uint8_t* img, int stride, uint8_t* levels_out)
 {
     if (!c || !img) return DSDTM_E_ARG;

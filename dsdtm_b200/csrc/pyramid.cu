@@ -261,107 +261,153 @@ __global__ void __launch_bounds__(1024) pyrdown_bulk_kernel(uint8_t* __restrict_
 
 // ---------------------------------------------------------------------------------------------------------------
 // Whole-level kernel for the SMALL ragged levels (752x480: 188x120 -> 94x60 -> 47x30, widths that are not multiples of 8): one CTA
-// stages an entire source level in shared memory (one contiguous, 16-byte aligned range of <= 22.6 KB), does the horizontal pass into
-// a u16 plane and the vertical pass from it -- 5 + 5 shared-memory reads per output -- and keeps its output in shared memory as the
-// source of the NEXT level, so the whole tail of the pyramid is one launch and one read of its first level. (The tile kernel's 64x16
-// tiles carry a 2.6x halo overhead at this size: 0.38 TB/s on these two levels = 45 % of the 752x480 pyramid's time.)
-// Warps walk rows, lanes walk column groups: no integer division in the loops.
+// stages an entire source level in shared memory and keeps every level it produces there as the source of the next one, so the whole
+// tail of the pyramid is one launch and one read of its first level. (The tile kernel's 64x16 tiles carry a 2.6x halo overhead at
+// this size: 0.38 TB/s on these two levels = 45 % of the 752x480 pyramid's time.)
+//   staging   one cp.async.bulk of the dense level (offsets are 16-byte aligned, the size is rounded up to 16 bytes into the slot's
+//             zero padding) when its rows are 4-byte aligned (w % 4 == 0); byte loads into a 4-byte pitch otherwise
+//   borders   only the LAST group of four output columns of a row touches columns >= w. Its 16 source bytes (columns c0 - 4 ..
+//             c0 + 11, reflect-101 applied) are gathered once per row into an edge table; the thread that owns the last group reads the
+//             table instead of the plane -- same instructions, different address, no divergence, no edge arithmetic in the loop
+//   work      a thread owns one group of four output columns and a strip of output rows: the bulk kernel's register window
+//             (4 LDS.32 + 4 DP4A per source row, vertical pass on packed u16 pairs). Round 1's warp-per-row separable form spent
+//             33.9 k warp instructions per 752x480 frame on loop and index overhead for 8.5 k sums (94.6 us per 2048 frames, 6 % of
+//             the pyramid's bytes in 35 % of its time: profiles/r1_euroc_sweep.md).
 constexpr int SMALL_THREADS = 256;
 constexpr int SMALL_SMEM_LIMIT = 96 * 1024;
-constexpr int SMALL_FP = 8;                  // bytes in front of column 0 of a staged row (columns -2, -1 live there)
-// A staged plane keeps every row at an 8-byte aligned pitch with the reflect-101 border MATERIALISED (columns -2, -1 and
-// w .. w + 10), so that every group of four outputs is the interior formula of the bulk kernel -- one aligned LDS.64 + two LDS.32 +
-// four DP4A -- whatever the width: no edge cases, no byte-wide arithmetic (the first version did 5 LDS.U8 + 4 multiply-adds per
-// sum and was issue-bound: 116 us per 2048 frames for 6 % of the pyramid's bytes).
-__host__ __device__ constexpr int small_pitch(int w) { return (SMALL_FP + w + 11 + 7) & ~7; }
+constexpr int SMALL_PAD = 16;                // bytes in front of / behind every plane (group 0 reads one word in front, the last rows a few bytes behind)
+__host__ __device__ constexpr int small_pitch(int w) { return (w + 3) & ~3; }
 
 struct SmallChain {
     int n;                                   // levels produced by this launch
     int w[DSDTM_MAX_LEVELS], h[DSDTM_MAX_LEVELS];      // [0] = the staged source level, [i + 1] = the i-th produced level
     unsigned off[DSDTM_MAX_LEVELS];
-    int a_bytes, h_bytes;                    // shared-memory plan: plane A | packed horizontal sums | plane B
+    int a_bytes, b_bytes, e_bytes;           // shared-memory plan: pad | plane A | pad | plane B | pad | edge table | mbarrier
 };
 
-__device__ __forceinline__ void small_fill_border(uint8_t* plane, int w, int h, int pitch, int warp, int lane)
+__device__ __forceinline__ uint2 hrow_e(const uint8_t* p, bool left)
 {
-    // columns -2, -1 <- 2, 1 ; columns w + k <- reflect101(w + k), k = 0 .. 10
-    for (int r = warp; r < h; r += SMALL_THREADS / 32) {
-        uint8_t* row = plane + r * pitch + SMALL_FP;
-        if (lane < 13) {
-            const int col = lane < 2 ? lane - 2 : w + (lane - 2);
-            row[col] = row[reflect101(col, w)];
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(p), w1 = *reinterpret_cast<const uint32_t*>(p + 4);
+    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(p + 8);
+    uint32_t wm1 = *reinterpret_cast<const uint32_t*>(p - 4);
+    if (left) wm1 = __byte_perm(w0, 0, 0x1200);          // reflect-101: cols -2, -1 -> 2, 1
+    const uint32_t K = 0x04060401u;
+    const uint32_t h0 = __dp4a(__byte_perm(wm1, w0, 0x5432), K, __byte_perm(w0, 0, 0x4442));
+    const uint32_t h1 = __dp4a(w0, K, __byte_perm(w1, 0, 0x4440));
+    const uint32_t h2 = __dp4a(__byte_perm(w0, w1, 0x5432), K, __byte_perm(w1, 0, 0x4442));
+    const uint32_t h3 = __dp4a(w1, K, __byte_perm(w2, 0, 0x4440));
+    return make_uint2(__byte_perm(h0, h1, 0x5410), __byte_perm(h2, h3, 0x5410));
+}
+
+// edge[r] = columns c0 - 4 .. c0 + 11 of row r, reflect-101 applied (columns the sums never use are clamped into the row)
+__device__ __forceinline__ void small_fill_edge(uint32_t* edge, const uint8_t* plane, int pitch, int w, int h, int c0, int tid)
+{
+    for (int i = tid; i < 4 * h; i += SMALL_THREADS) {
+        const uint8_t* row = plane + (i >> 2) * pitch;
+        const int col0 = c0 - 4 + 4 * (i & 3);
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int col = col0 + b;
+            col = col < 0 ? -col : col;
+            col = col >= w ? 2 * w - 2 - col : col;
+            col = min(max(col, 0), w - 1);
+            v |= (uint32_t)row[col] << (8 * b);
         }
+        edge[i] = v;
     }
 }
 
 __global__ void __launch_bounds__(SMALL_THREADS) pyrdown_small_kernel(uint8_t* __restrict__ frames, unsigned frame_stride, int first_slot,
                                                                       const int* __restrict__ slots, const SmallChain ch)
 {
-    extern __shared__ __align__(16) uint8_t s_small[];
-    uint8_t* s_a = s_small;
-    uint2* s_h = reinterpret_cast<uint2*>(s_small + ch.a_bytes);
-    uint8_t* s_b = s_small + ch.a_bytes + ch.h_bytes;
+    extern __shared__ __align__(128) uint8_t s_small[];
+    uint8_t* s_a = s_small + SMALL_PAD;
+    uint8_t* s_b = s_a + ch.a_bytes + SMALL_PAD;
+    uint32_t* s_e = reinterpret_cast<uint32_t*>(s_b + ch.b_bytes + SMALL_PAD);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(s_e) + ch.e_bytes);
     const int slot = slots ? slots[blockIdx.x] : first_slot + blockIdx.x;
     uint8_t* __restrict__ frame = frames + (size_t)slot * frame_stride;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = SMALL_THREADS / 32;
+    const int tid = threadIdx.x;
+    int pitch;                                                           // of the plane that holds the current source level
     {
-        const int w = ch.w[0], h = ch.h[0], pitch = small_pitch(w);
+        const int w = ch.w[0], h = ch.h[0];
         const uint8_t* __restrict__ src = frame + ch.off[0];
-        if ((w & 3) == 0) {                                              // rows start on 4-byte boundaries on both sides
-            for (int r = warp; r < h; r += NW)
-                for (int j = lane; j < (w >> 2); j += 32)
-                    *reinterpret_cast<uint32_t*>(s_a + r * pitch + SMALL_FP + 4 * j) = __ldg(reinterpret_cast<const uint32_t*>(src + r * w) + j);
+        if ((w & 3) == 0) {
+            pitch = w;
+            const uint32_t bytes = ((uint32_t)w * (uint32_t)h + 15u) & ~15u;
+            if (tid == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_bar)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(s_a)), "l"(src), "r"(bytes), "r"(smem_u32(s_bar)) : "memory");
+            }
+            uint32_t done = 0;
+            int spins = 0;
+            while (!done) {
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(smem_u32(s_bar)) : "memory");
+                if (!done && ++spins > (1 << 22)) __trap();              // a lost copy must not hang the GPU
+            }
         } else {
-            for (int r = warp; r < h; r += NW)
-                for (int j = lane; j < w; j += 32) s_a[r * pitch + SMALL_FP + j] = __ldg(src + r * w + j);
+            pitch = small_pitch(w);
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int r = warp; r < h; r += SMALL_THREADS / 32)
+                for (int j = lane; j < w; j += 32) s_a[r * pitch + j] = __ldg(src + r * w + j);
+            __syncthreads();
         }
-        __syncthreads();
-        small_fill_border(s_a, w, h, pitch, warp, lane);
-        __syncthreads();
     }
     uint8_t* cur = s_a;
     uint8_t* nxt = s_b;
     for (int l = 0; l < ch.n; ++l) {
         const int w = ch.w[l], h = ch.h[l], dw = ch.w[l + 1], dh = ch.h[l + 1];
-        const int pitch = small_pitch(w), G = (dw + 3) >> 2;             // G groups of four outputs per row
-        for (int r = warp; r < h; r += NW) {
-            const uint8_t* row = cur + r * pitch + SMALL_FP;
-            for (int g = lane; g < G; g += 32) s_h[r * G + g] = hrow_s(row, 8 * g, false, false);
-        }
+        const int G = (dw + 3) >> 2;                                     // groups of four outputs per row
+        small_fill_edge(s_e, cur, pitch, w, h, 8 * (G - 1), tid);
         __syncthreads();
+        const int lanes = SMALL_THREADS / G;                             // strips that fit one pass of the CTA (0: more groups than threads)
+        const int rpt = lanes > 0 ? (dh + lanes - 1) / lanes : dh;       // output rows per thread
+        const int strips = (dh + rpt - 1) / rpt;
         uint8_t* __restrict__ dst = frame + ch.off[l + 1];
         const bool keep = l + 1 < ch.n;
         const int npitch = small_pitch(dw);
-        for (int y = warp; y < dh; y += NW) {
-            const int r = 2 * y;
-            const uint2* p0 = s_h + reflect101(r - 2, h) * G;
-            const uint2* p1 = s_h + reflect101(r - 1, h) * G;
-            const uint2* p2 = s_h + r * G;
-            const uint2* p3 = s_h + reflect101(r + 1, h) * G;
-            const uint2* p4 = s_h + reflect101(r + 2, h) * G;
-            for (int g = lane; g < G; g += 32) {
-                const uint2 r0 = p0[g], r1 = p1[g], r2 = p2[g], r3 = p3[g], r4 = p4[g];
+        for (int u = tid; u < G * strips; u += SMALL_THREADS) {
+            const int strip = u / G, g = u - strip * G;
+            const int y0 = strip * rpt, y1 = min(y0 + rpt, dh);
+            const bool last = g == G - 1, left = g == 0 && !last;
+            const uint8_t* base = last ? reinterpret_cast<const uint8_t*>(s_e) + 4 : cur + 8 * g;     // column c0 of row 0
+            const int stride = last ? 16 : pitch;
+            uint2 r0 = hrow_e(base + reflect_row(2 * y0 - 2, h) * stride, left);
+            uint2 r1 = hrow_e(base + reflect_row(2 * y0 - 1, h) * stride, left);
+            uint2 r2 = hrow_e(base + (2 * y0) * stride, left);
+            const int x = 4 * g;
+            for (int y = y0; y < y1; ++y) {
+                const uint2 r3 = hrow_e(base + reflect_row(2 * y + 1, h) * stride, left);
+                const uint2 r4 = hrow_e(base + reflect_row(2 * y + 2, h) * stride, left);
                 const uint32_t a = r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + 0x00800080u;
                 const uint32_t b = r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + 0x00800080u;
                 const uint32_t out = __byte_perm(a, b, 0x7531);
-                const int x = 4 * g;
+                uint8_t* o = dst + y * dw + x;
                 if ((dw & 3) == 0) {
-                    *reinterpret_cast<uint32_t*>(dst + y * dw + x) = out;
+                    *reinterpret_cast<uint32_t*>(o) = out;
+                } else if ((dw & 1) == 0) {                              // rows start on 2-byte boundaries; x + 1 < dw whenever x < dw
+                    *reinterpret_cast<uint16_t*>(o) = (uint16_t)out;
+                    if (x + 2 < dw) *reinterpret_cast<uint16_t*>(o + 2) = (uint16_t)(out >> 16);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (x + k < dw) dst[y * dw + x + k] = (uint8_t)(out >> (8 * k));
+                        if (x + k < dw) o[k] = (uint8_t)(out >> (8 * k));
                 }
-                if (keep) *reinterpret_cast<uint32_t*>(nxt + y * npitch + SMALL_FP + x) = out;   // columns >= dw are rewritten by the border fill
+                if (keep) *reinterpret_cast<uint32_t*>(nxt + y * npitch + x) = out;   // columns >= dw of the last group are never read as data
+                r0 = r2; r1 = r3; r2 = r4;
             }
         }
         __syncthreads();
-        if (keep) {
-            small_fill_border(nxt, dw, dh, npitch, warp, lane);
-            __syncthreads();
-        }
         uint8_t* t = cur; cur = nxt; nxt = t;      // the produced level is the next source
+        pitch = npitch;
     }
 }
 
@@ -372,10 +418,10 @@ int plan_small_chain(const LevelGeom& g, int first, SmallChain& ch, size_t& smem
     if (h0 < 3 || w0 < 3) return 0;
     ch.n = 0;
     ch.w[0] = w0; ch.h[0] = h0; ch.off[0] = g.off[first - 1];
-    ch.a_bytes = (h0 * small_pitch(w0) + 15) & ~15;                     // every later plane that lands here is smaller
-    ch.h_bytes = (h0 * ((g.w[first] + 3) >> 2) * 8 + 15) & ~15;
-    const int b_bytes = (g.h[first] * small_pitch(g.w[first]) + 15) & ~15;
-    smem = (size_t)ch.a_bytes + ch.h_bytes + b_bytes;
+    ch.a_bytes = (h0 * small_pitch(w0) + 15) & ~15;                     // the bulk copy's rounded-up size fits; every later plane that lands here is smaller
+    ch.b_bytes = (g.h[first] * small_pitch(g.w[first]) + 15) & ~15;
+    ch.e_bytes = 16 * h0;
+    smem = (size_t)3 * SMALL_PAD + ch.a_bytes + ch.b_bytes + ch.e_bytes + 16;
     if (smem > (size_t)SMALL_SMEM_LIMIT) return 0;
     for (int l = first; l < g.levels; ++l) {
         if (g.h[l - 1] < 3 || g.w[l - 1] < 3) break;

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <unordered_map>
+#include <mutex>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -83,15 +85,42 @@ SE3 SE3::exp(const double x[6])
     return r;
 }
 
+// Image-sized buffers are recycled: a fresh 300 KB allocation per mask per frame is an mmap plus ~75 page faults (about 20 us each
+// time), which the per-frame constructors would pay three times over.
+namespace {
+struct BufPool {
+    std::mutex m;
+    std::unordered_map<size_t, std::vector<std::vector<uchar>*>> idle;
+    static BufPool& get() { static BufPool* p = new BufPool; return *p; }     // never destroyed: buffers may outlive static teardown
+    std::shared_ptr<std::vector<uchar>> take(size_t n)
+    {
+        std::vector<uchar>* v = nullptr;
+        if (n >= 4096) {
+            std::lock_guard<std::mutex> g(m);
+            auto& l = idle[n];
+            if (!l.empty()) { v = l.back(); l.pop_back(); }
+        }
+        if (!v) v = new std::vector<uchar>(n);
+        return std::shared_ptr<std::vector<uchar>>(v, [n](std::vector<uchar>* q) {
+            BufPool& p = BufPool::get();
+            std::lock_guard<std::mutex> g(p.m);
+            auto& l = p.idle[n];
+            if (n >= 4096 && l.size() < 16) l.push_back(q); else delete q;
+        });
+    }
+};
+}  // namespace
+
 Mat8::Mat8(int rows_, int cols_, uchar fill) : rows(rows_), cols(cols_), step(cols_)
 {
-    store = std::make_shared<std::vector<uchar>>((size_t)rows * cols, fill);
+    store = BufPool::get().take((size_t)rows * cols);
     data = store->data();
+    std::memset(data, fill, (size_t)rows * cols);
 }
 
 Mat8::Mat8(int rows_, int cols_, const uchar* src, int src_step) : rows(rows_), cols(cols_), step(cols_)
 {
-    store = std::make_shared<std::vector<uchar>>((size_t)rows * cols);
+    store = BufPool::get().take((size_t)rows * cols);
     data = store->data();
     for (int y = 0; y < rows; ++y) std::memcpy(data + (size_t)y * cols, src + (size_t)y * src_step, cols);
 }
@@ -234,8 +263,10 @@ std::shared_ptr<GpuSlot> GpuRuntime::Upload(const Mat8& img, uint8_t* levels_out
 {
     auto s = std::make_shared<GpuSlot>(img);
     s->slot = Acquire(s.get());
-    if (dsdtm_frame_upload_pyramid_host(mCtx, s->slot, s->host.data, s->host.step, levels_out) != 0)
-        throw std::runtime_error(std::string("dsdtm_frame_upload_pyramid_host: ") + dsdtm_last_error(mCtx));
+    // no host copies wanted: queue the copy + pyramid and return; every later call on the context is ordered after them
+    const int rc = levels_out ? dsdtm_frame_upload_pyramid_host(mCtx, s->slot, s->host.data, s->host.step, levels_out)
+                              : dsdtm_frame_upload_pyramid_async(mCtx, s->slot, s->host.data, s->host.step);
+    if (rc != 0) throw std::runtime_error(std::string("dsdtm_frame_upload_pyramid: ") + dsdtm_last_error(mCtx));
     return s;
 }
 
@@ -275,23 +306,31 @@ Frame::Frame(CameraPtr cam, const Mat8& gray, double ts) : mCamera(cam), mdCloTi
 
 Frame::~Frame() { if (g_runtime && g_runtime->DepthOwner() == this) g_runtime->SetDepthOwner(nullptr); }
 
-void Frame::ComputeImagePyramid(const Mat8 image, std::vector<Mat8>& pyr)   // ref: src/Frame.cpp:74-81
+void Frame::ComputeImagePyramid(const Mat8 image, PyrLevels& pyr)   // ref: src/Frame.cpp:74-81
 {
     GpuRuntime& rt = GpuRuntime::Instance();
-    pyr[0] = image;                                               // level 0 aliases the caller's image
-    // H2D + pyrDown chain on the device; the host copies of levels 1.. (mvImg_Pyr stays usable by code outside the hot path:
-    // viewer, depth lookup -- the GPU stages never read them) come back in the same synchronisation
-    const int L = (int)pyr.size();
-    std::vector<uint8_t> tail;
-    std::vector<size_t> off(L, 0);
-    std::vector<int> lw(L, 0), lh(L, 0);
-    for (int l = 0; l < L; ++l) dsdtm_level_info(rt.ctx(), l, &lw[l], &lh[l], &off[l]);
-    if (L > 1) tail.resize(off[L - 1] + (size_t)lw[L - 1] * lh[L - 1] - off[1]);
-    mGpu = rt.Upload(image, tail.empty() ? nullptr : tail.data());
-    for (int l = 1; l < L; ++l) {
-        pyr[l] = Mat8(lh[l], lw[l], 0);
-        std::memcpy(pyr[l].data, tail.data() + (off[l] - off[1]), (size_t)lw[l] * lh[l]);
-    }
+    pyr.Set(0, image);                                            // level 0 aliases the caller's image
+    // H2D + pyrDown chain on the device. The GPU stages never read host copies of levels 1..; mvImg_Pyr[l] fetches one on first use.
+    mGpu = rt.Upload(image);
+    pyr.Bind(mGpu);
+}
+
+void PyrLevels::Bind(const std::shared_ptr<GpuSlot>& g)
+{
+    gpu = g;
+    for (size_t l = 1; l < m.size(); ++l) pending[l] = 1;
+}
+
+void PyrLevels::Fetch(size_t l) const
+{
+    GpuRuntime& rt = GpuRuntime::Instance();
+    int w = 0, h = 0; size_t off = 0;
+    dsdtm_level_info(rt.ctx(), (int)l, &w, &h, &off);
+    Mat8 img(h, w, 0);
+    const int slot = rt.Resident(gpu);                            // re-uploads and rebuilds the pyramid if the slot was recycled
+    if (dsdtm_frame_download_level(rt.ctx(), slot, (int)l, img.data) != 0)
+        throw std::runtime_error(std::string("dsdtm_frame_download_level: ") + dsdtm_last_error(rt.ctx()));
+    m[l] = img; pending[l] = 0;
 }
 
 void Frame::Add_Feature(Feature* f, bool normal)                  // ref: src/Frame.cpp:83-92

@@ -96,6 +96,26 @@ private:
     std::shared_ptr<std::vector<uchar>> store;
 };
 
+class GpuSlot;
+// Stands in for std::vector<cv::Mat> mvImg_Pyr (ref: include/Frame.h:113). Level 0 is the caller's image; levels 1.. are built on the
+// device and only the device stages read them, so their host copies are fetched from HBM on the FIRST read of mvImg_Pyr[l] (viewer,
+// debugging) instead of in every Frame constructor.
+class PyrLevels {
+public:
+    size_t size() const { return m.size(); }
+    void resize(size_t n) { m.resize(n); pending.assign(n, 0); }
+    Mat8& operator[](size_t l) { if (pending[l]) Fetch(l); return m[l]; }
+    const Mat8& operator[](size_t l) const { if (pending[l]) Fetch(l); return m[l]; }
+    void Set(size_t l, const Mat8& img) { m[l] = img; pending[l] = 0; }
+    void Bind(const std::shared_ptr<GpuSlot>& gpu);             // levels 1.. now live in that slot's pyramid: host copies on demand
+    bool Pending(size_t l) const { return pending[l] != 0; }
+private:
+    void Fetch(size_t l) const;
+    mutable std::vector<Mat8> m;
+    mutable std::vector<char> pending;
+    std::shared_ptr<GpuSlot> gpu;
+};
+
 int cvRound(double v);                                       // round-half-to-even like OpenCV on x86
 void circle(Mat8& img, Point2f center, int radius, uchar color);   // cv::circle(img, c, r, color, -1)
 
@@ -185,7 +205,7 @@ class Frame {   // ref: include/Frame.h:18-136, src/Frame.cpp:48-92,167-174,286-
 public:
     Frame(CameraPtr cam, const Mat8& gray, double timestamp = 0);
     virtual ~Frame();
-    void ComputeImagePyramid(const Mat8 image, std::vector<Mat8>& pyr);      // GPU: dsdtm_frame_upload_pyramid
+    void ComputeImagePyramid(const Mat8 image, PyrLevels& pyr);              // GPU: dsdtm_frame_upload_pyramid
     void Add_Feature(Feature* f, bool normal = true);
     void Add_MapPoint(MapPoint* mp) { mvMapPoints.push_back(mp); }
     void Set_Pose(const SE3& pose);
@@ -206,7 +226,7 @@ public:
     static unsigned long mlNextId;
     double mdCloTimestamp;
     Mat8 mColorImg;
-    std::vector<Mat8> mvImg_Pyr;
+    PyrLevels mvImg_Pyr;
     Features mvFeatures;
     std::vector<MapPoint*> mvMapPoints;
     Mat8 mImgMask, mDynamicMask;
@@ -227,7 +247,7 @@ public:
     SE3 Get_Pose() const { return mT_c2w; }
     void Set_Pose(const SE3& p);
     Vector3d Get_CameraCnt() const { return mOw; }
-    std::vector<Mat8> mvImg_Pyr;
+    PyrLevels mvImg_Pyr;
     Features mvFeatures;
     std::shared_ptr<GpuSlot> mGpu;
     // position of this key frame in the table of the snapshot being built (valid while mSnapEpoch == the snapshot's number)

@@ -124,6 +124,11 @@ int dsdtm_frame_upload_pyramid(dsdtm_ctx* ctx, int slot, const uint8_t* img, int
  * mvImg_Pyr) in the SAME synchronisation: levels_out receives dsdtm_frame_stride() - level-1-offset bytes laid out like the
  * slot (level l at dsdtm_level_info offset[l] - offset[1], dense rows). levels_out may be NULL. */
 int dsdtm_frame_upload_pyramid_host(dsdtm_ctx* ctx, int slot, const uint8_t* img, int stride, uint8_t* levels_out);
+/* dsdtm_frame_upload_pyramid without the closing synchronisation: the copy and the pyramid kernels are queued on the context's
+ * stream, where every later call on this context is ordered after them. For pageable `img` (any ordinary host buffer) the call
+ * returns once the image has left the caller's buffer; a page-locked `img` must stay unmodified until the next synchronising call
+ * (dsdtm_sync or any call that returns results). Errors of the queued work surface at that call. */
+int dsdtm_frame_upload_pyramid_async(dsdtm_ctx* ctx, int slot, const uint8_t* img, int stride);
 /* batched: n dense (stride == width) images into slots first_slot .. first_slot+n-1 */
 int dsdtm_frames_upload_pyramid(dsdtm_ctx* ctx, int first_slot, int n, const uint8_t* imgs);
 /* device-resident variant: level 0 of the n slots is already in HBM (e.g. written by a previous upload); rebuild levels */

@@ -339,3 +339,20 @@ def test_optimizer_pose_optimization_after_search_local_points(built, scenario):
     found_after = np.array([L.hs_mappoint_found(int(i)) for i in ids])
     assert (found_after == expect).all()
     assert 0 < (expect != found_before).sum() < nb            # the threshold splits the matches: both branches ran
+
+
+@pytest.mark.gpu
+def test_pyramid_levels_are_fetched_on_first_read_even_after_the_slot_was_recycled(built, scenario):   # last: it re-configures the runtime
+    """mvImg_Pyr[l] (l >= 1) is a lazy host copy: nothing is downloaded in the constructor; a read after the frame's slot went
+    to another frame re-uploads level 0, rebuilds the pyramid and returns the same bytes (ref: src/Frame.cpp:74-81)."""
+    cam_h = HL.configure(scenario["cam"], max_fts=300, max_frames=4)
+    first = HL.HFrame(cam_h, scenario["ref_img"], scenario["T_ref"])
+    others = [HL.HFrame(cam_h, scenario["cur_img"], scenario["T_ref"]) for _ in range(6)]     # 6 > 4 slots: `first` is evicted
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    for l in (4, 1, 3, 2, 0):
+        want = O.pyr_level(packed, offs, ws, hs, l)
+        assert (first.level(l, want.shape) == want).all(), l
+    packed, offs, ws, hs = scenario["cur_pyr"]
+    for l in range(5):
+        want = O.pyr_level(packed, offs, ws, hs, l)
+        assert (others[-1].level(l, want.shape) == want).all(), l
