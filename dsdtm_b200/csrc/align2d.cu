@@ -197,45 +197,83 @@ struct WaArgs {
     const int* n_dev;      // optional device-side count of valid entries
 };
 
-__global__ void __launch_bounds__(256) warp_affine_kernel(const WaArgs a)
+// A CTA owns WA_PPC consecutive candidates = WA_PPC * 100 consecutive output bytes. One lane per candidate derives the per-patch
+// constants (the fp64 2x2 inverse with its division used to run on all 32 lanes of a warp per patch: a third of the kernel's
+// instructions); then 320 threads walk the 1600 samples in 5 full rounds (a warp per patch left 100 samples on 32 lanes = 4 rounds at
+// 78 % of the lanes). A thread keeps its patch column and steps two patch rows per round, so the loop has no division.
+constexpr int WA_PPC = 16;
+constexpr int WA_THREADS = 320;
+
+__global__ void __launch_bounds__(WA_THREADS) warp_affine_kernel(const WaArgs a)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = a.i0 + blockIdx.x * 8 + warp;
-    if (i >= a.i0 + (a.n_dev ? min(a.n, *a.n_dev) : a.n)) return;
-    const int slot = a.meta[3 * i], rl = a.meta[3 * i + 1], sl = a.meta[3 * i + 2];
-    if (slot < 0) return;                                           // candidate skipped by candidate_prep_kernel
-    const double A00 = a.A[4 * i], A01 = a.A[4 * i + 1], A10 = a.A[4 * i + 2], A11 = a.A[4 * i + 3];
-    // Eigen 2x2 inverse in double, then cast<float>() (ref: :211)
-    const double det = __dsub_rn(__dmul_rn(A00, A11), __dmul_rn(A10, A01));
-    const double invdet = __ddiv_rn(1.0, det);
-    const float a00 = (float)__dmul_rn(A11, invdet), a01 = (float)__dmul_rn(-A01, invdet);
-    const float a10 = (float)__dmul_rn(-A10, invdet), a11 = (float)__dmul_rn(A00, invdet);
-    const float rx = __fdiv_rn(a.ref_px[2 * i], (float)(1 << rl)), ry = __fdiv_rn(a.ref_px[2 * i + 1], (float)(1 << rl));   // ref: :215-216
-    const float kf = (float)(1 / (1 << sl));                                                                                 // ref: :231 (Q3)
-    const int w = a.geo.w[rl], h = a.geo.h[rl];
-    const uint8_t* __restrict__ img = a.frames + (size_t)slot * a.frame_stride + a.geo.off[rl];
-    for (int j = lane; j < 100; j += 32) {
-        const float gx = (float)(j % 10 - 5), gy = (float)(j / 10 - 5);
-        float wx = __fmul_rn(__fadd_rn(__fmul_rn(a00, gx), __fmul_rn(a01, gy)), kf);
-        float wy = __fmul_rn(__fadd_rn(__fmul_rn(a10, gx), __fmul_rn(a11, gy)), kf);
-        wx = __fadd_rn(wx, rx); wy = __fadd_rn(wy, ry);
-        uint8_t o = 0;
-        if (!(wx < 0 || wy < 0 || wx > (float)(w - 1) || wy > (float)(h - 1))) {       // ref: :249
-            const int fx = (int)floor((double)wx), fy = (int)floor((double)wy);
-            const float sx = __fsub_rn(wx, (float)fx), sy = __fsub_rn(wy, (float)fy);
-            const float ox = __fsub_rn(1.0f, sx), oy = __fsub_rn(1.0f, sy);
-            const float W00 = __fmul_rn(ox, oy), W01 = __fmul_rn(ox, sy), W10 = __fmul_rn(sx, oy);
-            const float W11 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, W00), W01), W10);      // ref: :244
-            const bool xin = fx + 1 < w, yin = fy + 1 < h;
-            const int p00 = __ldg(img + (size_t)fy * w + fx);
-            const int p01 = yin ? __ldg(img + (size_t)(fy + 1) * w + fx) : 0;
-            const int p10 = xin ? __ldg(img + (size_t)fy * w + fx + 1) : 0;
-            const int p11 = (xin && yin) ? __ldg(img + (size_t)(fy + 1) * w + fx + 1) : 0;
-            const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(W00, (float)p00), __fmul_rn(W01, (float)p01)), __fmul_rn(W10, (float)p10)),
-                                      __fmul_rn(W11, (float)p11));                                                               // ref: :254-255
-            o = (uint8_t)(int)v;   // truncating store
+    __shared__ float s_f[WA_PPC][8];            // a00 a01 a10 a11 rx ry kf
+    __shared__ int s_i[WA_PPC][4];              // w, h, valid
+    __shared__ const uint8_t* s_img[WA_PPC];
+    const int tid = threadIdx.x;
+    const int first = a.i0 + blockIdx.x * WA_PPC;
+    const int end = a.i0 + (a.n_dev ? min(a.n, *a.n_dev) : a.n);
+    if (first >= end) return;
+    if (tid < WA_PPC) {
+        const int i = first + tid;
+        int valid = 0;
+        if (i < end) {
+            const int slot = a.meta[3 * i], rl = a.meta[3 * i + 1], sl = a.meta[3 * i + 2];
+            if (slot >= 0) {                                        // else: candidate skipped by candidate_prep_kernel
+                valid = 1;
+                const double A00 = a.A[4 * i], A01 = a.A[4 * i + 1], A10 = a.A[4 * i + 2], A11 = a.A[4 * i + 3];
+                // Eigen 2x2 inverse in double, then cast<float>() (ref: :211)
+                const double det = __dsub_rn(__dmul_rn(A00, A11), __dmul_rn(A10, A01));
+                const double invdet = __ddiv_rn(1.0, det);
+                s_f[tid][0] = (float)__dmul_rn(A11, invdet); s_f[tid][1] = (float)__dmul_rn(-A01, invdet);
+                s_f[tid][2] = (float)__dmul_rn(-A10, invdet); s_f[tid][3] = (float)__dmul_rn(A00, invdet);
+                s_f[tid][4] = __fdiv_rn(a.ref_px[2 * i], (float)(1 << rl));                    // ref: :215-216
+                s_f[tid][5] = __fdiv_rn(a.ref_px[2 * i + 1], (float)(1 << rl));
+                s_f[tid][6] = (float)(1 / (1 << sl));                                          // ref: :231 (Q3)
+                s_i[tid][0] = a.geo.w[rl]; s_i[tid][1] = a.geo.h[rl];
+                s_img[tid] = a.frames + (size_t)slot * a.frame_stride + a.geo.off[rl];
+            }
         }
-        a.out[(size_t)i * 100 + j] = o;
+        s_i[tid][2] = valid;
+    }
+    __syncthreads();
+    // sample s = tid + 320 k: patch s / 100, row (s % 100) / 10, column s % 10; 320 = 3 patches + 2 rows
+    int p = tid / 100;
+    const int j0 = tid - p * 100;
+    int row = j0 / 10;
+    const int col = j0 - row * 10;
+    const float gx = (float)(col - 5);
+    uint8_t* __restrict__ out = a.out + (size_t)first * 100 + tid;
+#pragma unroll
+    for (int k = 0; k < WA_PPC * 100 / WA_THREADS; ++k) {
+        if (s_i[p][2]) {
+            const float a00 = s_f[p][0], a01 = s_f[p][1], a10 = s_f[p][2], a11 = s_f[p][3], kf = s_f[p][6];
+            const int w = s_i[p][0], h = s_i[p][1];
+            const uint8_t* __restrict__ img = s_img[p];
+            const float gy = (float)(row - 5);
+            float wx = __fmul_rn(__fadd_rn(__fmul_rn(a00, gx), __fmul_rn(a01, gy)), kf);
+            float wy = __fmul_rn(__fadd_rn(__fmul_rn(a10, gx), __fmul_rn(a11, gy)), kf);
+            wx = __fadd_rn(wx, s_f[p][4]); wy = __fadd_rn(wy, s_f[p][5]);
+            uint8_t o = 0;
+            if (!(wx < 0 || wy < 0 || wx > (float)(w - 1) || wy > (float)(h - 1))) {       // ref: :249
+                const int fx = __float2int_rd(wx), fy = __float2int_rd(wy);                // floor(): exact in either precision
+                const float sx = __fsub_rn(wx, (float)fx), sy = __fsub_rn(wy, (float)fy);
+                const float ox = __fsub_rn(1.0f, sx), oy = __fsub_rn(1.0f, sy);
+                const float W00 = __fmul_rn(ox, oy), W01 = __fmul_rn(ox, sy), W10 = __fmul_rn(sx, oy);
+                const float W11 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, W00), W01), W10);      // ref: :244
+                const bool xin = fx + 1 < w, yin = fy + 1 < h;
+                const uint8_t* q = img + fy * w + fx;
+                const int p00 = __ldg(q);
+                const int p01 = yin ? __ldg(q + w) : 0;
+                const int p10 = xin ? __ldg(q + 1) : 0;
+                const int p11 = (xin && yin) ? __ldg(q + w + 1) : 0;
+                const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(W00, (float)p00), __fmul_rn(W01, (float)p01)), __fmul_rn(W10, (float)p10)),
+                                          __fmul_rn(W11, (float)p11));                                                               // ref: :254-255
+                o = (uint8_t)(int)v;   // truncating store
+            }
+            out[k * WA_THREADS] = o;
+        }
+        p += 3; row += 2;
+        if (row >= 10) { row -= 10; ++p; }
     }
 }
 
@@ -284,7 +322,7 @@ cudaError_t launch_warp_affine(dsdtm_ctx* c, int n, uint8_t* out_d, cudaStream_t
     a.i0 = i0; a.n_dev = n_dev;
     a.frames = c->frames_d; a.frame_stride = c->geo.frame_stride; a.geo = c->geo;
     a.A = c->wa_A_d; a.ref_px = c->wa_px_d; a.meta = c->wa_meta_d; a.out = out_d; a.n = n;
-    warp_affine_kernel<<<(n + 7) / 8, 256, 0, s>>>(a);
+    warp_affine_kernel<<<(n + WA_PPC - 1) / WA_PPC, WA_THREADS, 0, s>>>(a);
     c->launches++;
     return cudaGetLastError();
 }

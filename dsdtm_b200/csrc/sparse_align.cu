@@ -23,6 +23,8 @@
 //     identical in all lanes), WPP > 1 adds one shared-memory row per warp summed in warp order => deterministic;
 //   * lane 0 solves the 6x6 system with Eigen's pivoted LDL^T entirely in registers (se3_ldlt.cuh), applies SE3::exp and
 //     the reference's accept / revert / converge rules, and publishes the pose through shared memory.
+#include <algorithm>
+#include <mutex>
 #include "ctx.cuh"
 #include <type_traits>
 
@@ -880,13 +882,19 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
 {
     const int nf = round_nf(c->prm.max_feats);
     const int bytes = smem_bytes(nf);
-    cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    // the attribute belongs to the kernel, not to the context: several contexts in one process (different max_feats) must only ever
+    // RAISE it, or the context with the larger feature table fails its next launch with "invalid argument"
+    static std::mutex attr_mutex;
+    static int attr_bytes = 0, attr_bytes_ws = 0;
+    std::lock_guard<std::mutex> attr_lock(attr_mutex);
+    attr_bytes = std::max(attr_bytes, bytes);
+    cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_bytes);
 #ifdef DSDTM_SA_CARVEOUT
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, DSDTM_SA_CARVEOUT);
 #endif
@@ -898,7 +906,7 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sparse_align_kernel<10>, 320, bytes) == cudaSuccess) c->sa_ctas_per_sm[10] = n;
         (void)cudaGetLastError();
     }
-    const int bw = smem_bytes_ws(nf);
+    const int bw = attr_bytes_ws = std::max(attr_bytes_ws, smem_bytes_ws(nf));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw);

@@ -112,6 +112,14 @@ def test_sparse_align_many_features_and_other_geometry(built):
         _compare_traces(lo, lg)
     with pytest.raises(capi.DsdtmError):                      # more features than the capacity is an error, never a silent truncation
         c.sparse_align(0, 1, np.zeros(600, O.REF_FEAT_DT), sc["ref_center"], S.IDENTITY, 4, 0, 30)
+    # a SECOND context with a smaller feature table must not shrink what this one may launch (the shared-memory limit is a property
+    # of the kernel, shared by every context of the process)
+    small = capi.Context(cam, levels=4, cell_size=30, max_feats=64, max_patches=8, max_frames=2, max_batch=1)
+    c.set_option("sa_warps_per_pair", 0)
+    pg, ng, _ = c.sparse_align(0, 1, sc["feats"], sc["ref_center"], S.IDENTITY, 4, 0, 30)
+    d = S.pose_dist(po, pg)
+    assert d[0] < POSE_TOL and d[1] < POSE_TOL and no == ng
+    small.close()
     c.close()
 
 
