@@ -87,6 +87,11 @@ __device__ __forceinline__ void qrot(double qw, double qx, double qy, double qz,
 #ifndef DSDTM_SA_STRICT
 #define DSDTM_SA_STRICT 0
 #endif
+#ifndef DSDTM_SA_MOM
+#define DSDTM_SA_MOM 1      // second moments (needed by the first iteration of a level only): 0 `if (first)` per pixel = 6 FSEL + 3 DFMA per
+                            // pixel on EVERY iteration (8.5 % of all executed instructions were FSEL), 1 always accumulate, 2 uniform
+                            // branch per patch row. ms per 4096 pairs: 1.346 / 1.295 / 1.305 (profiles/r2_sparse_align.md)
+#endif
 __device__ __forceinline__ double bil(double w0, double w1, double w2, double w3, double i0, double i1, double i2, double i3)
 {
 #if DSDTM_SA_STRICT
@@ -377,13 +382,22 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     cvt_cur((r + 1) & 1, r + 1);
                     const int g0 = r % 3, g1 = (r + 1) % 3, g2 = (r + 2) % 3;   // G rows r, r+1, r+2
                     const int ca = r & 1, cb = ca ^ 1;                          // Cw rows r, r+1
+#if DSDTM_SA_MOM == 2
+                    double dxa[4], dya[4];
+#endif
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const double refv = R.G[g1][c + 1];
                         // 2*dx, 2*dy: the reference's 0.5 factor (ref: :150-158) is applied once to the sums below (exact: power of two)
                         const double dx2 = __dsub_rn(R.G[g1][c + 2], R.G[g1][c]);
                         const double dy2 = __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]);
+#if DSDTM_SA_MOM == 0
                         if (first) { Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy); }
+#elif DSDTM_SA_MOM == 1
+                        Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy);
+#else
+                        dxa[c] = dx2; dya[c] = dy2;
+#endif
                         const double cur = bil(me.tl, me.tr, me.bl, me.br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
                         const double res = __dsub_rn(cur, refv);                                          // ref: :282
 #if DSDTM_SA_STRICT
@@ -394,6 +408,13 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                         Sx = fma(dx2, res, Sx);
                         Sy = fma(dy2, res, Sy);
                     }
+#if DSDTM_SA_MOM == 2
+                    if (first) {                              // uniform over the CTA: a real branch (the asm keeps it from becoming 6 selects per pixel)
+                        asm volatile("" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { Sxx = fma(dxa[c], dxa[c], Sxx); Sxy = fma(dxa[c], dya[c], Sxy); Syy = fma(dya[c], dya[c], Syy); }
+                    }
+#endif
                 }
                 if (first) { s_S[f] = 0.25 * Sxx; s_S[NF + f] = 0.25 * Sxy; s_S[2 * NF + f] = 0.25 * Syy; }   // (0.5 d2)^2, exact scaling
                 if (first && !vis) return;
