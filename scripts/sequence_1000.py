@@ -70,7 +70,7 @@ def main():
     kfs = [L.hs_keyframe_new(g_last.h)]
     L.hs_map_add_keyframe(kfs[-1])
     kf_frames = {0: g_last}
-    T = {k: [] for k in ("frame", "run", "search", "opt", "keyframe")}
+    T = {k: [] for k in ("frame", "run", "search", "opt", "keyframe", "kf_detect", "kf_lift", "kf_map")}
     tracked, matches, iters, err_sa, err_po, n_local, n_reproj = [], [], [], [], [], [], []
     lost = 0
     checked = []
@@ -115,11 +115,14 @@ def main():
             t5 = time.perf_counter()
             n_old = len(g_cur.features()[0])
             g_cur.detect(5.0, use_existing=True)
+            t6 = time.perf_counter()
             lift(g_cur, depth[k], n_old)
+            t7 = time.perf_counter()
             kfs.append(L.hs_keyframe_new(g_cur.h))
             L.hs_map_add_keyframe(kfs[-1])
             kf_frames[k] = g_cur
-            T["keyframe"].append(time.perf_counter() - t5)
+            t8 = time.perf_counter()
+            T["keyframe"].append(t8 - t5); T["kf_detect"].append(t6 - t5); T["kf_lift"].append(t7 - t6); T["kf_map"].append(t8 - t7)
         if g_last is not None and (k - 1) not in kf_frames:
             g_last.free()
         g_last = g_cur
@@ -130,7 +133,9 @@ def main():
           % (np.median(tracked), np.min(tracked), np.median(matches), np.min(matches), np.mean(iters), np.max(iters)))
     print("local key frames per frame: median %d max %d; reprojected local map points: median %d max %d" % (np.median(n_local), np.max(n_local), np.median(n_reproj), np.max(n_reproj)))
     for key, name in (("frame", "Frame ctor (upload + pyramid)"), ("run", "Sprase_ImgAlign::Run"), ("search", "UpdateLocalMap + SearchLocalPoints"),
-                      ("opt", "Optimizer::PoseOptimization"), ("keyframe", "CraeteKeyframe (detect + lift), per key frame")):
+                      ("opt", "Optimizer::PoseOptimization"), ("keyframe", "CraeteKeyframe (detect + lift), per key frame"),
+                      ("kf_detect", "  of which Feature_detector::detect"), ("kf_lift", "  of which depth upload + UndistortFeatures + map points"),
+                      ("kf_map", "  of which KeyFrame copy + Map::AddKeyFrame")):
         print("%-46s: median %.1f us, p95 %.1f us" % ((name,) + us(T[key])))
     tot = np.array(T["frame"]) + np.array(T["run"]) + np.array(T["search"]) + np.array(T["opt"])
     print("%-46s: median %.1f us, p95 %.1f us  (%.0f frames/s)" % (("front end per frame",) + us(tot) + (1.0 / np.mean(tot),)))
