@@ -61,35 +61,76 @@ def shard(n_total, world, rank):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons; started early (nvidia-smi needs ~1 s to produce its first line) and
-    filtered to the wall-clock window of the timed region afterwards."""
+    """SM clock and throttle reasons DURING the timed regions: NVML polled every 2 ms from a thread (the C-ABI calls release the GIL),
+    filtered to the wall-clock window of a region afterwards. Falls back to `nvidia-smi -lms 20` when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
+        self.samples = []            # (t, sm_mhz, max_mhz, set(reasons))
         self.p = None
+        self.nvml = None
+        self.how = None
+        self._stop = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.how = "NVML, 2 ms period"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                        "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.how = "nvidia-smi -lms 20"
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
             self.p = None
 
+    def _poll(self):
+        N = self.nvml
+        bits = (("hw_slowdown", getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(N, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                mhz = float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.h))
+                self.samples.append((time.perf_counter(), mhz, self.max_mhz, {n for n, b in bits if mask & b}))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.p.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm, mx = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.samples.append((time.perf_counter(), sm, mx, {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
 
     def wait_first(self, timeout=5.0):
         t0 = time.perf_counter()
-        while self.p and not self.lines and time.perf_counter() - t0 < timeout:
+        while (self.p or self.nvml) and not self.samples and time.perf_counter() - t0 < timeout:
             time.sleep(0.02)
 
     def stop(self):
+        self._stop.set()
         if self.p:
             self.p.terminate()
             try:
@@ -98,24 +139,14 @@ class ClockSampler:
                 self.p.kill()
 
     def summary(self, t0, t1):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        sm, mx, reasons = [], [], set()
-        for ts, ln in self.lines:
-            if ts < t0 or ts > t1 + 0.03:
-                continue
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not (self.p or self.nvml):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"], "samples": 0}
+        sel = [x for x in self.samples if t0 <= x[0] <= t1 + 0.03]
+        reasons = set()
+        for x in sel:
+            reasons |= x[3]
+        return {"sm_mhz": float(np.median([x[1] for x in sel])) if sel else None, "sm_max_mhz": max(x[2] for x in sel) if sel else None,
+                "reasons": sorted(reasons), "samples": len(sel), "sampler": self.how}
 
 
 def bind_to_gpu_numa(index):
