@@ -13,7 +13,7 @@
 //   (max 16 * 4080 = 65280 < 2^16: no carry between halves). One 32-bit store per 4 outputs.
 //   pyrdown_tile_kernel (any size; odd / tiny levels): 64x16 output tile staged through shared memory with reflect-101.
 // HBM-bound stage: algorithmic bytes per frame = sum_l (w_{l-1} h_{l-1} + w_l h_l) (510 000 B @640x480x5).
-// Round-1 profile (profiles/r1_bench_first.md): the tile kernel alone ran at 600 GB/s = 9 % of HBM peak, issue-bound on
+// Round-1 measurement (history in profiles/r1_pyramid_fast_align2d.md): the tile kernel alone ran at 600 GB/s = 9 % of HBM peak, issue-bound on
 // byte-wide shared-memory traffic -- hence the register/DP4A strip kernel. (Fetching the 3 halo bytes from neighbouring lanes by
 // shuffle instead of two extra L1-hit 4-byte loads was measured SLOWER: 0.384 vs 0.267 ms per 2072 frames.
 // An 8-outputs-per-thread variant (one 16-byte load per row, 44 registers) and rows-per-thread 4/16/32 x unroll 2/4 were also
