@@ -222,6 +222,7 @@ void hs_frame_set_feature(void* f, int i, const double* normal3, int level)
     ft->mlevel = level;
 }
 void hs_mappoint_set_bad(int id, int bad) { if (id >= 0 && id < (int)g_mps.size()) g_mps[id]->SetBad(bad != 0); }
+void hs_mappoint_set_pose(int id, const double* p3) { if (id >= 0 && id < (int)g_mps.size()) g_mps[id]->Set_Pose(Vector3d(p3[0], p3[1], p3[2])); }
 int hs_mappoint_is_bad(int id) { return (id >= 0 && id < (int)g_mps.size()) ? (g_mps[id]->IsBad() ? 1 : 0) : -1; }
 
 void* hs_keyframe_new(void* f)

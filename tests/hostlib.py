@@ -55,6 +55,7 @@ def lib():
         L.hs_set_use_store.argtypes = [C.c_int]
         L.hs_set_speculate.argtypes = [C.c_int]
         L.hs_mappoint_set_bad.argtypes = [C.c_int, C.c_int]
+        L.hs_mappoint_set_pose.argtypes = [C.c_int, C.c_void_p]
         L.hs_search_local_points_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_frame_attach_points_from.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hs_frame_feature_mp_ids.argtypes = [C.c_void_p, C.c_void_p]

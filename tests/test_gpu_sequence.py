@@ -429,6 +429,78 @@ def test_update_local_map_selects_the_oracles_keyframes(built):
     assert (local2 == lo2).all() and local2[-1] == 2 and m2 >= 100
 
 
+@pytest.mark.gpu
+def test_map_store_follows_recycled_slots_bad_flags_and_moved_points(built):
+    """The device-resident map tables are maintained incrementally (Map::SyncStore): key frames whose pyramids were evicted from the
+    frame pool come back in OTHER slots (dsdtm_store_set_keyframe), map points flagged bad or moved by a bundle adjustment are
+    rewritten in place (dsdtm_store_update_points). After each kind of change the device path must still equal the reference's literal
+    per-object loop (ref: src/Tracking.cpp:283-297, src/MapPoint.cpp:133-174) run on the same host objects."""
+    cam = dict(S.KINECT)
+    scene = S.Scene(77)
+    cam_h = HL.configure(cam, max_fts=300, max_frames=12, dist=(0.0, 0.0, 0.0, 0.0, 0.0))
+    L = HL.lib()
+    kf_poses = [S.pose_from_xi(np.array([0.3 * k, 0.04 * (k % 3), 0.02 * k, 0.0, 0.01 * k, 0.0])) for k in range(8)]
+    frames = []
+    for k, pose in enumerate(kf_poses):
+        img, _, pts = S.render(scene, cam, pose, want_points=True)
+        g = HL.HFrame(cam_h, img, pose)
+        n = g.detect(5.0)
+        px, _, _ = g.features()
+        g.attach_points(pts[px[:, 1].astype(int), px[:, 0].astype(int)], np.ones(n, np.uint8))
+        L.hs_map_add_keyframe(L.hs_keyframe_new(g.h))
+        frames.append(g)
+    pose_cur = S.pose_mul(S.pose_from_xi(np.array([0.012, -0.008, 0.006, 0.002, -0.003, 0.001])), kf_poses[3])
+    img, _ = S.render(scene, cam, pose_cur)
+
+    def track(use_store):
+        L.hs_set_use_store(1 if use_store else 0)
+        try:
+            cur = HL.HFrame(cam_h, img, pose_cur)
+            m, local, nrep = HL.track_local_map(cam_h, cur)
+        finally:
+            L.hs_set_use_store(1)
+        px, lv, _ = cur.features()
+        ids = cur.mp_ids()
+        for i in ids:
+            L.hs_mappoint_increase_found(int(i), -1)                  # every run starts from the same found counters
+        cur.free()
+        return m, local, nrep, px, lv, ids
+
+    def same(a, b):
+        return a[0] == b[0] and (a[1] == b[1]).all() and a[2] == b[2] and (a[3] == b[3]).all() and (a[4] == b[4]).all() and (a[5] == b[5]).all()
+
+    base = track(True)
+    assert base[0] >= 150 and len(base[1]) >= 3 and same(base, track(False))
+    # 1. ten frames that stay alive push the oldest key-frame pyramids out of the 12-slot pool; once they are gone the key frames are
+    #    re-uploaded into whatever slots are free: the rows of the table must follow
+    junk = [HL.HFrame(cam_h, img, pose_cur) for _ in range(10)]
+    for j in junk:
+        j.free()
+    again = track(True)
+    assert same(base, again)
+    # 2. a fifth of the matched points is flagged bad, another fifth moves by 1-2 cm (LocalBundleAdjustment): the bad ones disappear
+    #    from the candidates, the moved ones are projected from their new positions -- in both paths alike
+    ids = base[5]
+    bad_ids, moved_ids = ids[::5], ids[2::5]
+    for i in bad_ids:
+        L.hs_mappoint_set_bad(int(i), 1)
+    rng = np.random.default_rng(3)
+    for i in moved_ids:
+        p = np.zeros(3)
+        L.hs_mappoint_pose(int(i), HL._p(p))
+        p += rng.uniform(-0.02, 0.02, 3)
+        L.hs_mappoint_set_pose(int(i), HL._p(np.ascontiguousarray(p)))
+    dev, host = track(True), track(False)
+    assert same(dev, host)
+    assert dev[2] < base[2] and not (set(dev[5].tolist()) & set(int(i) for i in bad_ids))
+    assert dev[0] >= 100
+    # 3. the flags are cleared again: the first result comes back except for the moved points
+    for i in bad_ids:
+        L.hs_mappoint_set_bad(int(i), 0)
+    dev2, host2 = track(True), track(False)
+    assert same(dev2, host2) and dev2[2] > dev[2] and abs(dev2[2] - base[2]) <= len(moved_ids)
+
+
 def test_run_and_update_local_map_as_one_submission_equal_the_separate_calls(built):
     """Sprase_ImgAlign::Run also runs Tracking::UpdateLocalMap's device stage in the same submission (dsdtm_track_frame_store) and
     Tracking::UpdateLocalMap takes the parked records: poses, tracked counts, local key frames, matches, pixels, levels and map-point
