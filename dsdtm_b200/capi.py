@@ -205,6 +205,12 @@ class Context:
         assert img.shape == (self.height, self.width)
         self._ck(self.L.dsdtm_frame_upload_pyramid(self.hp, int(slot), _p(img), img.shape[1]))
 
+    def upload_async(self, slot, img):
+        """dsdtm_frame_upload_pyramid_async: queued on the context's stream, no synchronisation (later calls are ordered after it)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        assert img.shape == (self.height, self.width)
+        self._ck(self.L.dsdtm_frame_upload_pyramid_async(self.hp, int(slot), _p(img), img.shape[1]))
+
     def upload_level(self, slot, level, img):
         img = np.ascontiguousarray(img, np.uint8)
         assert img.shape == (self.hs[level], self.ws[level])

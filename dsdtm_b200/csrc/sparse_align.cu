@@ -349,7 +349,12 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
             // pose-independent second moments Sxx, Sxy, Syy of every VALID feature (visible or not) and parks them in shared memory for
             // H. One instantiation serves both cases (round 1 compiled the pass twice: half of the 120 KB of SASS, and the first
             // iteration of every level ran cold code -- profiles/r2_sparse_align.md).
+#if DSDTM_SA_MOM == 3
+            auto stage2 = [&](auto first_tag, int f, int k, const Pre& me) {
+                constexpr bool first = decltype(first_tag)::value;
+#else
             auto stage2 = [&](bool first, int f, int k, const Pre& me) {
+#endif
                 if (!(first ? me.valid : me.vis)) return;
                 const bool vis = me.vis;
                 if (vis) { vis_mask |= 1u << k; ++cnt; }
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                         // 2*dx, 2*dy: the reference's 0.5 factor (ref: :150-158) is applied once to the sums below (exact: power of two)
                         const double dx2 = __dsub_rn(R.G[g1][c + 2], R.G[g1][c]);
                         const double dy2 = __dsub_rn(R.G[g2][c + 1], R.G[g0][c + 1]);
-#if DSDTM_SA_MOM == 0
+#if DSDTM_SA_MOM == 0 || DSDTM_SA_MOM == 3
                         if (first) { Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy); }
 #elif DSDTM_SA_MOM == 1
                         Sxx = fma(dx2, dx2, Sxx); Sxy = fma(dx2, dy2, Sxy); Syy = fma(dy2, dy2, Syy);
@@ -432,11 +437,19 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
             {
                 const bool first = (it == 0);
                 int kq = 0;
+#if DSDTM_SA_MOM == 3
+                if (first) {
+                    for (int f = tid; f < nfeat; f += NT, ++kq) { Pre me; stage1(f, me); stage2(std::true_type{}, f, kq, me); }
+                } else {
+                    for (int f = tid; f < nfeat; f += NT, ++kq) { Pre me; stage1(f, me); stage2(std::false_type{}, f, kq, me); }
+                }
+#else
                 for (int f = tid; f < nfeat; f += NT, ++kq) {
                     Pre me;
                     stage1(f, me);
                     stage2(first, f, kq, me);
                 }
+#endif
             }
 #ifdef DSDTM_SA_TIMING
             const long long tk1 = clock64();

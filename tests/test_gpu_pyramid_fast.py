@@ -65,6 +65,21 @@ def test_pyramid_tile_kernel_option_is_bit_exact_too(ctx, scenario):
         ctx.set_option("no_such_option", 1)
 
 
+def test_pyramid_async_upload_is_ordered_before_later_calls(ctx, scenario):
+    """dsdtm_frame_upload_pyramid_async returns without a synchronisation; the caller's (pageable) buffer may be reused right away and
+    every later call on the context sees the finished pyramid (ref: src/Frame.cpp:74-81 through the Frame adapter's constructor)."""
+    packed, offs, ws, hs = scenario["ref_pyr"]
+    cpacked = scenario["cur_pyr"][0]
+    buf = scenario["ref_img"].copy()
+    ctx.upload_async(6, buf)
+    buf[:] = scenario["cur_img"]                     # overwrite the source immediately: the first image has already left the buffer
+    ctx.upload_async(7, buf)
+    buf[:] = 0
+    for l in range(5):
+        assert (ctx.download_level(6, l) == O.pyr_level(packed, offs, ws, hs, l)).all(), l
+        assert (ctx.download_level(7, l) == O.pyr_level(cpacked, offs, ws, hs, l)).all(), l
+
+
 def test_pyramid_batch_and_rebuild(ctx, scenario):
     imgs = np.stack([scenario["ref_img"], scenario["cur_img"], scenario["ref_img"][::-1].copy()])
     ctx.upload_batch(2, imgs)
