@@ -39,8 +39,25 @@ def _deps():
     return [os.path.join(CSRC, s) for s in SOURCES] + _headers()
 
 
+STAMP = os.path.join(LIBDIR, "flags.stamp")
+
+
+def _flag_key():
+    return " ".join(NVCC_FLAGS + extra_flags())
+
+
+def _stamp_matches():
+    """The flags the objects in lib/ were compiled with. An experiment built with DSDTM_NVCC_FLAGS must never be mistaken for the
+    default build by a later plain build() (the library is newer than every source in that case)."""
+    try:
+        with open(STAMP) as f:
+            return f.read() == _flag_key()
+    except OSError:
+        return False
+
+
 def stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not _stamp_matches():
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(p) > t for p in _deps())
@@ -50,6 +67,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    if not _stamp_matches():
+        force = True                      # other flags: every object is rebuilt
     objs = []
     log = []
     for s in SOURCES:
@@ -70,6 +89,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("link failed")
     with open(os.path.join(LIBDIR, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
+    with open(STAMP, "w") as f:
+        f.write(_flag_key())
     if verbose:
         print("\n".join(log))
     return LIB
