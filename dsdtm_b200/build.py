@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libdsdtm_gpu.so")
+# DSDTM_GPU_LIB: measurement scripts load a prebuilt experiment library (scripts/sa_build_variants.py) instead of the default build
+LIB = os.environ.get("DSDTM_GPU_LIB") or os.path.join(LIBDIR, "libdsdtm_gpu.so")
 SOURCES = ["capi.cu", "pyramid.cu", "fast.cu", "sparse_align.cu", "align2d.cu", "local_map.cu", "ingest.cu", "clahe.cu", "pose_opt.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
@@ -57,6 +58,8 @@ def _stamp_matches():
 
 
 def stale():
+    if os.environ.get("DSDTM_GPU_LIB"):
+        return False                      # an explicitly named library is taken as it is
     if not os.path.exists(LIB) or not _stamp_matches():
         return True
     t = os.path.getmtime(LIB)

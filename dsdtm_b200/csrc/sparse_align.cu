@@ -53,17 +53,37 @@ constexpr int NB_WORDS = 14;   // 7 rows x 2 words (7 bytes) of the reference ne
 __device__ __forceinline__ double u8_to_f64(uint32_t word, int byte)
 {
 #ifndef DSDTM_SA_CVT
-#define DSDTM_SA_CVT 1      // measured (ms per 2072 pairs): 0 magic-number add 0.847, 1 PRMT + I2F.F64 0.816, 2 shift + I2F.F64 0.828; all exact
+#define DSDTM_SA_CVT 3      // measured (ms per 2072 pairs, round 1): 0 magic-number add 0.847, 1 PRMT + I2F.F64 0.816, 2 shift + I2F.F64 0.828; all exact.
+                            // 3 (round 2, main kernel): subnormal encoding, no conversion instruction -- 1.295 -> 1.267 ms per 4096 pairs, bit-equal
 #endif
 #if DSDTM_SA_CVT == 0
     // exact int -> double without the slow I2F.F64 path: 2^52 + b has b in its low mantissa bits
     return __hiloint2double(0x43300000, (int)__byte_perm(word, 0, 0x4440 | byte)) - 4503599627370496.0;
-#elif DSDTM_SA_CVT == 1
+#elif DSDTM_SA_CVT == 1 || DSDTM_SA_CVT == 3
     return (double)__byte_perm(word, 0, 0x4440 | byte);                 // PRMT + I2F.F64.U32
 #else
     return (double)(unsigned char)(word >> (8 * byte));                 // lets ptxas pick I2F.F64.U8 with a byte selector
 #endif
 }
+
+// DSDTM_SA_CVT == 3 (main kernel only): NO conversion instruction at all. One PRMT puts the byte into bits 8..15 of the HIGH word of
+// a double whose exponent field is 0: the subnormal b * 2^-1034, exactly proportional to the byte (0 -> +0.0). The bilinear weights
+// carry 2^SA_WEXP, so every sample is the reference's value times 2^(SA_WEXP - 1034) = 2^-24 with the SAME rounding (scaling by a power
+// of two commutes with IEEE rounding while nothing under- or overflows: products are >= 2^-46 * 2^-24, far from 2^-1022), and so are
+// residuals and central differences; sums of products carry 2^-48 and are restored by one exact multiplication each. Bit-identical
+// results, 74 I2F.F64 (XU pipe, quarter rate) less per feature and iteration.
+#if DSDTM_SA_CVT == 3
+#define SA_WSCALE 0x1p1010
+#define SA_RESTORE2 0x1p48          // 1 / (2^-24)^2
+__device__ __forceinline__ double u8_to_f64s(uint32_t word, int byte)
+{
+    return __hiloint2double((int)__byte_perm(word, 0, 0x4404 | (byte << 4)), 0);
+}
+#else
+#define SA_WSCALE 1.0
+#define SA_RESTORE2 1.0
+__device__ __forceinline__ double u8_to_f64s(uint32_t word, int byte) { return u8_to_f64(word, byte); }
+#endif
 
 __device__ __forceinline__ void qrot(double qw, double qx, double qy, double qz, double v0, double v1, double v2,
                                      double& o0, double& o1, double& o2)   // Eigen _transformVector, non-contracted
@@ -111,7 +131,8 @@ __device__ __forceinline__ double warp_sum(double v)
 // Reference-side samples of one feature, re-derived from its staged 7x7 neighbourhood. Row r of the 4x4 patch:
 //   ref[c] = G[r+1][c+1], dx[c] = 0.5 (G[r+1][c+2] - G[r+1][c]), dy[c] = 0.5 (G[r+2][c+1] - G[r][c+1])
 // with G[y][x] = bil(w; N[y][x], N[y][x+1], N[y+1][x], N[y+1][x+1]) -- the reference's expressions (ref: :147-158).
-struct RefRows {
+template <bool SCALED>
+struct RefRowsT {
     double w00, w01, w10, w11;
     double Nd[2][7];      // two converted neighbourhood rows (y, y+1)
     double G[3][6];       // G rows y-1, y, y+1
@@ -122,16 +143,16 @@ struct RefRows {
     {
         const uint32_t lo = nb[(2 * y) * NF], hi = nb[(2 * y + 1) * NF];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Nd[slot][c] = u8_to_f64(lo, c);
+        for (int c = 0; c < 4; ++c) Nd[slot][c] = SCALED ? u8_to_f64s(lo, c) : u8_to_f64(lo, c);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Nd[slot][4 + c] = u8_to_f64(hi, c);
+        for (int c = 0; c < 3; ++c) Nd[slot][4 + c] = SCALED ? u8_to_f64s(hi, c) : u8_to_f64(hi, c);
     }
     __device__ __forceinline__ void load_row_words(int slot, uint32_t lo, uint32_t hi)
     {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Nd[slot][c] = u8_to_f64(lo, c);
+        for (int c = 0; c < 4; ++c) Nd[slot][c] = SCALED ? u8_to_f64s(lo, c) : u8_to_f64(lo, c);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Nd[slot][4 + c] = u8_to_f64(hi, c);
+        for (int c = 0; c < 3; ++c) Nd[slot][4 + c] = SCALED ? u8_to_f64s(hi, c) : u8_to_f64(hi, c);
     }
     __device__ __forceinline__ void grid_row(int g, int a, int b)   // G[g][x] from Nd[a] (row y) and Nd[b] (row y+1)
     {
@@ -139,6 +160,7 @@ struct RefRows {
         for (int x = 0; x < 6; ++x) G[g][x] = bil(w00, w01, w10, w11, Nd[a][x], Nd[a][x + 1], Nd[b][x], Nd[b][x + 1]);
     }
 };
+using RefRows = RefRowsT<false>;
 
 // the serial tail of one GN iteration, kept out of line: it runs on one lane once per iteration and must not bloat
 // (or evict from the instruction cache) the per-feature loop. H only changes when the visibility set changes, so the
@@ -202,6 +224,12 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 // (Tried and removed: staging an 8 x 7 window of the CURRENT image per feature in shared memory at level start, so that the
 // iterations of a level stop re-gathering it from global memory. 173 instead of 113 B/feature of shared memory took more L1
 // away than the re-gathers cost: 1.68 vs 1.55 ms per 4096 pairs, 86 vs 84 us for a single pair. profiles/r1_sparse_align_v3.md)
+#ifndef DSDTM_SA_STAGE
+#define DSDTM_SA_STAGE 1         // 1 = level staging with two features per thread in flight + level-independent prologue (1.295 -> 1.242 ms per 4096 pairs; with CVT 3: 1.216); 0 = one feature at a time
+#endif
+#ifndef DSDTM_SA_PREF
+#define DSDTM_SA_PREF 0          // 1 = the level staging prefetches the current-image rows of the first iteration (needs DSDTM_SA_STAGE 1): measured SLOWER, 1.292 vs 1.216 ms
+#endif
 #ifndef DSDTM_SA_MINB3
 #define DSDTM_SA_MINB3 4         // resident CTAs per SM the 3-warp variant is compiled for (5 -> 128 regs, 60 B spills: 1.79 vs 1.52 ms; 6 -> 96 regs: 2.89 ms)
 #endif
@@ -221,8 +249,9 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
     double* s_S = reinterpret_cast<double*>(s_raw + (size_t)24 * NF);                      // [3][NF] Sxx, Sxy, Syy of the ref patch
     double* s_zi = reinterpret_cast<double*>(s_raw + (size_t)48 * NF);                     // [NF] 1 / P.z (pose-independent: one division per level instead of one per iteration)
     uint32_t* s_nb = reinterpret_cast<uint32_t*>(s_raw + (size_t)56 * NF);                 // [14][NF] 7x7 u8 neighbourhood
-    float2* s_sub = reinterpret_cast<float2*>(s_raw + (size_t)(56 + 4 * NB_WORDS) * NF);   // [NF] sub-pixel offsets
-    uint8_t* s_valid = s_raw + (size_t)(56 + 4 * NB_WORDS + 8) * NF;                       // [NF]
+    float2* s_sub = reinterpret_cast<float2*>(s_raw + (size_t)(56 + 4 * NB_WORDS) * NF);   // [NF] sub-pixel offsets (DSDTM_SA_STAGE 0) ...
+    float2* s_px = s_sub;                                                                  // ... or the feature's level-0 pixel (DSDTM_SA_STAGE 1)
+    uint8_t* s_valid = s_raw + (size_t)(56 + 4 * NB_WORDS + 8) * NF;                       // [NF] bit 0: staged at this level, bit 1: has a map point (all levels)
     __shared__ double s_red[WPP][8];
     __shared__ int s_cnt[WPP];
     __shared__ double s_redH[WPP][22];
@@ -243,6 +272,33 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
 
     if (tid < 7) { s_T[tid] = a.poses_in[7 * pair + tid]; s_Told[tid] = s_T[tid]; }
     if (tid == 0) { s_npts = 0; s_nlog = 0; s_stop = 0; s_chi2prev = 0.0; }
+#if DSDTM_SA_STAGE == 1
+    // prologue: what GetJocabianMat derives per feature that does not depend on the level (ref: :86, :95 zero test, :117-119), once;
+    // two 64-byte records per thread in flight
+    for (int f0 = tid; f0 < nfeat; f0 += 2 * NT) {
+        dsdtm_ref_feat ft[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) ft[g] = a.feats[(size_t)pair * a.feat_stride + min(f0 + g * NT, nfeat - 1)];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int f = f0 + g * NT;
+            if (f < nfeat) {
+                const bool zero = (ft[g].point_w[0] == 0.0 && ft[g].point_w[1] == 0.0 && ft[g].point_w[2] == 0.0);
+                const bool eligible = ft[g].initial && !zero;
+                if (eligible) {
+                    const double d0 = __dsub_rn(ft[g].point_w[0], cen0), d1 = __dsub_rn(ft[g].point_w[1], cen1), d2 = __dsub_rn(ft[g].point_w[2], cen2);
+                    const double depth = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));   // ref: :117-118
+                    s_P[f] = __dmul_rn(ft[g].normal[0], depth);                                       // ref: :119
+                    s_P[NF + f] = __dmul_rn(ft[g].normal[1], depth);
+                    s_P[2 * NF + f] = __dmul_rn(ft[g].normal[2], depth);
+                    s_zi[f] = 1.0 / __dmul_rn(ft[g].normal[2], depth);
+                }
+                s_px[f] = make_float2(ft[g].px[0], ft[g].px[1]);
+                s_valid[f] = eligible ? 2 : 0;
+            }
+        }
+    }
+#endif
     __syncthreads();
 
     for (int level = a.max_level - 1; level >= a.min_level; --level) {
@@ -253,6 +309,80 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
         const double fs2 = fs * fs;
 
         // ------------------------------------------------ level staging = the pose-independent part of GetJocabianMat (ref: :62-132)
+#if DSDTM_SA_STAGE == 1
+        // Two features per thread and step, straight-line: both features' 21 aligned window loads are in flight together (the loop
+        // used to pay two dependent DRAM round trips per feature -- record, then window -- four times per level: ~15 k cycles of
+        // a 360 k-cycle pair). The level-independent part (point in the reference camera, 1 / z) is done once in the prologue.
+        {
+            const uint8_t* __restrict__ img = ref_frame + a.geo.off[level];
+            for (int f0 = tid; f0 < nfeat; f0 += 2 * NT) {
+                uint32_t w[2][7][3];
+                unsigned a0[2];
+                bool val[2];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int f = f0 + g * NT;
+                    val[g] = false; a0[g] = 0u;
+                    if (f < nfeat && (s_valid[f] & 2)) {                                                  // ref: :86 and the zero-point test of :95
+                        const float2 p = s_px[f];
+                        const double px = (double)p.x * scale, py = (double)p.y * scale;                  // ref: :89-91
+                        const int boarder = 3;                                                             // ref: :67
+                        if (!(px - boarder < 0 || py - boarder < 0 || px + boarder >= cols || py + boarder >= rows)) {   // ref: :95-96
+                            val[g] = true;
+                            const int fxi = __double2int_rd(px), fyi = __double2int_rd(py);
+                            // rows fyi-3 .. fyi+3, cols fxi-3 .. fxi+3 : three aligned 32-bit loads + funnel shifts per row
+                            a0[g] = (unsigned)(fyi - 3) * (unsigned)cols + (unsigned)(fxi - 3);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {          // unconditional (offset 0 for a feature that is not staged): no branch between the loads
+                        const unsigned ad = a0[g] + (unsigned)r * (unsigned)cols;
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (ad & ~3u));
+                        w[g][r][0] = __ldg(wp); w[g][r][1] = __ldg(wp + 1); w[g][r][2] = __ldg(wp + 2);
+                    }
+                }
+#if DSDTM_SA_PREF
+                // while the reference windows are in flight: ask for the rows of the CURRENT image the first iteration of this level
+                // will gather (pose at level start). Addresses only -- fp32 projection, nothing here reaches a result.
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int f = f0 + g * NT;
+                    if (val[g]) {
+                        const float q0 = (float)s_T[0], q1 = (float)s_T[1], q2 = (float)s_T[2], q3 = (float)s_T[3];
+                        const float v0 = (float)s_P[f], v1 = (float)s_P[NF + f], v2 = (float)s_P[2 * NF + f];
+                        const float uv0 = 2.f * (q2 * v2 - q3 * v1), uv1 = 2.f * (q3 * v0 - q1 * v2), uv2 = 2.f * (q1 * v1 - q2 * v0);
+                        const float X = v0 + q0 * uv0 + (q2 * uv2 - q3 * uv1) + (float)s_T[4];
+                        const float Y = v1 + q0 * uv1 + (q3 * uv0 - q1 * uv2) + (float)s_T[5];
+                        const float Z = v2 + q0 * uv2 + (q1 * uv1 - q2 * uv0) + (float)s_T[6];
+                        const float iz = __frcp_rn(Z);
+                        const float uu = (a.fx * X * iz + a.cx) * tScale, vv = (a.fy * Y * iz + a.cy) * tScale;
+                        if (uu >= 3.f && vv >= 3.f && uu < (float)(cols - 3) && vv < (float)(rows - 3)) {
+                            const uint8_t* q = cur_frame + a.geo.off[level] + ((unsigned)((int)vv - 2) * (unsigned)cols + (unsigned)((int)uu - 2));
+#pragma unroll
+                            for (int r = 0; r < 5; ++r) {
+                                asm volatile("prefetch.global.L1 [%0];" :: "l"(q + (size_t)r * cols));
+                                asm volatile("prefetch.global.L1 [%0];" :: "l"(q + (size_t)r * cols + 7));
+                            }
+                        }
+                    }
+                }
+#endif
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int f = f0 + g * NT;
+                    if (f < nfeat) {
+#pragma unroll
+                        for (int r = 0; r < 7; ++r) {
+                            const int sh = 8 * ((a0[g] + (unsigned)r * (unsigned)cols) & 3u);
+                            s_nb[(2 * r) * NF + f] = __funnelshift_r(w[g][r][0], w[g][r][1], sh);
+                            s_nb[(2 * r + 1) * NF + f] = __funnelshift_r(w[g][r][1], w[g][r][2], sh);
+                        }
+                        s_valid[f] = (uint8_t)((s_valid[f] & 2) | (val[g] ? 1 : 0));
+                    }
+                }
+            }
+        }
+#else
         {
             const uint8_t* __restrict__ img = ref_frame + a.geo.off[level];
             for (int f = tid; f < nfeat; f += NT) {
@@ -288,6 +418,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 s_valid[f] = valid ? 1 : 0;
             }
         }
+#endif
         __syncthreads();
 
         unsigned prev_vis = 0;
@@ -309,7 +440,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
             auto stage1 = [&](int f, Pre& p) {
                 p.valid = false; p.vis = false;
                 if (f >= nfeat) return;
-                if (!s_valid[f]) return;
+                if (!(s_valid[f] & 1)) return;
                 p.valid = true;
                 const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
                 double Q0, Q1, Q2;
@@ -331,8 +462,11 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 p.vis = true;
                 const int ui = (int)uf, vi = (int)vf;
                 const double su = u - uf, sv = v - vf;
-                p.tl = __dmul_rn(1.0 - su, 1.0 - sv); p.tr = __dmul_rn(su, 1.0 - sv);
-                p.bl = __dmul_rn(1.0 - su, sv); p.br = __dmul_rn(su, sv);                     // ref: :267-270
+                {   // ref: :267-270; the second factor carries SA_WSCALE (a power of two: the products round exactly as unscaled)
+                    const double osv = (1.0 - sv) * SA_WSCALE, svs = sv * SA_WSCALE;
+                    p.tl = __dmul_rn(1.0 - su, osv); p.tr = __dmul_rn(su, osv);
+                    p.bl = __dmul_rn(1.0 - su, svs); p.br = __dmul_rn(su, svs);
+                }
                 const unsigned c0w = (unsigned)(vi - 2) * (unsigned)cols + (unsigned)(ui - 2);
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
@@ -358,12 +492,21 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 if (!(first ? me.valid : me.vis)) return;
                 const bool vis = me.vis;
                 if (vis) { vis_mask |= 1u << k; ++cnt; }
-                RefRows R;
+                RefRowsT<true> R;
                 {
+#if DSDTM_SA_STAGE == 1
+                    // the level pixel and its fraction in fp32: exact (a float scaled by 2^-level, minus its floor), the same values
+                    // as the reference's double expressions (ref: :89-91, :123-127)
+                    const float2 p0 = s_px[f];
+                    const float plx = p0.x * tScale, ply = p0.y * tScale;
+                    const double sx = (double)(plx - floorf(plx)), sy = (double)(ply - floorf(ply));
+#else
                     const float2 sub = s_sub[f];
                     const double sx = (double)sub.x, sy = (double)sub.y;
-                    R.w00 = __dmul_rn(1.0 - sx, 1.0 - sy); R.w01 = __dmul_rn(sx, 1.0 - sy);
-                    R.w10 = __dmul_rn(1.0 - sx, sy); R.w11 = __dmul_rn(sx, sy);               // ref: :129-132
+#endif
+                    const double osy = (1.0 - sy) * SA_WSCALE, sys = sy * SA_WSCALE;
+                    R.w00 = __dmul_rn(1.0 - sx, osy); R.w01 = __dmul_rn(sx, osy);
+                    R.w10 = __dmul_rn(1.0 - sx, sys); R.w11 = __dmul_rn(sx, sys);             // ref: :129-132
                 }
                 R.nb = s_nb + f; R.NF = NF;
                 R.load_row(0, 0); R.load_row(1, 1);
@@ -373,8 +516,8 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 double Cw[2][5];
                 auto cvt_cur = [&](int slot, int r) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) Cw[slot][c] = u8_to_f64(me.cw0[r], c);
-                    Cw[slot][4] = u8_to_f64(me.cw1[r], 0);
+                    for (int c = 0; c < 4; ++c) Cw[slot][c] = u8_to_f64s(me.cw0[r], c);
+                    Cw[slot][4] = u8_to_f64s(me.cw1[r], 0);
                 };
                 cvt_cur(0, 0);
                 double Sx = 0, Sy = 0, c2 = 0, Sxx = 0, Sxy = 0, Syy = 0;
@@ -421,9 +564,9 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     }
 #endif
                 }
-                if (first) { s_S[f] = 0.25 * Sxx; s_S[NF + f] = 0.25 * Sxy; s_S[2 * NF + f] = 0.25 * Syy; }   // (0.5 d2)^2, exact scaling
+                if (first) { s_S[f] = (0.25 * SA_RESTORE2) * Sxx; s_S[NF + f] = (0.25 * SA_RESTORE2) * Sxy; s_S[2 * NF + f] = (0.25 * SA_RESTORE2) * Syy; }   // (0.5 d2)^2, exact scaling
                 if (first && !vis) return;
-                Sx *= 0.5; Sy *= 0.5;
+                Sx *= 0.5 * SA_RESTORE2; Sy *= 0.5 * SA_RESTORE2;
                 // GetJocabianBA(P) rows (ref: :169-193); a1 = b0 = 0.   b_j = fs * (a * Sx + b * Sy)
                 const double P0 = s_P[f], P1 = s_P[NF + f];
                 const double zi = s_zi[f], zi2 = zi * zi;
@@ -454,6 +597,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
 #ifdef DSDTM_SA_TIMING
             const long long tk1 = clock64();
 #endif
+            accc *= SA_RESTORE2;      // the lane's sum of squared residuals carried 2^-48 (exact: a sum of scaled terms is the scaled sum)
             acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2); acc3 = warp_sum(acc3);
             acc4 = warp_sum(acc4); acc5 = warp_sum(acc5); accc = warp_sum(accc);
             cnt = __reduce_add_sync(0xffffffffu, cnt);

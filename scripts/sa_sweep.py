@@ -1,6 +1,6 @@
 """Sparse-alignment kernel sweep on one staged batch: (variant, warps per pair) -> ms per launch (CUDA events through the stage
 profiler) + bitwise comparison of the poses against variant 0 at the same warps-per-pair."""
-import argparse, os, sys
+import argparse, hashlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dsdtm_b200 import capi, synth as S, workload as W
@@ -37,8 +37,9 @@ def main():
             base[w] = (poses.copy(), nt.copy())
         same = "-" if w not in base else ("bit-equal to variant 0" if (poses == base[w][0]).all() and (nt == base[w][1]).all() else "DIFFERS max %.3g" % np.abs(poses - base[w][0]).max())
         err = np.median([S.pose_dist(poses[i], batch["truth"][i]) for i in range(min(B, 64))], 0)
-        print("variant %d wpp %2d: sparse_align %.4f ms per launch (%d pairs) | pyramid %.4f align2d %.4f | %s | median pose err %.2e rad %.2e m" % (
-            v, w, st["sparse_align"][0] / a.steps, B, st["pyramid"][0] / a.steps, st["align2d"][0] / a.steps, same, err[0], err[1]), flush=True)
+        dig = hashlib.sha1(poses.tobytes() + nt.tobytes()).hexdigest()[:12]     # equal digests across libraries = bit-equal poses and counts
+        print("variant %d wpp %2d: sparse_align %.4f ms per launch (%d pairs) | pyramid %.4f align2d %.4f | %s | median pose err %.2e rad %.2e m | sha1 %s" % (
+            v, w, st["sparse_align"][0] / a.steps, B, st["pyramid"][0] / a.steps, st["align2d"][0] / a.steps, same, err[0], err[1], dig), flush=True)
     ctx.close()
 
 
