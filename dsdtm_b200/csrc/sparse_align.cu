@@ -46,6 +46,7 @@ struct SaArgs {
     int nf;      // shared-memory column count (multiple of 16, >= every n_feats)
     int pair0;
     int variant;   // 0 recompute, 1 L2 workspace
+    double* mom;   // DSDTM_SA_SGLOBAL: per-pair [3][nf] second moments (the head of the pair's workspace block)
 };
 
 constexpr int NB_WORDS = 14;   // 7 rows x 2 words (7 bytes) of the reference neighbourhood
@@ -227,6 +228,22 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 #ifndef DSDTM_SA_STAGE
 #define DSDTM_SA_STAGE 1         // 1 = level staging with two features per thread in flight + level-independent prologue (1.295 -> 1.242 ms per 4096 pairs; with CVT 3: 1.216); 0 = one feature at a time
 #endif
+#ifndef DSDTM_SA_STAGE_G
+#define DSDTM_SA_STAGE_G 2       // features per thread whose window loads are in flight together in the level staging (4: 1.227 vs 1.216 ms)
+#endif
+#ifndef DSDTM_SA_SGLOBAL
+#define DSDTM_SA_SGLOBAL 0       // 1 = the parked second moments live in a per-pair global workspace (L2) instead of shared memory: 97 instead of 121 B / feature,
+                                 // 96 instead of 64 KB of L1 -- measured slower (1.247 vs 1.216 ms)
+#endif
+#ifndef DSDTM_SA_COMPACT
+#define DSDTM_SA_COMPACT 0       // 1 = the features staged at a level are compacted into an index list: the pass runs ceil(valid / lanes) rounds instead of
+                                 // ceil(n / lanes). Measured: no gain on the sweep batch (1.215 vs 1.215 ms: 295-297 of its 300 features are staged at
+                                 // every level, the fourth round stays) and a different (equally valid) summation order; off
+#endif
+#ifndef DSDTM_SA_RMAT
+#define DSDTM_SA_RMAT 0          // 1 = the point is rotated with the 3x3 matrix of the pose's quaternion (9 FMA) instead of Eigen's quaternion formula (30 operations):
+                                 // 1.210 vs 1.215 ms, results move in the last bits; not worth leaving the reference's expression
+#endif
 #ifndef DSDTM_SA_PREF
 #define DSDTM_SA_PREF 0          // 1 = the level staging prefetches the current-image rows of the first iteration (needs DSDTM_SA_STAGE 1): measured SLOWER, 1.292 vs 1.216 ms
 #endif
@@ -246,12 +263,23 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int NF = a.nf;
     double* s_P = reinterpret_cast<double*>(s_raw);                                        // [3][NF] point in the ref camera
+#if DSDTM_SA_SGLOBAL
+    constexpr int SB = 32;                                                                 // bytes per feature in front of the neighbourhood
+    double* s_S = a.mom + (size_t)(blockIdx.x + a.pair0) * 48 * NF;                        // [3][NF] Sxx, Sxy, Syy: written and read by the same thread, L2-resident
+    double* s_zi = reinterpret_cast<double*>(s_raw + (size_t)24 * NF);                     // [NF] 1 / P.z
+#else
+    constexpr int SB = 56;
     double* s_S = reinterpret_cast<double*>(s_raw + (size_t)24 * NF);                      // [3][NF] Sxx, Sxy, Syy of the ref patch
     double* s_zi = reinterpret_cast<double*>(s_raw + (size_t)48 * NF);                     // [NF] 1 / P.z (pose-independent: one division per level instead of one per iteration)
-    uint32_t* s_nb = reinterpret_cast<uint32_t*>(s_raw + (size_t)56 * NF);                 // [14][NF] 7x7 u8 neighbourhood
-    float2* s_sub = reinterpret_cast<float2*>(s_raw + (size_t)(56 + 4 * NB_WORDS) * NF);   // [NF] sub-pixel offsets (DSDTM_SA_STAGE 0) ...
+#endif
+    uint32_t* s_nb = reinterpret_cast<uint32_t*>(s_raw + (size_t)SB * NF);                 // [14][NF] 7x7 u8 neighbourhood
+    float2* s_sub = reinterpret_cast<float2*>(s_raw + (size_t)(SB + 4 * NB_WORDS) * NF);   // [NF] sub-pixel offsets (DSDTM_SA_STAGE 0) ...
     float2* s_px = s_sub;                                                                  // ... or the feature's level-0 pixel (DSDTM_SA_STAGE 1)
-    uint8_t* s_valid = s_raw + (size_t)(56 + 4 * NB_WORDS + 8) * NF;                       // [NF] bit 0: staged at this level, bit 1: has a map point (all levels)
+    uint8_t* s_valid = s_raw + (size_t)(SB + 4 * NB_WORDS + 8) * NF;                       // [NF] bit 0: staged at this level, bit 1: has a map point (all levels)
+#if DSDTM_SA_COMPACT
+    uint16_t* s_idx = reinterpret_cast<uint16_t*>(s_raw + (size_t)(SB + 4 * NB_WORDS + 8 + 1) * NF);   // [NF] the features staged at this level, ascending
+    __shared__ int s_nvalid;
+#endif
     __shared__ double s_red[WPP][8];
     __shared__ int s_cnt[WPP];
     __shared__ double s_redH[WPP][22];
@@ -270,6 +298,9 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
     const double cen0 = a.centers[3 * pair], cen1 = a.centers[3 * pair + 1], cen2 = a.centers[3 * pair + 2];
     const double fx = (double)a.fx, fy = (double)a.fy, cx = (double)a.cx, cy = (double)a.cy;
 
+#ifdef DSDTM_SA_TIMING
+    const long long tkp0 = clock64();
+#endif
     if (tid < 7) { s_T[tid] = a.poses_in[7 * pair + tid]; s_Told[tid] = s_T[tid]; }
     if (tid == 0) { s_npts = 0; s_nlog = 0; s_stop = 0; s_chi2prev = 0.0; }
 #if DSDTM_SA_STAGE == 1
@@ -308,19 +339,23 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
         const double fs = (double)a.f * scale;     // == (v * f) * scale bit-exactly, scale being a power of two
         const double fs2 = fs * fs;
 
+#ifdef DSDTM_SA_TIMING
+        const long long tks0 = clock64();     // x[2] of a level's first log entry: cycles of the level staging; x[1] of the very first entry: the prologue
+#endif
         // ------------------------------------------------ level staging = the pose-independent part of GetJocabianMat (ref: :62-132)
 #if DSDTM_SA_STAGE == 1
         // Two features per thread and step, straight-line: both features' 21 aligned window loads are in flight together (the loop
         // used to pay two dependent DRAM round trips per feature -- record, then window -- four times per level: ~15 k cycles of
         // a 360 k-cycle pair). The level-independent part (point in the reference camera, 1 / z) is done once in the prologue.
         {
+            constexpr int SG = DSDTM_SA_STAGE_G;
             const uint8_t* __restrict__ img = ref_frame + a.geo.off[level];
-            for (int f0 = tid; f0 < nfeat; f0 += 2 * NT) {
-                uint32_t w[2][7][3];
-                unsigned a0[2];
-                bool val[2];
+            for (int f0 = tid; f0 < nfeat; f0 += SG * NT) {
+                uint32_t w[SG][7][3];
+                unsigned a0[SG];
+                bool val[SG];
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < SG; ++g) {
                     const int f = f0 + g * NT;
                     val[g] = false; a0[g] = 0u;
                     if (f < nfeat && (s_valid[f] & 2)) {                                                  // ref: :86 and the zero-point test of :95
@@ -345,7 +380,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 // while the reference windows are in flight: ask for the rows of the CURRENT image the first iteration of this level
                 // will gather (pose at level start). Addresses only -- fp32 projection, nothing here reaches a result.
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < SG; ++g) {
                     const int f = f0 + g * NT;
                     if (val[g]) {
                         const float q0 = (float)s_T[0], q1 = (float)s_T[1], q2 = (float)s_T[2], q3 = (float)s_T[3];
@@ -368,7 +403,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 }
 #endif
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < SG; ++g) {
                     const int f = f0 + g * NT;
                     if (f < nfeat) {
 #pragma unroll
@@ -420,6 +455,25 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
         }
 #endif
         __syncthreads();
+#if DSDTM_SA_COMPACT
+        // stable compaction of the staged features (warp 0, ballot + popc per chunk of 32): deterministic, ascending feature order
+        if (warp == 0) {
+            int base = 0;
+            for (int c = 0; c < nfeat; c += 32) {
+                const int f = c + lane;
+                const bool v = f < nfeat && (s_valid[f] & 1);
+                const unsigned m = __ballot_sync(0xffffffffu, v);
+                if (v) s_idx[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)f;
+                base += __popc(m);
+            }
+            if (lane == 0) s_nvalid = base;
+        }
+        __syncthreads();
+        const int nvalid = s_nvalid;
+#endif
+#ifdef DSDTM_SA_TIMING
+        const long long tks1 = clock64();
+#endif
 
         unsigned prev_vis = 0;
         const uint8_t* __restrict__ cimg = cur_frame + a.geo.off[level];
@@ -431,6 +485,11 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
 #endif
             const double qw = s_T[0], qx = s_T[1], qy = s_T[2], qz = s_T[3];
             const double t0 = s_T[4], t1 = s_T[5], t2 = s_T[6];
+#if DSDTM_SA_RMAT && !DSDTM_SA_STRICT
+            const double r00 = 1.0 - 2.0 * (qy * qy + qz * qz), r01 = 2.0 * (qx * qy - qw * qz), r02 = 2.0 * (qx * qz + qw * qy);
+            const double r10 = 2.0 * (qx * qy + qw * qz), r11 = 1.0 - 2.0 * (qx * qx + qz * qz), r12 = 2.0 * (qy * qz - qw * qx);
+            const double r20 = 2.0 * (qx * qz - qw * qy), r21 = 2.0 * (qy * qz + qw * qx), r22 = 1.0 - 2.0 * (qx * qx + qy * qy);
+#endif
             double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0, accc = 0;
             int cnt = 0;
             static_assert(DSDTM_MAX_FEATS_LIMIT <= 32 * 32, "vis_mask holds one bit per feature of a lane: at most 32 features per lane at WPP = 1");
@@ -444,8 +503,14 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 p.valid = true;
                 const double P0 = s_P[f], P1 = s_P[NF + f], P2 = s_P[2 * NF + f];
                 double Q0, Q1, Q2;
+#if DSDTM_SA_RMAT && !DSDTM_SA_STRICT
+                Q0 = fma(r02, P2, fma(r01, P1, fma(r00, P0, t0)));
+                Q1 = fma(r12, P2, fma(r11, P1, fma(r10, P0, t1)));
+                Q2 = fma(r22, P2, fma(r21, P1, fma(r20, P0, t2)));
+#else
                 qrot(qw, qx, qy, qz, P0, P1, P2, Q0, Q1, Q2);                                  // ref: :254
                 Q0 = __dadd_rn(Q0, t0); Q1 = __dadd_rn(Q1, t1); Q2 = __dadd_rn(Q2, t2);
+#endif
                 // Camera2Pixel * tScale (ref: src/Camera.cpp:167-171, :255): (fx*X)/Z + cx
 #if DSDTM_SA_STRICT
                 const double u = __dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(fx, Q0), Q2), cx), scale);
@@ -587,11 +652,20 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     for (int f = tid; f < nfeat; f += NT, ++kq) { Pre me; stage1(f, me); stage2(std::false_type{}, f, kq, me); }
                 }
 #else
+#if DSDTM_SA_COMPACT
+                for (int k = tid; k < nvalid; k += NT, ++kq) {
+                    const int f = s_idx[k];
+                    Pre me;
+                    stage1(f, me);
+                    stage2(first, f, kq, me);
+                }
+#else
                 for (int f = tid; f < nfeat; f += NT, ++kq) {
                     Pre me;
                     stage1(f, me);
                     stage2(first, f, kq, me);
                 }
+#endif
 #endif
             }
 #ifdef DSDTM_SA_TIMING
@@ -635,8 +709,13 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                         }
                 };
                 int kk = 0;
+#if DSDTM_SA_COMPACT
+                for (int k = tid; k < nvalid; k += NT, ++kk)
+                    if ((vis_mask >> kk) & 1u) add_H(s_idx[k]);
+#else
                 for (int f = tid; f < nfeat; f += NT, ++kk)
                     if ((vis_mask >> kk) & 1u) add_H(f);
+#endif
 #pragma unroll
                 for (int i = 0; i < 21; ++i) {
                     const double h = warp_sum(hacc[i]);
@@ -702,6 +781,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                             for (int q = 0; q < 6; ++q) e->x[q] = x[q];
 #ifdef DSDTM_SA_TIMING
                             e->x[3] = (double)(tk1 - tk0); e->x[4] = (double)(tk2 - tk1); e->x[5] = (double)(clock64() - tk2);
+                            if (it == 0) { e->x[2] = (double)(tks1 - tks0); if (level == a.max_level - 1) e->x[1] = (double)(tks0 - tkp0); }
 #endif
                         }
                         s_nlog = n + 1;
@@ -1038,7 +1118,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 8 : (WPP == 3 ? 4 : (WP
     }
 }
 
-int smem_bytes(int nf) { return (56 + 4 * NB_WORDS + 8 + 1) * nf; }
+int smem_bytes(int nf) { return ((DSDTM_SA_SGLOBAL ? 32 : 56) + 4 * NB_WORDS + 8 + 1 + (DSDTM_SA_COMPACT ? 2 : 0)) * nf; }
 int round_nf(int max_feats) { return (max_feats + 15) / 16 * 16; }
 
 int smem_bytes_ws(int nf) { return (48 + 1) * nf; }
@@ -1131,6 +1211,7 @@ cudaError_t launch_sparse_align(dsdtm_ctx* c, int n_pairs, int feat_stride, int 
     a.nf = round_nf(c->prm.max_feats);
     a.ws = (c->sa_variant == 1) ? c->sa_ws_d : nullptr;
     a.variant = c->sa_variant;
+    a.mom = c->sa_ws_d;
     a.pair0 = pair0;
     c->launches++;
     // warps-per-pair is chosen from the size of the WHOLE batch so that chunked (e2e) and single-launch runs reduce in the same order

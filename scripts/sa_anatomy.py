@@ -9,7 +9,7 @@ from dsdtm_b200 import capi, synth as S, workload as W
 
 def main():
     cam = dict(S.KINECT)
-    for B, wpps in ((1, (10,)), (4096, (3, 4))):
+    for B, wpps in ((1, (10,)), (4096, (3,))):
         ctx = capi.Context(cam, levels=5, max_feats=320, max_patches=300, max_frames=2 * B + 2, max_batch=B)
         batch = W.build_batch(ctx, cam, B, scenes=W.render_scenes(2, cam, procs=1), n_feats=300, feat_stride=320, patches_per_pair=300)
         for wpp in wpps:
@@ -22,6 +22,8 @@ def main():
                 c = r["x"][:, 3:6]
                 print("pairs %4d wpp %2d %-27s n=%4d  pass %7.0f  reduce+barrier %6.0f  tail %6.0f cycles (median) | tail share %.0f %%" % (
                     B, wpp, name, len(r), np.median(c[:, 0]), np.median(c[:, 1]), np.median(c[:, 2]), 100 * np.median(c[:, 2]) / np.median(c.sum(1))))
+            print("pairs %4d wpp %2d level staging %7.0f cycles (median), prologue %7.0f" % (B, wpp, np.median(first["x"][:, 2]),
+                  np.median(rows[(rows["iter"] == 0) & (rows["level"] == 3)]["x"][:, 1])))
         ctx.close()
 
 
