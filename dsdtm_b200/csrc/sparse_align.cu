@@ -244,6 +244,10 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 #define DSDTM_SA_RMAT 0          // 1 = the point is rotated with the 3x3 matrix of the pose's quaternion (9 FMA) instead of Eigen's quaternion formula (30 operations):
                                  // 1.210 vs 1.215 ms, results move in the last bits; not worth leaving the reference's expression
 #endif
+#ifndef DSDTM_SA_LD64
+#define DSDTM_SA_LD64 0          // bit 0: level staging, bit 1: feature pass gather with 8-byte aligned 64-bit loads (the second load predicated): fewer L1 requests,
+                                 // measured 1.224 (staging) / 1.285 (pass) vs 1.219 ms -- L1 request slots are not what the gathers wait for; off
+#endif
 #ifndef DSDTM_SA_PREF
 #define DSDTM_SA_PREF 0          // 1 = the level staging prefetches the current-image rows of the first iteration (needs DSDTM_SA_STAGE 1): measured SLOWER, 1.292 vs 1.216 ms
 #endif
@@ -369,12 +373,27 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                             a0[g] = (unsigned)(fyi - 3) * (unsigned)cols + (unsigned)(fxi - 3);
                         }
                     }
+#if DSDTM_SA_LD64 & 1
+                    // 8-byte aligned 64-bit loads: the 7 bytes of a row start at byte s = ad & 7 of the first pair of words and need the second
+                    // pair only for s >= 2 -- 1.75 load requests per row instead of three 32-bit ones (the staging is bound by L1 request slots)
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {
+                        const unsigned ad = a0[g] + (unsigned)r * (unsigned)cols;
+                        const uint2* wp = reinterpret_cast<const uint2*>(img + (ad & ~7u));
+                        const uint2 lo = __ldg(wp);
+                        uint2 hi = make_uint2(0u, 0u);
+                        if ((ad & 7u) >= 2u) hi = __ldg(wp + 1);
+                        const bool up = (ad & 4u) != 0u;
+                        w[g][r][0] = up ? lo.y : lo.x; w[g][r][1] = up ? hi.x : lo.y; w[g][r][2] = up ? hi.y : hi.x;
+                    }
+#else
 #pragma unroll
                     for (int r = 0; r < 7; ++r) {          // unconditional (offset 0 for a feature that is not staged): no branch between the loads
                         const unsigned ad = a0[g] + (unsigned)r * (unsigned)cols;
                         const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (ad & ~3u));
                         w[g][r][0] = __ldg(wp); w[g][r][1] = __ldg(wp + 1); w[g][r][2] = __ldg(wp + 2);
                     }
+#endif
                 }
 #if DSDTM_SA_PREF
                 // while the reference windows are in flight: ask for the rows of the CURRENT image the first iteration of this level
@@ -536,8 +555,18 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
                     const unsigned ad = c0w + (unsigned)r * (unsigned)cols;
+#if DSDTM_SA_LD64 & 2
+                    // bytes s .. s+4 of the row, s = ad & 7: one 8-byte aligned 64-bit load, plus the next word only for s >= 4
+                    const uint2* wp = reinterpret_cast<const uint2*>(cimg + (ad & ~7u));
+                    const uint2 w01 = __ldg(wp);
+                    uint32_t w2 = 0u;
+                    if ((ad & 7u) >= 4u) w2 = __ldg(reinterpret_cast<const uint32_t*>(wp + 1));
+                    const bool up = (ad & 4u) != 0u;
+                    const uint32_t lo = up ? w01.y : w01.x, hi = up ? w2 : w01.y;
+#else
                     const uint32_t* wp = reinterpret_cast<const uint32_t*>(cimg + (ad & ~3u));
                     const uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
+#endif
                     const int sh = 8 * (ad & 3u);
                     p.cw0[r] = __funnelshift_r(lo, hi, sh);
                     p.cw1[r] = hi >> sh;
