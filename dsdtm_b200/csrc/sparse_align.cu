@@ -1147,7 +1147,10 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 8 : (WPP == 3 ? 4 : (WP
     }
 }
 
-int smem_bytes(int nf) { return ((DSDTM_SA_SGLOBAL ? 32 : 56) + 4 * NB_WORDS + 8 + 1 + (DSDTM_SA_COMPACT ? 2 : 0)) * nf; }
+#ifndef DSDTM_SA_PAD
+#define DSDTM_SA_PAD 0           // experiment: bytes of unused dynamic shared memory per CTA (with DSDTM_SA_CARVEOUT3 it caps the resident CTAs per SM)
+#endif
+int smem_bytes(int nf) { return ((DSDTM_SA_SGLOBAL ? 32 : 56) + 4 * NB_WORDS + 8 + 1 + (DSDTM_SA_COMPACT ? 2 : 0)) * nf + DSDTM_SA_PAD; }
 int round_nf(int max_feats) { return (max_feats + 15) / 16 * 16; }
 
 int smem_bytes_ws(int nf) { return (48 + 1) * nf; }
@@ -1184,6 +1187,9 @@ cudaError_t sparse_align_init(dsdtm_ctx* c)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_bytes);
 #ifdef DSDTM_SA_CARVEOUT
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, DSDTM_SA_CARVEOUT);
+#endif
+#ifdef DSDTM_SA_CARVEOUT3
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, DSDTM_SA_CARVEOUT3);
 #endif
     if (e == cudaSuccess) {
         int n = 0;
