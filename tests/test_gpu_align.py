@@ -123,6 +123,37 @@ def test_sparse_align_many_features_and_other_geometry(built):
     c.close()
 
 
+def test_sparse_align_subnormal_byte_encoding_keeps_full_precision(ctx):
+    """The kernel feeds image bytes to the fp64 arithmetic as subnormals b * 2^-1034 with weights scaled by 2^1010 (csrc/sparse_align.cu,
+    DSDTM_SA_CVT 3); the claim is that every sample keeps the reference's rounding. Stress it where a loss would show: images of
+    extreme bytes (0 / 255 blocks, so that products with tiny weights sit next to full-scale ones), refined (non-dyadic float) feature
+    positions, a start pose with arbitrary fractions. Agreement with the oracle must be at summation-order level (1e-12), six orders
+    tighter than the north_star tolerances, at every logged iteration."""
+    sc = H.make_scenario(11, trans=0.015, rot_deg=0.4)
+    rng = np.random.default_rng(5)
+    hard = {}
+    for k in ("ref_img", "cur_img"):
+        img = sc[k].copy()
+        img[(img > 150)] = 255
+        img[(img < 90)] = 0
+        hard[k] = img
+    ctx.upload(4, hard["ref_img"])
+    ctx.upload(5, hard["cur_img"])
+    ref_pyr = O.pyramid(hard["ref_img"], 5)
+    cur_pyr = O.pyramid(hard["cur_img"], 5)
+    feats = sc["feats"].copy()
+    feats["px"] = (feats["px"] + rng.uniform(0.0, 1.0, feats["px"].shape)).astype(np.float32)      # refined positions: arbitrary float fractions
+    start = S.pose_from_xi(rng.uniform(-0.003, 0.003, 6))
+    packed, offs, ws, hs = ref_pyr
+    po, no, lo = O.sparse_align(H.ocam(sc["cam"]), packed, cur_pyr[0], offs, ws, hs, feats, sc["ref_center"], start, 4, 0, 30)
+    pg, ng, lg = ctx.sparse_align(4, 5, feats, sc["ref_center"], start, 4, 0, 30)
+    assert no == ng and len(lo) == len(lg)
+    assert np.abs(po - pg).max() < 1e-12
+    for a, b in zip(lo, lg):
+        assert (a["level"], a["iter"], a["n_pts"], a["flags"]) == (b["level"], b["iter"], b["n_pts"], b["flags"])
+        assert abs(a["chi2"] - b["chi2"]) <= 1e-12 * abs(a["chi2"])
+
+
 def test_sparse_align_rank_deficient_system_is_handled(ctx, scenario):
     """Two visible features give a rank-4 H. In floating point the two 'zero' pivots come out as rounding noise (1e-17
     relative), Eigen's ldlt().solve divides by them (its zero rule only triggers below 5e-309), and the step is dominated
