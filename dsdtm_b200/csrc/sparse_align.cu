@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     // pair only for s >= 2 -- 1.75 load requests per row instead of three 32-bit ones (the staging is bound by L1 request slots)
 #pragma unroll
                     for (int r = 0; r < 7; ++r) {
-                        const unsigned ad = a0[g] + (unsigned)r * (unsigned)cols;
+                        const unsigned ad = a0[g] + (unsigned)r * (val[g] ? (unsigned)cols : 0u);
                         const uint2* wp = reinterpret_cast<const uint2*>(img + (ad & ~7u));
                         const uint2 lo = __ldg(wp);
                         uint2 hi = make_uint2(0u, 0u);
@@ -387,9 +387,12 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                         w[g][r][0] = up ? lo.y : lo.x; w[g][r][1] = up ? hi.x : lo.y; w[g][r][2] = up ? hi.y : hi.x;
                     }
 #else
+                    // unconditional: no branch between the loads. A feature that is not staged reads the first 12 bytes of the level seven
+                    // times (row stride 0), which exist for every level geometry (a slot ends with 64 zero bytes)
+                    const unsigned rstride = val[g] ? (unsigned)cols : 0u;
 #pragma unroll
-                    for (int r = 0; r < 7; ++r) {          // unconditional (offset 0 for a feature that is not staged): no branch between the loads
-                        const unsigned ad = a0[g] + (unsigned)r * (unsigned)cols;
+                    for (int r = 0; r < 7; ++r) {
+                        const unsigned ad = a0[g] + (unsigned)r * rstride;
                         const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (ad & ~3u));
                         w[g][r][0] = __ldg(wp); w[g][r][1] = __ldg(wp + 1); w[g][r][2] = __ldg(wp + 2);
                     }
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     if (f < nfeat) {
 #pragma unroll
                         for (int r = 0; r < 7; ++r) {
-                            const int sh = 8 * ((a0[g] + (unsigned)r * (unsigned)cols) & 3u);
+                            const int sh = 8 * ((a0[g] + (unsigned)r * (val[g] ? (unsigned)cols : 0u)) & 3u);
                             s_nb[(2 * r) * NF + f] = __funnelshift_r(w[g][r][0], w[g][r][1], sh);
                             s_nb[(2 * r + 1) * NF + f] = __funnelshift_r(w[g][r][1], w[g][r][2], sh);
                         }

@@ -123,6 +123,29 @@ def test_sparse_align_many_features_and_other_geometry(built):
     c.close()
 
 
+def test_sparse_align_levels_too_small_for_any_feature(built):
+    """A 160x96 image with five levels ends in a 10x6 level: no feature passes the 3-pixel border test there (ref:
+    src/Sprase_ImageAlign.cpp:95-96), so the level staging stages nothing -- its unconditional window loads must stay inside the level
+    (the reference frame sits in the LAST slot of the pool here) -- chi2 is NaN (Q2) and the pose moves on to the next level unchanged."""
+    from dsdtm_b200 import capi
+    cam = dict(width=160, height=96, fx=130.0, fy=130.0, cx=79.5, cy=47.5, f=130.0)
+    sc = H.make_scenario(5, cam, levels=5, max_fts=150, trans=0.004, rot_deg=0.1)
+    c = capi.Context(cam, levels=5, cell_size=15, max_feats=160, max_patches=8, max_frames=2, max_batch=1)
+    c.upload(1, sc["ref_img"]); c.upload(0, sc["cur_img"])
+    packed, offs, ws, hs = sc["ref_pyr"]
+    assert hs[4] < 7
+    po, no, lo = O.sparse_align(H.ocam(cam), packed, sc["cur_pyr"][0], offs, ws, hs, sc["feats"], sc["ref_center"], S.IDENTITY, 5, 0, 8)
+    for wpp in (0, 1, 3):
+        c.set_option("sa_warps_per_pair", wpp)
+        pg, ng, lg = c.sparse_align(1, 0, sc["feats"], sc["ref_center"], S.IDENTITY, 5, 0, 8)
+        pg2, ng2, lg2 = c.sparse_align(1, 0, sc["feats"], sc["ref_center"], S.IDENTITY, 5, 0, 8)
+        assert (pg == pg2).all() and ng == ng2 and np.isfinite(pg).all()
+        assert lg[0]["level"] == 4 and lg[0]["n_pts"] == 0 == lo[0]["n_pts"] and np.isnan(lg[0]["chi2"]) and lg[0]["flags"] == lo[0]["flags"]
+        first3 = [e for e in lg if e["level"] == 3][0]; ofirst3 = [e for e in lo if e["level"] == 3][0]
+        assert first3["n_pts"] == ofirst3["n_pts"] and abs(first3["chi2"] - ofirst3["chi2"]) <= 1e-9 * abs(ofirst3["chi2"])
+    c.close()
+
+
 def test_sparse_align_subnormal_byte_encoding_keeps_full_precision(ctx):
     """The kernel feeds image bytes to the fp64 arithmetic as subnormals b * 2^-1034 with weights scaled by 2^1010 (csrc/sparse_align.cu,
     DSDTM_SA_CVT 3); the claim is that every sample keeps the reference's rounding. Stress it where a loss would show: images of
