@@ -217,11 +217,16 @@ __device__ DSDTM_TAIL_ATTR void pose_update(const double* T, const double (&x)[6
     for (int q = 0; q < 7; ++q) Tn[q] = To[q];
 }
 
-struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
-
 #ifndef DSDTM_SA_PIPELINE
-#define DSDTM_SA_PIPELINE 0      // 1 = issue feature k+1's gather before feature k's arithmetic. Measured slower (1.22 vs 1.12 ms, profiles/r1_sparse_align_v3.md): registers
+#define DSDTM_SA_PIPELINE 0      // 1 = issue feature k+1's projection + gather before feature k's arithmetic. Round 1: slower (registers). Round 2 again, now
+                                 // without spills (158 registers): 1.274 vs 1.220 ms -- the pass does not wait for memory, hiding the gather buys nothing
 #endif
+#if DSDTM_SA_PIPELINE
+struct Pre { bool valid, vis; double su, sv; uint32_t cw0[5], cw1[5]; };     // carried across a feature's arithmetic: fractions instead of the four weights
+#else
+struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
+#endif
+
 // (Tried and removed: staging an 8 x 7 window of the CURRENT image per feature in shared memory at level start, so that the
 // iterations of a level stop re-gathering it from global memory. 173 instead of 113 B/feature of shared memory took more L1
 // away than the re-gathers cost: 1.68 vs 1.55 ms per 4096 pairs, 86 vs 84 us for a single pair. profiles/r1_sparse_align_v3.md)
@@ -549,11 +554,15 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 p.vis = true;
                 const int ui = (int)uf, vi = (int)vf;
                 const double su = u - uf, sv = v - vf;
+#if DSDTM_SA_PIPELINE
+                p.su = su; p.sv = sv;
+#else
                 {   // ref: :267-270; the second factor carries SA_WSCALE (a power of two: the products round exactly as unscaled)
                     const double osv = (1.0 - sv) * SA_WSCALE, svs = sv * SA_WSCALE;
                     p.tl = __dmul_rn(1.0 - su, osv); p.tr = __dmul_rn(su, osv);
                     p.bl = __dmul_rn(1.0 - su, svs); p.br = __dmul_rn(su, svs);
                 }
+#endif
                 const unsigned c0w = (unsigned)(vi - 2) * (unsigned)cols + (unsigned)(ui - 2);
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
@@ -588,6 +597,13 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
 #endif
                 if (!(first ? me.valid : me.vis)) return;
                 const bool vis = me.vis;
+#if DSDTM_SA_PIPELINE
+                const double osv_ = (1.0 - me.sv) * SA_WSCALE, svs_ = me.sv * SA_WSCALE;
+                const double me_tl = __dmul_rn(1.0 - me.su, osv_), me_tr = __dmul_rn(me.su, osv_);
+                const double me_bl = __dmul_rn(1.0 - me.su, svs_), me_br = __dmul_rn(me.su, svs_);
+#else
+                const double me_tl = me.tl, me_tr = me.tr, me_bl = me.bl, me_br = me.br;
+#endif
                 if (vis) { vis_mask |= 1u << k; ++cnt; }
                 RefRowsT<true> R;
                 {
@@ -643,7 +659,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
 #else
                         dxa[c] = dx2; dya[c] = dy2;
 #endif
-                        const double cur = bil(me.tl, me.tr, me.bl, me.br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
+                        const double cur = bil(me_tl, me_tr, me_bl, me_br, Cw[ca][c], Cw[ca][c + 1], Cw[cb][c], Cw[cb][c + 1]);   // ref: :281
                         const double res = __dsub_rn(cur, refv);                                          // ref: :282
 #if DSDTM_SA_STRICT
                         c2 = __dadd_rn(c2, __dmul_rn(res, res));                                          // ref: :284
@@ -684,7 +700,18 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     for (int f = tid; f < nfeat; f += NT, ++kq) { Pre me; stage1(f, me); stage2(std::false_type{}, f, kq, me); }
                 }
 #else
-#if DSDTM_SA_COMPACT
+#if DSDTM_SA_PIPELINE
+                {
+                    Pre me, nx;
+                    int f = tid;
+                    stage1(f, me);
+                    for (; f < nfeat; f += NT, ++kq) {
+                        stage1(f + NT, nx);            // the next feature's projection and window loads are in flight during this one's arithmetic
+                        stage2(first, f, kq, me);
+                        me = nx;
+                    }
+                }
+#elif DSDTM_SA_COMPACT
                 for (int k = tid; k < nvalid; k += NT, ++kq) {
                     const int f = s_idx[k];
                     Pre me;
