@@ -129,6 +129,36 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+#ifndef DSDTM_SA_TREDUCE
+#define DSDTM_SA_TREDUCE 1       // 1 = the 7 per-iteration sums and the 21 entries of H meet in a transposed warp reduction (lane l ends with total l:
+                                 // 21 resp. 31 exchanges instead of 35 resp. 105) and lanes write their own entry of the shared-memory row
+#endif
+// Sum N <= 32 per-lane values over the warp so that lane l ends up with the total of value l (the reduction of pose_opt.cuh): at the stage
+// with offset o a lane keeps the half of its values whose index has bit o equal to its own lane bit and hands the other half to its partner.
+// Deterministic; lanes >= N end with the total of a zero column.
+template <int N>
+__device__ __forceinline__ double warp_sum_transposed(const double (&v)[N])
+{
+    static_assert(N <= 32, "one value per lane");
+    const int lane = threadIdx.x & 31;
+    double w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = i < N ? v[i] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            if (i >= N) continue;
+            const double lo = w[i], hi = w[i + o];
+            const double keep = up ? hi : lo;
+            const double send = up ? lo : hi;
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return w[0];
+}
+
 // Reference-side samples of one feature, re-derived from its staged 7x7 neighbourhood. Row r of the 4x4 patch:
 //   ref[c] = G[r+1][c+1], dx[c] = 0.5 (G[r+1][c+2] - G[r+1][c]), dy[c] = 0.5 (G[r+2][c+1] - G[r][c+1])
 // with G[y][x] = bil(w; N[y][x], N[y][x+1], N[y+1][x], N[y+1][x+1]) -- the reference's expressions (ref: :147-158).
@@ -731,14 +761,29 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
             const long long tk1 = clock64();
 #endif
             accc *= SA_RESTORE2;      // the lane's sum of squared residuals carried 2^-48 (exact: a sum of scaled terms is the scaled sum)
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+#if DSDTM_SA_TREDUCE
+            {
+                const double av7[7] = { acc0, acc1, acc2, acc3, acc4, acc5, accc };
+                const double tot = warp_sum_transposed(av7);          // lane l < 7: total of value l
+                if (WPP > 1) {
+                    if (lane < 7) s_red[warp][lane] = tot;
+                    if (lane == 0) s_cnt[warp] = cnt;
+                } else {
+                    acc0 = __shfl_sync(0xffffffffu, tot, 0); acc1 = __shfl_sync(0xffffffffu, tot, 1); acc2 = __shfl_sync(0xffffffffu, tot, 2);
+                    acc3 = __shfl_sync(0xffffffffu, tot, 3); acc4 = __shfl_sync(0xffffffffu, tot, 4); acc5 = __shfl_sync(0xffffffffu, tot, 5);
+                    accc = __shfl_sync(0xffffffffu, tot, 6);
+                }
+            }
+#else
             acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2); acc3 = warp_sum(acc3);
             acc4 = warp_sum(acc4); acc5 = warp_sum(acc5); accc = warp_sum(accc);
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
             if (WPP > 1 && lane == 0) {
                 s_red[warp][0] = acc0; s_red[warp][1] = acc1; s_red[warp][2] = acc2; s_red[warp][3] = acc3;
                 s_red[warp][4] = acc4; s_red[warp][5] = acc5; s_red[warp][6] = accc;
                 s_cnt[warp] = cnt;
             }
+#endif
             const int need_H = __syncthreads_or((it == 0) || (vis_mask != prev_vis));
             prev_vis = vis_mask;
             if (need_H) {
@@ -775,12 +820,19 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                 for (int f = tid; f < nfeat; f += NT, ++kk)
                     if ((vis_mask >> kk) & 1u) add_H(f);
 #endif
+#if DSDTM_SA_TREDUCE
+                {
+                    const double h = warp_sum_transposed(hacc);       // lane l < 21: total of entry l
+                    if (lane < 21) { if (WPP > 1) s_redH[warp][lane] = h; else s_H[lane] = h; }
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < 21; ++i) {
                     const double h = warp_sum(hacc[i]);
                     if (WPP > 1) { if (lane == 0) s_redH[warp][i] = h; }
                     else if (lane == 0) s_H[i] = h;
                 }
+#endif
                 if (WPP > 1) __syncthreads();
             }
             if (warp == 0) {
