@@ -283,6 +283,10 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 #define DSDTM_SA_LD64 0          // bit 0: level staging, bit 1: feature pass gather with 8-byte aligned 64-bit loads (the second load predicated): fewer L1 requests,
                                  // measured 1.224 (staging) / 1.285 (pass) vs 1.219 ms -- L1 request slots are not what the gathers wait for; off
 #endif
+#ifndef DSDTM_SA_PREF_NEXT
+#define DSDTM_SA_PREF_NEXT 0     // 1 = the staging of a level prefetches the next level's reference rows into L2: 1.260 vs 1.205 ms (a scattered prefetch costs a
+                                 // full L1 request per lane like a load); off
+#endif
 #ifndef DSDTM_SA_PREF
 #define DSDTM_SA_PREF 0          // 1 = the level staging prefetches the current-image rows of the first iteration (needs DSDTM_SA_STAGE 1): measured SLOWER, 1.292 vs 1.216 ms
 #endif
@@ -433,6 +437,31 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     }
 #endif
                 }
+#if DSDTM_SA_PREF_NEXT
+                // while this level's windows are in flight: pull the NEXT (finer) level's reference rows of the same features into L2, so that
+                // the next staging finds them there instead of in DRAM. Fire and forget; addresses only.
+                if (level > a.min_level) {
+                    const int ncols = a.geo.w[level - 1], nrows = a.geo.h[level - 1];
+                    const uint8_t* __restrict__ nimg = ref_frame + a.geo.off[level - 1];
+                    const float nscale = 2.0f * tScale;
+#pragma unroll
+                    for (int g = 0; g < SG; ++g) {
+                        const int f = f0 + g * NT;
+                        if (f < nfeat && (s_valid[f] & 2)) {
+                            const float2 p = s_px[f];
+                            const int nx = (int)(p.x * nscale), ny = (int)(p.y * nscale);
+                            if (nx >= 3 && ny >= 3 && nx + 3 < ncols && ny + 3 < nrows) {
+                                const uint8_t* q = nimg + (unsigned)(ny - 3) * (unsigned)ncols + (unsigned)(nx - 3);
+#pragma unroll
+                                for (int r = 0; r < 7; ++r) {
+                                    asm volatile("prefetch.global.L2 [%0];" :: "l"(q + (size_t)r * ncols));
+                                    if (((size_t)(q + (size_t)r * ncols) & 31) > 25) asm volatile("prefetch.global.L2 [%0];" :: "l"(q + (size_t)r * ncols + 6));
+                                }
+                            }
+                        }
+                    }
+                }
+#endif
 #if DSDTM_SA_PREF
                 // while the reference windows are in flight: ask for the rows of the CURRENT image the first iteration of this level
                 // will gather (pose at level start). Addresses only -- fp32 projection, nothing here reaches a result.
