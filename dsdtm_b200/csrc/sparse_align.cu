@@ -135,7 +135,7 @@ __device__ __forceinline__ double warp_sum(double v)
 #endif
 // Sum N <= 32 per-lane values over the warp so that lane l ends up with the total of value l (the reduction of pose_opt.cuh): at the stage
 // with offset o a lane keeps the half of its values whose index has bit o equal to its own lane bit and hands the other half to its partner.
-// Deterministic; lanes >= N end with the total of a zero column.
+// Deterministic; only lanes < N hold a defined result.
 template <int N>
 __device__ __forceinline__ double warp_sum_transposed(const double (&v)[N])
 {
@@ -150,6 +150,12 @@ __device__ __forceinline__ double warp_sum_transposed(const double (&v)[N])
 #pragma unroll
         for (int i = 0; i < o; ++i) {
             if (i >= N) continue;
+            if (i + o >= N) {
+                // the partner column is a zero column: the plain butterfly gives the lanes that keep column i the same sum without the two
+                // selects (the other lanes then carry a value nobody reads: later stages only pair lanes with equal upper bits)
+                w[i] += __shfl_xor_sync(0xffffffffu, w[i], o);
+                continue;
+            }
             const double lo = w[i], hi = w[i + o];
             const double keep = up ? hi : lo;
             const double send = up ? lo : hi;
