@@ -235,20 +235,33 @@ DSDTM_HD void ldlt6_subst_spd(const double (&Lp)[15], const double (&dinv)[6], c
 struct Quat { double w, x, y, z; };
 
 // out = T * exp(x); pose7 = {qw,qx,qy,qz,tx,ty,tz}. (ref: src/Sprase_ImageAlign.cpp:335; Sophus SE3::exp, SE3::operator*=)
-DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&out)[7])
+DSDTM_HD double se3_theta2(const double (&x)[6])
+{
+    const double o0 = x[3], o1 = x[4], o2 = x[5];
+    return o0 * o0 + o1 * o1 + o2 * o2;
+}
+DSDTM_HD bool se3_exp_uses_series(double t2)
+{
+#ifndef DSDTM_SE3_SERIES
+#define DSDTM_SE3_SERIES 1
+#endif
+    return DSDTM_SE3_SERIES && t2 < 0.25;
+}
+
+// `series4` (optional): the values of the four power series below for se3_theta2(x), evaluated elsewhere with the same Horner steps (the
+// sparse-alignment kernel spreads them over four lanes of the warp that runs the solve, csrc/sparse_align.cu); only read when
+// se3_exp_uses_series(se3_theta2(x)).
+DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&out)[7], const double* series4 = nullptr)
 {
     // This runs on ONE lane while the rest of the CTA waits, so the dependent chain is kept short: one sincos (the full-angle
     // values come from the half-angle identities), reciprocals instead of repeated divisions. Against the literal Sophus
     // sequence (the oracle) the result differs by a few ulp (tests/test_host_math.py: <= 1e-15 absolute).
     const double SMALL_EPS = 1e-10;
     const double u0 = x[0], u1 = x[1], u2 = x[2], o0 = x[3], o1 = x[4], o2 = x[5];
-    const double t2 = o0 * o0 + o1 * o1 + o2 * o2;
+    const double t2 = se3_theta2(x);
     double theta, ch, imag, a, b;
     double ew, ex, ey, ez;
-#ifndef DSDTM_SE3_SERIES
-#define DSDTM_SE3_SERIES 1
-#endif
-    const bool series = DSDTM_SE3_SERIES && t2 < 0.25;
+    const bool series = se3_exp_uses_series(t2);
     if (series) {
         // |theta| < 0.5 rad (every Gauss-Newton step of a tracker; larger updates take the generic branch below): the four scalar
         // functions of Sophus' exp are even power series in theta,
@@ -257,6 +270,8 @@ DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&o
         // (truncation < 1e-18 relative at theta = 0.5) instead of a dependent sqrt -> sincos -> 1/theta sequence of several hundred
         // cycles on the one lane the whole CTA waits for. (Sophus' own Taylor terms for theta < 1e-10 vanish in fp64: same imag.)
         const double h2 = 0.25 * t2;                                     // (theta/2)^2
+        if (series4) { ch = series4[0]; imag = 0.5 * series4[1]; a = series4[2]; b = series4[3]; }
+        else {
         ch = fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, -1.0 / 87178291200.0, 1.0 / 479001600.0), -1.0 / 3628800.0), 1.0 / 40320.0),
                                              -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
         imag = 0.5 * fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0), -1.0 / 39916800.0), 1.0 / 362880.0),
@@ -265,6 +280,7 @@ DSDTM_HD void se3_mul_exp(const double (&T)[7], const double (&x)[6], double (&o
                                         -1.0 / 40320.0), 1.0 / 720.0), -1.0 / 24.0), 0.5);
         b = fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, -1.0 / 355687428096000.0, 1.0 / 1307674368000.0), -1.0 / 6227020800.0), 1.0 / 39916800.0),
                                         -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
+        }
         // only tested against SMALL_EPS below. Sophus switches to V = R(q) for theta < 1e-10 (first-order different from the series:
         // R u = u + w x u, V u = u + w x u / 2); reproduced, the reference's step is what counts
         theta = (t2 < SMALL_EPS * SMALL_EPS) ? 0.0 : 1.0;

@@ -199,6 +199,86 @@ struct RefRowsT {
 };
 using RefRows = RefRowsT<false>;
 
+#ifndef DSDTM_SA_TAIL_LANES
+#define DSDTM_SA_TAIL_LANES 0    // 1 = the solve + pose update run redundantly on ALL lanes of warp 0 so that the four power series of SE3::exp are one
+                                 // Horner chain on four lanes (7 instead of 28 DFMA, no 64-bit immediates) and the fresh factor is used from registers.
+                                 // Bit-equal, but SLOWER (1.205 vs 1.194 ms): an FP64 instruction of a warp with one active lane occupies the pipe for
+                                 // one 16-lane pass, with 32 active lanes for two -- the one-lane tail is the cheaper form. 0 = everything on lane 0
+#endif
+// Coefficient k (highest power first) of series j of se3_mul_exp (se3_ldlt.cuh): j = 0 cos(theta/2) and 1 2 sin(theta/2)/theta in (theta/2)^2,
+// 2 (1 - cos theta)/theta^2 and 3 (theta - sin theta)/theta^3 in theta^2. The same constant expressions as there: the same doubles.
+__constant__ double kSe3SeriesCoef[32] = {
+    -1.0 / 87178291200.0, -1.0 / 1307674368000.0, -1.0 / 20922789888000.0, -1.0 / 355687428096000.0,
+    1.0 / 479001600.0, 1.0 / 6227020800.0, 1.0 / 87178291200.0, 1.0 / 1307674368000.0,
+    -1.0 / 3628800.0, -1.0 / 39916800.0, -1.0 / 479001600.0, -1.0 / 6227020800.0,
+    1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
+    -1.0 / 720.0, -1.0 / 5040.0, -1.0 / 40320.0, -1.0 / 362880.0,
+    1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+    -0.5, -1.0 / 6.0, -1.0 / 24.0, -1.0 / 120.0,
+    1.0, 1.0, 0.5, 1.0 / 6.0 };
+
+// all 32 lanes of the calling warp, uniform x: T * exp(x) with the four series evaluated by lanes 0..3 (every lane runs the chain of its
+// lane & 3) -- the same Horner steps as se3_mul_exp's own, so the same bits
+__device__ __forceinline__ void pose_update_lanes(const double* T, const double (&x)[6], double* Tn, const double* s_coef, int lane)
+{
+    double Tc[7], To[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) Tc[q] = T[q];
+    const double t2 = se3_theta2(x);
+    double s4[4] = { 0.0, 0.0, 0.0, 0.0 };
+    if (se3_exp_uses_series(t2)) {
+        const int j = lane & 3;
+        const double arg = (j < 2) ? 0.25 * t2 : t2;
+        double r = s_coef[j];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) r = fma(arg, r, s_coef[4 * k + j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s4[q] = __shfl_sync(0xffffffffu, r, q);
+    }
+    se3_mul_exp(Tc, x, To, s4);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) Tn[q] = To[q];
+}
+
+// the solve on every lane of the warp (uniform inputs): a fresh factorisation is used from registers and parked by lane 0
+__device__ __forceinline__ void solve_all_lanes(const double* __restrict__ sH /*21 packed*/, double* __restrict__ sF /*22*/, bool refactor,
+                                                const double (&bvec)[6], double (&x)[6], int lane)
+{
+    double Lp[15], d[6];
+    bool ok;
+    if (refactor) {
+        double Hm[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) { Hm[r][c] = sH[r * (r + 1) / 2 + c]; Hm[c][r] = Hm[r][c]; }
+        ok = ldlt6_factor_spd(Hm, Lp, d);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 15; ++i) sF[i] = Lp[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) sF[15 + i] = d[i];
+            sF[21] = ok ? 1.0 : 0.0;
+        }
+    } else {
+        ok = sF[21] != 0.0;
+#pragma unroll
+        for (int i = 0; i < 15; ++i) Lp[i] = sF[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) d[i] = sF[15 + i];
+    }
+    if (ok) {
+        ldlt6_subst_spd(Lp, d, bvec, x);                                   // ref: :318 (Eigen ldlt().solve), SPD fast path
+    } else {
+        double Hm[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) { Hm[r][c] = sH[r * (r + 1) / 2 + c]; Hm[c][r] = Hm[r][c]; }
+        ldlt6_solve_reg(Hm, bvec, x);                                      // Eigen's pivoted LDL^T incl. its zero-pivot rule
+    }
+}
+
 // the serial tail of one GN iteration, kept out of line: it runs on one lane once per iteration and must not bloat
 // (or evict from the instruction cache) the per-feature loop. H only changes when the visibility set changes, so the
 // factorisation is cached in shared memory (sF: 15 entries of L, 6 pivots, 1 flag) and most iterations only substitute.
@@ -337,10 +417,16 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
     __shared__ double s_T[7], s_Told[7];
     __shared__ double s_chi2prev;
     __shared__ int s_stop, s_npts, s_nlog;
+#if DSDTM_SA_TAIL_LANES
+    __shared__ double s_coef[32];       // kSe3SeriesCoef: read with a lane-dependent index (a constant-bank read would serialise)
+#endif
 
     constexpr int NT = 32 * WPP;
     const int pair = blockIdx.x + a.pair0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if DSDTM_SA_TAIL_LANES
+    if (tid < 32) s_coef[tid] = kSe3SeriesCoef[tid];
+#endif
     const int nfeat = min(a.n_feats[pair], NF);
     const uint8_t* __restrict__ ref_frame = a.frames + (size_t)a.ref_slots[pair] * a.frame_stride;
     const uint8_t* __restrict__ cur_frame = a.frames + (size_t)a.cur_slots[pair] * a.frame_stride;
@@ -888,37 +974,60 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     cnt = npts;
                 }
                 __syncwarp();
+#if DSDTM_SA_TAIL_LANES
+                {   // every lane of warp 0 holds the same sums: the tail runs on all of them (no extra cost in SIMT), lane 0 publishes
+                    const bool l0 = (lane == 0);
+#else
                 if (lane == 0) {
+                    const bool l0 = true;
+#endif
 #ifdef DSDTM_SA_TIMING
                     const long long tk2 = clock64();
 #endif
                     const double chi2New = accc / (double)(16 * cnt);                      // ref: :298 (NaN if nothing visible)
                     const double bvec[6] = { acc0, acc1, acc2, acc3, acc4, acc5 };
                     double x[6];
+#if DSDTM_SA_TAIL_LANES
+                    solve_all_lanes(s_H, s_F, need_H != 0, bvec, x, lane);                 // ref: :318
+#else
                     solve_and_update(s_H, s_F, need_H != 0, bvec, x);                      // ref: :318
+#endif
                     int flags = 0;
                     bool stop = false;
                     if (isnan(x[0])) { stop = true; flags |= 4; }                          // ref: :321-326
                     if ((it > 0 && chi2New > s_chi2prev) || stop) {                        // ref: :328-332
+                        if (l0) {
 #pragma unroll
-                        for (int q = 0; q < 7; ++q) s_T[q] = s_Told[q];
+                            for (int q = 0; q < 7; ++q) s_T[q] = s_Told[q];
+                        }
                         flags |= 2;
                         stop = true;
                     } else {
-                        double Tn[7];
-                        pose_update(s_T, x, Tn);                                           // ref: :335
+                        double Tn[7], Tcur[7];
 #pragma unroll
-                        for (int q = 0; q < 7; ++q) { s_Told[q] = s_T[q]; s_T[q] = Tn[q]; } // ref: :336-337
-                        s_chi2prev = chi2New;                                              // ref: :339
+                        for (int q = 0; q < 7; ++q) Tcur[q] = s_T[q];
+#if DSDTM_SA_TAIL_LANES
+                        pose_update_lanes(Tcur, x, Tn, s_coef, lane);                      // ref: :335
+                        __syncwarp();                                                      // every lane has read s_T and s_chi2prev
+#else
+                        pose_update(Tcur, x, Tn);                                          // ref: :335
+#endif
+                        if (l0) {
+#pragma unroll
+                            for (int q = 0; q < 7; ++q) { s_Told[q] = Tcur[q]; s_T[q] = Tn[q]; } // ref: :336-337
+                            s_chi2prev = chi2New;                                          // ref: :339
+                        }
                         flags |= 1;
                         double mx = 0;
 #pragma unroll
                         for (int q = 0; q < 6; ++q) mx = fmax(mx, fabs(x[q]));
                         if (mx <= 1e-8) { stop = true; flags |= 8; }                       // ref: :341
                     }
+                    if (l0) {
                     s_npts = cnt;
                     s_stop = stop ? 1 : 0;
-                    if (a.log) {
+                    }
+                    if (l0 && a.log) {
                         const int n = s_nlog;
                         if (n < a.log_cap) {
                             dsdtm_iter_log* e = a.log + (size_t)pair * a.log_cap + n;
