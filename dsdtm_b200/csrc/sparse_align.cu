@@ -240,6 +240,34 @@ __device__ __forceinline__ void pose_update_lanes(const double* T, const double 
     for (int q = 0; q < 7; ++q) Tn[q] = To[q];
 }
 
+#ifndef DSDTM_SA_TAIL_CONST
+#define DSDTM_SA_TAIL_CONST 0    // 1 = lane 0 evaluates the four exp series with coefficients read from the constant bank (operands of the DFMA) instead of
+                                 // 64-bit immediates moved through uniform registers (two UMOV per coefficient), and uses a fresh factor from registers
+#endif
+// lane 0 (or any single lane): T * exp(x), the four series from the constant table -- the same Horner steps and doubles as se3_mul_exp's own
+__device__ __forceinline__ void pose_update_const(const double* T, const double (&x)[6], double* Tn)
+{
+    double Tc[7], To[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) Tc[q] = T[q];
+    const double t2 = se3_theta2(x);
+    double s4[4] = { 0.0, 0.0, 0.0, 0.0 };
+    if (se3_exp_uses_series(t2)) {
+        const double h2 = 0.25 * t2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double arg = (j < 2) ? h2 : t2;
+            double r = kSe3SeriesCoef[j];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) r = fma(arg, r, kSe3SeriesCoef[4 * k + j]);
+            s4[j] = r;
+        }
+    }
+    se3_mul_exp(Tc, x, To, s4);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) Tn[q] = To[q];
+}
+
 // the solve on every lane of the warp (uniform inputs): a fresh factorisation is used from registers and parked by lane 0
 __device__ __forceinline__ void solve_all_lanes(const double* __restrict__ sH /*21 packed*/, double* __restrict__ sF /*22*/, bool refactor,
                                                 const double (&bvec)[6], double (&x)[6], int lane)
@@ -369,6 +397,9 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
 #define DSDTM_SA_LD64 0          // bit 0: level staging, bit 1: feature pass gather with 8-byte aligned 64-bit loads (the second load predicated): fewer L1 requests,
                                  // measured 1.224 (staging) / 1.285 (pass) vs 1.219 ms -- L1 request slots are not what the gathers wait for; off
 #endif
+#ifndef DSDTM_SA_PRO_G
+#define DSDTM_SA_PRO_G 2         // feature records per thread in flight in the prologue
+#endif
 #ifndef DSDTM_SA_PREF_NEXT
 #define DSDTM_SA_PREF_NEXT 0     // 1 = the staging of a level prefetches the next level's reference rows into L2: 1.260 vs 1.205 ms (a scattered prefetch costs a
                                  // full L1 request per lane like a load); off
@@ -440,13 +471,13 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
     if (tid == 0) { s_npts = 0; s_nlog = 0; s_stop = 0; s_chi2prev = 0.0; }
 #if DSDTM_SA_STAGE == 1
     // prologue: what GetJocabianMat derives per feature that does not depend on the level (ref: :86, :95 zero test, :117-119), once;
-    // two 64-byte records per thread in flight
-    for (int f0 = tid; f0 < nfeat; f0 += 2 * NT) {
-        dsdtm_ref_feat ft[2];
+    // DSDTM_SA_PRO_G 64-byte records per thread in flight
+    for (int f0 = tid; f0 < nfeat; f0 += DSDTM_SA_PRO_G * NT) {
+        dsdtm_ref_feat ft[DSDTM_SA_PRO_G];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) ft[g] = a.feats[(size_t)pair * a.feat_stride + min(f0 + g * NT, nfeat - 1)];
+        for (int g = 0; g < DSDTM_SA_PRO_G; ++g) ft[g] = a.feats[(size_t)pair * a.feat_stride + min(f0 + g * NT, nfeat - 1)];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < DSDTM_SA_PRO_G; ++g) {
             const int f = f0 + g * NT;
             if (f < nfeat) {
                 const bool zero = (ft[g].point_w[0] == 0.0 && ft[g].point_w[1] == 0.0 && ft[g].point_w[2] == 0.0);
@@ -987,7 +1018,7 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                     const double chi2New = accc / (double)(16 * cnt);                      // ref: :298 (NaN if nothing visible)
                     const double bvec[6] = { acc0, acc1, acc2, acc3, acc4, acc5 };
                     double x[6];
-#if DSDTM_SA_TAIL_LANES
+#if DSDTM_SA_TAIL_LANES || DSDTM_SA_TAIL_CONST
                     solve_all_lanes(s_H, s_F, need_H != 0, bvec, x, lane);                 // ref: :318
 #else
                     solve_and_update(s_H, s_F, need_H != 0, bvec, x);                      // ref: :318
@@ -1009,6 +1040,8 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
 #if DSDTM_SA_TAIL_LANES
                         pose_update_lanes(Tcur, x, Tn, s_coef, lane);                      // ref: :335
                         __syncwarp();                                                      // every lane has read s_T and s_chi2prev
+#elif DSDTM_SA_TAIL_CONST
+                        pose_update_const(Tcur, x, Tn);                                    // ref: :335
 #else
                         pose_update(Tcur, x, Tn);                                          // ref: :335
 #endif
@@ -1018,10 +1051,18 @@ __global__ void __launch_bounds__(32 * WPP, (WPP <= 2) ? 6 : (WPP == 3 ? DSDTM_S
                             s_chi2prev = chi2New;                                          // ref: :339
                         }
                         flags |= 1;
+#if DSDTM_SA_TAIL_CONST
+                        // max_q |x_q| <= 1e-8 (ref: :341; Eigen's maxCoeff and fmax both pass over a NaN) as six compares into one predicate
+                        bool small = true;
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) small = small && !(fabs(x[q]) > 1e-8);
+                        if (small) { stop = true; flags |= 8; }
+#else
                         double mx = 0;
 #pragma unroll
                         for (int q = 0; q < 6; ++q) mx = fmax(mx, fabs(x[q]));
                         if (mx <= 1e-8) { stop = true; flags |= 8; }                       // ref: :341
+#endif
                     }
                     if (l0) {
                     s_npts = cnt;
