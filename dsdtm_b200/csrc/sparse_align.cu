@@ -241,7 +241,7 @@ __device__ __forceinline__ void pose_update_lanes(const double* T, const double 
 }
 
 #ifndef DSDTM_SA_TAIL_CONST
-#define DSDTM_SA_TAIL_CONST 0    // 1 = lane 0 evaluates the four exp series with coefficients read from the constant bank (operands of the DFMA) instead of
+#define DSDTM_SA_TAIL_CONST 1    // (1.193 -> 1.187 ms, bit-equal) 1 = lane 0 evaluates the four exp series with coefficients read from the constant bank (operands of the DFMA) instead of
                                  // 64-bit immediates moved through uniform registers (two UMOV per coefficient), and uses a fresh factor from registers
 #endif
 // lane 0 (or any single lane): T * exp(x), the four series from the constant table -- the same Horner steps and doubles as se3_mul_exp's own
@@ -398,7 +398,7 @@ struct Pre { bool valid, vis; double tl, tr, bl, br; uint32_t cw0[5], cw1[5]; };
                                  // measured 1.224 (staging) / 1.285 (pass) vs 1.219 ms -- L1 request slots are not what the gathers wait for; off
 #endif
 #ifndef DSDTM_SA_PRO_G
-#define DSDTM_SA_PRO_G 2         // feature records per thread in flight in the prologue
+#define DSDTM_SA_PRO_G 2         // feature records per thread in flight in the prologue (4: 1.185 vs 1.187 ms, within noise)
 #endif
 #ifndef DSDTM_SA_PREF_NEXT
 #define DSDTM_SA_PREF_NEXT 0     // 1 = the staging of a level prefetches the next level's reference rows into L2: 1.260 vs 1.205 ms (a scattered prefetch costs a
