@@ -182,7 +182,7 @@ def peaks():
 
 def traffic_file():
     """the newest committed ncu --set full capture of the dominant kernel"""
-    for name in ("r2d_traffic.json", "r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):
+    for name in ("r2e_traffic.json", "r2d_traffic.json", "r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             return p
