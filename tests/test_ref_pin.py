@@ -139,6 +139,40 @@ def test_sparse_align_run_with_moved_reference_and_start_offsets(kin, kin_tree):
             assert d[0] < 3e-4 and d[1] < 1e-3
 
 
+def test_sparse_align_refined_positions_and_extreme_bytes_are_bit_equal(kin):
+    """The inputs of tests/test_gpu_align.py::test_sparse_align_subnormal_byte_encoding_keeps_full_precision, against the REFERENCE: features at
+    refined (arbitrary float) positions -- the case inside Tracking, where the last frame's features come out of Align2D -- on images of
+    saturated 0 / 255 blocks, from a start pose with arbitrary fractions. The bilinear weights are then general doubles at every level."""
+    sc = H.make_scenario(11, trans=0.015, rot_deg=0.4)
+    rng = np.random.default_rng(5)
+    hard = {}
+    for k in ("ref_img", "cur_img"):
+        img = sc[k].copy()
+        img[(img > 150)] = 255
+        img[(img < 90)] = 0
+        hard[k] = img
+    feats = sc["feats"].copy()
+    feats["px"] = (feats["px"] + rng.uniform(0.0, 1.0, feats["px"].shape)).astype(np.float32)
+    oc = H.ocam(sc["cam"])
+    for f in feats:
+        f["normal"] = O.feature_normal(oc, f["px"])                  # what Frame::Add_Feature derives from the pixel (ref: src/Frame.cpp:83-92)
+    start_c2r = S.pose_from_xi(rng.uniform(-0.003, 0.003, 6))
+    start = O.se3_mul(start_c2r, sc["T_ref"])
+    kin.reset()
+    ref = kin.frame(hard["ref_img"], sc["T_ref"]); cur = kin.frame(hard["cur_img"], start)
+    kf = kin.keyframe(ref)
+    for f in feats:
+        k = kin.add_feature(ref, f["px"], f["level"], True)
+        kin.set_mappoint(ref, k, kin.mappoint(f["point_w"], kf))
+    pr, nr = kin.sparse_align_run(cur, ref, 4, 0, 30)
+    ref_pyr = O.pyramid(hard["ref_img"], 5); cur_pyr = O.pyramid(hard["cur_img"], 5)
+    T0 = O.se3_mul(start, O.se3_inv(sc["T_ref"]))
+    po, no, log = O.sparse_align(oc, ref_pyr[0], cur_pyr[0], ref_pyr[1], ref_pyr[2], ref_pyr[3], feats, sc["ref_center"], T0, 4, 0, 30)
+    want = O.se3_mul(po, sc["T_ref"])
+    assert nr == no and (pr == want).all(), (np.abs(pr - want).max(), nr, no)
+    assert len(log) >= 8
+
+
 def test_sparse_align_too_few_features_returns_zero(kin):
     sc = H.make_scenario(3, max_fts=40)                             # Camera.Min_fts = 50 (ref: src/Sprase_ImageAlign.cpp:34-38)
     ref, cur = _load_pair(kin, sc, sc["T_ref"])
