@@ -8,10 +8,13 @@
 //     level x iteration loop runs on the device (the chain of dependent GN steps never returns to the host).
 //     WPP = 1 packs 6 independent pairs on one SM (throughput: other pairs fill the serial solve of this one),
 //     WPP = 10 gives one feature per lane (single-pair latency);
-//   * per level the 7x7 u8 neighbourhood of every reference feature (49 B), its 3-D point and sub-pixel offsets are
-//     staged ONCE in shared memory (121 B / feature incl. the parked second moments and 1 / z, instead of the 384 B of precomputed
-//     fp64 patches which limited v1 to one pair per SM); the bilinear reference samples and their central differences are re-derived from the bytes
-//     with the reference's expressions each iteration (2x the flops, 1/3 the shared memory, 6x the residency);
+//   * per level the 7x7 u8 neighbourhood of every reference feature (49 B) is staged ONCE in shared memory next to its 3-D point, 1 / z,
+//     level-0 pixel and parked second moments (121 B / feature, instead of the 384 B of precomputed fp64 patches which limited v1 to one
+//     pair per SM); the level-independent part runs once per pair in a prologue, the staging keeps two features' 42 window loads in flight
+//     per thread; the bilinear reference samples and their central differences are re-derived from the bytes with the reference's
+//     expressions each iteration (2x the flops, 1/3 the shared memory, 6x the residency);
+//   * bytes enter the fp64 arithmetic WITHOUT a conversion instruction: as subnormals b * 2^-1034 built by one PRMT, with bilinear weights
+//     that carry 2^1010 and sums restored by exact powers of two (DSDTM_SA_CVT 3 below): the reference's roundings, bit for bit;
 //   * inverse-compositional structure: the Jacobian row of pixel p of feature j is
 //         J_jp = (dx_jp * a_j + dy_jp * b_j) * (f * scale)          (ref: :160; a_j, b_j = rows of GetJocabianBA(P_j))
 //     so  sum_p J_jp J_jp^T = (f*scale)^2 (Sxx a a^T + Sxy (a b^T + b a^T) + Syy b b^T) is pose-independent: H is
@@ -19,8 +22,8 @@
 //     and the per-iteration work is  b += (f*scale)(a_j sum_p dx r + b_j sum_p dy r),  chi2 += sum_p r^2.
 //     Same mathematics, different summation order than the reference's sequential accumulation
 //     (documented tolerance: chi2 1e-4 relative, pose 1e-5 rad / m);
-//   * reductions: per-lane accumulation over its features, one warp xor-shuffle butterfly per iteration (bitwise
-//     identical in all lanes), WPP > 1 adds one shared-memory row per warp summed in warp order => deterministic;
+//   * reductions: per-lane accumulation over its features, then a transposed warp reduction (lane l ends with total l; the pairing
+//     tree of the xor butterfly, so the same bits), WPP > 1 adds one shared-memory row per warp summed in warp order => deterministic;
 //   * lane 0 solves the 6x6 system with Eigen's pivoted LDL^T entirely in registers (se3_ldlt.cuh), applies SE3::exp and
 //     the reference's accept / revert / converge rules, and publishes the pose through shared memory.
 #include <algorithm>
