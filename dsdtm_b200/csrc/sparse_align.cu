@@ -220,6 +220,7 @@ __constant__ double kSe3SeriesCoef[32] = {
     -0.5, -1.0 / 6.0, -1.0 / 24.0, -1.0 / 120.0,
     1.0, 1.0, 0.5, 1.0 / 6.0 };
 
+#if DSDTM_SA_TAIL_LANES
 // all 32 lanes of the calling warp, uniform x: T * exp(x) with the four series evaluated by lanes 0..3 (every lane runs the chain of its
 // lane & 3) -- the same Horner steps as se3_mul_exp's own, so the same bits
 __device__ __forceinline__ void pose_update_lanes(const double* T, const double (&x)[6], double* Tn, const double* s_coef, int lane)
@@ -243,10 +244,12 @@ __device__ __forceinline__ void pose_update_lanes(const double* T, const double 
     for (int q = 0; q < 7; ++q) Tn[q] = To[q];
 }
 
+#endif
 #ifndef DSDTM_SA_TAIL_CONST
 #define DSDTM_SA_TAIL_CONST 1    // (1.193 -> 1.187 ms, bit-equal) 1 = lane 0 evaluates the four exp series with coefficients read from the constant bank (operands of the DFMA) instead of
                                  // 64-bit immediates moved through uniform registers (two UMOV per coefficient), and uses a fresh factor from registers
 #endif
+#if DSDTM_SA_TAIL_CONST
 // lane 0 (or any single lane): T * exp(x), the four series from the constant table -- the same Horner steps and doubles as se3_mul_exp's own
 __device__ __forceinline__ void pose_update_const(const double* T, const double (&x)[6], double* Tn)
 {
@@ -271,6 +274,7 @@ __device__ __forceinline__ void pose_update_const(const double* T, const double 
     for (int q = 0; q < 7; ++q) Tn[q] = To[q];
 }
 
+#endif
 // the solve on every lane of the warp (uniform inputs): a fresh factorisation is used from registers and parked by lane 0
 __device__ __forceinline__ void solve_all_lanes(const double* __restrict__ sH /*21 packed*/, double* __restrict__ sF /*22*/, bool refactor,
                                                 const double (&bvec)[6], double (&x)[6], int lane)
