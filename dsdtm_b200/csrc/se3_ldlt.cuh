@@ -235,6 +235,19 @@ DSDTM_HD void ldlt6_subst_spd(const double (&Lp)[15], const double (&dinv)[6], c
 struct Quat { double w, x, y, z; };
 
 // out = T * exp(x); pose7 = {qw,qx,qy,qz,tx,ty,tz}. (ref: src/Sprase_ImageAlign.cpp:335; Sophus SE3::exp, SE3::operator*=)
+// Coefficient k (highest power first) of series j of se3_mul_exp below, as the flat list {k = 0: j = 0..3, k = 1: j = 0..3, ...}: j = 0
+// cos(theta/2) and 1 2 sin(theta/2)/theta in (theta/2)^2, 2 (1 - cos theta)/theta^2 and 3 (theta - sin theta)/theta^3 in theta^2. The same
+// constant expressions as in the Horner chains of se3_mul_exp: the same doubles (tests/test_host_math.py checks the two forms bit for bit).
+#define DSDTM_SE3_SERIES_COEF_LIST \
+    -1.0 / 87178291200.0, -1.0 / 1307674368000.0, -1.0 / 20922789888000.0, -1.0 / 355687428096000.0, \
+    1.0 / 479001600.0, 1.0 / 6227020800.0, 1.0 / 87178291200.0, 1.0 / 1307674368000.0, \
+    -1.0 / 3628800.0, -1.0 / 39916800.0, -1.0 / 479001600.0, -1.0 / 6227020800.0, \
+    1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0, \
+    -1.0 / 720.0, -1.0 / 5040.0, -1.0 / 40320.0, -1.0 / 362880.0, \
+    1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, \
+    -0.5, -1.0 / 6.0, -1.0 / 24.0, -1.0 / 120.0, \
+    1.0, 1.0, 0.5, 1.0 / 6.0
+
 DSDTM_HD double se3_theta2(const double (&x)[6])
 {
     const double o0 = x[3], o1 = x[4], o2 = x[5];

@@ -208,17 +208,8 @@ using RefRows = RefRowsT<false>;
                                  // Bit-equal, but SLOWER (1.205 vs 1.194 ms): an FP64 instruction of a warp with one active lane occupies the pipe for
                                  // one 16-lane pass, with 32 active lanes for two -- the one-lane tail is the cheaper form. 0 = everything on lane 0
 #endif
-// Coefficient k (highest power first) of series j of se3_mul_exp (se3_ldlt.cuh): j = 0 cos(theta/2) and 1 2 sin(theta/2)/theta in (theta/2)^2,
-// 2 (1 - cos theta)/theta^2 and 3 (theta - sin theta)/theta^3 in theta^2. The same constant expressions as there: the same doubles.
-__constant__ double kSe3SeriesCoef[32] = {
-    -1.0 / 87178291200.0, -1.0 / 1307674368000.0, -1.0 / 20922789888000.0, -1.0 / 355687428096000.0,
-    1.0 / 479001600.0, 1.0 / 6227020800.0, 1.0 / 87178291200.0, 1.0 / 1307674368000.0,
-    -1.0 / 3628800.0, -1.0 / 39916800.0, -1.0 / 479001600.0, -1.0 / 6227020800.0,
-    1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
-    -1.0 / 720.0, -1.0 / 5040.0, -1.0 / 40320.0, -1.0 / 362880.0,
-    1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
-    -0.5, -1.0 / 6.0, -1.0 / 24.0, -1.0 / 120.0,
-    1.0, 1.0, 0.5, 1.0 / 6.0 };
+// the series coefficients of se3_mul_exp (se3_ldlt.cuh), [k][j] = coefficient k (highest power first) of series j
+__constant__ double kSe3SeriesCoef[32] = { DSDTM_SE3_SERIES_COEF_LIST };
 
 #if DSDTM_SA_TAIL_LANES
 // all 32 lanes of the calling warp, uniform x: T * exp(x) with the four series evaluated by lanes 0..3 (every lane runs the chain of its

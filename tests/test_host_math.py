@@ -73,3 +73,18 @@ def test_se3_update_matches_oracle(prod):
         prod.prod_se3_mul_exp(_p(T), _p(np.ascontiguousarray(x)), _p(out))
         want = O.se3_mul(T, O.se3_exp(x))
         assert np.allclose(out, want, rtol=0, atol=1e-15)
+
+
+def test_se3_update_with_series_from_the_coefficient_table_is_bit_equal(prod):
+    """The sparse-alignment kernel's tail (csrc/sparse_align.cu, DSDTM_SA_TAIL_CONST) evaluates the four power series of SE3::exp from a
+    coefficient table and hands them to se3_mul_exp; the Horner steps and the doubles are those of se3_mul_exp's own chains, so the
+    pose must come out with the same bits -- for tracker-sized steps, tiny ones, and large ones that take the generic branch."""
+    rng = np.random.default_rng(9)
+    for t in range(400):
+        T = O.se3_exp(rng.uniform(-0.5, 0.5, 6))
+        scale = (0.05, 1e-6, 1e-12, 0.45, 1.5)[t % 5]                   # 1.5: |omega|^2 >= 0.25, no series
+        x = rng.uniform(-scale, scale, 6)
+        a = np.empty(7); b = np.empty(7)
+        prod.prod_se3_mul_exp(_p(T), _p(np.ascontiguousarray(x)), _p(a))
+        prod.prod_se3_mul_exp_table(_p(T), _p(np.ascontiguousarray(x)), _p(b))
+        assert (a == b).all(), (t, np.abs(a - b).max())
