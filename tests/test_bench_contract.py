@@ -35,3 +35,17 @@ def test_reference_arm_other_ranks_exit_quietly(built):
     # under torchrun only rank 0 runs the CPU arm; the other ranks print nothing and exit 0
     lines = _run([], env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert lines == []
+
+
+def test_roofline_inputs_of_the_gpu_arm_are_committed():
+    """bench.py's `roofline` for the dominant kernel reads the newest committed ncu capture (profiles/*_traffic.json): the FP64-pipe
+    instruction count and the DRAM traffic per pair must be there and plausible, or the bench line silently loses its roofline."""
+    import bench
+    p = bench.traffic_file()
+    assert os.path.exists(p), p
+    fpi = bench.fp64_insts_per_pair("sparse_align_kernel")
+    tr = bench.measured_traffic("sparse_align_kernel", 4096)
+    assert fpi is not None and 5e4 < fpi < 2e5                      # ~78 k FP64 warp instructions per pair
+    assert tr is not None and 1e9 < tr < 5e9                        # ~2.3 GB per launch of 4096 pairs
+    s = bench.ncu_summary("sparse_align_kernel")
+    assert "fp64_pipe_pct" in s and "source" in s
